@@ -1,0 +1,606 @@
+"""CPU oracle for the MoPoE-MIMIC training step.  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, never the product: only ``tests/``, ``__graft_entry__.smoke()``
+and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  Nothing under
+``mopoe_mimic_b200/`` imports it, and the product raises if its CUDA library is missing.
+
+It is a *functional* restatement (a flat ``state`` dict of tensors + plain functions on
+``torch.nn.functional``) of the reference's module tree, so that weights, dropout masks and
+the reparameterisation noise can be injected explicitly.  All numerics live in PyTorch CPU ops
+(the reference's own third-party dependency, ``torch~=1.6`` in requirements.txt:3; torch 2.11 here).
+
+Parity pin: the reference's own tests hold NO golden vectors for this path.  The
+oracle is pinned instead against the reference itself, run live in the build container by
+``oracle/gen_golden.py`` (imports /root/reference from a writable copy, loads the same state,
+patches dropout / reparameterize to the injected masks / eps) — outputs are committed under
+``tests/golden/`` and checked by ``tests/test_oracle_golden.py``.
+
+Reference citations are relative to /root/reference/mimic/.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from collections import OrderedDict
+from itertools import chain, combinations
+from types import SimpleNamespace
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5          # torch BatchNorm default (no override in networks/ResidualBlocks.py)
+BN_MOMENTUM = 0.1
+RES_A, RES_B = 2.0, 0.3  # FeatureExtractorImg.py:24, DataGeneratorImg.py:30, char_encoding/*:6
+LAPLACE_SCALE = 0.75   # networks/ConvNetworksImgMimic.py:54
+POE_EPS = 1e-8         # evaluation/divergence_measures/mm_div.py:10
+
+
+def default_flags(**kw):
+    """Flag fields the hot path reads; defaults = utils/flags.py, BaseFlags.py."""
+    f = dict(batch_size=16, class_dim=128, img_size=128, image_channels=1, DIM_img=128, DIM_text=128,
+             text_encoding='char', len_sequence=1024, num_features=71,
+             method='joint_elbo', mods=('PA', 'Lateral', 'text'),
+             beta=5.0, beta_style=1.0, beta_content=1.0,
+             rec_weights={'PA': 0.33, 'Lateral': 0.33, 'text': 0.33},
+             alpha_modalities=[0.25, 0.25, 0.25, 0.25])
+    f.update(kw)
+    return SimpleNamespace(**f)
+
+
+# --------------------------------------------------------------------------------------
+# architecture tables (what the reference's constructors build)
+# --------------------------------------------------------------------------------------
+def img_encoder_blocks(flags):
+    """FeatureExtractorImg.py:29-59 -> list of (cin, cout, k, stride, pad)."""
+    d = flags.DIM_img
+    blocks = [(d, 2 * d, 4, 2, 1), (2 * d, 3 * d, 4, 2, 1), (3 * d, 4 * d, 4, 2, 1)]
+    if flags.img_size == 64:
+        blocks += [(4 * d, 5 * d, 4, 2, 0)]
+    elif flags.img_size == 128:
+        blocks += [(4 * d, 5 * d, 4, 2, 1), (5 * d, 5 * d, 4, 2, 0)]
+    elif flags.img_size == 256:
+        blocks += [(4 * d, 5 * d, 4, 4, 1), (5 * d, 5 * d, 4, 2, 0)]
+    else:
+        raise NotImplementedError(flags.img_size)
+    return blocks
+
+
+def img_decoder_blocks(flags):
+    """DataGeneratorImg.py:33-79 -> list of (cin, cout, k, stride, pad)."""
+    d = flags.DIM_img
+    blocks = [(5 * d, 4 * d, 4, 1, 0), (4 * d, 3 * d, 4, 2, 1), (3 * d, 2 * d, 4, 2, 1), (2 * d, d, 4, 2, 1)]
+    if flags.img_size == 128:
+        blocks += [(d, d, 4, 2, 1)]
+    if flags.img_size == 256:
+        blocks += [(d, d, 4, 2, 1), (d, d, 4, 2, 1)]
+    return blocks
+
+
+def text_encoder_blocks(flags):
+    """char_encoding/FeatureExtractorText.py:32-56."""
+    d = flags.DIM_text
+    chans = [(d, 2 * d), (2 * d, 3 * d), (3 * d, 4 * d), (4 * d, 4 * d), (4 * d, 4 * d), (4 * d, 5 * d),
+             (5 * d, 5 * d), (5 * d, 5 * d)]
+    return [(ci, co, 4, 2, 1 if i < 7 else 0) for i, (ci, co) in enumerate(chans)]
+
+
+def text_decoder_blocks(flags):
+    """char_encoding/DataGeneratorText.py:28-43."""
+    d = flags.DIM_text
+    chans = [(5 * d, 5 * d), (5 * d, 5 * d), (5 * d, 5 * d), (5 * d, 4 * d), (4 * d, 4 * d), (4 * d, 3 * d),
+             (3 * d, 2 * d), (2 * d, d)]
+    return [(ci, co, 4, 1 if i == 0 else 2, 0 if i == 0 else 1) for i, (ci, co) in enumerate(chans)]
+
+
+ENC_NAME = {'PA': 'encoder_pa', 'Lateral': 'encoder_lat', 'text': 'encoder_text'}
+DEC_NAME = {'PA': 'decoder_pa', 'Lateral': 'decoder_lat', 'text': 'decoder_text'}
+
+
+def _bn_spec(spec, p, c):
+    spec[p + '.weight'] = (c,)
+    spec[p + '.bias'] = (c,)
+    spec[p + '.running_mean'] = (c,)
+    spec[p + '.running_var'] = (c,)
+    spec[p + '.num_batches_tracked'] = ()
+
+
+def _block_spec(spec, p, cin, cout, k, nd, transposed, inner_bias, short):
+    """ResidualBlocks.py:5-131 + the make_res_block_* helpers: registration order of the modules."""
+    ks = (k,) * nd
+    one = (1,) * nd
+    w2 = (cin, cout) + ks if transposed else (cout, cin) + ks
+    if nd == 1:   # 1-D blocks register bn1, conv1, bn2, conv2, shortcut (ResidualBlocks.py:8-16)
+        _bn_spec(spec, p + '.bn1', cin)
+        spec[p + '.conv1.weight'] = (cin, cin) + one
+        spec[p + '.conv1.bias'] = (cin,)
+        _bn_spec(spec, p + '.bn2', cin)
+        spec[p + '.conv2.weight'] = w2
+        spec[p + '.conv2.bias'] = (cout,)
+    else:         # 2-D blocks register conv1, bn1, bn2, conv2 (ResidualBlocks.py:71-80), no bias
+        spec[p + '.conv1.weight'] = (cin, cin) + one
+        _bn_spec(spec, p + '.bn1', cin)
+        _bn_spec(spec, p + '.bn2', cin)
+        spec[p + '.conv2.weight'] = w2
+    spec[p + '.%s.0.weight' % short] = w2
+    spec[p + '.%s.0.bias' % short] = (cout,)
+    _bn_spec(spec, p + '.%s.1' % short, cout)
+
+
+def param_spec(flags):
+    """Ordered name -> shape for every state_dict entry (params + BN buffers) of the model."""
+    spec = OrderedDict()
+    D = flags.class_dim
+    for m in flags.mods:
+        e = ENC_NAME[m]
+        if m == 'text':
+            d = flags.DIM_text
+            spec[e + '.feature_extractor.conv1.weight'] = (d, flags.num_features, 4)
+            spec[e + '.feature_extractor.conv1.bias'] = (d,)
+            for i, (ci, co, k, s, p) in enumerate(text_encoder_blocks(flags)):
+                _block_spec(spec, e + '.feature_extractor.resblock_%d.0' % (i + 1), ci, co, k, 1, False, True,
+                            'downsample')
+        else:
+            d = flags.DIM_img
+            spec[e + '.feature_extractor.conv1.weight'] = (d, flags.image_channels, 3, 3)
+            for i, (ci, co, k, s, p) in enumerate(img_encoder_blocks(flags)):
+                _block_spec(spec, e + '.feature_extractor.resblock_%d.0' % (i + 1), ci, co, k, 2, False, False,
+                            'downsample')
+        for head in ('content_mu', 'content_logvar'):
+            spec[e + '.feature_compressor.%s.weight' % head] = (D, 5 * d)
+            spec[e + '.feature_compressor.%s.bias' % head] = (D,)
+    for m in flags.mods:
+        dn = DEC_NAME[m]
+        if m == 'text':
+            d = flags.DIM_text
+            spec[dn + '.feature_generator.weight'] = (5 * d, D)
+            spec[dn + '.feature_generator.bias'] = (5 * d,)
+            for i, (ci, co, k, s, p) in enumerate(text_decoder_blocks(flags)):
+                _block_spec(spec, dn + '.text_generator.resblock_%d.0' % (i + 1), ci, co, k, 1, True, True,
+                            'upsample')
+            spec[dn + '.text_generator.conv2.weight'] = (d, flags.num_features, 4)
+            spec[dn + '.text_generator.conv2.bias'] = (flags.num_features,)
+        else:
+            d = flags.DIM_img
+            spec[dn + '.feature_generator.weight'] = (5 * d, D)
+            spec[dn + '.feature_generator.bias'] = (5 * d,)
+            blocks = img_decoder_blocks(flags)
+            for i, (ci, co, k, s, p) in enumerate(blocks):
+                _block_spec(spec, dn + '.img_generator.generator.%d.0' % i, ci, co, k, 2, True, False, 'upsample')
+            spec[dn + '.img_generator.generator.%d.weight' % len(blocks)] = (d, flags.image_channels, 3, 3)
+            spec[dn + '.img_generator.generator.%d.bias' % len(blocks)] = (flags.image_channels,)
+    return spec
+
+
+def _seed_for(name, seed):
+    h = hashlib.sha256(('%d:%s' % (seed, name)).encode()).digest()
+    return int.from_bytes(h[:6], 'little')
+
+
+def seeded_uniform(name, seed, shape, lo=0.0, hi=1.0, dtype=torch.float64):
+    """Deterministic per-name tensor, independent of creation order (CPU mt19937, fp64 draw)."""
+    g = torch.Generator(device='cpu')
+    g.manual_seed(_seed_for(name, seed))
+    return (torch.rand(tuple(shape), generator=g, dtype=torch.float64) * (hi - lo) + lo).to(dtype)
+
+
+def make_state(flags, seed=0, dtype=torch.float32):
+    """Deterministic synthetic weights with torch's default-init *scales* (U(+-1/sqrt(fan_in)));
+    BN affine is perturbed away from (1, 0) so gamma/beta gradients are exercised."""
+    st = OrderedDict()
+    for name, shape in param_spec(flags).items():
+        if name.endswith('num_batches_tracked'):
+            st[name] = torch.zeros((), dtype=torch.int64)
+        elif name.endswith('running_mean'):
+            st[name] = torch.zeros(shape, dtype=dtype)
+        elif name.endswith('running_var'):
+            st[name] = torch.ones(shape, dtype=dtype)
+        elif len(shape) == 1 and ('.bn' in name or 'sample.1.' in name):
+            if name.endswith('weight'):
+                st[name] = seeded_uniform(name, seed, shape, 0.8, 1.2, dtype)
+            else:
+                st[name] = seeded_uniform(name, seed, shape, -0.1, 0.1, dtype)
+        else:
+            # torch default init: U(+-1/sqrt(fan_in)), fan_in = weight.size(1) * receptive field
+            # (the same rule for Conv, ConvTranspose and Linear); a bias uses its sibling weight's fan_in
+            wshape = param_spec_cached(flags)[name[:-4] + 'weight'] if len(shape) == 1 else shape
+            fan_in = wshape[1] * int(math.prod(wshape[2:]))
+            b = 1.0 / math.sqrt(fan_in)
+            st[name] = seeded_uniform(name, seed, shape, -b, b, dtype)
+    return st
+
+
+_spec_cache = {}
+
+
+def param_spec_cached(flags):
+    key = (flags.class_dim, flags.img_size, flags.DIM_img, flags.DIM_text, tuple(flags.mods), flags.num_features)
+    if key not in _spec_cache:
+        _spec_cache[key] = param_spec(flags)
+    return _spec_cache[key]
+
+
+def make_batch(flags, seed=1, dtype=torch.float32, batch=None):
+    """Synthetic inputs of the reference's own shapes (dataio/MimicDataset.py:414-428), with TRUE
+    one-hot text (torch>=2 validates OneHotCategorical targets)."""
+    B = batch or flags.batch_size
+    out = OrderedDict()
+    for m in flags.mods:
+        if m == 'text':
+            idx = (seeded_uniform('text', seed, (B, flags.len_sequence)) * flags.num_features).long()
+            idx.clamp_(0, flags.num_features - 1)
+            out[m] = F.one_hot(idx, flags.num_features).to(dtype)
+        else:
+            out[m] = seeded_uniform(m, seed, (B, flags.image_channels, flags.img_size, flags.img_size), dtype=dtype)
+    return out
+
+
+def dropout_sites(flags, batch=None):
+    """name -> mask shape for every Dropout/Dropout2d call of one train-mode forward, in the order
+    the reference consumes RNG.  2-D: [B,C,1,1] (Dropout2d), 1-D: [B,C,L]."""
+    B = batch or flags.batch_size
+    sites = OrderedDict()
+
+    def enc(m):
+        e = ENC_NAME[m] + '.feature_extractor.resblock_%d.0'
+        if m == 'text':
+            L = flags.len_sequence // 2
+            for i, (ci, co, k, s, p) in enumerate(text_encoder_blocks(flags)):
+                sites[(e % (i + 1)) + '.dropout1'] = (B, ci, L)
+                L = (L + 2 * p - k) // s + 1
+                sites[(e % (i + 1)) + '.dropout2'] = (B, co, L)
+        else:
+            for i, (ci, co, k, s, p) in enumerate(img_encoder_blocks(flags)):
+                sites[(e % (i + 1)) + '.dropout1'] = (B, ci, 1, 1)
+                sites[(e % (i + 1)) + '.dropout2'] = (B, co, 1, 1)
+
+    def dec(m):
+        if m == 'text':
+            dn = DEC_NAME[m] + '.text_generator.resblock_%d.0'
+            L = 1
+            for i, (ci, co, k, s, p) in enumerate(text_decoder_blocks(flags)):
+                sites[(dn % (i + 1)) + '.dropout1'] = (B, ci, L)
+                L = (L - 1) * s - 2 * p + k
+                sites[(dn % (i + 1)) + '.dropout2'] = (B, co, L)
+        else:
+            dn = DEC_NAME[m] + '.img_generator.generator.%d.0'
+            for i, (ci, co, k, s, p) in enumerate(img_decoder_blocks(flags)):
+                sites[(dn % i) + '.dropout1'] = (B, ci, 1, 1)
+                sites[(dn % i) + '.dropout2'] = (B, co, 1, 1)
+
+    for m in flags.mods:
+        enc(m)
+    for m in flags.mods:
+        dec(m)
+    return sites
+
+
+def make_noise(flags, seed=2, dtype=torch.float32, batch=None):
+    """Injected randomness: Bernoulli(0.5) keep-masks (values {0,1}) for every dropout site and the
+    reparameterisation eps ~ N(0,1) [B, class_dim] (Box-Muller on the seeded uniform stream)."""
+    B = batch or flags.batch_size
+    masks = OrderedDict()
+    for name, shape in dropout_sites(flags, B).items():
+        masks[name] = (seeded_uniform(name, seed, shape) < 0.5).to(dtype)
+    u1 = seeded_uniform('eps.u1', seed, (B, flags.class_dim)).clamp_min(1e-12)
+    u2 = seeded_uniform('eps.u2', seed, (B, flags.class_dim))
+    eps = (torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2.0 * math.pi * u2)).to(dtype)
+    return masks, eps
+
+
+# --------------------------------------------------------------------------------------
+# networks
+# --------------------------------------------------------------------------------------
+class _Ctx:
+    """Carries state, masks, train flag and collects the BN running-stat updates."""
+
+    def __init__(self, state, masks, train):
+        self.s, self.masks, self.train = state, masks, train
+        self.bn_updates = OrderedDict()
+
+
+def _bn(ctx, p, x):
+    """nn.BatchNorm{1,2}d defaults: train -> biased batch var for normalisation, running stats
+    updated with momentum 0.1 and the UNBIASED var; eval -> running stats."""
+    s = ctx.s
+    if ctx.train:
+        dims = [0] + list(range(2, x.dim()))
+        n = x.numel() // x.shape[1]
+        with torch.no_grad():
+            mean = x.mean(dims)
+            var_b = x.var(dims, unbiased=False)
+            ctx.bn_updates[p + '.running_mean'] = (1 - BN_MOMENTUM) * s[p + '.running_mean'] + BN_MOMENTUM * mean
+            ctx.bn_updates[p + '.running_var'] = ((1 - BN_MOMENTUM) * s[p + '.running_var']
+                                                  + BN_MOMENTUM * var_b * (n / max(n - 1, 1)))
+        return F.batch_norm(x, None, None, s[p + '.weight'], s[p + '.bias'], True, BN_MOMENTUM, BN_EPS)
+    return F.batch_norm(x, s[p + '.running_mean'], s[p + '.running_var'], s[p + '.weight'], s[p + '.bias'],
+                        False, BN_MOMENTUM, BN_EPS)
+
+
+def _dropout(ctx, name, x):
+    """nn.Dropout(p=.5) / nn.Dropout2d(p=.5): survivors scaled by 1/(1-p) = 2 (ResidualBlocks.py:10,73)."""
+    if not ctx.train:
+        return x
+    return x * ctx.masks[name] * 2.0
+
+
+def _res_block(ctx, p, x, k, stride, pad, nd, transposed):
+    """ResidualBlocks.py forward():20-33 / 51-65 / 84-97 / 118-131 (all four are the same graph)."""
+    s = ctx.s
+    if nd == 1:
+        conv, convt = F.conv1d, F.conv_transpose1d
+    else:
+        conv, convt = F.conv2d, F.conv_transpose2d
+    short = 'upsample' if transposed else 'downsample'
+    out = F.relu(_bn(ctx, p + '.bn1', x))
+    b1 = s.get(p + '.conv1.bias')
+    out = (convt if transposed else conv)(out, s[p + '.conv1.weight'], b1)
+    out = _dropout(ctx, p + '.dropout1', out)
+    out = F.relu(_bn(ctx, p + '.bn2', out))
+    b2 = s.get(p + '.conv2.bias')
+    if transposed:
+        out = convt(out, s[p + '.conv2.weight'], b2, stride=stride, padding=pad)
+        res = convt(x, s[p + '.%s.0.weight' % short], s[p + '.%s.0.bias' % short], stride=stride, padding=pad)
+    else:
+        out = conv(out, s[p + '.conv2.weight'], b2, stride=stride, padding=pad)
+        res = conv(x, s[p + '.%s.0.weight' % short], s[p + '.%s.0.bias' % short], stride=stride, padding=pad)
+    out = _dropout(ctx, p + '.dropout2', out)
+    res = _bn(ctx, p + '.%s.1' % short, res)
+    return RES_A * res + RES_B * out
+
+
+def encoder_img(ctx, flags, e, x):
+    """EncoderImg.forward (ConvNetworksImgMimic.py:29-36) -> FeatureExtractorImg.forward
+    (FeatureExtractorImg.py:61-81) -> LinearFeatureCompressor.forward (FeatureCompressor.py:21-28)."""
+    s = ctx.s
+    h = F.conv2d(x, s[e + '.feature_extractor.conv1.weight'], None, stride=2, padding=1)
+    for i, (ci, co, k, st, p) in enumerate(img_encoder_blocks(flags)):
+        h = _res_block(ctx, e + '.feature_extractor.resblock_%d.0' % (i + 1), h, k, st, p, 2, False)
+    f = h.reshape(h.shape[0], -1)
+    mu = F.linear(f, s[e + '.feature_compressor.content_mu.weight'], s[e + '.feature_compressor.content_mu.bias'])
+    lv = F.linear(f, s[e + '.feature_compressor.content_logvar.weight'],
+                  s[e + '.feature_compressor.content_logvar.bias'])
+    return mu, lv
+
+
+def encoder_text(ctx, flags, e, x):
+    """EncoderText.forward (ConvNetworksTextMimic.py:23-36) -> FeatureExtractorText.forward
+    (char_encoding/FeatureExtractorText.py:58-81).  x: [B, L, num_features]."""
+    s = ctx.s
+    h = F.conv1d(x.transpose(-2, -1), s[e + '.feature_extractor.conv1.weight'],
+                 s[e + '.feature_extractor.conv1.bias'], stride=2, padding=1)
+    for i, (ci, co, k, st, p) in enumerate(text_encoder_blocks(flags)):
+        h = _res_block(ctx, e + '.feature_extractor.resblock_%d.0' % (i + 1), h, k, st, p, 1, False)
+    f = h.reshape(h.shape[0], -1)
+    mu = F.linear(f, s[e + '.feature_compressor.content_mu.weight'], s[e + '.feature_compressor.content_mu.bias'])
+    lv = F.linear(f, s[e + '.feature_compressor.content_logvar.weight'],
+                  s[e + '.feature_compressor.content_logvar.bias'])
+    return mu, lv
+
+
+def decoder_img(ctx, flags, d, z):
+    """DecoderImg.forward (ConvNetworksImgMimic.py:46-54) -> DataGeneratorImg (DataGeneratorImg.py:29-98).
+    Returns loc of the Laplace likelihood [B,1,px,px] (scale is the constant 0.75)."""
+    s = ctx.s
+    h = F.linear(z, s[d + '.feature_generator.weight'], s[d + '.feature_generator.bias'])
+    h = h.view(h.shape[0], h.shape[1], 1, 1)
+    blocks = img_decoder_blocks(flags)
+    for i, (ci, co, k, st, p) in enumerate(blocks):
+        h = _res_block(ctx, d + '.img_generator.generator.%d.0' % i, h, k, st, p, 2, True)
+    n = len(blocks)
+    return F.conv_transpose2d(h, s[d + '.img_generator.generator.%d.weight' % n],
+                              s[d + '.img_generator.generator.%d.bias' % n], stride=2, padding=1, output_padding=1)
+
+
+def decoder_text(ctx, flags, d, z):
+    """DecoderText.forward (ConvNetworksTextMimic.py:51-68) -> DataGeneratorText.forward
+    (char_encoding/DataGeneratorText.py:53-76).  Returns log-softmaxed logits [B, L, num_features]."""
+    s = ctx.s
+    h = F.linear(z, s[d + '.feature_generator.weight'], s[d + '.feature_generator.bias']).unsqueeze(-1)
+    for i, (ci, co, k, st, p) in enumerate(text_decoder_blocks(flags)):
+        h = _res_block(ctx, d + '.text_generator.resblock_%d.0' % (i + 1), h, k, st, p, 1, True)
+    h = F.conv_transpose1d(h, s[d + '.text_generator.conv2.weight'], s[d + '.text_generator.conv2.bias'],
+                           stride=2, padding=1)
+    return F.log_softmax(h, dim=1).transpose(-2, -1)
+
+
+# --------------------------------------------------------------------------------------
+# MoPoE fusion / ELBO
+# --------------------------------------------------------------------------------------
+def subset_keys(mod_names):
+    """BaseExperiment.set_subsets (utils/BaseExperiment.py:66-82): powerset in itertools order,
+    key = '_'.join(sorted(names)), members sorted by name.  Returns OrderedDict key -> [names]."""
+    xs = list(mod_names)
+    out = OrderedDict()
+    for names in chain.from_iterable(combinations(xs, n) for n in range(len(xs) + 1)):
+        out['_'.join(sorted(names))] = sorted(names)
+    return out
+
+
+def poe(mu, logvar):
+    """mm_div.poe (evaluation/divergence_measures/mm_div.py:10-17).  mu, logvar: [m, B, D]."""
+    var = torch.exp(logvar) + POE_EPS
+    T = 1.0 / var
+    pd_mu = torch.sum(mu * T, dim=0) / torch.sum(T, dim=0)
+    pd_var = 1.0 / torch.sum(T, dim=0)
+    return pd_mu, torch.log(pd_var)
+
+
+def selection_bounds(num_samples, weights):
+    """utils.mixture_component_selection index math (utils/utils.py:62-73) with FP32 weights:
+    end_k = start_k + int(floor(B * w_k)); the last component takes the remainder."""
+    w = torch.as_tensor(weights, dtype=torch.float32)
+    w = w / w.sum()                       # reweight_weights (utils/utils.py:51-52) in moe_fusion
+    starts, ends = [], []
+    for k in range(w.shape[0]):
+        i_start = 0 if k == 0 else ends[k - 1]
+        if k == w.shape[0] - 1:
+            i_end = num_samples
+        else:
+            i_end = i_start + int(torch.floor(num_samples * w[k]))
+        starts.append(i_start)
+        ends.append(i_end)
+    ends[-1] = num_samples
+    return starts, ends
+
+
+def mixture_component_selection(mus, logvars, weights):
+    """utils/utils.py:55-77.  mus, logvars [S,B,D] -> [B,D] by contiguous batch ranges."""
+    starts, ends = selection_bounds(mus.shape[1], weights)
+    S = len(starts)
+    mu = torch.cat([mus[k, starts[k]:ends[k], :] for k in range(S)])
+    lv = torch.cat([logvars[k, starts[k]:ends[k], :] for k in range(S)])
+    return mu, lv
+
+
+def kl_to_standard_normal(mu, logvar, norm_value):
+    """kl_div.calc_kl_divergence, prior branch (evaluation/divergence_measures/kl_div.py:8-16)."""
+    return -0.5 * torch.sum(1 - logvar.exp() - mu.pow(2) + logvar) / float(norm_value)
+
+
+def inference(enc_mods, flags, present):
+    """BaseMMVae.inference (utils/BaseMMVae.py:139-196) for methods moe / poe / joint_elbo.
+    enc_mods: name -> (mu, logvar); present: modality names in the input batch (dict order)."""
+    method = flags.method
+    subsets = subset_keys(flags.mods)
+    mus, logvars, distr = [], [], OrderedDict()
+    for key, members in subsets.items():
+        if key == '' or not all(m in present for m in members):
+            continue
+        mu_s = torch.stack([enc_mods[m][0] for m in members])
+        lv_s = torch.stack([enc_mods[m][1] for m in members])
+        if method in ('poe', 'joint_elbo'):
+            if method == 'poe':           # prior expert appended to EVERY subset (BaseMMVae.py:117-124)
+                z = torch.zeros_like(mu_s[:1])
+                mu_s, lv_s = torch.cat((mu_s, z)), torch.cat((lv_s, z))
+            s_mu, s_lv = poe(mu_s, lv_s)
+        else:                              # moe: selection among the members, uniform weights
+            w = torch.full((mu_s.shape[0],), 1.0 / mu_s.shape[0])
+            s_mu, s_lv = mixture_component_selection(mu_s, lv_s, w)
+        distr[key] = (s_mu, s_lv)
+        if method == 'moe':
+            cond = len(members) == 1                  # fusion_condition_moe  :130-131
+        elif method == 'poe':
+            cond = len(members) == len(present)       # fusion_condition_poe  :133-134
+        else:
+            cond = True                               # fusion_condition_joint:136-137
+        if cond:
+            mus.append(s_mu)
+            logvars.append(s_lv)
+    mus, logvars = torch.stack(mus), torch.stack(logvars)
+    S = mus.shape[0]
+    weights = torch.full((S,), 1.0 / S, dtype=torch.float32)
+    j_mu, j_lv = mixture_component_selection(mus, logvars, weights)
+    return dict(modalities=enc_mods, mus=mus, logvars=logvars, weights=weights, joint=(j_mu, j_lv), subsets=distr)
+
+
+def laplace_log_prob_sum(loc, target):
+    """dist.Laplace(loc, 0.75).log_prob(target).sum()  (modalities/Modality.py:25-30)."""
+    b = LAPLACE_SCALE
+    # the reference's scale is an fp32 tensor (torch.tensor(0.75)), so log(2b) is evaluated in fp32
+    log2b = float(torch.log(torch.tensor(2 * b, dtype=torch.float32)))
+    return (-log2b - (target - loc).abs() / b).sum()
+
+
+def categorical_log_prob_sum(logits, target):
+    """dist.OneHotCategorical(logits=logits).log_prob(target).sum(): logits are re-normalised
+    (idempotent after the decoder's LogSoftmax) and indexed by argmax(target)."""
+    ln = logits - logits.logsumexp(dim=-1, keepdim=True)
+    idx = target.max(-1)[1]
+    return ln.gather(-1, idx.unsqueeze(-1)).sum()
+
+
+def forward(state, batch, flags, masks=None, eps=None, train=True, present=None):
+    """VAEtrimodalMimic.forward (networks/VAEtrimodalMimic.py:31-62), tolerant of missing modalities
+    in the decode loop (the intended behaviour for calc_poe_loss)."""
+    ctx = _Ctx(state, masks or {}, train)
+    present = list(present or [m for m in flags.mods if m in batch])
+    enc = OrderedDict()
+    for m in present:
+        if m == 'text':
+            enc[m] = encoder_text(ctx, flags, ENC_NAME[m], batch[m])
+        else:
+            enc[m] = encoder_img(ctx, flags, ENC_NAME[m], batch[m])
+    lat = inference(enc, flags, present)
+    # calc_group_divergence_moe (mm_div.py:90-110): the reference collects the per-subset KLs in
+    # `torch.zeros(num_mods)` -- an FP32 tensor whatever the model dtype -- and the weights are FP32 too
+    # (BaseMMVae.py:187), so joint_divergence is an fp32 quantity even in an fp64 run.
+    w = lat['weights'] / lat['weights'].sum()
+    klds_ind = torch.stack([kl_to_standard_normal(lat['mus'][k], lat['logvars'][k], flags.batch_size)
+                            for k in range(lat['mus'].shape[0])]).to(torch.float32)
+    joint_div = (w * klds_ind).sum()
+    j_mu, j_lv = lat['joint']
+    if eps is None:
+        eps = torch.zeros_like(j_mu)
+    z = eps * torch.exp(0.5 * j_lv) + j_mu   # utils.reparameterize (utils/utils.py:45-48)
+    rec = OrderedDict()
+    for m in present:
+        if m == 'text':
+            rec[m] = decoder_text(ctx, flags, DEC_NAME[m], z)
+        else:
+            rec[m] = decoder_img(ctx, flags, DEC_NAME[m], z)
+    return dict(latents=lat, joint_divergence=joint_div, individual_divs=klds_ind, z=z, rec=rec,
+                bn_updates=ctx.bn_updates)
+
+
+def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks=None):
+    """run_epochs.basic_routine_epoch (run_epochs.py:52-96): forward, calc_log_probs (losses.py:6-21),
+    calc_klds (:24-31), calc_joint_elbo_loss (:80-89) or calc_poe_loss (:54-77, intended semantics)."""
+    res = forward(state, batch, flags, masks, eps, train)
+    Bn = float(flags.batch_size)
+    log_probs, weighted = OrderedDict(), 0.0
+    for m in flags.mods:
+        if m == 'text':
+            lp = categorical_log_prob_sum(res['rec'][m], batch[m])
+        else:
+            lp = laplace_log_prob_sum(res['rec'][m], batch[m])
+        log_probs[m] = -lp / Bn
+        weighted = weighted + flags.rec_weights[m] * log_probs[m]
+    klds = OrderedDict((k, kl_to_standard_normal(mu, lv, Bn)) for k, (mu, lv) in res['latents']['subsets'].items())
+    if flags.method in ('moe', 'joint_elbo'):
+        total = weighted + flags.beta * (flags.beta_style * 0.0 + flags.beta_content * res['joint_divergence'])
+    elif flags.method == 'poe':
+        total = weighted + flags.beta * flags.beta_content * res['joint_divergence']   # calc_elbo 'joint'
+        state2 = dict(state)              # the unimodal passes see the BN buffers the joint pass updated
+        state2.update(res['bn_updates'])
+        for i, m in enumerate(flags.mods):
+            um, ue = (uni_masks or {}).get(m, (masks, eps))
+            r_m = forward(state2, {m: batch[m]}, flags, um, ue, train, present=[m])
+            lp = (categorical_log_prob_sum if m == 'text' else laplace_log_prob_sum)(r_m['rec'][m], batch[m])
+            total = total + (-lp / Bn) + flags.beta * flags.beta_content * klds[m]     # calc_elbo modality
+            for k, v in r_m['bn_updates'].items():
+                res['bn_updates'][k] = v
+    else:
+        raise NotImplementedError(flags.method)
+    return dict(results=res, log_probs=log_probs, klds=klds, total_loss=total, weighted_log_prob=weighted)
+
+
+def step_with_grads(state, batch, flags, masks=None, eps=None, uni_masks=None):
+    """One train-mode step: losses + d(total_loss)/d(param) for every float parameter."""
+    params = {k: v for k, v in state.items() if v.is_floating_point() and 'running_' not in k}
+    for v in params.values():
+        v.requires_grad_(True)
+        v.grad = None
+    out = step_losses(state, batch, flags, masks, eps, True, uni_masks=uni_masks)
+    out['total_loss'].backward()
+    grads = OrderedDict((k, v.grad.detach().clone()) for k, v in params.items())
+    for v in params.values():
+        v.requires_grad_(False)
+        v.grad = None
+    out['grads'] = grads
+    return out
+
+
+step_with_grads_full = step_with_grads
+
+
+def adam_step(params, grads, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam defaults as used by MimicExperiment.set_optimizer (utils/experiment.py:171-178):
+    no weight decay, no amsgrad.  In-place on params/m/v; `step` is the 1-based step count."""
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    for k in params:
+        g = grads[k]
+        m[k].mul_(b1).add_(g, alpha=1 - b1)
+        v[k].mul_(b2).addcmul_(g, g, value=1 - b2)
+        denom = (v[k].sqrt() / math.sqrt(bc2)).add_(eps)
+        params[k].addcdiv_(m[k], denom, value=-lr / bc1)
