@@ -1,0 +1,203 @@
+/* mopoe_b200.h — C ABI of libmopoe_b200.so, the sm_100a compute library behind the MoPoE-MIMIC
+ * training step.
+ *
+ * The reference (Jimmy2027/MoPoE-MIMIC) is pure Python on torch.nn: it has NO FFI/plugin interface
+ * for this path.  Each entry point below therefore replaces a torch library call
+ * site of the reference, cited as file:line relative to /root/reference/mimic/.  The Python host
+ * (mopoe_mimic_b200/*.py) mirrors the reference's module API and reaches this library with ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every buffer (inputs, outputs, workspaces) is owned by the
+ *    caller (device memory from the PyTorch caching allocator); the library never allocates device
+ *    memory, so the reference's 'CUDA out of memory.' contract (run_epochs.py:37-49) is untouched;
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t) and returns; it is re-entrant and
+ *    may be called from the autograd worker thread;
+ *  - return value 0 = ok, otherwise a non-zero code; mopoe_last_error() gives the text
+ *    (thread-local);
+ *  - activations are channels-last: [B, H, W, C] (1-D text: H = 1, W = L) described by a
+ *    mopoe_view_t whose `ptr` addresses interior element (0,0,0,0); padded tensors carry a zero
+ *    border of ph rows / pw columns that producing kernels write themselves.
+ */
+#ifndef MOPOE_B200_H
+#define MOPOE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { MOPOE_F32 = 0, MOPOE_BF16 = 1 };
+/* dropout-mask addressing: none, one byte per (b,c) [Dropout2d], one byte per element in the
+ * plain [B,H,W,C] order [Dropout].  Byte value 1 = keep (scaled by 2), 0 = drop. */
+enum { MOPOE_MASK_NONE = 0, MOPOE_MASK_BC = 1, MOPOE_MASK_ELEM = 2 };
+
+typedef struct {
+    void*   ptr;        /* interior element (b=0,h=0,w=0,c=0) */
+    int32_t dtype;      /* MOPOE_F32 | MOPOE_BF16 */
+    int32_t B, H, W, C;
+    int32_t ph, pw;     /* zero border (rows, cols) present around the interior in storage */
+    int32_t _pad;
+    int64_t sB, sH, sW; /* element strides; channel stride is 1 */
+} mopoe_view_t;
+
+/* implicit-GEMM operand description shared by the fprop/dgrad and wgrad entry points:
+ *   A[m, r, k] = a[a_off + m0*sA0 + m1*sA1 + m2*sA2 + r*sAr + k],  m = (m2, m1, m0) over E2 x E1 x E0,
+ *   r < R window rows, k < KW contiguous window elements (taps x channels).  K = R*KW. */
+typedef struct {
+    const void* a;
+    int32_t a_dtype;
+    int32_t E0, E1, E2;
+    int32_t R, KW;
+    int32_t _pad;
+    int64_t a_off, sA0, sA1, sA2, sAr;
+} mopoe_window_t;
+
+/* row addressing of a GEMM output / wgrad "dY" operand: row m at d_off + m0*s0 + m1*s1 + m2*s2, n contiguous */
+typedef struct {
+    void*   d;
+    int32_t d_dtype;
+    int32_t N;
+    int64_t d_off, s0, s1, s2;
+} mopoe_rows_t;
+
+const char* mopoe_last_error(void);
+int mopoe_version(void);
+/* 1 when the tcgen05/TMA kernels are usable on the current device (cc 10.x + driver entry point found) */
+int mopoe_tc_available(void);
+
+/* ---- implicit-GEMM convolution family -------------------------------------------------------------
+ * D[m, n] = sum_{r,k} A[m,r,k] * Wp[n, r*KW + k] + bias[n]
+ * Replaces nn.Conv{1,2}d / nn.ConvTranspose{1,2}d / nn.Linear forward and their input-gradient
+ * (networks/ResidualBlocks.py:8-16,71-80,103-111; FeatureExtractorImg.py:29-34; DataGeneratorImg.py:10-16;
+ * FeatureCompressor.py:13-19; char_encoding/FeatureExtractorText.py:30-31, DataGeneratorText.py:44-49).
+ * Wp has the dtype of A.  impl: 0 = auto (tcgen05 when eligible), 1 = force SIMT fp32-accumulate path. */
+int mopoe_conv_gemm(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D,
+                    int impl, void* stream);
+
+/* dWp[n, r*KW + k] (+)= sum_m dY[m, n] * A[m,r,k]   (fp32 output).  `ws` holds split partials
+ * (ws_bytes from mopoe_conv_wgrad_ws); replaces the weight-gradient half of autograd's conv backward
+ * (run_epochs.py:130 total_loss.backward()). */
+size_t mopoe_conv_wgrad_ws(const mopoe_window_t* A, const mopoe_rows_t* dY, int impl);
+int mopoe_conv_wgrad(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate,
+                     void* ws, size_t ws_bytes, int impl, void* stream);
+
+/* out[c] (+)= sum over rows of v[.., c]  (bias gradients).  ws: 2*nchunk*C doubles. */
+int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, void* stream);
+
+/* ---- BatchNorm (training statistics) + fused pre-activation ----------------------------------------
+ * nn.BatchNorm{1,2}d in train mode (ResidualBlocks.py:8,12,73-75,...): per-channel mean / biased var
+ * of v = x * (2*mask); running stats updated with momentum and the unbiased var.
+ * ws: 2*nchunk*C doubles.  running_* may be NULL (no update). */
+int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, double* ws, int nchunk,
+                   float eps, float momentum, float* mean, float* invstd,
+                   float* running_mean, float* running_var, void* stream);
+/* out = act(gamma * (x*2mask - mean) * invstd + beta), act = relu when relu != 0; writes the zero border
+ * of `out`.  bn1->relu / dropout1->bn2->relu of ResidualBlocks.py:20-33 in one pass. */
+int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
+                   const float* invstd, const float* gamma, const float* beta, int relu,
+                   const mopoe_view_t* out, void* stream);
+/* out = a * BN(r) + b * (c * 2mask)   — `out = self.a * residual + self.b * out` with the shortcut's
+ * BatchNorm and dropout2 folded in (ResidualBlocks.py:29-33). */
+int mopoe_combine(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma,
+                  const float* beta, const mopoe_view_t* c, const uint8_t* mask, int mask_mode,
+                  float a, float b, const mopoe_view_t* out, void* stream);
+/* BN backward, reduction half: g = gscale * dy * [gate > 0];  xhat = (x*2mask - mean)*invstd;
+ * dbeta (+)= sum g, dgamma (+)= sum g*xhat, sums[0:C] = sum g, sums[C:2C] = sum g*xhat. */
+int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
+                        const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
+                        const float* mean, const float* invstd, double* ws, int nchunk,
+                        float* dgamma, float* dbeta, int accumulate, float* sums, void* stream);
+/* BN backward, apply half: out = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend. */
+int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
+                       const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
+                       const float* mean, const float* invstd, const float* gamma, const float* sums,
+                       const mopoe_view_t* addend, const mopoe_view_t* out, void* stream);
+/* out = scale * dy * 2mask (+ zero border): dropout backward / the b*dropout2 branch. */
+int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int mask_mode, float scale,
+                     const mopoe_view_t* out, void* stream);
+/* generic layout/dtype conversion between views of equal B,H,W; channels beyond src->C are zero filled.
+ * src_nchw != 0: src->ptr is an NCHW fp32 user tensor [B,C,H,W] (strides ignored). */
+int mopoe_convert(const mopoe_view_t* src, int src_nchw, const mopoe_view_t* dst, void* stream);
+/* Bernoulli(0.5) keep-mask bytes from a counter-based generator (Philox-4x32-10). */
+int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- single-channel image layers (CUDA-core direct kernels) ---------------------------------------
+ * first conv  nn.Conv2d(1, C, 3, stride 2, pad 1, bias=False)  (FeatureExtractorImg.py:29-34)
+ * x: fp32 [B, 1, H, W]; w: fp32 [C, 1, 3, 3]; out view [B, H/2, W/2, C]. */
+int mopoe_conv3x3s2_c1_fwd(const float* x, const float* w, int B, int H, int W, const mopoe_view_t* out,
+                           void* stream);
+int mopoe_conv3x3s2_c1_wgrad(const float* x, const mopoe_view_t* dy, int B, int H, int W, float* dw,
+                             int accumulate, double* ws, int nchunk, void* stream);
+/* last deconv nn.ConvTranspose2d(C, 1, 3, stride 2, pad 1, output_padding 1) (DataGeneratorImg.py:84-90)
+ * x view [B, H, W, C]; w fp32 [C,1,3,3]; out fp32 [B,1,2H,2W]. */
+int mopoe_deconv3x3s2_c1_fwd(const mopoe_view_t* x, const float* w, const float* bias, float* out, void* stream);
+/* given dout fp32 [B,1,2H,2W]: dx view, dw fp32 [C,1,3,3], dbias[1]. ws: nchunk*(9*C+1) doubles. */
+int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, const float* dout, const mopoe_view_t* dx,
+                             float* dw, float* dbias, int accumulate, double* ws, int nchunk, void* stream);
+
+/* ---- fused MoPoE kernel (north_star item 2) --------------------------------------------------------
+ * BaseMMVae.inference (utils/BaseMMVae.py:139-196) + poe (mm_div.py:10-17) + mixture_component_selection
+ * (utils/utils.py:55-77) + reparameterize (:45-48) + calc_kl_divergence for every subset (kl_div.py:8-16).
+ * All tensors fp32.  mu/logvar: M pointers to [B, D].  Subset s has member bitmask members[s] (bit i =
+ * modality i, in the caller's modality order).  fuse_mode 0 = product of experts, 1 = mixture (batch-range
+ * selection among members, uniform weights).  prior_expert != 0 appends N(0,I) to every product (poe method).
+ * stacked[j] (j < S) are the subsets forming the joint mixture; sel_end[j] their exclusive batch-row ends
+ * (host-computed with the reference's fp32 floor rule).
+ * Outputs: sub_mu/sub_lv [nsub, B, D]; joint_mu/joint_lv/z [B, D]; kl[nsub] = KL(subset || N(0,I)) / norm;
+ * nan_flag[0] != 0 when an encoder mean/logvar is NaN (utils.check_latents, utils/utils.py:201-208).
+ * ws: nsub * kl_chunks doubles. */
+typedef struct {
+    int32_t M, B, D, nsub, S;
+    int32_t fuse_mode, prior_expert, kl_chunks;
+    int32_t members[16];
+    int32_t stacked[16];
+    int32_t sel_end[16];
+    int32_t mem_cnt[16];    /* number of members of subset s */
+    int32_t mem_idx[16][4]; /* members of subset s in the reference's stacking order (sorted by name) */
+    int32_t mem_end[16][4]; /* mixture mode: exclusive batch-row end of the j-th stacked member */
+    float   norm;
+    float   _pad;
+} mopoe_fusion_cfg_t;
+int mopoe_fusion_fwd(const mopoe_fusion_cfg_t* cfg, const float* const* mu, const float* const* logvar,
+                     const float* eps, float* sub_mu, float* sub_lv, float* joint_mu, float* joint_lv,
+                     float* z, float* kl, int32_t* nan_flag, double* ws, void* stream);
+/* Backward: upstream d_z [B,D], d_joint_mu/d_joint_lv [B,D], d_sub_mu/d_sub_lv [nsub,B,D], d_kl [nsub]
+ * (any may be NULL = zero) -> d_mu/d_lv: M pointers to [B, D] (overwritten). */
+int mopoe_fusion_bwd(const mopoe_fusion_cfg_t* cfg, const float* const* mu, const float* const* logvar,
+                     const float* eps, const float* sub_mu, const float* sub_lv,
+                     const float* d_z, const float* d_joint_mu, const float* d_joint_lv,
+                     const float* d_sub_mu, const float* d_sub_lv, const float* d_kl,
+                     float* const* d_mu, float* const* d_lv, void* stream);
+
+/* ---- fused reconstruction log-likelihoods (north_star item 3) --------------------------------------
+ * Laplace(loc, scale).log_prob(x).sum()  (modalities/Modality.py:25-30, scale 0.75 from
+ * networks/ConvNetworksImgMimic.py:54): out[0] = sum_i -(log(2*scale) + |x_i - loc_i| / scale).
+ * ws: nchunk doubles. */
+int mopoe_laplace_logprob_sum(const float* loc, const float* x, int64_t n, float scale, float* out,
+                              double* ws, int nchunk, void* stream);
+/* dloc_i = (*gout) * sign(x_i - loc_i) / scale   (gradient of the log-prob sum; gout on device) */
+int mopoe_laplace_logprob_bwd(const float* loc, const float* x, int64_t n, float scale, const float* gout,
+                              float* dloc, void* stream);
+/* LogSoftmax(dim=vocab) of the text decoder (char_encoding/DataGeneratorText.py:51,75) fused with
+ * OneHotCategorical(logits).log_prob(target).sum() (modalities/utils.py:7-8, MimicText.py:37-40).
+ * y: pre-softmax [rows, V] fp32 (rows = B*L); target: one-hot(ish) fp32 [rows, V] (argmax taken) or NULL
+ * with idx int32 [rows].  logits_out [rows, V] = log_softmax(y) (may be NULL); idx_out (may be NULL)
+ * receives the argmax; out[0] = sum_rows logits[row, idx]. */
+int mopoe_categorical_logprob_sum(const float* y, const float* target, const int32_t* idx, int64_t rows,
+                                  int V, float* logits_out, int32_t* idx_out, float* out, double* ws,
+                                  int nchunk, void* stream);
+/* dy[row, v] = (*gout) * (onehot(idx)[v] - softmax(y)[row, v]) + dlogits-path (NULL) */
+int mopoe_categorical_logprob_bwd(const float* y, const int32_t* idx, int64_t rows, int V,
+                                  const float* gout, float* dy, void* stream);
+
+/* ---- optimizer: torch.optim.Adam defaults (experiment.py:171-178) over the FLAT
+ * parameter / gradient / moment buffers (all 420 tensors are views into one allocation): one launch.
+ * `step` is the 1-based step count; g is multiplied by grad_scale first (1/world_size under DP). */
+int mopoe_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,453 @@
+"""autograd.Function wrappers: each Function runs a whole sub-graph (a residual block, a stem, a head,
+a likelihood reduction) through the CUDA library in forward and in backward.  PyTorch's autograd only
+chains these coarse nodes; no torch math op is on the hot path.
+
+Reference graph of one block (networks/ResidualBlocks.py:20-33 / 51-65 / 84-97 / 118-131):
+    out = conv2(relu(bn2(dropout1(conv1(relu(bn1(x))))))); out = dropout2(out)
+    res = BN(shortcut_conv(x));  y = a * res + b * out
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+from .engine import Act, conv_form, conv_form_grad, full_form, phase_form
+
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+class BlockSpec:
+    """Static description of one residual block."""
+
+    def __init__(self, name, nd, cin, cout, k, stride, pad, transposed, a=2.0, b=0.3):
+        self.name, self.nd, self.cin, self.cout = name, nd, cin, cout
+        self.k, self.stride, self.pad, self.transposed = k, stride, pad, transposed
+        self.a, self.b = a, b
+        self.inner_bias = nd == 1          # 1-D convs carry biases, 2-D inner convs do not
+        if k == 4 and stride == 2 and pad == 1:
+            self.kind = 'S'
+        elif not transposed and k == 4 and pad == 0:
+            self.kind = 'Z'                # 4 -> 1 valid conv
+        elif transposed and k == 4 and stride == 1 and pad == 0:
+            self.kind = 'U'                # 1 -> 4 transposed conv
+        elif not transposed and k == 4 and stride == 4 and pad == 1:
+            self.kind = 'Q'
+        else:
+            raise NotImplementedError('block geometry k=%d s=%d p=%d T=%s' % (k, stride, pad, transposed))
+        self.needs_pad = 1 if self.kind in ('S', 'Q') else 0   # border the block INPUT must carry
+
+    def out_hw(self, H, W):
+        k, s, p = self.k, self.stride, self.pad
+        f = (lambda n: (n - 1) * s - 2 * p + k) if self.transposed else (lambda n: (n + 2 * p - k) // s + 1)
+        return (1 if self.nd == 1 else f(H)), f(W)
+
+    def param_names(self):
+        short = 'upsample' if self.transposed else 'downsample'
+        n = ['bn1.weight', 'bn1.bias', 'conv1.weight']
+        if self.inner_bias:
+            n.append('conv1.bias')
+        n += ['bn2.weight', 'bn2.bias', 'conv2.weight']
+        if self.inner_bias:
+            n.append('conv2.bias')
+        n += [short + '.0.weight', short + '.0.bias', short + '.1.weight', short + '.1.bias']
+        return n
+
+
+class BlockRun:
+    """Per-call context handed to ResBlockFn (not a tensor): engine, geometry, BN buffers, masks."""
+
+    def __init__(self, eng, spec, B, H, W, in_pad, out_pad, train, buffers, masks):
+        self.eng, self.spec, self.B, self.H, self.W = eng, spec, B, H, W
+        self.in_pad, self.out_pad, self.train = in_pad, out_pad, train
+        self.buffers = buffers          # dict: 'bn1'/'bn2'/'short' -> (running_mean, running_var)
+        self.masks = masks              # (mask1, mask2) uint8 tensors or None
+
+
+def _pads(nd, p):
+    return (0 if nd == 1 else p), p
+
+
+def _eval_stats(rm, rv):
+    return torch.stack((rm, torch.rsqrt(rv + BN_EPS)))
+
+
+def _main_fwd(eng, spec, x, Wg, bias, dtype):
+    """conv2 / shortcut forward by geometry kind -> plain Act"""
+    if spec.kind == 'S' and not spec.transposed:
+        return eng.gemm_down(x, conv_form(Wg, dtype), bias, 4, 2, 1, spec.cout)
+    if spec.kind == 'S':
+        return eng.gemm_up(x, phase_form(Wg, dtype), bias, spec.cout)
+    if spec.kind == 'Z':
+        return eng.gemm_down(x, conv_form(Wg, dtype), bias, 4, 2, 0, spec.cout)
+    if spec.kind == 'Q':
+        return eng.gemm_down(x, conv_form(Wg, dtype), bias, 4, 4, 1, spec.cout)
+    taps = 4 ** spec.nd if spec.nd == 2 else 4                     # 'U'
+    bb = bias.repeat(taps) if bias is not None else None
+    oh, ow = spec.out_hw(x.H, x.W)
+    return eng.gemm_rows(x, full_form(Wg, dtype), bb, taps * spec.cout, out_shape=(x.B, oh, ow, spec.cout))
+
+
+def _main_dgrad(eng, spec, dout, Wg, dtype, H, W):
+    """d/d(input) of conv2 / shortcut: dout is a bordered Act -> plain Act [B,H,W,cin]"""
+    if spec.kind == 'S' and not spec.transposed:
+        return eng.gemm_up(dout, phase_form(Wg, dtype), None, spec.cin)
+    if spec.kind == 'S':
+        return eng.gemm_down(dout, conv_form(Wg, dtype), None, 4, 2, 1, spec.cin)
+    if spec.kind == 'Z':
+        taps = 16 if spec.nd == 2 else 4
+        return eng.gemm_rows(dout, full_form(Wg, dtype), None, taps * spec.cin, out_shape=(dout.B, H, W, spec.cin))
+    if spec.kind == 'U':
+        return eng.gemm_down(dout, conv_form(Wg, dtype), None, 4, 1, 0, spec.cin)
+    raise NotImplementedError('dgrad for stride-4 blocks (256 px) is not built yet')
+
+
+def _main_wgrad(eng, spec, xin, dout, shape):
+    """weight gradient in the parameter's own layout"""
+    if spec.transposed:
+        s = 1 if spec.kind == 'U' else 2
+        g = eng.wgrad_down(dout, 4, s, spec.pad if spec.kind == 'S' else 0, xin)
+    else:
+        g = eng.wgrad_down(xin, 4, spec.stride, spec.pad, dout)
+    return conv_form_grad(g, shape)
+
+
+class ResBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x_t, run, *params):
+        eng, sp = run.eng, run.spec
+        dt = x_t.dtype
+        P = dict(zip(sp.param_names(), params))
+        short = 'upsample' if sp.transposed else 'downsample'
+        B, H, W = run.B, run.H, run.W
+        iph, ipw = _pads(sp.nd, run.in_pad)
+        x = Act.like(x_t, B, H, W, sp.cin, iph, ipw)
+        mode = L.MASK_NONE if not run.train else (L.MASK_BC if sp.nd == 2 else L.MASK_ELEM)
+        m1, m2 = run.masks if run.train else (None, None)
+        bufs = run.buffers
+        # bn1 -> relu
+        st1 = eng.bn_stats(x, None, L.MASK_NONE, *bufs['bn1']) if run.train else _eval_stats(*bufs['bn1'])
+        a1 = eng.bn_apply(x, None, L.MASK_NONE, st1, P['bn1.weight'], P['bn1.bias'], True,
+                          Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device))
+        # conv1 (1x1)
+        W1 = P['conv1.weight'].reshape(sp.cin, sp.cin)
+        w1f = (W1.t() if sp.transposed else W1).to(dt).contiguous()
+        hh = eng.gemm_rows(a1, w1f, P.get('conv1.bias'), sp.cin)
+        # dropout1 -> bn2 -> relu  (written with the border conv2 needs)
+        st2 = eng.bn_stats(hh, m1, mode, *bufs['bn2']) if run.train else _eval_stats(*bufs['bn2'])
+        pph, ppw = _pads(sp.nd, sp.needs_pad)
+        a2 = eng.bn_apply(hh, m1, mode, st2, P['bn2.weight'], P['bn2.bias'], True,
+                          Act.empty(B, H, W, sp.cin, pph, ppw, dt, eng.device))
+        # conv2 and shortcut conv
+        c = _main_fwd(eng, sp, a2, P['conv2.weight'], P.get('conv2.bias'), dt)
+        r = _main_fwd(eng, sp, x, P[short + '.0.weight'], P[short + '.0.bias'], dt)
+        st3 = eng.bn_stats(r, None, L.MASK_NONE, *bufs['short']) if run.train else _eval_stats(*bufs['short'])
+        oph, opw = _pads(sp.nd, run.out_pad)
+        y = eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b,
+                        Act.empty(B, r.H, r.W, sp.cout, oph, opw, dt, eng.device))
+        ctx.run = run
+        ctx.geo = (r.H, r.W)
+        ctx.save_for_backward(x_t, a1.t, hh.t, a2.t, r.t, st1, st2, st3, *params)
+        ctx.mask_refs = (m1, m2, mode)
+        return y.t
+
+    @staticmethod
+    def backward(ctx, dy_t):
+        run = ctx.run
+        eng, sp = run.eng, run.spec
+        if not run.train:
+            raise RuntimeError('backward through an eval-mode block is not supported')
+        x_t, a1_t, hh_t, a2_t, r_t, st1, st2, st3, *params = ctx.saved_tensors
+        P = dict(zip(sp.param_names(), params))
+        short = 'upsample' if sp.transposed else 'downsample'
+        dt = x_t.dtype
+        B, H, W = run.B, run.H, run.W
+        OH, OW = ctx.geo
+        m1, m2, mode = ctx.mask_refs
+        iph, ipw = _pads(sp.nd, run.in_pad)
+        oph, opw = _pads(sp.nd, run.out_pad)
+        pph, ppw = _pads(sp.nd, sp.needs_pad)
+        bph, bpw = _pads(sp.nd, 1)
+        x = Act.like(x_t, B, H, W, sp.cin, iph, ipw)
+        a1 = Act.like(a1_t, B, H, W, sp.cin)
+        hh = Act.like(hh_t, B, H, W, sp.cin)
+        a2 = Act.like(a2_t, B, H, W, sp.cin, pph, ppw)
+        r = Act.like(r_t, B, OH, OW, sp.cout)
+        dy = Act.like(dy_t.contiguous(), B, OH, OW, sp.cout, oph, opw)
+        G = {}
+        # y = a*BN3(r) + b*(c*2m2)
+        G[short + '.1.weight'], G[short + '.1.bias'] = eng.f32(sp.cout), eng.f32(sp.cout)
+        dr = eng.bn_bwd(dy, None, sp.a, r, None, L.MASK_NONE, st3, P[short + '.1.weight'], G[short + '.1.weight'],
+                        G[short + '.1.bias'], None, Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device))
+        dc = eng.scale_mask(dy, m2, mode, sp.b, Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device))
+        # shortcut conv
+        Ws_ = P[short + '.0.weight']
+        G[short + '.0.weight'] = _main_wgrad(eng, sp, x, dr, Ws_.shape)
+        G[short + '.0.bias'] = eng.colsum(dr)
+        dxs = _main_dgrad(eng, sp, dr, Ws_, dt, H, W)
+        # conv2
+        W2 = P['conv2.weight']
+        G['conv2.weight'] = _main_wgrad(eng, sp, a2, dc, W2.shape)
+        if sp.inner_bias:
+            G['conv2.bias'] = eng.colsum(dc)
+        da2 = _main_dgrad(eng, sp, dc, W2, dt, H, W)
+        # relu, bn2, dropout1
+        G['bn2.weight'], G['bn2.bias'] = eng.f32(sp.cin), eng.f32(sp.cin)
+        dh = eng.bn_bwd(da2, a2, 1.0, hh, m1, mode, st2, P['bn2.weight'], G['bn2.weight'], G['bn2.bias'], None,
+                        Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device))
+        # conv1 (1x1)
+        W1 = P['conv1.weight'].reshape(sp.cin, sp.cin)
+        g1 = eng.wgrad_rows(a1, dh)                                   # [n_out, c_in]
+        G['conv1.weight'] = (g1.t() if sp.transposed else g1).reshape(P['conv1.weight'].shape)
+        if sp.inner_bias:
+            G['conv1.bias'] = eng.colsum(dh)
+        w1b = (W1 if sp.transposed else W1.t()).to(dt).contiguous()    # [c_in, n_out]
+        da1 = eng.gemm_rows(dh, w1b, None, sp.cin)
+        # relu, bn1 (+ the shortcut's input gradient)
+        G['bn1.weight'], G['bn1.bias'] = eng.f32(sp.cin), eng.f32(sp.cin)
+        dx = eng.bn_bwd(da1, a1, 1.0, x, None, L.MASK_NONE, st1, P['bn1.weight'], G['bn1.weight'], G['bn1.bias'], dxs,
+                        Act.empty(B, H, W, sp.cin, iph, ipw, dt, eng.device))
+        grads = [G[n] for n in sp.param_names()]
+        return (dx.t.view_as(x_t), None, *grads)
+
+
+# ---- stems and heads ------------------------------------------------------------------------------------------
+class ImgStemFn(torch.autograd.Function):
+    """nn.Conv2d(1, C, 3, 2, 1, bias=False) on the NCHW fp32 image (FeatureExtractorImg.py:29-34, :72)."""
+
+    @staticmethod
+    def forward(ctx, x, w, eng, out_pad):
+        B, _, H, W = x.shape
+        Cc = w.shape[0]
+        x = x.contiguous().float()
+        y = Act.empty(B, H // 2, W // 2, Cc, out_pad, out_pad, eng.dtype, eng.device)
+        L.call('mopoe_conv3x3s2_c1_fwd', L.ptr(x), L.ptr(w), B, H, W, C.byref(y.view()), L.stream_ptr())
+        ctx.save_for_backward(x, w)
+        ctx.eng, ctx.out_pad = eng, out_pad
+        return y.t
+
+    @staticmethod
+    def backward(ctx, dy_t):
+        x, w = ctx.saved_tensors
+        eng = ctx.eng
+        B, _, H, W = x.shape
+        Cc = w.shape[0]
+        dy = Act.like(dy_t.contiguous(), B, H // 2, W // 2, Cc, ctx.out_pad, ctx.out_pad)
+        nc = eng.nchunk(B * (H // 2) * (W // 2), Cc)
+        ws = eng.ws64(nc * 9 * Cc)
+        dw = eng.f32(*w.shape)
+        L.call('mopoe_conv3x3s2_c1_wgrad', L.ptr(x), C.byref(dy.view()), B, H, W, L.ptr(dw), 0, L.ptr(ws), nc,
+               L.stream_ptr())
+        return None, dw, None, None
+
+
+class ImgLastFn(torch.autograd.Function):
+    """nn.ConvTranspose2d(C, 1, 3, 2, 1, output_padding=1) -> fp32 NCHW loc (DataGeneratorImg.py:84-90)."""
+
+    @staticmethod
+    def forward(ctx, x_t, w, bias, eng, B, H, W):
+        Cc = w.shape[0]
+        x = Act.like(x_t, B, H, W, Cc)
+        out = eng.f32(B, 1, 2 * H, 2 * W)
+        L.call('mopoe_deconv3x3s2_c1_fwd', C.byref(x.view()), L.ptr(w), L.ptr(bias), L.ptr(out), L.stream_ptr())
+        ctx.save_for_backward(x_t, w)
+        ctx.eng, ctx.geo = eng, (B, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_t, w = ctx.saved_tensors
+        eng = ctx.eng
+        B, H, W = ctx.geo
+        Cc = w.shape[0]
+        x = Act.like(x_t, B, H, W, Cc)
+        dx = Act.empty(B, H, W, Cc, 0, 0, x_t.dtype, eng.device)
+        nc = eng.nchunk(B * H * W, Cc)
+        ws = eng.ws64(nc * (9 * Cc + 1))
+        dw, db = eng.f32(*w.shape), eng.f32(1)
+        L.call('mopoe_deconv3x3s2_c1_bwd', C.byref(x.view()), L.ptr(w), L.ptr(dout.contiguous()), C.byref(dx.view()),
+               L.ptr(dw), L.ptr(db), 0, L.ptr(ws), nc, L.stream_ptr())
+        return dx.t.view_as(x_t), dw, db, None, None, None, None
+
+
+class TextStemFn(torch.autograd.Function):
+    """x.transpose(-2,-1) -> nn.Conv1d(71, C, 4, 2, 1) (char_encoding/FeatureExtractorText.py:30-31, :71-72):
+    the [B, L, F] input already IS channels-last; it is copied once into a bordered, channel-padded buffer."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, eng, out_pad):
+        B, Lq, Fq = x.shape
+        Cc = w.shape[0]
+        Fp = (Fq + 15) // 16 * 16
+        x = x.contiguous().float()
+        xin = Act.empty(B, 1, Lq, Fp, 0, 1, eng.dtype, eng.device)
+        src = L.View(x.data_ptr(), L.F32, B, 1, Lq, Fq, 0, 0, 0, Lq * Fq, Lq * Fq, Fq)
+        eng.convert(src, False, xin)
+        wp = torch.zeros(Cc, Fp, 4, dtype=torch.float32, device=eng.device)
+        wp[:, :Fq] = w
+        y = Act(torch.zeros((B, 1, Lq // 2 + 2 * out_pad, Cc), dtype=eng.dtype, device=eng.device), B, 1, Lq // 2, Cc,
+                0, out_pad)
+        eng.gemm_down(xin, conv_form(wp, eng.dtype), bias, 4, 2, 1, Cc, out=y)
+        ctx.save_for_backward(xin.t, w)
+        ctx.eng, ctx.geo = eng, (B, Lq, Fq, Fp, out_pad)
+        return y.t
+
+    @staticmethod
+    def backward(ctx, dy_t):
+        xin_t, w = ctx.saved_tensors
+        eng = ctx.eng
+        B, Lq, Fq, Fp, out_pad = ctx.geo
+        Cc = w.shape[0]
+        xin = Act.like(xin_t, B, 1, Lq, Fp, 0, 1)
+        dy = Act.like(dy_t.contiguous(), B, 1, Lq // 2, Cc, 0, out_pad)
+        g = eng.wgrad_down(xin, 4, 2, 1, dy)                   # [Cc, 4*Fp]
+        dw = g.view(Cc, 4, Fp)[:, :, :Fq].permute(0, 2, 1).contiguous()
+        db = eng.colsum(dy)
+        return None, dw, db, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on [B, K] rows -> [B, N] (FeatureCompressor.py:13-19, ConvNetworks*Mimic.py feature_generator).
+    in_act: x_t is an activation (act dtype, possibly bordered 1x1); else x_t is an fp32 [B, K] tensor."""
+
+    @staticmethod
+    def forward(ctx, x_t, w, bias, eng, B, in_pad, nd, out_act):
+        N, K = w.shape
+        if in_pad is None:                 # fp32 latent rows
+            xa = Act.like(x_t.contiguous().to(eng.dtype), B, 1, 1, K)
+        else:
+            xa = Act.like(x_t, B, 1, 1, K, *_pads(nd, in_pad))
+        out = eng.gemm_rows(xa, w.to(eng.dtype).contiguous(), bias, N, out_dtype=eng.dtype if out_act else torch.float32)
+        ctx.save_for_backward(xa.t, w)
+        ctx.eng, ctx.geo = eng, (B, in_pad, nd, out_act, x_t.dtype, tuple(x_t.shape))
+        return out.t.view(B, N) if not out_act else out.t
+
+    @staticmethod
+    def backward(ctx, dy_t):
+        xa_t, w = ctx.saved_tensors
+        eng = ctx.eng
+        B, in_pad, nd, out_act, x_dtype, x_shape = ctx.geo
+        N, K = w.shape
+        ph, pw = (0, 0) if in_pad is None else _pads(nd, in_pad)
+        xa = Act.like(xa_t, B, 1, 1, K, ph, pw)
+        dy = Act.like(dy_t.contiguous().to(eng.dtype), B, 1, 1, N)
+        dw = eng.wgrad_rows(xa, dy)
+        db = eng.colsum(dy)
+        dxp = eng.gemm_rows(dy, w.t().to(eng.dtype).contiguous(), None, K,
+                            out_dtype=torch.float32 if in_pad is None else eng.dtype)
+        if in_pad is None:
+            dx = dxp.t.view(x_shape).to(x_dtype)
+        elif ph == 0 and pw == 0:
+            dx = dxp.t.view(x_shape)
+        else:
+            full = Act(torch.zeros(x_shape, dtype=eng.dtype, device=eng.device), B, 1, 1, K, ph, pw)
+            full.interior().copy_(dxp.t.view(B, 1, 1, K))
+            dx = full.t
+        return dx, dw, db, None, None, None, None, None
+
+
+class TextLastFn(torch.autograd.Function):
+    """nn.ConvTranspose1d(C, 71, 4, 2, 1) -> fp32 pre-softmax scores [B, L, 71]
+    (char_encoding/DataGeneratorText.py:44-49, :73-74); the LogSoftmax lives in the likelihood kernel."""
+
+    @staticmethod
+    def forward(ctx, x_t, w, bias, eng, B, Lq, in_pad):
+        Cc, Fq = w.shape[0], w.shape[1]
+        x = Act.like(x_t, B, 1, Lq, Cc, 0, in_pad)
+        out = eng.gemm_up(x, phase_form(w, eng.dtype), bias, Fq, out_dtype=torch.float32)
+        ctx.save_for_backward(x_t, w)
+        ctx.eng, ctx.geo = eng, (B, Lq, in_pad)
+        return out.t.view(B, 2 * Lq, Fq)
+
+    @staticmethod
+    def backward(ctx, dy_t):
+        x_t, w = ctx.saved_tensors
+        eng = ctx.eng
+        B, Lq, in_pad = ctx.geo
+        Cc, Fq = w.shape[0], w.shape[1]
+        Fp = (Fq + 15) // 16 * 16
+        x = Act.like(x_t, B, 1, Lq, Cc, 0, in_pad)
+        # bordered, channel-padded copy of the fp32 gradient in the activation dtype
+        dyp = Act.empty(B, 1, 2 * Lq, Fp, 0, 1, eng.dtype, eng.device)
+        dyc = dy_t.contiguous()
+        src = L.View(dyc.data_ptr(), L.F32, B, 1, 2 * Lq, Fq, 0, 0, 0, 2 * Lq * Fq, 2 * Lq * Fq, Fq)
+        eng.convert(src, False, dyp)
+        db = eng.colsum(Act.like(dyc, B, 1, 2 * Lq, Fq)) if Fq % 4 == 0 else dyc.sum((0, 1))
+        wpad = torch.zeros(Cc, Fp, 4, dtype=torch.float32, device=eng.device)
+        wpad[:, :Fq] = w
+        # dgrad of a stride-2 deconv = stride-2 conv over the bordered gradient, conv-form weights [ci,(kx,co)]
+        dx = eng.gemm_down(dyp, conv_form(wpad, eng.dtype), None, 4, 2, 1, Cc)
+        g = eng.wgrad_down(dyp, 4, 2, 1, x)                     # [Cc, 4*Fp]
+        dw = g.view(Cc, 4, Fp)[:, :, :Fq].permute(0, 2, 1).contiguous()
+        if in_pad:
+            full = Act(torch.zeros_like(x_t), B, 1, Lq, Cc, 0, in_pad)
+            full.interior().copy_(dx.t)
+            dxt = full.t
+        else:
+            dxt = dx.t.view_as(x_t)
+        return dxt, dw, db, None, None, None, None
+
+
+# ---- likelihood reductions ------------------------------------------------------------------------------------
+class LaplaceLogProbSumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, loc, target, scale, eng):
+        loc = loc.contiguous()
+        target = target.contiguous().float()
+        n = loc.numel()
+        nc = int(min(148 * 8, max(1, n // 4096)))
+        out = eng.f32(1)
+        L.call('mopoe_laplace_logprob_sum', L.ptr(loc), L.ptr(target), n, float(scale), L.ptr(out),
+               L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
+        ctx.save_for_backward(loc, target)
+        ctx.eng, ctx.scale = eng, float(scale)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        loc, target = ctx.saved_tensors
+        dloc = torch.empty_like(loc)
+        L.call('mopoe_laplace_logprob_bwd', L.ptr(loc), L.ptr(target), loc.numel(), ctx.scale,
+               L.ptr(g.contiguous().float()), L.ptr(dloc), L.stream_ptr())
+        return dloc, None, None, None
+
+
+class CategoricalLogProbSumFn(torch.autograd.Function):
+    """scores: pre-softmax [B, L, V]; target: one-hot [B, L, V]."""
+
+    @staticmethod
+    def forward(ctx, scores, target, eng):
+        scores = scores.contiguous()
+        target = target.contiguous().float()
+        V = scores.shape[-1]
+        rows = scores.numel() // V
+        nc = int(min(148 * 8, max(1, rows // 64)))
+        out = eng.f32(1)
+        idx = torch.empty(rows, dtype=torch.int32, device=scores.device)
+        L.call('mopoe_categorical_logprob_sum', L.ptr(scores), L.ptr(target), None, rows, V, None, L.ptr(idx),
+               L.ptr(out), L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
+        ctx.save_for_backward(scores, idx)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        scores, idx = ctx.saved_tensors
+        V = scores.shape[-1]
+        d = torch.empty_like(scores)
+        L.call('mopoe_categorical_logprob_bwd', L.ptr(scores), L.ptr(idx), scores.numel() // V, V,
+               L.ptr(g.contiguous().float()), L.ptr(d), L.stream_ptr())
+        return d, None, None
+
+
+def log_softmax_rows(scores, eng):
+    """log_softmax over the last dim through the categorical kernel (no grad; API/`.logits` use)."""
+    scores = scores.detach().contiguous()
+    V = scores.shape[-1]
+    rows = scores.numel() // V
+    out = torch.empty_like(scores)
+    idx = torch.zeros(rows, dtype=torch.int32, device=scores.device)
+    dummy = eng.f32(1)
+    nc = int(min(148 * 8, max(1, rows // 64)))
+    L.call('mopoe_categorical_logprob_sum', L.ptr(scores), None, L.ptr(idx), rows, V, L.ptr(out), None, L.ptr(dummy),
+           L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
+    return out

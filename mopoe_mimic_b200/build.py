@@ -1,0 +1,57 @@
+"""Build libmopoe_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libmopoe_b200.so')
+SOURCES = ['elementwise.cu', 'fusion.cu', 'nll.cu', 'conv_direct.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gemm_api.cu']
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC']
+
+
+def _nvcc():
+    for c in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return 'nvcc'
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    objdir = os.path.join(HERE, 'build')
+    os.makedirs(objdir, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
+    headers.append(os.path.join(os.path.dirname(HERE), 'include', 'mopoe_b200.h'))
+    nvcc = _nvcc()
+    jobs = []
+    for s in SOURCES:
+        src = os.path.join(CSRC, s)
+        obj = os.path.join(objdir, s[:-3] + '.o')
+        if force or _stale(obj, [src] + headers):
+            jobs.append([nvcc] + NVCC_FLAGS + ['-c', src, '-o', obj])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed: %s\n%s\n%s' % (' '.join(cmd), r.stdout, r.stderr))
+        if verbose and (r.stdout or r.stderr):
+            print(r.stdout, r.stderr)
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    objs = [os.path.join(objdir, s[:-3] + '.o') for s in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        run([nvcc, '-shared', '-o', LIB] + objs)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose=True))

@@ -1,0 +1,528 @@
+// elementwise.cu — HBM-bound passes of the residual blocks: training-mode BatchNorm statistics,
+// fused BN+ReLU(+dropout) apply, residual combine, their backward halves, layout conversion,
+// dropout-mask generation and the flat Adam update.
+//
+// All kernels address activations through channels-last views (4 consecutive channels per thread,
+// so a warp touches 512 B (fp32) / 256 B (bf16) contiguous per pixel row) and accumulate reductions
+// in fp64 with a fixed two-stage order (per-chunk partials, then one thread per channel sums the
+// chunks in order) — run-to-run deterministic, no atomics.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+// ---- error string ------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void mopoe_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* mopoe_last_error(void) { return g_err; }
+extern "C" int mopoe_version(void) { return 100; }
+
+constexpr int VEC = 4;
+constexpr int EW_THREADS = 256;
+
+static int check_same(const mopoe_view_t* a, const mopoe_view_t* b, const char* what) {
+    if (a->B != b->B || a->H != b->H || a->W != b->W || a->C != b->C || a->dtype != b->dtype)
+        MOPOE_FAIL("%s: view mismatch [%d,%d,%d,%d]/%d vs [%d,%d,%d,%d]/%d", what, a->B, a->H, a->W, a->C,
+                   a->dtype, b->B, b->H, b->W, b->C, b->dtype);
+    return 0;
+}
+
+// decode a flat index over the STORAGE of `o` (interior + border) into coordinates
+template <typename T>
+__device__ __forceinline__ bool decode_storage(const DView<T>& o, long long idx, int& b, int& h, int& w, int& c) {
+    const int CV = o.C / VEC;
+    const int Ws = o.W + 2 * o.pw, Hs = o.H + 2 * o.ph;
+    c = (int)(idx % CV) * VEC;
+    long long pos = idx / CV;
+    int ws = (int)(pos % Ws);
+    pos /= Ws;
+    int hs = (int)(pos % Hs);
+    b = (int)(pos / Hs);
+    h = hs - o.ph;
+    w = ws - o.pw;
+    return h >= 0 && h < o.H && w >= 0 && w < o.W;
+}
+template <typename T>
+static long long storage_threads(const DView<T>& o) {
+    return (long long)o.B * (o.H + 2 * o.ph) * (o.W + 2 * o.pw) * (o.C / VEC);
+}
+template <typename T>
+__device__ __forceinline__ long long vaddr(const DView<T>& v, int b, int h, int w, int c) {
+    return (long long)b * v.sB + (long long)h * v.sH + (long long)w * v.sW + c;
+}
+
+// ---- per-channel reductions (BN stats, BN backward sums, bias gradient) ------------------------------
+// block = (32 channel-vec lanes, 8 row lanes); grid = (ceil(C/128), nchunk)
+enum { RED_STATS = 0, RED_BNBWD = 1, RED_COLSUM = 2 };
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DView<const T> dy, DView<const T> gate,
+                                                          int has_gate, float gscale, const uint8_t* mask,
+                                                          int mask_mode, const float* mean, const float* invstd,
+                                                          double* ws, int nchunk) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int c = (blockIdx.x * 32 + tx) * VEC;
+    const bool cvalid = c < x.C;
+    const long long rows = (long long)x.B * x.H * x.W;
+    const long long rpc = (rows + nchunk - 1) / nchunk;
+    const long long r0 = (long long)blockIdx.y * rpc;
+    const long long r1 = min(rows, r0 + rpc);
+    double s0[VEC], s1[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s0[i] = s1[i] = 0.0;
+    float mu[VEC], is[VEC];
+    if (MODE == RED_BNBWD && cvalid) {
+        ldv<VEC>(mean + c, mu);
+        ldv<VEC>(invstd + c, is);
+    }
+    if (cvalid) {
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            int w = (int)(r % x.W);
+            long long t = r / x.W;
+            int h = (int)(t % x.H);
+            int b = (int)(t / x.H);
+            float xv[VEC], mk[VEC];
+            ldv<VEC>(x.p + vaddr(x, b, h, w, c), xv);
+            ldmask<VEC>(mask, mask_mode, (long long)b * x.C + c, r * x.C + c, mk);
+            if (MODE == RED_STATS) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    double v = (double)(xv[i] * mk[i]);
+                    s0[i] += v;
+                    s1[i] += v * v;
+                }
+            } else if (MODE == RED_COLSUM) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) s0[i] += (double)xv[i];
+            } else {
+                float g[VEC], gt[VEC];
+                ldv<VEC>(dy.p + vaddr(dy, b, h, w, c), g);
+                if (has_gate) ldv<VEC>(gate.p + vaddr(gate, b, h, w, c), gt);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    float gg = gscale * g[i];
+                    if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
+                    float xh = (xv[i] * mk[i] - mu[i]) * is[i];
+                    s0[i] += (double)gg;
+                    s1[i] += (double)gg * (double)xh;
+                }
+            }
+        }
+    }
+    __shared__ double sm[2][8][32][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        sm[0][ty][tx][i] = s0[i];
+        sm[1][ty][tx][i] = s1[i];
+    }
+    __syncthreads();
+    if (ty == 0 && cvalid) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            double a = 0.0, b2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a += sm[0][j][tx][i];
+                b2 += sm[1][j][tx][i];
+            }
+            ws[((long long)blockIdx.y * 2 + 0) * x.C + c + i] = a;
+            ws[((long long)blockIdx.y * 2 + 1) * x.C + c + i] = b2;
+        }
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* ws, int nchunk, int C, double count, float eps, float momentum,
+                                   float* mean, float* invstd, float* rmean, float* rvar) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < nchunk; ++k) {
+        s += ws[((long long)k * 2 + 0) * C + c];
+        q += ws[((long long)k * 2 + 1) * C + c];
+    }
+    double m = s / count;
+    double var = q / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean) {
+        double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+        rmean[c] = (float)((1.0 - momentum) * (double)rmean[c] + momentum * m);
+        rvar[c] = (float)((1.0 - momentum) * (double)rvar[c] + momentum * unb);
+    }
+}
+
+__global__ void sums_finalize_kernel(const double* ws, int nchunk, int C, float* out0, float* out1, int accumulate,
+                                     float* sums) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < nchunk; ++k) {
+        s += ws[((long long)k * 2 + 0) * C + c];
+        q += ws[((long long)k * 2 + 1) * C + c];
+    }
+    if (out0) out0[c] = (accumulate ? out0[c] : 0.f) + (float)s;   // dbeta / colsum
+    if (out1) out1[c] = (accumulate ? out1[c] : 0.f) + (float)q;   // dgamma
+    if (sums) {
+        sums[c] = (float)s;
+        sums[C + c] = (float)q;
+    }
+}
+
+template <int MODE>
+static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
+                         const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, double* ws,
+                         int nchunk, cudaStream_t st) {
+    MOPOE_REQUIRE(x->C % VEC == 0, "reduce: C=%d not a multiple of %d", x->C, VEC);
+    MOPOE_REQUIRE(nchunk >= 1 && ws, "reduce: bad workspace");
+    dim3 block(32, 8), grid((x->C + 127) / 128, nchunk);
+    MOPOE_DISPATCH_T(x->dtype, T, {
+        DView<const T> xv = make_dview<const T>(x);
+        DView<const T> dv = dy ? make_dview<const T>(dy) : xv;
+        DView<const T> gv = gate ? make_dview<const T>(gate) : xv;
+        reduce_rows_kernel<T, MODE><<<grid, block, 0, st>>>(xv, dv, gv, gate != nullptr, gscale, mask, mask_mode,
+                                                           mean, invstd, ws, nchunk);
+    });
+    MOPOE_CHECK_LAUNCH("reduce_rows");
+    return 0;
+}
+
+extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, double* ws, int nchunk,
+                              float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                              float* running_var, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_reduce<RED_STATS>(x, nullptr, nullptr, 1.f, mask, mask_mode, nullptr, nullptr, ws, nchunk, st)) return 1;
+    double count = (double)x->B * x->H * x->W;
+    bn_finalize_kernel<<<(x->C + 127) / 128, 128, 0, st>>>(ws, nchunk, x->C, count, eps, momentum, mean, invstd,
+                                                          running_mean, running_var);
+    MOPOE_CHECK_LAUNCH("bn_finalize");
+    return 0;
+}
+
+extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_reduce<RED_COLSUM>(v, nullptr, nullptr, 1.f, nullptr, MOPOE_MASK_NONE, nullptr, nullptr, ws, nchunk, st))
+        return 1;
+    sums_finalize_kernel<<<(v->C + 127) / 128, 128, 0, st>>>(ws, nchunk, v->C, out, nullptr, accumulate, nullptr);
+    MOPOE_CHECK_LAUNCH("colsum_finalize");
+    return 0;
+}
+
+extern "C" int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
+                                   const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
+                                   const float* invstd, double* ws, int nchunk, float* dgamma, float* dbeta,
+                                   int accumulate, float* sums, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (check_same(x, dy, "bn_bwd_reduce(dy)")) return 1;
+    if (gate && check_same(x, gate, "bn_bwd_reduce(gate)")) return 1;
+    if (launch_reduce<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st)) return 1;
+    sums_finalize_kernel<<<(x->C + 127) / 128, 128, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
+    MOPOE_CHECK_LAUNCH("bn_bwd_finalize");
+    return 0;
+}
+
+// ---- forward apply kernels ----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(DView<const T> x, const uint8_t* mask, int mask_mode,
+                                                              const float* mean, const float* invstd,
+                                                              const float* gamma, const float* beta, int relu,
+                                                              DView<T> out, long long total) {
+    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+    if (idx >= total) return;
+    int b, h, w, c;
+    bool in = decode_storage(out, idx, b, h, w, c);
+    float o[VEC] = {0.f, 0.f, 0.f, 0.f};
+    if (in) {
+        float xv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
+        ldv<VEC>(x.p + vaddr(x, b, h, w, c), xv);
+        ldmask<VEC>(mask, mask_mode, (long long)b * x.C + c, (((long long)b * x.H + h) * x.W + w) * x.C + c, mk);
+        ldv<VEC>(mean + c, mu);
+        ldv<VEC>(invstd + c, is);
+        ldv<VEC>(gamma + c, ga);
+        ldv<VEC>(beta + c, be);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float y = (xv[i] * mk[i] - mu[i]) * is[i] * ga[i] + be[i];
+            o[i] = (relu && y < 0.f) ? 0.f : y;
+        }
+    }
+    stv<VEC>(out.p + vaddr(out, b, h, w, c), o);
+}
+
+extern "C" int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
+                              const float* invstd, const float* gamma, const float* beta, int relu,
+                              const mopoe_view_t* out, void* stream) {
+    if (check_same(x, out, "bn_apply")) return 1;
+    MOPOE_REQUIRE(x->C % VEC == 0, "bn_apply: C=%d", x->C);
+    MOPOE_DISPATCH_T(x->dtype, T, {
+        DView<T> ov = make_dview<T>(out);
+        long long total = storage_threads(ov);
+        bn_apply_kernel<T><<<(unsigned)ceil_div64(total, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
+            make_dview<const T>(x), mask, mask_mode, mean, invstd, gamma, beta, relu, ov, total);
+    });
+    MOPOE_CHECK_LAUNCH("bn_apply");
+    return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) combine_kernel(DView<const T> r, const float* mean, const float* invstd,
+                                                             const float* gamma, const float* beta, DView<const T> cc,
+                                                             const uint8_t* mask, int mask_mode, float a, float bcoef,
+                                                             DView<T> out, long long total) {
+    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+    if (idx >= total) return;
+    int b, h, w, c;
+    bool in = decode_storage(out, idx, b, h, w, c);
+    float o[VEC] = {0.f, 0.f, 0.f, 0.f};
+    if (in) {
+        float rv[VEC], cv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
+        ldv<VEC>(r.p + vaddr(r, b, h, w, c), rv);
+        ldv<VEC>(cc.p + vaddr(cc, b, h, w, c), cv);
+        ldmask<VEC>(mask, mask_mode, (long long)b * r.C + c, (((long long)b * r.H + h) * r.W + w) * r.C + c, mk);
+        ldv<VEC>(mean + c, mu);
+        ldv<VEC>(invstd + c, is);
+        ldv<VEC>(gamma + c, ga);
+        ldv<VEC>(beta + c, be);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+            o[i] = a * ((rv[i] - mu[i]) * is[i] * ga[i] + be[i]) + bcoef * (cv[i] * mk[i]);
+    }
+    stv<VEC>(out.p + vaddr(out, b, h, w, c), o);
+}
+
+extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma,
+                             const float* beta, const mopoe_view_t* c, const uint8_t* mask, int mask_mode, float a,
+                             float b, const mopoe_view_t* out, void* stream) {
+    if (check_same(r, out, "combine(out)") || check_same(r, c, "combine(c)")) return 1;
+    MOPOE_REQUIRE(r->C % VEC == 0, "combine: C=%d", r->C);
+    MOPOE_DISPATCH_T(r->dtype, T, {
+        DView<T> ov = make_dview<T>(out);
+        long long total = storage_threads(ov);
+        combine_kernel<T><<<(unsigned)ceil_div64(total, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
+            make_dview<const T>(r), mean, invstd, gamma, beta, make_dview<const T>(c), mask, mask_mode, a, b, ov, total);
+    });
+    MOPOE_CHECK_LAUNCH("combine");
+    return 0;
+}
+
+// ---- backward apply kernels ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T> dy, DView<const T> gate, int has_gate,
+                                                                  float gscale, DView<const T> x, const uint8_t* mask,
+                                                                  int mask_mode, const float* mean, const float* invstd,
+                                                                  const float* gamma, const float* sums, float inv_cnt,
+                                                                  DView<const T> addend, int has_add, DView<T> out,
+                                                                  long long total) {
+    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+    if (idx >= total) return;
+    int b, h, w, c;
+    bool in = decode_storage(out, idx, b, h, w, c);
+    float o[VEC] = {0.f, 0.f, 0.f, 0.f};
+    if (in) {
+        const int C = x.C;
+        float g[VEC], gt[VEC], xv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], sg[VEC], sgx[VEC], ad[VEC];
+        ldv<VEC>(dy.p + vaddr(dy, b, h, w, c), g);
+        if (has_gate) ldv<VEC>(gate.p + vaddr(gate, b, h, w, c), gt);
+        ldv<VEC>(x.p + vaddr(x, b, h, w, c), xv);
+        ldmask<VEC>(mask, mask_mode, (long long)b * C + c, (((long long)b * x.H + h) * x.W + w) * C + c, mk);
+        ldv<VEC>(mean + c, mu);
+        ldv<VEC>(invstd + c, is);
+        ldv<VEC>(gamma + c, ga);
+        ldv<VEC>(sums + c, sg);
+        ldv<VEC>(sums + C + c, sgx);
+        if (has_add) ldv<VEC>(addend.p + vaddr(addend, b, h, w, c), ad);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float gg = gscale * g[i];
+            if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
+            float xh = (xv[i] * mk[i] - mu[i]) * is[i];
+            float dv = ga[i] * is[i] * (gg - sg[i] * inv_cnt - xh * sgx[i] * inv_cnt);
+            o[i] = dv * mk[i] + (has_add ? ad[i] : 0.f);
+        }
+    }
+    stv<VEC>(out.p + vaddr(out, b, h, w, c), o);
+}
+
+extern "C" int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
+                                  const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
+                                  const float* invstd, const float* gamma, const float* sums,
+                                  const mopoe_view_t* addend, const mopoe_view_t* out, void* stream) {
+    if (check_same(x, dy, "bn_bwd_apply(dy)") || check_same(x, out, "bn_bwd_apply(out)")) return 1;
+    if (gate && check_same(x, gate, "bn_bwd_apply(gate)")) return 1;
+    if (addend && check_same(x, addend, "bn_bwd_apply(addend)")) return 1;
+    MOPOE_REQUIRE(x->C % VEC == 0, "bn_bwd_apply: C=%d", x->C);
+    float inv_cnt = 1.f / ((float)x->B * (float)x->H * (float)x->W);
+    MOPOE_DISPATCH_T(x->dtype, T, {
+        DView<T> ov = make_dview<T>(out);
+        DView<const T> xv = make_dview<const T>(x);
+        long long total = storage_threads(ov);
+        bn_bwd_apply_kernel<T><<<(unsigned)ceil_div64(total, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
+            make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate != nullptr, gscale, xv, mask,
+            mask_mode, mean, invstd, gamma, sums, inv_cnt, addend ? make_dview<const T>(addend) : xv,
+            addend != nullptr, ov, total);
+    });
+    MOPOE_CHECK_LAUNCH("bn_bwd_apply");
+    return 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(EW_THREADS) scale_mask_kernel(DView<const T> dy, const uint8_t* mask, int mask_mode,
+                                                                float scale, DView<T> out, long long total) {
+    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+    if (idx >= total) return;
+    int b, h, w, c;
+    bool in = decode_storage(out, idx, b, h, w, c);
+    float o[VEC] = {0.f, 0.f, 0.f, 0.f};
+    if (in) {
+        float g[VEC], mk[VEC];
+        ldv<VEC>(dy.p + vaddr(dy, b, h, w, c), g);
+        ldmask<VEC>(mask, mask_mode, (long long)b * dy.C + c, (((long long)b * dy.H + h) * dy.W + w) * dy.C + c, mk);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = scale * g[i] * mk[i];
+    }
+    stv<VEC>(out.p + vaddr(out, b, h, w, c), o);
+}
+
+extern "C" int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int mask_mode, float scale,
+                                const mopoe_view_t* out, void* stream) {
+    if (check_same(dy, out, "scale_mask")) return 1;
+    MOPOE_REQUIRE(dy->C % VEC == 0, "scale_mask: C=%d", dy->C);
+    MOPOE_DISPATCH_T(dy->dtype, T, {
+        DView<T> ov = make_dview<T>(out);
+        long long total = storage_threads(ov);
+        scale_mask_kernel<T><<<(unsigned)ceil_div64(total, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
+            make_dview<const T>(dy), mask, mask_mode, scale, ov, total);
+    });
+    MOPOE_CHECK_LAUNCH("scale_mask");
+    return 0;
+}
+
+// ---- layout / dtype conversion ------------------------------------------------------------------------
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(EW_THREADS) convert_kernel(DView<const TS> s, int src_nchw, DView<TD> d,
+                                                            long long total) {
+    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+    if (idx >= total) return;
+    const int Ws = d.W + 2 * d.pw, Hs = d.H + 2 * d.ph;
+    int c = (int)(idx % d.C);
+    long long pos = idx / d.C;
+    int ws = (int)(pos % Ws);
+    pos /= Ws;
+    int hs = (int)(pos % Hs);
+    int b = (int)(pos / Hs);
+    int h = hs - d.ph, w = ws - d.pw;
+    float v = 0.f;
+    if (h >= 0 && h < d.H && w >= 0 && w < d.W && c < s.C) {
+        long long a = src_nchw ? (((long long)b * s.C + c) * s.H + h) * s.W + w : vaddr(s, b, h, w, c);
+        if constexpr (sizeof(TS) == 4) v = s.p[a]; else v = __bfloat162float(s.p[a]);
+    }
+    long long o = vaddr(d, b, h, w, c);
+    if constexpr (sizeof(TD) == 4) d.p[o] = v; else d.p[o] = __float2bfloat16_rn(v);
+}
+
+extern "C" int mopoe_convert(const mopoe_view_t* src, int src_nchw, const mopoe_view_t* dst, void* stream) {
+    MOPOE_REQUIRE(src->B == dst->B && src->H == dst->H && src->W == dst->W && src->C <= dst->C,
+                  "convert: shape mismatch");
+    long long total = (long long)dst->B * (dst->H + 2 * dst->ph) * (dst->W + 2 * dst->pw) * dst->C;
+    unsigned grid = (unsigned)ceil_div64(total, EW_THREADS);
+    cudaStream_t st = (cudaStream_t)stream;
+    MOPOE_DISPATCH_T(src->dtype, TS, {
+        MOPOE_DISPATCH_T(dst->dtype, TD, {
+            convert_kernel<TS, TD><<<grid, EW_THREADS, 0, st>>>(make_dview<const TS>(src), src_nchw,
+                                                                 make_dview<TD>(dst), total);
+        });
+    });
+    MOPOE_CHECK_LAUNCH("convert");
+    return 0;
+}
+
+// ---- dropout masks: Philox-4x32-10, one 128-bit block -> 128 keep bytes per thread -------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+        uint32_t n0 = hi1 ^ ctr[1] ^ k0, n1 = lo1, n2 = hi0 ^ ctr[3] ^ k1, n3 = lo0;
+        ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__global__ void dropout_mask_kernel(uint8_t* mask, long long n, uint64_t seed, uint64_t offset) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long base = t * 128;
+    if (base >= n) return;
+    uint64_t cidx = (uint64_t)t + offset;
+    uint32_t ctr[4] = {(uint32_t)cidx, (uint32_t)(cidx >> 32), 0x6d6f706fu, 0x65u};
+    philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+    if (base + 128 <= n && ((uintptr_t)(mask + base) & 15) == 0) {
+#pragma unroll
+        for (int wd = 0; wd < 4; ++wd) {
+            uint32_t bits = ctr[wd];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t nib = (bits >> (q * 16 + j * 4)) & 0xFu;
+                    o[j] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+                }
+                *reinterpret_cast<uint4*>(mask + base + wd * 32 + q * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    } else {
+        for (int i = 0; i < 128 && base + i < n; ++i) mask[base + i] = (ctr[i >> 5] >> (i & 31)) & 1u;
+    }
+}
+extern "C" int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+    if (n <= 0) return 0;
+    long long threads = ceil_div64(n, 128);
+    dropout_mask_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, seed, offset);
+    MOPOE_CHECK_LAUNCH("dropout_mask");
+    return 0;
+}
+
+// ---- flat Adam -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, long long n4,
+                                                   long long n, float lr_c, float b1, float b2, float eps, float inv_sqrt_bc2,
+                                                   float gscale) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gk = G[k] * gscale;
+            M[k] = b1 * M[k] + (1.f - b1) * gk;
+            V[k] = b2 * V[k] + (1.f - b2) * gk * gk;
+            P[k] -= lr_c * M[k] / (sqrtf(V[k]) * inv_sqrt_bc2 + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    } else if (i == n4) {
+        for (long long k = n4 * 4; k < n; ++k) {
+            float gk = g[k] * gscale;
+            m[k] = b1 * m[k] + (1.f - b1) * gk;
+            v[k] = b2 * v[k] + (1.f - b2) * gk * gk;
+            p[k] -= lr_c * m[k] / (sqrtf(v[k]) * inv_sqrt_bc2 + eps);
+        }
+    }
+}
+extern "C" int mopoe_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                               float beta2, float eps, int step, float grad_scale, void* stream) {
+    if (n <= 0) return 0;
+    MOPOE_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam: unaligned buffers");
+    double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    long long n4 = n / 4;
+    adam_kernel<<<(unsigned)ceil_div64(n4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
+        p, g, m, v, n4, n, (float)(lr / bc1), beta1, beta2, eps, (float)(1.0 / sqrt(bc2)), grad_scale);
+    MOPOE_CHECK_LAUNCH("adam");
+    return 0;
+}

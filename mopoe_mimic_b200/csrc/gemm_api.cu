@@ -1,0 +1,32 @@
+// gemm_api.cu — public implicit-GEMM entry points: pick the tcgen05/TMA kernel when the problem is
+// eligible (bf16 operands, tile-aligned shapes, sm_100 device), else the CUDA-core kernel.
+#include "common.cuh"
+
+int mopoe_conv_gemm_simt(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* stream);
+size_t mopoe_conv_wgrad_ws_simt(const mopoe_window_t* A, const mopoe_rows_t* dY);
+int mopoe_conv_wgrad_simt(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
+                          size_t ws_bytes, void* stream);
+// gemm_tc.cu
+int mopoe_tc_fwd_eligible(const mopoe_window_t* A, const mopoe_rows_t* D);
+int mopoe_conv_gemm_tc(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* stream);
+int mopoe_tc_wgrad_eligible(const mopoe_window_t* A, const mopoe_rows_t* dY);
+size_t mopoe_conv_wgrad_ws_tc(const mopoe_window_t* A, const mopoe_rows_t* dY);
+int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
+                        size_t ws_bytes, void* stream);
+
+extern "C" int mopoe_conv_gemm(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D,
+                               int impl, void* stream) {
+    if (impl == 2 && !mopoe_tc_fwd_eligible(A, D)) MOPOE_FAIL("conv_gemm: tcgen05 path forced but problem not eligible");
+    if (impl != 1 && mopoe_tc_fwd_eligible(A, D)) return mopoe_conv_gemm_tc(A, Wp, bias, D, stream);
+    return mopoe_conv_gemm_simt(A, Wp, bias, D, stream);
+}
+extern "C" size_t mopoe_conv_wgrad_ws(const mopoe_window_t* A, const mopoe_rows_t* dY, int impl) {
+    if (impl != 1 && mopoe_tc_wgrad_eligible(A, dY)) return mopoe_conv_wgrad_ws_tc(A, dY);
+    return mopoe_conv_wgrad_ws_simt(A, dY);
+}
+extern "C" int mopoe_conv_wgrad(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
+                                size_t ws_bytes, int impl, void* stream) {
+    if (impl == 2 && !mopoe_tc_wgrad_eligible(A, dY)) MOPOE_FAIL("conv_wgrad: tcgen05 path forced but problem not eligible");
+    if (impl != 1 && mopoe_tc_wgrad_eligible(A, dY)) return mopoe_conv_wgrad_tc(A, dY, dWp, accumulate, ws, ws_bytes, stream);
+    return mopoe_conv_wgrad_simt(A, dY, dWp, accumulate, ws, ws_bytes, stream);
+}

@@ -1,0 +1,237 @@
+// nll.cu — fused reconstruction log-likelihood reductions (HBM-bound; north_star item 3).
+//
+//   Laplace:      sum_i -(log(2b) + |x_i - loc_i| / b)                      modalities/Modality.py:25-30
+//   Categorical:  log_softmax over the vocabulary + gather at argmax(target) char_encoding/DataGeneratorText.py:51,75
+//                                                                            modalities/utils.py:7-8
+// Reductions: per-thread fp32 over a short strip -> block fp64 -> per-block partial -> one warp sums
+// the partials in a fixed order (deterministic).
+#include "common.cuh"
+
+__device__ __forceinline__ double block_sum_256(double v) {
+    __shared__ double sm[8];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < 8 ? sm[threadIdx.x] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+__global__ void final_sum_kernel(const double* part, int n, float* out, float scale) {
+    double acc = 0.0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        int i = i0 + threadIdx.x;
+        acc += warp_sum(i < n ? part[i] : 0.0);
+    }
+    if (threadIdx.x == 0) out[0] = (float)(acc * (double)scale);
+}
+
+// ---- Laplace ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) laplace_fwd_kernel(const float* __restrict__ loc, const float* __restrict__ x,
+                                                          long long n, float inv_b, double* __restrict__ part) {
+    const long long n4 = n >> 2;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(loc) + i);
+        float4 b = __ldg(reinterpret_cast<const float4*>(x) + i);
+        acc += fabsf(b.x - a.x) + fabsf(b.y - a.y) + fabsf(b.z - a.z) + fabsf(b.w - a.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = n4 << 2; i < n; ++i) acc += fabsf(x[i] - loc[i]);
+    double s = block_sum_256((double)acc * (double)inv_b);
+    if (threadIdx.x == 0) part[blockIdx.x] = s;
+}
+__global__ void laplace_final_kernel(const double* part, int nchunk, double n, float log2b, float* out) {
+    double acc = 0.0;
+    for (int i0 = 0; i0 < nchunk; i0 += 32) {
+        int i = i0 + threadIdx.x;
+        acc += warp_sum(i < nchunk ? part[i] : 0.0);
+    }
+    if (threadIdx.x == 0) out[0] = (float)(-(n * (double)log2b) - acc);
+}
+extern "C" int mopoe_laplace_logprob_sum(const float* loc, const float* x, int64_t n, float scale, float* out,
+                                         double* ws, int nchunk, void* stream) {
+    MOPOE_REQUIRE(nchunk >= 1 && nchunk <= 65535, "laplace: nchunk=%d", nchunk);
+    MOPOE_REQUIRE((((uintptr_t)loc | (uintptr_t)x) & 15) == 0, "laplace: unaligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    laplace_fwd_kernel<<<nchunk, 256, 0, st>>>(loc, x, n, 1.f / scale, ws);
+    MOPOE_CHECK_LAUNCH("laplace_fwd");
+    // the reference evaluates log(2*scale) on an fp32 tensor (torch.tensor(0.75), ConvNetworksImgMimic.py:54)
+    laplace_final_kernel<<<1, 32, 0, st>>>(ws, nchunk, (double)n, logf(2.f * scale), out);
+    MOPOE_CHECK_LAUNCH("laplace_final");
+    return 0;
+}
+__global__ void __launch_bounds__(256) laplace_bwd_kernel(const float* __restrict__ loc, const float* __restrict__ x,
+                                                          long long n, float inv_b, const float* __restrict__ gout,
+                                                          float* __restrict__ dloc) {
+    const float g = gout[0] * inv_b;
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(loc) + i);
+        float4 b = __ldg(reinterpret_cast<const float4*>(x) + i);
+        float4 o;   // d/dloc of -|x - loc|/b = sign(x - loc)/b
+        o.x = b.x > a.x ? g : (b.x < a.x ? -g : 0.f);
+        o.y = b.y > a.y ? g : (b.y < a.y ? -g : 0.f);
+        o.z = b.z > a.z ? g : (b.z < a.z ? -g : 0.f);
+        o.w = b.w > a.w ? g : (b.w < a.w ? -g : 0.f);
+        reinterpret_cast<float4*>(dloc)[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = n4 << 2; i < n; ++i) dloc[i] = x[i] > loc[i] ? g : (x[i] < loc[i] ? -g : 0.f);
+}
+extern "C" int mopoe_laplace_logprob_bwd(const float* loc, const float* x, int64_t n, float scale, const float* gout,
+                                         float* dloc, void* stream) {
+    long long blocks = ceil_div64(n >> 2, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    laplace_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(loc, x, n, 1.f / scale, gout, dloc);
+    MOPOE_CHECK_LAUNCH("laplace_bwd");
+    return 0;
+}
+
+// ---- Categorical: one warp per (b, l) row of V logits -------------------------------------------------
+constexpr int CAT_MAXV_PER_LANE = 8;   // V <= 256
+
+__global__ void __launch_bounds__(256) categorical_fwd_kernel(const float* __restrict__ y, const float* __restrict__ target,
+                                                              const int* __restrict__ idx_in, long long rows, int V,
+                                                              float* __restrict__ logits_out, int* __restrict__ idx_out,
+                                                              double* __restrict__ part) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (long long row = (long long)blockIdx.x * 8 + wib; row < rows; row += (long long)gridDim.x * 8) {
+        const float* yr = y + row * V;
+        float v[CAT_MAXV_PER_LANE];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) {
+            int k = lane + 32 * j;
+            v[j] = k < V ? yr[k] : -INFINITY;
+            mx = fmaxf(mx, v[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+#pragma unroll
+        for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) se += (lane + 32 * j < V) ? expf(v[j] - mx) : 0.f;
+        se = warp_sum(se);
+        const float lse = mx + logf(se);
+        int id;
+        if (target) {   // argmax of the target row, first maximum wins (torch .max(-1)[1] semantics)
+            const float* tr = target + row * V;
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) {
+                int k = lane + 32 * j;
+                if (k < V) {
+                    float t = tr[k];
+                    if (t > best) { best = t; bi = k; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            id = bi;
+        } else {
+            id = idx_in[row];
+        }
+        if (idx_out && lane == 0) idx_out[row] = id;
+        if (logits_out) {
+#pragma unroll
+            for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) {
+                int k = lane + 32 * j;
+                if (k < V) logits_out[row * V + k] = v[j] - lse;
+            }
+        }
+        // OneHotCategorical(logits=l).log_prob renormalises l again (idempotent up to rounding): emulate it
+        float l2[CAT_MAXV_PER_LANE], mx2 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) {
+            l2[j] = (lane + 32 * j < V) ? v[j] - lse : -INFINITY;
+            mx2 = fmaxf(mx2, l2[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+        float se2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) se2 += (lane + 32 * j < V) ? expf(l2[j] - mx2) : 0.f;
+        se2 = warp_sum(se2);
+        const float lse2 = mx2 + logf(se2);
+        float pick = 0.f;
+#pragma unroll
+        for (int j = 0; j < CAT_MAXV_PER_LANE; ++j)
+            if (lane + 32 * j == id) pick = l2[j] - lse2;
+        pick = warp_sum(pick);
+        if (lane == 0) acc += (double)pick;
+    }
+    __shared__ double sm[8];
+    if (lane == 0) sm[wib] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i];
+        part[blockIdx.x] = s;
+    }
+}
+extern "C" int mopoe_categorical_logprob_sum(const float* y, const float* target, const int32_t* idx, int64_t rows,
+                                             int V, float* logits_out, int32_t* idx_out, float* out, double* ws,
+                                             int nchunk, void* stream) {
+    MOPOE_REQUIRE(V >= 1 && V <= 32 * CAT_MAXV_PER_LANE, "categorical: V=%d unsupported (max %d)", V,
+                  32 * CAT_MAXV_PER_LANE);
+    MOPOE_REQUIRE(target || idx, "categorical: need target or idx");
+    MOPOE_REQUIRE(nchunk >= 1 && nchunk <= 65535, "categorical: nchunk=%d", nchunk);
+    cudaStream_t st = (cudaStream_t)stream;
+    categorical_fwd_kernel<<<nchunk, 256, 0, st>>>(y, target, idx, rows, V, logits_out, idx_out, ws);
+    MOPOE_CHECK_LAUNCH("categorical_fwd");
+    final_sum_kernel<<<1, 32, 0, st>>>(ws, nchunk, out, 1.f);
+    MOPOE_CHECK_LAUNCH("categorical_final");
+    return 0;
+}
+__global__ void __launch_bounds__(256) categorical_bwd_kernel(const float* __restrict__ y, const int* __restrict__ idx,
+                                                              long long rows, int V, const float* __restrict__ gout,
+                                                              float* __restrict__ dy) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const float g = gout[0];
+    for (long long row = (long long)blockIdx.x * 8 + wib; row < rows; row += (long long)gridDim.x * 8) {
+        const float* yr = y + row * V;
+        float v[CAT_MAXV_PER_LANE];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) {
+            int k = lane + 32 * j;
+            v[j] = k < V ? yr[k] : -INFINITY;
+            mx = fmaxf(mx, v[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+#pragma unroll
+        for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) se += (lane + 32 * j < V) ? expf(v[j] - mx) : 0.f;
+        se = warp_sum(se);
+        const float inv = 1.f / se;
+        const int id = idx[row];
+#pragma unroll
+        for (int j = 0; j < CAT_MAXV_PER_LANE; ++j) {
+            int k = lane + 32 * j;
+            if (k < V) dy[row * V + k] = g * ((k == id ? 1.f : 0.f) - expf(v[j] - mx) * inv);
+        }
+    }
+}
+extern "C" int mopoe_categorical_logprob_bwd(const float* y, const int32_t* idx, int64_t rows, int V,
+                                             const float* gout, float* dy, void* stream) {
+    MOPOE_REQUIRE(V >= 1 && V <= 32 * CAT_MAXV_PER_LANE, "categorical: V=%d unsupported", V);
+    long long blocks = ceil_div64(rows, 8);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    categorical_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, idx, rows, V, gout, dy);
+    MOPOE_CHECK_LAUNCH("categorical_bwd");
+    return 0;
+}

@@ -1,0 +1,295 @@
+"""Host-side engine: channels-last activation descriptors, implicit-GEMM problem builders, weight
+packing, and thin wrappers over the C ABI.  No math happens here — every op is a call into
+libmopoe_b200.so; torch is used for device memory, streams and (tiny) weight re-layouts.
+
+Layouts
+  activation  [B, H+2ph, W+2pw, C]  (1-D text: H = 1, ph = 0), zero border written by the producer
+  conv-form weights   Wc [a, (ky, kx, b)]       from a weight tensor Wg[a, b, ky, kx]
+  phase-form weights  Wp[py,px] [b, (r, kxi, a)] = Wg[a, b, KY[py][r], KX[px][kxi]],  KY = KX = ((3,1),(2,0))
+  full-form weights   Wf [(ky, kx, b), a]
+so that  conv k4/s2/p1  = one GEMM over 4-tap row windows of the padded input (conv-form),
+         deconv k4/s2/p1 = 2^nd sub-pixel phase GEMMs over 2-tap windows (phase-form),
+and each layer's dgrad is the other kind; wgrad always produces conv-form.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+KTAPS = ((3, 1), (2, 0))     # phase -> kernel taps in memory order of the 2-wide window
+
+
+class Act:
+    """Channels-last activation: storage tensor `t` [B, H+2ph, W+2pw, C]."""
+    __slots__ = ('t', 'B', 'H', 'W', 'C', 'ph', 'pw')
+
+    def __init__(self, t, B, H, W, C_, ph, pw):
+        self.t, self.B, self.H, self.W, self.C, self.ph, self.pw = t, B, H, W, C_, ph, pw
+
+    @staticmethod
+    def empty(B, H, W, C_, ph, pw, dtype, device):
+        return Act(torch.empty((B, H + 2 * ph, W + 2 * pw, C_), dtype=dtype, device=device), B, H, W, C_, ph, pw)
+
+    @staticmethod
+    def like(t, B, H, W, C_, ph=0, pw=0):
+        assert t.numel() == B * (H + 2 * ph) * (W + 2 * pw) * C_, (t.shape, B, H, W, C_, ph, pw)
+        return Act(t, B, H, W, C_, ph, pw)
+
+    @property
+    def Ws(self):
+        return self.W + 2 * self.pw
+
+    @property
+    def Hs(self):
+        return self.H + 2 * self.ph
+
+    @property
+    def dtype(self):
+        return self.t.dtype
+
+    def origin(self):
+        """element offset of interior (0,0,0,0) in storage"""
+        return (self.ph * self.Ws + self.pw) * self.C
+
+    def view(self):
+        isz = self.t.element_size()
+        return L.View(self.t.data_ptr() + self.origin() * isz, L.dtype_code(self.t.dtype), self.B, self.H, self.W,
+                      self.C, self.ph, self.pw, 0, self.Hs * self.Ws * self.C, self.Ws * self.C, self.C)
+
+    def interior(self):
+        return self.t[:, self.ph:self.ph + self.H, self.pw:self.pw + self.W, :]
+
+
+class Engine:
+    """Per-device scratch + launch helpers.  One per model; all calls go to the current CUDA stream."""
+
+    def __init__(self, device, dtype=torch.float32, impl=L.IMPL_AUTO):
+        L.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('mopoe_mimic_b200 needs a CUDA device (sm_100a); no CPU fallback exists')
+        self.dtype = dtype
+        self.impl = impl
+        self._ws64 = None
+        self._wsf = None
+        self.rng_offset = 0
+
+    # ---- scratch ------------------------------------------------------------------------------------
+    def ws64(self, n):
+        if self._ws64 is None or self._ws64.numel() < n:
+            self._ws64 = torch.empty(max(n, 1 << 16), dtype=torch.float64, device=self.device)
+        return self._ws64
+
+    def wsf(self, nbytes):
+        n = (nbytes + 3) // 4
+        if self._wsf is None or self._wsf.numel() < n:
+            self._wsf = torch.empty(max(n, 1 << 20), dtype=torch.float32, device=self.device)
+        return self._wsf
+
+    @staticmethod
+    def nchunk(rows, C_, per=1):
+        cg = (C_ + 127) // 128
+        want = max(1, (148 * 4 + cg - 1) // cg)
+        return int(max(1, min(want, (rows + 31) // 32)))
+
+    def f32(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    # ---- elementwise wrappers ---------------------------------------------------------------------------
+    def bn_stats(self, x, mask, mode, rmean=None, rvar=None, eps=1e-5, momentum=0.1):
+        rows = x.B * x.H * x.W
+        nc = self.nchunk(rows, x.C)
+        ws = self.ws64(2 * nc * x.C)
+        stats = self.f32(2, x.C)
+        L.call('mopoe_bn_stats', C.byref(x.view()), L.ptr(mask), mode, L.ptr(ws), nc, eps, momentum,
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(rmean), L.ptr(rvar), L.stream_ptr())
+        return stats
+
+    def bn_apply(self, x, mask, mode, stats, gamma, beta, relu, out):
+        L.call('mopoe_bn_apply', C.byref(x.view()), L.ptr(mask), mode, L.ptr(stats[0]), L.ptr(stats[1]),
+               L.ptr(gamma), L.ptr(beta), int(relu), C.byref(out.view()), L.stream_ptr())
+        return out
+
+    def combine(self, r, stats, gamma, beta, c, mask, mode, a, b, out):
+        L.call('mopoe_combine', C.byref(r.view()), L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(beta),
+               C.byref(c.view()), L.ptr(mask), mode, float(a), float(b), C.byref(out.view()), L.stream_ptr())
+        return out
+
+    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out):
+        """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x)."""
+        rows = x.B * x.H * x.W
+        nc = self.nchunk(rows, x.C)
+        ws = self.ws64(2 * nc * x.C)
+        sums = self.f32(2, x.C)
+        gv = C.byref(gate.view()) if gate is not None else None
+        L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums),
+               L.stream_ptr())
+        av = C.byref(addend.view()) if addend is not None else None
+        L.call('mopoe_bn_bwd_apply', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), av, C.byref(out.view()), L.stream_ptr())
+        return out
+
+    def scale_mask(self, dy, mask, mode, scale, out):
+        L.call('mopoe_scale_mask', C.byref(dy.view()), L.ptr(mask), mode, float(scale), C.byref(out.view()),
+               L.stream_ptr())
+        return out
+
+    def colsum(self, v, out=None):
+        rows = v.B * v.H * v.W
+        nc = self.nchunk(rows, v.C)
+        ws = self.ws64(2 * nc * v.C)
+        if out is None:
+            out = self.f32(v.C)
+        L.call('mopoe_colsum', C.byref(v.view()), L.ptr(out), 0, L.ptr(ws), nc, L.stream_ptr())
+        return out
+
+    def convert(self, src_view, nchw, dst):
+        L.call('mopoe_convert', C.byref(src_view), int(nchw), C.byref(dst.view()), L.stream_ptr())
+        return dst
+
+    def dropout_mask(self, n, seed):
+        m = torch.empty(n, dtype=torch.uint8, device=self.device)
+        L.call('mopoe_dropout_mask', L.ptr(m), n, int(seed) & (2 ** 64 - 1), self.rng_offset, L.stream_ptr())
+        self.rng_offset += (n + 127) // 128
+        return m
+
+    # ---- implicit-GEMM problem builders -------------------------------------------------------------------
+    def _gemm(self, win, wp, bias, rows):
+        assert wp.is_contiguous() and wp.dtype == self._win_dtype(win)
+        L.call('mopoe_conv_gemm', C.byref(win), L.ptr(wp), L.ptr(bias), C.byref(rows), self.impl, L.stream_ptr())
+
+    @staticmethod
+    def _win_dtype(win):
+        return torch.float32 if win.a_dtype == L.F32 else torch.bfloat16
+
+    def _wgrad(self, win, rows, N, K):
+        out = self.f32(N, K)
+        nbytes = L.load().mopoe_conv_wgrad_ws(C.byref(win), C.byref(rows), self.impl)
+        ws = self.wsf(nbytes) if nbytes else None
+        L.call('mopoe_conv_wgrad', C.byref(win), C.byref(rows), L.ptr(out), 0, L.ptr(ws), nbytes, self.impl,
+               L.stream_ptr())
+        return out
+
+    @staticmethod
+    def win_down(x, k, s, p):
+        """windows of a stride-s, kernel-k (k taps contiguous along W) conv over padded `x`"""
+        assert x.pw >= p and (x.H == 1 or x.ph >= p)
+        Cc = x.C
+        if x.H == 1:
+            OW = (x.W + 2 * p - k) // s + 1
+            return L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), OW, 1, x.B, 1, k * Cc, 0,
+                            (x.pw - p) * Cc, s * Cc, 0, x.Ws * Cc, 0), 1, OW
+        OH = (x.H + 2 * p - k) // s + 1
+        OW = (x.W + 2 * p - k) // s + 1
+        a_off = ((x.ph - p) * x.Ws + (x.pw - p)) * Cc
+        return L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), OW, OH, x.B, k, k * Cc, 0,
+                        a_off, s * Cc, s * x.Ws * Cc, x.Hs * x.Ws * Cc, x.Ws * Cc), OH, OW
+
+    @staticmethod
+    def rows_of(act, N=None):
+        """row addressing over the interior pixels of `act` in (w, h, b) order"""
+        return L.Rows(act.t.data_ptr(), L.dtype_code(act.dtype), N or act.C, act.origin(), act.C,
+                      act.Ws * act.C, act.Hs * act.Ws * act.C)
+
+    def gemm_down(self, x, wc, bias, k, s, p, n, out_dtype=None, out=None):
+        win, OH, OW = self.win_down(x, k, s, p)
+        if out is None:
+            out = Act.empty(x.B, OH, OW, n, 0, 0, out_dtype or x.dtype, self.device)
+        assert (out.B, out.H, out.W, out.C) == (x.B, OH, OW, n)
+        self._gemm(win, wc, bias, self.rows_of(out))
+        return out
+
+    def wgrad_down(self, xwin, k, s, p, yrows):
+        win, OH, OW = self.win_down(xwin, k, s, p)
+        assert (yrows.H, yrows.W, yrows.B) == (OH, OW, xwin.B), ((yrows.H, yrows.W), (OH, OW))
+        return self._wgrad(win, self.rows_of(yrows), yrows.C, win.R * win.KW)
+
+    def gemm_up(self, x, wph, bias, n, out_dtype=None):
+        """stride-2 k4 p1 transposed conv as 2^nd sub-pixel phase GEMMs (x must carry a border >= 1)"""
+        Cc = x.C
+        assert x.pw >= 1 and (x.H == 1 or x.ph >= 1)
+        if x.H == 1:
+            out = Act.empty(x.B, 1, 2 * x.W, n, 0, 0, out_dtype or x.dtype, self.device)
+            for px in range(2):
+                win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, 1, x.B, 1, 2 * Cc, 0,
+                               (x.pw - 1 + px) * Cc, Cc, 0, x.Ws * Cc, 0)
+                rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, px * n, 2 * n, 0, 2 * x.W * n)
+                self._gemm(win, wph[px], bias, rows)
+            return out
+        out = Act.empty(x.B, 2 * x.H, 2 * x.W, n, 0, 0, out_dtype or x.dtype, self.device)
+        OW = 2 * x.W
+        for py in range(2):
+            for px in range(2):
+                a_off = ((x.ph - 1 + py) * x.Ws + (x.pw - 1 + px)) * Cc
+                win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 2, 2 * Cc, 0,
+                               a_off, Cc, x.Ws * Cc, x.Hs * x.Ws * Cc, x.Ws * Cc)
+                rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, (py * OW + px) * n, 2 * n, 2 * OW * n,
+                              2 * x.H * OW * n)
+                self._gemm(win, wph[py * 2 + px], bias, rows)
+        return out
+
+    def gemm_rows(self, x, w, bias, n, out_shape=None, out_dtype=None):
+        """pointwise GEMM over the interior pixels of x: out[m, n] = sum_c x[m, c] w[n, c] (+bias)"""
+        Cc = x.C
+        if x.ph == 0 and x.pw == 0:
+            win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.B * x.H * x.W, 1, 1, 1, Cc, 0, 0, Cc, 0, 0, 0)
+        else:
+            win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 1, Cc, 0, x.origin(), Cc,
+                           x.Ws * Cc, x.Hs * x.Ws * Cc, 0)
+        B, H, W = out_shape[:3] if out_shape else (x.B, x.H, x.W)
+        nn_ = out_shape[3] if out_shape else n
+        out = Act.empty(B, H, W, nn_, 0, 0, out_dtype or x.dtype, self.device)
+        if x.ph == 0 and x.pw == 0:
+            rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, 0, n, 0, 0)
+        else:
+            rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, 0, n, x.W * n, x.H * x.W * n)
+        self._gemm(win, w, bias, rows)
+        return out
+
+    def wgrad_rows(self, x, dy):
+        """dW[n, c] = sum_m dy[m, n] x[m, c] over interior pixels (both any padding)"""
+        Cc = x.C
+        win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 1, Cc, 0, x.origin(), Cc,
+                       x.Ws * Cc, x.Hs * x.Ws * Cc, 0)
+        assert (x.B, x.H, x.W) == (dy.B, dy.H, dy.W)
+        return self._wgrad(win, self.rows_of(dy), dy.C, Cc)
+
+
+# ---- weight packing (tiny torch re-layouts of the fp32 master weights) ------------------------------------
+def conv_form(Wg, dtype):
+    a, b = Wg.shape[:2]
+    if Wg.dim() == 3:
+        return Wg.permute(0, 2, 1).reshape(a, -1).to(dtype).contiguous()
+    return Wg.permute(0, 2, 3, 1).reshape(a, -1).to(dtype).contiguous()
+
+
+def conv_form_grad(g, shape):
+    """inverse of conv_form for a gradient [a, taps*b] -> Wg layout"""
+    a, b = shape[:2]
+    if len(shape) == 3:
+        return g.view(a, shape[2], b).permute(0, 2, 1)
+    return g.view(a, shape[2], shape[3], b).permute(0, 3, 1, 2)
+
+
+def phase_form(Wg, dtype):
+    a, b = Wg.shape[:2]
+    out = []
+    if Wg.dim() == 3:
+        for px in range(2):
+            w = Wg[:, :, list(KTAPS[px])]                      # [a, b, 2]
+            out.append(w.permute(1, 2, 0).reshape(b, -1).to(dtype).contiguous())
+        return out
+    for py in range(2):
+        for px in range(2):
+            w = Wg[:, :, list(KTAPS[py]), :][:, :, :, list(KTAPS[px])]   # [a, b, 2, 2]
+            out.append(w.permute(1, 2, 3, 0).reshape(b, -1).to(dtype).contiguous())
+    return out
+
+
+def full_form(Wg, dtype):
+    a, b = Wg.shape[:2]
+    if Wg.dim() == 3:
+        return Wg.permute(2, 1, 0).reshape(-1, a).to(dtype).contiguous()
+    return Wg.permute(2, 3, 1, 0).reshape(-1, a).to(dtype).contiguous()

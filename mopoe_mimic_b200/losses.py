@@ -1,0 +1,106 @@
+"""ELBO assembly with the reference's free-function contract (evaluation/losses.py:6-89,
+utils/utils.py:105-127): same names, same argument meaning, same return types.  The heavy parts
+(log-likelihood reductions, per-subset KLs) come from fused CUDA kernels; what is left here is scalar
+bookkeeping on 0-dim device tensors.
+"""
+from collections import OrderedDict
+
+import torch
+
+from .fusion import FusionFn, FusionPlan
+
+
+def calc_kl_divergence(mu0, logvar0, mu1=None, logvar1=None, norm_value=None):
+    """kl_div.calc_kl_divergence (evaluation/divergence_measures/kl_div.py:8-16), prior branch, through the
+    fusion kernel's KL reduction.  (The two-Gaussian branch is only used by the jsd path — not built.)"""
+    if mu1 is not None or logvar1 is not None:
+        raise NotImplementedError('KL between two Gaussians is only needed by the jsd path (SURVEY.md N4)')
+    from .engine import Engine
+    B, D = mu0.shape
+    plan = FusionPlan(['e0'], ['e0'], ['e0'], [['e0']], 'moe', B, D, float(norm_value) if norm_value else 1.0)
+    eng = _engine_for(mu0.device)
+    out = FusionFn.apply(plan, eng, torch.zeros(B, D, device=mu0.device), mu0, logvar0)
+    return out[5][0]
+
+
+_ENGINES = {}
+
+
+def _engine_for(device):
+    from .engine import Engine
+    key = str(device)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(device, torch.float32)
+    return _ENGINES[key]
+
+
+def calc_log_probs(exp, result, batch):
+    """losses.py:6-21: log_probs[m] = -log p(x_m | z) / batch_size ; weighted sum with exp.rec_weights."""
+    mods = exp.modalities
+    log_probs = {}
+    weighted_log_prob = 0.0
+    for m_key in mods:
+        mod = mods[m_key]
+        ba = batch[0][mod.name]
+        log_probs[mod.name] = -mod.calc_log_prob(out_dist=result['rec'][mod.name], target=ba,
+                                                 norm_value=exp.flags.batch_size)
+        weighted_log_prob += exp.rec_weights[mod.name] * log_probs[mod.name]
+    return log_probs, weighted_log_prob
+
+
+def calc_klds(exp, result):
+    """losses.py:24-31: KL(subset || N(0,I)) / batch_size for every entry of latents['subsets'].  The fused
+    inference kernel has already reduced them; a foreign result dict falls back to the standalone reduction."""
+    latents = result['latents']
+    fused = latents.get('_klds')
+    if fused is not None and list(fused.keys()) == list(latents['subsets'].keys()):
+        return OrderedDict(fused)
+    klds = {}
+    for key in latents['subsets']:
+        mu, logvar = latents['subsets'][key]
+        klds[key] = calc_kl_divergence(mu, logvar, norm_value=exp.flags.batch_size)
+    return klds
+
+
+def calc_klds_style(exp, result):
+    """losses.py:34-42 — style latents are not built (all BASELINE configs use style_dim = 0)."""
+    return {}
+
+
+def calc_style_kld(exp, klds):
+    return 0.0
+
+
+def calc_elbo(exp, modality, recs, klds):
+    """utils.calc_elbo (utils/utils.py:105-127) without style terms (factorized_representation is False)."""
+    flags = exp.flags
+    kld_content = klds['content']
+    if modality == 'joint':
+        rec_error = 0.0
+        for m_key in exp.modalities:
+            rec_error += exp.rec_weights[m_key] * recs[m_key]
+    else:
+        rec_error = 1.0 * recs[modality]
+    div = flags.beta_content * kld_content + flags.beta_style * 0.0
+    return rec_error + flags.beta * div
+
+
+def calc_poe_loss(exp, mods, group_divergence, klds, klds_style, batch_d, mm_vae, log_probs):
+    """losses.py:54-77: one unimodal forward pass per modality + the joint ELBO."""
+    klds_joint = {'content': group_divergence, 'style': {}}
+    elbos = {}
+    for m_key in mods.keys():
+        mod = mods[m_key]
+        r_mod = mm_vae({m_key: batch_d[m_key]})
+        log_prob_mod = -mod.calc_log_prob(r_mod['rec'][m_key], batch_d[m_key], exp.flags.batch_size)
+        klds_mod = {'content': klds[m_key], 'style': {m_key: 0.0}}
+        elbos[m_key] = calc_elbo(exp, m_key, {m_key: log_prob_mod}, klds_mod)
+    elbos['joint'] = calc_elbo(exp, 'joint', log_probs, klds_joint)
+    return sum(elbos.values())
+
+
+def calc_joint_elbo_loss(exp, klds_style, group_divergence, beta_style, beta_content, weighted_log_prob, beta):
+    """losses.py:80-89."""
+    kld_style = 0.0
+    kld_weighted = beta_style * kld_style + beta_content * group_divergence
+    return 1.0 * weighted_log_prob + beta * kld_weighted

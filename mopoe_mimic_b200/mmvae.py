@@ -1,0 +1,304 @@
+"""Multimodal VAE with the reference's model API (utils/BaseMMVae.py:14-231, networks/VAEtrimodalMimic.py:12-163):
+same constructor, same method names, same result-dict nesting — so run_epochs.basic_routine_epoch and the
+evaluation callers drive it unchanged.  Inference runs ONE fused CUDA kernel for all
+subsets / selection / reparameterisation / KLs instead of ~150 tiny torch ops.
+"""
+import os
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .fusion import FusionFn, FusionPlan, selection_ends, set_subsets, uniform_weights  # noqa: F401
+from .modalities import CategoricalLikelihood, LaplaceLikelihood
+from .networks import Runtime
+
+ENC_NAME = {'PA': 'encoder_pa', 'Lateral': 'encoder_lat', 'text': 'encoder_text'}
+DEC_NAME = {'PA': 'decoder_pa', 'Lateral': 'decoder_lat', 'text': 'decoder_text'}
+LHOOD_NAME = {'PA': 'lhood_pa', 'Lateral': 'lhood_lat', 'text': 'lhood_text'}
+
+
+def reweight_weights(w):
+    return w / w.sum()
+
+
+def method_of(flags):
+    if getattr(flags, 'modality_moe', False):
+        return 'moe'
+    if getattr(flags, 'modality_jsd', False):
+        return 'jsd'
+    if getattr(flags, 'modality_poe', False):
+        return 'poe'
+    if getattr(flags, 'joint_elbo', False):
+        return 'joint_elbo'
+    raise ValueError('flags select no fusion method (modality_moe / modality_poe / joint_elbo)')
+
+
+class BaseMMVae(nn.Module):
+    def __init__(self, flags, modalities, subsets):
+        super().__init__()
+        self.num_modalities = len(modalities.keys())
+        self.flags = flags
+        self.modalities = modalities
+        self.subsets = subsets
+        object.__setattr__(self, 'rt', Runtime(flags))
+        self._plans = {}
+        self.set_fusion_functions()
+
+    # ---- method selection (BaseMMVae.py:51-69) ----------------------------------------------------------------
+    def set_fusion_functions(self):
+        w = torch.tensor(list(self.flags.alpha_modalities), dtype=torch.float32)
+        self.weights = reweight_weights(w)
+        self.method = method_of(self.flags)
+        if self.method == 'jsd':
+            raise NotImplementedError('the jsd dynamic prior is outside the built scope (SURVEY.md §8 a22 / N4)')
+        if self.method == 'moe':
+            self.modality_fusion, self.fusion_condition = self.moe_fusion, self.fusion_condition_moe
+        elif self.method == 'poe':
+            self.modality_fusion, self.fusion_condition = self.poe_fusion, self.fusion_condition_poe
+        else:
+            self.modality_fusion, self.fusion_condition = self.poe_fusion, self.fusion_condition_joint
+        self.calc_joint_divergence = self.divergence_static_prior
+
+    def fusion_condition_moe(self, subset, input_batch=None):
+        return len(subset) == 1
+
+    def fusion_condition_poe(self, subset, input_batch=None):
+        return len(subset) == len(input_batch.keys())
+
+    def fusion_condition_joint(self, subset, input_batch=None):
+        return True
+
+    # ---- engine helpers -------------------------------------------------------------------------------------------
+    def _eng(self, device):
+        return self.rt.eng(device)
+
+    def _plan(self, present, B):
+        key = (tuple(present), B)
+        if key not in self._plans:
+            keys = list(self.subsets.keys())
+            members = [[m.name for m in self.subsets[k]] for k in keys]
+            self._plans[key] = FusionPlan(list(self.modalities.keys()), present, keys, members, self.method, B,
+                                          self.flags.class_dim, self.flags.batch_size)
+        return self._plans[key]
+
+    def _eps(self, B, device):
+        if self.rt.injected_eps is not None:
+            e = self.rt.injected_eps
+            assert tuple(e.shape) == (B, self.flags.class_dim)
+            return e
+        return torch.randn(B, self.flags.class_dim, device=device)
+
+    # ---- standalone fusion API (kept for callers; the hot path uses inference()) --------------------------------------
+    def _kernel_rows(self, mus, logvars, fuse_mode, prior):
+        """run the fusion kernel on m <= 4 stacked experts as one all-member subset"""
+        m, B, D = mus.shape
+        names = ['e%d' % i for i in range(m)]
+        plan = FusionPlan(names, names, ['all'], [names], 'poe' if prior else 'joint_elbo', B, D, self.flags.batch_size)
+        plan.cfg.fuse_mode = fuse_mode
+        eng = self._eng(mus.device)
+        out = FusionFn.apply(plan, eng, torch.zeros(B, D, device=mus.device), *[mus[i] for i in range(m)],
+                             *[logvars[i] for i in range(m)])
+        return out
+
+    def poe_fusion(self, mus, logvars, weights=None):
+        """Product of experts over stacked [m, B, D] (BaseMMVae.py:113-128 -> mm_div.poe)."""
+        if mus.shape[0] > 4:
+            raise NotImplementedError('standalone poe_fusion takes at most 4 experts')
+        out = self._kernel_rows(mus, logvars, 0, self.method == 'poe')
+        return [out[0][0], out[1][0]]
+
+    def moe_fusion(self, mus, logvars, weights=None):
+        """Positional mixture selection over stacked [S, B, D] (BaseMMVae.py:101-111 -> utils.py:55-77).
+        Pure row-range gathering (no arithmetic): done with device copies."""
+        if weights is None:
+            weights = self.weights
+        w = reweight_weights(torch.as_tensor(weights, dtype=torch.float32).cpu())
+        ends = selection_ends(mus.shape[1], w)
+        starts = [0] + ends[:-1]
+        mu = torch.cat([mus[k, starts[k]:ends[k], :] for k in range(w.shape[0])])
+        lv = torch.cat([logvars[k, starts[k]:ends[k], :] for k in range(w.shape[0])])
+        return [mu, lv]
+
+    def divergence_static_prior(self, mus, logvars, weights=None):
+        """sum_k w_k KL(N(mu_k, var_k) || N(0, I)) / batch_size  (BaseMMVae.py:71-85, mm_div.py:90-110)."""
+        if weights is None:
+            weights = self.weights
+        w = reweight_weights(weights.clone().float()).to(mus.device)
+        klds = []
+        for k0 in range(0, mus.shape[0], 4):        # identity "mixture" subsets -> per-row KLs from the kernel
+            m = min(4, mus.shape[0] - k0)
+            B, D = mus.shape[1:]
+            names = ['e%d' % i for i in range(m)]
+            plan = FusionPlan(names, names, names, [[n] for n in names], 'moe', B, D, self.flags.batch_size)
+            out = FusionFn.apply(plan, self._eng(mus.device), torch.zeros(B, D, device=mus.device),
+                                 *[mus[k0 + i] for i in range(m)], *[logvars[k0 + i] for i in range(m)])
+            klds.append(out[5])
+        klds = torch.cat(klds)
+        return {'joint_divergence': (w * klds).sum(dim=0), 'individual_divs': klds, 'dyn_prior': None}
+
+    # ---- inference (BaseMMVae.py:139-196) ---------------------------------------------------------------------------
+    def inference(self, input_batch, num_samples=None):
+        enc_mods = self.encode(input_batch)
+        present = [m for m in self.modalities if m in input_batch]
+        first = enc_mods[present[0]][0]
+        B = first.shape[0]
+        plan = self._plan(present, B)
+        eng = self._eng(first.device)
+        eps = self._eps(B, first.device)
+        mus_in = [enc_mods[m][0] for m in plan.mods]
+        lvs_in = [enc_mods[m][1] for m in plan.mods]
+        sub_mu, sub_lv, jmu, jlv, z, kl, nan_flag = FusionFn.apply(plan, eng, eps, *mus_in, *lvs_in)
+        latents = {'modalities': enc_mods}
+        distr_subsets = OrderedDict((k, [sub_mu[i], sub_lv[i]]) for i, k in enumerate(plan.keys))
+        st = plan.stacked
+        if st == list(range(len(plan.keys))):
+            latents['mus'], latents['logvars'] = sub_mu, sub_lv
+        else:
+            latents['mus'] = sub_mu[st[0]:st[-1] + 1] if st == list(range(st[0], st[-1] + 1)) else sub_mu[st]
+            latents['logvars'] = sub_lv[st[0]:st[-1] + 1] if st == list(range(st[0], st[-1] + 1)) else sub_lv[st]
+        latents['weights'] = plan.weights.to(first.device)
+        latents['joint'] = [jmu, jlv]
+        latents['subsets'] = distr_subsets
+        # fused by-products (private): reparameterised sample, per-subset KLs, NaN flag
+        latents['_z'] = z
+        latents['_klds'] = OrderedDict((k, kl[i]) for i, k in enumerate(plan.keys))
+        latents['_kl_stacked'] = kl[st[0]:st[-1] + 1] if st == list(range(st[0], st[-1] + 1)) else kl[st]
+        latents['_nan_flag'] = nan_flag
+        return latents
+
+    # ---- generation API (BaseMMVae.py:198-231) ----------------------------------------------------------------------
+    def generate(self, num_samples=None):
+        if num_samples is None:
+            num_samples = self.flags.batch_size
+        dev = next(self.parameters()).device
+        z_class = torch.randn(num_samples, self.flags.class_dim, device=dev)
+        random_latents = {'content': z_class, 'style': self.get_random_styles(num_samples)}
+        return self.generate_from_latents(random_latents)
+
+    def generate_from_latents(self, latents):
+        suff_stats = self.generate_sufficient_statistics_from_latents(latents)
+        return {m_key: suff_stats[m_key].mean for m_key in latents['style'].keys()}
+
+    def cond_generation(self, latent_distributions, num_samples=None):
+        if num_samples is None:
+            num_samples = self.flags.batch_size
+        style_latents = self.get_random_styles(num_samples)
+        cond_gen_samples = {}
+        for key in latent_distributions.keys():
+            mu, logvar = latent_distributions[key]
+            content_rep = reparameterize(mu=mu, logvar=logvar)
+            cond_gen_samples[key] = self.generate_from_latents({'content': content_rep, 'style': style_latents})
+        return cond_gen_samples
+
+
+def reparameterize(mu, logvar):
+    """utils.reparameterize (utils/utils.py:45-48) for callers outside the fused path (cond_generation)."""
+    std = logvar.mul(0.5).exp()
+    return torch.randn_like(std).mul(std).add(mu)
+
+
+class MMVaeMimic(BaseMMVae):
+    """Any non-empty subset of {PA, Lateral, text}; VAEtrimodalMimic is the 3-modality instance."""
+
+    def __init__(self, flags, modalities, subsets):
+        super().__init__(flags, modalities, subsets)
+        for m in modalities:                               # registration order of VAEtrimodalMimic.__init__:15-20
+            setattr(self, ENC_NAME[m], modalities[m].encoder)
+        for m in modalities:
+            setattr(self, DEC_NAME[m], modalities[m].decoder)
+        for m in modalities:
+            setattr(self, LHOOD_NAME[m], modalities[m].likelihood)
+        for m in modalities:
+            for net, nm in ((modalities[m].encoder, ENC_NAME[m]), (modalities[m].decoder, DEC_NAME[m])):
+                object.__setattr__(net, 'rt', self.rt)
+                object.__setattr__(net, 'prefix', nm)
+        self.to(flags.device)
+
+    def encode(self, input_batch):
+        latents = {}
+        for m in self.modalities:
+            if m in input_batch:
+                L.require_cuda(input_batch[m])
+                latents[m] = list(getattr(self, ENC_NAME[m])(input_batch[m])[:2])
+            else:
+                latents[m + '_style'] = [None, None]
+                latents[m] = [None, None]
+        return latents
+
+    def _decode(self, m_key, z):
+        eng = self._eng(z.device)
+        dec = getattr(self, DEC_NAME[m_key])
+        if m_key == 'text':
+            return CategoricalLikelihood(scores=dec(None, z)[0], eng=eng)
+        loc, scale = dec(None, z)
+        return LaplaceLikelihood(loc, scale, eng=eng)
+
+    def forward(self, input_batch):
+        """VAEtrimodalMimic.forward:31-62; absent modalities are skipped in the decode loop (the intended
+        behaviour for calc_poe_loss — the shipped reference raises KeyError there)."""
+        if self.rt.schedule:
+            self.rt.injected_masks, self.rt.injected_eps = self.rt.schedule.pop(0)
+        latents = self.inference(input_batch)
+        results = {'latents': latents}
+        w = reweight_weights(latents['weights'])
+        klds = latents['_kl_stacked']
+        results['joint_divergence'] = (w * klds).sum(dim=0)
+        results['individual_divs'] = klds
+        results['dyn_prior'] = None
+        results['group_distr'] = latents['joint']
+        class_embeddings = latents['_z']
+        results_rec = {}
+        for m_key in self.modalities:
+            if m_key in input_batch and input_batch[m_key] is not None:
+                results_rec[m_key] = self._decode(m_key, class_embeddings)
+        results['rec'] = results_rec
+        return results
+
+    def get_random_styles(self, num_samples):
+        return {m: None for m in self.modalities}
+
+    def get_random_style_dists(self, num_samples):
+        dev = next(self.parameters()).device
+        return {m: [torch.zeros(num_samples, 0, device=dev), torch.zeros(num_samples, 0, device=dev)]
+                for m in self.modalities}
+
+    def generate_sufficient_statistics_from_latents(self, latents):
+        content = latents['content']
+        return {m: self._decode(m, content) for m in self.modalities}
+
+    def save_networks(self):
+        names = {'PA': ('encoder_save_m1', 'decoder_save_m1'), 'Lateral': ('encoder_save_m2', 'decoder_save_m2'),
+                 'text': ('encoder_save_m3', 'decoder_save_m3')}
+        for m in self.modalities:
+            e, d = names[m]
+            torch.save(getattr(self, ENC_NAME[m]).state_dict(), os.path.join(self.flags.dir_checkpoints, getattr(self.flags, e)))
+            torch.save(getattr(self, DEC_NAME[m]).state_dict(), os.path.join(self.flags.dir_checkpoints, getattr(self.flags, d)))
+
+    # ---- flat parameter / gradient storage (one Adam launch, one all-reduce buffer) ---------------------------------
+    def flatten_(self):
+        params = [p for p in self.parameters()]
+        total = sum(p.numel() for p in params)
+        total_pad = (total + 3) // 4 * 4
+        dev = params[0].device
+        flat = torch.zeros(total_pad, dtype=torch.float32, device=dev)
+        flat_g = torch.zeros(total_pad, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            n = p.numel()
+            flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = flat[off:off + n].view(p.shape)
+            p.grad = flat_g[off:off + n].view(p.shape)
+            off += n
+        object.__setattr__(self, 'flat_params', flat)
+        object.__setattr__(self, 'flat_grads', flat_g)
+        object.__setattr__(self, 'flat_numel', total)
+        return flat, flat_g
+
+
+class VAEtrimodalMimic(MMVaeMimic):
+    def __init__(self, flags, modalities, subsets):
+        if list(modalities.keys()) != ['PA', 'Lateral', 'text']:
+            raise ValueError('VAEtrimodalMimic needs modalities PA, Lateral, text (in this order)')
+        super().__init__(flags, modalities, subsets)

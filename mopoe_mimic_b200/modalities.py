@@ -1,0 +1,129 @@
+"""Modality descriptors and likelihood objects (reference: modalities/Modality.py:15-47, MimicPA.py:7-17,
+MimicLateral.py:7-17, MimicText.py:12-40, modalities/utils.py:4-15).
+
+The likelihood objects behave like the torch.distributions the reference builds (`.log_prob(target)`,
+`.mean`, `.loc` / `.logits`) for the evaluation callers and add the fused
+`log_prob_sum(target)` path that Modality.calc_log_prob uses on the hot path.
+"""
+import math
+
+import torch
+
+from .blocks import CategoricalLogProbSumFn, LaplaceLogProbSumFn, log_softmax_rows
+
+
+class LaplaceLikelihood:
+    """dist.Laplace(loc, scale) stand-in.  scale is the constant 0.75 tensor the decoder returns."""
+
+    def __init__(self, loc, scale, eng=None):
+        self.loc, self.scale, self._eng = loc, scale, eng
+        self._scale_f = float(scale) if not torch.is_tensor(scale) or scale.numel() == 1 else None
+
+    @property
+    def mean(self):
+        return self.loc
+
+    def log_prob(self, value):
+        # elementwise (evaluation callers only): -log(2b) - |x - loc| / b
+        return -torch.log(2 * self.scale) - torch.abs(value - self.loc) / self.scale
+
+    def log_prob_sum(self, value):
+        if self._eng is None or self._scale_f is None:
+            return self.log_prob(value).sum()
+        return LaplaceLogProbSumFn.apply(self.loc, value, self._scale_f, self._eng)
+
+
+class CategoricalLikelihood:
+    """dist.OneHotCategorical(logits=...) stand-in built from the decoder's PRE-softmax scores [B, L, V]."""
+
+    def __init__(self, logits=None, scores=None, eng=None):
+        self._scores = scores if scores is not None else logits
+        self._eng = eng
+        self._logits = None
+
+    @property
+    def logits(self):
+        if self._logits is None:
+            if self._eng is not None:
+                self._logits = log_softmax_rows(self._scores, self._eng)
+            else:
+                self._logits = self._scores - self._scores.logsumexp(-1, keepdim=True)
+        return self._logits
+
+    @property
+    def probs(self):
+        return self.logits.exp()
+
+    @property
+    def mean(self):
+        return self.probs
+
+    def log_prob(self, value):
+        idx = value.max(-1)[1]
+        return self.logits.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
+
+    def log_prob_sum(self, value):
+        if self._eng is None:
+            return self.log_prob(value).sum()
+        return CategoricalLogProbSumFn.apply(self._scores, value, self._eng)
+
+
+def get_likelihood(name):
+    """modalities/utils.py:4-15 (laplace / categorical are the ones the MIMIC modalities use)."""
+    if name == 'laplace':
+        return LaplaceLikelihood
+    if name == 'categorical':
+        return CategoricalLikelihood
+    raise NotImplementedError('likelihood %r is not used by the MIMIC modalities' % name)
+
+
+class Modality:
+    def calc_log_prob(self, out_dist, target, norm_value):
+        """log P(target | out_dist) / norm_value  (Modality.py:25-30); fused reduction when available."""
+        if hasattr(out_dist, 'log_prob_sum'):
+            log_prob = out_dist.log_prob_sum(target)
+        else:
+            log_prob = out_dist.log_prob(target).sum()
+        return log_prob / norm_value
+
+
+class _MimicImg(Modality):
+    def __init__(self, name, enc, dec, args):
+        self.name = name
+        self.likelihood_name = 'laplace'
+        self.data_size = torch.Size((1, args.img_size, args.img_size))
+        self.gen_quality_eval = True
+        self.file_suffix = '.png'
+        self.encoder = enc
+        self.decoder = dec
+        self.likelihood = get_likelihood(self.likelihood_name)
+
+
+class MimicPA(_MimicImg):
+    def __init__(self, enc, dec, args):
+        super().__init__('PA', enc, dec, args)
+
+
+class MimicLateral(_MimicImg):
+    def __init__(self, enc, dec, args):
+        super().__init__('Lateral', enc, dec, args)
+
+
+class MimicText(Modality):
+    def __init__(self, enc, dec, len_sequence, plotImgSize=None, font=None, args=None):
+        self.name = 'text'
+        self.args = args
+        self.likelihood_name = 'categorical'
+        self.len_sequence = len_sequence
+        if args.text_encoding == 'char':
+            self.alphabet = getattr(args, 'alphabet', None)
+            self.data_size = torch.Size((args.num_features, len_sequence))
+        else:
+            raise NotImplementedError('word encoding is outside the built scope (SURVEY.md N4)')
+        self.plot_img_size = plotImgSize
+        self.font = font
+        self.gen_quality_eval = False
+        self.file_suffix = '.txt'
+        self.encoder = enc
+        self.decoder = dec
+        self.likelihood = get_likelihood(self.likelihood_name)

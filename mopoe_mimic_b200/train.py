@@ -1,0 +1,151 @@
+"""The training step: run_epochs.basic_routine_epoch (run_epochs.py:52-96) and the step tail of
+run_epochs.train (:128-142) — forward, ELBO, backward, (all-reduce), Adam — plus the experiment
+object the reference passes around (only the fields the hot path reads).
+"""
+import ctypes as C
+from collections import OrderedDict
+from types import SimpleNamespace
+
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from .fusion import set_subsets
+from .losses import calc_joint_elbo_loss, calc_klds, calc_log_probs, calc_poe_loss
+from .mmvae import MMVaeMimic, VAEtrimodalMimic
+from .modalities import MimicLateral, MimicPA, MimicText
+from .networks import DecoderImg, DecoderText, EncoderImg, EncoderText
+
+
+class NaNInLatent(Exception):
+    """utils/exceptions.py:1-2"""
+
+
+class CudaOutOfMemory(Exception):
+    """utils/exceptions.py:4-5"""
+
+
+def default_flags(**kw):
+    """The ~30 flag fields the hot path reads, with the reference's defaults (utils/flags.py, BaseFlags.py)."""
+    f = dict(device=torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu'),
+             batch_size=16, class_dim=128, img_size=128, image_channels=1, DIM_img=128, DIM_text=128,
+             text_encoding='char', len_sequence=1024, num_features=71, alphabet='x' * 71,
+             feature_extractor_img='resnet', factorized_representation=False,
+             style_pa_dim=0, style_lat_dim=0, style_text_dim=0,
+             modality_moe=False, modality_jsd=False, modality_poe=False, joint_elbo=True, poe_unimodal_elbos=True,
+             alpha_modalities=[0.25, 0.25, 0.25, 0.25], beta=5.0, beta_style=1.0, beta_content=1.0,
+             rec_weight_m1=0.33, rec_weight_m2=0.33, rec_weight_m3=0.33,
+             initial_learning_rate=1e-3, beta_1=0.9, beta_2=0.999,
+             dataset='testing', distributed=False, world_size=1, compute_dtype='bf16',
+             mods=('PA', 'Lateral', 'text'))
+    f.update(kw)
+    m = f.pop('method', None)
+    if m is not None:
+        f['modality_moe'], f['modality_poe'], f['joint_elbo'] = m == 'moe', m == 'poe', m == 'joint_elbo'
+    return SimpleNamespace(**f)
+
+
+class Experiment:
+    """Stand-in for MimicExperiment (utils/experiment.py:40-72) restricted to the hot path:
+    .flags .modalities .subsets .mm_vae .optimizer .rec_weights .style_weights"""
+
+    def __init__(self, flags):
+        self.flags = flags
+        self.modalities = self.set_modalities()
+        self.subsets = set_subsets(self.modalities)
+        self.rec_weights = {'PA': flags.rec_weight_m1, 'Lateral': flags.rec_weight_m2, 'text': flags.rec_weight_m3}
+        self.style_weights = {'PA': 1.0, 'Lateral': 1.0, 'text': 1.0}
+        self.mm_vae = self.set_model()
+        self.optimizer = None
+
+    def set_modalities(self):
+        """experiment.py:80-92 — dict order PA, Lateral, text"""
+        fl = self.flags
+        mods = OrderedDict()
+        for m in getattr(fl, 'mods', ('PA', 'Lateral', 'text')):
+            if m == 'PA':
+                mods[m] = MimicPA(EncoderImg(fl, 0), DecoderImg(fl, 0), fl)
+            elif m == 'Lateral':
+                mods[m] = MimicLateral(EncoderImg(fl, 0), DecoderImg(fl, 0), fl)
+            elif m == 'text':
+                mods[m] = MimicText(EncoderText(fl, 0), DecoderText(fl, 0), fl.len_sequence, None, None, fl)
+            else:
+                raise ValueError(m)
+        return mods
+
+    def set_model(self):
+        if list(self.modalities.keys()) == ['PA', 'Lateral', 'text']:
+            return VAEtrimodalMimic(self.flags, self.modalities, self.subsets)
+        return MMVaeMimic(self.flags, self.modalities, self.subsets)
+
+    def set_optimizer(self):
+        """experiment.py:171-178: Adam(lr, betas), eps 1e-8, no weight decay — as ONE fused launch over the flat buffers."""
+        self.optimizer = FlatAdam(self.mm_vae, self.flags.initial_learning_rate, (self.flags.beta_1, self.flags.beta_2))
+        return self.optimizer
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics over the model's flat parameter / gradient buffers (mopoe_adam_flat)."""
+
+    def __init__(self, model, lr, betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        if not hasattr(model, 'flat_params'):
+            model.flatten_()
+        self.p, self.g = model.flat_params, model.flat_grads
+        self.m = torch.zeros_like(self.p)
+        self.v = torch.zeros_like(self.p)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
+        self.grad_scale = 1.0
+
+    def zero_grad(self, set_to_none=False):
+        self.g.zero_()
+
+    def step(self):
+        self.step_count += 1
+        L.call('mopoe_adam_flat', L.ptr(self.p), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.p.numel(),
+               float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count,
+               float(self.grad_scale), L.stream_ptr())
+
+
+def basic_routine_epoch(exp, batch):
+    """run_epochs.basic_routine_epoch:52-96.  One device->host read (the NaN flag) instead of nine."""
+    flags = exp.flags
+    mm_vae = exp.mm_vae
+    batch_d = batch[0]
+    for m_key in batch_d.keys():
+        batch_d[m_key] = batch_d[m_key].to(flags.device, non_blocking=True)
+    results = mm_vae(batch_d)
+    if flags.dataset != 'testing' and int(results['latents']['_nan_flag'].item()) != 0:
+        raise NaNInLatent('The latent representations contain NaNs')
+    log_probs, weighted_log_prob = calc_log_probs(exp, results, batch)
+    group_divergence = results['joint_divergence']
+    klds = calc_klds(exp, results)
+    if flags.modality_jsd or flags.modality_moe or flags.joint_elbo:
+        total_loss = calc_joint_elbo_loss(exp, None, group_divergence, flags.beta_style, flags.beta_content,
+                                          weighted_log_prob, flags.beta)
+    elif flags.modality_poe:
+        total_loss = calc_poe_loss(exp, exp.modalities, group_divergence, klds, None, batch_d, mm_vae, log_probs)
+    else:
+        raise ValueError('no fusion method selected')
+    return {'results': results, 'log_probs': log_probs, 'total_loss': total_loss, 'klds': klds}
+
+
+def train_step(exp, batch, allreduce=None):
+    """run_epochs.train:118-131 for one batch: forward + loss, zero_grad, backward, (DP all-reduce), Adam."""
+    out = basic_routine_epoch(exp, batch)
+    exp.optimizer.zero_grad()
+    out['total_loss'].backward()
+    if allreduce is not None:
+        allreduce(exp.mm_vae.flat_grads)
+    exp.optimizer.step()
+    return out
+
+
+def packed_stats(out):
+    """One device vector with every scalar the reference logs per step (run_epochs.py:133-142): total loss,
+    joint divergence, per-subset KLs, per-modality log-probs -> a single D2H copy instead of ~18 .item() syncs."""
+    vals = [out['total_loss'].detach().reshape(1), out['results']['joint_divergence'].detach().reshape(1)]
+    vals += [v.detach().reshape(1) for v in out['klds'].values()]
+    vals += [v.detach().reshape(1) for v in out['log_probs'].values()]
+    return torch.cat([v.float() for v in vals])

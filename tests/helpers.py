@@ -1,0 +1,106 @@
+"""Shared harness for the GPU parity tests: build the product model from the oracle's deterministic
+state, inject the oracle's dropout masks / eps (converted to the product's layouts), run one step on
+both and compare."""
+import os
+from collections import OrderedDict
+
+import torch
+
+from oracle import mopoe_oracle as O
+
+
+def oracle_flags(**kw):
+    fl = O.default_flags(**kw)
+    if 'rec_weights' not in kw:
+        fl.rec_weights = {m: 0.33 for m in fl.mods}
+    return fl
+
+
+def product_flags(ofl, compute_dtype, device='cuda'):
+    import mopoe_mimic_b200 as P
+    return P.default_flags(device=torch.device(device), batch_size=ofl.batch_size, class_dim=ofl.class_dim,
+                           img_size=ofl.img_size, DIM_img=ofl.DIM_img, DIM_text=ofl.DIM_text,
+                           len_sequence=ofl.len_sequence, num_features=ofl.num_features, method=ofl.method,
+                           mods=tuple(ofl.mods), beta=ofl.beta, compute_dtype=compute_dtype)
+
+
+def masks_to_product(masks, device):
+    """oracle keep-masks (float {0,1}; 2-D [B,C,1,1], 1-D [B,C,L]) -> uint8 [B,C] / [B,L,C] on device"""
+    out = {}
+    for k, m in masks.items():
+        if m.dim() == 4:
+            out[k] = m.reshape(m.shape[0], m.shape[1]).to(torch.uint8).contiguous().to(device)
+        else:
+            out[k] = m.permute(0, 2, 1).to(torch.uint8).contiguous().to(device)
+    return out
+
+
+def make_case(kw, actual_batch=None, dtype=torch.float32, seeds=(0, 1, 2)):
+    ofl = oracle_flags(**kw)
+    B = actual_batch or ofl.batch_size
+    state = O.make_state(ofl, seeds[0], dtype)
+    batch = O.make_batch(ofl, seeds[1], dtype, B)
+    noise = [O.make_noise(ofl, seeds[2] + i, dtype, B) for i in range(1 + len(ofl.mods))]
+    return ofl, state, batch, noise
+
+
+def run_oracle(ofl, state, batch, noise):
+    st = OrderedDict((k, v.clone()) for k, v in state.items())
+    uni = {m: noise[1 + i] for i, m in enumerate(ofl.mods)}
+    return O.step_with_grads(st, batch, ofl, noise[0][0], noise[0][1], uni_masks=uni)
+
+
+def run_product(ofl, state, batch, noise, compute_dtype):
+    import mopoe_mimic_b200 as P
+    fl = product_flags(ofl, compute_dtype)
+    exp = P.Experiment(fl)
+    vae = exp.mm_vae
+    vae.load_state_dict({k: v.float() for k, v in state.items()})
+    exp.set_optimizer()        # flattens params/grads
+    vae.train()
+    dev = fl.device
+    vae.rt.schedule = [(masks_to_product(m, dev), e.float().to(dev)) for m, e in noise]
+    b = OrderedDict((k, v.float().to(dev)) for k, v in batch.items())
+    out = P.basic_routine_epoch(exp, (b, None))
+    exp.optimizer.zero_grad()
+    out['total_loss'].backward()
+    torch.cuda.synchronize()
+    grads = OrderedDict((k, p.grad.detach().cpu()) for k, p in vae.named_parameters())
+    return exp, out, grads
+
+
+def rel_err(a, b, floor=0.0):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + floor + 1e-300))
+
+
+def compare_step(orc, out, grads, state_after=None):
+    """returns dict of relative errors (max-abs / max-abs) per quantity"""
+    errs = OrderedDict()
+    errs['total_loss'] = rel_err(out['total_loss'], orc['total_loss'])
+    errs['joint_div'] = rel_err(out['results']['joint_divergence'], orc['results']['joint_divergence'])
+    for k, v in orc['klds'].items():
+        errs['kld.' + k] = rel_err(out['klds'][k], v)
+    for k, v in orc['log_probs'].items():
+        errs['logp.' + k] = rel_err(out['log_probs'][k], v)
+    olat, plat = orc['results']['latents'], out['results']['latents']
+    for m, (mu, lv) in olat['modalities'].items():
+        errs['enc_mu.' + m] = rel_err(plat['modalities'][m][0], mu)
+        errs['enc_lv.' + m] = rel_err(plat['modalities'][m][1], lv)
+    for k, (mu, lv) in olat['subsets'].items():
+        errs['sub_mu.' + k] = rel_err(plat['subsets'][k][0], mu)
+        errs['sub_lv.' + k] = rel_err(plat['subsets'][k][1], lv)
+    errs['joint_mu'] = rel_err(plat['joint'][0], olat['joint'][0])
+    errs['z'] = rel_err(plat['_z'], orc['results']['z'])
+    for m, r in orc['results']['rec'].items():
+        pr = out['results']['rec'][m]
+        errs['rec.' + m] = rel_err(pr.loc if m != 'text' else pr.logits, r)
+    gscale = max(float(g.abs().max()) for g in orc['grads'].values())
+    worst = (0.0, None)
+    for k, g in orc['grads'].items():
+        e = rel_err(grads[k], g, floor=1e-4 * gscale)
+        errs['grad.' + k] = e
+        if e > worst[0]:
+            worst = (e, k)
+    errs['_worst_grad'] = worst
+    return errs
