@@ -279,18 +279,19 @@ class MMVaeMimic(BaseMMVae):
     # ---- flat parameter / gradient storage (one Adam launch, one all-reduce buffer) ---------------------------------
     def flatten_(self):
         params = [p for p in self.parameters()]
-        total = sum(p.numel() for p in params)
-        total_pad = (total + 3) // 4 * 4
-        dev = params[0].device
-        flat = torch.zeros(total_pad, dtype=torch.float32, device=dev)
-        flat_g = torch.zeros(total_pad, dtype=torch.float32, device=dev)
-        off = 0
+        ALIGN = 64                      # elements: every tensor starts 256-B aligned (kernels use 16-B vector loads)
+        offs, total = [], 0
         for p in params:
+            offs.append(total)
+            total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        dev = params[0].device
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, off in zip(params, offs):
             n = p.numel()
             flat[off:off + n].copy_(p.data.reshape(-1))
             p.data = flat[off:off + n].view(p.shape)
             p.grad = flat_g[off:off + n].view(p.shape)
-            off += n
         object.__setattr__(self, 'flat_params', flat)
         object.__setattr__(self, 'flat_grads', flat_g)
         object.__setattr__(self, 'flat_numel', total)
