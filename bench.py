@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py — train samples/sec of the MoPoE training step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the CPU oracle port of the reference step on the host cores
+
+One "step" = forward (3 encoders, fused MoPoE, 3 decoders, likelihoods) + ELBO + backward + gradient all-reduce
+(N > 1) + Adam on a synthetic batch: configs[1] of BASELINE.json (PA+Lateral+text, 128 px, 1024x71 char text,
+class_dim 128, per-GPU batch 256, bf16 storage / fp32 accumulation).  Weak scaling: per-GPU batch is fixed.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_SAMPLE_TRAIN = 52.09     # 3 x 17.36 GFLOP fwd (2 x 8.681 GMAC) at 128 px tri-modal
+WORKLOAD = 'MoPoE PA+Lateral+text 128px char1024x71 class_dim128 joint_elbo'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=256, help='per-GPU batch')
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--cpu-batch', type=int, default=16)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-kernels', action='store_true', help='print per-op-class device time of one step')
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.15)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 7 and r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        mx = max((int(r[1]) for r in self.rows if len(r) >= 7 and r[1].isdigit()), default=None)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def cpu_reference(args, steps, warmup):
+    """The reference's CPU path: its algorithm restated in oracle/ (pure torch CPU ops, same call sites), full
+    step = forward + ELBO + backward + Adam, fp32, all host threads, batch `cpu_batch` (a bounded sample of the
+    same workload)."""
+    import torch
+    from oracle import mopoe_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fl = O.default_flags(batch_size=args.cpu_batch)
+    state = O.make_state(fl, 0, torch.float32)
+    batch = O.make_batch(fl, 1, torch.float32)
+    masks, eps = O.make_noise(fl, 2, torch.float32)
+    params = {k: v for k, v in state.items() if v.is_floating_point() and 'running_' not in k}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v = {k: torch.zeros_like(p) for k, p in params.items()}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.step_with_grads(state, batch, fl, masks, eps)
+        with torch.no_grad():
+            O.adam_step(params, out['grads'], m, v, it + 1)
+            state.update(out['results']['bn_updates'])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return {'value': args.cpu_batch / sec, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d timed steps (after %d warm-up) of batch %d, fp32, torch CPU ops, %.2f s/step'
+                      % (steps, warmup, args.cpu_batch, sec)}, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warmup = max(1, min(args.warmup, 1))
+    cb, sec = cpu_reference(args, steps, warmup)
+    line = {'metric': 'train samples/sec (3-modality MoPoE, 128px)', 'value': cb['value'], 'unit': 'samples/s',
+            'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': WORKLOAD, 'per_gpu_batch': args.cpu_batch, 'note': 'CPU oracle port of the reference step'},
+            'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import mopoe_mimic_b200 as P
+    from mopoe_mimic_b200 import _lib as L
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.batch
+    fl = P.default_flags(device=dev, batch_size=B, compute_dtype=args.dtype, distributed=world > 1, world_size=world)
+    torch.manual_seed(0)
+    exp = P.Experiment(fl)
+    exp.set_optimizer()
+    vae = exp.mm_vae
+    vae.train()
+    if world > 1:
+        dist.broadcast(vae.flat_params, 0)
+        exp.optimizer.grad_scale = 1.0 / world
+    # synthetic inputs of the reference's shapes (dataio/MimicDataset.py:414-428), true one-hot text
+    g = torch.Generator(device='cpu').manual_seed(1 + rank)
+    host = {'PA': torch.rand(B, 1, 128, 128, generator=g).pin_memory(),
+            'Lateral': torch.rand(B, 1, 128, 128, generator=g).pin_memory(),
+            'text': torch.nn.functional.one_hot(torch.randint(0, 71, (B, 1024), generator=g), 71).float().pin_memory()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def allreduce(flat_g):
+        dist.all_reduce(flat_g)
+
+    def step_resident():
+        return P.train_step(exp, (dict(resident), None), allreduce if world > 1 else None)
+
+    stats_host = torch.empty(12, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        out = P.train_step(exp, (b, None), allreduce if world > 1 else None)
+        st = P.packed_stats(out)
+        stats_host[:st.numel()].copy_(st, non_blocking=True)
+        return st.numel() * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.LAUNCHES = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.LAUNCHES
+    # end-to-end: pinned host inputs -> device each step, packed stats back
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    d2h = 0
+    for _ in range(args.steps):
+        d2h = step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # roofline of the dominant kernel family (implicit-GEMM convs): one instrumented step, CUDA events per launch
+    eng = vae.rt.engine
+    eng.profile = []
+    step_resident()
+    torch.cuda.synchronize()
+    prof, eng.profile = eng.profile, None
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+        peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback'
+        gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
+        gemm_flop = sum(f for _, _, f, _ in prof)
+        by_kind = {}
+        for a, b, f, kind in prof:
+            d = by_kind.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += a.elapsed_time(b)
+            d[1] += f
+            d[2] += 1
+        achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        value = world * B * args.steps / (ms * 1e-3)
+        line = {'metric': 'train samples/sec (3-modality MoPoE, 128px)', 'value': value, 'unit': 'samples/s',
+                'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
+                'data': 'synthetic',
+                'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': B * world,
+                           'parallelism': 'dp%d' % world, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
+                'clocks': sampler.summary(),
+                'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s',
+                        'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h},
+                'gpu_launches': launches,
+                'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                             'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                             'kernel': 'implicit-GEMM conv family (fprop+dgrad+wgrad), %d launches/step' % len(prof),
+                             'gemm_ms_per_step': gemm_ms, 'step_tensor_frac': value / world * GFLOP_PER_SAMPLE_TRAIN / 1e3 / peak_tf,
+                             'by_kind': {k: {'ms': v[0], 'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else 0.0, 'launches': v[2]}
+                                         for k, v in by_kind.items()}}}
+        if not args.no_cpu_baseline:
+            cb, _ = cpu_reference(args, 2, 1)
+            line['cpu_baseline'] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

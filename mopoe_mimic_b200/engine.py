@@ -74,6 +74,7 @@ class Engine:
         self._ws64 = None
         self._wsf = None
         self.rng_offset = 0
+        self.profile = None      # list of (start_event, end_event, flops, kind) when bench.py instruments a step
 
     # ---- scratch ------------------------------------------------------------------------------------
     def ws64(self, n):
@@ -156,9 +157,21 @@ class Engine:
         return m
 
     # ---- implicit-GEMM problem builders -------------------------------------------------------------------
+    def _timed(self, kind, flops, fn):
+        if self.profile is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        self.profile.append((a, b, flops, kind))
+        return r
+
     def _gemm(self, win, wp, bias, rows):
         assert wp.is_contiguous() and wp.dtype == self._win_dtype(win)
-        L.call('mopoe_conv_gemm', C.byref(win), L.ptr(wp), L.ptr(bias), C.byref(rows), self.impl, L.stream_ptr())
+        flops = 2.0 * win.E0 * win.E1 * win.E2 * rows.N * win.R * win.KW
+        self._timed('fprop/dgrad', flops, lambda: L.call('mopoe_conv_gemm', C.byref(win), L.ptr(wp), L.ptr(bias),
+                                                         C.byref(rows), self.impl, L.stream_ptr()))
 
     @staticmethod
     def _win_dtype(win):
@@ -168,8 +181,9 @@ class Engine:
         out = self.f32(N, K)
         nbytes = L.load().mopoe_conv_wgrad_ws(C.byref(win), C.byref(rows), self.impl)
         ws = self.wsf(nbytes) if nbytes else None
-        L.call('mopoe_conv_wgrad', C.byref(win), C.byref(rows), L.ptr(out), 0, L.ptr(ws), nbytes, self.impl,
-               L.stream_ptr())
+        flops = 2.0 * win.E0 * win.E1 * win.E2 * N * K
+        self._timed('wgrad', flops, lambda: L.call('mopoe_conv_wgrad', C.byref(win), C.byref(rows), L.ptr(out), 0,
+                                                   L.ptr(ws), nbytes, self.impl, L.stream_ptr()))
         return out
 
     @staticmethod
