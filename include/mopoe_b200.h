@@ -65,6 +65,8 @@ const char* mopoe_last_error(void);
 int mopoe_version(void);
 /* 1 when the tcgen05/TMA kernels are usable on the current device (cc 10.x + driver entry point found) */
 int mopoe_tc_available(void);
+/* 1 when the tcgen05 weight-gradient kernel is compiled in */
+int mopoe_tc_wgrad_built(void);
 
 /* ---- implicit-GEMM convolution family -------------------------------------------------------------
  * D[m, n] = sum_{r,k} A[m,r,k] * Wp[n, r*KW + k] + bias[n]

@@ -48,6 +48,7 @@ SIGNATURES = {
     'mopoe_last_error': (C.c_char_p, []),
     'mopoe_version': (_I, []),
     'mopoe_tc_available': (_I, []),
+    'mopoe_tc_wgrad_built': (_I, []),
     'mopoe_conv_gemm': (_I, [_W, _P, _P, _R, _I, _P]),
     'mopoe_conv_wgrad_ws': (_S, [_W, _R, _I]),
     'mopoe_conv_wgrad': (_I, [_W, _R, _P, _I, _P, _S, _I, _P]),

@@ -234,6 +234,10 @@ __global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restri
     out[i] = (accumulate ? out[i] : 0.f) + s;
 }
 
+void mopoe_split_reduce_launch(const float* ws, int Z, long long n, float* out, int accumulate, cudaStream_t st) {
+    split_reduce_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(ws, Z, n, out, accumulate);
+}
+
 static int wgrad_splits(long long M, int N, int K) {
     long long tiles = ceil_div64(N, BN) * ceil_div64(K, BM);
     long long z = ceil_div64(148 * 4, tiles);

@@ -1,8 +1,520 @@
-// gemm_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM kernels (placeholder: not yet eligible for any shape)
+// gemm_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM convolution kernels (bf16 operands, fp32 accumulate).
+//
+// fprop / dgrad  (conv_gemm_tc_kernel):   D[m, n] = sum_{r,k} A[m, r, k] * Wp[n, r*KW + k] + bias[n]
+//   * A is never materialised: a 5-D TMA tensor map (k, m0, m1, r, m2) with OVERLAPPING strides describes
+//     the conv windows of the bordered channels-last activation directly (a 4-tap row of a k4/s2 conv is
+//     4C contiguous elements); one box = 128 output pixels x 64 window elements, landed in shared memory
+//     in the 128-byte-swizzled K-major layout tcgen05.mma consumes.  No im2col buffer, no padding logic:
+//     the zero border lives in the tensor, tile overhang is TMA zero fill.
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, accumulator
+//     128 x BN fp32 in TMEM), warps 2-5 = epilogue (tcgen05.ld -> +bias -> bf16/fp32 -> global rows).
+//   * smem ring of 4-8 stages (A 16 KB + B BN*128 B each), mbarrier full/empty pairs, tcgen05.commit
+//     releases a stage as soon as the MMAs reading it retire.
+//
+// wgrad (conv_wgrad_tc_kernel):   dWp[n, r*KW + j] = sum_m dY[m, n] * A[m, r, j]
+//   * the reduction runs over pixels, so both operands are MN-major: the same 5-D window map (box 64 window
+//     elements x 64 pixels) and a 4-D row map of dY, UMMA descriptors with the MN-major bit set;
+//   * split over pixel ranges across CTAs, fp32 partial tiles to a workspace, fixed-order reduction
+//     (deterministic — no atomics).
 #include "common.cuh"
-extern "C" int mopoe_tc_available(void) { return 0; }
-int mopoe_tc_fwd_eligible(const mopoe_window_t*, const mopoe_rows_t*) { return 0; }
-int mopoe_conv_gemm_tc(const mopoe_window_t*, const void*, const float*, const mopoe_rows_t*, void*) { MOPOE_FAIL("tc: not built"); }
-int mopoe_tc_wgrad_eligible(const mopoe_window_t*, const mopoe_rows_t*) { return 0; }
-size_t mopoe_conv_wgrad_ws_tc(const mopoe_window_t*, const mopoe_rows_t*) { return 0; }
-int mopoe_conv_wgrad_tc(const mopoe_window_t*, const mopoe_rows_t*, float*, int, void*, size_t, void*) { MOPOE_FAIL("tc: not built"); }
+#include "tc_common.cuh"
+
+using namespace tc;
+
+// ---- driver entry point for tensor-map encoding (no libcuda link) ------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static int g_tc_state = -1;   // -1 unknown, 0 unavailable, 1 ok
+
+static int tc_init() {
+    if (g_tc_state >= 0) return g_tc_state;
+    g_tc_state = 0;
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+        return 0;
+    g_encode = (PFN_encodeTiled)fn;
+    g_tc_state = 1;
+    return 1;
+}
+extern "C" int mopoe_tc_available(void) { return tc_init(); }
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                      const uint32_t* box, const char* what) {
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+    }
+    for (int i = 1; i < rank; ++i) {
+        uint64_t s = strides_elems[i] * 2;           // bf16 bytes
+        if (dims[i] == 1 && s == 0) s = 16;          // a singleton dim never advances; any legal stride will do
+        if (s % 16 != 0) MOPOE_FAIL("%s: stride[%d]=%llu bytes not a multiple of 16", what, i, (unsigned long long)s);
+        gstr[i - 1] = s;
+    }
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        MOPOE_FAIL("%s: cuTensorMapEncodeTiled failed (CUresult %d) dims=[%llu,%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u,%u]", what,
+                   (int)r, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                   (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                   (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+                   rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+    }
+    return 0;
+}
+
+static int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+// split a `rows`-row tile over (m0, m1, m2): BX * BY * NB == rows
+static void tile_split(int E0, int E1, int rows, int& BX, int& BY, int& NB) {
+    BX = E0 >= rows ? rows : pow2_ceil(E0);
+    int rem = rows / BX;
+    BY = rem < pow2_ceil(E1) ? rem : pow2_ceil(E1);
+    NB = rem / BY;
+}
+
+constexpr int TC_THREADS = 192;
+constexpr int SMEM_LIMIT = 232448;   // 227 KB
+constexpr int SMEM_HEADER = 1024;    // barriers + tmem pointer + bias staging lives after the stages
+
+struct TcFwdParams {
+    int E0, E1, E2, BX, BY, NB, T0, T1, T2;
+    int R, KW, N, BN, stages, tmem_cols;
+    long long d_off, s0, s1, s2;
+    void* d;
+    int d_is_bf16;
+    const float* bias;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B atoms need 1024-B alignment
+    uint8_t* const gen = smem_raw + (base - raw);
+    const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)p.BN * 128;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t hdr = base + (uint32_t)p.stages * stage_bytes;  // header after the ring
+    // header: full[stages] | empty[stages] | tmem_full | tmem_ptr | bias[BN]
+    const uint32_t full0 = hdr, empty0 = hdr + 8u * p.stages, tmem_full = hdr + 16u * p.stages, tmem_slot = tmem_full + 8;
+    uint8_t* const hdr_gen = gen + (size_t)p.stages * stage_bytes;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(hdr_gen + 16 * p.stages + 8);
+    float* bias_s = reinterpret_cast<float*>(hdr_gen + 16 * p.stages + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int t0 = tile % p.T0, t1 = (tile / p.T0) % p.T1, t2 = tile / (p.T0 * p.T1);
+    const int n0 = blockIdx.y * p.BN;
+    const int kpw = p.KW >> 6;                                    // 64-element k-blocks per window row
+    const int nkb = p.R * kpw;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapB);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp >= 2) {
+        for (int j = threadIdx.x - 64; j < p.BN; j += 128) bias_s[j] = (p.bias && n0 + j < p.N) ? p.bias[n0 + j] : 0.f;
+    }
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < nkb; ++it) {
+                const int r = it / kpw, kc = it - r * kpw;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
+                mbar_expect_tx(full0 + 8 * stage, stage_bytes);
+                tma_load_5d(sa, &mapA, full0 + 8 * stage, kc * 64, t0 * p.BX, t1 * p.BY, r, t2 * p.NB);
+                tma_load_2d(sb, &mapB, full0 + 8 * stage, r * p.KW + kc * 64, n0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < nkb; ++it) {
+                mbar_wait(full0 + 8 * stage, phase);
+                fence_after();
+                const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
+                const uint64_t da = smem_desc_sw128(sa, 0, 1024), db = smem_desc_sw128(sb, 0, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)                       // 4 x (K = 16) per 64-element block: +32 B per step
+                    umma_bf16(tmem_base, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                umma_commit(empty0 + 8 * stage);                  // frees the smem stage when these MMAs retire
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // ===== epilogue: 4 warps, warp q reads TMEM lanes [32q, 32q+32) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
+        const int m0 = t0 * p.BX + i1, m1 = t1 * p.BY + i2, m2 = t2 * p.NB + i4;
+        const bool rvalid = m0 < p.E0 && m1 < p.E1 && m2 < p.E2;
+        const long long o = p.d_off + (long long)m0 * p.s0 + (long long)m1 * p.s1 + (long long)m2 * p.s2 + n0;
+        mbar_wait(tmem_full, 0);
+        fence_after();
+        for (int c = 0; c < p.BN; c += 16) {
+            float v[16];
+            __syncwarp();
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            if (rvalid && n0 + c < p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += bias_s[c + j];
+            const bool full16 = n0 + c + 16 <= p.N;
+            if (p.d_is_bf16) {
+                bf16* dp = reinterpret_cast<bf16*>(p.d) + o + c;
+                if (full16 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        w[j] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    reinterpret_cast<uint4*>(dp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    reinterpret_cast<uint4*>(dp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c + j < p.N) dp[j] = __float2bfloat16_rn(v[j]);
+                }
+            } else {
+                float* dp = reinterpret_cast<float*>(p.d) + o + c;
+                if (full16 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        reinterpret_cast<float4*>(dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c + j < p.N) dp[j] = v[j];
+                }
+            }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------
+static int pick_bn(int N) {
+    if (N <= 256) return (N + 15) / 16 * 16;
+    const int cands[] = {256, 192, 160, 128};
+    int best = 128, best_tiles = 1 << 30, best_waste = 1 << 30;
+    for (int c : cands) {
+        int tiles = (N + c - 1) / c, waste = tiles * c - N;
+        if (waste < best_waste || (waste == best_waste && tiles < best_tiles)) {
+            best = c; best_tiles = tiles; best_waste = waste;
+        }
+    }
+    return best;
+}
+
+int mopoe_tc_fwd_eligible(const mopoe_window_t* A, const mopoe_rows_t* D) {
+    if (!tc_init()) return 0;
+    if (A->a_dtype != MOPOE_BF16) return 0;
+    if (A->KW % 64 != 0) return 0;
+    if (D->N < 16) return 0;
+    if ((A->sA0 % 8) || (A->sA1 % 8) || (A->sA2 % 8) || (A->sAr % 8) || (A->a_off % 8)) return 0;
+    if ((reinterpret_cast<uintptr_t>(A->a) & 15) != 0) return 0;
+    if ((long long)A->E0 * A->E1 * A->E2 >= (1ll << 31)) return 0;
+    return 1;
+}
+
+static bool g_fwd_attr_set = false;
+
+int mopoe_conv_gemm_tc(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* stream) {
+    TcFwdParams p;
+    p.E0 = A->E0; p.E1 = A->E1; p.E2 = A->E2; p.R = A->R; p.KW = A->KW; p.N = D->N;
+    tile_split(p.E0, p.E1, 128, p.BX, p.BY, p.NB);
+    p.T0 = (p.E0 + p.BX - 1) / p.BX; p.T1 = (p.E1 + p.BY - 1) / p.BY; p.T2 = (p.E2 + p.NB - 1) / p.NB;
+    p.BN = pick_bn(p.N);
+    p.tmem_cols = pow2_ceil(p.BN < 32 ? 32 : p.BN);
+    const int stage_bytes = 128 * 128 + p.BN * 128;
+    const int hdr_bytes = 16 * 8 + 16 + 4 * p.BN + 64;
+    int stages = (SMEM_LIMIT - 1024 - hdr_bytes) / stage_bytes;
+    if (stages > 8) stages = 8;
+    const int nkb = p.R * (p.KW / 64);
+    if (stages > nkb) stages = nkb;
+    MOPOE_REQUIRE(stages >= 1, "conv_gemm_tc: no room for a stage (BN=%d)", p.BN);
+    p.stages = stages;
+    p.d_off = D->d_off; p.s0 = D->s0; p.s1 = D->s1; p.s2 = D->s2; p.d = D->d;
+    p.d_is_bf16 = D->d_dtype == MOPOE_BF16;
+    p.bias = bias;
+    CUtensorMap mapA, mapB;
+    {
+        const uint64_t dims[5] = {(uint64_t)A->KW, (uint64_t)A->E0, (uint64_t)A->E1, (uint64_t)A->R, (uint64_t)A->E2};
+        const uint64_t str[5] = {1, (uint64_t)A->sA0, (uint64_t)A->sA1, (uint64_t)A->sAr, (uint64_t)A->sA2};
+        const uint32_t box[5] = {64, (uint32_t)p.BX, (uint32_t)p.BY, 1, (uint32_t)p.NB};
+        const bf16* basep = reinterpret_cast<const bf16*>(A->a) + A->a_off;
+        if (encode_map(&mapA, basep, 5, dims, str, box, "conv_gemm_tc(A)")) return 1;
+    }
+    {
+        const uint64_t K = (uint64_t)A->R * A->KW;
+        const uint64_t dims[2] = {K, (uint64_t)p.N};
+        const uint64_t str[2] = {1, K};
+        const uint32_t box[2] = {64, (uint32_t)p.BN};
+        if (encode_map(&mapB, Wp, 2, dims, str, box, "conv_gemm_tc(B)")) return 1;
+    }
+    const int smem = 1024 + stages * stage_bytes + hdr_bytes;
+    if (!g_fwd_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        g_fwd_attr_set = true;
+    }
+    dim3 grid((unsigned)(p.T0 * p.T1 * p.T2), (unsigned)((p.N + p.BN - 1) / p.BN));
+    conv_gemm_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(mapA, mapB, p);
+    MOPOE_CHECK_LAUNCH("conv_gemm_tc");
+    return 0;
+}
+
+// =====================================================================================================================
+// wgrad:  dWp[n, r*KW + j] = sum_m dY[m, n] * A[m, r, j]
+// =====================================================================================================================
+constexpr int WG_BKM = 64;            // pixels (reduction rows) per pipeline stage
+
+struct TcWgParams {
+    int E0, E1, E2, bx, by, nb, T0, T1, T2, TM;
+    int R, KW, N, BNJ, JT, stages, tmem_cols;
+    int Z, m_per_split;
+    long long K;                      // R*KW
+    float* out;                       // dWp (Z == 1) or workspace [Z][N][K]
+    int accumulate;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapY, const TcWgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* const gen = smem_raw + (base - raw);
+    const uint32_t y_bytes = 2 * WG_BKM * 128, a_bytes = (uint32_t)(p.BNJ / 64) * WG_BKM * 128;
+    const uint32_t stage_bytes = y_bytes + a_bytes;
+    const uint32_t hdr = base + (uint32_t)p.stages * stage_bytes;
+    const uint32_t full0 = hdr, empty0 = hdr + 8u * p.stages, tmem_full = hdr + 16u * p.stages, tmem_slot = tmem_full + 8;
+    volatile uint32_t* tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(gen + (size_t)p.stages * stage_bytes + 16 * p.stages + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int jt = blockIdx.x;                       // tile over (r, j-block)
+    const int r = jt / p.JT, j0 = (jt - r * p.JT) * p.BNJ;
+    const int n0 = blockIdx.y * 128;
+    const int z = blockIdx.z;
+    const int mt_begin = z * p.m_per_split;
+    const int mt_end = min(p.TM, mt_begin + p.m_per_split);
+    const int nkb = mt_end - mt_begin;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapY);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0 && nkb > 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int mt = mt_begin; mt < mt_end; ++mt) {
+                const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                const uint32_t sy = base + stage * stage_bytes, sa = sy + y_bytes;
+                const uint32_t bar = full0 + 8 * stage;
+                mbar_expect_tx(bar, stage_bytes);
+                tma_load_4d(sy, &mapY, bar, n0, t0 * p.bx, t1 * p.by, t2 * p.nb);
+                tma_load_4d(sy + WG_BKM * 128, &mapY, bar, n0 + 64, t0 * p.bx, t1 * p.by, t2 * p.nb);
+                for (int qd = 0; qd < p.BNJ / 64; ++qd)
+                    tma_load_5d(sa + qd * WG_BKM * 128, &mapA, bar, j0 + 64 * qd, t0 * p.bx, t1 * p.by, r, t2 * p.nb);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nkb > 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.BNJ, 1, 1);      // both operands MN-major
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < nkb; ++it) {
+                mbar_wait(full0 + 8 * stage, phase);
+                fence_after();
+                const uint32_t sy = base + stage * stage_bytes, sa = sy + y_bytes;
+                // MN-major SW128: 64-wide MN chunks are LBO = BKM*128 B apart, 8 reduction rows are SBO = 1024 B apart
+                const uint64_t dy = smem_desc_sw128(sy, WG_BKM * 128, 1024), da = smem_desc_sw128(sa, WG_BKM * 128, 1024);
+#pragma unroll
+                for (int k = 0; k < WG_BKM / 16; ++k)                      // 16 reduction rows = 2048 B per step
+                    umma_bf16(tmem_base, dy + 128 * k, da + 128 * k, idesc, (it | k) != 0);
+                umma_commit(empty0 + 8 * stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int n = n0 + q * 32 + lane;
+        float* orow = p.out + ((long long)z * p.N + n) * p.K + (long long)r * p.KW + j0;
+        const bool direct_acc = p.Z == 1 && p.accumulate;
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            fence_after();
+        }
+        for (int c = 0; c < p.BNJ; c += 16) {
+            float v[16];
+            if (nkb > 0) {
+                __syncwarp();
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (n < p.N && j0 + c < p.KW) {
+                float* dp = orow + c;
+                if (j0 + c + 16 <= p.KW && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (direct_acc) {
+                            float4 e = reinterpret_cast<float4*>(dp)[j];
+                            o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+                        }
+                        reinterpret_cast<float4*>(dp)[j] = o;
+                    }
+                } else {
+                    for (int j = 0; j < 16; ++j)
+                        if (j0 + c + j < p.KW) dp[j] = (direct_acc ? dp[j] : 0.f) + v[j];
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+void mopoe_split_reduce_launch(const float* ws, int Z, long long n, float* out, int accumulate, cudaStream_t st);
+
+extern "C" int mopoe_tc_wgrad_built(void) { return 1; }
+
+int mopoe_tc_wgrad_eligible(const mopoe_window_t* A, const mopoe_rows_t* dY) {
+    if (!tc_init()) return 0;
+    if (A->a_dtype != MOPOE_BF16 || dY->d_dtype != MOPOE_BF16) return 0;
+    if (A->KW % 64 != 0 || dY->N < 64 || dY->N % 8 != 0) return 0;
+    if ((A->sA0 % 8) || (A->sA1 % 8) || (A->sA2 % 8) || (A->sAr % 8) || (A->a_off % 8)) return 0;
+    if ((dY->s0 % 8) || (dY->s1 % 8) || (dY->s2 % 8) || (dY->d_off % 8)) return 0;
+    if ((reinterpret_cast<uintptr_t>(A->a) & 15) || (reinterpret_cast<uintptr_t>(dY->d) & 15)) return 0;
+    return 1;
+}
+
+static void wg_plan(const mopoe_window_t* A, const mopoe_rows_t* dY, TcWgParams& p) {
+    p.E0 = A->E0; p.E1 = A->E1; p.E2 = A->E2; p.R = A->R; p.KW = A->KW; p.N = dY->N;
+    p.K = (long long)A->R * A->KW;
+    tile_split(p.E0, p.E1, WG_BKM, p.bx, p.by, p.nb);
+    p.T0 = (p.E0 + p.bx - 1) / p.bx; p.T1 = (p.E1 + p.by - 1) / p.by; p.T2 = (p.E2 + p.nb - 1) / p.nb;
+    p.TM = p.T0 * p.T1 * p.T2;
+    const int cands[] = {256, 192, 128, 64};
+    int best = 64, best_cost = 1 << 30;
+    for (int c : cands) {
+        int tiles = (p.KW + c - 1) / c;
+        int cost = tiles * c;                        // MMA columns issued per window row (waste included)
+        if (cost < best_cost) { best = c; best_cost = cost; }
+    }
+    p.BNJ = best;
+    p.JT = (p.KW + p.BNJ - 1) / p.BNJ;
+    p.tmem_cols = pow2_ceil(p.BNJ < 32 ? 32 : p.BNJ);
+    const int tiles_out = p.R * p.JT * ((p.N + 127) / 128);
+    int Z = (148 * 2 + tiles_out - 1) / tiles_out;
+    if (Z > p.TM) Z = p.TM;
+    const long long ws_cap = 1ll << 29;              // 512 MB of partials at most
+    while (Z > 1 && (long long)Z * p.N * p.K * 4 > ws_cap) --Z;
+    if (Z < 1) Z = 1;
+    p.m_per_split = (p.TM + Z - 1) / Z;
+    p.Z = (p.TM + p.m_per_split - 1) / p.m_per_split;
+    const int stage_bytes = 2 * WG_BKM * 128 + (p.BNJ / 64) * WG_BKM * 128;
+    int stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
+    if (stages > 8) stages = 8;
+    p.stages = stages;
+}
+
+size_t mopoe_conv_wgrad_ws_tc(const mopoe_window_t* A, const mopoe_rows_t* dY) {
+    TcWgParams p;
+    wg_plan(A, dY, p);
+    return p.Z > 1 ? (size_t)p.Z * p.N * p.K * sizeof(float) : 0;
+}
+
+static bool g_wg_attr_set = false;
+
+int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
+                        size_t ws_bytes, void* stream) {
+    TcWgParams p;
+    wg_plan(A, dY, p);
+    const size_t need = p.Z > 1 ? (size_t)p.Z * p.N * p.K * sizeof(float) : 0;
+    MOPOE_REQUIRE(ws_bytes >= need, "conv_wgrad_tc: workspace %zu < %zu", ws_bytes, need);
+    p.out = p.Z > 1 ? (float*)ws : dWp;
+    p.accumulate = accumulate;
+    CUtensorMap mapA, mapY;
+    {
+        const uint64_t dims[5] = {(uint64_t)A->KW, (uint64_t)A->E0, (uint64_t)A->E1, (uint64_t)A->R, (uint64_t)A->E2};
+        const uint64_t str[5] = {1, (uint64_t)A->sA0, (uint64_t)A->sA1, (uint64_t)A->sAr, (uint64_t)A->sA2};
+        const uint32_t box[5] = {64, (uint32_t)p.bx, (uint32_t)p.by, 1, (uint32_t)p.nb};
+        if (encode_map(&mapA, reinterpret_cast<const bf16*>(A->a) + A->a_off, 5, dims, str, box, "conv_wgrad_tc(A)")) return 1;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)dY->N, (uint64_t)A->E0, (uint64_t)A->E1, (uint64_t)A->E2};
+        const uint64_t str[4] = {1, (uint64_t)dY->s0, (uint64_t)dY->s1, (uint64_t)dY->s2};
+        const uint32_t box[4] = {64, (uint32_t)p.bx, (uint32_t)p.by, (uint32_t)p.nb};
+        if (encode_map(&mapY, reinterpret_cast<const bf16*>(dY->d) + dY->d_off, 4, dims, str, box, "conv_wgrad_tc(dY)")) return 1;
+    }
+    const int stage_bytes = 2 * WG_BKM * 128 + (p.BNJ / 64) * WG_BKM * 128;
+    const int smem = 1024 + p.stages * stage_bytes + 256;
+    if (!g_wg_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) MOPOE_FAIL("conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        g_wg_attr_set = true;
+    }
+    dim3 grid((unsigned)(p.R * p.JT), (unsigned)((p.N + 127) / 128), (unsigned)p.Z);
+    cudaStream_t st = (cudaStream_t)stream;
+    conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapY, p);
+    MOPOE_CHECK_LAUNCH("conv_wgrad_tc");
+    if (p.Z > 1) {
+        mopoe_split_reduce_launch((const float*)ws, p.Z, (long long)p.N * p.K, dWp, accumulate, st);
+        MOPOE_CHECK_LAUNCH("split_reduce");
+    }
+    return 0;
+}

@@ -1,0 +1,134 @@
+"""Implicit-GEMM kernels through the C ABI against torch CPU convolutions (the reference's own call sites:
+nn.Conv*/nn.ConvTranspose*), for both kernel families (CUDA-core fp32 path and tcgen05 bf16 path)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _eng(dtype, impl):
+    from mopoe_mimic_b200 import _lib as L
+    from mopoe_mimic_b200.engine import Engine
+    e = Engine('cuda', dtype, {'simt': L.IMPL_SIMT, 'tc': L.IMPL_TC, 'auto': L.IMPL_AUTO}[impl])
+    return e
+
+
+def _act(x_nchw, pad, dtype, nd):
+    """NCHW / NCL cpu tensor -> bordered channels-last Act on the GPU"""
+    from mopoe_mimic_b200.engine import Act
+    if nd == 1:
+        B, Cc, W = x_nchw.shape
+        H = 1
+        cl = x_nchw.permute(0, 2, 1).reshape(B, 1, W, Cc)
+        ph, pw = 0, pad
+    else:
+        B, Cc, H, W = x_nchw.shape
+        cl = x_nchw.permute(0, 2, 3, 1)
+        ph = pw = pad
+    t = torch.zeros(B, H + 2 * ph, W + 2 * pw, Cc, dtype=dtype, device='cuda')
+    t[:, ph:ph + H, pw:pw + W] = cl.to(dtype).cuda()
+    return Act(t, B, H, W, Cc, ph, pw)
+
+
+def _to_nchw(act, nd):
+    t = act.interior().float().cpu()
+    return t.permute(0, 3, 1, 2) if nd == 2 else t[:, 0].permute(0, 2, 1)
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.rand(shape, generator=g) * 2 - 1) * scale
+    return x.to(dtype).float()      # values exactly representable in `dtype`
+
+
+CASES = [
+    # (nd, B, Cin, Cout, spatial)
+    (2, 4, 64, 128, 16),
+    (2, 2, 128, 256, 32),
+    (2, 3, 64, 192, 8),
+    (2, 16, 128, 160, 4),
+    (1, 4, 64, 128, 64),
+    (1, 2, 128, 96, 512),
+    (2, 5, 128, 640, 8),
+]
+
+
+@pytest.mark.parametrize('impl,dtype', [('simt', torch.float32), ('simt', torch.bfloat16), ('tc', torch.bfloat16)])
+@pytest.mark.parametrize('nd,B,ci,co,sp', CASES)
+def test_conv_k4s2p1_fwd_dgrad_wgrad(impl, dtype, nd, B, ci, co, sp):
+    from mopoe_mimic_b200.engine import conv_form, conv_form_grad, phase_form
+    eng = _eng(dtype, impl)
+    shp = (B, ci, sp) if nd == 1 else (B, ci, sp, sp)
+    wshape = (co, ci, 4) if nd == 1 else (co, ci, 4, 4)
+    x = _rand(shp, 1, 1.0, dtype)
+    w = _rand(wshape, 2, 0.05, dtype)
+    bias = _rand((co,), 3, 0.1)
+    conv = F.conv1d if nd == 1 else F.conv2d
+    convt = F.conv_transpose1d if nd == 1 else F.conv_transpose2d
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    # forward
+    ref = conv(x, w, bias, stride=2, padding=1)
+    xa = _act(x, 1, dtype, nd)
+    out = eng.gemm_down(xa, conv_form(w.cuda(), dtype), bias.cuda(), 4, 2, 1, co)
+    torch.cuda.synchronize()
+    got = _to_nchw(out, nd)
+    assert (got - ref).abs().max() <= tol * ref.abs().max()
+    # dgrad = transposed conv of the output gradient
+    gshape = ref.shape
+    g = _rand(gshape, 4, 1.0, dtype)
+    ref_dx = convt(g, w, None, stride=2, padding=1)
+    ga = _act(g, 1, dtype, nd)
+    dx = eng.gemm_up(ga, phase_form(w.cuda(), dtype), None, ci)
+    torch.cuda.synchronize()
+    assert (_to_nchw(dx, nd) - ref_dx).abs().max() <= tol * ref_dx.abs().max()
+    # wgrad
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    conv(xr, wr, None, stride=2, padding=1).backward(g)
+    from mopoe_mimic_b200 import _lib as L
+    if impl == 'tc' and not L.load().mopoe_tc_wgrad_built():
+        eng.impl = L.IMPL_AUTO
+    gw = eng.wgrad_down(xa, 4, 2, 1, ga)
+    torch.cuda.synchronize()
+    gw = conv_form_grad(gw, wshape).cpu()
+    assert (gw - wr.grad).abs().max() <= tol * wr.grad.abs().max()
+
+
+@pytest.mark.parametrize('impl,dtype', [('simt', torch.float32), ('tc', torch.bfloat16)])
+def test_pointwise_and_rows(impl, dtype):
+    eng = _eng(dtype, impl)
+    B, Cc, N, sp = 4, 128, 192, 8
+    x = _rand((B, Cc, sp, sp), 5, 1.0, dtype)
+    w = _rand((N, Cc), 6, 0.05, dtype)
+    bias = _rand((N,), 7, 0.1)
+    ref = F.conv2d(x, w.view(N, Cc, 1, 1), bias)
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    for pad in (0, 1):
+        xa = _act(x, pad, dtype, 2)
+        out = eng.gemm_rows(xa, w.to(dtype).cuda().contiguous(), bias.cuda(), N)
+        torch.cuda.synchronize()
+        assert (_to_nchw(out, 2) - ref).abs().max() <= tol * ref.abs().max()
+
+
+@pytest.mark.parametrize('impl,dtype', [('simt', torch.float32), ('tc', torch.bfloat16)])
+def test_valid_4to1_and_1to4(impl, dtype):
+    """k4/s2/p0 conv on 4x4 -> 1x1 (encoder tail) and k4/s1/p0 deconv 1x1 -> 4x4 (decoder head)"""
+    from mopoe_mimic_b200.engine import conv_form, full_form
+    eng = _eng(dtype, impl)
+    B, ci, co = 128, 128, 64
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    x = _rand((B, ci, 4, 4), 8, 1.0, dtype)
+    w = _rand((co, ci, 4, 4), 9, 0.05, dtype)
+    ref = F.conv2d(x, w, None, stride=2, padding=0)
+    xa = _act(x, 1, dtype, 2)
+    out = eng.gemm_down(xa, conv_form(w.cuda(), dtype), None, 4, 2, 0, co)
+    torch.cuda.synchronize()
+    assert (_to_nchw(out, 2) - ref).abs().max() <= tol * ref.abs().max()
+    z = _rand((B, ci, 1, 1), 10, 1.0, dtype)
+    wt = _rand((ci, co, 4, 4), 11, 0.05, dtype)
+    ref2 = F.conv_transpose2d(z, wt, None, stride=1, padding=0)
+    za = _act(z, 0, dtype, 2)
+    out2 = eng.gemm_rows(za, full_form(wt.cuda(), dtype), None, 16 * co, out_shape=(B, 4, 4, co))
+    torch.cuda.synchronize()
+    assert (_to_nchw(out2, 2) - ref2).abs().max() <= tol * ref2.abs().max()
