@@ -36,6 +36,7 @@ def parse():
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-batch', type=int, default=16)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the captured CUDA graph')
     ap.add_argument('--profile-kernels', action='store_true', help='print per-op-class device time of one step')
     return ap.parse_args()
 
@@ -155,17 +156,31 @@ def main():
     def allreduce(flat_g):
         dist.all_reduce(flat_g)
 
-    def step_resident():
-        return P.train_step(exp, (dict(resident), None), allreduce if world > 1 else None)
+    ar = allreduce if world > 1 else None
+    stats_host = torch.empty(16, dtype=torch.float32).pin_memory()
+    launches_per_step = None
+    if args.no_graph or args.profile_kernels:
+        def step_resident():
+            return P.train_step(exp, (dict(resident), None), ar)
 
-    stats_host = torch.empty(12, dtype=torch.float32).pin_memory()
+        def step_e2e():
+            b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            out = P.train_step(exp, (b, None), ar)
+            st = P.packed_stats(out)
+            stats_host[:st.numel()].copy_(st, non_blocking=True)
+            return st.numel() * 4
+    else:
+        c0 = L.LAUNCHES
+        gstep = P.GraphedTrainStep(exp, resident, ar)          # 2 eager warm-up steps + 1 captured step
+        launches_per_step = (L.LAUNCHES - c0) // 3
 
-    def step_e2e():
-        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-        out = P.train_step(exp, (b, None), allreduce if world > 1 else None)
-        st = P.packed_stats(out)
-        stats_host[:st.numel()].copy_(st, non_blocking=True)
-        return st.numel() * 4
+        def step_resident():
+            return gstep(resident)
+
+        def step_e2e():
+            st = gstep(host)                                   # pinned host -> static device inputs, then replay
+            stats_host[:st.numel()].copy_(st, non_blocking=True)
+            return st.numel() * 4
 
     def barrier():
         if world > 1:
@@ -175,6 +190,20 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     barrier()
+    if args.profile_kernels and rank == 0:
+        # developer aid: device time per kernel name for ONE step (CUPTI via torch.profiler), then exit
+        from torch.profiler import ProfilerActivity, profile
+        t_cpu0 = time.perf_counter()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step_resident()
+            torch.cuda.synchronize()
+        print('one step wall %.1f ms' % ((time.perf_counter() - t_cpu0) * 1e3))
+        rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0]
+        tot = sum(r[2] for r in rows)
+        for k, n, t in sorted(rows, key=lambda r: -r[2])[:45]:
+            print('%-70s %5d %9.1f us %5.1f%%' % (k[:70], n, t, 100.0 * t / tot))
+        print('total device time %.1f ms' % (tot / 1e3))
+        return
     sampler = ClockSampler(local)
     sampler.start()
     L.LAUNCHES = 0
@@ -185,7 +214,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = L.LAUNCHES
+    launches = L.LAUNCHES if launches_per_step is None else launches_per_step * args.steps
     # end-to-end: pinned host inputs -> device each step, packed stats back
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -203,7 +232,7 @@ def main():
     # roofline of the dominant kernel family (implicit-GEMM convs): one instrumented step, CUDA events per launch
     eng = vae.rt.engine
     eng.profile = []
-    step_resident()
+    P.train_step(exp, (dict(resident), None), ar)              # eager, so every GEMM launch is bracketed by events
     torch.cuda.synchronize()
     prof, eng.profile = eng.profile, None
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
@@ -233,7 +262,7 @@ def main():
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
                 'data': 'synthetic',
                 'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': B * world,
-                           'parallelism': 'dp%d' % world, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
+                           'parallelism': 'dp%d' % world, 'cuda_graph': not args.no_graph, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
                 'clocks': sampler.summary(),
                 'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s',
                         'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h},

@@ -122,7 +122,17 @@ int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int mask_mode,
  * src_nchw != 0: src->ptr is an NCHW fp32 user tensor [B,C,H,W] (strides ignored). */
 int mopoe_convert(const mopoe_view_t* src, int src_nchw, const mopoe_view_t* dst, void* stream);
 /* Bernoulli(0.5) keep-mask bytes from a counter-based generator (Philox-4x32-10). */
-int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+/* step_ptr (may be NULL): device counter of the training step, mixed into the Philox counter so a captured
+ * CUDA graph draws fresh masks on every replay. */
+int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* step_ptr,
+                       void* stream);
+/* fp32 master weight W[A][B][KH][KW] -> packed GEMM operand (dst_dtype): form 0 conv-form [A, KH*KW*bpad],
+ * 1 phase-form (py,px) [B, taps*A], 2 full-form [KH*KW*B, A], 3 [A,B], 4 [B,A]  (layouts in DESIGN.md). */
+int mopoe_pack_weight(const float* W, int A, int B, int KH, int KW, int form, int py, int px, int bpad,
+                      void* dst, int dst_dtype, void* stream);
+/* advance the device-side step state (dropout step counter, Adam step + bias-correction coefficients) */
+int mopoe_step_advance(uint64_t* rng_step, int32_t* adam_step, float* adam_coef, float lr, float beta1,
+                       float beta2, void* stream);
 
 /* ---- single-channel image layers (CUDA-core direct kernels) ---------------------------------------
  * first conv  nn.Conv2d(1, C, 3, stride 2, pad 1, bias=False)  (FeatureExtractorImg.py:29-34)
@@ -198,6 +208,9 @@ int mopoe_categorical_logprob_bwd(const float* y, const int32_t* idx, int64_t ro
  * `step` is the 1-based step count; g is multiplied by grad_scale first (1/world_size under DP). */
 int mopoe_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, int step, float grad_scale, void* stream);
+
+int mopoe_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* coef,
+                        float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 """mopoe_mimic_b200 — B200-native MoPoE-MIMIC training step (hand-written sm_100a CUDA behind the reference's
 Python model API).  See DESIGN.md / INTEGRATION.md."""
 from . import _lib
-from .train import (CudaOutOfMemory, Experiment, FlatAdam, NaNInLatent, basic_routine_epoch, default_flags,  # noqa: F401
+from .train import (CudaOutOfMemory, Experiment, FlatAdam, GraphedTrainStep, NaNInLatent, basic_routine_epoch, default_flags,  # noqa: F401
                     packed_stats, train_step)
 from .mmvae import BaseMMVae, MMVaeMimic, VAEtrimodalMimic  # noqa: F401
 from .networks import DecoderImg, DecoderText, EncoderImg, EncoderText  # noqa: F401

@@ -60,7 +60,10 @@ SIGNATURES = {
     'mopoe_bn_bwd_apply': (_I, [_V, _V, _F, _V, _P, _I, _P, _P, _P, _P, _V, _V, _P]),
     'mopoe_scale_mask': (_I, [_V, _P, _I, _F, _V, _P]),
     'mopoe_convert': (_I, [_V, _I, _V, _P]),
-    'mopoe_dropout_mask': (_I, [_P, _L, C.c_uint64, C.c_uint64, _P]),
+    'mopoe_dropout_mask': (_I, [_P, _L, C.c_uint64, C.c_uint64, _P, _P]),
+    'mopoe_pack_weight': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
+    'mopoe_step_advance': (_I, [_P, _P, _P, _F, _F, _F, _P]),
+    'mopoe_adam_flat_dev': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),
     'mopoe_conv3x3s2_c1_fwd': (_I, [_P, _P, _I, _I, _I, _V, _P]),
     'mopoe_conv3x3s2_c1_wgrad': (_I, [_P, _V, _I, _I, _I, _P, _I, _P, _I, _P]),
     'mopoe_deconv3x3s2_c1_fwd': (_I, [_V, _P, _P, _P, _P]),

@@ -75,30 +75,30 @@ def _eval_stats(rm, rv):
 def _main_fwd(eng, spec, x, Wg, bias, dtype):
     """conv2 / shortcut forward by geometry kind -> plain Act"""
     if spec.kind == 'S' and not spec.transposed:
-        return eng.gemm_down(x, conv_form(Wg, dtype), bias, 4, 2, 1, spec.cout)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 1, spec.cout)
     if spec.kind == 'S':
-        return eng.gemm_up(x, phase_form(Wg, dtype), bias, spec.cout)
+        return eng.gemm_up(x, eng.packed(Wg, "phase"), bias, spec.cout)
     if spec.kind == 'Z':
-        return eng.gemm_down(x, conv_form(Wg, dtype), bias, 4, 2, 0, spec.cout)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 0, spec.cout)
     if spec.kind == 'Q':
-        return eng.gemm_down(x, conv_form(Wg, dtype), bias, 4, 4, 1, spec.cout)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 4, 1, spec.cout)
     taps = 4 ** spec.nd if spec.nd == 2 else 4                     # 'U'
     bb = bias.repeat(taps) if bias is not None else None
     oh, ow = spec.out_hw(x.H, x.W)
-    return eng.gemm_rows(x, full_form(Wg, dtype), bb, taps * spec.cout, out_shape=(x.B, oh, ow, spec.cout))
+    return eng.gemm_rows(x, eng.packed(Wg, "full"), bb, taps * spec.cout, out_shape=(x.B, oh, ow, spec.cout))
 
 
 def _main_dgrad(eng, spec, dout, Wg, dtype, H, W):
     """d/d(input) of conv2 / shortcut: dout is a bordered Act -> plain Act [B,H,W,cin]"""
     if spec.kind == 'S' and not spec.transposed:
-        return eng.gemm_up(dout, phase_form(Wg, dtype), None, spec.cin)
+        return eng.gemm_up(dout, eng.packed(Wg, "phase"), None, spec.cin)
     if spec.kind == 'S':
-        return eng.gemm_down(dout, conv_form(Wg, dtype), None, 4, 2, 1, spec.cin)
+        return eng.gemm_down(dout, eng.packed(Wg, "conv"), None, 4, 2, 1, spec.cin)
     if spec.kind == 'Z':
         taps = 16 if spec.nd == 2 else 4
-        return eng.gemm_rows(dout, full_form(Wg, dtype), None, taps * spec.cin, out_shape=(dout.B, H, W, spec.cin))
+        return eng.gemm_rows(dout, eng.packed(Wg, "full"), None, taps * spec.cin, out_shape=(dout.B, H, W, spec.cin))
     if spec.kind == 'U':
-        return eng.gemm_down(dout, conv_form(Wg, dtype), None, 4, 1, 0, spec.cin)
+        return eng.gemm_down(dout, eng.packed(Wg, "conv"), None, 4, 1, 0, spec.cin)
     raise NotImplementedError('dgrad for stride-4 blocks (256 px) is not built yet')
 
 
@@ -130,8 +130,7 @@ class ResBlockFn(torch.autograd.Function):
         a1 = eng.bn_apply(x, None, L.MASK_NONE, st1, P['bn1.weight'], P['bn1.bias'], True,
                           Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device))
         # conv1 (1x1)
-        W1 = P['conv1.weight'].reshape(sp.cin, sp.cin)
-        w1f = (W1.t() if sp.transposed else W1).to(dt).contiguous()
+        w1f = eng.packed(P['conv1.weight'], 'matT' if sp.transposed else 'mat')
         hh = eng.gemm_rows(a1, w1f, P.get('conv1.bias'), sp.cin)
         # dropout1 -> bn2 -> relu  (written with the border conv2 needs)
         st2 = eng.bn_stats(hh, m1, mode, *bufs['bn2']) if run.train else _eval_stats(*bufs['bn2'])
@@ -196,12 +195,11 @@ class ResBlockFn(torch.autograd.Function):
         dh = eng.bn_bwd(da2, a2, 1.0, hh, m1, mode, st2, P['bn2.weight'], G['bn2.weight'], G['bn2.bias'], None,
                         Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device))
         # conv1 (1x1)
-        W1 = P['conv1.weight'].reshape(sp.cin, sp.cin)
         g1 = eng.wgrad_rows(a1, dh)                                   # [n_out, c_in]
         G['conv1.weight'] = (g1.t() if sp.transposed else g1).reshape(P['conv1.weight'].shape)
         if sp.inner_bias:
             G['conv1.bias'] = eng.colsum(dh)
-        w1b = (W1 if sp.transposed else W1.t()).to(dt).contiguous()    # [c_in, n_out]
+        w1b = eng.packed(P['conv1.weight'], 'mat' if sp.transposed else 'matT')   # [c_in, n_out]
         da1 = eng.gemm_rows(dh, w1b, None, sp.cin)
         # relu, bn1 (+ the shortcut's input gradient)
         G['bn1.weight'], G['bn1.bias'] = eng.f32(sp.cin), eng.f32(sp.cin)
@@ -283,11 +281,9 @@ class TextStemFn(torch.autograd.Function):
         xin = Act.empty(B, 1, Lq, Fp, 0, 1, eng.dtype, eng.device)
         src = L.View(x.data_ptr(), L.F32, B, 1, Lq, Fq, 0, 0, 0, Lq * Fq, Lq * Fq, Fq)
         eng.convert(src, False, xin)
-        wp = torch.zeros(Cc, Fp, 4, dtype=torch.float32, device=eng.device)
-        wp[:, :Fq] = w
         y = Act(torch.zeros((B, 1, Lq // 2 + 2 * out_pad, Cc), dtype=eng.dtype, device=eng.device), B, 1, Lq // 2, Cc,
                 0, out_pad)
-        eng.gemm_down(xin, conv_form(wp, eng.dtype), bias, 4, 2, 1, Cc, out=y)
+        eng.gemm_down(xin, eng.packed(w, 'conv', bpad=Fp), bias, 4, 2, 1, Cc, out=y)
         ctx.save_for_backward(xin.t, w)
         ctx.eng, ctx.geo = eng, (B, Lq, Fq, Fp, out_pad)
         return y.t
@@ -317,7 +313,7 @@ class LinearFn(torch.autograd.Function):
             xa = Act.like(x_t.contiguous().to(eng.dtype), B, 1, 1, K)
         else:
             xa = Act.like(x_t, B, 1, 1, K, *_pads(nd, in_pad))
-        out = eng.gemm_rows(xa, w.to(eng.dtype).contiguous(), bias, N, out_dtype=eng.dtype if out_act else torch.float32)
+        out = eng.gemm_rows(xa, eng.packed(w, 'mat'), bias, N, out_dtype=eng.dtype if out_act else torch.float32)
         ctx.save_for_backward(xa.t, w)
         ctx.eng, ctx.geo = eng, (B, in_pad, nd, out_act, x_t.dtype, tuple(x_t.shape))
         return out.t.view(B, N) if not out_act else out.t
@@ -333,7 +329,7 @@ class LinearFn(torch.autograd.Function):
         dy = Act.like(dy_t.contiguous().to(eng.dtype), B, 1, 1, N)
         dw = eng.wgrad_rows(xa, dy)
         db = eng.colsum(dy)
-        dxp = eng.gemm_rows(dy, w.t().to(eng.dtype).contiguous(), None, K,
+        dxp = eng.gemm_rows(dy, eng.packed(w, 'matT'), None, K,
                             out_dtype=torch.float32 if in_pad is None else eng.dtype)
         if in_pad is None:
             dx = dxp.t.view(x_shape).to(x_dtype)
@@ -354,7 +350,7 @@ class TextLastFn(torch.autograd.Function):
     def forward(ctx, x_t, w, bias, eng, B, Lq, in_pad):
         Cc, Fq = w.shape[0], w.shape[1]
         x = Act.like(x_t, B, 1, Lq, Cc, 0, in_pad)
-        out = eng.gemm_up(x, phase_form(w, eng.dtype), bias, Fq, out_dtype=torch.float32)
+        out = eng.gemm_up(x, eng.packed(w, 'phase'), bias, Fq, out_dtype=torch.float32)
         ctx.save_for_backward(x_t, w)
         ctx.eng, ctx.geo = eng, (B, Lq, in_pad)
         return out.t.view(B, 2 * Lq, Fq)
@@ -372,11 +368,9 @@ class TextLastFn(torch.autograd.Function):
         dyc = dy_t.contiguous()
         src = L.View(dyc.data_ptr(), L.F32, B, 1, 2 * Lq, Fq, 0, 0, 0, 2 * Lq * Fq, 2 * Lq * Fq, Fq)
         eng.convert(src, False, dyp)
-        db = eng.colsum(Act.like(dyc, B, 1, 2 * Lq, Fq)) if Fq % 4 == 0 else dyc.sum((0, 1))
-        wpad = torch.zeros(Cc, Fp, 4, dtype=torch.float32, device=eng.device)
-        wpad[:, :Fq] = w
+        db = eng.colsum(dyp)[:Fq]
         # dgrad of a stride-2 deconv = stride-2 conv over the bordered gradient, conv-form weights [ci,(kx,co)]
-        dx = eng.gemm_down(dyp, conv_form(wpad, eng.dtype), None, 4, 2, 1, Cc)
+        dx = eng.gemm_down(dyp, eng.packed(w, 'conv', bpad=Fp), None, 4, 2, 1, Cc)
         g = eng.wgrad_down(dyp, 4, 2, 1, x)                     # [Cc, 4*Fp]
         dw = g.view(Cc, 4, Fp)[:, :, :Fq].permute(0, 2, 1).contiguous()
         if in_pad:

@@ -135,15 +135,26 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
     }
 }
 
-__global__ void bn_finalize_kernel(const double* ws, int nchunk, int C, double count, float eps, float momentum,
-                                   float* mean, float* invstd, float* rmean, float* rvar) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < nchunk; ++k) {
-        s += ws[((long long)k * 2 + 0) * C + c];
-        q += ws[((long long)k * 2 + 1) * C + c];
+// finalize: ONE WARP per channel; lane l sums chunks l, l+32, ... then a shuffle tree — a fixed order, so the
+// result is run-to-run deterministic, and the chunk loop is 32x shorter than a thread-per-channel walk.
+__device__ __forceinline__ void chunk_sums(const double* ws, int nchunk, int C, int c, double& s, double& q) {
+    const int lane = threadIdx.x & 31;
+    double a = 0.0, b = 0.0;
+    for (int k = lane; k < nchunk; k += 32) {
+        a += ws[((long long)k * 2 + 0) * C + c];
+        b += ws[((long long)k * 2 + 1) * C + c];
     }
+    s = warp_sum(a);
+    q = warp_sum(b);
+}
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const double* ws, int nchunk, int C, double count, float eps,
+                                                          float momentum, float* mean, float* invstd, float* rmean,
+                                                          float* rvar) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= C) return;
+    double s, q;
+    chunk_sums(ws, nchunk, C, c, s, q);
+    if ((threadIdx.x & 31) != 0) return;
     double m = s / count;
     double var = q / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -156,15 +167,13 @@ __global__ void bn_finalize_kernel(const double* ws, int nchunk, int C, double c
     }
 }
 
-__global__ void sums_finalize_kernel(const double* ws, int nchunk, int C, float* out0, float* out1, int accumulate,
-                                     float* sums) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) sums_finalize_kernel(const double* ws, int nchunk, int C, float* out0, float* out1,
+                                                            int accumulate, float* sums) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < nchunk; ++k) {
-        s += ws[((long long)k * 2 + 0) * C + c];
-        q += ws[((long long)k * 2 + 1) * C + c];
-    }
+    double s, q;
+    chunk_sums(ws, nchunk, C, c, s, q);
+    if ((threadIdx.x & 31) != 0) return;
     if (out0) out0[c] = (accumulate ? out0[c] : 0.f) + (float)s;   // dbeta / colsum
     if (out1) out1[c] = (accumulate ? out1[c] : 0.f) + (float)q;   // dgamma
     if (sums) {
@@ -197,7 +206,7 @@ extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int ma
     cudaStream_t st = (cudaStream_t)stream;
     if (launch_reduce<RED_STATS>(x, nullptr, nullptr, 1.f, mask, mask_mode, nullptr, nullptr, ws, nchunk, st)) return 1;
     double count = (double)x->B * x->H * x->W;
-    bn_finalize_kernel<<<(x->C + 127) / 128, 128, 0, st>>>(ws, nchunk, x->C, count, eps, momentum, mean, invstd,
+    bn_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, count, eps, momentum, mean, invstd,
                                                           running_mean, running_var);
     MOPOE_CHECK_LAUNCH("bn_finalize");
     return 0;
@@ -207,7 +216,7 @@ extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, d
     cudaStream_t st = (cudaStream_t)stream;
     if (launch_reduce<RED_COLSUM>(v, nullptr, nullptr, 1.f, nullptr, MOPOE_MASK_NONE, nullptr, nullptr, ws, nchunk, st))
         return 1;
-    sums_finalize_kernel<<<(v->C + 127) / 128, 128, 0, st>>>(ws, nchunk, v->C, out, nullptr, accumulate, nullptr);
+    sums_finalize_kernel<<<(v->C + 7) / 8, 256, 0, st>>>(ws, nchunk, v->C, out, nullptr, accumulate, nullptr);
     MOPOE_CHECK_LAUNCH("colsum_finalize");
     return 0;
 }
@@ -220,7 +229,7 @@ extern "C" int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* g
     if (check_same(x, dy, "bn_bwd_reduce(dy)")) return 1;
     if (gate && check_same(x, gate, "bn_bwd_reduce(gate)")) return 1;
     if (launch_reduce<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st)) return 1;
-    sums_finalize_kernel<<<(x->C + 127) / 128, 128, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
+    sums_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
     MOPOE_CHECK_LAUNCH("bn_bwd_finalize");
     return 0;
 }
@@ -452,12 +461,15 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, u
         k1 += 0xBB67AE85u;
     }
 }
-__global__ void dropout_mask_kernel(uint8_t* mask, long long n, uint64_t seed, uint64_t offset) {
+__global__ void dropout_mask_kernel(uint8_t* mask, long long n, uint64_t seed, uint64_t offset,
+                                    const unsigned long long* __restrict__ step_ptr) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long base = t * 128;
     if (base >= n) return;
     uint64_t cidx = (uint64_t)t + offset;
-    uint32_t ctr[4] = {(uint32_t)cidx, (uint32_t)(cidx >> 32), 0x6d6f706fu, 0x65u};
+    // the training-step index lives in device memory so that a captured CUDA graph draws fresh masks on every replay
+    const unsigned long long step = step_ptr ? step_ptr[0] : 0ull;
+    uint32_t ctr[4] = {(uint32_t)cidx, (uint32_t)(cidx >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ 0x6d6f7065u};
     philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
     if (base + 128 <= n && ((uintptr_t)(mask + base) & 15) == 0) {
 #pragma unroll
@@ -478,10 +490,12 @@ __global__ void dropout_mask_kernel(uint8_t* mask, long long n, uint64_t seed, u
         for (int i = 0; i < 128 && base + i < n; ++i) mask[base + i] = (ctr[i >> 5] >> (i & 31)) & 1u;
     }
 }
-extern "C" int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* step_ptr,
+                                  void* stream) {
     if (n <= 0) return 0;
     long long threads = ceil_div64(n, 128);
-    dropout_mask_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)stream>>>(mask, n, seed, offset);
+    dropout_mask_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, (cudaStream_t)stream>>>(
+        mask, n, seed, offset, (const unsigned long long*)step_ptr);
     MOPOE_CHECK_LAUNCH("dropout_mask");
     return 0;
 }
@@ -490,8 +504,12 @@ extern "C" int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint6
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n4,
                                                    long long n, float lr_c, float b1, float b2, float eps, float inv_sqrt_bc2,
-                                                   float gscale) {
+                                                   float gscale, const float* __restrict__ coef) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (coef) {            // device-side bias corrections (graph-captured step)
+        lr_c = coef[0];
+        inv_sqrt_bc2 = coef[1];
+    }
     if (i < n4) {
         float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<const float4*>(g)[i];
         float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
@@ -522,7 +540,101 @@ extern "C" int mopoe_adam_flat(float* p, const float* g, float* m, float* v, int
     double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     long long n4 = n / 4;
     adam_kernel<<<(unsigned)ceil_div64(n4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(
-        p, g, m, v, n4, n, (float)(lr / bc1), beta1, beta2, eps, (float)(1.0 / sqrt(bc2)), grad_scale);
+        p, g, m, v, n4, n, (float)(lr / bc1), beta1, beta2, eps, (float)(1.0 / sqrt(bc2)), grad_scale, nullptr);
     MOPOE_CHECK_LAUNCH("adam");
+    return 0;
+}
+// same update, coefficients {lr/(1-b1^t), 1/sqrt(1-b2^t)} read from device memory (written by mopoe_step_advance)
+extern "C" int mopoe_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* coef, float beta1,
+                                   float beta2, float eps, float grad_scale, void* stream) {
+    if (n <= 0) return 0;
+    MOPOE_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, "adam: unaligned buffers");
+    long long n4 = n / 4;
+    adam_kernel<<<(unsigned)ceil_div64(n4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, 0.f, beta1, beta2, eps,
+                                                                                    1.f, grad_scale, coef);
+    MOPOE_CHECK_LAUNCH("adam");
+    return 0;
+}
+
+// ---- weight re-layout: fp32 master weights W[A][B][KH][KW] -> packed GEMM operand (bf16 or fp32) ------------------
+//   form 0 conv : dst[a][ky][kx][b']            (b' < bpad; zero for b' >= B)      conv-form  [A, KH*KW*bpad]
+//   form 1 phase: dst[b][r][kxi][a] = W[a][b][KT[py][r]][KT[px][kxi]]               phase-form [B, (KH>1?2:1)*2*A]
+//   form 2 full : dst[ky][kx][b][a]                                                  full-form  [KH*KW*B, A]
+//   form 3 mat  : dst[a][b]        form 4 matT : dst[b][a]                           (KH = KW = 1)
+template <typename TD>
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ W, int A, int B, int KH, int KW, int form,
+                                                          int py, int px, int bpad, TD* __restrict__ dst, long long total) {
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total) return;
+    const int KT[2][2] = {{3, 1}, {2, 0}};
+    int a, b, ky, kx;
+    bool zero = false;
+    if (form == 0) {
+        b = (int)(i % bpad);
+        long long t = i / bpad;
+        kx = (int)(t % KW); t /= KW;
+        ky = (int)(t % KH);
+        a = (int)(t / KH);
+        zero = b >= B;
+    } else if (form == 1) {
+        a = (int)(i % A);
+        long long t = i / A;
+        int kxi = (int)(t % 2); t /= 2;
+        int r = 0;
+        if (KH > 1) { r = (int)(t % 2); t /= 2; }
+        b = (int)t;
+        kx = KT[px][kxi];
+        ky = KH > 1 ? KT[py][r] : 0;
+    } else if (form == 2) {
+        a = (int)(i % A);
+        long long t = i / A;
+        b = (int)(t % B); t /= B;
+        kx = (int)(t % KW);
+        ky = (int)(t / KW);
+    } else if (form == 3) {
+        b = (int)(i % B); a = (int)(i / B); ky = kx = 0;
+    } else {
+        a = (int)(i % A); b = (int)(i / A); ky = kx = 0;
+    }
+    float v = zero ? 0.f : W[(((long long)a * B + b) * KH + ky) * KW + kx];
+    if constexpr (sizeof(TD) == 4) dst[i] = v; else dst[i] = __float2bfloat16_rn(v);
+}
+extern "C" int mopoe_pack_weight(const float* W, int A, int B, int KH, int KW, int form, int py, int px, int bpad,
+                                 void* dst, int dst_dtype, void* stream) {
+    long long total;
+    if (form == 0) total = (long long)A * KH * KW * bpad;
+    else if (form == 1) total = (long long)B * (KH > 1 ? 2 : 1) * 2 * A;
+    else if (form == 2) total = (long long)KH * KW * B * A;
+    else if (form == 3 || form == 4) total = (long long)A * B;
+    else MOPOE_FAIL("pack_weight: bad form %d", form);
+    MOPOE_REQUIRE(form != 0 || bpad >= B, "pack_weight: bpad < B");
+    MOPOE_REQUIRE(form != 1 || KW == 4, "pack_weight: phase form needs a 4-tap kernel");
+    unsigned grid = (unsigned)ceil_div64(total, 256);
+    if (dst_dtype == MOPOE_F32)
+        pack_weight_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(W, A, B, KH, KW, form, py, px, bpad, (float*)dst, total);
+    else
+        pack_weight_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(W, A, B, KH, KW, form, py, px, bpad, (bf16*)dst, total);
+    MOPOE_CHECK_LAUNCH("pack_weight");
+    return 0;
+}
+
+// ---- device-side step state: keeps the whole training step capturable in a CUDA graph ------------------------------
+// state[0] = step count (as float bits in an int), adam_coef[0] = lr / (1 - b1^t), adam_coef[1] = 1 / sqrt(1 - b2^t)
+__global__ void step_advance_kernel(unsigned long long* rng_step, int* adam_step, float* adam_coef, float lr, float b1, float b2) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (rng_step) rng_step[0] += 1ull;
+        if (adam_step) {
+            int t = adam_step[0] + 1;
+            adam_step[0] = t;
+            double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+            adam_coef[0] = (float)((double)lr / bc1);
+            adam_coef[1] = (float)(1.0 / sqrt(bc2));
+        }
+    }
+}
+extern "C" int mopoe_step_advance(uint64_t* rng_step, int32_t* adam_step, float* adam_coef, float lr, float beta1,
+                                  float beta2, void* stream) {
+    step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)rng_step, adam_step, adam_coef, lr, beta1, beta2);
+    MOPOE_CHECK_LAUNCH("step_advance");
     return 0;
 }

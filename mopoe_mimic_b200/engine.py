@@ -74,7 +74,54 @@ class Engine:
         self._ws64 = None
         self._wsf = None
         self.rng_offset = 0
-        self.profile = None      # list of (start_event, end_event, flops, kind) when bench.py instruments a step
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)   # device-side training-step counter
+        self._packs = {}
+        self.profile = None     # list of (start_event, end_event, flops, kind) when bench.py instruments a step
+
+    # ---- packed-weight cache: each re-layout is computed once per optimizer step (forward and backward share it)
+    def packed(self, Wg, form, bpad=None):
+        """GEMM-operand re-layout of an fp32 master weight (mopoe_pack_weight), cached until the weights change"""
+        key = (Wg.data_ptr(), Wg._version, form, bpad, self.dtype)
+        hit = self._packs.get(key)
+        if hit is None:
+            W = Wg.detach()
+            assert W.dtype == torch.float32 and W.is_contiguous()
+            A, B = W.shape[0], W.shape[1]
+            KH, KW = (1, 1) if W.dim() == 2 else ((1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3]))
+            code = L.dtype_code(self.dtype)
+
+            def run(fcode, shape, py=0, px=0):
+                dst = torch.empty(shape, dtype=self.dtype, device=self.device)
+                L.call('mopoe_pack_weight', L.ptr(W), A, B, KH, KW, fcode, py, px, bpad or B, L.ptr(dst), code,
+                       L.stream_ptr())
+                return dst
+            if form == 'conv':
+                hit = run(0, (A, KH * KW * (bpad or B)))
+            elif form == 'phase':
+                if KH > 1:
+                    hit = [run(1, (B, 4 * A), py, px) for py in range(2) for px in range(2)]
+                else:
+                    hit = [run(1, (B, 2 * A), 0, px) for px in range(2)]
+            elif form == 'full':
+                hit = run(2, (KH * KW * B, A))
+            elif form == 'mat':        # [n, k] from a 1x1 kernel / linear weight [n, k, 1(, 1)]
+                assert KH == 1 and KW == 1
+                hit = run(3, (A, B))
+            elif form == 'matT':
+                assert KH == 1 and KW == 1
+                hit = run(4, (B, A))
+            else:
+                raise ValueError(form)
+            self._packs[key] = hit
+        return hit
+
+    def begin_step(self):
+        """same within-step Philox offsets every step; the device-side step counter makes the draws differ"""
+        self.rng_offset = 0
+
+    def invalidate_packs(self):
+        """call after the parameters changed in place behind torch's back (the flat Adam kernel)"""
+        self._packs.clear()
 
     # ---- scratch ------------------------------------------------------------------------------------
     def ws64(self, n):
@@ -152,7 +199,8 @@ class Engine:
 
     def dropout_mask(self, n, seed):
         m = torch.empty(n, dtype=torch.uint8, device=self.device)
-        L.call('mopoe_dropout_mask', L.ptr(m), n, int(seed) & (2 ** 64 - 1), self.rng_offset, L.stream_ptr())
+        L.call('mopoe_dropout_mask', L.ptr(m), n, int(seed) & (2 ** 64 - 1), self.rng_offset, L.ptr(self.rng_step),
+               L.stream_ptr())
         self.rng_offset += (n + 127) // 128
         return m
 

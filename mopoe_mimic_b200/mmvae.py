@@ -158,7 +158,9 @@ class BaseMMVae(nn.Module):
         else:
             latents['mus'] = sub_mu[st[0]:st[-1] + 1] if st == list(range(st[0], st[-1] + 1)) else sub_mu[st]
             latents['logvars'] = sub_lv[st[0]:st[-1] + 1] if st == list(range(st[0], st[-1] + 1)) else sub_lv[st]
-        latents['weights'] = plan.weights.to(first.device)
+        if getattr(plan, 'weights_dev', None) is None or plan.weights_dev.device != first.device:
+            plan.weights_dev = plan.weights.to(first.device)       # once per plan (keeps the step graph-capturable)
+        latents['weights'] = plan.weights_dev
         latents['joint'] = [jmu, jlv]
         latents['subsets'] = distr_subsets
         # fused by-products (private): reparameterised sample, per-subset KLs, NaN flag

@@ -95,17 +95,27 @@ class FlatAdam:
         self.m = torch.zeros_like(self.p)
         self.v = torch.zeros_like(self.p)
         self.lr, self.betas, self.eps = lr, betas, eps
-        self.step_count = 0
         self.grad_scale = 1.0
+        dev = self.p.device
+        # step count and bias-correction coefficients live on the device: the step stays CUDA-graph capturable
+        self.step_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.coef = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    @property
+    def step_count(self):
+        return int(self.step_t.item())
 
     def zero_grad(self, set_to_none=False):
         self.g.zero_()
 
     def step(self):
-        self.step_count += 1
-        L.call('mopoe_adam_flat', L.ptr(self.p), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.p.numel(),
-               float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count,
-               float(self.grad_scale), L.stream_ptr())
+        eng = self.model.rt.eng(self.p.device)
+        L.call('mopoe_step_advance', L.ptr(eng.rng_step), L.ptr(self.step_t), L.ptr(self.coef), float(self.lr),
+               float(self.betas[0]), float(self.betas[1]), L.stream_ptr())
+        L.call('mopoe_adam_flat_dev', L.ptr(self.p), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.p.numel(),
+               L.ptr(self.coef), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.grad_scale),
+               L.stream_ptr())
+        eng.invalidate_packs()      # the kernel rewrote the weights in place: packed copies are stale
 
 
 def basic_routine_epoch(exp, batch):
@@ -133,6 +143,9 @@ def basic_routine_epoch(exp, batch):
 
 def train_step(exp, batch, allreduce=None):
     """run_epochs.train:118-131 for one batch: forward + loss, zero_grad, backward, (DP all-reduce), Adam."""
+    eng = exp.mm_vae.rt.engine
+    if eng is not None:
+        eng.begin_step()
     out = basic_routine_epoch(exp, batch)
     exp.optimizer.zero_grad()
     out['total_loss'].backward()
@@ -140,6 +153,52 @@ def train_step(exp, batch, allreduce=None):
         allreduce(exp.mm_vae.flat_grads)
     exp.optimizer.step()
     return out
+
+
+class GraphedTrainStep:
+    """The whole training step (forward, ELBO, backward, DP all-reduce, Adam) captured ONCE into a CUDA graph and
+    replayed per batch: ~1000 kernel launches become one graph launch, so the host never gates the device.
+
+    Everything step-dependent lives in device memory (dropout step counter, Adam step / bias corrections), the
+    batch is copied into static input buffers, and the scalars the reference logs come back as one packed vector.
+    The NaN-in-latent guard (utils.check_latents) is read from `nan_flag` after the replay instead of mid-step."""
+
+    def __init__(self, exp, example_batch, allreduce=None, warmup=2):
+        flags = exp.flags
+        dev = flags.device
+        self.exp = exp
+        self.static = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in example_batch.items()}
+        for k, v in example_batch.items():
+            self.static[k].copy_(v)
+        saved_dataset = flags.dataset
+        flags.dataset = 'testing'            # no mid-step .item() while capturing; the flag is checked after replay
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                train_step(exp, (dict(self.static), None), allreduce)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        mode = 'thread_local' if allreduce is not None else 'global'
+        with torch.cuda.graph(self.graph, capture_error_mode=mode):
+            out = train_step(exp, (dict(self.static), None), allreduce)
+            self.stats = packed_stats(out)
+            self.nan_flag = out['results']['latents']['_nan_flag']
+        flags.dataset = saved_dataset
+        self.keys = (['total_loss', 'joint_divergence'] + ['kld.' + k for k in out['klds']]
+                     + ['log_prob.' + k for k in out['log_probs']])
+
+    def __call__(self, batch):
+        for k, t in self.static.items():
+            t.copy_(batch[k], non_blocking=True)
+        self.graph.replay()
+        return self.stats
+
+    def check_latents(self):
+        if self.exp.flags.dataset != 'testing' and int(self.nan_flag.item()) != 0:
+            raise NaNInLatent('The latent representations contain NaNs')
 
 
 def packed_stats(out):
