@@ -235,7 +235,7 @@ class MMVaeMimic(BaseMMVae):
         if m_key == 'text':
             return CategoricalLikelihood(scores=dec(None, z)[0], eng=eng)
         loc, scale = dec(None, z)
-        return LaplaceLikelihood(loc, scale, eng=eng)
+        return LaplaceLikelihood(loc, scale, eng=eng, scale_value=0.75)   # ConvNetworksImgMimic.py:54
 
     def forward(self, input_batch):
         """VAEtrimodalMimic.forward:31-62; absent modalities are skipped in the decode loop (the intended

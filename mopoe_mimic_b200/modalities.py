@@ -15,9 +15,15 @@ from .blocks import CategoricalLogProbSumFn, LaplaceLogProbSumFn, log_softmax_ro
 class LaplaceLikelihood:
     """dist.Laplace(loc, scale) stand-in.  scale is the constant 0.75 tensor the decoder returns."""
 
-    def __init__(self, loc, scale, eng=None):
+    def __init__(self, loc, scale, eng=None, scale_value=None):
         self.loc, self.scale, self._eng = loc, scale, eng
-        self._scale_f = float(scale) if not torch.is_tensor(scale) or scale.numel() == 1 else None
+        # scale_value: the host copy of the (constant) scale — avoids a device->host sync per forward
+        if scale_value is not None:
+            self._scale_f = float(scale_value)
+        elif not torch.is_tensor(scale):
+            self._scale_f = float(scale)
+        else:
+            self._scale_f = float(scale) if scale.numel() == 1 and not scale.is_cuda else None
 
     @property
     def mean(self):
