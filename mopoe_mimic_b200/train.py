@@ -176,7 +176,7 @@ class GraphedTrainStep:
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            for _ in range(warmup):
+            for _ in range(max(1, warmup)):   # >= 1: allocates workspaces / plans / tensor-map entry points eagerly
                 train_step(exp, (dict(self.static), None), allreduce)
         cur.wait_stream(side)
         torch.cuda.synchronize()

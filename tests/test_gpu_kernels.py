@@ -1,0 +1,208 @@
+"""Kernel-level GPU tests through the C ABI: fused MoPoE kernel (bit-exact selection / subset order), likelihood
+reductions, flat Adam, dropout masks, CUDA-graph step, and size-independent properties at BASELINE.json's full
+batch sizes."""
+import math
+
+import pytest
+import torch
+
+from oracle import mopoe_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _eng():
+    from mopoe_mimic_b200.engine import Engine
+    return Engine('cuda', torch.float32)
+
+
+def _fusion(mods, method, B, D, norm, mus, lvs, eps):
+    from mopoe_mimic_b200.fusion import FusionFn, FusionPlan
+    sub = O.subset_keys(mods)
+    plan = FusionPlan(list(mods), list(mods), list(sub.keys()), list(sub.values()), method, B, D, norm)
+    out = FusionFn.apply(plan, _eng(), eps.cuda(), *[m.cuda().requires_grad_(True) for m in mus],
+                         *[l.cuda().requires_grad_(True) for l in lvs])
+    return plan, out
+
+
+@pytest.mark.parametrize('method', ['joint_elbo', 'moe', 'poe'])
+@pytest.mark.parametrize('mods,B,D', [(('PA', 'Lateral', 'text'), 16, 128), (('PA', 'text'), 256, 128),
+                                      (('PA', 'Lateral', 'text'), 37, 64), (('PA', 'Lateral', 'text'), 256, 512)])
+def test_fusion_forward_backward_vs_oracle(method, mods, B, D):
+    g = torch.Generator().manual_seed(B + D)
+    mus = [torch.randn(B, D, generator=g) for _ in mods]
+    lvs = [torch.randn(B, D, generator=g) * 0.5 for _ in mods]
+    eps = torch.randn(B, D, generator=g)
+    fl = O.default_flags(batch_size=B, class_dim=D, mods=mods, method=method)
+    enc = {m: (mus[i].clone().requires_grad_(True), lvs[i].clone().requires_grad_(True)) for i, m in enumerate(mods)}
+    lat = O.inference(enc, fl, list(mods))
+    plan, out = _fusion(mods, method, B, D, B, mus, lvs, eps)
+    sub_mu, sub_lv, jmu, jlv, z, kl, flag = out
+    # subset order bit-exact, values fp32-close
+    assert plan.keys == list(lat['subsets'].keys())
+    for i, k in enumerate(plan.keys):
+        torch.testing.assert_close(sub_mu[i].cpu(), lat['subsets'][k][0].detach(), rtol=2e-5, atol=2e-6)
+        torch.testing.assert_close(sub_lv[i].cpu(), lat['subsets'][k][1].detach(), rtol=2e-5, atol=2e-6)
+    # joint mixture: every row must be a BIT-EXACT copy of the owning subset's row (selection is pure indexing)
+    starts, ends = O.selection_bounds(B, [1.0 / len(plan.stacked)] * len(plan.stacked))
+    assert plan.sel_end == ends
+    for j, s in enumerate(plan.stacked):
+        assert torch.equal(jmu[starts[j]:ends[j]], sub_mu[s, starts[j]:ends[j]])
+        assert torch.equal(jlv[starts[j]:ends[j]], sub_lv[s, starts[j]:ends[j]])
+    torch.testing.assert_close(jmu.cpu(), lat['joint'][0].detach(), rtol=2e-5, atol=2e-6)
+    z_ref = eps * torch.exp(0.5 * lat['joint'][1]) + lat['joint'][0]
+    torch.testing.assert_close(z.cpu(), z_ref.detach(), rtol=2e-5, atol=2e-6)
+    kl_ref = torch.stack([O.kl_to_standard_normal(m_, l_, B) for m_, l_ in lat['subsets'].values()])
+    torch.testing.assert_close(kl.cpu(), kl_ref.detach().float(), rtol=2e-5, atol=1e-5)
+    assert int(flag.item()) == 0
+
+
+def test_fusion_gradients_vs_oracle():
+    from mopoe_mimic_b200.fusion import FusionFn, FusionPlan
+    mods, B, D = ('PA', 'Lateral', 'text'), 24, 64
+    for method in ('joint_elbo', 'moe', 'poe'):
+        g = torch.Generator().manual_seed(7)
+        mus = [torch.randn(B, D, generator=g) for _ in mods]
+        lvs = [torch.randn(B, D, generator=g) * 0.5 for _ in mods]
+        eps = torch.randn(B, D, generator=g)
+        gz = torch.randn(B, D, generator=g)
+        fl = O.default_flags(batch_size=B, class_dim=D, mods=mods, method=method)
+        cm = [m.clone().requires_grad_(True) for m in mus]
+        cl = [l.clone().requires_grad_(True) for l in lvs]
+        lat = O.inference({m: (cm[i], cl[i]) for i, m in enumerate(mods)}, fl, list(mods))
+        ck = torch.rand(len(lat['subsets']), generator=g)
+        z_ref = eps * torch.exp(0.5 * lat['joint'][1]) + lat['joint'][0]
+        kl_ref = torch.stack([O.kl_to_standard_normal(m_, l_, B) for m_, l_ in lat['subsets'].values()])
+        ((z_ref * gz).sum() + (kl_ref * ck).sum()).backward()
+        sub = O.subset_keys(mods)
+        plan = FusionPlan(list(mods), list(mods), list(sub.keys()), list(sub.values()), method, B, D, B)
+        gm = [m.cuda().requires_grad_(True) for m in mus]
+        gl = [l.cuda().requires_grad_(True) for l in lvs]
+        out = FusionFn.apply(plan, _eng(), eps.cuda(), *gm, *gl)
+        ((out[4] * gz.cuda()).sum() + (out[5] * ck.cuda()).sum()).backward()
+        for i in range(len(mods)):
+            torch.testing.assert_close(gm[i].grad.cpu(), cm[i].grad, rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(gl[i].grad.cpu(), cl[i].grad, rtol=1e-4, atol=1e-5)
+
+
+def test_fusion_nan_flag():
+    mods, B, D = ('PA', 'text'), 8, 32
+    mus = [torch.zeros(B, D) for _ in mods]
+    lvs = [torch.zeros(B, D) for _ in mods]
+    mus[1][3, 5] = float('nan')
+    plan, out = _fusion(mods, 'joint_elbo', B, D, B, mus, lvs, torch.zeros(B, D))
+    assert int(out[6].item()) == 1
+
+
+@pytest.mark.parametrize('n', [1, 7, 4096, 16 * 128 * 128, 256 * 128 * 128])
+def test_laplace_logprob_sum_and_grad(n):
+    from mopoe_mimic_b200.blocks import LaplaceLogProbSumFn
+    g = torch.Generator().manual_seed(n)
+    loc = torch.randn(n, generator=g)
+    x = torch.rand(n, generator=g)
+    ref_loc = loc.double().requires_grad_(True)
+    ref = O.laplace_log_prob_sum(ref_loc, x.double())
+    ref.backward()
+    l = loc.cuda().requires_grad_(True)
+    out = LaplaceLogProbSumFn.apply(l, x.cuda(), 0.75, _eng())
+    (out * 0.33).backward()
+    assert abs(float(out) - float(ref)) <= 2e-6 * abs(float(ref))
+    assert torch.equal(torch.sign(l.grad.cpu()), torch.sign(ref_loc.grad).float())     # sign() decisions bit-exact
+    torch.testing.assert_close(l.grad.cpu(), (ref_loc.grad * 0.33).float(), rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize('rows,V', [(1, 71), (1024, 71), (16 * 1024, 71), (333, 5), (64, 256)])
+def test_categorical_logprob_sum_and_grad(rows, V):
+    from mopoe_mimic_b200.blocks import CategoricalLogProbSumFn, log_softmax_rows
+    g = torch.Generator().manual_seed(rows + V)
+    y = torch.randn(rows, V, generator=g) * 3
+    idx = torch.randint(0, V, (rows,), generator=g)
+    tgt = torch.nn.functional.one_hot(idx, V).float()
+    yr = y.double().requires_grad_(True)
+    ref = O.categorical_log_prob_sum(torch.log_softmax(yr, -1), tgt.double())
+    ref.backward()
+    yc = y.cuda().requires_grad_(True)
+    out = CategoricalLogProbSumFn.apply(yc.view(1, rows, V), tgt.cuda().view(1, rows, V), _eng())
+    out.backward()
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-5
+    torch.testing.assert_close(yc.grad.cpu(), yr.grad.float(), rtol=1e-4, atol=1e-6)
+    ls = log_softmax_rows(y.cuda(), _eng())
+    torch.testing.assert_close(ls.cpu(), torch.log_softmax(y, -1), rtol=1e-5, atol=1e-5)
+
+
+def test_flat_adam_matches_oracle_adam():
+    from mopoe_mimic_b200 import _lib as L
+    n = 100003
+    g0 = torch.Generator().manual_seed(3)
+    p = torch.randn(n, generator=g0)
+    ref_p, ref_m, ref_v = {'w': p.clone()}, {'w': torch.zeros(n)}, {'w': torch.zeros(n)}
+    n_pad = (n + 3) // 4 * 4
+    dp = torch.zeros(n_pad, device='cuda')
+    dp[:n] = p.cuda()
+    dg, dm, dv = torch.zeros_like(dp), torch.zeros_like(dp), torch.zeros_like(dp)
+    step_t = torch.zeros(1, dtype=torch.int32, device='cuda')
+    coef = torch.zeros(2, device='cuda')
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=g0)
+        O.adam_step(ref_p, {'w': grad}, ref_m, ref_v, step)
+        dg[:n] = grad.cuda()
+        L.call('mopoe_step_advance', None, L.ptr(step_t), L.ptr(coef), 1e-3, 0.9, 0.999, L.stream_ptr())
+        L.call('mopoe_adam_flat_dev', L.ptr(dp), L.ptr(dg), L.ptr(dm), L.ptr(dv), n_pad, L.ptr(coef), 0.9, 0.999, 1e-8,
+               1.0, L.stream_ptr())
+    torch.testing.assert_close(dp[:n].cpu(), ref_p['w'], rtol=1e-5, atol=1e-7)
+    assert int(step_t.item()) == 3
+
+
+def test_dropout_mask_is_fair_and_step_dependent():
+    eng = _eng()
+    n = 1 << 20
+    m0 = eng.dropout_mask(n, 1234)
+    eng.rng_offset = 0
+    m_same = eng.dropout_mask(n, 1234)
+    assert torch.equal(m0, m_same)                      # counter-based: same (seed, offset, step) -> same bits
+    eng.rng_offset = 0
+    eng.rng_step += 1
+    m1 = eng.dropout_mask(n, 1234)
+    assert set(m0.unique().tolist()) <= {0, 1}
+    assert abs(float(m0.float().mean()) - 0.5) < 5e-3
+    assert abs(float((m0 != m1).float().mean()) - 0.5) < 5e-3
+
+
+def test_graphed_step_equals_eager_steps():
+    """The CUDA-graph replay must produce the same training trajectory as launching every kernel from the host."""
+    import mopoe_mimic_b200 as P
+    kw = dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32)
+    ofl = O.default_flags(**kw)
+    state = O.make_state(ofl, 0, torch.float32)
+    batch = {k: v.cuda() for k, v in O.make_batch(ofl, 1, torch.float32).items()}
+    losses = []
+    for graphed in (False, True):
+        torch.manual_seed(5)
+        exp = P.Experiment(P.default_flags(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, compute_dtype='fp32'))
+        exp.mm_vae.load_state_dict(state)
+        exp.set_optimizer()
+        exp.mm_vae.train()
+        exp.mm_vae.rt.seed = 99
+        exp.mm_vae.rt.injected_eps = torch.zeros(8, 32, device='cuda')
+        seq = []
+        if graphed:
+            gs = P.GraphedTrainStep(exp, batch, warmup=1)       # step 1 runs eagerly; capture itself executes nothing
+            for _ in range(2):
+                seq.append(float(gs(batch)[0]))                 # steps 2 and 3 are graph replays
+        else:
+            for _ in range(3):
+                seq.append(float(P.train_step(exp, (dict(batch), None))['total_loss']))
+            seq = seq[1:]
+        losses.append(seq)
+    assert losses[0][0] == pytest.approx(losses[1][0], rel=1e-4)
+    assert losses[0][1] == pytest.approx(losses[1][1], rel=1e-4)
+    assert losses[0][1] != losses[0][0]
+
+
+@pytest.mark.parametrize('B,S', [(256, 7), (1024, 7), (2048, 7), (128, 3), (64, 7)])
+def test_full_size_selection_ranges(B, S):
+    """BASELINE.json batch sizes: k * floor(B/S) boundaries, identical to the oracle's."""
+    from mopoe_mimic_b200.fusion import selection_ends, uniform_weights
+    ends = selection_ends(B, uniform_weights(S))
+    assert ends == O.selection_bounds(B, [1.0 / S] * S)[1]
+    assert ends[:-1] == [(k + 1) * (B // S) for k in range(S - 1)] and ends[-1] == B

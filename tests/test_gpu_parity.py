@@ -1,0 +1,187 @@
+"""GPU parity tests proper: the product (CUDA through the C ABI) against the CPU oracle on the same seeded
+inputs / weights / injected noise, and against the committed golden fixtures (reference outputs, fp64).
+
+Tolerances (BASELINE.json north_star): fp32 validation mode rtol 1e-5 on forward quantities (per-subset
+mu/logvar, KLDs, log-probs, loss); gradients are compared per tensor as max-abs error / max-abs value with a
+floor of 1e-4 of the largest gradient (conv biases feeding a train-mode BatchNorm have an analytically ZERO
+gradient, i.e. pure rounding noise in both implementations) — the L1 (Laplace) likelihood and the ReLU gates make
+the loss piecewise linear, so fp32 rounding flips a few sign()/gate decisions and bounds what any fp32
+implementation (the reference's included) can reproduce: the oracle's own fp32-vs-fp64 gap is measured in the same
+test and the product must stay within a small multiple of it.  bf16 mode: rtol 1e-2 on the loss terms, 3e-2 on
+latents.  Subset order and mixture-selection row ranges: bit-exact.
+"""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import mopoe_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32)
+CASES = {
+    'tri_joint': dict(SMALL),
+    'tri_moe': dict(SMALL, method='moe'),
+    'tri_poe': dict(SMALL, method='poe', batch_size=6),
+    'patext_joint': dict(SMALL, mods=('PA', 'text')),
+    'patext_moe': dict(SMALL, mods=('PA', 'text'), method='moe'),
+    'patext_poe': dict(SMALL, mods=('PA', 'text'), method='poe', batch_size=5),
+    'tri_64px': dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=16, img_size=64),
+}
+
+
+def _forward_errs(errs):
+    return {k: v for k, v in errs.items() if not k.startswith('grad.') and k != '_worst_grad'}
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_fp32_step_matches_oracle(name):
+    kw = CASES[name]
+    ofl, state, batch, noise = H.make_case(kw)
+    orc = H.run_oracle(ofl, state, batch, noise)
+    exp, out, grads = H.run_product(ofl, state, batch, noise, 'fp32')
+    errs = H.compare_step(orc, out, grads)
+    fwd = _forward_errs(errs)
+    assert max(fwd.values()) < 1e-5, sorted(fwd.items(), key=lambda kv: -kv[1])[:5]
+    # subset enumeration order: bit-exact
+    assert list(out['results']['latents']['subsets'].keys()) == list(orc['results']['latents']['subsets'].keys())
+    g = sorted(v for k, v in errs.items() if k.startswith('grad.'))
+    assert g[len(g) // 2] < 5e-5, 'median gradient error %.2e' % g[len(g) // 2]
+    assert g[-1] < 5e-2, errs['_worst_grad']
+
+
+def test_fp32_ragged_last_batch():
+    """flags.batch_size stays the nominal 8 while the tensors hold 5 rows (last batch of an epoch): every
+    normalisation uses flags.batch_size and the joint mixture gives all rows to the last subset."""
+    ofl, state, batch, noise = H.make_case(dict(SMALL), actual_batch=5)
+    orc = H.run_oracle(ofl, state, batch, noise)
+    exp, out, grads = H.run_product(ofl, state, batch, noise, 'fp32')
+    fwd = _forward_errs(H.compare_step(orc, out, grads))
+    assert max(fwd.values()) < 1e-5, sorted(fwd.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_fp32_against_golden_reference_and_fp32_noise_floor(golden_dir):
+    """Product (fp32) and oracle (fp32) both measured against the REFERENCE's fp64 outputs (golden fixture):
+    the product may not be further from the truth than 4x the oracle's own fp32 rounding gap (+1e-6)."""
+    fx = torch.load(os.path.join(golden_dir, 'small_tri_joint.pt'), weights_only=False)
+    ofl, state, batch, noise = H.make_case(fx['flags'], fx['actual_batch'])
+    orc = H.run_oracle(ofl, state, batch, noise)
+    exp, out, grads = H.run_product(ofl, state, batch, noise, 'fp32')
+
+    def rel(a, ref):
+        return abs(float(a) - ref) / abs(ref)
+    for key, ref in [('total_loss', fx['total_loss'])]:
+        assert rel(out[key], ref) < 1e-5 and rel(out[key], ref) <= 4 * rel(orc[key], ref) + 1e-6
+    for k, ref in fx['klds'].items():
+        assert rel(out['klds'][k], ref) <= 4 * rel(orc['klds'][k], ref) + 2e-6, k
+    for k, ref in fx['log_probs'].items():
+        assert rel(out['log_probs'][k], ref) <= 4 * rel(orc['log_probs'][k], ref) + 2e-6, k
+    for k, (mu, lv) in fx['subsets'].items():
+        pm = out['results']['latents']['subsets'][k][0].double().cpu()
+        om = orc['results']['latents']['subsets'][k][0].double()
+        assert (pm - mu).abs().max() <= 4 * (om - mu).abs().max() + 1e-5 * mu.abs().max(), k
+    # gradient checksums: l2 norm of every parameter gradient vs the reference's
+    bad = []
+    for k, cs in fx['grads'].items():
+        ref = cs['l2']
+        floor = 1e-4 * fx['grad_scale'] * cs['numel'] ** 0.5
+        ep = abs(float(grads[k].double().norm()) - ref)
+        eo = abs(float(orc['grads'][k].double().norm()) - ref)
+        if ep > 4 * eo + 1e-3 * ref + floor:
+            bad.append((k, ep / (ref + floor), eo / (ref + floor)))
+    assert not bad, bad[:5]
+
+
+def test_bf16_step_close_to_oracle():
+    ofl, state, batch, noise = H.make_case(dict(batch_size=16, DIM_img=64, DIM_text=64, class_dim=64))
+    orc = H.run_oracle(ofl, state, batch, noise)
+    exp, out, grads = H.run_product(ofl, state, batch, noise, 'bf16')
+    errs = H.compare_step(orc, out, grads)
+    assert errs['total_loss'] < 1e-2
+    for k, v in errs.items():
+        if k.startswith(('kld.', 'logp.')):
+            assert v < 1e-2, (k, v)
+        if k.startswith(('enc_', 'sub_', 'joint', 'z', 'rec.')):
+            assert v < 3e-2, (k, v)
+    # gradients: direction must agree with the fp32 oracle (cosine over all parameters)
+    dot = nn = no = 0.0
+    for k, g in orc['grads'].items():
+        a, b = grads[k].double().reshape(-1), g.double().reshape(-1)
+        dot += float(a @ b)
+        nn += float(a @ a)
+        no += float(b @ b)
+    assert dot / (nn ** 0.5 * no ** 0.5) > 0.99
+
+
+def test_cfg1_full_size_against_golden(golden_dir):
+    """BASELINE.json configs[0]: PA+Lateral+text, 128 px, 1024-token reports, class_dim 128, batch 16, one step —
+    the reference's own CPU-runnable case, against the reference outputs committed in the fixture."""
+    fx = torch.load(os.path.join(golden_dir, 'cfg1_tri_128_b16_joint.pt'), weights_only=False)
+    ofl, state, batch, noise = H.make_case(fx['flags'], fx['actual_batch'])
+    exp, out, grads = H.run_product(ofl, state, batch, noise, 'fp32')
+    assert abs(float(out['total_loss']) - fx['total_loss']) < 1e-5 * abs(fx['total_loss'])
+    assert abs(float(out['results']['joint_divergence']) - fx['joint_divergence']) < 2e-5 * abs(fx['joint_divergence'])
+    for k, ref in fx['klds'].items():
+        assert abs(float(out['klds'][k]) - ref) < 2e-5 * abs(ref), k
+    for k, ref in fx['log_probs'].items():
+        assert abs(float(out['log_probs'][k]) - ref) < 1e-5 * abs(ref), k
+    assert list(out['klds'].keys()) == [k for k in fx['subset_keys'] if k]
+    for k, (mu, lv) in fx['subsets'].items():
+        got = out['results']['latents']['subsets'][k]
+        assert (got[0].double().cpu() - mu).abs().max() < 1e-4 * mu.abs().max(), k
+        assert (got[1].double().cpu() - lv).abs().max() < 1e-4 * lv.abs().max(), k
+    # gradient l2 norms within 1 % of the reference for every tensor whose gradient is not pure noise
+    bad = []
+    for k, cs in fx['grads'].items():
+        ref = cs['l2']
+        floor = 1e-4 * fx['grad_scale'] * cs['numel'] ** 0.5
+        e = abs(float(grads[k].double().norm()) - ref) / (ref + floor)
+        if e > 1e-2:
+            bad.append((k, e))
+    assert not bad, bad[:8]
+    # BN running statistics after the step
+    sd = exp.mm_vae.state_dict()
+    for k, cs in fx['bn'].items():
+        assert abs(float(sd[k].double().norm()) - cs['l2']) < 1e-4 * (cs['l2'] + 1e-6), k
+
+
+def test_eval_mode_forward_matches_oracle():
+    """eval(): running-stat BatchNorm, no dropout (the mask-free cross-check of SURVEY.md §8c)."""
+    import mopoe_mimic_b200 as P
+    ofl, state, batch, noise = H.make_case(dict(SMALL))
+    st = {k: v.clone() for k, v in state.items()}
+    for k in st:                       # non-trivial running statistics
+        if k.endswith('running_var'):
+            st[k] = st[k] * 1.7
+        if k.endswith('running_mean'):
+            st[k] = st[k] + 0.05
+    ref = O.forward(st, batch, ofl, None, noise[0][1], train=False)
+    fl = H.product_flags(ofl, 'fp32')
+    exp = P.Experiment(fl)
+    exp.mm_vae.load_state_dict(st)
+    exp.mm_vae.eval()
+    exp.mm_vae.rt.injected_eps = noise[0][1].cuda()
+    with torch.no_grad():
+        res = exp.mm_vae({k: v.cuda() for k, v in batch.items()})
+    for m in ofl.mods:
+        got = res['rec'][m]
+        t = got.loc if m != 'text' else got.logits
+        assert H.rel_err(t, ref['rec'][m]) < 2e-5, m
+    assert H.rel_err(res['joint_divergence'], ref['joint_divergence']) < 1e-5
+
+
+def test_state_dict_roundtrip_and_names(golden_dir):
+    import mopoe_mimic_b200 as P
+    fx = torch.load(os.path.join(golden_dir, 'small_tri_joint.pt'), weights_only=False)
+    ofl, state, batch, noise = H.make_case(fx['flags'])
+    exp = P.Experiment(H.product_flags(ofl, 'fp32'))
+    sd = exp.mm_vae.state_dict()
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s)) for k, s in fx['state_keys']]
+    exp.mm_vae.load_state_dict(state)
+    exp.set_optimizer()                # flattening must keep the values and the names
+    sd2 = exp.mm_vae.state_dict()
+    for k, v in state.items():
+        assert torch.equal(sd2[k].cpu(), v), k
