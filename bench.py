@@ -153,10 +153,8 @@ def main():
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
-    def allreduce(flat_g):
-        dist.all_reduce(flat_g)
-
-    ar = allreduce if world > 1 else None
+    from mopoe_mimic_b200.dp import FlatGradAllReduce
+    ar = FlatGradAllReduce() if world > 1 else None      # bucketed NCCL all-reduce of the flat gradient buffer
     stats_host = torch.empty(16, dtype=torch.float32).pin_memory()
     launches_per_step = None
     if args.no_graph or args.profile_kernels:

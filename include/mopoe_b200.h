@@ -115,6 +115,12 @@ int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float g
                        const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
                        const float* mean, const float* invstd, const float* gamma, const float* sums,
                        const mopoe_view_t* addend, const mopoe_view_t* out, void* stream);
+/* backward of `y = a*BN(r) + b*(c*2mask2)` in ONE pass over dy: dr = BN-backward of g = a*dy (sums from
+ * mopoe_bn_bwd_reduce), dc = b * dy * 2mask2; dr and dc must share their border widths. */
+int mopoe_combine_bwd_apply(const mopoe_view_t* dy, float a, const mopoe_view_t* r, const float* mean,
+                            const float* invstd, const float* gamma, const float* sums,
+                            const uint8_t* mask2, int mask2_mode, float b, const mopoe_view_t* dr,
+                            const mopoe_view_t* dc, void* stream);
 /* out = scale * dy * 2mask (+ zero border): dropout backward / the b*dropout2 branch. */
 int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int mask_mode, float scale,
                      const mopoe_view_t* out, void* stream);

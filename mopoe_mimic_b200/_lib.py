@@ -58,6 +58,7 @@ SIGNATURES = {
     'mopoe_combine': (_I, [_V, _P, _P, _P, _P, _V, _P, _I, _F, _F, _V, _P]),
     'mopoe_bn_bwd_reduce': (_I, [_V, _V, _F, _V, _P, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P]),
     'mopoe_bn_bwd_apply': (_I, [_V, _V, _F, _V, _P, _I, _P, _P, _P, _P, _V, _V, _P]),
+    'mopoe_combine_bwd_apply': (_I, [_V, _F, _V, _P, _P, _P, _P, _P, _I, _F, _V, _V, _P]),
     'mopoe_scale_mask': (_I, [_V, _P, _I, _F, _V, _P]),
     'mopoe_convert': (_I, [_V, _I, _V, _P]),
     'mopoe_dropout_mask': (_I, [_P, _L, C.c_uint64, C.c_uint64, _P, _P]),

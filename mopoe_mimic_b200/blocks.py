@@ -176,13 +176,15 @@ class ResBlockFn(torch.autograd.Function):
         G = {}
         # y = a*BN3(r) + b*(c*2m2)
         G[short + '.1.weight'], G[short + '.1.bias'] = eng.f32(sp.cout), eng.f32(sp.cout)
-        dr = eng.bn_bwd(dy, None, sp.a, r, None, L.MASK_NONE, st3, P[short + '.1.weight'], G[short + '.1.weight'],
-                        G[short + '.1.bias'], None, Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device))
-        dc = eng.scale_mask(dy, m2, mode, sp.b, Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device))
+        dr, dc = eng.combine_bwd(dy, sp.a, r, st3, P[short + '.1.weight'], G[short + '.1.weight'], G[short + '.1.bias'],
+                                 m2, mode, sp.b, Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device),
+                                 Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device))
         # shortcut conv
         Ws_ = P[short + '.0.weight']
         G[short + '.0.weight'] = _main_wgrad(eng, sp, x, dr, Ws_.shape)
-        G[short + '.0.bias'] = eng.colsum(dr)
+        # the shortcut bias feeds a train-mode BatchNorm: its gradient sum(dr) is analytically zero (BN backward
+        # output sums to zero per channel); the reference only accumulates rounding noise there
+        G[short + '.0.bias'] = torch.zeros(sp.cout, dtype=torch.float32, device=eng.device)
         dxs = _main_dgrad(eng, sp, dr, Ws_, dt, H, W)
         # conv2
         W2 = P['conv2.weight']

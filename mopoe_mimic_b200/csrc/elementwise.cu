@@ -1,11 +1,12 @@
 // elementwise.cu — HBM-bound passes of the residual blocks: training-mode BatchNorm statistics,
 // fused BN+ReLU(+dropout) apply, residual combine, their backward halves, layout conversion,
-// dropout-mask generation and the flat Adam update.
+// dropout-mask generation, weight re-layout and the flat Adam update.
 //
-// All kernels address activations through channels-last views (4 consecutive channels per thread,
-// so a warp touches 512 B (fp32) / 256 B (bf16) contiguous per pixel row) and accumulate reductions
-// in fp64 with a fixed two-stage order (per-chunk partials, then one thread per channel sums the
-// chunks in order) — run-to-run deterministic, no atomics.
+// All streaming kernels address activations through channels-last views; one thread owns 8 consecutive
+// channels of one pixel (16-byte bf16 / 2x16-byte fp32 vector accesses, a warp covers 256 channels-pixels
+// contiguously), index math is 32-bit, and every reduction accumulates short fp32 strips into fp64 with a
+// fixed two-stage order (per-chunk partials, then one warp per channel sums the chunks lane-strided) —
+// run-to-run deterministic, no atomics.
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -19,9 +20,9 @@ void mopoe_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 extern "C" const char* mopoe_last_error(void) { return g_err; }
-extern "C" int mopoe_version(void) { return 100; }
+extern "C" int mopoe_version(void) { return 101; }
 
-constexpr int VEC = 4;
+constexpr int VEC = 8;
 constexpr int EW_THREADS = 256;
 
 static int check_same(const mopoe_view_t* a, const mopoe_view_t* b, const char* what) {
@@ -31,20 +32,66 @@ static int check_same(const mopoe_view_t* a, const mopoe_view_t* b, const char* 
     return 0;
 }
 
-// decode a flat index over the STORAGE of `o` (interior + border) into coordinates
 template <typename T>
-__device__ __forceinline__ bool decode_storage(const DView<T>& o, long long idx, int& b, int& h, int& w, int& c) {
-    const int CV = o.C / VEC;
-    const int Ws = o.W + 2 * o.pw, Hs = o.H + 2 * o.ph;
-    c = (int)(idx % CV) * VEC;
-    long long pos = idx / CV;
-    int ws = (int)(pos % Ws);
+__device__ __forceinline__ void ld8v(const T* p, float (&o)[8]) {
+    if constexpr (sizeof(T) == 2) {
+        uint4 t = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[2 * i] = __low2float(h[i]); o[2 * i + 1] = __high2float(h[i]); }
+    } else {
+        float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void st8v(T* p, const float (&o)[8]) {
+    if constexpr (sizeof(T) == 2) {
+        uint4 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = t;
+    } else {
+        reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+__device__ __forceinline__ void ld8f(const float* p, float (&o)[8]) { ld8v<float>(p, o); }
+// keep-mask bytes -> multiplier 2 (keep) / 0 (drop); bc_idx / el_idx are element indices into the mask
+__device__ __forceinline__ void ldmask8(const uint8_t* m, int mode, long long bc_idx, long long el_idx, float (&o)[8]) {
+    if (mode == MOPOE_MASK_NONE) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 1.f;
+    } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(m + (mode == MOPOE_MASK_BC ? bc_idx : el_idx));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[i] = ((t.x >> (8 * i)) & 0xffu) ? 2.f : 0.f;
+            o[4 + i] = ((t.y >> (8 * i)) & 0xffu) ? 2.f : 0.f;
+        }
+    }
+}
+
+// position of a flat thread index over the STORAGE (interior + zero border) of an output view
+struct Pos {
+    int b, h, w, c;
+    bool interior;
+};
+template <typename T>
+__device__ __forceinline__ Pos decode_storage(const DView<T>& o, unsigned idx) {
+    const unsigned CV = (unsigned)o.C / VEC, Ws = (unsigned)(o.W + 2 * o.pw), Hs = (unsigned)(o.H + 2 * o.ph);
+    Pos p;
+    p.c = (int)(idx % CV) * VEC;
+    unsigned pos = idx / CV;
+    const unsigned ws = pos % Ws;
     pos /= Ws;
-    int hs = (int)(pos % Hs);
-    b = (int)(pos / Hs);
-    h = hs - o.ph;
-    w = ws - o.pw;
-    return h >= 0 && h < o.H && w >= 0 && w < o.W;
+    const unsigned hs = pos % Hs;
+    p.b = (int)(pos / Hs);
+    p.h = (int)hs - o.ph;
+    p.w = (int)ws - o.pw;
+    p.interior = p.h >= 0 && p.h < o.H && p.w >= 0 && p.w < o.W;
+    return p;
 }
 template <typename T>
 static long long storage_threads(const DView<T>& o) {
@@ -54,10 +101,16 @@ template <typename T>
 __device__ __forceinline__ long long vaddr(const DView<T>& v, int b, int h, int w, int c) {
     return (long long)b * v.sB + (long long)h * v.sH + (long long)w * v.sW + c;
 }
+static int apply_grid(long long total, unsigned& grid) {
+    MOPOE_REQUIRE(total > 0 && total < (1ll << 32), "elementwise: %lld work items do not fit 32-bit indexing", total);
+    grid = (unsigned)ceil_div64(total, EW_THREADS);
+    return 0;
+}
 
 // ---- per-channel reductions (BN stats, BN backward sums, bias gradient) ------------------------------
-// block = (32 channel-vec lanes, 8 row lanes); grid = (ceil(C/128), nchunk)
+// block = (16 channel-octet lanes, 16 row lanes); grid = (ceil(C/128), nchunk)
 enum { RED_STATS = 0, RED_BNBWD = 1, RED_COLSUM = 2 };
+constexpr int RED_ROWS = 16;
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DView<const T> dy, DView<const T> gate,
@@ -65,73 +118,77 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
                                                           int mask_mode, const float* mean, const float* invstd,
                                                           double* ws, int nchunk) {
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int c = (blockIdx.x * 32 + tx) * VEC;
+    const int c = (blockIdx.x * 16 + tx) * VEC;
     const bool cvalid = c < x.C;
-    const long long rows = (long long)x.B * x.H * x.W;
-    const long long rpc = (rows + nchunk - 1) / nchunk;
-    const long long r0 = (long long)blockIdx.y * rpc;
-    const long long r1 = min(rows, r0 + rpc);
+    const unsigned rows = (unsigned)x.B * x.H * x.W;
+    const unsigned rpc = (rows + nchunk - 1) / nchunk;
+    const unsigned r0 = blockIdx.y * rpc;
+    const unsigned r1 = min(rows, r0 + rpc);
     double s0[VEC], s1[VEC];
+    float f0[VEC], f1[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) s0[i] = s1[i] = 0.0;
+    for (int i = 0; i < VEC; ++i) { s0[i] = s1[i] = 0.0; f0[i] = f1[i] = 0.f; }
     float mu[VEC], is[VEC];
     if (MODE == RED_BNBWD && cvalid) {
-        ldv<VEC>(mean + c, mu);
-        ldv<VEC>(invstd + c, is);
+        ld8f(mean + c, mu);
+        ld8f(invstd + c, is);
     }
     if (cvalid) {
-        for (long long r = r0 + ty; r < r1; r += 8) {
-            int w = (int)(r % x.W);
-            long long t = r / x.W;
-            int h = (int)(t % x.H);
-            int b = (int)(t / x.H);
+        int strip = 0;
+        for (unsigned r = r0 + ty; r < r1; r += RED_ROWS) {
+            const unsigned w = r % (unsigned)x.W;
+            const unsigned t = r / (unsigned)x.W;
+            const unsigned h = t % (unsigned)x.H;
+            const unsigned b = t / (unsigned)x.H;
             float xv[VEC], mk[VEC];
-            ldv<VEC>(x.p + vaddr(x, b, h, w, c), xv);
-            ldmask<VEC>(mask, mask_mode, (long long)b * x.C + c, r * x.C + c, mk);
+            ld8v<T>(x.p + vaddr(x, b, h, w, c), xv);
+            ldmask8(mask, mask_mode, (long long)b * x.C + c, (long long)r * x.C + c, mk);
             if (MODE == RED_STATS) {
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
-                    double v = (double)(xv[i] * mk[i]);
-                    s0[i] += v;
-                    s1[i] += v * v;
+                    const float v = xv[i] * mk[i];
+                    f0[i] += v;
+                    f1[i] = fmaf(v, v, f1[i]);
                 }
             } else if (MODE == RED_COLSUM) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) s0[i] += (double)xv[i];
+                for (int i = 0; i < VEC; ++i) f0[i] += xv[i];
             } else {
                 float g[VEC], gt[VEC];
-                ldv<VEC>(dy.p + vaddr(dy, b, h, w, c), g);
-                if (has_gate) ldv<VEC>(gate.p + vaddr(gate, b, h, w, c), gt);
+                ld8v<T>(dy.p + vaddr(dy, b, h, w, c), g);
+                if (has_gate) ld8v<T>(gate.p + vaddr(gate, b, h, w, c), gt);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) {
                     float gg = gscale * g[i];
                     if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
-                    float xh = (xv[i] * mk[i] - mu[i]) * is[i];
-                    s0[i] += (double)gg;
-                    s1[i] += (double)gg * (double)xh;
+                    const float xh = (xv[i] * mk[i] - mu[i]) * is[i];
+                    f0[i] += gg;
+                    f1[i] = fmaf(gg, xh, f1[i]);
                 }
+            }
+            if (++strip == 32) {      // fp32 strips of 32 rows, folded into fp64
+                strip = 0;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { s0[i] += (double)f0[i]; s1[i] += (double)f1[i]; f0[i] = f1[i] = 0.f; }
             }
         }
     }
-    __shared__ double sm[2][8][32][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { s0[i] += (double)f0[i]; s1[i] += (double)f1[i]; }
+    __shared__ double sm[2][RED_ROWS][16][VEC + 1];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
         sm[0][ty][tx][i] = s0[i];
         sm[1][ty][tx][i] = s1[i];
     }
     __syncthreads();
-    if (ty == 0 && cvalid) {
+    // thread (tx, ty): ty < 8 reduces sum-0 of channel c+ty, ty >= 8 reduces sum-1 of channel c+ty-8
+    if (cvalid) {
+        const int which = ty >> 3, ch = ty & 7;
+        double a = 0.0;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            double a = 0.0, b2 = 0.0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                a += sm[0][j][tx][i];
-                b2 += sm[1][j][tx][i];
-            }
-            ws[((long long)blockIdx.y * 2 + 0) * x.C + c + i] = a;
-            ws[((long long)blockIdx.y * 2 + 1) * x.C + c + i] = b2;
-        }
+        for (int j = 0; j < RED_ROWS; ++j) a += sm[which][j][tx][ch];
+        ws[((long long)blockIdx.y * 2 + which) * x.C + c + ch] = a;
     }
 }
 
@@ -188,7 +245,8 @@ static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mo
                          int nchunk, cudaStream_t st) {
     MOPOE_REQUIRE(x->C % VEC == 0, "reduce: C=%d not a multiple of %d", x->C, VEC);
     MOPOE_REQUIRE(nchunk >= 1 && ws, "reduce: bad workspace");
-    dim3 block(32, 8), grid((x->C + 127) / 128, nchunk);
+    MOPOE_REQUIRE((long long)x->B * x->H * x->W < (1ll << 31), "reduce: too many rows");
+    dim3 block(16, RED_ROWS), grid((x->C + 127) / 128, nchunk);
     MOPOE_DISPATCH_T(x->dtype, T, {
         DView<const T> xv = make_dview<const T>(x);
         DView<const T> dv = dy ? make_dview<const T>(dy) : xv;
@@ -207,7 +265,7 @@ extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int ma
     if (launch_reduce<RED_STATS>(x, nullptr, nullptr, 1.f, mask, mask_mode, nullptr, nullptr, ws, nchunk, st)) return 1;
     double count = (double)x->B * x->H * x->W;
     bn_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, count, eps, momentum, mean, invstd,
-                                                          running_mean, running_var);
+                                                      running_mean, running_var);
     MOPOE_CHECK_LAUNCH("bn_finalize");
     return 0;
 }
@@ -239,27 +297,28 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(DView<const T> x, const uint8_t* mask, int mask_mode,
                                                               const float* mean, const float* invstd,
                                                               const float* gamma, const float* beta, int relu,
-                                                              DView<T> out, long long total) {
-    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+                                                              DView<T> out, unsigned total) {
+    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
-    int b, h, w, c;
-    bool in = decode_storage(out, idx, b, h, w, c);
-    float o[VEC] = {0.f, 0.f, 0.f, 0.f};
-    if (in) {
+    const Pos p = decode_storage(out, idx);
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+    if (p.interior) {
         float xv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
-        ldv<VEC>(x.p + vaddr(x, b, h, w, c), xv);
-        ldmask<VEC>(mask, mask_mode, (long long)b * x.C + c, (((long long)b * x.H + h) * x.W + w) * x.C + c, mk);
-        ldv<VEC>(mean + c, mu);
-        ldv<VEC>(invstd + c, is);
-        ldv<VEC>(gamma + c, ga);
-        ldv<VEC>(beta + c, be);
+        ld8v<T>(x.p + vaddr(x, p.b, p.h, p.w, p.c), xv);
+        ldmask8(mask, mask_mode, (long long)p.b * x.C + p.c, (((long long)p.b * x.H + p.h) * x.W + p.w) * x.C + p.c, mk);
+        ld8f(mean + p.c, mu);
+        ld8f(invstd + p.c, is);
+        ld8f(gamma + p.c, ga);
+        ld8f(beta + p.c, be);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            float y = (xv[i] * mk[i] - mu[i]) * is[i] * ga[i] + be[i];
+            const float y = (xv[i] * mk[i] - mu[i]) * is[i] * ga[i] + be[i];
             o[i] = (relu && y < 0.f) ? 0.f : y;
         }
     }
-    stv<VEC>(out.p + vaddr(out, b, h, w, c), o);
+    st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
 }
 
 extern "C" int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
@@ -269,9 +328,11 @@ extern "C" int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int ma
     MOPOE_REQUIRE(x->C % VEC == 0, "bn_apply: C=%d", x->C);
     MOPOE_DISPATCH_T(x->dtype, T, {
         DView<T> ov = make_dview<T>(out);
-        long long total = storage_threads(ov);
-        bn_apply_kernel<T><<<(unsigned)ceil_div64(total, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
-            make_dview<const T>(x), mask, mask_mode, mean, invstd, gamma, beta, relu, ov, total);
+        unsigned grid;
+        const long long total = storage_threads(ov);
+        if (apply_grid(total, grid)) return 1;
+        bn_apply_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(make_dview<const T>(x), mask, mask_mode, mean,
+                                                                         invstd, gamma, beta, relu, ov, (unsigned)total);
     });
     MOPOE_CHECK_LAUNCH("bn_apply");
     return 0;
@@ -281,26 +342,27 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) combine_kernel(DView<const T> r, const float* mean, const float* invstd,
                                                              const float* gamma, const float* beta, DView<const T> cc,
                                                              const uint8_t* mask, int mask_mode, float a, float bcoef,
-                                                             DView<T> out, long long total) {
-    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+                                                             DView<T> out, unsigned total) {
+    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
-    int b, h, w, c;
-    bool in = decode_storage(out, idx, b, h, w, c);
-    float o[VEC] = {0.f, 0.f, 0.f, 0.f};
-    if (in) {
+    const Pos p = decode_storage(out, idx);
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+    if (p.interior) {
         float rv[VEC], cv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
-        ldv<VEC>(r.p + vaddr(r, b, h, w, c), rv);
-        ldv<VEC>(cc.p + vaddr(cc, b, h, w, c), cv);
-        ldmask<VEC>(mask, mask_mode, (long long)b * r.C + c, (((long long)b * r.H + h) * r.W + w) * r.C + c, mk);
-        ldv<VEC>(mean + c, mu);
-        ldv<VEC>(invstd + c, is);
-        ldv<VEC>(gamma + c, ga);
-        ldv<VEC>(beta + c, be);
+        ld8v<T>(r.p + vaddr(r, p.b, p.h, p.w, p.c), rv);
+        ld8v<T>(cc.p + vaddr(cc, p.b, p.h, p.w, p.c), cv);
+        ldmask8(mask, mask_mode, (long long)p.b * r.C + p.c, (((long long)p.b * r.H + p.h) * r.W + p.w) * r.C + p.c, mk);
+        ld8f(mean + p.c, mu);
+        ld8f(invstd + p.c, is);
+        ld8f(gamma + p.c, ga);
+        ld8f(beta + p.c, be);
 #pragma unroll
         for (int i = 0; i < VEC; ++i)
             o[i] = a * ((rv[i] - mu[i]) * is[i] * ga[i] + be[i]) + bcoef * (cv[i] * mk[i]);
     }
-    stv<VEC>(out.p + vaddr(out, b, h, w, c), o);
+    st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
 }
 
 extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma,
@@ -310,90 +372,127 @@ extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const flo
     MOPOE_REQUIRE(r->C % VEC == 0, "combine: C=%d", r->C);
     MOPOE_DISPATCH_T(r->dtype, T, {
         DView<T> ov = make_dview<T>(out);
-        long long total = storage_threads(ov);
-        combine_kernel<T><<<(unsigned)ceil_div64(total, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
-            make_dview<const T>(r), mean, invstd, gamma, beta, make_dview<const T>(c), mask, mask_mode, a, b, ov, total);
+        unsigned grid;
+        const long long total = storage_threads(ov);
+        if (apply_grid(total, grid)) return 1;
+        combine_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(make_dview<const T>(r), mean, invstd, gamma, beta,
+                                                                        make_dview<const T>(c), mask, mask_mode, a, b, ov,
+                                                                        (unsigned)total);
     });
     MOPOE_CHECK_LAUNCH("combine");
     return 0;
 }
 
 // ---- backward apply kernels ---------------------------------------------------------------------------
+// out  = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend,  g = gscale * dy * [gate > 0]
+// out2 = scale2 * dy * 2mask2   (optional second output sharing the read of dy: the dropout2 branch of a block)
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T> dy, DView<const T> gate, int has_gate,
                                                                   float gscale, DView<const T> x, const uint8_t* mask,
                                                                   int mask_mode, const float* mean, const float* invstd,
                                                                   const float* gamma, const float* sums, float inv_cnt,
                                                                   DView<const T> addend, int has_add, DView<T> out,
-                                                                  long long total) {
-    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+                                                                  DView<T> out2, int has_out2, const uint8_t* mask2,
+                                                                  int mask2_mode, float scale2, unsigned total) {
+    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
-    int b, h, w, c;
-    bool in = decode_storage(out, idx, b, h, w, c);
-    float o[VEC] = {0.f, 0.f, 0.f, 0.f};
-    if (in) {
+    const Pos p = decode_storage(out, idx);
+    float o[VEC], o2[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = o2[i] = 0.f;
+    if (p.interior) {
         const int C = x.C;
         float g[VEC], gt[VEC], xv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], sg[VEC], sgx[VEC], ad[VEC];
-        ldv<VEC>(dy.p + vaddr(dy, b, h, w, c), g);
-        if (has_gate) ldv<VEC>(gate.p + vaddr(gate, b, h, w, c), gt);
-        ldv<VEC>(x.p + vaddr(x, b, h, w, c), xv);
-        ldmask<VEC>(mask, mask_mode, (long long)b * C + c, (((long long)b * x.H + h) * x.W + w) * C + c, mk);
-        ldv<VEC>(mean + c, mu);
-        ldv<VEC>(invstd + c, is);
-        ldv<VEC>(gamma + c, ga);
-        ldv<VEC>(sums + c, sg);
-        ldv<VEC>(sums + C + c, sgx);
-        if (has_add) ldv<VEC>(addend.p + vaddr(addend, b, h, w, c), ad);
+        ld8v<T>(dy.p + vaddr(dy, p.b, p.h, p.w, p.c), g);
+        if (has_gate) ld8v<T>(gate.p + vaddr(gate, p.b, p.h, p.w, p.c), gt);
+        ld8v<T>(x.p + vaddr(x, p.b, p.h, p.w, p.c), xv);
+        const long long bc = (long long)p.b * C + p.c, el = (((long long)p.b * x.H + p.h) * x.W + p.w) * C + p.c;
+        ldmask8(mask, mask_mode, bc, el, mk);
+        ld8f(mean + p.c, mu);
+        ld8f(invstd + p.c, is);
+        ld8f(gamma + p.c, ga);
+        ld8f(sums + p.c, sg);
+        ld8f(sums + C + p.c, sgx);
+        if (has_add) ld8v<T>(addend.p + vaddr(addend, p.b, p.h, p.w, p.c), ad);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             float gg = gscale * g[i];
             if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
-            float xh = (xv[i] * mk[i] - mu[i]) * is[i];
-            float dv = ga[i] * is[i] * (gg - sg[i] * inv_cnt - xh * sgx[i] * inv_cnt);
+            const float xh = (xv[i] * mk[i] - mu[i]) * is[i];
+            const float dv = ga[i] * is[i] * (gg - sg[i] * inv_cnt - xh * sgx[i] * inv_cnt);
             o[i] = dv * mk[i] + (has_add ? ad[i] : 0.f);
         }
+        if (has_out2) {
+            float mk2[VEC];
+            ldmask8(mask2, mask2_mode, bc, el, mk2);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o2[i] = scale2 * g[i] * mk2[i];
+        }
     }
-    stv<VEC>(out.p + vaddr(out, b, h, w, c), o);
+    st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
+    if (has_out2) st8v<T>(out2.p + vaddr(out2, p.b, p.h, p.w, p.c), o2);
 }
 
-extern "C" int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
-                                  const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
-                                  const float* invstd, const float* gamma, const float* sums,
-                                  const mopoe_view_t* addend, const mopoe_view_t* out, void* stream) {
+static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const mopoe_view_t* x,
+                             const uint8_t* mask, int mask_mode, const float* mean, const float* invstd,
+                             const float* gamma, const float* sums, const mopoe_view_t* addend, const mopoe_view_t* out,
+                             const mopoe_view_t* out2, const uint8_t* mask2, int mask2_mode, float scale2, void* stream) {
     if (check_same(x, dy, "bn_bwd_apply(dy)") || check_same(x, out, "bn_bwd_apply(out)")) return 1;
     if (gate && check_same(x, gate, "bn_bwd_apply(gate)")) return 1;
     if (addend && check_same(x, addend, "bn_bwd_apply(addend)")) return 1;
+    if (out2) {
+        if (check_same(x, out2, "bn_bwd_apply(out2)")) return 1;
+        MOPOE_REQUIRE(out2->ph == out->ph && out2->pw == out->pw, "bn_bwd_apply: out and out2 must share their border");
+    }
     MOPOE_REQUIRE(x->C % VEC == 0, "bn_bwd_apply: C=%d", x->C);
     float inv_cnt = 1.f / ((float)x->B * (float)x->H * (float)x->W);
     MOPOE_DISPATCH_T(x->dtype, T, {
         DView<T> ov = make_dview<T>(out);
         DView<const T> xv = make_dview<const T>(x);
-        long long total = storage_threads(ov);
-        bn_bwd_apply_kernel<T><<<(unsigned)ceil_div64(total, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
-            make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate != nullptr, gscale, xv, mask,
-            mask_mode, mean, invstd, gamma, sums, inv_cnt, addend ? make_dview<const T>(addend) : xv,
-            addend != nullptr, ov, total);
+        unsigned grid;
+        const long long total = storage_threads(ov);
+        if (apply_grid(total, grid)) return 1;
+        bn_bwd_apply_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(
+            make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate != nullptr, gscale, xv, mask, mask_mode,
+            mean, invstd, gamma, sums, inv_cnt, addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,
+            out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2, (unsigned)total);
     });
     MOPOE_CHECK_LAUNCH("bn_bwd_apply");
     return 0;
 }
+extern "C" int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
+                                  const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
+                                  const float* invstd, const float* gamma, const float* sums,
+                                  const mopoe_view_t* addend, const mopoe_view_t* out, void* stream) {
+    return bn_bwd_apply_impl(dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, sums, addend, out, nullptr, nullptr,
+                             MOPOE_MASK_NONE, 0.f, stream);
+}
+// backward of `y = a*BN(r) + b*(c*2mask2)` in ONE pass over dy:  dr = BN-backward(a*dy),  dc = b * dy * 2mask2
+extern "C" int mopoe_combine_bwd_apply(const mopoe_view_t* dy, float a, const mopoe_view_t* r, const float* mean,
+                                       const float* invstd, const float* gamma, const float* sums,
+                                       const uint8_t* mask2, int mask2_mode, float b, const mopoe_view_t* dr,
+                                       const mopoe_view_t* dc, void* stream) {
+    return bn_bwd_apply_impl(dy, nullptr, a, r, nullptr, MOPOE_MASK_NONE, mean, invstd, gamma, sums, nullptr, dr, dc, mask2,
+                             mask2_mode, b, stream);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) scale_mask_kernel(DView<const T> dy, const uint8_t* mask, int mask_mode,
-                                                                float scale, DView<T> out, long long total) {
-    long long idx = (long long)blockIdx.x * EW_THREADS + threadIdx.x;
+                                                                float scale, DView<T> out, unsigned total) {
+    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
-    int b, h, w, c;
-    bool in = decode_storage(out, idx, b, h, w, c);
-    float o[VEC] = {0.f, 0.f, 0.f, 0.f};
-    if (in) {
+    const Pos p = decode_storage(out, idx);
+    float o[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+    if (p.interior) {
         float g[VEC], mk[VEC];
-        ldv<VEC>(dy.p + vaddr(dy, b, h, w, c), g);
-        ldmask<VEC>(mask, mask_mode, (long long)b * dy.C + c, (((long long)b * dy.H + h) * dy.W + w) * dy.C + c, mk);
+        ld8v<T>(dy.p + vaddr(dy, p.b, p.h, p.w, p.c), g);
+        ldmask8(mask, mask_mode, (long long)p.b * dy.C + p.c, (((long long)p.b * dy.H + p.h) * dy.W + p.w) * dy.C + p.c, mk);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) o[i] = scale * g[i] * mk[i];
     }
-    stv<VEC>(out.p + vaddr(out, b, h, w, c), o);
+    st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
 }
 
 extern "C" int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int mask_mode, float scale,
@@ -402,9 +501,11 @@ extern "C" int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int
     MOPOE_REQUIRE(dy->C % VEC == 0, "scale_mask: C=%d", dy->C);
     MOPOE_DISPATCH_T(dy->dtype, T, {
         DView<T> ov = make_dview<T>(out);
-        long long total = storage_threads(ov);
-        scale_mask_kernel<T><<<(unsigned)ceil_div64(total, EW_THREADS), EW_THREADS, 0, (cudaStream_t)stream>>>(
-            make_dview<const T>(dy), mask, mask_mode, scale, ov, total);
+        unsigned grid;
+        const long long total = storage_threads(ov);
+        if (apply_grid(total, grid)) return 1;
+        scale_mask_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(make_dview<const T>(dy), mask, mask_mode, scale,
+                                                                           ov, (unsigned)total);
     });
     MOPOE_CHECK_LAUNCH("scale_mask");
     return 0;

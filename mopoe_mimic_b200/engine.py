@@ -179,6 +179,20 @@ class Engine:
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), av, C.byref(out.view()), L.stream_ptr())
         return out
 
+    def combine_bwd(self, dy, a, r, stats, gamma, dgamma, dbeta, mask2, mode2, b, dr, dc):
+        """backward of y = a*BN(r) + b*(c*2mask2): BN reduction over (dy, r), then ONE pass writing dr and dc"""
+        rows = r.B * r.H * r.W
+        nc = self.nchunk(rows, r.C)
+        ws = self.ws64(2 * nc * r.C)
+        sums = self.f32(2, r.C)
+        L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), None, float(a), C.byref(r.view()), None, L.MASK_NONE,
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums),
+               L.stream_ptr())
+        L.call('mopoe_combine_bwd_apply', C.byref(dy.view()), float(a), C.byref(r.view()), L.ptr(stats[0]),
+               L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), L.ptr(mask2), mode2, float(b), C.byref(dr.view()),
+               C.byref(dc.view()), L.stream_ptr())
+        return dr, dc
+
     def scale_mask(self, dy, mask, mode, scale, out):
         L.call('mopoe_scale_mask', C.byref(dy.view()), L.ptr(mask), mode, float(scale), C.byref(out.view()),
                L.stream_ptr())

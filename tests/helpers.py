@@ -69,6 +69,47 @@ def run_product(ofl, state, batch, noise, compute_dtype):
     return exp, out, grads
 
 
+def smooth_grads(ofl, state, batch, noise, compute_dtype):
+    """Gradients of a SMOOTH surrogate loss (mean-square of every reconstruction + the joint divergence) on both
+    sides.  The ELBO's Laplace term is piecewise linear: fp32 rounding flips a handful of sign(x - loc) decisions
+    per image, which moves decoder gradients by ~1e-3..1e-2 in ANY fp32 implementation; the surrogate exercises the
+    identical conv / BN / dropout / fusion backward kernels without that chaos, so it can be compared tightly."""
+    import mopoe_mimic_b200 as P
+
+    def oracle_grads(dt):
+        st = OrderedDict((k, (v.clone().to(dt) if v.is_floating_point() else v.clone())) for k, v in state.items())
+        params = {k: v for k, v in st.items() if v.is_floating_point() and 'running_' not in k}
+        for v in params.values():
+            v.requires_grad_(True)
+        b = OrderedDict((k, v.to(dt)) for k, v in batch.items())
+        masks = {k: v.to(dt) for k, v in noise[0][0].items()}
+        res = O.forward(st, b, ofl, masks, noise[0][1].to(dt), True)
+        loss = sum((r ** 2).mean() for r in res['rec'].values()) * 100.0 + 5.0 * res['joint_divergence']
+        loss.backward()
+        return loss, OrderedDict((k, v.grad.detach().clone()) for k, v in params.items())
+    loss_o, g_o = oracle_grads(torch.float32)
+    _, g_o64 = oracle_grads(torch.float64)        # truth: the same fp32-rounded inputs evaluated in fp64
+    smooth_grads.truth = g_o64
+    fl = product_flags(ofl, compute_dtype)
+    exp = P.Experiment(fl)
+    vae = exp.mm_vae
+    vae.load_state_dict({k: v.detach().float() for k, v in state.items()})
+    exp.set_optimizer()
+    vae.train()
+    dev = fl.device
+    vae.rt.schedule = [(masks_to_product(noise[0][0], dev), noise[0][1].float().to(dev))]
+    out = vae(OrderedDict((k, v.float().to(dev)) for k, v in batch.items()))
+    recs = []
+    for m, r in out['rec'].items():
+        recs.append(torch.log_softmax(r._scores, -1) if m == 'text' else r.loc)
+    loss_p = sum((r ** 2).mean() for r in recs) * 100.0 + 5.0 * out['joint_divergence']
+    exp.optimizer.zero_grad()
+    loss_p.backward()
+    torch.cuda.synchronize()
+    g_p = OrderedDict((k, p.grad.detach().cpu()) for k, p in vae.named_parameters())
+    return float(loss_o), float(loss_p), g_o, g_p
+
+
 def rel_err(a, b, floor=0.0):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + floor + 1e-300))

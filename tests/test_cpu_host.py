@@ -1,0 +1,163 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every declared symbol, host logic of the fusion
+plan (subset enumeration, bit-exact selection ranges), state_dict layout, weight-packing index maps, and the
+data-parallel host path on a 2-rank gloo group."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import mopoe_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from mopoe_mimic_b200 import _lib as L
+    from mopoe_mimic_b200 import build as B
+    B.build()
+    lib = L.load()                                   # binds every name in SIGNATURES (AttributeError otherwise)
+    header = open(os.path.join(ROOT, 'include', 'mopoe_b200.h')).read()
+    declared = set(re.findall(r'\b(mopoe_[a-z0-9_]+)\s*\(', header)) - {'mopoe_window_t', 'mopoe_rows_t'}
+    assert declared, 'no declarations found'
+    for name in sorted(declared):
+        assert hasattr(lib, name), 'libmopoe_b200.so does not export %s' % name
+    assert declared <= set(L.SIGNATURES), sorted(declared - set(L.SIGNATURES))
+    assert lib.mopoe_version() >= 100
+
+
+def test_product_refuses_cpu():
+    import mopoe_mimic_b200 as P
+    from mopoe_mimic_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine('cpu')
+    fl = P.default_flags(device=torch.device('cpu'), DIM_img=8, DIM_text=8, class_dim=16, batch_size=2)
+    exp = P.Experiment(fl)
+    with pytest.raises(RuntimeError):
+        exp.mm_vae({'PA': torch.rand(2, 1, 128, 128), 'Lateral': torch.rand(2, 1, 128, 128),
+                    'text': torch.zeros(2, 1024, 71)})
+
+
+def test_product_does_not_import_oracle():
+    src = os.path.join(ROOT, 'mopoe_mimic_b200')
+    for fn in os.listdir(src):
+        if fn.endswith('.py'):
+            text = open(os.path.join(src, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+[\w.]*oracle', text, re.M), fn
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(mods=('PA', 'text')), dict(img_size=64), dict(img_size=256)])
+def test_state_dict_layout_matches_oracle_spec(kw):
+    import mopoe_mimic_b200 as P
+    small = dict(DIM_img=8, DIM_text=8, class_dim=16, batch_size=2)
+    fl = P.default_flags(device=torch.device('cpu'), **small, **kw)
+    sd = P.Experiment(fl).mm_vae.state_dict()
+    spec = O.param_spec(O.default_flags(**small, **kw))
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s)) for k, s in spec.items()]
+
+
+def test_set_subsets_and_selection_bit_exact():
+    from mopoe_mimic_b200.fusion import FusionPlan, selection_ends, set_subsets, uniform_weights
+    mods = {'PA': object(), 'Lateral': object(), 'text': object()}
+    assert list(set_subsets(mods).keys()) == list(O.subset_keys(mods.keys()).keys())
+    assert list(set_subsets({'PA': 1, 'text': 2}).keys()) == ['', 'PA', 'text', 'PA_text']
+    for B in (1, 5, 6, 7, 8, 16, 37, 64, 128, 255, 256, 1000, 1024, 2048, 4096):
+        for S in (1, 2, 3, 4, 7):
+            assert selection_ends(B, uniform_weights(S)) == O.selection_bounds(B, [1.0 / S] * S)[1], (B, S)
+    sub = O.subset_keys(('PA', 'Lateral', 'text'))
+    for method, S in (('joint_elbo', 7), ('moe', 3), ('poe', 1)):
+        plan = FusionPlan(['PA', 'Lateral', 'text'], ['PA', 'Lateral', 'text'], list(sub.keys()), list(sub.values()),
+                          method, 256, 128, 256)
+        assert plan.keys == [k for k in sub if k] and len(plan.stacked) == S
+        # members are kept in the reference's stacking order (sorted by name): Lateral < PA < text
+        assert [plan.cfg.mem_idx[3][j] for j in range(2)] == [1, 0]          # 'Lateral_PA' -> (Lateral, PA)
+    # unimodal pass of the poe loss: only subsets fully present are built
+    plan = FusionPlan(['PA', 'Lateral', 'text'], ['text'], list(sub.keys()), list(sub.values()), 'poe', 8, 32, 8)
+    assert plan.keys == ['text'] and plan.cfg.prior_expert == 1
+
+
+def test_weight_packing_index_maps_against_conv_identities():
+    """conv-form / phase-form / full-form (torch reference re-layouts in engine.py, mirrored by the CUDA pack kernel):
+    a stride-2 deconv equals its 4 sub-pixel phase GEMMs, checked on CPU with plain matmuls."""
+    import torch.nn.functional as F
+    from mopoe_mimic_b200.engine import KTAPS, conv_form, full_form, phase_form
+    g = torch.Generator().manual_seed(0)
+    ci, co, H = 3, 5, 4
+    x = torch.randn(2, ci, H, H, generator=g)
+    wt = torch.randn(ci, co, 4, 4, generator=g)
+    ref = F.conv_transpose2d(x, wt, stride=2, padding=1)
+    xp = F.pad(x, (1, 1, 1, 1)).permute(0, 2, 3, 1)                  # bordered channels-last
+    ph = phase_form(wt, torch.float32)
+    out = torch.zeros(2, 2 * H, 2 * H, co)
+    for py in range(2):
+        for px in range(2):
+            for t in range(H):
+                for s in range(H):
+                    win = xp[:, t + py:t + py + 2, s + px:s + px + 2, :].reshape(2, -1)    # (r, kxi, ci)
+                    out[:, 2 * t + py, 2 * s + px] = win @ ph[py * 2 + px].t()
+    torch.testing.assert_close(out.permute(0, 3, 1, 2), ref, rtol=1e-5, atol=1e-5)
+    w = torch.randn(co, ci, 4, 4, generator=g)
+    refc = F.conv2d(x, w, stride=2, padding=1)
+    wc = conv_form(w, torch.float32)
+    outc = torch.zeros(2, H // 2, H // 2, co)
+    for oy in range(H // 2):
+        for ox in range(H // 2):
+            win = xp[:, 2 * oy:2 * oy + 4, 2 * ox:2 * ox + 4, :].reshape(2, -1)
+            outc[:, oy, ox] = win @ wc.t()
+    torch.testing.assert_close(outc.permute(0, 3, 1, 2), refc, rtol=1e-5, atol=1e-5)
+    z = torch.randn(2, ci, 1, 1, generator=g)
+    reff = F.conv_transpose2d(z, wt, stride=1, padding=0)
+    outf = (z.reshape(2, ci) @ full_form(wt, torch.float32).t()).reshape(2, 4, 4, co)
+    torch.testing.assert_close(outf.permute(0, 3, 1, 2), reff, rtol=1e-5, atol=1e-5)
+    assert KTAPS == ((3, 1), (2, 0))
+
+
+_DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from mopoe_mimic_b200.dp import FlatGradAllReduce, broadcast_flat, shard_batch, bucket_bounds
+rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%%s' %% os.environ['MASTER_PORT'], rank=rank, world_size=world)
+torch.manual_seed(0)
+full = {'PA': torch.arange(8 * 3, dtype=torch.float32).reshape(8, 3), 'text': torch.arange(8, dtype=torch.float32).reshape(8, 1)}
+mine = shard_batch(full, rank, world)
+assert mine['PA'].shape[0] == 8 // world and float(mine['text'][0]) == rank * (8 // world)
+# "gradient" of a mean-over-local-batch loss: DP mean of per-rank grads == gradient of the global-batch mean
+w = torch.ones(3, requires_grad=True)
+loss = (mine['PA'] @ w).mean()
+loss.backward()
+n = 1000
+flat = torch.zeros(n)
+flat[:3] = w.grad
+flat[3:] = rank + 1.0
+ar = FlatGradAllReduce(bucket_mb=0.001)            # forces several buckets
+assert len(bucket_bounds(n, ar.bucket_elems)) > 1
+ar(flat)
+flat *= ar.grad_scale
+wg = torch.ones(3, requires_grad=True)
+(full['PA'] @ wg).mean().backward()
+assert torch.allclose(flat[:3], wg.grad), (flat[:3], wg.grad)
+assert torch.allclose(flat[3:], torch.full((n - 3,), (1.0 + world) / 2))
+p = torch.full((10,), float(rank))
+broadcast_flat(p, 0)
+assert float(p.sum()) == 0.0
+dist.destroy_process_group()
+print('rank', rank, 'ok')
+'''
+
+
+def test_data_parallel_host_path_gloo_world2(tmp_path):
+    script = tmp_path / 'dp_worker.py'
+    script.write_text(_DP_WORKER % ROOT)
+    port = str(29500 + os.getpid() % 500)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE='2', MASTER_ADDR='127.0.0.1', MASTER_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert 'rank %d ok' % r in o

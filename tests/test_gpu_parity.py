@@ -48,9 +48,38 @@ def test_fp32_step_matches_oracle(name):
     assert max(fwd.values()) < 1e-5, sorted(fwd.items(), key=lambda kv: -kv[1])[:5]
     # subset enumeration order: bit-exact
     assert list(out['results']['latents']['subsets'].keys()) == list(orc['results']['latents']['subsets'].keys())
+    # ELBO gradients: bounded by the sign()/ReLU-gate flips of the piecewise-linear loss (see smooth test below)
     g = sorted(v for k, v in errs.items() if k.startswith('grad.'))
-    assert g[len(g) // 2] < 5e-5, 'median gradient error %.2e' % g[len(g) // 2]
+    assert g[len(g) // 2] < 2e-3, 'median gradient error %.2e' % g[len(g) // 2]
     assert g[-1] < 5e-2, errs['_worst_grad']
+
+
+@pytest.mark.parametrize('name', ['tri_joint', 'tri_moe', 'patext_joint', 'tri_64px'])
+def test_fp32_gradients_of_smooth_loss_match_oracle(name):
+    """Every conv / deconv / BN / dropout / fusion backward kernel, compared tightly: same graph, smooth loss."""
+    kw = CASES[name]
+    ofl, state, batch, noise = H.make_case(kw)
+    lo, lp, g_o, g_p = H.smooth_grads(ofl, state, batch, noise, 'fp32')
+    assert abs(lo - lp) < 1e-5 * abs(lo)
+    truth = H.smooth_grads.truth                 # the same fp32-rounded inputs evaluated in fp64
+    gscale = max(float(g.abs().max()) for g in truth.values())
+    rows = []
+    for k, t in truth.items():
+        if k.endswith(('downsample.0.bias', 'upsample.0.bias')):
+            continue                              # analytically zero (bias feeding a train-mode BN): pure noise
+        ep = H.rel_err(g_p[k], t, floor=1e-4 * gscale)
+        eo = H.rel_err(g_o[k], t, floor=1e-4 * gscale)
+        rows.append((ep, eo, k))
+    med_p = sorted(r[0] for r in rows)[len(rows) // 2]
+    med_o = sorted(r[1] for r in rows)[len(rows) // 2]
+    assert med_p < 2e-5 and med_p < 4 * med_o + 2e-6, (med_p, med_o)
+    # Tensor by tensor: within 4x the reference arithmetic's own fp32 gap + 3e-4 — except for ISOLATED ReLU-gate
+    # flips: two fp32 implementations that sum in different orders disagree by ~1e-6 on pre-activations, so of the
+    # ~1e6 gated elements a handful land on the other side of zero; each flip moves the gradients of the one block
+    # it sits in by ~1e-3 (seen as a bn bias / 1x1 weight of a single block being off, the rest at 1e-6).
+    bad = sorted(r for r in rows if r[0] > 4 * r[1] + 3e-4)
+    assert len(bad) <= max(3, len(rows) // 25), bad[-8:]
+    assert all(r[0] < 2e-2 for r in bad), bad[-5:]
 
 
 def test_fp32_ragged_last_batch():
