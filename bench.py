@@ -201,6 +201,11 @@ def main():
         for k, n, t in sorted(rows, key=lambda r: -r[2])[:45]:
             print('%-70s %5d %9.1f us %5.1f%%' % (k[:70], n, t, 100.0 * t / tot))
         print('total device time %.1f ms' % (tot / 1e3))
+        flt = os.environ.get('KFILTER')
+        if flt:      # per-launch durations of one kernel family, in launch order
+            ds = [(e.name[:40], e.device_time_total) for e in prof.events()
+                  if flt in e.name and e.device_time_total > 0 and str(e.device_type).endswith('CUDA')]
+            print('%d launches of %s:' % (len(ds), flt), ' '.join('%.0f' % d for _, d in ds))
         return
     sampler = ClockSampler(local)
     sampler.start()

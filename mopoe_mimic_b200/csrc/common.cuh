@@ -28,12 +28,33 @@ void mopoe_set_error(const char* fmt, ...);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ---- division by a runtime constant as multiply-high + shift (valid for n < 2^31) ----------------------
+struct FastDiv {
+    unsigned d, mul, shr;
+    __host__ __device__ FastDiv() : d(1), mul(0), shr(0) {}
+    explicit FastDiv(unsigned div) : d(div), mul(0), shr(0) {
+        if (div > 1) {
+            unsigned l = 0;
+            while ((1u << l) < div) ++l;                      // ceil(log2 d)
+            const unsigned p = 31 + l;
+            mul = (unsigned)(((1ull << p) + div - 1) / div);
+            shr = p - 32;
+        }
+    }
+    __device__ __forceinline__ unsigned div(unsigned n) const { return d == 1 ? n : (__umulhi(n, mul) >> shr); }
+    __device__ __forceinline__ void divmod(unsigned n, unsigned& q, unsigned& r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+
 // ---- device view (mirror of mopoe_view_t with a typed pointer) --------------------------------------
 template <typename T>
 struct DView {
     T* p;
     int B, H, W, C, ph, pw;
     long long sB, sH, sW;
+    FastDiv fW, fH, fWs, fHs, fCV8;      // W, H, W+2pw, H+2ph, C/8
 };
 template <typename T>
 static inline DView<T> make_dview(const mopoe_view_t* v) {
@@ -41,6 +62,11 @@ static inline DView<T> make_dview(const mopoe_view_t* v) {
     d.p = (T*)v->ptr;
     d.B = v->B; d.H = v->H; d.W = v->W; d.C = v->C; d.ph = v->ph; d.pw = v->pw;
     d.sB = v->sB; d.sH = v->sH; d.sW = v->sW;
+    d.fW = FastDiv((unsigned)v->W);
+    d.fH = FastDiv((unsigned)v->H);
+    d.fWs = FastDiv((unsigned)(v->W + 2 * v->pw));
+    d.fHs = FastDiv((unsigned)(v->H + 2 * v->ph));
+    d.fCV8 = FastDiv((unsigned)(v->C >= 8 ? v->C / 8 : 1));
     return d;
 }
 

@@ -112,20 +112,19 @@ __global__ void __launch_bounds__(256) tap_grad_kernel(DView<const T> v, const f
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = (blockIdx.x * 16 + tx) * CV8;
     const bool cvalid = c < v.C;
-    const long long rows = (long long)v.B * v.H * v.W;
-    const long long rpc = (rows + nchunk - 1) / nchunk;
-    const long long r0 = (long long)blockIdx.y * rpc, r1 = min(rows, r0 + rpc);
+    const unsigned rows = (unsigned)v.B * v.H * v.W;
+    const unsigned gstride = (unsigned)nchunk * 16;      // interleaved 16-row groups (compact streaming window)
     float acc[9][CV8];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int i = 0; i < CV8; ++i) acc[t][i] = 0.f;
     if (cvalid) {
-        for (long long r = r0 + ty; r < r1; r += 16) {
-            int px = (int)(r % v.W);
-            long long t2 = r / v.W;
-            int py = (int)(t2 % v.H);
-            int b = (int)(t2 / v.H);
+        for (unsigned r = blockIdx.y * 16 + ty; r < rows; r += gstride) {
+            int px = (int)(r % (unsigned)v.W);
+            unsigned t2 = r / (unsigned)v.W;
+            int py = (int)(t2 % (unsigned)v.H);
+            int b = (int)(t2 / (unsigned)v.H);
             float g[CV8];
             ld8<T>(v.p + (long long)b * v.sB + (long long)py * v.sH + (long long)px * v.sW + c, g);
             const float* sb = s + (long long)b * SH * SW;

@@ -58,8 +58,32 @@ __device__ __forceinline__ void st8v(T* p, const float (&o)[8]) {
     }
 }
 __device__ __forceinline__ void ld8f(const float* p, float (&o)[8]) { ld8v<float>(p, o); }
+// 8 consecutive channels held PACKED (4 registers for bf16) between the load and the use
+template <typename T>
+struct Raw8;
+template <>
+struct Raw8<bf16> {
+    uint4 v;
+    __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void unpack(float (&o)[8]) const {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[2 * i] = __low2float(h[i]); o[2 * i + 1] = __high2float(h[i]); }
+    }
+};
+template <>
+struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = reinterpret_cast<const float4*>(p)[0];
+        b = reinterpret_cast<const float4*>(p)[1];
+    }
+    __device__ __forceinline__ void unpack(float (&o)[8]) const {
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+};
 // keep-mask bytes -> multiplier 2 (keep) / 0 (drop); bc_idx / el_idx are element indices into the mask
-__device__ __forceinline__ void ldmask8(const uint8_t* m, int mode, long long bc_idx, long long el_idx, float (&o)[8]) {
+__device__ __forceinline__ void ldmask8(const uint8_t* m, int mode, int bc_idx, int el_idx, float (&o)[8]) {
     if (mode == MOPOE_MASK_NONE) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = 1.f;
@@ -97,14 +121,36 @@ template <typename T>
 static long long storage_threads(const DView<T>& o) {
     return (long long)o.B * (o.H + 2 * o.ph) * (o.W + 2 * o.pw) * (o.C / VEC);
 }
+// element offset relative to the interior origin; 32-bit (hosts check numel < 2^31), may be negative on the border
 template <typename T>
-__device__ __forceinline__ long long vaddr(const DView<T>& v, int b, int h, int w, int c) {
-    return (long long)b * v.sB + (long long)h * v.sH + (long long)w * v.sW + c;
+__device__ __forceinline__ int vaddr(const DView<T>& v, int b, int h, int w, int c) {
+    return b * (int)v.sB + h * (int)v.sH + w * (int)v.sW + c;
 }
-static int apply_grid(long long total, unsigned& grid) {
-    MOPOE_REQUIRE(total > 0 && total < (1ll << 32), "elementwise: %lld work items do not fit 32-bit indexing", total);
-    grid = (unsigned)ceil_div64(total, EW_THREADS);
+// Launch shape of the apply kernels: every thread keeps ONE channel octet (its per-channel parameters stay in
+// registers) and strides over ~4 pixels, so the total thread count must be a multiple of C/8.
+static unsigned gcd_u(unsigned a, unsigned b) { while (b) { unsigned t = a % b; a = b; b = t; } return a; }
+static int apply_grid(long long total, int C, unsigned& grid, unsigned& stride) {
+    MOPOE_REQUIRE(total > 0 && total < (1ll << 31), "elementwise: %lld work items do not fit 32-bit indexing", total);
+    const unsigned CV = (unsigned)C / VEC;
+    const unsigned m = CV / gcd_u(CV, EW_THREADS);          // blocks must be a multiple of m
+    unsigned blocks = (unsigned)ceil_div64(ceil_div64(total, 4), EW_THREADS);
+    blocks = (blocks + m - 1) / m * m;
+    grid = blocks;
+    stride = blocks * EW_THREADS;
     return 0;
+}
+template <typename T>
+__device__ __forceinline__ Pos decode_pixel(const DView<T>& o, unsigned pos, int c) {
+    Pos p;
+    p.c = c;
+    unsigned ws, hs, q, bb;
+    o.fWs.divmod(pos, q, ws);
+    o.fHs.divmod(q, bb, hs);
+    p.b = (int)bb;
+    p.h = (int)hs - o.ph;
+    p.w = (int)ws - o.pw;
+    p.interior = p.h >= 0 && p.h < o.H && p.w >= 0 && p.w < o.W;
+    return p;
 }
 
 // ---- per-channel reductions (BN stats, BN backward sums, bias gradient) ------------------------------
@@ -120,66 +166,92 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = (blockIdx.x * 16 + tx) * VEC;
     const bool cvalid = c < x.C;
+    // rows are dealt to the blocks in interleaved groups of 16 (block y takes groups y, y+nchunk, ...): at any moment
+    // the whole grid streams one compact window of the tensor (DRAM-page / TLB friendly), unlike a blocked split
     const unsigned rows = (unsigned)x.B * x.H * x.W;
-    const unsigned rpc = (rows + nchunk - 1) / nchunk;
-    const unsigned r0 = blockIdx.y * rpc;
-    const unsigned r1 = min(rows, r0 + rpc);
-    double s0[VEC], s1[VEC];
+    const unsigned r1 = rows;
+    const unsigned gstride = (unsigned)nchunk * RED_ROWS;
     float f0[VEC], f1[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) { s0[i] = s1[i] = 0.0; f0[i] = f1[i] = 0.f; }
+    for (int i = 0; i < VEC; ++i) f0[i] = f1[i] = 0.f;
     float mu[VEC], is[VEC];
     if (MODE == RED_BNBWD && cvalid) {
         ld8f(mean + c, mu);
         ld8f(invstd + c, is);
     }
     if (cvalid) {
-        int strip = 0;
-        for (unsigned r = r0 + ty; r < r1; r += RED_ROWS) {
-            const unsigned w = r % (unsigned)x.W;
-            const unsigned t = r / (unsigned)x.W;
-            const unsigned h = t % (unsigned)x.H;
-            const unsigned b = t / (unsigned)x.H;
-            float xv[VEC], mk[VEC];
-            ld8v<T>(x.p + vaddr(x, b, h, w, c), xv);
-            ldmask8(mask, mask_mode, (long long)b * x.C + c, (long long)r * x.C + c, mk);
-            if (MODE == RED_STATS) {
+        constexpr int U = 4;                  // row groups in flight per thread
+        for (unsigned rb = blockIdx.y * RED_ROWS + ty; rb < r1; rb += U * gstride) {
+            // issue all loads of the U row groups first (kept PACKED: 4 registers per bf16 octet), unpack at use
+            Raw8<T> xr[U], gr[U], tr[U];
+            uint2 mr[U];
+            bool ok[U];
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const float v = xv[i] * mk[i];
-                    f0[i] += v;
-                    f1[i] = fmaf(v, v, f1[i]);
-                }
-            } else if (MODE == RED_COLSUM) {
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) f0[i] += xv[i];
-            } else {
-                float g[VEC], gt[VEC];
-                ld8v<T>(dy.p + vaddr(dy, b, h, w, c), g);
-                if (has_gate) ld8v<T>(gate.p + vaddr(gate, b, h, w, c), gt);
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    float gg = gscale * g[i];
-                    if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
-                    const float xh = (xv[i] * mk[i] - mu[i]) * is[i];
-                    f0[i] += gg;
-                    f1[i] = fmaf(gg, xh, f1[i]);
+            for (int u = 0; u < U; ++u) {
+                const unsigned r = rb + u * gstride;
+                ok[u] = r < r1;
+                if (ok[u]) {
+                    unsigned w, t, h, b;
+                    x.fW.divmod(r, t, w);
+                    x.fH.divmod(t, b, h);
+                    xr[u].load(x.p + vaddr(x, b, h, w, c));
+                    if (mask_mode != MOPOE_MASK_NONE)
+                        mr[u] = *reinterpret_cast<const uint2*>(mask + (mask_mode == MOPOE_MASK_BC ? (int)(b * x.C + c)
+                                                                                                  : (int)(r * x.C + c)));
+                    if (MODE == RED_BNBWD) {
+                        gr[u].load(dy.p + vaddr(dy, b, h, w, c));
+                        if (has_gate) tr[u].load(gate.p + vaddr(gate, b, h, w, c));
+                    }
                 }
             }
-            if (++strip == 32) {      // fp32 strips of 32 rows, folded into fp64
-                strip = 0;
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) { s0[i] += (double)f0[i]; s1[i] += (double)f1[i]; f0[i] = f1[i] = 0.f; }
+            for (int u = 0; u < U; ++u) {
+                if (ok[u]) {
+                    float xv[VEC], mk[VEC];
+                    xr[u].unpack(xv);
+                    if (mask_mode != MOPOE_MASK_NONE) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            mk[i] = ((mr[u].x >> (8 * i)) & 0xffu) ? 2.f : 0.f;
+                            mk[4 + i] = ((mr[u].y >> (8 * i)) & 0xffu) ? 2.f : 0.f;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) mk[i] = 1.f;
+                    }
+                    if (MODE == RED_STATS) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            const float v = xv[i] * mk[i];
+                            f0[i] += v;
+                            f1[i] = fmaf(v, v, f1[i]);
+                        }
+                    } else if (MODE == RED_COLSUM) {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) f0[i] += xv[i];
+                    } else {
+                        float g[VEC], gt[VEC];
+                        gr[u].unpack(g);
+                        if (has_gate) tr[u].unpack(gt);
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) {
+                            float gg = gscale * g[i];
+                            if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
+                            const float xh = (xv[i] * mk[i] - mu[i]) * is[i];
+                            f0[i] += gg;
+                            f1[i] = fmaf(gg, xh, f1[i]);
+                        }
+                    }
+                }
             }
         }
     }
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) { s0[i] += (double)f0[i]; s1[i] += (double)f1[i]; }
+    // each thread summed <= rows / (16 * nchunk) (~100) values in fp32; everything above that level is fp64
     __shared__ double sm[2][RED_ROWS][16][VEC + 1];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-        sm[0][ty][tx][i] = s0[i];
-        sm[1][ty][tx][i] = s1[i];
+        sm[0][ty][tx][i] = (double)f0[i];
+        sm[1][ty][tx][i] = (double)f1[i];
     }
     __syncthreads();
     // thread (tx, ty): ty < 8 reduces sum-0 of channel c+ty, ty >= 8 reduces sum-1 of channel c+ty-8
@@ -297,28 +369,36 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(DView<const T> x, const uint8_t* mask, int mask_mode,
                                                               const float* mean, const float* invstd,
                                                               const float* gamma, const float* beta, int relu,
-                                                              DView<T> out, unsigned total) {
-    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
+                                                              DView<T> out, unsigned total, unsigned stride) {
+    unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
-    const Pos p = decode_storage(out, idx);
-    float o[VEC];
+    const unsigned CV = (unsigned)out.C / VEC;
+    const int c = (int)(idx % CV) * VEC;
+    float sc[VEC], sh[VEC];                    // y = v * sc + sh
+    {
+        float mu[VEC], is[VEC], ga[VEC], be[VEC];
+        ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(beta + c, be);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = 0.f;
-    if (p.interior) {
-        float xv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
-        ld8v<T>(x.p + vaddr(x, p.b, p.h, p.w, p.c), xv);
-        ldmask8(mask, mask_mode, (long long)p.b * x.C + p.c, (((long long)p.b * x.H + p.h) * x.W + p.w) * x.C + p.c, mk);
-        ld8f(mean + p.c, mu);
-        ld8f(invstd + p.c, is);
-        ld8f(gamma + p.c, ga);
-        ld8f(beta + p.c, be);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float y = (xv[i] * mk[i] - mu[i]) * is[i] * ga[i] + be[i];
-            o[i] = (relu && y < 0.f) ? 0.f : y;
-        }
+        for (int i = 0; i < VEC; ++i) { sc[i] = is[i] * ga[i]; sh[i] = be[i] - mu[i] * sc[i]; }
     }
-    st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
+#pragma unroll 2
+    for (; idx < total; idx += stride) {
+        const Pos p = decode_pixel(out, out.fCV8.div(idx), c);
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+        if (p.interior) {
+            float xv[VEC], mk[VEC];
+            ld8v<T>(x.p + vaddr(x, p.b, p.h, p.w, p.c), xv);
+            ldmask8(mask, mask_mode, p.b * x.C + p.c, ((p.b * x.H + p.h) * x.W + p.w) * x.C + p.c, mk);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float y = fmaf(xv[i] * mk[i], sc[i], sh[i]);
+                o[i] = (relu && y < 0.f) ? 0.f : y;
+            }
+        }
+        st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
+    }
 }
 
 extern "C" int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
@@ -328,11 +408,12 @@ extern "C" int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int ma
     MOPOE_REQUIRE(x->C % VEC == 0, "bn_apply: C=%d", x->C);
     MOPOE_DISPATCH_T(x->dtype, T, {
         DView<T> ov = make_dview<T>(out);
-        unsigned grid;
+        unsigned grid, stride;
         const long long total = storage_threads(ov);
-        if (apply_grid(total, grid)) return 1;
+        if (apply_grid(total, x->C, grid, stride)) return 1;
         bn_apply_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(make_dview<const T>(x), mask, mask_mode, mean,
-                                                                         invstd, gamma, beta, relu, ov, (unsigned)total);
+                                                                         invstd, gamma, beta, relu, ov, (unsigned)total,
+                                                                         stride);
     });
     MOPOE_CHECK_LAUNCH("bn_apply");
     return 0;
@@ -342,27 +423,34 @@ template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) combine_kernel(DView<const T> r, const float* mean, const float* invstd,
                                                              const float* gamma, const float* beta, DView<const T> cc,
                                                              const uint8_t* mask, int mask_mode, float a, float bcoef,
-                                                             DView<T> out, unsigned total) {
-    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
+                                                             DView<T> out, unsigned total, unsigned stride) {
+    unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
-    const Pos p = decode_storage(out, idx);
-    float o[VEC];
+    const unsigned CV = (unsigned)out.C / VEC;
+    const int c = (int)(idx % CV) * VEC;
+    float sc[VEC], sh[VEC];                    // a * BN(r) = r * sc + sh
+    {
+        float mu[VEC], is[VEC], ga[VEC], be[VEC];
+        ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(beta + c, be);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = 0.f;
-    if (p.interior) {
-        float rv[VEC], cv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], be[VEC];
-        ld8v<T>(r.p + vaddr(r, p.b, p.h, p.w, p.c), rv);
-        ld8v<T>(cc.p + vaddr(cc, p.b, p.h, p.w, p.c), cv);
-        ldmask8(mask, mask_mode, (long long)p.b * r.C + p.c, (((long long)p.b * r.H + p.h) * r.W + p.w) * r.C + p.c, mk);
-        ld8f(mean + p.c, mu);
-        ld8f(invstd + p.c, is);
-        ld8f(gamma + p.c, ga);
-        ld8f(beta + p.c, be);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i)
-            o[i] = a * ((rv[i] - mu[i]) * is[i] * ga[i] + be[i]) + bcoef * (cv[i] * mk[i]);
+        for (int i = 0; i < VEC; ++i) { sc[i] = a * is[i] * ga[i]; sh[i] = a * be[i] - mu[i] * sc[i]; }
     }
-    st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
+#pragma unroll 2
+    for (; idx < total; idx += stride) {
+        const Pos p = decode_pixel(out, out.fCV8.div(idx), c);
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+        if (p.interior) {
+            float rv[VEC], cv[VEC], mk[VEC];
+            ld8v<T>(r.p + vaddr(r, p.b, p.h, p.w, p.c), rv);
+            ld8v<T>(cc.p + vaddr(cc, p.b, p.h, p.w, p.c), cv);
+            ldmask8(mask, mask_mode, p.b * r.C + p.c, ((p.b * r.H + p.h) * r.W + p.w) * r.C + p.c, mk);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = fmaf(rv[i], sc[i], sh[i]) + bcoef * (cv[i] * mk[i]);
+        }
+        st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
+    }
 }
 
 extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma,
@@ -372,12 +460,12 @@ extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const flo
     MOPOE_REQUIRE(r->C % VEC == 0, "combine: C=%d", r->C);
     MOPOE_DISPATCH_T(r->dtype, T, {
         DView<T> ov = make_dview<T>(out);
-        unsigned grid;
+        unsigned grid, stride;
         const long long total = storage_threads(ov);
-        if (apply_grid(total, grid)) return 1;
+        if (apply_grid(total, r->C, grid, stride)) return 1;
         combine_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(make_dview<const T>(r), mean, invstd, gamma, beta,
                                                                         make_dview<const T>(c), mask, mask_mode, a, b, ov,
-                                                                        (unsigned)total);
+                                                                        (unsigned)total, stride);
     });
     MOPOE_CHECK_LAUNCH("combine");
     return 0;
@@ -393,44 +481,58 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T>
                                                                   const float* gamma, const float* sums, float inv_cnt,
                                                                   DView<const T> addend, int has_add, DView<T> out,
                                                                   DView<T> out2, int has_out2, const uint8_t* mask2,
-                                                                  int mask2_mode, float scale2, unsigned total) {
-    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
+                                                                  int mask2_mode, float scale2, unsigned total,
+                                                                  unsigned stride) {
+    unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
-    const Pos p = decode_storage(out, idx);
-    float o[VEC], o2[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = o2[i] = 0.f;
-    if (p.interior) {
-        const int C = x.C;
-        float g[VEC], gt[VEC], xv[VEC], mk[VEC], mu[VEC], is[VEC], ga[VEC], sg[VEC], sgx[VEC], ad[VEC];
-        ld8v<T>(dy.p + vaddr(dy, p.b, p.h, p.w, p.c), g);
-        if (has_gate) ld8v<T>(gate.p + vaddr(gate, p.b, p.h, p.w, p.c), gt);
-        ld8v<T>(x.p + vaddr(x, p.b, p.h, p.w, p.c), xv);
-        const long long bc = (long long)p.b * C + p.c, el = (((long long)p.b * x.H + p.h) * x.W + p.w) * C + p.c;
-        ldmask8(mask, mask_mode, bc, el, mk);
-        ld8f(mean + p.c, mu);
-        ld8f(invstd + p.c, is);
-        ld8f(gamma + p.c, ga);
-        ld8f(sums + p.c, sg);
-        ld8f(sums + C + p.c, sgx);
-        if (has_add) ld8v<T>(addend.p + vaddr(addend, p.b, p.h, p.w, p.c), ad);
+    const int C = x.C;
+    const unsigned CV = (unsigned)C / VEC;
+    const int c = (int)(idx % CV) * VEC;
+    // dv = k1 * (gg - m_g - xh * m_gx),  xh = v * is - mu*is
+    float k1[VEC], mg[VEC], mgx[VEC], is[VEC], mis[VEC];
+    {
+        float mu[VEC], ga[VEC], sg[VEC], sgx[VEC];
+        ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(sums + c, sg); ld8f(sums + C + c, sgx);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-            float gg = gscale * g[i];
-            if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
-            const float xh = (xv[i] * mk[i] - mu[i]) * is[i];
-            const float dv = ga[i] * is[i] * (gg - sg[i] * inv_cnt - xh * sgx[i] * inv_cnt);
-            o[i] = dv * mk[i] + (has_add ? ad[i] : 0.f);
-        }
-        if (has_out2) {
-            float mk2[VEC];
-            ldmask8(mask2, mask2_mode, bc, el, mk2);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) o2[i] = scale2 * g[i] * mk2[i];
+            k1[i] = ga[i] * is[i];
+            mg[i] = sg[i] * inv_cnt;
+            mgx[i] = sgx[i] * inv_cnt;
+            mis[i] = mu[i] * is[i];
         }
     }
-    st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
-    if (has_out2) st8v<T>(out2.p + vaddr(out2, p.b, p.h, p.w, p.c), o2);
+#pragma unroll 2
+    for (; idx < total; idx += stride) {
+        const Pos p = decode_pixel(out, out.fCV8.div(idx), c);
+        float o[VEC], o2[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = o2[i] = 0.f;
+        if (p.interior) {
+            float g[VEC], gt[VEC], xv[VEC], mk[VEC], ad[VEC];
+            ld8v<T>(dy.p + vaddr(dy, p.b, p.h, p.w, p.c), g);
+            if (has_gate) ld8v<T>(gate.p + vaddr(gate, p.b, p.h, p.w, p.c), gt);
+            ld8v<T>(x.p + vaddr(x, p.b, p.h, p.w, p.c), xv);
+            const int bc = p.b * C + p.c, el = ((p.b * x.H + p.h) * x.W + p.w) * C + p.c;
+            ldmask8(mask, mask_mode, bc, el, mk);
+            if (has_add) ld8v<T>(addend.p + vaddr(addend, p.b, p.h, p.w, p.c), ad);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float gg = gscale * g[i];
+                if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
+                const float xh = (xv[i] * mk[i]) * is[i] - mis[i];
+                const float dv = k1[i] * (gg - mg[i] - xh * mgx[i]);
+                o[i] = dv * mk[i] + (has_add ? ad[i] : 0.f);
+            }
+            if (has_out2) {
+                float mk2[VEC];
+                ldmask8(mask2, mask2_mode, bc, el, mk2);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o2[i] = scale2 * g[i] * mk2[i];
+            }
+        }
+        st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
+        if (has_out2) st8v<T>(out2.p + vaddr(out2, p.b, p.h, p.w, p.c), o2);
+    }
 }
 
 static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const mopoe_view_t* x,
@@ -449,13 +551,13 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
     MOPOE_DISPATCH_T(x->dtype, T, {
         DView<T> ov = make_dview<T>(out);
         DView<const T> xv = make_dview<const T>(x);
-        unsigned grid;
+        unsigned grid, stride;
         const long long total = storage_threads(ov);
-        if (apply_grid(total, grid)) return 1;
+        if (apply_grid(total, x->C, grid, stride)) return 1;
         bn_bwd_apply_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(
             make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate != nullptr, gscale, xv, mask, mask_mode,
             mean, invstd, gamma, sums, inv_cnt, addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,
-            out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2, (unsigned)total);
+            out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2, (unsigned)total, stride);
     });
     MOPOE_CHECK_LAUNCH("bn_bwd_apply");
     return 0;
@@ -478,21 +580,26 @@ extern "C" int mopoe_combine_bwd_apply(const mopoe_view_t* dy, float a, const mo
 
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) scale_mask_kernel(DView<const T> dy, const uint8_t* mask, int mask_mode,
-                                                                float scale, DView<T> out, unsigned total) {
-    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
+                                                                float scale, DView<T> out, unsigned total, unsigned stride) {
+    unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
-    const Pos p = decode_storage(out, idx);
-    float o[VEC];
+    const unsigned CV = (unsigned)out.C / VEC;
+    const int c = (int)(idx % CV) * VEC;
+#pragma unroll 2
+    for (; idx < total; idx += stride) {
+        const Pos p = decode_pixel(out, out.fCV8.div(idx), c);
+        float o[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) o[i] = 0.f;
-    if (p.interior) {
-        float g[VEC], mk[VEC];
-        ld8v<T>(dy.p + vaddr(dy, p.b, p.h, p.w, p.c), g);
-        ldmask8(mask, mask_mode, (long long)p.b * dy.C + p.c, (((long long)p.b * dy.H + p.h) * dy.W + p.w) * dy.C + p.c, mk);
+        for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+        if (p.interior) {
+            float g[VEC], mk[VEC];
+            ld8v<T>(dy.p + vaddr(dy, p.b, p.h, p.w, p.c), g);
+            ldmask8(mask, mask_mode, p.b * dy.C + p.c, ((p.b * dy.H + p.h) * dy.W + p.w) * dy.C + p.c, mk);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = scale * g[i] * mk[i];
+            for (int i = 0; i < VEC; ++i) o[i] = scale * g[i] * mk[i];
+        }
+        st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
     }
-    st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
 }
 
 extern "C" int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int mask_mode, float scale,
@@ -501,11 +608,11 @@ extern "C" int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int
     MOPOE_REQUIRE(dy->C % VEC == 0, "scale_mask: C=%d", dy->C);
     MOPOE_DISPATCH_T(dy->dtype, T, {
         DView<T> ov = make_dview<T>(out);
-        unsigned grid;
+        unsigned grid, stride;
         const long long total = storage_threads(ov);
-        if (apply_grid(total, grid)) return 1;
+        if (apply_grid(total, dy->C, grid, stride)) return 1;
         scale_mask_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(make_dview<const T>(dy), mask, mask_mode, scale,
-                                                                           ov, (unsigned)total);
+                                                                           ov, (unsigned)total, stride);
     });
     MOPOE_CHECK_LAUNCH("scale_mask");
     return 0;

@@ -138,7 +138,7 @@ class Engine:
     @staticmethod
     def nchunk(rows, C_, per=1):
         cg = (C_ + 127) // 128
-        want = max(1, (148 * 4 + cg - 1) // cg)
+        want = max(1, (148 * 8 + cg - 1) // cg)
         return int(max(1, min(want, (rows + 31) // 32)))
 
     def f32(self, *shape):

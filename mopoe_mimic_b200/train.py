@@ -141,14 +141,20 @@ def basic_routine_epoch(exp, batch):
     return {'results': results, 'log_probs': log_probs, 'total_loss': total_loss, 'klds': klds}
 
 
-def train_step(exp, batch, allreduce=None):
-    """run_epochs.train:118-131 for one batch: forward + loss, zero_grad, backward, (DP all-reduce), Adam."""
+def forward_backward(exp, batch):
+    """forward + ELBO + zero_grad + backward (everything of the step before the gradient exchange)"""
     eng = exp.mm_vae.rt.engine
     if eng is not None:
         eng.begin_step()
     out = basic_routine_epoch(exp, batch)
     exp.optimizer.zero_grad()
     out['total_loss'].backward()
+    return out
+
+
+def train_step(exp, batch, allreduce=None):
+    """run_epochs.train:118-131 for one batch: forward + loss, zero_grad, backward, (DP all-reduce), Adam."""
+    out = forward_backward(exp, batch)
     if allreduce is not None:
         allreduce(exp.mm_vae.flat_grads)
     exp.optimizer.step()
@@ -156,8 +162,10 @@ def train_step(exp, batch, allreduce=None):
 
 
 class GraphedTrainStep:
-    """The whole training step (forward, ELBO, backward, DP all-reduce, Adam) captured ONCE into a CUDA graph and
-    replayed per batch: ~1000 kernel launches become one graph launch, so the host never gates the device.
+    """The training step captured ONCE into CUDA graphs and replayed per batch: ~1000 kernel launches become one
+    graph launch, so the host never gates the device.  Single GPU: one graph (forward, ELBO, backward, Adam).
+    Data parallel: graph A (forward, ELBO, backward) -> NCCL all-reduce of the flat gradient buffer, launched by
+    the host between the graphs -> graph B (Adam).
 
     Everything step-dependent lives in device memory (dropout step counter, Adam step / bias corrections), the
     batch is copied into static input buffers, and the scalars the reference logs come back as one packed vector.
@@ -167,6 +175,7 @@ class GraphedTrainStep:
         flags = exp.flags
         dev = flags.device
         self.exp = exp
+        self.allreduce = allreduce
         self.static = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in example_batch.items()}
         for k, v in example_batch.items():
             self.static[k].copy_(v)
@@ -181,11 +190,17 @@ class GraphedTrainStep:
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        mode = 'thread_local' if allreduce is not None else 'global'
-        with torch.cuda.graph(self.graph, capture_error_mode=mode):
-            out = train_step(exp, (dict(self.static), None), allreduce)
+        self.graph_b = None
+        with torch.cuda.graph(self.graph):
+            out = forward_backward(exp, (dict(self.static), None))
             self.stats = packed_stats(out)
             self.nan_flag = out['results']['latents']['_nan_flag']
+            if allreduce is None:
+                exp.optimizer.step()
+        if allreduce is not None:
+            self.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):
+                exp.optimizer.step()
         flags.dataset = saved_dataset
         self.keys = (['total_loss', 'joint_divergence'] + ['kld.' + k for k in out['klds']]
                      + ['log_prob.' + k for k in out['log_probs']])
@@ -194,6 +209,9 @@ class GraphedTrainStep:
         for k, t in self.static.items():
             t.copy_(batch[k], non_blocking=True)
         self.graph.replay()
+        if self.graph_b is not None:
+            self.allreduce(self.exp.mm_vae.flat_grads)
+            self.graph_b.replay()
         return self.stats
 
     def check_latents(self):
