@@ -77,6 +77,13 @@ int mopoe_tc_wgrad_built(void);
 int mopoe_conv_gemm(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D,
                     int impl, void* stream);
 
+/* Same contraction for up to 4 problems of IDENTICAL shape (E0,E1,E2,R,KW,N, output tensor and row strides) in one
+ * launch — the 2^nd sub-pixel phases of a stride-2 nn.ConvTranspose{1,2}d (ResidualBlocks.py:44-46,108-110) or of a
+ * strided conv's input gradient: they differ only in window origin, weight slice and output origin.  On the tcgen05
+ * path this is a persistent kernel (one CTA per SM, double-buffered TMEM accumulators). */
+int mopoe_conv_gemm_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                            const mopoe_rows_t* D, int impl, void* stream);
+
 /* dWp[n, r*KW + k] (+)= sum_m dY[m, n] * A[m,r,k]   (fp32 output).  `ws` holds split partials
  * (ws_bytes from mopoe_conv_wgrad_ws); replaces the weight-gradient half of autograd's conv backward
  * (run_epochs.py:130 total_loss.backward()). */

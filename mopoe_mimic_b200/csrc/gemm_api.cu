@@ -30,3 +30,19 @@ extern "C" int mopoe_conv_wgrad(const mopoe_window_t* A, const mopoe_rows_t* dY,
     if (impl != 1 && mopoe_tc_wgrad_eligible(A, dY)) return mopoe_conv_wgrad_tc(A, dY, dWp, accumulate, ws, ws_bytes, stream);
     return mopoe_conv_wgrad_simt(A, dY, dWp, accumulate, ws, ws_bytes, stream);
 }
+
+// ---- batched fprop/dgrad: up to 4 problems of identical shape in one launch (sub-pixel phases) -------------------------
+int mopoe_conv_gemm_tc_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                               const mopoe_rows_t* D, void* stream);
+
+extern "C" int mopoe_conv_gemm_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                                       const mopoe_rows_t* D, int impl, void* stream) {
+    MOPOE_REQUIRE(nprob >= 1 && nprob <= 4, "conv_gemm_batched: nprob=%d (1..4)", nprob);
+    bool tc = impl != 1;
+    for (int i = 0; i < nprob && tc; ++i) tc = mopoe_tc_fwd_eligible(&A[i], &D[i]) != 0;
+    if (impl == 2 && !tc) MOPOE_FAIL("conv_gemm_batched: tcgen05 path forced but problem not eligible");
+    if (tc) return mopoe_conv_gemm_tc_batched(nprob, A, Wp, bias, D, stream);
+    for (int i = 0; i < nprob; ++i)
+        if (mopoe_conv_gemm_simt(&A[i], Wp[i], bias, &D[i], stream)) return 1;
+    return 0;
+}

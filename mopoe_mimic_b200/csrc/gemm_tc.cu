@@ -518,3 +518,12 @@ int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* 
     }
     return 0;
 }
+
+// ---- helpers shared with gemm_tc_persist.cu ---------------------------------------------------------------------------
+int mopoe_tc_encode(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                    const uint32_t* box, const char* what) {
+    return encode_map(map, base, rank, dims, strides_elems, box, what);
+}
+int mopoe_tc_init_state() { return tc_init(); }
+void mopoe_tc_tile_split(int E0, int E1, int rows, int& BX, int& BY, int& NB) { tile_split(E0, E1, rows, BX, BY, NB); }
+int mopoe_tc_pick_bn(int N) { return pick_bn(N); }

@@ -76,6 +76,9 @@ class Engine:
         self.rng_offset = 0
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)   # device-side training-step counter
         self._packs = {}
+        import os
+        self.batched = os.environ.get('MOPOE_GEMM_BATCHED', '1') != '0'       # phases of a deconv in one launch
+        self.persistent = os.environ.get('MOPOE_GEMM_PERSISTENT', '1') != '0'   # persistent kernel for single GEMMs too
         self.profile = None     # list of (start_event, end_event, flops, kind) when bench.py instruments a step
 
     # ---- packed-weight cache: each re-layout is computed once per optimizer step (forward and backward share it)
@@ -230,10 +233,25 @@ class Engine:
         return r
 
     def _gemm(self, win, wp, bias, rows):
-        assert wp.is_contiguous() and wp.dtype == self._win_dtype(win)
-        flops = 2.0 * win.E0 * win.E1 * win.E2 * rows.N * win.R * win.KW
-        self._timed('fprop/dgrad', flops, lambda: L.call('mopoe_conv_gemm', C.byref(win), L.ptr(wp), L.ptr(bias),
-                                                         C.byref(rows), self.impl, L.stream_ptr()))
+        self._gemm_batched([win], [wp], bias, [rows])
+
+    def _gemm_batched(self, wins, wps, bias, rows_list):
+        """up to 4 same-shape problems in ONE launch (persistent tcgen05 kernel when eligible)"""
+        n = len(wins)
+        for wp in wps:
+            assert wp.is_contiguous() and wp.dtype == self._win_dtype(wins[0])
+        flops = sum(2.0 * w.E0 * w.E1 * w.E2 * r.N * w.R * w.KW for w, r in zip(wins, rows_list))
+        if self.batched and (n > 1 or self.persistent):
+            WA = (L.Window * n)(*wins)
+            RA = (L.Rows * n)(*rows_list)
+            PA = (C.c_void_p * n)(*[wp.data_ptr() for wp in wps])
+            self._timed('fprop/dgrad', flops, lambda: L.call('mopoe_conv_gemm_batched', n, WA, PA, L.ptr(bias), RA,
+                                                             self.impl, L.stream_ptr()))
+        else:
+            for w, wp, r in zip(wins, wps, rows_list):
+                f1 = 2.0 * w.E0 * w.E1 * w.E2 * r.N * w.R * w.KW
+                self._timed('fprop/dgrad', f1, lambda w=w, wp=wp, r=r: L.call(
+                    'mopoe_conv_gemm', C.byref(w), L.ptr(wp), L.ptr(bias), C.byref(r), self.impl, L.stream_ptr()))
 
     @staticmethod
     def _win_dtype(win):
@@ -288,22 +306,24 @@ class Engine:
         assert x.pw >= 1 and (x.H == 1 or x.ph >= 1)
         if x.H == 1:
             out = Act.empty(x.B, 1, 2 * x.W, n, 0, 0, out_dtype or x.dtype, self.device)
+            wins, rows_l = [], []
             for px in range(2):
-                win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, 1, x.B, 1, 2 * Cc, 0,
-                               (x.pw - 1 + px) * Cc, Cc, 0, x.Ws * Cc, 0)
-                rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, px * n, 2 * n, 0, 2 * x.W * n)
-                self._gemm(win, wph[px], bias, rows)
+                wins.append(L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, 1, x.B, 1, 2 * Cc, 0,
+                                     (x.pw - 1 + px) * Cc, Cc, 0, x.Ws * Cc, 0))
+                rows_l.append(L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, px * n, 2 * n, 0, 2 * x.W * n))
+            self._gemm_batched(wins, list(wph), bias, rows_l)
             return out
         out = Act.empty(x.B, 2 * x.H, 2 * x.W, n, 0, 0, out_dtype or x.dtype, self.device)
         OW = 2 * x.W
+        wins, rows_l = [], []
         for py in range(2):
             for px in range(2):
                 a_off = ((x.ph - 1 + py) * x.Ws + (x.pw - 1 + px)) * Cc
-                win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 2, 2 * Cc, 0,
-                               a_off, Cc, x.Ws * Cc, x.Hs * x.Ws * Cc, x.Ws * Cc)
-                rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, (py * OW + px) * n, 2 * n, 2 * OW * n,
-                              2 * x.H * OW * n)
-                self._gemm(win, wph[py * 2 + px], bias, rows)
+                wins.append(L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 2, 2 * Cc, 0,
+                                     a_off, Cc, x.Ws * Cc, x.Hs * x.Ws * Cc, x.Ws * Cc))
+                rows_l.append(L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, (py * OW + px) * n, 2 * n,
+                                     2 * OW * n, 2 * x.H * OW * n))
+        self._gemm_batched(wins, list(wph), bias, rows_l)
         return out
 
     def gemm_rows(self, x, w, bias, n, out_shape=None, out_dtype=None):
