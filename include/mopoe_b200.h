@@ -91,6 +91,13 @@ size_t mopoe_conv_wgrad_ws(const mopoe_window_t* A, const mopoe_rows_t* dY, int 
 int mopoe_conv_wgrad(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate,
                      void* ws, size_t ws_bytes, int impl, void* stream);
 
+/* Weight gradient delivered in the PARAMETER's layout: grad[a][b][t] (+)= sum_m dY[m, a] * A[m, (t, b')]  (b' < bpad,
+ * the window's channel padding).  The split-K reduction, the conv-form -> [a][b][taps] re-layout and the accumulation
+ * into the caller's (flat) gradient buffer are one kernel after the GEMM.  ws_bytes from mopoe_conv_wgrad_param_ws. */
+size_t mopoe_conv_wgrad_param_ws(const mopoe_window_t* A, const mopoe_rows_t* dY, int impl);
+int mopoe_conv_wgrad_param(const mopoe_window_t* A, const mopoe_rows_t* dY, float* grad, int pa, int pb, int taps,
+                           int bpad, int accumulate, void* ws, size_t ws_bytes, int impl, void* stream);
+
 /* out[c] (+)= sum over rows of v[.., c]  (bias gradients).  ws: 2*nchunk*C doubles. */
 int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, void* stream);
 
@@ -143,6 +150,10 @@ int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint64_t offset,
  * 1 phase-form (py,px) [B, taps*A], 2 full-form [KH*KW*B, A], 3 [A,B], 4 [B,A]  (layouts in DESIGN.md). */
 int mopoe_pack_weight(const float* W, int A, int B, int KH, int KW, int form, int py, int px, int bpad,
                       void* dst, int dst_dtype, void* stream);
+/* same re-layouts through a shared-memory tile (sector-efficient reads AND writes); form 1 fills dsts[0..3]
+ * (2-D) / dsts[0..1] (1-D) with all sub-pixel phases in one launch; form 3 = [A,B], form 4 = [B,A] for 1x1 kernels. */
+int mopoe_pack_weight_tiled(const float* W, int A, int B, int KH, int KW, int form, int bpad, void* const* dsts,
+                            int dst_dtype, void* stream);
 /* advance the device-side step state (dropout step counter, Adam step + bias-correction coefficients) */
 int mopoe_step_advance(uint64_t* rng_step, int32_t* adam_step, float* adam_coef, float lr, float beta1,
                        float beta2, void* stream);

@@ -63,6 +63,9 @@ SIGNATURES = {
     'mopoe_scale_mask': (_I, [_V, _P, _I, _F, _V, _P]),
     'mopoe_convert': (_I, [_V, _I, _V, _P]),
     'mopoe_dropout_mask': (_I, [_P, _L, C.c_uint64, C.c_uint64, _P, _P]),
+    'mopoe_pack_weight_tiled': (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
+    'mopoe_conv_wgrad_param_ws': (_S, [_W, _R, _I]),
+    'mopoe_conv_wgrad_param': (_I, [_W, _R, _P, _I, _I, _I, _I, _I, _P, _S, _I, _P]),
     'mopoe_pack_weight': (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     'mopoe_step_advance': (_I, [_P, _P, _P, _F, _F, _F, _P]),
     'mopoe_adam_flat_dev': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),

@@ -102,14 +102,17 @@ def _main_dgrad(eng, spec, dout, Wg, dtype, H, W):
     raise NotImplementedError('dgrad for stride-4 blocks (256 px) is not built yet')
 
 
-def _main_wgrad(eng, spec, xin, dout, shape):
-    """weight gradient in the parameter's own layout"""
+def _main_wgrad(eng, spec, xin, dout, param):
+    """weight gradient of conv2 / shortcut: accumulated straight into param.grad when the model's gradients live in
+    the flat buffer (returns None for autograd), else returned in the parameter's layout"""
     if spec.transposed:
         s = 1 if spec.kind == 'U' else 2
-        g = eng.wgrad_down(dout, 4, s, spec.pad if spec.kind == 'S' else 0, xin)
+        args = (dout, 4, s, spec.pad if spec.kind == 'S' else 0, xin)
     else:
-        g = eng.wgrad_down(xin, 4, spec.stride, spec.pad, dout)
-    return conv_form_grad(g, shape)
+        args = (xin, 4, spec.stride, spec.pad, dout)
+    if eng.wgrad_down_param(*args, param):
+        return None
+    return conv_form_grad(eng.wgrad_down(*args), param.shape)
 
 
 class ResBlockFn(torch.autograd.Function):
@@ -181,14 +184,14 @@ class ResBlockFn(torch.autograd.Function):
                                  Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device))
         # shortcut conv
         Ws_ = P[short + '.0.weight']
-        G[short + '.0.weight'] = _main_wgrad(eng, sp, x, dr, Ws_.shape)
+        G[short + '.0.weight'] = _main_wgrad(eng, sp, x, dr, run.param_objs[short + '.0.weight'])
         # the shortcut bias feeds a train-mode BatchNorm: its gradient sum(dr) is analytically zero (BN backward
         # output sums to zero per channel); the reference only accumulates rounding noise there
         G[short + '.0.bias'] = torch.zeros(sp.cout, dtype=torch.float32, device=eng.device)
         dxs = _main_dgrad(eng, sp, dr, Ws_, dt, H, W)
         # conv2
         W2 = P['conv2.weight']
-        G['conv2.weight'] = _main_wgrad(eng, sp, a2, dc, W2.shape)
+        G['conv2.weight'] = _main_wgrad(eng, sp, a2, dc, run.param_objs['conv2.weight'])
         if sp.inner_bias:
             G['conv2.bias'] = eng.colsum(dc)
         da2 = _main_dgrad(eng, sp, dc, W2, dt, H, W)

@@ -5,14 +5,16 @@
 int mopoe_conv_gemm_simt(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* stream);
 size_t mopoe_conv_wgrad_ws_simt(const mopoe_window_t* A, const mopoe_rows_t* dY);
 int mopoe_conv_wgrad_simt(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
-                          size_t ws_bytes, void* stream);
+                          size_t ws_bytes, void* stream, const int* fin);
+size_t mopoe_conv_wgrad_ws_simt_fin(const mopoe_window_t* A, const mopoe_rows_t* dY);
+size_t mopoe_conv_wgrad_ws_tc_fin(const mopoe_window_t* A, const mopoe_rows_t* dY);
 // gemm_tc.cu
 int mopoe_tc_fwd_eligible(const mopoe_window_t* A, const mopoe_rows_t* D);
 int mopoe_conv_gemm_tc(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* stream);
 int mopoe_tc_wgrad_eligible(const mopoe_window_t* A, const mopoe_rows_t* dY);
 size_t mopoe_conv_wgrad_ws_tc(const mopoe_window_t* A, const mopoe_rows_t* dY);
 int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
-                        size_t ws_bytes, void* stream);
+                        size_t ws_bytes, void* stream, const int* fin);
 
 extern "C" int mopoe_conv_gemm(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D,
                                int impl, void* stream) {
@@ -27,8 +29,8 @@ extern "C" size_t mopoe_conv_wgrad_ws(const mopoe_window_t* A, const mopoe_rows_
 extern "C" int mopoe_conv_wgrad(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
                                 size_t ws_bytes, int impl, void* stream) {
     if (impl == 2 && !mopoe_tc_wgrad_eligible(A, dY)) MOPOE_FAIL("conv_wgrad: tcgen05 path forced but problem not eligible");
-    if (impl != 1 && mopoe_tc_wgrad_eligible(A, dY)) return mopoe_conv_wgrad_tc(A, dY, dWp, accumulate, ws, ws_bytes, stream);
-    return mopoe_conv_wgrad_simt(A, dY, dWp, accumulate, ws, ws_bytes, stream);
+    if (impl != 1 && mopoe_tc_wgrad_eligible(A, dY)) return mopoe_conv_wgrad_tc(A, dY, dWp, accumulate, ws, ws_bytes, stream, nullptr);
+    return mopoe_conv_wgrad_simt(A, dY, dWp, accumulate, ws, ws_bytes, stream, nullptr);
 }
 
 // ---- batched fprop/dgrad: up to 4 problems of identical shape in one launch (sub-pixel phases) -------------------------
@@ -45,4 +47,19 @@ extern "C" int mopoe_conv_gemm_batched(int nprob, const mopoe_window_t* A, const
     for (int i = 0; i < nprob; ++i)
         if (mopoe_conv_gemm_simt(&A[i], Wp[i], bias, &D[i], stream)) return 1;
     return 0;
+}
+
+// ---- weight gradient straight into the parameter's layout --------------------------------------------------------------
+// grad[a][b][t] (+)= conv-form( sum_m dY[m, n=a] * A[m, (t, b')] ), b' < bpad: split reduction, re-layout and
+// accumulation into the (flat) gradient buffer are ONE kernel after the GEMM.
+extern "C" size_t mopoe_conv_wgrad_param_ws(const mopoe_window_t* A, const mopoe_rows_t* dY, int impl) {
+    if (impl != 1 && mopoe_tc_wgrad_eligible(A, dY)) return mopoe_conv_wgrad_ws_tc_fin(A, dY);
+    return mopoe_conv_wgrad_ws_simt_fin(A, dY);
+}
+extern "C" int mopoe_conv_wgrad_param(const mopoe_window_t* A, const mopoe_rows_t* dY, float* grad, int pa, int pb, int taps,
+                                      int bpad, int accumulate, void* ws, size_t ws_bytes, int impl, void* stream) {
+    const int fin[4] = {pa, pb, taps, bpad};
+    if (impl == 2 && !mopoe_tc_wgrad_eligible(A, dY)) MOPOE_FAIL("conv_wgrad_param: tcgen05 path forced but problem not eligible");
+    if (impl != 1 && mopoe_tc_wgrad_eligible(A, dY)) return mopoe_conv_wgrad_tc(A, dY, grad, accumulate, ws, ws_bytes, stream, fin);
+    return mopoe_conv_wgrad_simt(A, dY, grad, accumulate, ws, ws_bytes, stream, fin);
 }

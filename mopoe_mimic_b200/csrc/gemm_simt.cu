@@ -253,27 +253,38 @@ size_t mopoe_conv_wgrad_ws_simt(const mopoe_window_t* A, const mopoe_rows_t* dY)
     int Z = wgrad_splits(M, dY->N, K);
     return Z > 1 ? (size_t)Z * dY->N * K * sizeof(float) : 0;
 }
+void mopoe_wgrad_finish_launch(const float* part, int Z, int A, int B, int T, int bpad, float* grad, int accumulate,
+                               cudaStream_t st);
+size_t mopoe_conv_wgrad_ws_simt_fin(const mopoe_window_t* A, const mopoe_rows_t* dY) {
+    long long M = (long long)A->E0 * A->E1 * A->E2;
+    int K = A->R * A->KW;
+    return (size_t)wgrad_splits(M, dY->N, K) * dY->N * K * sizeof(float);
+}
 int mopoe_conv_wgrad_simt(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
-                          size_t ws_bytes, void* stream) {
+                          size_t ws_bytes, void* stream, const int* fin) {
     const long long Ml = (long long)A->E0 * A->E1 * A->E2;
     const int K = A->R * A->KW;
     MOPOE_REQUIRE(Ml > 0 && Ml < (1ll << 31), "conv_wgrad: M=%lld", Ml);
     MOPOE_REQUIRE(A->KW % 8 == 0, "conv_wgrad: KW=%d must be a multiple of 8", A->KW);
     MOPOE_REQUIRE(A->a_dtype == dY->d_dtype, "conv_wgrad: A and dY dtypes differ");
     int Z = wgrad_splits(Ml, dY->N, K);
-    size_t need = Z > 1 ? (size_t)Z * dY->N * K * sizeof(float) : 0;
+    size_t need = (Z > 1 || fin) ? (size_t)Z * dY->N * K * sizeof(float) : 0;
     MOPOE_REQUIRE(ws_bytes >= need, "conv_wgrad: workspace %zu < %zu", ws_bytes, need);
     int mps = (int)(ceil_div64(ceil_div64(Ml, Z), BK) * BK);
     dim3 grid((unsigned)ceil_div64(K, BM), (unsigned)ceil_div64(dY->N, BN), Z);
     cudaStream_t st = (cudaStream_t)stream;
     WinDev w = to_dev(A);
     RowsDev r = to_dev(dY);
-    float* out = Z > 1 ? (float*)ws : dWp;
+    float* out = (Z > 1 || fin) ? (float*)ws : dWp;
     MOPOE_DISPATCH_T(A->a_dtype, T, {
-        gemm_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>(w, r, out, (int)Ml, K, mps, Z == 1, accumulate);
+        gemm_wgrad_simt_kernel<T><<<grid, 256, 0, st>>>(w, r, out, (int)Ml, K, mps, Z == 1, fin ? 0 : accumulate);
     });
     MOPOE_CHECK_LAUNCH("gemm_wgrad_simt");
-    if (Z > 1) {
+    if (fin) {
+        MOPOE_REQUIRE(fin[0] == dY->N && fin[2] * fin[3] == K, "conv_wgrad: finish spec does not match N/K");
+        mopoe_wgrad_finish_launch((const float*)ws, Z, fin[0], fin[1], fin[2], fin[3], dWp, accumulate, st);
+        MOPOE_CHECK_LAUNCH("wgrad_finish");
+    } else if (Z > 1) {
         long long n = (long long)dY->N * K;
         split_reduce_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>((const float*)ws, Z, n, dWp, accumulate);
         MOPOE_CHECK_LAUNCH("split_reduce");

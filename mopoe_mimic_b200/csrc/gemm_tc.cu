@@ -429,6 +429,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 }
 
 void mopoe_split_reduce_launch(const float* ws, int Z, long long n, float* out, int accumulate, cudaStream_t st);
+void mopoe_wgrad_finish_launch(const float* part, int Z, int A, int B, int T, int bpad, float* grad, int accumulate,
+                               cudaStream_t st);
 
 extern "C" int mopoe_tc_wgrad_built(void) { return 1; }
 
@@ -459,11 +461,19 @@ static void wg_plan(const mopoe_window_t* A, const mopoe_rows_t* dY, TcWgParams&
     p.JT = (p.KW + p.BNJ - 1) / p.BNJ;
     p.tmem_cols = pow2_ceil(p.BNJ < 32 ? 32 : p.BNJ);
     const int tiles_out = p.R * p.JT * ((p.N + 127) / 128);
-    int Z = (148 * 2 + tiles_out - 1) / tiles_out;
-    if (Z > p.TM) Z = p.TM;
+    // split count: fill the 148 SMs in whole waves (a 2.05-wave grid wastes a third of its time in the tail) while
+    // keeping >= 8 pixel blocks per CTA and the partials workspace bounded
     const long long ws_cap = 1ll << 29;              // 512 MB of partials at most
-    while (Z > 1 && (long long)Z * p.N * p.K * 4 > ws_cap) --Z;
-    if (Z < 1) Z = 1;
+    int Z = 1;
+    double best_eff = -1.0;
+    for (int z = 1; z <= 64 && z <= p.TM; ++z) {
+        if (z > 1 && (p.TM / z < 8 || (long long)z * p.N * p.K * 4 > ws_cap)) break;
+        const long long items = (long long)tiles_out * z;
+        const long long waves = (items + 147) / 148;
+        if (waves > 4 && z > 1) break;
+        const double eff = (double)items / (double)(waves * 148);
+        if (eff > best_eff + 0.02) { best_eff = eff; Z = z; }
+    }
     p.m_per_split = (p.TM + Z - 1) / Z;
     p.Z = (p.TM + p.m_per_split - 1) / p.m_per_split;
     const int stage_bytes = 2 * WG_BKM * 128 + (p.BNJ / 64) * WG_BKM * 128;
@@ -480,14 +490,17 @@ size_t mopoe_conv_wgrad_ws_tc(const mopoe_window_t* A, const mopoe_rows_t* dY) {
 
 static bool g_wg_attr_set = false;
 
+// fin != nullptr: partial sums always go to `ws`, then ONE kernel reduces the splits, re-lays the conv-form gradient
+// out into the parameter's own layout and accumulates into the (flat) gradient buffer: fin = {A, B, taps, bpad}
 int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* dWp, int accumulate, void* ws,
-                        size_t ws_bytes, void* stream) {
+                        size_t ws_bytes, void* stream, const int* fin) {
     TcWgParams p;
     wg_plan(A, dY, p);
-    const size_t need = p.Z > 1 ? (size_t)p.Z * p.N * p.K * sizeof(float) : 0;
+    const size_t need = (p.Z > 1 || fin) ? (size_t)p.Z * p.N * p.K * sizeof(float) : 0;
     MOPOE_REQUIRE(ws_bytes >= need, "conv_wgrad_tc: workspace %zu < %zu", ws_bytes, need);
-    p.out = p.Z > 1 ? (float*)ws : dWp;
-    p.accumulate = accumulate;
+    p.out = (p.Z > 1 || fin) ? (float*)ws : dWp;
+    p.accumulate = fin ? 0 : accumulate;
+    if (fin) p.Z = p.Z;   // (Z == 1 with fin: the kernel's direct path writes the single partial into ws[0])
     CUtensorMap mapA, mapY;
     {
         const uint64_t dims[5] = {(uint64_t)A->KW, (uint64_t)A->E0, (uint64_t)A->E1, (uint64_t)A->R, (uint64_t)A->E2};
@@ -512,11 +525,20 @@ int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* 
     cudaStream_t st = (cudaStream_t)stream;
     conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapY, p);
     MOPOE_CHECK_LAUNCH("conv_wgrad_tc");
-    if (p.Z > 1) {
+    if (fin) {
+        MOPOE_REQUIRE(fin[0] == p.N && (long long)fin[2] * fin[3] == p.K, "conv_wgrad_tc: finish spec does not match N/K");
+        mopoe_wgrad_finish_launch((const float*)ws, p.Z, fin[0], fin[1], fin[2], fin[3], dWp, accumulate, st);
+        MOPOE_CHECK_LAUNCH("wgrad_finish");
+    } else if (p.Z > 1) {
         mopoe_split_reduce_launch((const float*)ws, p.Z, (long long)p.N * p.K, dWp, accumulate, st);
         MOPOE_CHECK_LAUNCH("split_reduce");
     }
     return 0;
+}
+size_t mopoe_conv_wgrad_ws_tc_fin(const mopoe_window_t* A, const mopoe_rows_t* dY) {
+    TcWgParams p;
+    wg_plan(A, dY, p);
+    return (size_t)p.Z * p.N * p.K * sizeof(float);
 }
 
 // ---- helpers shared with gemm_tc_persist.cu ---------------------------------------------------------------------------

@@ -93,26 +93,23 @@ class Engine:
             KH, KW = (1, 1) if W.dim() == 2 else ((1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3]))
             code = L.dtype_code(self.dtype)
 
-            def run(fcode, shape, py=0, px=0):
-                dst = torch.empty(shape, dtype=self.dtype, device=self.device)
-                L.call('mopoe_pack_weight', L.ptr(W), A, B, KH, KW, fcode, py, px, bpad or B, L.ptr(dst), code,
-                       L.stream_ptr())
-                return dst
+            def run(fcode, shapes):
+                dsts = [torch.empty(sh, dtype=self.dtype, device=self.device) for sh in shapes]
+                arr = (C.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
+                L.call('mopoe_pack_weight_tiled', L.ptr(W), A, B, KH, KW, fcode, bpad or B, arr, code, L.stream_ptr())
+                return dsts
             if form == 'conv':
-                hit = run(0, (A, KH * KW * (bpad or B)))
+                hit = run(0, [(A, KH * KW * (bpad or B))])[0]
             elif form == 'phase':
-                if KH > 1:
-                    hit = [run(1, (B, 4 * A), py, px) for py in range(2) for px in range(2)]
-                else:
-                    hit = [run(1, (B, 2 * A), 0, px) for px in range(2)]
+                hit = run(1, [(B, 4 * A)] * 4 if KH > 1 else [(B, 2 * A)] * 2)
             elif form == 'full':
-                hit = run(2, (KH * KW * B, A))
+                hit = run(2, [(KH * KW * B, A)])[0]
             elif form == 'mat':        # [n, k] from a 1x1 kernel / linear weight [n, k, 1(, 1)]
                 assert KH == 1 and KW == 1
-                hit = run(3, (A, B))
+                hit = run(3, [(A, B)])[0]
             elif form == 'matT':
                 assert KH == 1 and KW == 1
-                hit = run(4, (B, A))
+                hit = run(4, [(B, A)])[0]
             else:
                 raise ValueError(form)
             self._packs[key] = hit
@@ -265,6 +262,27 @@ class Engine:
         self._timed('wgrad', flops, lambda: L.call('mopoe_conv_wgrad', C.byref(win), C.byref(rows), L.ptr(out), 0,
                                                    L.ptr(ws), nbytes, self.impl, L.stream_ptr()))
         return out
+
+    def _wgrad_param(self, win, rows, param, taps, bpad):
+        """weight gradient accumulated straight into param.grad (parameter layout [a, b, *taps]); False if the
+        parameter has no contiguous .grad to accumulate into (caller then uses the packed-gradient path)"""
+        g = param.grad
+        if g is None or not g.is_contiguous() or g.dtype != torch.float32:
+            return False
+        A, B = param.shape[0], param.shape[1]
+        lib = L.load()
+        nbytes = lib.mopoe_conv_wgrad_param_ws(C.byref(win), C.byref(rows), self.impl)
+        ws = self.wsf(nbytes)
+        flops = 2.0 * win.E0 * win.E1 * win.E2 * rows.N * win.R * win.KW
+        self._timed('wgrad', flops, lambda: L.call('mopoe_conv_wgrad_param', C.byref(win), C.byref(rows), L.ptr(g), A, B,
+                                                   taps, bpad, 1, L.ptr(ws), nbytes, self.impl, L.stream_ptr()))
+        return True
+
+    def wgrad_down_param(self, xwin, k, s, p, yrows, param, bpad=None):
+        win, OH, OW = self.win_down(xwin, k, s, p)
+        assert (yrows.H, yrows.W, yrows.B) == (OH, OW, xwin.B), ((yrows.H, yrows.W), (OH, OW))
+        taps = param[0, 0].numel()
+        return self._wgrad_param(win, self.rows_of(yrows), param, taps, bpad or param.shape[1])
 
     @staticmethod
     def win_down(x, k, s, p):

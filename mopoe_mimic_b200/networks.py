@@ -118,6 +118,7 @@ class ResBlock(nn.Module):
         run = BlockRun(eng, sp, B, H, W, in_pad, out_pad, train, bufs, masks)
         named = dict(self.named_parameters())
         params = [named[n] for n in sp.param_names()]
+        run.param_objs = dict(zip(sp.param_names(), params))     # the Parameter objects (their .grad is the flat view)
         return ResBlockFn.apply(x_t, run, *params)
 
 
