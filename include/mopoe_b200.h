@@ -119,16 +119,20 @@ int mopoe_combine(const mopoe_view_t* r, const float* mean, const float* invstd,
                   const float* beta, const mopoe_view_t* c, const uint8_t* mask, int mask_mode,
                   float a, float b, const mopoe_view_t* out, void* stream);
 /* BN backward, reduction half: g = gscale * dy * [gate > 0];  xhat = (x*2mask - mean)*invstd;
- * dbeta (+)= sum g, dgamma (+)= sum g*xhat, sums[0:C] = sum g, sums[C:2C] = sum g*xhat. */
+ * dbeta (+)= sum g, dgamma (+)= sum g*xhat, sums[0:C] = sum g, sums[C:2C] = sum g*xhat.
+ * The ReLU gate is either read from `gate` (the saved activation), or — gate == NULL and gate_gamma/gate_beta
+ * given — RECOMPUTED as [gamma*xhat + beta > 0] with the forward kernel's exact arithmetic (no activation re-read),
+ * or absent (all NULL). */
 int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                         const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
                         const float* mean, const float* invstd, double* ws, int nchunk,
-                        float* dgamma, float* dbeta, int accumulate, float* sums, void* stream);
+                        float* dgamma, float* dbeta, int accumulate, float* sums,
+                        const float* gate_gamma, const float* gate_beta, void* stream);
 /* BN backward, apply half: out = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend. */
 int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                        const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
                        const float* mean, const float* invstd, const float* gamma, const float* sums,
-                       const mopoe_view_t* addend, const mopoe_view_t* out, void* stream);
+                       const mopoe_view_t* addend, const mopoe_view_t* out, const float* gate_beta, void* stream);
 /* backward of `y = a*BN(r) + b*(c*2mask2)` in ONE pass over dy: dr = BN-backward of g = a*dy (sums from
  * mopoe_bn_bwd_reduce), dc = b * dy * 2mask2; dr and dc must share their border widths. */
 int mopoe_combine_bwd_apply(const mopoe_view_t* dy, float a, const mopoe_view_t* r, const float* mean,

@@ -97,6 +97,19 @@ __device__ __forceinline__ void ldmask8(const uint8_t* m, int mode, int bc_idx, 
     }
 }
 
+// y = v * sc + sh  ==  gamma * (v - mean) * invstd + beta.  ONE definition shared by the forward apply kernel and
+// the backward kernels that RECOMPUTE the ReLU gate from x instead of re-reading the activation: identical
+// instruction sequence -> bit-identical sign decisions.
+__device__ __forceinline__ void bn_affine(const float (&mu)[8], const float (&is)[8], const float (&ga)[8],
+                                          const float (&be)[8], float (&sc)[8], float (&sh)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = is[i] * ga[i];
+        sh[i] = be[i] - mu[i] * sc[i];
+    }
+}
+__device__ __forceinline__ float bn_eval(float v, float sc, float sh) { return fmaf(v, sc, sh); }
+
 // position of a flat thread index over the STORAGE (interior + zero border) of an output view
 struct Pos {
     int b, h, w, c;
@@ -162,7 +175,8 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DView<const T> dy, DView<const T> gate,
                                                           int has_gate, float gscale, const uint8_t* mask,
                                                           int mask_mode, const float* mean, const float* invstd,
-                                                          double* ws, int nchunk) {
+                                                          const float* ggamma, const float* gbeta, double* ws,
+                                                          int nchunk) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = (blockIdx.x * 16 + tx) * VEC;
     const bool cvalid = c < x.C;
@@ -174,10 +188,16 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
     float f0[VEC], f1[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) f0[i] = f1[i] = 0.f;
-    float mu[VEC], is[VEC];
+    float mu[VEC], is[VEC], gsc[VEC], gsh[VEC];
     if (MODE == RED_BNBWD && cvalid) {
         ld8f(mean + c, mu);
         ld8f(invstd + c, is);
+        if (has_gate == 2) {              // gate = [relu(BN(x)) > 0], recomputed from x: no activation re-read
+            float ga[VEC], be[VEC];
+            ld8f(ggamma + c, ga);
+            ld8f(gbeta + c, be);
+            bn_affine(mu, is, ga, be, gsc, gsh);
+        }
     }
     if (cvalid) {
         constexpr int U = 4;                  // row groups in flight per thread
@@ -200,7 +220,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
                                                                                                   : (int)(r * x.C + c)));
                     if (MODE == RED_BNBWD) {
                         gr[u].load(dy.p + vaddr(dy, b, h, w, c));
-                        if (has_gate) tr[u].load(gate.p + vaddr(gate, b, h, w, c));
+                        if (has_gate == 1) tr[u].load(gate.p + vaddr(gate, b, h, w, c));
                     }
                 }
             }
@@ -232,11 +252,12 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
                     } else {
                         float g[VEC], gt[VEC];
                         gr[u].unpack(g);
-                        if (has_gate) tr[u].unpack(gt);
+                        if (has_gate == 1) tr[u].unpack(gt);
 #pragma unroll
                         for (int i = 0; i < VEC; ++i) {
                             float gg = gscale * g[i];
-                            if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
+                            if (has_gate == 1 && !(gt[i] > 0.f)) gg = 0.f;
+                            if (has_gate == 2 && !(bn_eval(xv[i] * mk[i], gsc[i], gsh[i]) > 0.f)) gg = 0.f;
                             const float xh = (xv[i] * mk[i] - mu[i]) * is[i];
                             f0[i] += gg;
                             f1[i] = fmaf(gg, xh, f1[i]);
@@ -314,7 +335,7 @@ __global__ void __launch_bounds__(256) sums_finalize_kernel(const double* ws, in
 template <int MODE>
 static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                          const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, double* ws,
-                         int nchunk, cudaStream_t st) {
+                         int nchunk, cudaStream_t st, const float* ggamma = nullptr, const float* gbeta = nullptr) {
     MOPOE_REQUIRE(x->C % VEC == 0, "reduce: C=%d not a multiple of %d", x->C, VEC);
     MOPOE_REQUIRE(nchunk >= 1 && ws, "reduce: bad workspace");
     MOPOE_REQUIRE((long long)x->B * x->H * x->W < (1ll << 31), "reduce: too many rows");
@@ -323,8 +344,9 @@ static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mo
         DView<const T> xv = make_dview<const T>(x);
         DView<const T> dv = dy ? make_dview<const T>(dy) : xv;
         DView<const T> gv = gate ? make_dview<const T>(gate) : xv;
-        reduce_rows_kernel<T, MODE><<<grid, block, 0, st>>>(xv, dv, gv, gate != nullptr, gscale, mask, mask_mode,
-                                                           mean, invstd, ws, nchunk);
+        const int gmode = gate ? 1 : ((ggamma && gbeta) ? 2 : 0);
+        reduce_rows_kernel<T, MODE><<<grid, block, 0, st>>>(xv, dv, gv, gmode, gscale, mask, mask_mode, mean, invstd,
+                                                           ggamma, gbeta, ws, nchunk);
     });
     MOPOE_CHECK_LAUNCH("reduce_rows");
     return 0;
@@ -354,11 +376,13 @@ extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, d
 extern "C" int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                                    const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
                                    const float* invstd, double* ws, int nchunk, float* dgamma, float* dbeta,
-                                   int accumulate, float* sums, void* stream) {
+                                   int accumulate, float* sums, const float* gate_gamma, const float* gate_beta,
+                                   void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (check_same(x, dy, "bn_bwd_reduce(dy)")) return 1;
     if (gate && check_same(x, gate, "bn_bwd_reduce(gate)")) return 1;
-    if (launch_reduce<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st)) return 1;
+    if (launch_reduce<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st, gate_gamma, gate_beta))
+        return 1;
     sums_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
     MOPOE_CHECK_LAUNCH("bn_bwd_finalize");
     return 0;
@@ -378,8 +402,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(DView<const T> x, 
     {
         float mu[VEC], is[VEC], ga[VEC], be[VEC];
         ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(beta + c, be);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) { sc[i] = is[i] * ga[i]; sh[i] = be[i] - mu[i] * sc[i]; }
+        bn_affine(mu, is, ga, be, sc, sh);
     }
 #pragma unroll 2
     for (; idx < total; idx += stride) {
@@ -393,7 +416,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(DView<const T> x, 
             ldmask8(mask, mask_mode, p.b * x.C + p.c, ((p.b * x.H + p.h) * x.W + p.w) * x.C + p.c, mk);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const float y = fmaf(xv[i] * mk[i], sc[i], sh[i]);
+                const float y = bn_eval(xv[i] * mk[i], sc[i], sh[i]);
                 o[i] = (relu && y < 0.f) ? 0.f : y;
             }
         }
@@ -481,18 +504,23 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T>
                                                                   const float* gamma, const float* sums, float inv_cnt,
                                                                   DView<const T> addend, int has_add, DView<T> out,
                                                                   DView<T> out2, int has_out2, const uint8_t* mask2,
-                                                                  int mask2_mode, float scale2, unsigned total,
-                                                                  unsigned stride) {
+                                                                  int mask2_mode, float scale2, const float* gbeta,
+                                                                  unsigned total, unsigned stride) {
     unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
     const int C = x.C;
     const unsigned CV = (unsigned)C / VEC;
     const int c = (int)(idx % CV) * VEC;
     // dv = k1 * (gg - m_g - xh * m_gx),  xh = v * is - mu*is
-    float k1[VEC], mg[VEC], mgx[VEC], is[VEC], mis[VEC];
+    float k1[VEC], mg[VEC], mgx[VEC], is[VEC], mis[VEC], gsc[VEC], gsh[VEC];
     {
         float mu[VEC], ga[VEC], sg[VEC], sgx[VEC];
         ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(sums + c, sg); ld8f(sums + C + c, sgx);
+        if (has_gate == 2) {
+            float be[VEC];
+            ld8f(gbeta + c, be);
+            bn_affine(mu, is, ga, be, gsc, gsh);
+        }
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             k1[i] = ga[i] * is[i];
@@ -510,7 +538,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T>
         if (p.interior) {
             float g[VEC], gt[VEC], xv[VEC], mk[VEC], ad[VEC];
             ld8v<T>(dy.p + vaddr(dy, p.b, p.h, p.w, p.c), g);
-            if (has_gate) ld8v<T>(gate.p + vaddr(gate, p.b, p.h, p.w, p.c), gt);
+            if (has_gate == 1) ld8v<T>(gate.p + vaddr(gate, p.b, p.h, p.w, p.c), gt);
             ld8v<T>(x.p + vaddr(x, p.b, p.h, p.w, p.c), xv);
             const int bc = p.b * C + p.c, el = ((p.b * x.H + p.h) * x.W + p.w) * C + p.c;
             ldmask8(mask, mask_mode, bc, el, mk);
@@ -518,7 +546,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T>
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
                 float gg = gscale * g[i];
-                if (has_gate && !(gt[i] > 0.f)) gg = 0.f;
+                if (has_gate == 1 && !(gt[i] > 0.f)) gg = 0.f;
+                if (has_gate == 2 && !(bn_eval(xv[i] * mk[i], gsc[i], gsh[i]) > 0.f)) gg = 0.f;
                 const float xh = (xv[i] * mk[i]) * is[i] - mis[i];
                 const float dv = k1[i] * (gg - mg[i] - xh * mgx[i]);
                 o[i] = dv * mk[i] + (has_add ? ad[i] : 0.f);
@@ -538,7 +567,8 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T>
 static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const mopoe_view_t* x,
                              const uint8_t* mask, int mask_mode, const float* mean, const float* invstd,
                              const float* gamma, const float* sums, const mopoe_view_t* addend, const mopoe_view_t* out,
-                             const mopoe_view_t* out2, const uint8_t* mask2, int mask2_mode, float scale2, void* stream) {
+                             const mopoe_view_t* out2, const uint8_t* mask2, int mask2_mode, float scale2, void* stream,
+                             const float* gate_beta = nullptr) {
     if (check_same(x, dy, "bn_bwd_apply(dy)") || check_same(x, out, "bn_bwd_apply(out)")) return 1;
     if (gate && check_same(x, gate, "bn_bwd_apply(gate)")) return 1;
     if (addend && check_same(x, addend, "bn_bwd_apply(addend)")) return 1;
@@ -555,9 +585,9 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
         const long long total = storage_threads(ov);
         if (apply_grid(total, x->C, grid, stride)) return 1;
         bn_bwd_apply_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(
-            make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate != nullptr, gscale, xv, mask, mask_mode,
+            make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate ? 1 : (gate_beta ? 2 : 0), gscale, xv, mask, mask_mode,
             mean, invstd, gamma, sums, inv_cnt, addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,
-            out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2, (unsigned)total, stride);
+            out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2, gate_beta, (unsigned)total, stride);
     });
     MOPOE_CHECK_LAUNCH("bn_bwd_apply");
     return 0;
@@ -565,9 +595,10 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
 extern "C" int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                                   const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
                                   const float* invstd, const float* gamma, const float* sums,
-                                  const mopoe_view_t* addend, const mopoe_view_t* out, void* stream) {
+                                  const mopoe_view_t* addend, const mopoe_view_t* out, const float* gate_beta,
+                                  void* stream) {
     return bn_bwd_apply_impl(dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, sums, addend, out, nullptr, nullptr,
-                             MOPOE_MASK_NONE, 0.f, stream);
+                             MOPOE_MASK_NONE, 0.f, stream, gate_beta);
 }
 // backward of `y = a*BN(r) + b*(c*2mask2)` in ONE pass over dy:  dr = BN-backward(a*dy),  dc = b * dy * 2mask2
 extern "C" int mopoe_combine_bwd_apply(const mopoe_view_t* dy, float a, const mopoe_view_t* r, const float* mean,

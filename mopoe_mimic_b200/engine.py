@@ -164,19 +164,21 @@ class Engine:
                C.byref(c.view()), L.ptr(mask), mode, float(a), float(b), C.byref(out.view()), L.stream_ptr())
         return out
 
-    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out):
-        """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x)."""
+    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out, relu_beta=None):
+        """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x).  relu_beta given (and gate None):
+        the ReLU gate is recomputed from x with the forward's arithmetic instead of re-reading the activation."""
         rows = x.B * x.H * x.W
         nc = self.nchunk(rows, x.C)
         ws = self.ws64(2 * nc * x.C)
         sums = self.f32(2, x.C)
         gv = C.byref(gate.view()) if gate is not None else None
+        gg, gb = (L.ptr(gamma), L.ptr(relu_beta)) if (gate is None and relu_beta is not None) else (None, None)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
-               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums),
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums), gg, gb,
                L.stream_ptr())
         av = C.byref(addend.view()) if addend is not None else None
         L.call('mopoe_bn_bwd_apply', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
-               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), av, C.byref(out.view()), L.stream_ptr())
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), av, C.byref(out.view()), gb, L.stream_ptr())
         return out
 
     def combine_bwd(self, dy, a, r, stats, gamma, dgamma, dbeta, mask2, mode2, b, dr, dc):
@@ -186,7 +188,7 @@ class Engine:
         ws = self.ws64(2 * nc * r.C)
         sums = self.f32(2, r.C)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), None, float(a), C.byref(r.view()), None, L.MASK_NONE,
-               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums),
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums), None, None,
                L.stream_ptr())
         L.call('mopoe_combine_bwd_apply', C.byref(dy.view()), float(a), C.byref(r.view()), L.ptr(stats[0]),
                L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), L.ptr(mask2), mode2, float(b), C.byref(dr.view()),
