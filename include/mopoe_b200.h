@@ -99,15 +99,18 @@ int mopoe_conv_wgrad_param(const mopoe_window_t* A, const mopoe_rows_t* dY, floa
                            int bpad, int accumulate, void* ws, size_t ws_bytes, int impl, void* stream);
 
 /* out[c] (+)= sum over rows of v[.., c]  (bias gradients).  ws: 2*nchunk*C doubles. */
-int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, void* stream);
+int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, int* counters,
+                 void* stream);
 
 /* ---- BatchNorm (training statistics) + fused pre-activation ----------------------------------------
  * nn.BatchNorm{1,2}d in train mode (ResidualBlocks.py:8,12,73-75,...): per-channel mean / biased var
  * of v = x * (2*mask); running stats updated with momentum and the unbiased var.
- * ws: 2*nchunk*C doubles.  running_* may be NULL (no update). */
+ * ws: 2*nchunk*C doubles.  running_* may be NULL (no update).
+ * counters (may be NULL): >= ceil(C/128) zero-initialised ints; when given, the last-arriving block of each channel
+ * group finalises in the same launch (fixed summation order -> deterministic) and resets its counter. */
 int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, double* ws, int nchunk,
                    float eps, float momentum, float* mean, float* invstd,
-                   float* running_mean, float* running_var, void* stream);
+                   float* running_mean, float* running_var, int* counters, void* stream);
 /* out = act(gamma * (x*2mask - mean) * invstd + beta), act = relu when relu != 0; writes the zero border
  * of `out`.  bn1->relu / dropout1->bn2->relu of ResidualBlocks.py:20-33 in one pass. */
 int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
@@ -127,7 +130,7 @@ int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* gate, float 
                         const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
                         const float* mean, const float* invstd, double* ws, int nchunk,
                         float* dgamma, float* dbeta, int accumulate, float* sums,
-                        const float* gate_gamma, const float* gate_beta, void* stream);
+                        const float* gate_gamma, const float* gate_beta, int* counters, void* stream);
 /* BN backward, apply half: out = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend. */
 int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                        const mopoe_view_t* x, const uint8_t* mask, int mask_mode,

@@ -53,11 +53,11 @@ SIGNATURES = {
     'mopoe_conv_gemm_batched': (_I, [_I, _W, _P, _P, _R, _I, _P]),
     'mopoe_conv_wgrad_ws': (_S, [_W, _R, _I]),
     'mopoe_conv_wgrad': (_I, [_W, _R, _P, _I, _P, _S, _I, _P]),
-    'mopoe_colsum': (_I, [_V, _P, _I, _P, _I, _P]),
-    'mopoe_bn_stats': (_I, [_V, _P, _I, _P, _I, _F, _F, _P, _P, _P, _P, _P]),
+    'mopoe_colsum': (_I, [_V, _P, _I, _P, _I, _P, _P]),
+    'mopoe_bn_stats': (_I, [_V, _P, _I, _P, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
     'mopoe_bn_apply': (_I, [_V, _P, _I, _P, _P, _P, _P, _I, _V, _P]),
     'mopoe_combine': (_I, [_V, _P, _P, _P, _P, _V, _P, _I, _F, _F, _V, _P]),
-    'mopoe_bn_bwd_reduce': (_I, [_V, _V, _F, _V, _P, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P]),
+    'mopoe_bn_bwd_reduce': (_I, [_V, _V, _F, _V, _P, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
     'mopoe_bn_bwd_apply': (_I, [_V, _V, _F, _V, _P, _I, _P, _P, _P, _P, _V, _V, _P, _P]),
     'mopoe_combine_bwd_apply': (_I, [_V, _F, _V, _P, _P, _P, _P, _P, _I, _F, _V, _V, _P]),
     'mopoe_scale_mask': (_I, [_V, _P, _I, _F, _V, _P]),

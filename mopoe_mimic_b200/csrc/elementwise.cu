@@ -171,12 +171,45 @@ __device__ __forceinline__ Pos decode_pixel(const DView<T>& o, unsigned pos, int
 enum { RED_STATS = 0, RED_BNBWD = 1, RED_COLSUM = 2 };
 constexpr int RED_ROWS = 16;
 
+// Fused finalize: the LAST block of a channel group to finish (a self-resetting arrival counter) sums the per-chunk
+// partials in a FIXED lane-strided order — so which block happens to be last does not change a single bit — and
+// writes mean / invstd / running stats (BN statistics) or dbeta / dgamma / sums (BN backward, bias gradient).
+struct FinArgs {
+    int* counter;            // one int per channel group (grid.x); NULL -> separate finalize launch
+    double count;
+    float eps, momentum;
+    float *mean, *invstd, *rmean, *rvar;     // RED_STATS
+    float *out0, *out1, *sums;               // RED_BNBWD / RED_COLSUM
+    int accumulate;
+};
+__device__ __forceinline__ void finalize_channel(int mode, const FinArgs& f, int C, int c, double s, double q) {
+    if (mode == RED_STATS) {
+        double m = s / f.count;
+        double var = q / f.count - m * m;
+        if (var < 0.0) var = 0.0;
+        f.mean[c] = (float)m;
+        f.invstd[c] = (float)(1.0 / sqrt(var + (double)f.eps));
+        if (f.rmean) {
+            double unb = f.count > 1.0 ? var * f.count / (f.count - 1.0) : var;
+            f.rmean[c] = (float)((1.0 - f.momentum) * (double)f.rmean[c] + f.momentum * m);
+            f.rvar[c] = (float)((1.0 - f.momentum) * (double)f.rvar[c] + f.momentum * unb);
+        }
+    } else {
+        if (f.out0) f.out0[c] = (f.accumulate ? f.out0[c] : 0.f) + (float)s;   // dbeta / colsum
+        if (f.out1) f.out1[c] = (f.accumulate ? f.out1[c] : 0.f) + (float)q;   // dgamma
+        if (f.sums) {
+            f.sums[c] = (float)s;
+            f.sums[C + c] = (float)q;
+        }
+    }
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DView<const T> dy, DView<const T> gate,
                                                           int has_gate, float gscale, const uint8_t* mask,
                                                           int mask_mode, const float* mean, const float* invstd,
                                                           const float* ggamma, const float* gbeta, double* ws,
-                                                          int nchunk) {
+                                                          int nchunk, FinArgs fin) {
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int c = (blockIdx.x * 16 + tx) * VEC;
     const bool cvalid = c < x.C;
@@ -283,6 +316,30 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
         for (int j = 0; j < RED_ROWS; ++j) a += sm[which][j][tx][ch];
         ws[((long long)blockIdx.y * 2 + which) * x.C + c + ch] = a;
     }
+    if (fin.counter == nullptr) return;
+    // ---- fused finalize by the last-arriving block of this channel group ----
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    const int tid = ty * 16 + tx;
+    if (tid == 0) s_last = (atomicAdd(fin.counter + blockIdx.x, 1) == nchunk - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j = 0; j < 16; ++j) {
+        const int ch = blockIdx.x * 128 + warp * 16 + j;          // 8 warps x 16 channels = this group's 128
+        if (ch >= x.C) break;
+        double a = 0.0, b = 0.0;
+        for (int k = lane; k < nchunk; k += 32) {
+            a += __ldcg(ws + ((long long)k * 2 + 0) * x.C + ch);
+            b += __ldcg(ws + ((long long)k * 2 + 1) * x.C + ch);
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) finalize_channel(MODE, fin, x.C, ch, a, b);
+    }
+    if (tid == 0) fin.counter[blockIdx.x] = 0;                    // self-resetting: ready for the next launch
 }
 
 // finalize: ONE WARP per channel; lane l sums chunks l, l+32, ... then a shuffle tree — a fixed order, so the
@@ -335,7 +392,8 @@ __global__ void __launch_bounds__(256) sums_finalize_kernel(const double* ws, in
 template <int MODE>
 static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                          const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, double* ws,
-                         int nchunk, cudaStream_t st, const float* ggamma = nullptr, const float* gbeta = nullptr) {
+                         int nchunk, cudaStream_t st, const FinArgs& fin, const float* ggamma = nullptr,
+                         const float* gbeta = nullptr) {
     MOPOE_REQUIRE(x->C % VEC == 0, "reduce: C=%d not a multiple of %d", x->C, VEC);
     MOPOE_REQUIRE(nchunk >= 1 && ws, "reduce: bad workspace");
     MOPOE_REQUIRE((long long)x->B * x->H * x->W < (1ll << 31), "reduce: too many rows");
@@ -346,7 +404,7 @@ static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mo
         DView<const T> gv = gate ? make_dview<const T>(gate) : xv;
         const int gmode = gate ? 1 : ((ggamma && gbeta) ? 2 : 0);
         reduce_rows_kernel<T, MODE><<<grid, block, 0, st>>>(xv, dv, gv, gmode, gscale, mask, mask_mode, mean, invstd,
-                                                           ggamma, gbeta, ws, nchunk);
+                                                           ggamma, gbeta, ws, nchunk, fin);
     });
     MOPOE_CHECK_LAUNCH("reduce_rows");
     return 0;
@@ -354,22 +412,34 @@ static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mo
 
 extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, double* ws, int nchunk,
                               float eps, float momentum, float* mean, float* invstd, float* running_mean,
-                              float* running_var, void* stream) {
+                              float* running_var, int* counters, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (launch_reduce<RED_STATS>(x, nullptr, nullptr, 1.f, mask, mask_mode, nullptr, nullptr, ws, nchunk, st)) return 1;
-    double count = (double)x->B * x->H * x->W;
-    bn_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, count, eps, momentum, mean, invstd,
-                                                      running_mean, running_var);
-    MOPOE_CHECK_LAUNCH("bn_finalize");
+    FinArgs fin = {};
+    fin.counter = counters;
+    fin.count = (double)x->B * x->H * x->W;
+    fin.eps = eps; fin.momentum = momentum;
+    fin.mean = mean; fin.invstd = invstd; fin.rmean = running_mean; fin.rvar = running_var;
+    if (launch_reduce<RED_STATS>(x, nullptr, nullptr, 1.f, mask, mask_mode, nullptr, nullptr, ws, nchunk, st, fin)) return 1;
+    if (!counters) {
+        bn_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, fin.count, eps, momentum, mean, invstd,
+                                                          running_mean, running_var);
+        MOPOE_CHECK_LAUNCH("bn_finalize");
+    }
     return 0;
 }
 
-extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, void* stream) {
+extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, int* counters,
+                            void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (launch_reduce<RED_COLSUM>(v, nullptr, nullptr, 1.f, nullptr, MOPOE_MASK_NONE, nullptr, nullptr, ws, nchunk, st))
+    FinArgs fin = {};
+    fin.counter = counters;
+    fin.out0 = out; fin.accumulate = accumulate;
+    if (launch_reduce<RED_COLSUM>(v, nullptr, nullptr, 1.f, nullptr, MOPOE_MASK_NONE, nullptr, nullptr, ws, nchunk, st, fin))
         return 1;
-    sums_finalize_kernel<<<(v->C + 7) / 8, 256, 0, st>>>(ws, nchunk, v->C, out, nullptr, accumulate, nullptr);
-    MOPOE_CHECK_LAUNCH("colsum_finalize");
+    if (!counters) {
+        sums_finalize_kernel<<<(v->C + 7) / 8, 256, 0, st>>>(ws, nchunk, v->C, out, nullptr, accumulate, nullptr);
+        MOPOE_CHECK_LAUNCH("colsum_finalize");
+    }
     return 0;
 }
 
@@ -377,14 +447,19 @@ extern "C" int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* g
                                    const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
                                    const float* invstd, double* ws, int nchunk, float* dgamma, float* dbeta,
                                    int accumulate, float* sums, const float* gate_gamma, const float* gate_beta,
-                                   void* stream) {
+                                   int* counters, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (check_same(x, dy, "bn_bwd_reduce(dy)")) return 1;
     if (gate && check_same(x, gate, "bn_bwd_reduce(gate)")) return 1;
-    if (launch_reduce<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st, gate_gamma, gate_beta))
+    FinArgs fin = {};
+    fin.counter = counters;
+    fin.out0 = dbeta; fin.out1 = dgamma; fin.sums = sums; fin.accumulate = accumulate;
+    if (launch_reduce<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st, fin, gate_gamma, gate_beta))
         return 1;
-    sums_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
-    MOPOE_CHECK_LAUNCH("bn_bwd_finalize");
+    if (!counters) {
+        sums_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
+        MOPOE_CHECK_LAUNCH("bn_bwd_finalize");
+    }
     return 0;
 }
 

@@ -74,7 +74,10 @@ class Engine:
         self._ws64 = None
         self._wsf = None
         self.rng_offset = 0
-        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)   # device-side training-step counter
+        self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # arrival counters for the library's fused-finalize path (last block finalises).  Measured SLOWER on B200 than
+        # a separate one-warp-per-channel finalize launch (the lone last block serialises 16 channels), so it stays off.
+        self.counters = None
         self._packs = {}
         import os
         self.batched = os.environ.get('MOPOE_GEMM_BATCHED', '1') != '0'       # phases of a deconv in one launch
@@ -151,7 +154,7 @@ class Engine:
         ws = self.ws64(2 * nc * x.C)
         stats = self.f32(2, x.C)
         L.call('mopoe_bn_stats', C.byref(x.view()), L.ptr(mask), mode, L.ptr(ws), nc, eps, momentum,
-               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(rmean), L.ptr(rvar), L.stream_ptr())
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(rmean), L.ptr(rvar), L.ptr(self.counters), L.stream_ptr())
         return stats
 
     def bn_apply(self, x, mask, mode, stats, gamma, beta, relu, out):
@@ -175,7 +178,7 @@ class Engine:
         gg, gb = (L.ptr(gamma), L.ptr(relu_beta)) if (gate is None and relu_beta is not None) else (None, None)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums), gg, gb,
-               L.stream_ptr())
+               L.ptr(self.counters), L.stream_ptr())
         av = C.byref(addend.view()) if addend is not None else None
         L.call('mopoe_bn_bwd_apply', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), av, C.byref(out.view()), gb, L.stream_ptr())
@@ -189,7 +192,7 @@ class Engine:
         sums = self.f32(2, r.C)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), None, float(a), C.byref(r.view()), None, L.MASK_NONE,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums), None, None,
-               L.stream_ptr())
+               L.ptr(self.counters), L.stream_ptr())
         L.call('mopoe_combine_bwd_apply', C.byref(dy.view()), float(a), C.byref(r.view()), L.ptr(stats[0]),
                L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), L.ptr(mask2), mode2, float(b), C.byref(dr.view()),
                C.byref(dc.view()), L.stream_ptr())
@@ -206,7 +209,7 @@ class Engine:
         ws = self.ws64(2 * nc * v.C)
         if out is None:
             out = self.f32(v.C)
-        L.call('mopoe_colsum', C.byref(v.view()), L.ptr(out), 0, L.ptr(ws), nc, L.stream_ptr())
+        L.call('mopoe_colsum', C.byref(v.view()), L.ptr(out), 0, L.ptr(ws), nc, L.ptr(self.counters), L.stream_ptr())
         return out
 
     def convert(self, src_view, nchw, dst):
