@@ -123,9 +123,9 @@ int mopoe_combine(const mopoe_view_t* r, const float* mean, const float* invstd,
                   float a, float b, const mopoe_view_t* out, void* stream);
 /* BN backward, reduction half: g = gscale * dy * [gate > 0];  xhat = (x*2mask - mean)*invstd;
  * dbeta (+)= sum g, dgamma (+)= sum g*xhat, sums[0:C] = sum g, sums[C:2C] = sum g*xhat.
- * The ReLU gate is either read from `gate` (the saved activation), or — gate == NULL and gate_gamma/gate_beta
- * given — RECOMPUTED as [gamma*xhat + beta > 0] with the forward kernel's exact arithmetic (no activation re-read),
- * or absent (all NULL). */
+ * The ReLU gate is read from `gate` (the saved activation) or absent (NULL).  gate_gamma / gate_beta are reserved
+ * (must be NULL): recomputing the gate from x was measured slower than re-reading the bf16 activation on B200 —
+ * these passes are issue-bound, not DRAM-bound. */
 int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                         const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
                         const float* mean, const float* invstd, double* ws, int nchunk,

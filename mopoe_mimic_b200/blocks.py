@@ -197,8 +197,8 @@ class ResBlockFn(torch.autograd.Function):
         da2 = _main_dgrad(eng, sp, dc, W2, dt, H, W)
         # relu, bn2, dropout1
         G['bn2.weight'], G['bn2.bias'] = eng.f32(sp.cin), eng.f32(sp.cin)
-        # (the library can also RECOMPUTE the ReLU gate from hh — relu_beta=... — but on B200 the extra per-element
-        #  math costs more than re-reading the bf16 activation: these passes are issue-bound, not DRAM-bound)
+        # (recomputing the ReLU gate from hh instead of re-reading a2 was measured SLOWER on B200: these passes are
+        #  issue-bound, not DRAM-bound)
         dh = eng.bn_bwd(da2, a2, 1.0, hh, m1, mode, st2, P['bn2.weight'], G['bn2.weight'], G['bn2.bias'], None,
                         Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device))
         # conv1 (1x1)

@@ -54,47 +54,45 @@ template <typename T>
 __global__ void __launch_bounds__(256) conv3x3s2_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                int H, int W, DView<T> out, long long total) {
     extern __shared__ float wsm[];
-    stage_filter(w, wsm, out.C);
-    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int C = out.C, CG = C / CV8;
-    const int Ws = out.W + 2 * out.pw, Hs = out.H + 2 * out.ph;
-    int c = (int)(idx % CG) * CV8;
-    long long pos = idx / CG;
-    int ws = (int)(pos % Ws);
-    pos /= Ws;
-    int hs = (int)(pos % Hs);
-    int b = (int)(pos / Hs);
-    int oy = hs - out.ph, ox = ws - out.pw;
-    float o[8];
+    stage_filter(w, wsm, out.C);                      // once per CTA; the CTA then strides over many pixels
+    const int C = out.C;
+    const unsigned CG = (unsigned)C / CV8;
+    for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < (unsigned)total; idx += gridDim.x * 256u) {
+        const int c = (int)(idx % CG) * CV8;
+        unsigned pos = out.fCV8.div(idx), ws, hs, q, bb;
+        out.fWs.divmod(pos, q, ws);
+        out.fHs.divmod(q, bb, hs);
+        const int b = (int)bb, oy = (int)hs - out.ph, ox = (int)ws - out.pw;
+        float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.f;
-    if (oy >= 0 && oy < out.H && ox >= 0 && ox < out.W) {
-        const float* xb = x + (long long)b * H * W;
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        if (oy >= 0 && oy < out.H && ox >= 0 && ox < out.W) {
+            const float* xb = x + (long long)b * H * W;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            int iy = 2 * oy - 1 + ky;
-            if (iy < 0 || iy >= H) continue;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = 2 * oy - 1 + ky;
+                if (iy < 0 || iy >= H) continue;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                int ix = 2 * ox - 1 + kx;
-                if (ix < 0 || ix >= W) continue;
-                float xv = __ldg(xb + (long long)iy * W + ix);
-                const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c);
-                const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c + 4);
-                o[0] += xv * w0.x; o[1] += xv * w0.y; o[2] += xv * w0.z; o[3] += xv * w0.w;
-                o[4] += xv * w1.x; o[5] += xv * w1.y; o[6] += xv * w1.z; o[7] += xv * w1.w;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = 2 * ox - 1 + kx;
+                    if (ix < 0 || ix >= W) continue;
+                    const float xv = __ldg(xb + iy * W + ix);
+                    const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c + 4);
+                    o[0] += xv * w0.x; o[1] += xv * w0.y; o[2] += xv * w0.z; o[3] += xv * w0.w;
+                    o[4] += xv * w1.x; o[5] += xv * w1.y; o[6] += xv * w1.z; o[7] += xv * w1.w;
+                }
             }
         }
+        st8<T>(out.p + (long long)b * out.sB + (long long)oy * out.sH + (long long)ox * out.sW + c, o);
     }
-    st8<T>(out.p + (long long)b * out.sB + (long long)oy * out.sH + (long long)ox * out.sW + c, o);
 }
 extern "C" int mopoe_conv3x3s2_c1_fwd(const float* x, const float* w, int B, int H, int W, const mopoe_view_t* out,
                                       void* stream) {
     MOPOE_REQUIRE(out->B == B && out->H == H / 2 && out->W == W / 2 && out->C % CV8 == 0, "conv3x3s2_c1_fwd: bad out view");
     long long total = (long long)B * (out->H + 2 * out->ph) * (out->W + 2 * out->pw) * (out->C / CV8);
     MOPOE_DISPATCH_T(out->dtype, T, {
-        conv3x3s2_c1_fwd_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 9 * out->C * sizeof(float), (cudaStream_t)stream>>>(
+        conv3x3s2_c1_fwd_kernel<T><<<(unsigned)min((long long)ceil_div64(total, 256), 148ll * 16), 256, 9 * out->C * sizeof(float), (cudaStream_t)stream>>>(
             x, w, H, W, make_dview<T>(out), total);
     });
     MOPOE_CHECK_LAUNCH("conv3x3s2_c1_fwd");
@@ -225,7 +223,25 @@ __global__ void __launch_bounds__(256) deconv3x3s2_c1_fwd_kernel(DView<const T> 
                 o10 += a[i] * wr[i][7] + ad[i] * wr[i][1];
                 o11 += a[i] * wr[i][8] + ar[i] * wr[i][6] + ad[i] * wr[i][2] + adr[i] * wr[i][0];
             }
-            o00 = warp_sum(o00); o01 = warp_sum(o01); o10 = warp_sum(o10); o11 = warp_sum(o11);
+            // transposing butterfly: 4 values x 32 lanes -> 4 totals with 2 + 1 + 3 shuffles instead of 4 x 5
+            {
+                const bool hi = lane & 16;
+                float sa = hi ? o00 : o10, sb = hi ? o01 : o11;          // what this lane gives away
+                float ka = hi ? o10 : o00, kb = hi ? o11 : o01;          // what it keeps (lo: row 0, hi: row 1)
+                ka += __shfl_xor_sync(0xffffffffu, sa, 16);
+                kb += __shfl_xor_sync(0xffffffffu, sb, 16);
+                const bool h8 = lane & 8;
+                float give = h8 ? ka : kb, keep = h8 ? kb : ka;          // lo8: col 0, hi8: col 1
+                keep += __shfl_xor_sync(0xffffffffu, give, 8);
+                keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+                keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+                keep += __shfl_xor_sync(0xffffffffu, keep, 1);
+                // lanes 0 / 8 / 16 / 24 now hold o00 / o01 / o10 / o11
+                o00 = __shfl_sync(0xffffffffu, keep, 0);
+                o01 = __shfl_sync(0xffffffffu, keep, 8);
+                o10 = __shfl_sync(0xffffffffu, keep, 16);
+                o11 = __shfl_sync(0xffffffffu, keep, 24);
+            }
             if (lane == 0) {
                 const int OW = 2 * x.W;
                 float* ob = out + ((long long)b * 2 * x.H + 2 * t) * OW + 2 * s;
@@ -261,40 +277,38 @@ __global__ void __launch_bounds__(256) deconv3x3s2_c1_dx_kernel(const float* __r
                                                                 DView<T> dx, long long total) {
     extern __shared__ float wsm[];
     stage_filter(w, wsm, dx.C);
-    long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (idx >= total) return;
-    const int C = dx.C, CG = C / CV8;
-    const int Ws = dx.W + 2 * dx.pw, Hs = dx.H + 2 * dx.ph;
-    int c = (int)(idx % CG) * CV8;
-    long long pos = idx / CG;
-    int ws = (int)(pos % Ws);
-    pos /= Ws;
-    int hs = (int)(pos % Hs);
-    int b = (int)(pos / Hs);
-    int t = hs - dx.ph, s = ws - dx.pw;
-    float o[8];
+    const int C = dx.C;
+    const unsigned CG = (unsigned)C / CV8;
+    const int OH = 2 * dx.H, OW = 2 * dx.W;
+    for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < (unsigned)total; idx += gridDim.x * 256u) {
+        const int c = (int)(idx % CG) * CV8;
+        unsigned pos = dx.fCV8.div(idx), ws, hs, q, bb;
+        dx.fWs.divmod(pos, q, ws);
+        dx.fHs.divmod(q, bb, hs);
+        const int b = (int)bb, t = (int)hs - dx.ph, s = (int)ws - dx.pw;
+        float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = 0.f;
-    if (t >= 0 && t < dx.H && s >= 0 && s < dx.W) {
-        const int OH = 2 * dx.H, OW = 2 * dx.W;
-        const float* db = dout + (long long)b * OH * OW;
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        if (t >= 0 && t < dx.H && s >= 0 && s < dx.W) {
+            const float* db = dout + (long long)b * OH * OW;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            int oy = 2 * t - 1 + ky;
-            if (oy < 0 || oy >= OH) continue;
+            for (int ky = 0; ky < 3; ++ky) {
+                const int oy = 2 * t - 1 + ky;
+                if (oy < 0 || oy >= OH) continue;
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                int ox = 2 * s - 1 + kx;
-                if (ox < 0 || ox >= OW) continue;
-                float g = __ldg(db + (long long)oy * OW + ox);
-                const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c);
-                const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c + 4);
-                o[0] += g * w0.x; o[1] += g * w0.y; o[2] += g * w0.z; o[3] += g * w0.w;
-                o[4] += g * w1.x; o[5] += g * w1.y; o[6] += g * w1.z; o[7] += g * w1.w;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ox = 2 * s - 1 + kx;
+                    if (ox < 0 || ox >= OW) continue;
+                    const float g = __ldg(db + oy * OW + ox);
+                    const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c + 4);
+                    o[0] += g * w0.x; o[1] += g * w0.y; o[2] += g * w0.z; o[3] += g * w0.w;
+                    o[4] += g * w1.x; o[5] += g * w1.y; o[6] += g * w1.z; o[7] += g * w1.w;
+                }
             }
         }
+        st8<T>(dx.p + (long long)b * dx.sB + (long long)t * dx.sH + (long long)s * dx.sW + c, o);
     }
-    st8<T>(dx.p + (long long)b * dx.sB + (long long)t * dx.sH + (long long)s * dx.sW + c, o);
 }
 __global__ void __launch_bounds__(256) sum_partial_kernel(const float* __restrict__ v, long long n, double* __restrict__ part) {
     double acc = 0.0;
@@ -323,7 +337,7 @@ extern "C" int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, c
     long long total = (long long)dx->B * (dx->H + 2 * dx->ph) * (dx->W + 2 * dx->pw) * (dx->C / CV8);
     dim3 block(16, 16), grid((x->C + 127) / 128, nchunk);
     MOPOE_DISPATCH_T(x->dtype, T, {
-        deconv3x3s2_c1_dx_kernel<T><<<(unsigned)ceil_div64(total, 256), 256, 9 * x->C * sizeof(float), st>>>(
+        deconv3x3s2_c1_dx_kernel<T><<<(unsigned)min((long long)ceil_div64(total, 256), 148ll * 16), 256, 9 * x->C * sizeof(float), st>>>(
             dout, w, make_dview<T>(dx), total);
         tap_grad_kernel<T, false><<<grid, block, 0, st>>>(make_dview<const T>(x), dout, 2 * x->H, 2 * x->W, ws, nchunk);
     });

@@ -221,16 +221,10 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
     float f0[VEC], f1[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) f0[i] = f1[i] = 0.f;
-    float mu[VEC], is[VEC], gsc[VEC], gsh[VEC];
+    float mu[VEC], is[VEC];
     if (MODE == RED_BNBWD && cvalid) {
         ld8f(mean + c, mu);
         ld8f(invstd + c, is);
-        if (has_gate == 2) {              // gate = [relu(BN(x)) > 0], recomputed from x: no activation re-read
-            float ga[VEC], be[VEC];
-            ld8f(ggamma + c, ga);
-            ld8f(gbeta + c, be);
-            bn_affine(mu, is, ga, be, gsc, gsh);
-        }
     }
     if (cvalid) {
         constexpr int U = 4;                  // row groups in flight per thread
@@ -290,7 +284,6 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
                         for (int i = 0; i < VEC; ++i) {
                             float gg = gscale * g[i];
                             if (has_gate == 1 && !(gt[i] > 0.f)) gg = 0.f;
-                            if (has_gate == 2 && !(bn_eval(xv[i] * mk[i], gsc[i], gsh[i]) > 0.f)) gg = 0.f;
                             const float xh = (xv[i] * mk[i] - mu[i]) * is[i];
                             f0[i] += gg;
                             f1[i] = fmaf(gg, xh, f1[i]);
@@ -402,7 +395,8 @@ static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mo
         DView<const T> xv = make_dview<const T>(x);
         DView<const T> dv = dy ? make_dview<const T>(dy) : xv;
         DView<const T> gv = gate ? make_dview<const T>(gate) : xv;
-        const int gmode = gate ? 1 : ((ggamma && gbeta) ? 2 : 0);
+        MOPOE_REQUIRE(!(ggamma || gbeta) || gate, "bn_bwd_reduce: gate recompute is not compiled in; pass the gate view");
+        const int gmode = gate ? 1 : 0;
         reduce_rows_kernel<T, MODE><<<grid, block, 0, st>>>(xv, dv, gv, gmode, gscale, mask, mask_mode, mean, invstd,
                                                            ggamma, gbeta, ws, nchunk, fin);
     });
@@ -587,15 +581,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T>
     const unsigned CV = (unsigned)C / VEC;
     const int c = (int)(idx % CV) * VEC;
     // dv = k1 * (gg - m_g - xh * m_gx),  xh = v * is - mu*is
-    float k1[VEC], mg[VEC], mgx[VEC], is[VEC], mis[VEC], gsc[VEC], gsh[VEC];
+    float k1[VEC], mg[VEC], mgx[VEC], is[VEC], mis[VEC];
     {
         float mu[VEC], ga[VEC], sg[VEC], sgx[VEC];
         ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(sums + c, sg); ld8f(sums + C + c, sgx);
-        if (has_gate == 2) {
-            float be[VEC];
-            ld8f(gbeta + c, be);
-            bn_affine(mu, is, ga, be, gsc, gsh);
-        }
+
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             k1[i] = ga[i] * is[i];
@@ -622,7 +612,6 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T>
             for (int i = 0; i < VEC; ++i) {
                 float gg = gscale * g[i];
                 if (has_gate == 1 && !(gt[i] > 0.f)) gg = 0.f;
-                if (has_gate == 2 && !(bn_eval(xv[i] * mk[i], gsc[i], gsh[i]) > 0.f)) gg = 0.f;
                 const float xh = (xv[i] * mk[i]) * is[i] - mis[i];
                 const float dv = k1[i] * (gg - mg[i] - xh * mgx[i]);
                 o[i] = dv * mk[i] + (has_add ? ad[i] : 0.f);
@@ -645,6 +634,7 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
                              const mopoe_view_t* out2, const uint8_t* mask2, int mask2_mode, float scale2, void* stream,
                              const float* gate_beta = nullptr) {
     if (check_same(x, dy, "bn_bwd_apply(dy)") || check_same(x, out, "bn_bwd_apply(out)")) return 1;
+    MOPOE_REQUIRE(gate_beta == nullptr, "bn_bwd_apply: gate recompute is not compiled in; pass the gate view");
     if (gate && check_same(x, gate, "bn_bwd_apply(gate)")) return 1;
     if (addend && check_same(x, addend, "bn_bwd_apply(addend)")) return 1;
     if (out2) {
@@ -660,7 +650,7 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
         const long long total = storage_threads(ov);
         if (apply_grid(total, x->C, grid, stride)) return 1;
         bn_bwd_apply_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(
-            make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate ? 1 : (gate_beta ? 2 : 0), gscale, xv, mask, mask_mode,
+            make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate ? 1 : 0, gscale, xv, mask, mask_mode,
             mean, invstd, gamma, sums, inv_cnt, addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,
             out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2, gate_beta, (unsigned)total, stride);
     });

@@ -167,15 +167,15 @@ class Engine:
                C.byref(c.view()), L.ptr(mask), mode, float(a), float(b), C.byref(out.view()), L.stream_ptr())
         return out
 
-    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out, relu_beta=None):
-        """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x).  relu_beta given (and gate None):
-        the ReLU gate is recomputed from x with the forward's arithmetic instead of re-reading the activation."""
+    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out):
+        """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x).  gate = the saved post-ReLU
+        activation (None: no ReLU)."""
         rows = x.B * x.H * x.W
         nc = self.nchunk(rows, x.C)
         ws = self.ws64(2 * nc * x.C)
         sums = self.f32(2, x.C)
         gv = C.byref(gate.view()) if gate is not None else None
-        gg, gb = (L.ptr(gamma), L.ptr(relu_beta)) if (gate is None and relu_beta is not None) else (None, None)
+        gg = gb = None      # reserved gate-recompute operands of the C ABI (not compiled in)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums), gg, gb,
                L.ptr(self.counters), L.stream_ptr())
