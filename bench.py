@@ -232,12 +232,38 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    # roofline of the dominant kernel family (implicit-GEMM convs): one instrumented step, CUDA events per launch
+    # roofline of the dominant kernel family (implicit-GEMM convs): one instrumented step with a CUDA event pair
+    # around every GEMM launch.  The events are captured INTO a copy of the step graph (event-record nodes), so the
+    # durations are the kernels' own in-step durations — bracketing eager launches instead also counts the host's
+    # enqueue latency between the event and the kernel, which is comparable to these 20-100 us kernels.
     eng = vae.rt.engine
-    eng.profile = []
-    P.train_step(exp, (dict(resident), None), ar)              # eager, so every GEMM launch is bracketed by events
-    torch.cuda.synchronize()
-    prof, eng.profile = eng.profile, None
+    prof, timing = None, None
+    if not args.no_graph:
+        try:
+            eng.profile, eng.profile_external = [], True
+            saved_dataset, fl.dataset = fl.dataset, 'testing'
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=gstep.graph.pool()):
+                P.forward_backward(exp, (dict(gstep.static), None))
+            fl.dataset = saved_dataset
+            prof = eng.profile
+            for _ in range(3):
+                g2.replay()
+            torch.cuda.synchronize()
+            _ = [p_[0].elapsed_time(p_[1]) for p_ in prof[:2]]
+            timing = 'CUDA event pairs captured as nodes of the step graph (in-step kernel durations)'
+        except Exception as e:       # noqa: BLE001
+            print('graph-captured event timing unavailable (%r); bracketing eager launches' % (e,), file=sys.stderr)
+            prof = None
+            torch.cuda.synchronize()
+        finally:
+            eng.profile, eng.profile_external = None, False
+    if prof is None:
+        eng.profile = []
+        P.train_step(exp, (dict(resident), None), ar)          # eager: includes host enqueue latency per launch
+        torch.cuda.synchronize()
+        prof, eng.profile = eng.profile, None
+        timing = 'CUDA event pairs around eager launches (includes host enqueue latency)'
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -250,15 +276,24 @@ def main():
             pass
         peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
         peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback'
-        gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
-        gemm_flop = sum(f for _, _, f, _ in prof)
+        gemm_ms = sum(p_[0].elapsed_time(p_[1]) for p_ in prof)
+        gemm_flop = sum(p_[2] for p_ in prof)
         by_kind = {}
-        for a, b, f, kind in prof:
+        for a, b, f, kind, _tag in prof:
             d = by_kind.setdefault(kind, [0.0, 0.0, 0])
             d[0] += a.elapsed_time(b)
             d[1] += f
             d[2] += 1
         achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        if os.environ.get('MOPOE_BENCH_SHAPES'):       # developer aid: GEMM time per problem shape
+            agg = {}
+            for a, b, f, kind, tag in prof:
+                d = agg.setdefault(tag, [0.0, 0.0, 0])
+                d[0] += a.elapsed_time(b)
+                d[1] += f
+                d[2] += 1
+            for tag, d in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+                print('%-46s n=%3d %8.3f ms %7.1f TF/s' % (tag, d[2], d[0], d[1] / d[0] / 1e9), file=sys.stderr)
         value = world * B * args.steps / (ms * 1e-3)
         line = {'metric': 'train samples/sec (3-modality MoPoE, 128px)', 'value': value, 'unit': 'samples/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
@@ -271,7 +306,7 @@ def main():
                         'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h},
                 'gpu_launches': launches,
                 'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                             'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src,
+                             'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src, 'timing': timing,
                              'kernel': 'implicit-GEMM conv family (fprop+dgrad+wgrad), %d launches/step' % len(prof),
                              'gemm_ms_per_step': gemm_ms, 'step_tensor_frac': value / world * GFLOP_PER_SAMPLE_TRAIN / 1e3 / peak_tf,
                              'by_kind': {k: {'ms': v[0], 'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else 0.0, 'launches': v[2]}

@@ -2,7 +2,7 @@
 Python model API).  See DESIGN.md / INTEGRATION.md."""
 from . import _lib
 from .train import (CudaOutOfMemory, Experiment, FlatAdam, GraphedTrainStep, NaNInLatent, basic_routine_epoch, default_flags,  # noqa: F401
-                    packed_stats, train_step)
+                    forward_backward, packed_stats, train_step)
 from .mmvae import BaseMMVae, MMVaeMimic, VAEtrimodalMimic  # noqa: F401
 from .networks import DecoderImg, DecoderText, EncoderImg, EncoderText  # noqa: F401
 from .modalities import MimicLateral, MimicPA, MimicText  # noqa: F401

@@ -99,7 +99,9 @@ def _main_dgrad(eng, spec, dout, Wg, dtype, H, W):
         return eng.gemm_rows(dout, eng.packed(Wg, "full"), None, taps * spec.cin, out_shape=(dout.B, H, W, spec.cin))
     if spec.kind == 'U':
         return eng.gemm_down(dout, eng.packed(Wg, "conv"), None, 4, 1, 0, spec.cin)
-    raise NotImplementedError('dgrad for stride-4 blocks (256 px) is not built yet')
+    if spec.kind == 'Q':
+        return eng.gemm_unfold(dout, eng.packed(Wg, "full"), spec.cin, H, W, 4, 1)
+    raise NotImplementedError('dgrad for block kind %r' % spec.kind)
 
 
 def _main_wgrad(eng, spec, xin, dout, param):

@@ -83,6 +83,7 @@ class Engine:
         self.batched = os.environ.get('MOPOE_GEMM_BATCHED', '1') != '0'       # phases of a deconv in one launch
         self.persistent = os.environ.get('MOPOE_GEMM_PERSISTENT', '1') != '0'   # persistent kernel for single GEMMs too
         self.profile = None     # list of (start_event, end_event, flops, kind) when bench.py instruments a step
+        self.profile_external = False   # True: events become event-record NODES of a CUDA graph being captured
 
     # ---- packed-weight cache: each re-layout is computed once per optimizer step (forward and backward share it)
     def packed(self, Wg, form, bpad=None):
@@ -224,14 +225,15 @@ class Engine:
         return m
 
     # ---- implicit-GEMM problem builders -------------------------------------------------------------------
-    def _timed(self, kind, flops, fn):
+    def _timed(self, kind, flops, fn, tag=None):
         if self.profile is None:
             return fn()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ext = {'external': True} if self.profile_external else {}
+        a, b = torch.cuda.Event(enable_timing=True, **ext), torch.cuda.Event(enable_timing=True, **ext)
         a.record()
         r = fn()
         b.record()
-        self.profile.append((a, b, flops, kind))
+        self.profile.append((a, b, flops, kind, tag))
         return r
 
     def _gemm(self, win, wp, bias, rows):
@@ -247,8 +249,10 @@ class Engine:
             WA = (L.Window * n)(*wins)
             RA = (L.Rows * n)(*rows_list)
             PA = (C.c_void_p * n)(*[wp.data_ptr() for wp in wps])
+            w0 = wins[0]
             self._timed('fprop/dgrad', flops, lambda: L.call('mopoe_conv_gemm_batched', n, WA, PA, L.ptr(bias), RA,
-                                                             self.impl, L.stream_ptr()))
+                                                             self.impl, L.stream_ptr()),
+                        'x%d M=%dx%dx%d N=%d K=%dx%d' % (n, w0.E2, w0.E1, w0.E0, rows_list[0].N, w0.R, w0.KW))
         else:
             for w, wp, r in zip(wins, wps, rows_list):
                 f1 = 2.0 * w.E0 * w.E1 * w.E2 * r.N * w.R * w.KW
@@ -265,7 +269,8 @@ class Engine:
         ws = self.wsf(nbytes) if nbytes else None
         flops = 2.0 * win.E0 * win.E1 * win.E2 * N * K
         self._timed('wgrad', flops, lambda: L.call('mopoe_conv_wgrad', C.byref(win), C.byref(rows), L.ptr(out), 0,
-                                                   L.ptr(ws), nbytes, self.impl, L.stream_ptr()))
+                                                   L.ptr(ws), nbytes, self.impl, L.stream_ptr()),
+                    'wg0 M=%dx%dx%d N=%d K=%dx%d' % (win.E2, win.E1, win.E0, N, win.R, win.KW))
         return out
 
     def _wgrad_param(self, win, rows, param, taps, bpad):
@@ -280,7 +285,8 @@ class Engine:
         ws = self.wsf(nbytes)
         flops = 2.0 * win.E0 * win.E1 * win.E2 * rows.N * win.R * win.KW
         self._timed('wgrad', flops, lambda: L.call('mopoe_conv_wgrad_param', C.byref(win), C.byref(rows), L.ptr(g), A, B,
-                                                   taps, bpad, 1, L.ptr(ws), nbytes, self.impl, L.stream_ptr()))
+                                                   taps, bpad, 1, L.ptr(ws), nbytes, self.impl, L.stream_ptr()),
+                    'wg M=%dx%dx%d N=%d K=%dx%d' % (win.E2, win.E1, win.E0, rows.N, win.R, win.KW))
         return True
 
     def wgrad_down_param(self, xwin, k, s, p, yrows, param, bpad=None):
@@ -347,6 +353,27 @@ class Engine:
                 rows_l.append(L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, (py * OW + px) * n, 2 * n,
                                      2 * OW * n, 2 * x.H * OW * n))
         self._gemm_batched(wins, list(wph), bias, rows_l)
+        return out
+
+    def gemm_unfold(self, dy, wfull, n, H, W, k, p):
+        """input gradient of a conv whose stride equals its kernel (the 256-px stage: k4 s4 p1, FeatureExtractorImg.py
+        :52-59): windows tile the input without overlap, so every dy pixel scatters ONE k x k x n patch and dgrad is a
+        plain GEMM.  One problem per patch row ky (same A, weight slice and output origin differ): row (b,oy,ox) of
+        problem ky is the k*n contiguous elements dX[b, k*oy-p+ky, k*ox-p .. +k, :].  The result carries a border of p
+        that receives the (unused) gradients of the padding; input pixels no window covers stay zero."""
+        Cc = dy.C
+        assert wfull.shape == (k * k * n, Cc) and p <= 1
+        out = Act(torch.zeros(dy.B, H + 2 * p, W + 2 * p, n, dtype=dy.dtype, device=self.device), dy.B, H, W, n, p, p)
+        assert k * dy.H - 1 < out.Hs and k * dy.W <= out.Ws
+        win = L.Window(dy.t.data_ptr(), L.dtype_code(dy.dtype), dy.W, dy.H, dy.B, 1, Cc, 0, dy.origin(), Cc,
+                       dy.Ws * Cc, dy.Hs * dy.Ws * Cc, 0)
+        wins, wps, rows_l = [], [], []
+        for ky in range(k):
+            wins.append(win)
+            wps.append(wfull[ky * k * n:(ky + 1) * k * n])
+            rows_l.append(L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), k * n, ky * out.Ws * n, k * n,
+                                 k * out.Ws * n, out.Hs * out.Ws * n))
+        self._gemm_batched(wins, wps, None, rows_l)
         return out
 
     def gemm_rows(self, x, w, bias, n, out_shape=None, out_dtype=None):
