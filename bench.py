@@ -24,6 +24,19 @@ sys.path.insert(0, ROOT)
 
 GFLOP_PER_SAMPLE_TRAIN = 52.09     # 3 x 17.36 GFLOP fwd (2 x 8.681 GMAC) at 128 px tri-modal
 WORKLOAD = 'MoPoE PA+Lateral+text 128px char1024x71 class_dim128 joint_elbo'
+# BASELINE.json configs.  '2' is the configuration the metric is quoted on (the default, and the only bench line the
+# driver reads); the others run the same step at their per-GPU sizes for parity / capacity checks.
+CONFIGS = {
+    '2': dict(flags={}, batch=256, workload=WORKLOAD, gflop=GFLOP_PER_SAMPLE_TRAIN),
+    '4': dict(flags=dict(img_size=256, class_dim=512), batch=64, gflop=167.95,
+              workload='MoPoE PA+Lateral+text 256px char1024x71 class_dim512 joint_elbo'),
+    '5-joint': dict(flags=dict(mods=('PA', 'text')), batch=128, gflop=29.09,
+                    workload='MoPoE PA+text 128px char1024x71 class_dim128 joint_elbo'),
+    '5-moe': dict(flags=dict(mods=('PA', 'text'), method='moe'), batch=128, gflop=29.09,
+                  workload='MoPoE PA+text 128px char1024x71 class_dim128 moe'),
+    '5-poe': dict(flags=dict(mods=('PA', 'text'), method='poe'), batch=128, gflop=58.2,
+                  workload='MoPoE PA+text 128px char1024x71 class_dim128 poe (+2 unimodal passes)'),
+}
 
 
 def parse():
@@ -32,7 +45,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=256, help='per-GPU batch')
+    ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the config\'s)')
+    ap.add_argument('--config', default='2', choices=sorted(CONFIGS), help='BASELINE.json configuration (default 2)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-batch', type=int, default=16)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -81,17 +95,18 @@ def cpu_reference(args, steps, warmup):
     from oracle import mopoe_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    fl = O.default_flags(batch_size=args.cpu_batch)
+    fl = O.default_flags(batch_size=args.cpu_batch, **CONFIGS[args.config]['flags'])
     state = O.make_state(fl, 0, torch.float32)
     batch = O.make_batch(fl, 1, torch.float32)
     masks, eps = O.make_noise(fl, 2, torch.float32)
+    uni = {m: O.make_noise(fl, 3 + i, torch.float32) for i, m in enumerate(fl.mods)} if fl.method == 'poe' else None
     params = {k: v for k, v in state.items() if v.is_floating_point() and 'running_' not in k}
     m = {k: torch.zeros_like(v) for k, v in params.items()}
     v = {k: torch.zeros_like(p) for k, p in params.items()}
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        out = O.step_with_grads(state, batch, fl, masks, eps)
+        out = O.step_with_grads(state, batch, fl, masks, eps, uni_masks=uni)
         with torch.no_grad():
             O.adam_step(params, out['grads'], m, v, it + 1)
             state.update(out['results']['bn_updates'])
@@ -114,7 +129,8 @@ def run_reference(args):
     line = {'metric': 'train samples/sec (3-modality MoPoE, 128px)', 'value': cb['value'], 'unit': 'samples/s',
             'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': WORKLOAD, 'per_gpu_batch': args.cpu_batch, 'note': 'CPU oracle port of the reference step'},
+            'config': {'workload': CONFIGS[args.config]['workload'], 'per_gpu_batch': args.cpu_batch,
+                       'note': 'CPU oracle port of the reference step'},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -135,8 +151,10 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    B = args.batch
-    fl = P.default_flags(device=dev, batch_size=B, compute_dtype=args.dtype, distributed=world > 1, world_size=world)
+    cfg = CONFIGS[args.config]
+    B = args.batch or cfg['batch']
+    fl = P.default_flags(device=dev, batch_size=B, compute_dtype=args.dtype, distributed=world > 1, world_size=world,
+                         **cfg['flags'])
     torch.manual_seed(0)
     exp = P.Experiment(fl)
     exp.set_optimizer()
@@ -147,9 +165,11 @@ def main():
         exp.optimizer.grad_scale = 1.0 / world
     # synthetic inputs of the reference's shapes (dataio/MimicDataset.py:414-428), true one-hot text
     g = torch.Generator(device='cpu').manual_seed(1 + rank)
-    host = {'PA': torch.rand(B, 1, 128, 128, generator=g).pin_memory(),
-            'Lateral': torch.rand(B, 1, 128, 128, generator=g).pin_memory(),
+    px = fl.img_size
+    host = {'PA': torch.rand(B, 1, px, px, generator=g).pin_memory(),
+            'Lateral': torch.rand(B, 1, px, px, generator=g).pin_memory(),
             'text': torch.nn.functional.one_hot(torch.randint(0, 71, (B, 1024), generator=g), 71).float().pin_memory()}
+    host = {k: v for k, v in host.items() if k in fl.mods}
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
@@ -295,11 +315,14 @@ def main():
             for tag, d in sorted(agg.items(), key=lambda kv: -kv[1][0]):
                 print('%-46s n=%3d %8.3f ms %7.1f TF/s' % (tag, d[2], d[0], d[1] / d[0] / 1e9), file=sys.stderr)
         value = world * B * args.steps / (ms * 1e-3)
-        line = {'metric': 'train samples/sec (3-modality MoPoE, 128px)', 'value': value, 'unit': 'samples/s',
+        metric = 'train samples/sec (3-modality MoPoE, 128px)'
+        if args.config != '2':
+            metric = 'train samples/sec (BASELINE config %s)' % args.config
+        line = {'metric': metric, 'value': value, 'unit': 'samples/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
                 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': B * world,
+                'config': {'workload': cfg['workload'], 'per_gpu_batch': B, 'global_batch': B * world,
                            'parallelism': 'dp%d' % world, 'cuda_graph': not args.no_graph, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
                 'clocks': sampler.summary(),
                 'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s',
@@ -308,7 +331,7 @@ def main():
                 'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                              'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src, 'timing': timing,
                              'kernel': 'implicit-GEMM conv family (fprop+dgrad+wgrad), %d launches/step' % len(prof),
-                             'gemm_ms_per_step': gemm_ms, 'step_tensor_frac': value / world * GFLOP_PER_SAMPLE_TRAIN / 1e3 / peak_tf,
+                             'gemm_ms_per_step': gemm_ms, 'step_tensor_frac': value / world * cfg['gflop'] / 1e3 / peak_tf,
                              'by_kind': {k: {'ms': v[0], 'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else 0.0, 'launches': v[2]}
                                          for k, v in by_kind.items()}}}
         if not args.no_cpu_baseline:
