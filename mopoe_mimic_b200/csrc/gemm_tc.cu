@@ -310,6 +310,7 @@ struct TcWgParams {
     long long K;                      // R*KW
     float* out;                       // dWp (Z == 1) or workspace [Z][N][K]
     int accumulate;
+    int NTN, tiles_out, items;        // persistent schedule: n-tiles, output tiles, tiles_out * Z work items
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -428,6 +429,146 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// PERSISTENT variant: one CTA per SM loops over work items (output tile x pixel split); the accumulator is
+// double-buffered in TMEM (2 x BNJ columns), so draining item i (tcgen05.ld -> fp32 partial tile in global) overlaps
+// the MMAs of item i+1 and the TMEM allocation / barrier set-up is paid once per SM instead of once per tile.
+// Items are ordered split-major: the CTAs running side by side work on the SAME pixel range, so the dY / window
+// tiles they share come out of L2.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapY,
+                             const TcWgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* const gen = smem_raw + (base - raw);
+    const uint32_t y_bytes = 2 * WG_BKM * 128, a_bytes = (uint32_t)(p.BNJ / 64) * WG_BKM * 128;
+    const uint32_t stage_bytes = y_bytes + a_bytes;
+    const uint32_t hdr = base + (uint32_t)p.stages * stage_bytes;
+    // header: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+    const uint32_t full0 = hdr, empty0 = hdr + 8u * p.stages, tfull0 = hdr + 16u * p.stages, tempty0 = tfull0 + 16,
+                   tmem_slot = tempty0 + 16;
+    volatile uint32_t* tmem_slot_gen =
+        reinterpret_cast<volatile uint32_t*>(gen + (size_t)p.stages * stage_bytes + 16 * p.stages + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA);
+        prefetch_tmap(&mapY);
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(tfull0 + 8 * s, 1);
+            mbar_init(tempty0 + 8 * s, 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+                const int z = item / p.tiles_out, tile = item - z * p.tiles_out;
+                const int jt = tile / p.NTN, nt = tile - jt * p.NTN;
+                const int r = jt / p.JT, j0 = (jt - r * p.JT) * p.BNJ, n0 = nt * 128;
+                const int mt_begin = z * p.m_per_split, mt_end = min(p.TM, mt_begin + p.m_per_split);
+                for (int mt = mt_begin; mt < mt_end; ++mt) {
+                    const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t sy = base + stage * stage_bytes, sa = sy + y_bytes;
+                    const uint32_t bar = full0 + 8 * stage;
+                    mbar_expect_tx(bar, stage_bytes);
+                    tma_load_4d(sy, &mapY, bar, n0, t0 * p.bx, t1 * p.by, t2 * p.nb);
+                    tma_load_4d(sy + WG_BKM * 128, &mapY, bar, n0 + 64, t0 * p.bx, t1 * p.by, t2 * p.nb);
+                    for (int qd = 0; qd < p.BNJ / 64; ++qd)
+                        tma_load_5d(sa + qd * WG_BKM * 128, &mapA, bar, j0 + 64 * qd, t0 * p.bx, t1 * p.by, r, t2 * p.nb);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.BNJ, 1, 1);      // both operands MN-major
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++iter) {
+                const int z = item / p.tiles_out;
+                const int mt_begin = z * p.m_per_split, mt_end = min(p.TM, mt_begin + p.m_per_split);
+                const int nkb = mt_end - mt_begin;
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);              // epilogue has drained this accumulator
+                fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BNJ);
+                for (int it = 0; it < nkb; ++it) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    fence_after();
+                    const uint32_t sy = base + stage * stage_bytes, sa = sy + y_bytes;
+                    const uint64_t dy = smem_desc_sw128(sy, WG_BKM * 128, 1024), da = smem_desc_sw128(sa, WG_BKM * 128, 1024);
+#pragma unroll
+                    for (int k = 0; k < WG_BKM / 16; ++k)
+                        umma_bf16(d_tmem, dy + 128 * k, da + 128 * k, idesc, (it | k) != 0);
+                    umma_commit(empty0 + 8 * stage);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull0 + 8 * acc);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const bool direct_acc = p.Z == 1 && p.accumulate;
+        int iter = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++iter) {
+            const int z = item / p.tiles_out, tile = item - z * p.tiles_out;
+            const int jt = tile / p.NTN, nt = tile - jt * p.NTN;
+            const int r = jt / p.JT, j0 = (jt - r * p.JT) * p.BNJ;
+            const int n = nt * 128 + q * 32 + lane;
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
+            float* orow = p.out + ((long long)z * p.N + n) * p.K + (long long)r * p.KW + j0;
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BNJ);
+            for (int c = 0; c < p.BNJ; c += 16) {
+                float v[16];
+                __syncwarp();
+                tmem_ld16(t_addr + (uint32_t)c, v);
+                if (n < p.N && j0 + c < p.KW) {
+                    float* dp = orow + c;
+                    if (j0 + c + 16 <= p.KW && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            if (direct_acc) {
+                                float4 e = reinterpret_cast<float4*>(dp)[j];
+                                o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+                            }
+                            reinterpret_cast<float4*>(dp)[j] = o;
+                        }
+                    } else {
+                        for (int j = 0; j < 16; ++j)
+                            if (j0 + c + j < p.KW) dp[j] = (direct_acc ? dp[j] : 0.f) + v[j];
+                    }
+                }
+            }
+            fence_before();
+            mbar_arrive(tempty0 + 8 * acc);
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
 void mopoe_split_reduce_launch(const float* ws, int Z, long long n, float* out, int accumulate, cudaStream_t st);
 void mopoe_wgrad_finish_launch(const float* part, int Z, int A, int B, int T, int bpad, float* grad, int accumulate,
                                cudaStream_t st);
@@ -442,6 +583,15 @@ int mopoe_tc_wgrad_eligible(const mopoe_window_t* A, const mopoe_rows_t* dY) {
     if ((dY->s0 % 8) || (dY->s1 % 8) || (dY->s2 % 8) || (dY->d_off % 8)) return 0;
     if ((reinterpret_cast<uintptr_t>(A->a) & 15) || (reinterpret_cast<uintptr_t>(dY->d) & 15)) return 0;
     return 1;
+}
+
+static int wg_persistent() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_WGRAD_PERSISTENT");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
 }
 
 static void wg_plan(const mopoe_window_t* A, const mopoe_rows_t* dY, TcWgParams& p) {
@@ -474,8 +624,28 @@ static void wg_plan(const mopoe_window_t* A, const mopoe_rows_t* dY, TcWgParams&
         const double eff = (double)items / (double)(waves * 148);
         if (eff > best_eff + 0.02) { best_eff = eff; Z = z; }
     }
+    if (wg_persistent()) {
+        // persistent schedule: no per-item set-up cost, so the split only trades tail waste against partial-tile traffic.
+        // estimated time (us) = ceil(items / 148) * (k-blocks per item * t_kb + t_item) + Z * N * K * 8 B / ~5 TB/s
+        const double t_kb = 0.14 * (double)(p.BNJ / 64) + 0.05, t_item = 0.6;
+        double best_t = 1e30;
+        Z = 1;
+        for (int z = 1; z <= 64 && z <= p.TM; ++z) {
+            const int mps = (p.TM + z - 1) / z;
+            const int zz = (p.TM + mps - 1) / mps;
+            if (zz != z) continue;
+            if (z > 1 && (mps < 4 || (long long)z * p.N * p.K * 4 > ws_cap)) break;
+            const long long items = (long long)tiles_out * z;
+            const double t = (double)((items + 147) / 148) * (mps * t_kb + t_item) + (z > 1 ? (double)z : 0.5) * p.N * (double)p.K * 8.0 / 5.0e6;
+            if (t < best_t * 0.98) { best_t = t; Z = z; }
+        }
+    }
     p.m_per_split = (p.TM + Z - 1) / Z;
     p.Z = (p.TM + p.m_per_split - 1) / p.m_per_split;
+    p.NTN = (p.N + 127) / 128;
+    p.tiles_out = tiles_out;
+    p.items = tiles_out * p.Z;
+    if (wg_persistent()) p.tmem_cols = pow2_ceil(2 * p.BNJ < 32 ? 32 : 2 * p.BNJ);
     const int stage_bytes = 2 * WG_BKM * 128 + (p.BNJ / 64) * WG_BKM * 128;
     int stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -521,10 +691,26 @@ int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* 
         if (e != cudaSuccess) MOPOE_FAIL("conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         g_wg_attr_set = true;
     }
-    dim3 grid((unsigned)(p.R * p.JT), (unsigned)((p.N + 127) / 128), (unsigned)p.Z);
     cudaStream_t st = (cudaStream_t)stream;
-    conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapY, p);
-    MOPOE_CHECK_LAUNCH("conv_wgrad_tc");
+    if (wg_persistent()) {
+        static bool attr_p = false;
+        static int num_sms = 148;
+        if (!attr_p) {
+            cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+            if (e != cudaSuccess) MOPOE_FAIL("conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+            attr_p = true;
+        }
+        const int grid = p.items < num_sms ? p.items : num_sms;
+        conv_wgrad_tc_persist_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapY, p);
+        MOPOE_CHECK_LAUNCH("conv_wgrad_tc_persist");
+    } else {
+        dim3 grid((unsigned)(p.R * p.JT), (unsigned)((p.N + 127) / 128), (unsigned)p.Z);
+        conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapY, p);
+        MOPOE_CHECK_LAUNCH("conv_wgrad_tc");
+    }
     if (fin) {
         MOPOE_REQUIRE(fin[0] == p.N && (long long)fin[2] * fin[3] == p.K, "conv_wgrad_tc: finish spec does not match N/K");
         mopoe_wgrad_finish_launch((const float*)ws, p.Z, fin[0], fin[1], fin[2], fin[3], dWp, accumulate, st);
