@@ -176,6 +176,7 @@ class GraphedTrainStep:
         dev = flags.device
         self.exp = exp
         self.allreduce = allreduce
+        self._copy_stream = None
         self.static = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in example_batch.items()}
         for k, v in example_batch.items():
             self.static[k].copy_(v)
@@ -205,9 +206,37 @@ class GraphedTrainStep:
         self.keys = (['total_loss', 'joint_divergence'] + ['kld.' + k for k in out['klds']]
                      + ['log_prob.' + k for k in out['log_probs']])
 
-    def __call__(self, batch):
+    def _stage_host_batch(self, batch):
+        """Host (pinned) batch -> one of two device staging sets on a COPY stream, so the H2D transfer of step i+1
+        runs under step i's graph instead of in front of its own (the loader side of run_epochs.py:61-62)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staging = [{k: torch.empty_like(t) for k, t in self.static.items()} for _ in range(2)]
+            self._staged = [torch.cuda.Event(), torch.cuda.Event()]
+            self._consumed = [None, None]
+            self._slot = 0
+        i = self._slot
+        self._slot ^= 1
+        cs, cur = self._copy_stream, torch.cuda.current_stream()
+        if self._consumed[i] is not None:
+            cs.wait_event(self._consumed[i])          # the step that last read this staging set has copied it out
+        with torch.cuda.stream(cs):
+            for k, t in self._staging[i].items():
+                t.copy_(batch[k], non_blocking=True)
+            self._staged[i].record(cs)
+        cur.wait_event(self._staged[i])
         for k, t in self.static.items():
-            t.copy_(batch[k], non_blocking=True)
+            t.copy_(self._staging[i][k], non_blocking=True)
+        if self._consumed[i] is None:
+            self._consumed[i] = torch.cuda.Event()
+        self._consumed[i].record(cur)
+
+    def __call__(self, batch):
+        if all(not batch[k].is_cuda for k in self.static):
+            self._stage_host_batch(batch)
+        else:
+            for k, t in self.static.items():
+                t.copy_(batch[k], non_blocking=True)
         self.graph.replay()
         if self.graph_b is not None:
             self.allreduce(self.exp.mm_vae.flat_grads)
