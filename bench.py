@@ -46,6 +46,9 @@ def parse():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=None, help='per-GPU batch (default: the config\'s)')
+    ap.add_argument('--dp-exchange', default='peer', choices=['peer', 'nccl'],
+                    help='N>1 gradient exchange: fused reduce-scatter+Adam+all-gather kernel over NVLink peer memory '
+                         '(default) or bucketed NCCL all-reduce followed by Adam')
     ap.add_argument('--config', default='2', choices=sorted(CONFIGS), help='BASELINE.json configuration (default 2)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-batch', type=int, default=16)
@@ -157,10 +160,12 @@ def main():
                          **cfg['flags'])
     torch.manual_seed(0)
     exp = P.Experiment(fl)
-    exp.set_optimizer()
+    from mopoe_mimic_b200.dp import FlatGradAllReduce, PeerExchange
+    peer = world > 1 and args.dp_exchange == 'peer'
+    exp.set_optimizer(exchange=PeerExchange(dev) if peer else None)     # (broadcasts rank 0's parameters)
     vae = exp.mm_vae
     vae.train()
-    if world > 1:
+    if world > 1 and not peer:
         dist.broadcast(vae.flat_params, 0)
         exp.optimizer.grad_scale = 1.0 / world
     # synthetic inputs of the reference's shapes (dataio/MimicDataset.py:414-428), true one-hot text
@@ -173,8 +178,7 @@ def main():
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
-    from mopoe_mimic_b200.dp import FlatGradAllReduce
-    ar = FlatGradAllReduce() if world > 1 else None      # bucketed NCCL all-reduce of the flat gradient buffer
+    ar = FlatGradAllReduce() if (world > 1 and not peer) else None      # bucketed NCCL all-reduce of the flat gradients
     stats_host = torch.empty(16, dtype=torch.float32).pin_memory()
     launches_per_step = None
     if args.no_graph or args.profile_kernels:
@@ -323,7 +327,7 @@ def main():
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
                 'data': 'synthetic',
                 'config': {'workload': cfg['workload'], 'per_gpu_batch': B, 'global_batch': B * world,
-                           'parallelism': 'dp%d' % world, 'cuda_graph': not args.no_graph, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
+                           'parallelism': 'dp%d' % world + ('' if world == 1 else (' peer-memory fused exchange' if peer else ' nccl all-reduce')), 'cuda_graph': not args.no_graph, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
                 'clocks': sampler.summary(),
                 'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s',
                         'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h},

@@ -243,6 +243,28 @@ int mopoe_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, flo
 int mopoe_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* coef,
                         float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* ---- data-parallel exchange (SURVEY §8 a25 / e): gradient reduce-scatter + Adam + parameter all-gather as ONE kernel
+ * over NVLink peer memory.  Replaces DistributedDataParallel's all-reduce followed by optimizer.step()
+ * (main_mimic.py:44-48, utils/utils.py:179-185, run_epochs.py:130-131).
+ * peers: for every rank r, the address (mapped into THIS process: CUDA IPC / symmetric memory) of its flat gradient
+ * buffer, its flat parameter buffer and its flag array (>= 2*world uint32, zero-initialised before the first call).
+ * Rank `rank` sums slice [rank*ceil(n/4/world)*4, ...) of all gradient buffers in rank order, multiplies by grad_scale,
+ * applies Adam (moments m, v: local, only the own slice is touched) and stores the new parameters into every rank's
+ * parameter buffer.  state: 2 local uint32 {epoch (initialise to 1), 0}.  coef as mopoe_adam_flat_dev.  Every rank
+ * must enqueue the same sequence of calls; the kernel completes only when all peers are done with this rank's
+ * buffers.  CUDA-graph capturable (nothing step-dependent is a launch argument).
+ * mc_grad / mc_param (both or neither): NVSwitch multicast addresses of the gradient / parameter buffers.  When given,
+ * the sum is formed inside the switch (multimem.ld_reduce) and the parameters are broadcast by it (multimem.st); the
+ * summation order is then the switch's, not rank order. */
+typedef struct {
+    const float* grad[16];
+    float*       param[16];
+    uint32_t*    flags[16];
+} mopoe_dp_peers_t;
+int mopoe_dp_adam_exchange(const mopoe_dp_peers_t* peers, const float* mc_grad, float* mc_param, float* m, float* v,
+                           int64_t n, int rank, int world, uint32_t* state, const float* coef, float beta1,
+                           float beta2, float eps, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

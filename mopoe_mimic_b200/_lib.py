@@ -40,6 +40,10 @@ class FusionCfg(C.Structure):
                 ('mem_cnt', C.c_int32 * 16), ('mem_idx', (C.c_int32 * 4) * 16), ('mem_end', (C.c_int32 * 4) * 16), ('norm', C.c_float), ('_pad', C.c_float)]
 
 
+class DpPeers(C.Structure):
+    _fields_ = [('grad', C.c_void_p * 16), ('param', C.c_void_p * 16), ('flags', C.c_void_p * 16)]
+
+
 _P, _I, _F, _L, _S = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_size_t
 _V, _W, _R = C.POINTER(View), C.POINTER(Window), C.POINTER(Rows)
 
@@ -79,6 +83,7 @@ SIGNATURES = {
     'mopoe_laplace_logprob_bwd': (_I, [_P, _P, _L, _F, _P, _P, _P]),
     'mopoe_categorical_logprob_sum': (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P]),
     'mopoe_categorical_logprob_bwd': (_I, [_P, _P, _L, _I, _P, _P, _P]),
+    'mopoe_dp_adam_exchange': (_I, [C.POINTER(DpPeers), _P, _P, _P, _P, _L, _I, _I, _P, _P, _F, _F, _F, _F, _P]),
     'mopoe_adam_flat': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P]),
 }
 

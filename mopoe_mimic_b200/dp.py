@@ -47,6 +47,88 @@ class FlatGradAllReduce:
         return flat
 
 
+class PeerExchange:
+    """NVLink peer-memory plumbing of the fused exchange kernel (mopoe_dp_adam_exchange, csrc/dp_exchange.cu).
+
+    The flat parameter and gradient buffers are allocated from torch's symmetric-memory pool, so after `connect()`
+    every rank holds the address of every peer's buffers; one kernel per step then does reduce-scatter (P2P loads),
+    Adam on the own 1/world slice and the parameter all-gather (P2P stores).  No NCCL call is on the step path and
+    the whole DP step stays ONE CUDA graph.  Adam moments are owner-sharded (ZeRO-1 style): `gather_moments()`
+    assembles the full tensors for a checkpoint."""
+
+    def __init__(self, device, group=None, multicast=None):
+        """multicast: None = use NVSwitch multicast (NVLS) when the symmetric allocation has it and world > 2
+        (MOPOE_DP_MULTICAST=0/1 overrides); True / False force it."""
+        import os
+        import torch.distributed._symmetric_memory as symm
+        env = os.environ.get('MOPOE_DP_MULTICAST')
+        self.want_multicast = multicast if multicast is not None else (None if env is None else env == '1')
+        self.symm = symm
+        self.device = device
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 16:
+            raise RuntimeError('PeerExchange supports up to 16 ranks on one NVLink domain')
+        self.params = self.grads = self.flags = self.state = self.peers = None
+        self.grad_scale = 1.0 / self.world
+
+    def alloc(self, total):
+        self.params = self.symm.empty(total, dtype=torch.float32, device=self.device)
+        self.grads = self.symm.empty(total, dtype=torch.float32, device=self.device)
+        self.flags = self.symm.empty(64, dtype=torch.int32, device=self.device)
+        self.flags.zero_()
+        return self.params, self.grads
+
+    def connect(self):
+        """exchange buffer addresses with the peers (collective) and broadcast rank 0's parameters"""
+        from . import _lib as L
+        hp = self.symm.rendezvous(self.params, group=self.group)
+        hg = self.symm.rendezvous(self.grads, group=self.group)
+        hf = self.symm.rendezvous(self.flags, group=self.group)
+        pk = L.DpPeers()
+        # the handles describe the symmetric ALLOCATION; our tensors may sit at an offset inside it (same on all ranks)
+        og = self.grads.data_ptr() - hg.buffer_ptrs[self.rank]
+        op = self.params.data_ptr() - hp.buffer_ptrs[self.rank]
+        of = self.flags.data_ptr() - hf.buffer_ptrs[self.rank]
+        for r in range(self.world):
+            pk.grad[r], pk.param[r], pk.flags[r] = hg.buffer_ptrs[r] + og, hp.buffer_ptrs[r] + op, hf.buffer_ptrs[r] + of
+        self.peers, self._handles = pk, (hp, hg, hf)
+        have_mc = bool(hp.multicast_ptr) and bool(hg.multicast_ptr)
+        use = self.want_multicast if self.want_multicast is not None else self.world > 2
+        if use and not have_mc:
+            if self.want_multicast:
+                raise RuntimeError('NVSwitch multicast was requested but the symmetric allocation has no multicast address')
+            use = False
+        self.multicast = use
+        self.mc_grad, self.mc_param = (hg.multicast_ptr + og, hp.multicast_ptr + op) if use else (0, 0)
+        self.state = torch.tensor([1, 0], dtype=torch.int32, device=self.device)
+        dist.broadcast(self.params, 0, group=self.group)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)          # every rank's flags are zeroed and mapped before the first kernel
+
+    def adam_step(self, m, v, coef, betas, eps):
+        import ctypes as C
+        from . import _lib as L
+        L.call('mopoe_dp_adam_exchange', C.byref(self.peers), C.c_void_p(self.mc_grad), C.c_void_p(self.mc_param),
+               L.ptr(m), L.ptr(v), self.params.numel(), self.rank,
+               self.world, L.ptr(self.state), L.ptr(coef), float(betas[0]), float(betas[1]), float(eps),
+               float(self.grad_scale), L.stream_ptr())
+
+    def slice_bounds(self):
+        n4 = self.params.numel() // 4
+        per = (n4 + self.world - 1) // self.world
+        return [(min(n4, r * per) * 4, min(n4, (r + 1) * per) * 4) for r in range(self.world)]
+
+    def gather_moments(self, m, v):
+        """full Adam moments on every rank (for optimizer checkpoints): each slice comes from its owner"""
+        for r, (s, e) in enumerate(self.slice_bounds()):
+            if e > s:
+                dist.broadcast(m[s:e], r, group=self.group)
+                dist.broadcast(v[s:e], r, group=self.group)
+        return m, v
+
+
 def broadcast_flat(flat, src=0, group=None):
     """rank-0 parameters to every rank (what DDP's constructor does)"""
     if dist.is_initialized() and dist.get_world_size(group) > 1:

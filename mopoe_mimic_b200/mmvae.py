@@ -279,7 +279,9 @@ class MMVaeMimic(BaseMMVae):
             torch.save(getattr(self, DEC_NAME[m]).state_dict(), os.path.join(self.flags.dir_checkpoints, getattr(self.flags, d)))
 
     # ---- flat parameter / gradient storage (one Adam launch, one all-reduce buffer) ---------------------------------
-    def flatten_(self):
+    def flatten_(self, alloc=None):
+        """Move every parameter (and its .grad) into ONE flat fp32 buffer each.  alloc(total) -> (flat, flat_grads)
+        lets the data-parallel exchange supply NVLink-shared (symmetric) buffers instead of plain device memory."""
         params = [p for p in self.parameters()]
         ALIGN = 64                      # elements: every tensor starts 256-B aligned (kernels use 16-B vector loads)
         offs, total = [], 0
@@ -287,8 +289,14 @@ class MMVaeMimic(BaseMMVae):
             offs.append(total)
             total += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
         dev = params[0].device
-        flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        if alloc is not None:
+            flat, flat_g = alloc(total)
+            assert flat.numel() == total and flat_g.numel() == total and flat.dtype == flat_g.dtype == torch.float32
+            flat.zero_()
+            flat_g.zero_()
+        else:
+            flat = torch.zeros(total, dtype=torch.float32, device=dev)
+            flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         for p, off in zip(params, offs):
             n = p.numel()
             flat[off:off + n].copy_(p.data.reshape(-1))

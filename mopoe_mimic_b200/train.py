@@ -78,20 +78,28 @@ class Experiment:
             return VAEtrimodalMimic(self.flags, self.modalities, self.subsets)
         return MMVaeMimic(self.flags, self.modalities, self.subsets)
 
-    def set_optimizer(self):
-        """experiment.py:171-178: Adam(lr, betas), eps 1e-8, no weight decay — as ONE fused launch over the flat buffers."""
-        self.optimizer = FlatAdam(self.mm_vae, self.flags.initial_learning_rate, (self.flags.beta_1, self.flags.beta_2))
+    def set_optimizer(self, exchange=None):
+        """experiment.py:171-178: Adam(lr, betas), eps 1e-8, no weight decay — as ONE fused launch over the flat buffers.
+        exchange: a dp.PeerExchange — the flat buffers then live in NVLink-shared memory and step() becomes the fused
+        reduce-scatter + Adam + all-gather kernel (the DDP all-reduce + optimizer.step of the reference)."""
+        self.optimizer = FlatAdam(self.mm_vae, self.flags.initial_learning_rate, (self.flags.beta_1, self.flags.beta_2),
+                                  exchange=exchange)
         return self.optimizer
 
 
 class FlatAdam:
     """torch.optim.Adam semantics over the model's flat parameter / gradient buffers (mopoe_adam_flat)."""
 
-    def __init__(self, model, lr, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, model, lr, betas=(0.9, 0.999), eps=1e-8, exchange=None):
         self.model = model
+        self.exchange = exchange
         if not hasattr(model, 'flat_params'):
-            model.flatten_()
+            model.flatten_(exchange.alloc if exchange is not None else None)
+        elif exchange is not None:
+            raise RuntimeError('the model was flattened before the peer exchange was attached')
         self.p, self.g = model.flat_params, model.flat_grads
+        if exchange is not None:
+            exchange.connect()
         self.m = torch.zeros_like(self.p)
         self.v = torch.zeros_like(self.p)
         self.lr, self.betas, self.eps = lr, betas, eps
@@ -112,9 +120,13 @@ class FlatAdam:
         eng = self.model.rt.eng(self.p.device)
         L.call('mopoe_step_advance', L.ptr(eng.rng_step), L.ptr(self.step_t), L.ptr(self.coef), float(self.lr),
                float(self.betas[0]), float(self.betas[1]), L.stream_ptr())
-        L.call('mopoe_adam_flat_dev', L.ptr(self.p), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.p.numel(),
-               L.ptr(self.coef), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.grad_scale),
-               L.stream_ptr())
+        if self.exchange is not None:
+            # reduce-scatter + Adam + all-gather in one kernel over peer memory; moments of a slice live on its owner
+            self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps)
+        else:
+            L.call('mopoe_adam_flat_dev', L.ptr(self.p), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.p.numel(),
+                   L.ptr(self.coef), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.grad_scale),
+                   L.stream_ptr())
         eng.invalidate_packs()      # the kernel rewrote the weights in place: packed copies are stale
 
 
@@ -197,7 +209,7 @@ class GraphedTrainStep:
             self.stats = packed_stats(out)
             self.nan_flag = out['results']['latents']['_nan_flag']
             if allreduce is None:
-                exp.optimizer.step()
+                exp.optimizer.step()          # (with a PeerExchange this IS the gradient exchange: still one graph)
         if allreduce is not None:
             self.graph_b = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_b, pool=self.graph.pool()):

@@ -1,0 +1,122 @@
+"""Multi-GPU check of the fused peer-memory exchange kernel (run under torchrun, one rank per GPU; also launched by
+tests/test_gpu_dp.py when the box has >= 2 GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 \
+        tests/dp_peer_check.py
+
+mopoe_dp_adam_exchange (reduce-scatter + Adam + all-gather over NVLink peer memory) against the unfused path it
+replaces: NCCL all-reduce of the gradients followed by mopoe_adam_flat_dev — several steps, eagerly and replayed from
+a CUDA graph.  With 2 ranks the gradient sum has one possible order, so the comparison is bit-exact; with more ranks
+NCCL's ring order differs from the kernel's rank order and the tolerance is a few ulps.
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    for mc in (False, True):
+        run(mc)
+    dist.destroy_process_group()
+
+
+def run(multicast):
+    from mopoe_mimic_b200 import _lib as L
+    from mopoe_mimic_b200.dp import PeerExchange
+    world = int(os.environ['WORLD_SIZE'])
+    rank = int(os.environ['RANK'])
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=dev)
+    n = (3 << 20) + 192                       # not a multiple of world * 1024: ragged last slice
+    px = PeerExchange(dev, multicast=multicast)
+    params, grads = px.alloc(n)
+    g0 = torch.Generator(device='cpu').manual_seed(0)
+    params.copy_(torch.randn(n, generator=g0))
+    if rank != 0:
+        params.add_(1.0)                      # connect() must overwrite this with rank 0's values
+    px.connect()
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    p_ref, m_ref, v_ref = params.clone(), m.clone(), v.clone()
+    coef = torch.zeros(2, device=dev)
+    b1, b2, eps, lr = 0.9, 0.999, 1e-8, 1e-3
+    gr = torch.Generator(device='cpu').manual_seed(100 + rank)
+    step_grads = [torch.randn(n, generator=gr).to(dev) * (1 + rank) for _ in range(6)]
+    tol = 0.0 if world == 2 else 1e-6
+    worst = 0.0
+
+    def set_coef(t):
+        coef.copy_(torch.tensor([lr / (1 - b1 ** t), 1.0 / (1 - b2 ** t) ** 0.5]))
+
+    def reference_step(g):
+        gs = g.clone()
+        dist.all_reduce(gs)
+        L.call('mopoe_adam_flat_dev', L.ptr(p_ref), L.ptr(gs), L.ptr(m_ref), L.ptr(v_ref), n, L.ptr(coef), b1, b2, eps,
+               1.0 / world, L.stream_ptr())
+
+    def check(tag):
+        nonlocal worst
+        torch.cuda.synchronize()
+        err = float((params - p_ref).abs().max())
+        s, e = px.slice_bounds()[rank]
+        em = float((m[s:e] - m_ref[s:e]).abs().max()) if e > s else 0.0
+        worst = max(worst, err, em)
+        assert err <= tol and em <= tol, '%s: rank %d param err %.3e moment err %.3e' % (tag, rank, err, em)
+
+    # eager steps
+    for t in range(3):
+        set_coef(t + 1)
+        grads.copy_(step_grads[t])
+        px.adam_step(m, v, coef, (b1, b2), eps)
+        reference_step(step_grads[t])
+        check('eager step %d' % t)
+    # the same kernel replayed from a CUDA graph (epochs advance on the device)
+    static_g = torch.zeros(n, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        grads.copy_(static_g)
+        px.adam_step(m, v, coef, (b1, b2), eps)
+    for t in range(3, 6):
+        set_coef(t + 1)
+        static_g.copy_(step_grads[t])
+        graph.replay()
+        reference_step(step_grads[t])
+        check('graph step %d' % t)
+    # sharded moments -> full tensors
+    px.gather_moments(m, v)
+    torch.cuda.synchronize()
+    assert float((m - m_ref).abs().max()) <= tol and float((v - v_ref).abs().max()) <= tol
+    if os.environ.get('DP_PEER_TIME'):          # developer aid: kernel time at the model's real size (612 MB buffers)
+        nbig = 153067136
+        px2 = PeerExchange(dev, multicast=multicast)
+        px2.alloc(nbig)
+        px2.connect()
+        m2, v2 = torch.zeros(nbig, device=dev), torch.zeros(nbig, device=dev)
+        for _ in range(3):
+            px2.adam_step(m2, v2, coef, (b1, b2), eps)
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            px2.adam_step(m2, v2, coef, (b1, b2), eps)
+        b.record()
+        torch.cuda.synchronize()
+        if rank == 0:
+            print('exchange kernel (multicast=%s) at n=%d: %.3f ms/step' % (multicast, nbig, a.elapsed_time(b) / 10), flush=True)
+    dist.barrier()
+    if rank == 0:
+        print('dp_peer_check PASS world=%d multicast=%s n=%d worst abs err %.3e' % (world, multicast, n, worst), flush=True)
+
+
+if __name__ == '__main__':
+    main()
