@@ -20,6 +20,7 @@
 
 constexpr int DPX_MAX_WORLD = 16;
 constexpr int DPX_THREADS = 256;
+constexpr int DPX_UNROLL = 4;
 constexpr unsigned long long DPX_TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
 
 struct DpxPeers {
@@ -94,33 +95,59 @@ dp_adam_exchange_kernel(const DpxPeers peers, const float* __restrict__ mc_grad,
     const long long per = (n4 + world - 1) / world;
     const long long begin = (long long)rank * per, end = begin + per < n4 ? begin + per : n4;
     float4* const p_own = reinterpret_cast<float4*>(peers.param[rank]);
-    const long long stride = (long long)gridDim.x * DPX_THREADS;
-    for (long long i = begin + (long long)blockIdx.x * DPX_THREADS + threadIdx.x; i < end; i += stride) {
-        float4 g;
-        if (MC) {
-            g = mc_ld_reduce(reinterpret_cast<const float4*>(mc_grad) + i);
-        } else {
-            g = ld_peer(reinterpret_cast<const float4*>(peers.grad[0]) + i);
+    // DPX_UNROLL independent float4 per thread and iteration, every remote load issued before the first use: NVLink
+    // round trips are microseconds, so the bytes in flight per SM — not the instruction count — set the throughput
+    const long long stride = (long long)gridDim.x * DPX_THREADS * DPX_UNROLL;
+    for (long long i0 = begin + (long long)blockIdx.x * DPX_THREADS * DPX_UNROLL + threadIdx.x; i0 < end; i0 += stride) {
+        float4 g[DPX_UNROLL], pp[DPX_UNROLL], mm[DPX_UNROLL], vv[DPX_UNROLL];
+#pragma unroll
+        for (int u = 0; u < DPX_UNROLL; ++u) {
+            const long long i = i0 + (long long)u * DPX_THREADS;
+            if (i < end) g[u] = MC ? mc_ld_reduce(reinterpret_cast<const float4*>(mc_grad) + i)
+                                   : ld_peer(reinterpret_cast<const float4*>(peers.grad[0]) + i);
+        }
+        if (!MC) {
             for (int r = 1; r < world; ++r) {
-                const float4 t = ld_peer(reinterpret_cast<const float4*>(peers.grad[r]) + i);
-                g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+                float4 t[DPX_UNROLL];
+#pragma unroll
+                for (int u = 0; u < DPX_UNROLL; ++u) {
+                    const long long i = i0 + (long long)u * DPX_THREADS;
+                    if (i < end) t[u] = ld_peer(reinterpret_cast<const float4*>(peers.grad[r]) + i);
+                }
+#pragma unroll
+                for (int u = 0; u < DPX_UNROLL; ++u) {          // rank order: fixed summation order
+                    g[u].x += t[u].x; g[u].y += t[u].y; g[u].z += t[u].z; g[u].w += t[u].w;
+                }
             }
         }
-        float4 pp = p_own[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
-        float* P = &pp.x; float* G = &g.x; float* M = &mm.x; float* V = &vv.x;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {          // same arithmetic as adam_kernel (elementwise.cu)
-            const float gk = G[k] * gscale;
-            M[k] = b1 * M[k] + (1.f - b1) * gk;
-            V[k] = b2 * V[k] + (1.f - b2) * gk * gk;
-            P[k] -= lr_c * M[k] / (sqrtf(V[k]) * inv_sqrt_bc2 + eps);
+        for (int u = 0; u < DPX_UNROLL; ++u) {
+            const long long i = i0 + (long long)u * DPX_THREADS;
+            if (i < end) {
+                pp[u] = p_own[i];
+                mm[u] = reinterpret_cast<float4*>(m)[i];
+                vv[u] = reinterpret_cast<float4*>(v)[i];
+            }
         }
-        reinterpret_cast<float4*>(m)[i] = mm;
-        reinterpret_cast<float4*>(v)[i] = vv;
-        if (MC) {
-            mc_st(reinterpret_cast<float4*>(mc_param) + i, pp);
-        } else {
-            for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.param[r])[i] = pp;
+#pragma unroll
+        for (int u = 0; u < DPX_UNROLL; ++u) {
+            const long long i = i0 + (long long)u * DPX_THREADS;
+            if (i >= end) continue;
+            float* P = &pp[u].x; float* G = &g[u].x; float* M = &mm[u].x; float* V = &vv[u].x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {          // same arithmetic as adam_kernel (elementwise.cu)
+                const float gk = G[k] * gscale;
+                M[k] = b1 * M[k] + (1.f - b1) * gk;
+                V[k] = b2 * V[k] + (1.f - b2) * gk * gk;
+                P[k] -= lr_c * M[k] / (sqrtf(V[k]) * inv_sqrt_bc2 + eps);
+            }
+            reinterpret_cast<float4*>(m)[i] = mm[u];
+            reinterpret_cast<float4*>(v)[i] = vv[u];
+            if (MC) {
+                mc_st(reinterpret_cast<float4*>(mc_param) + i, pp[u]);
+            } else {
+                for (int r = 0; r < world; ++r) reinterpret_cast<float4*>(peers.param[r])[i] = pp[u];
+            }
         }
     }
     // ---- barrier 2: my stores have landed everywhere; wait until every peer is done with my buffers ---------------
@@ -161,7 +188,7 @@ extern "C" int mopoe_dp_adam_exchange(const mopoe_dp_peers_t* peers, const float
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     const long long n4 = n / 4, per = (n4 + world - 1) / world;
-    long long blocks = (per + DPX_THREADS - 1) / DPX_THREADS;
+    long long blocks = (per + DPX_THREADS * DPX_UNROLL - 1) / (DPX_THREADS * DPX_UNROLL);
     if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
     if (blocks < 1) blocks = 1;
     MOPOE_REQUIRE((mc_grad == nullptr) == (mc_param == nullptr), "dp_adam_exchange: give both multicast addresses or neither");

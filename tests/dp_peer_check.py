@@ -48,7 +48,7 @@ def run(multicast):
     b1, b2, eps, lr = 0.9, 0.999, 1e-8, 1e-3
     gr = torch.Generator(device='cpu').manual_seed(100 + rank)
     step_grads = [torch.randn(n, generator=gr).to(dev) * (1 + rank) for _ in range(6)]
-    tol = 0.0 if world == 2 else 1e-6
+    tol = 0.0 if world == 2 else 2e-5        # (more ranks: NCCL's ring order vs the kernel's rank order)
     worst = 0.0
 
     def set_coef(t):
