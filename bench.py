@@ -181,7 +181,7 @@ def main():
     ar = FlatGradAllReduce() if (world > 1 and not peer) else None      # bucketed NCCL all-reduce of the flat gradients
     stats_host = torch.empty(16, dtype=torch.float32).pin_memory()
     launches_per_step = None
-    if args.no_graph or args.profile_kernels:
+    if args.no_graph:
         def step_resident():
             return P.train_step(exp, (dict(resident), None), ar)
 

@@ -117,6 +117,13 @@ def _main_wgrad(eng, spec, xin, dout, param):
     return conv_form_grad(eng.wgrad_down(*args), param.shape)
 
 
+def grad_slot(param):
+    """the parameter's view into the flat gradient buffer, when kernels may accumulate into it directly (the autograd
+    node then returns None for it: no AccumulateGrad add kernel, no temporary)"""
+    g = param.grad if param is not None else None
+    return g if (g is not None and g.is_contiguous() and g.dtype == torch.float32) else None
+
+
 class ResBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_t, run, *params):
@@ -179,41 +186,66 @@ class ResBlockFn(torch.autograd.Function):
         r = Act.like(r_t, B, OH, OW, sp.cout)
         dy = Act.like(dy_t.contiguous(), B, OH, OW, sp.cout, oph, opw)
         G = {}
+        po = run.param_objs
+
+        def bn_slots(prefix):
+            """(dgamma, dbeta, accumulate): the flat-gradient views when present, else fresh tensors returned to autograd"""
+            pw, pb = po[prefix + '.weight'], po[prefix + '.bias']
+            gw, gb = grad_slot(pw), grad_slot(pb)
+            if gw is not None and gb is not None:
+                G[prefix + '.weight'] = G[prefix + '.bias'] = None
+                return gw, gb, True
+            G[prefix + '.weight'], G[prefix + '.bias'] = eng.f32(pw.numel()), eng.f32(pb.numel())
+            return G[prefix + '.weight'], G[prefix + '.bias'], False
+
+        def bias_grad(name, act):
+            slot = grad_slot(po[name])
+            if slot is not None:
+                eng.colsum(act, slot, accumulate=True)
+                return None
+            return eng.colsum(act)
+
         # y = a*BN3(r) + b*(c*2m2)
-        G[short + '.1.weight'], G[short + '.1.bias'] = eng.f32(sp.cout), eng.f32(sp.cout)
-        dr, dc = eng.combine_bwd(dy, sp.a, r, st3, P[short + '.1.weight'], G[short + '.1.weight'], G[short + '.1.bias'],
+        dg, db, acc = bn_slots(short + '.1')
+        dr, dc = eng.combine_bwd(dy, sp.a, r, st3, P[short + '.1.weight'], dg, db,
                                  m2, mode, sp.b, Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device),
-                                 Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device))
+                                 Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device), accumulate=acc)
         # shortcut conv
         Ws_ = P[short + '.0.weight']
-        G[short + '.0.weight'] = _main_wgrad(eng, sp, x, dr, run.param_objs[short + '.0.weight'])
+        G[short + '.0.weight'] = _main_wgrad(eng, sp, x, dr, po[short + '.0.weight'])
         # the shortcut bias feeds a train-mode BatchNorm: its gradient sum(dr) is analytically zero (BN backward
         # output sums to zero per channel); the reference only accumulates rounding noise there
-        G[short + '.0.bias'] = torch.zeros(sp.cout, dtype=torch.float32, device=eng.device)
+        G[short + '.0.bias'] = None if grad_slot(po[short + '.0.bias']) is not None else \
+            torch.zeros(sp.cout, dtype=torch.float32, device=eng.device)
         dxs = _main_dgrad(eng, sp, dr, Ws_, dt, H, W)
         # conv2
         W2 = P['conv2.weight']
-        G['conv2.weight'] = _main_wgrad(eng, sp, a2, dc, run.param_objs['conv2.weight'])
+        G['conv2.weight'] = _main_wgrad(eng, sp, a2, dc, po['conv2.weight'])
         if sp.inner_bias:
-            G['conv2.bias'] = eng.colsum(dc)
+            G['conv2.bias'] = bias_grad('conv2.bias', dc)
         da2 = _main_dgrad(eng, sp, dc, W2, dt, H, W)
         # relu, bn2, dropout1
-        G['bn2.weight'], G['bn2.bias'] = eng.f32(sp.cin), eng.f32(sp.cin)
         # (recomputing the ReLU gate from hh instead of re-reading a2 was measured SLOWER on B200: these passes are
         #  issue-bound, not DRAM-bound)
-        dh = eng.bn_bwd(da2, a2, 1.0, hh, m1, mode, st2, P['bn2.weight'], G['bn2.weight'], G['bn2.bias'], None,
-                        Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device))
-        # conv1 (1x1)
-        g1 = eng.wgrad_rows(a1, dh)                                   # [n_out, c_in]
-        G['conv1.weight'] = (g1.t() if sp.transposed else g1).reshape(P['conv1.weight'].shape)
+        dg, db, acc = bn_slots('bn2')
+        dh = eng.bn_bwd(da2, a2, 1.0, hh, m1, mode, st2, P['bn2.weight'], dg, db, None,
+                        Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device), accumulate=acc)
+        # conv1 (1x1): weight [n_out, c_in, 1..] (conv) or [c_in, n_out, 1..] (transposed conv)
+        w1p = po['conv1.weight']
+        done = eng.wgrad_rows_param(dh, a1, w1p) if sp.transposed else eng.wgrad_rows_param(a1, dh, w1p)
+        if done:
+            G['conv1.weight'] = None
+        else:
+            g1 = eng.wgrad_rows(a1, dh)                               # [n_out, c_in]
+            G['conv1.weight'] = (g1.t() if sp.transposed else g1).reshape(P['conv1.weight'].shape)
         if sp.inner_bias:
-            G['conv1.bias'] = eng.colsum(dh)
+            G['conv1.bias'] = bias_grad('conv1.bias', dh)
         w1b = eng.packed(P['conv1.weight'], 'mat' if sp.transposed else 'matT')   # [c_in, n_out]
         da1 = eng.gemm_rows(dh, w1b, None, sp.cin)
         # relu, bn1 (+ the shortcut's input gradient)
-        G['bn1.weight'], G['bn1.bias'] = eng.f32(sp.cin), eng.f32(sp.cin)
-        dx = eng.bn_bwd(da1, a1, 1.0, x, None, L.MASK_NONE, st1, P['bn1.weight'], G['bn1.weight'], G['bn1.bias'], dxs,
-                        Act.empty(B, H, W, sp.cin, iph, ipw, dt, eng.device))
+        dg, db, acc = bn_slots('bn1')
+        dx = eng.bn_bwd(da1, a1, 1.0, x, None, L.MASK_NONE, st1, P['bn1.weight'], dg, db, dxs,
+                        Act.empty(B, H, W, sp.cin, iph, ipw, dt, eng.device), accumulate=acc)
         grads = [G[n] for n in sp.param_names()]
         return (dx.t.view_as(x_t), None, *grads)
 

@@ -168,7 +168,7 @@ class Engine:
                C.byref(c.view()), L.ptr(mask), mode, float(a), float(b), C.byref(out.view()), L.stream_ptr())
         return out
 
-    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out):
+    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out, accumulate=False):
         """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x).  gate = the saved post-ReLU
         activation (None: no ReLU)."""
         rows = x.B * x.H * x.W
@@ -178,22 +178,22 @@ class Engine:
         gv = C.byref(gate.view()) if gate is not None else None
         gg = gb = None      # reserved gate-recompute operands of the C ABI (not compiled in)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
-               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums), gg, gb,
-               L.ptr(self.counters), L.stream_ptr())
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(sums),
+               gg, gb, L.ptr(self.counters), L.stream_ptr())
         av = C.byref(addend.view()) if addend is not None else None
         L.call('mopoe_bn_bwd_apply', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), av, C.byref(out.view()), gb, L.stream_ptr())
         return out
 
-    def combine_bwd(self, dy, a, r, stats, gamma, dgamma, dbeta, mask2, mode2, b, dr, dc):
+    def combine_bwd(self, dy, a, r, stats, gamma, dgamma, dbeta, mask2, mode2, b, dr, dc, accumulate=False):
         """backward of y = a*BN(r) + b*(c*2mask2): BN reduction over (dy, r), then ONE pass writing dr and dc"""
         rows = r.B * r.H * r.W
         nc = self.nchunk(rows, r.C)
         ws = self.ws64(2 * nc * r.C)
         sums = self.f32(2, r.C)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), None, float(a), C.byref(r.view()), None, L.MASK_NONE,
-               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), 0, L.ptr(sums), None, None,
-               L.ptr(self.counters), L.stream_ptr())
+               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(sums),
+               None, None, L.ptr(self.counters), L.stream_ptr())
         L.call('mopoe_combine_bwd_apply', C.byref(dy.view()), float(a), C.byref(r.view()), L.ptr(stats[0]),
                L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), L.ptr(mask2), mode2, float(b), C.byref(dr.view()),
                C.byref(dc.view()), L.stream_ptr())
@@ -204,13 +204,14 @@ class Engine:
                L.stream_ptr())
         return out
 
-    def colsum(self, v, out=None):
+    def colsum(self, v, out=None, accumulate=False):
         rows = v.B * v.H * v.W
         nc = self.nchunk(rows, v.C)
         ws = self.ws64(2 * nc * v.C)
         if out is None:
             out = self.f32(v.C)
-        L.call('mopoe_colsum', C.byref(v.view()), L.ptr(out), 0, L.ptr(ws), nc, L.ptr(self.counters), L.stream_ptr())
+        L.call('mopoe_colsum', C.byref(v.view()), L.ptr(out), int(accumulate), L.ptr(ws), nc, L.ptr(self.counters),
+               L.stream_ptr())
         return out
 
     def convert(self, src_view, nchw, dst):
@@ -393,6 +394,15 @@ class Engine:
             rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, 0, n, x.W * n, x.H * x.W * n)
         self._gemm(win, w, bias, rows)
         return out
+
+    def wgrad_rows_param(self, x, dy, param):
+        """param.grad[n, c] += sum_m dy[m, n] x[m, c] (a 1x1 conv / linear weight [n, c, 1..]); False if the parameter
+        has no flat fp32 .grad to accumulate into"""
+        Cc = x.C
+        win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 1, Cc, 0, x.origin(), Cc,
+                       x.Ws * Cc, x.Hs * x.Ws * Cc, 0)
+        assert (x.B, x.H, x.W) == (dy.B, dy.H, dy.W) and tuple(param.shape[:2]) == (dy.C, Cc)
+        return self._wgrad_param(win, self.rows_of(dy), param, 1, Cc)
 
     def wgrad_rows(self, x, dy):
         """dW[n, c] = sum_m dy[m, n] x[m, c] over interior pixels (both any padding)"""
