@@ -335,26 +335,46 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
     if (tid == 0) fin.counter[blockIdx.x] = 0;                    // self-resetting: ready for the next launch
 }
 
-// finalize: ONE WARP per channel; lane l sums chunks l, l+32, ... then a shuffle tree — a fixed order, so the
-// result is run-to-run deterministic, and the chunk loop is 32x shorter than a thread-per-channel walk.
-__device__ __forceinline__ void chunk_sums(const double* ws, int nchunk, int C, int c, double& s, double& q) {
-    const int lane = threadIdx.x & 31;
+// finalize: FIN_SPLIT warps per channel (block = 8 warps = FIN_CH channels).  Warp j of a channel sums chunks
+// j*32 + lane, + 32*FIN_SPLIT, ... then a shuffle tree, and the FIN_SPLIT warp totals are added in warp order — a fixed
+// order, so the result is run-to-run deterministic.  ~9 dependent L2 round trips per lane instead of ~37: these
+// launches are pure latency (the partials are a few MB in L2), and a training step has ~260 of them.
+constexpr int FIN_SPLIT = 4, FIN_CH = 8 / FIN_SPLIT;
+__device__ __forceinline__ bool chunk_sums(const double* ws, int nchunk, int C, int& c, double& s, double& q) {
+    __shared__ double part[2][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int local = warp / FIN_SPLIT, j = warp - local * FIN_SPLIT;
+    c = blockIdx.x * FIN_CH + local;
     double a = 0.0, b = 0.0;
-    for (int k = lane; k < nchunk; k += 32) {
-        a += ws[((long long)k * 2 + 0) * C + c];
-        b += ws[((long long)k * 2 + 1) * C + c];
+    if (c < C) {
+#pragma unroll 4
+        for (int k = j * 32 + lane; k < nchunk; k += 32 * FIN_SPLIT) {
+            a += ws[((long long)k * 2 + 0) * C + c];
+            b += ws[((long long)k * 2 + 1) * C + c];
+        }
     }
-    s = warp_sum(a);
-    q = warp_sum(b);
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+        part[0][warp] = a;
+        part[1][warp] = b;
+    }
+    __syncthreads();
+    if (c >= C || j != 0 || lane != 0) return false;
+    s = q = 0.0;
+#pragma unroll
+    for (int t = 0; t < FIN_SPLIT; ++t) {
+        s += part[0][warp + t];
+        q += part[1][warp + t];
+    }
+    return true;
 }
 __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* ws, int nchunk, int C, double count, float eps,
                                                           float momentum, float* mean, float* invstd, float* rmean,
                                                           float* rvar) {
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (c >= C) return;
+    int c;
     double s, q;
-    chunk_sums(ws, nchunk, C, c, s, q);
-    if ((threadIdx.x & 31) != 0) return;
+    if (!chunk_sums(ws, nchunk, C, c, s, q)) return;
     double m = s / count;
     double var = q / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -369,11 +389,9 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const double* ws, int 
 
 __global__ void __launch_bounds__(256) sums_finalize_kernel(const double* ws, int nchunk, int C, float* out0, float* out1,
                                                             int accumulate, float* sums) {
-    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (c >= C) return;
+    int c;
     double s, q;
-    chunk_sums(ws, nchunk, C, c, s, q);
-    if ((threadIdx.x & 31) != 0) return;
+    if (!chunk_sums(ws, nchunk, C, c, s, q)) return;
     if (out0) out0[c] = (accumulate ? out0[c] : 0.f) + (float)s;   // dbeta / colsum
     if (out1) out1[c] = (accumulate ? out1[c] : 0.f) + (float)q;   // dgamma
     if (sums) {
@@ -415,7 +433,7 @@ extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int ma
     fin.mean = mean; fin.invstd = invstd; fin.rmean = running_mean; fin.rvar = running_var;
     if (launch_reduce<RED_STATS>(x, nullptr, nullptr, 1.f, mask, mask_mode, nullptr, nullptr, ws, nchunk, st, fin)) return 1;
     if (!counters) {
-        bn_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, fin.count, eps, momentum, mean, invstd,
+        bn_finalize_kernel<<<(x->C + FIN_CH - 1) / FIN_CH, 256, 0, st>>>(ws, nchunk, x->C, fin.count, eps, momentum, mean, invstd,
                                                           running_mean, running_var);
         MOPOE_CHECK_LAUNCH("bn_finalize");
     }
@@ -431,7 +449,7 @@ extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, d
     if (launch_reduce<RED_COLSUM>(v, nullptr, nullptr, 1.f, nullptr, MOPOE_MASK_NONE, nullptr, nullptr, ws, nchunk, st, fin))
         return 1;
     if (!counters) {
-        sums_finalize_kernel<<<(v->C + 7) / 8, 256, 0, st>>>(ws, nchunk, v->C, out, nullptr, accumulate, nullptr);
+        sums_finalize_kernel<<<(v->C + FIN_CH - 1) / FIN_CH, 256, 0, st>>>(ws, nchunk, v->C, out, nullptr, accumulate, nullptr);
         MOPOE_CHECK_LAUNCH("colsum_finalize");
     }
     return 0;
@@ -451,7 +469,7 @@ extern "C" int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* g
     if (launch_reduce<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st, fin, gate_gamma, gate_beta))
         return 1;
     if (!counters) {
-        sums_finalize_kernel<<<(x->C + 7) / 8, 256, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
+        sums_finalize_kernel<<<(x->C + FIN_CH - 1) / FIN_CH, 256, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
         MOPOE_CHECK_LAUNCH("bn_bwd_finalize");
     }
     return 0;
