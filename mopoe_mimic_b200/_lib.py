@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmopoe_b200.so')
+LIB_PATH = os.environ.get('MOPOE_LIB_PATH') or os.path.join(_HERE, 'libmopoe_b200.so')     # (override: developer A/B builds)
 
 F32, BF16 = 0, 1
 MASK_NONE, MASK_BC, MASK_ELEM = 0, 1, 2

@@ -584,65 +584,130 @@ extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const flo
 // ---- backward apply kernels ---------------------------------------------------------------------------
 // out  = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend,  g = gscale * dy * [gate > 0]
 // out2 = scale2 * dy * 2mask2   (optional second output sharing the read of dy: the dropout2 branch of a block)
+__device__ __forceinline__ void mask8(const uint2& t, float (&o)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o[i] = ((t.x >> (8 * i)) & 0xffu) ? 2.f : 0.f;
+        o[4 + i] = ((t.y >> (8 * i)) & 0xffu) ? 2.f : 0.f;
+    }
+}
+// These passes are LATENCY-bound, not issue-bound (ncu: 39 % issue slots, long-scoreboard stalls, 115 registers -> 2
+// blocks/SM): what sets their speed is the number of bytes in flight per SM.  So: operands stay PACKED between load and
+// use (4 registers per bf16 octet), the loads of U pixels are issued before the first use, the per-channel terms are
+// folded into 3 coefficients (dv = k1*g + ca*v + cb) and the register budget is capped for 3 blocks/SM.
+#ifndef BWD_U
+#define BWD_U 2
+#endif
+#ifndef BWD_MINB
+#define BWD_MINB 2
+#endif
 template <typename T>
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(DView<const T> dy, DView<const T> gate, int has_gate,
-                                                                  float gscale, DView<const T> x, const uint8_t* mask,
-                                                                  int mask_mode, const float* mean, const float* invstd,
-                                                                  const float* gamma, const float* sums, float inv_cnt,
-                                                                  DView<const T> addend, int has_add, DView<T> out,
-                                                                  DView<T> out2, int has_out2, const uint8_t* mask2,
-                                                                  int mask2_mode, float scale2, const float* gbeta,
-                                                                  unsigned total, unsigned stride) {
+__global__ void __launch_bounds__(EW_THREADS, BWD_MINB) bn_bwd_apply_kernel(DView<const T> dy, DView<const T> gate, int has_gate,
+                                                                     float gscale, DView<const T> x, const uint8_t* mask,
+                                                                     int mask_mode, const float* mean, const float* invstd,
+                                                                     const float* gamma, const float* sums, float inv_cnt,
+                                                                     DView<const T> addend, int has_add, DView<T> out,
+                                                                     DView<T> out2, int has_out2, const uint8_t* mask2,
+                                                                     int mask2_mode, float scale2, const float* gbeta,
+                                                                     unsigned total, unsigned stride) {
     unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     if (idx >= total) return;
     const int C = x.C;
     const unsigned CV = (unsigned)C / VEC;
     const int c = (int)(idx % CV) * VEC;
-    // dv = k1 * (gg - m_g - xh * m_gx),  xh = v * is - mu*is
-    float k1[VEC], mg[VEC], mgx[VEC], is[VEC], mis[VEC];
+    // dv = k1 * (g - m_g - xhat * m_gx),  xhat = v*is - mu*is   ==   k1*g + ca*v + cb
+    float k1[VEC], ca[VEC], cb[VEC];
     {
-        float mu[VEC], ga[VEC], sg[VEC], sgx[VEC];
+        float mu[VEC], is[VEC], ga[VEC], sg[VEC], sgx[VEC];
         ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(sums + c, sg); ld8f(sums + C + c, sgx);
-
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             k1[i] = ga[i] * is[i];
-            mg[i] = sg[i] * inv_cnt;
-            mgx[i] = sgx[i] * inv_cnt;
-            mis[i] = mu[i] * is[i];
+            const float mg = sg[i] * inv_cnt, mgx = sgx[i] * inv_cnt;
+            ca[i] = -k1[i] * is[i] * mgx;
+            cb[i] = k1[i] * (mu[i] * is[i] * mgx - mg);
         }
     }
-#pragma unroll 2
-    for (; idx < total; idx += stride) {
-        const Pos p = decode_pixel(out, out.fCV8.div(idx), c);
-        float o[VEC], o2[VEC];
+    constexpr int U = BWD_U;
+    for (; idx < total; idx += U * stride) {
+        Pos p[U];
+        bool valid[U], in[U];
+        Raw8<T> gR[U], tR[U], xR[U], aR[U];
+        uint2 mR[U], m2R[U];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) o[i] = o2[i] = 0.f;
-        if (p.interior) {
-            float g[VEC], gt[VEC], xv[VEC], mk[VEC], ad[VEC];
-            ld8v<T>(dy.p + vaddr(dy, p.b, p.h, p.w, p.c), g);
-            if (has_gate == 1) ld8v<T>(gate.p + vaddr(gate, p.b, p.h, p.w, p.c), gt);
-            ld8v<T>(x.p + vaddr(x, p.b, p.h, p.w, p.c), xv);
-            const int bc = p.b * C + p.c, el = ((p.b * x.H + p.h) * x.W + p.w) * C + p.c;
-            ldmask8(mask, mask_mode, bc, el, mk);
-            if (has_add) ld8v<T>(addend.p + vaddr(addend, p.b, p.h, p.w, p.c), ad);
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                float gg = gscale * g[i];
-                if (has_gate == 1 && !(gt[i] > 0.f)) gg = 0.f;
-                const float xh = (xv[i] * mk[i]) * is[i] - mis[i];
-                const float dv = k1[i] * (gg - mg[i] - xh * mgx[i]);
-                o[i] = dv * mk[i] + (has_add ? ad[i] : 0.f);
+        for (int u = 0; u < U; ++u) {
+            const unsigned id = idx + u * stride;
+            valid[u] = id < total;
+            in[u] = false;
+            if (valid[u]) {
+                p[u] = decode_pixel(out, out.fCV8.div(id), c);
+                in[u] = p[u].interior;
             }
-            if (has_out2) {
-                float mk2[VEC];
-                ldmask8(mask2, mask2_mode, bc, el, mk2);
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) o2[i] = scale2 * g[i] * mk2[i];
+            if (in[u]) {
+                const Pos& q = p[u];
+                gR[u].load(dy.p + vaddr(dy, q.b, q.h, q.w, q.c));
+                if (has_gate == 1) tR[u].load(gate.p + vaddr(gate, q.b, q.h, q.w, q.c));
+                xR[u].load(x.p + vaddr(x, q.b, q.h, q.w, q.c));
+                if (has_add) aR[u].load(addend.p + vaddr(addend, q.b, q.h, q.w, q.c));
+                const int bc = q.b * C + q.c, el = ((q.b * x.H + q.h) * x.W + q.w) * C + q.c;
+                if (mask_mode != MOPOE_MASK_NONE)
+                    mR[u] = *reinterpret_cast<const uint2*>(mask + (mask_mode == MOPOE_MASK_BC ? bc : el));
+                if (has_out2 && mask2_mode != MOPOE_MASK_NONE)
+                    m2R[u] = *reinterpret_cast<const uint2*>(mask2 + (mask2_mode == MOPOE_MASK_BC ? bc : el));
             }
         }
-        st8v<T>(out.p + vaddr(out, p.b, p.h, p.w, p.c), o);
-        if (has_out2) st8v<T>(out2.p + vaddr(out2, p.b, p.h, p.w, p.c), o2);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!valid[u]) continue;
+            const Pos& q = p[u];
+            float o[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+            if (in[u]) {
+                float g[VEC], v[VEC];
+                gR[u].unpack(g);
+                xR[u].unpack(v);
+                if (has_out2) {
+                    float o2[VEC], mk2[VEC];
+                    if (mask2_mode != MOPOE_MASK_NONE) {
+                        mask8(m2R[u], mk2);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) mk2[i] = 1.f;
+                    }
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) o2[i] = scale2 * g[i] * mk2[i];
+                    st8v<T>(out2.p + vaddr(out2, q.b, q.h, q.w, q.c), o2);
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) g[i] *= gscale;
+                if (has_gate == 1) {
+                    float gt[VEC];
+                    tR[u].unpack(gt);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i)
+                        if (!(gt[i] > 0.f)) g[i] = 0.f;
+                }
+                if (mask_mode != MOPOE_MASK_NONE) {
+                    float mk[VEC];
+                    mask8(mR[u], mk);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) o[i] = fmaf(k1[i], g[i], fmaf(ca[i], v[i] * mk[i], cb[i])) * mk[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) o[i] = fmaf(k1[i], g[i], fmaf(ca[i], v[i], cb[i]));
+                }
+                if (has_add) {
+                    float ad[VEC];
+                    aR[u].unpack(ad);
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) o[i] += ad[i];
+                }
+            } else if (has_out2) {
+                st8v<T>(out2.p + vaddr(out2, q.b, q.h, q.w, q.c), o);      // zero border of the second output
+            }
+            st8v<T>(out.p + vaddr(out, q.b, q.h, q.w, q.c), o);
+        }
     }
 }
 

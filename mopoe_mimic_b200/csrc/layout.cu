@@ -114,7 +114,13 @@ __global__ void __launch_bounds__(256) wgrad_finish_kernel(const float* __restri
         float v = 0.f;
         if (b0 + bi < B) {
             const float* p = part + ((long long)a * T + t) * bpad + b0 + bi;
-            for (int z = 0; z < Z; ++z) v += p[z * zstride];          // fixed order: deterministic
+            int z = 0;
+            for (; z + 4 <= Z; z += 4) {                               // 4 loads in flight; summation order stays fixed
+                const float v0 = __ldcs(p + z * zstride), v1 = __ldcs(p + (z + 1) * zstride);
+                const float v2 = __ldcs(p + (z + 2) * zstride), v3 = __ldcs(p + (z + 3) * zstride);
+                v += v0; v += v1; v += v2; v += v3;
+            }
+            for (; z < Z; ++z) v += __ldcs(p + z * zstride);
         }
         s[bi][t] = v;
     }
