@@ -711,6 +711,157 @@ __global__ void __launch_bounds__(EW_THREADS, BWD_MINB) bn_bwd_apply_kernel(DVie
     }
 }
 
+// Variant B of the same pass (MOPOE_EW_ONESHOT=0 falls back to the kernel above): no grid-stride loop — one channel
+// octet per thread, the per-channel coefficients live in shared memory (computed once per block), the optional operands
+// are template flags and the arithmetic runs pair by pair straight from the packed registers.  A thread then carries
+// ~40 registers instead of ~110: occupancy, not per-thread unrolling, is what feeds HBM here (measured).
+template <typename T>
+__device__ __forceinline__ float2 pair_of(const Raw8<T>& r, int i);
+template <>
+__device__ __forceinline__ float2 pair_of<bf16>(const Raw8<bf16>& r, int i) {
+    const uint32_t w = i == 0 ? r.v.x : (i == 1 ? r.v.y : (i == 2 ? r.v.z : r.v.w));
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <>
+__device__ __forceinline__ float2 pair_of<float>(const Raw8<float>& r, int i) {
+    return i == 0 ? make_float2(r.a.x, r.a.y) : (i == 1 ? make_float2(r.a.z, r.a.w) : (i == 2 ? make_float2(r.b.x, r.b.y) : make_float2(r.b.z, r.b.w)));
+}
+__device__ __forceinline__ float2 mask_pair(const uint2& t, int i) {
+    const uint32_t w = (i < 2 ? t.x : t.y) >> (16 * (i & 1));
+    return make_float2((w & 0xffu) ? 2.f : 0.f, (w & 0xff00u) ? 2.f : 0.f);
+}
+template <typename T>
+__device__ __forceinline__ void store_pairs(T* p, const float2 (&o)[4]);
+template <>
+__device__ __forceinline__ void store_pairs<bf16>(bf16* p, const float2 (&o)[4]) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[i].x, o[i].y);
+    *reinterpret_cast<uint4*>(p) = t;
+}
+template <>
+__device__ __forceinline__ void store_pairs<float>(float* p, const float2 (&o)[4]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+    reinterpret_cast<float4*>(p)[1] = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+}
+
+template <typename T, bool GATE, bool ADD, bool OUT2>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_oneshot_kernel(
+    DView<const T> dy, DView<const T> gate, float gscale, DView<const T> x, const uint8_t* mask, int mask_mode,
+    const float* mean, const float* invstd, const float* gamma, const float* sums, float inv_cnt, DView<const T> addend,
+    DView<T> out, DView<T> out2, const uint8_t* mask2, int mask2_mode, float scale2, unsigned total) {
+    extern __shared__ float coef[];          // k1[C] | ca[C] | cb[C]
+    const int C = x.C;
+    const unsigned id = blockIdx.x * EW_THREADS + threadIdx.x;
+    const bool valid = id < total;
+    unsigned pix, cv;
+    out.fCV8.divmod(valid ? id : 0u, pix, cv);
+    const Pos q = decode_pixel(out, pix, (int)cv * VEC);
+    const bool in = valid && q.interior;
+    // the operand loads go out FIRST: they are in flight while the block computes its coefficient table
+    Raw8<T> gR, tR, xR, aR;
+    uint2 mR = make_uint2(0, 0), m2R = make_uint2(0, 0);
+    const bool masked = mask_mode != MOPOE_MASK_NONE, masked2 = OUT2 && mask2_mode != MOPOE_MASK_NONE;
+    if (in) {
+        gR.load(dy.p + vaddr(dy, q.b, q.h, q.w, q.c));
+        if (GATE) tR.load(gate.p + vaddr(gate, q.b, q.h, q.w, q.c));
+        xR.load(x.p + vaddr(x, q.b, q.h, q.w, q.c));
+        if (ADD) aR.load(addend.p + vaddr(addend, q.b, q.h, q.w, q.c));
+        const int bc = q.b * C + q.c, el = ((q.b * x.H + q.h) * x.W + q.w) * C + q.c;
+        if (masked) mR = *reinterpret_cast<const uint2*>(mask + (mask_mode == MOPOE_MASK_BC ? bc : el));
+        if (masked2) m2R = *reinterpret_cast<const uint2*>(mask2 + (mask2_mode == MOPOE_MASK_BC ? bc : el));
+    }
+    for (int ch = threadIdx.x; ch < C; ch += EW_THREADS) {
+        const float is = invstd[ch], k1 = gamma[ch] * is;
+        const float mg = sums[ch] * inv_cnt, mgx = sums[C + ch] * inv_cnt;
+        coef[ch] = k1;
+        coef[C + ch] = -k1 * is * mgx;
+        coef[2 * C + ch] = k1 * (mean[ch] * is * mgx - mg);
+    }
+    __syncthreads();
+    if (!valid) return;
+    T* const op = out.p + vaddr(out, q.b, q.h, q.w, q.c);
+    float2 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = make_float2(0.f, 0.f);
+    if (!in) {                                               // zero border of the output(s)
+        store_pairs<T>(op, o);
+        if (OUT2) store_pairs<T>(out2.p + vaddr(out2, q.b, q.h, q.w, q.c), o);
+        return;
+    }
+    if (OUT2) {
+        float2 o2[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 g = pair_of<T>(gR, i);
+            const float2 mk2 = masked2 ? mask_pair(m2R, i) : make_float2(1.f, 1.f);
+            o2[i] = make_float2(scale2 * g.x * mk2.x, scale2 * g.y * mk2.y);
+        }
+        store_pairs<T>(out2.p + vaddr(out2, q.b, q.h, q.w, q.c), o2);
+    }
+    const float* ck = coef + q.c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 g = pair_of<T>(gR, i);
+        const float2 v = pair_of<T>(xR, i);
+        const float2 k1 = *reinterpret_cast<const float2*>(ck + 2 * i);
+        const float2 ca = *reinterpret_cast<const float2*>(ck + C + 2 * i);
+        const float2 cb = *reinterpret_cast<const float2*>(ck + 2 * C + 2 * i);
+        g.x *= gscale;
+        g.y *= gscale;
+        if (GATE) {
+            const float2 gt = pair_of<T>(tR, i);
+            if (!(gt.x > 0.f)) g.x = 0.f;
+            if (!(gt.y > 0.f)) g.y = 0.f;
+        }
+        float2 r;
+        if (masked) {
+            const float2 mk = mask_pair(mR, i);
+            r.x = fmaf(k1.x, g.x, fmaf(ca.x, v.x * mk.x, cb.x)) * mk.x;
+            r.y = fmaf(k1.y, g.y, fmaf(ca.y, v.y * mk.y, cb.y)) * mk.y;
+        } else {
+            r.x = fmaf(k1.x, g.x, fmaf(ca.x, v.x, cb.x));
+            r.y = fmaf(k1.y, g.y, fmaf(ca.y, v.y, cb.y));
+        }
+        if (ADD) {
+            const float2 ad = pair_of<T>(aR, i);
+            r.x += ad.x;
+            r.y += ad.y;
+        }
+        o[i] = r;
+    }
+    store_pairs<T>(op, o);
+}
+template <typename T>
+static void launch_oneshot(long long total, cudaStream_t st, DView<const T> dy, DView<const T> gate, bool has_gate, float gscale,
+                           DView<const T> x, const uint8_t* mask, int mask_mode, const float* mean, const float* invstd,
+                           const float* gamma, const float* sums, float inv_cnt, DView<const T> addend, bool has_add,
+                           DView<T> out, DView<T> out2, bool has_out2, const uint8_t* mask2, int mask2_mode, float scale2) {
+    const size_t sm = (size_t)3 * x.C * sizeof(float);
+    const unsigned grid = (unsigned)ceil_div64(total, EW_THREADS);
+#define MOPOE_OS(G, A, O)                                                                                                        \
+    bn_bwd_apply_oneshot_kernel<T, G, A, O><<<grid, EW_THREADS, sm, st>>>(dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, \
+                                                                          sums, inv_cnt, addend, out, out2, mask2, mask2_mode,     \
+                                                                          scale2, (unsigned)total)
+    if (has_out2) {
+        if (has_gate) { if (has_add) MOPOE_OS(true, true, true); else MOPOE_OS(true, false, true); }
+        else { if (has_add) MOPOE_OS(false, true, true); else MOPOE_OS(false, false, true); }
+    } else {
+        if (has_gate) { if (has_add) MOPOE_OS(true, true, false); else MOPOE_OS(true, false, false); }
+        else { if (has_add) MOPOE_OS(false, true, false); else MOPOE_OS(false, false, false); }
+    }
+#undef MOPOE_OS
+}
+static int ew_oneshot() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_EW_ONESHOT");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const mopoe_view_t* x,
                              const uint8_t* mask, int mask_mode, const float* mean, const float* invstd,
                              const float* gamma, const float* sums, const mopoe_view_t* addend, const mopoe_view_t* out,
@@ -732,6 +883,13 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
         unsigned grid, stride;
         const long long total = storage_threads(ov);
         if (apply_grid(total, x->C, grid, stride)) return 1;
+        const int os = ew_oneshot();
+        if (os) {
+            launch_oneshot<T>(total, (cudaStream_t)stream, make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv,
+                              gate != nullptr, gscale, xv, mask, mask_mode, mean, invstd, gamma, sums, inv_cnt,
+                              addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,
+                              out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2);
+        } else
         bn_bwd_apply_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(
             make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate ? 1 : 0, gscale, xv, mask, mask_mode,
             mean, invstd, gamma, sums, inv_cnt, addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,
