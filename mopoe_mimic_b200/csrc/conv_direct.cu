@@ -40,6 +40,42 @@ __device__ __forceinline__ void st8<bf16>(bf16* p, const float (&o)[8]) {
     *reinterpret_cast<uint4*>(p) = t;
 }
 
+// The 9 taps of a stride-2, pad-1, 3x3 window around source pixel (2*oy, 2*ox): rows 2oy-1 .. 2oy+1, cols 2ox-1 .. 2ox+1.
+// With an even source extent only the FIRST row / column can fall outside (oy == 0 / ox == 0), so the whole bounds
+// logic is two predicates and the addressing is three row pointers with immediate offsets — the per-tap 64-bit index
+// math of the naive form was 2/3 of this kernel family's instruction stream (ncu: 250 integer ops per 72 FMAs).
+__device__ __forceinline__ void load_taps(const float* __restrict__ img, int SW, int oy, int ox, float (&t)[9]) {
+    const float* pc = img + (2 * oy) * SW + 2 * ox;
+    const float* pu = pc - SW;
+    const float* pd = pc + SW;
+    const bool top = oy > 0, left = ox > 0;
+    t[0] = (top && left) ? __ldg(pu - 1) : 0.f;
+    t[1] = top ? __ldg(pu) : 0.f;
+    t[2] = top ? __ldg(pu + 1) : 0.f;
+    t[3] = left ? __ldg(pc - 1) : 0.f;
+    t[4] = __ldg(pc);
+    t[5] = __ldg(pc + 1);
+    t[6] = left ? __ldg(pd - 1) : 0.f;
+    t[7] = __ldg(pd);
+    t[8] = __ldg(pd + 1);
+}
+
+// o[i] += sum_t tap[t] * w[t][i] with the packed fp32 FMA of sm_100 (FFMA2: two IEEE fmas per issue slot — same bits
+// as scalar fmaf, half the instructions; these kernels are issue-bound)
+__device__ __forceinline__ void fma_taps(const float (&tap)[9], const float (&w)[9][8], float (&o)[8]) {
+    float2 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float2(o[2 * j], o[2 * j + 1]);
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const float2 tv = make_float2(tap[t], tap[t]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = __ffma2_rn(tv, make_float2(w[t][2 * j], w[t][2 * j + 1]), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = acc[j].x; o[2 * j + 1] = acc[j].y; }
+}
+
 // stage w[C][9] -> smem [9][C]
 __device__ __forceinline__ void stage_filter(const float* __restrict__ w, float* ws, int C) {
     for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < 9 * C; i += blockDim.x * blockDim.y) {
@@ -57,8 +93,29 @@ __global__ void __launch_bounds__(256) conv3x3s2_c1_fwd_kernel(const float* __re
     stage_filter(w, wsm, out.C);                      // once per CTA; the CTA then strides over many pixels
     const int C = out.C;
     const unsigned CG = (unsigned)C / CV8;
-    for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < (unsigned)total; idx += gridDim.x * 256u) {
+    // the 9 x 8 filter taps of this thread's channel octet live in REGISTERS: when C/8 divides the grid stride (every
+    // power-of-two width) the octet never changes, so the inner loop is 9 broadcast loads + 72 FMAs + one 16-byte store
+    // instead of 18 shared-memory vector loads per pixel (which bounded the kernel at ~1 TB/s of output)
+    float wr[9][CV8];
+    int cprev = -1;
+    // each CTA owns a CONTIGUOUS run of pixels (not a grid-stride comb): successive iterations walk along image rows, so
+    // the 3x3 tap loads of neighbouring pixels hit L1 (a comb jumps ~9 images per iteration: 36 % L1 hits, 7 long-
+    // scoreboard stalls per issue in ncu)
+    const unsigned per_cta = (unsigned)(((total + gridDim.x - 1) / gridDim.x + 255) / 256) * 256u;
+    const unsigned cta_begin = blockIdx.x * per_cta;
+    const unsigned cta_end = (unsigned)min((long long)cta_begin + per_cta, total);
+    for (unsigned idx = cta_begin + threadIdx.x; idx < cta_end; idx += 256u) {
         const int c = (int)(idx % CG) * CV8;
+        if (c != cprev) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wsm + t * C + c);
+                const float4 w1 = *reinterpret_cast<const float4*>(wsm + t * C + c + 4);
+                wr[t][0] = w0.x; wr[t][1] = w0.y; wr[t][2] = w0.z; wr[t][3] = w0.w;
+                wr[t][4] = w1.x; wr[t][5] = w1.y; wr[t][6] = w1.z; wr[t][7] = w1.w;
+            }
+            cprev = c;
+        }
         unsigned pos = out.fCV8.div(idx), ws, hs, q, bb;
         out.fWs.divmod(pos, q, ws);
         out.fHs.divmod(q, bb, hs);
@@ -67,22 +124,9 @@ __global__ void __launch_bounds__(256) conv3x3s2_c1_fwd_kernel(const float* __re
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = 0.f;
         if (oy >= 0 && oy < out.H && ox >= 0 && ox < out.W) {
-            const float* xb = x + (long long)b * H * W;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int iy = 2 * oy - 1 + ky;
-                if (iy < 0 || iy >= H) continue;
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = 2 * ox - 1 + kx;
-                    if (ix < 0 || ix >= W) continue;
-                    const float xv = __ldg(xb + iy * W + ix);
-                    const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c + 4);
-                    o[0] += xv * w0.x; o[1] += xv * w0.y; o[2] += xv * w0.z; o[3] += xv * w0.w;
-                    o[4] += xv * w1.x; o[5] += xv * w1.y; o[6] += xv * w1.z; o[7] += xv * w1.w;
-                }
-            }
+            float xv[9];
+            load_taps(x + (long long)b * H * W, W, oy, ox, xv);
+            fma_taps(xv, wr, o);
         }
         st8<T>(out.p + (long long)b * out.sB + (long long)oy * out.sH + (long long)ox * out.sW + c, o);
     }
@@ -103,7 +147,7 @@ extern "C" int mopoe_conv3x3s2_c1_fwd(const float* x, const float* w, int B, int
 // acc[c, tap] = sum_rows v[row, c] * s[row, tap]   where v is a channel vector (dy or x) and s the 9 scalar taps
 // block = (16 channel-octet lanes, 16 row lanes); grid = (ceil(C/128), nchunk); ws layout [chunk][9][C]
 template <typename T, bool FIRST>
-__global__ void __launch_bounds__(256) tap_grad_kernel(DView<const T> v, const float* __restrict__ s, int SH, int SW,
+__global__ void __launch_bounds__(256, 2) tap_grad_kernel(DView<const T> v, const float* __restrict__ s, int SH, int SW,
                                                        double* __restrict__ ws, int nchunk) {
     // FIRST: v = dy [B,OH,OW,C], s = image x [B,SH,SW], tap (ky,kx) reads s[2*oy-1+ky, 2*ox-1+kx]
     // else : v = x  [B,H,W,C],   s = dout [B,SH=2H,SW=2W],   tap (ky,kx) reads s[2*t-1+ky, 2*s-1+kx]  (same form)
@@ -111,32 +155,49 @@ __global__ void __launch_bounds__(256) tap_grad_kernel(DView<const T> v, const f
     const int c = (blockIdx.x * 16 + tx) * CV8;
     const bool cvalid = c < v.C;
     const unsigned rows = (unsigned)v.B * v.H * v.W;
-    const unsigned gstride = (unsigned)nchunk * 16;      // interleaved 16-row groups (compact streaming window)
+    // block y owns a CONTIGUOUS run of rows (16-row groups walk along image rows: the scalar taps hit L1)
+    const unsigned rpc = ((rows + nchunk - 1) / nchunk + 15) / 16 * 16;
+    const unsigned row_begin = blockIdx.y * rpc, row_end = min(rows, row_begin + rpc);
+    const unsigned gstride = 16;
     float acc[9][CV8];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
         for (int i = 0; i < CV8; ++i) acc[t][i] = 0.f;
     if (cvalid) {
-        for (unsigned r = blockIdx.y * 16 + ty; r < rows; r += gstride) {
-            int px = (int)(r % (unsigned)v.W);
-            unsigned t2 = r / (unsigned)v.W;
-            int py = (int)(t2 % (unsigned)v.H);
-            int b = (int)(t2 / (unsigned)v.H);
-            float g[CV8];
-            ld8<T>(v.p + (long long)b * v.sB + (long long)py * v.sH + (long long)px * v.sW + c, g);
-            const float* sb = s + (long long)b * SH * SW;
+        constexpr int U = 2;                             // rows in flight per thread: the pass is latency-bound
+        for (unsigned r0 = row_begin + ty; r0 < row_end; r0 += U * gstride) {
+            float g[U][CV8], sv[U][9];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                int iy = 2 * py - 1 + ky;
+            for (int u = 0; u < U; ++u) {
+                const unsigned r = r0 + u * gstride;
+                const bool ok = r < row_end;
+                const unsigned rr = ok ? r : 0u;
+                int px = (int)(rr % (unsigned)v.W);
+                unsigned t2 = rr / (unsigned)v.W;
+                int py = (int)(t2 % (unsigned)v.H);
+                int b = (int)(t2 / (unsigned)v.H);
+                if (ok) {
+                    ld8<T>(v.p + (long long)b * v.sB + (long long)py * v.sH + (long long)px * v.sW + c, g[u]);
+                } else {
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    int ix = 2 * px - 1 + kx;
-                    float sv = (iy >= 0 && iy < SH && ix >= 0 && ix < SW) ? __ldg(sb + (long long)iy * SW + ix) : 0.f;
-#pragma unroll
-                    for (int i = 0; i < CV8; ++i) acc[ky * 3 + kx][i] += g[i] * sv;
+                    for (int i = 0; i < CV8; ++i) g[u][i] = 0.f;
                 }
+                load_taps(s + (long long)b * SH * SW, SW, py, px, sv[u]);      // (row 0 when !ok: g is zero there)
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const float2 tv = make_float2(sv[u][t], sv[u][t]);
+#pragma unroll
+                    for (int j = 0; j < CV8 / 2; ++j) {
+                        const float2 r = __ffma2_rn(make_float2(g[u][2 * j], g[u][2 * j + 1]), tv,
+                                                    make_float2(acc[t][2 * j], acc[t][2 * j + 1]));
+                        acc[t][2 * j] = r.x;
+                        acc[t][2 * j + 1] = r.y;
+                    }
+                }
         }
     }
     // rows per thread <= rpc/16 (a few hundred): fp32 strip sums, combined across the 16 row lanes in fp64
@@ -280,8 +341,26 @@ __global__ void __launch_bounds__(256) deconv3x3s2_c1_dx_kernel(const float* __r
     const int C = dx.C;
     const unsigned CG = (unsigned)C / CV8;
     const int OH = 2 * dx.H, OW = 2 * dx.W;
-    for (unsigned idx = blockIdx.x * 256u + threadIdx.x; idx < (unsigned)total; idx += gridDim.x * 256u) {
+    float wr[9][CV8];                                  // register-resident taps (see conv3x3s2_c1_fwd_kernel)
+    int cprev = -1;
+    // each CTA owns a CONTIGUOUS run of pixels (not a grid-stride comb): successive iterations walk along image rows, so
+    // the 3x3 tap loads of neighbouring pixels hit L1 (a comb jumps ~9 images per iteration: 36 % L1 hits, 7 long-
+    // scoreboard stalls per issue in ncu)
+    const unsigned per_cta = (unsigned)(((total + gridDim.x - 1) / gridDim.x + 255) / 256) * 256u;
+    const unsigned cta_begin = blockIdx.x * per_cta;
+    const unsigned cta_end = (unsigned)min((long long)cta_begin + per_cta, total);
+    for (unsigned idx = cta_begin + threadIdx.x; idx < cta_end; idx += 256u) {
         const int c = (int)(idx % CG) * CV8;
+        if (c != cprev) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wsm + t * C + c);
+                const float4 w1 = *reinterpret_cast<const float4*>(wsm + t * C + c + 4);
+                wr[t][0] = w0.x; wr[t][1] = w0.y; wr[t][2] = w0.z; wr[t][3] = w0.w;
+                wr[t][4] = w1.x; wr[t][5] = w1.y; wr[t][6] = w1.z; wr[t][7] = w1.w;
+            }
+            cprev = c;
+        }
         unsigned pos = dx.fCV8.div(idx), ws, hs, q, bb;
         dx.fWs.divmod(pos, q, ws);
         dx.fHs.divmod(q, bb, hs);
@@ -290,22 +369,9 @@ __global__ void __launch_bounds__(256) deconv3x3s2_c1_dx_kernel(const float* __r
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] = 0.f;
         if (t >= 0 && t < dx.H && s >= 0 && s < dx.W) {
-            const float* db = dout + (long long)b * OH * OW;
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int oy = 2 * t - 1 + ky;
-                if (oy < 0 || oy >= OH) continue;
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ox = 2 * s - 1 + kx;
-                    if (ox < 0 || ox >= OW) continue;
-                    const float g = __ldg(db + oy * OW + ox);
-                    const float4 w0 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wsm + (ky * 3 + kx) * C + c + 4);
-                    o[0] += g * w0.x; o[1] += g * w0.y; o[2] += g * w0.z; o[3] += g * w0.w;
-                    o[4] += g * w1.x; o[5] += g * w1.y; o[6] += g * w1.z; o[7] += g * w1.w;
-                }
-            }
+            float gv[9];
+            load_taps(dout + (long long)b * OH * OW, OW, t, s, gv);
+            fma_taps(gv, wr, o);
         }
         st8<T>(dx.p + (long long)b * dx.sB + (long long)t * dx.sH + (long long)s * dx.sW + c, o);
     }
