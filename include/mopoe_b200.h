@@ -243,6 +243,19 @@ int mopoe_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, flo
 int mopoe_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* coef,
                         float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* All weight re-layouts of a step in ONE launch.  jobs_dev: DEVICE array of njobs descriptors (same meaning as the
+ * arguments of mopoe_pack_weight_tiled; form 1 fills dst[0..3] / dst[0..1], the others dst[0]); tile0 = index of the
+ * job's first tile in the launch grid and nx = its tile-grid width, both from mopoe_pack_job_tiles (which returns the
+ * job's tile count).  total_tiles = sum of the tile counts.  Replaces nothing in the reference (torch.nn consumes its
+ * fp32 weights in place); it exists because the tcgen05 kernels want K-major bf16 operands. */
+typedef struct {
+    const float* W;
+    void*   dst[4];
+    int32_t A, B, KH, KW, form, bpad, tile0, nx;
+} mopoe_pack_job_t;
+int mopoe_pack_job_tiles(int A, int B, int KH, int KW, int form, int bpad, int* nx);
+int mopoe_pack_weights_batched(const mopoe_pack_job_t* jobs_dev, int njobs, int total_tiles, int dst_dtype, void* stream);
+
 /* ---- data-parallel exchange (SURVEY §8 a25 / e): gradient reduce-scatter + Adam + parameter all-gather as ONE kernel
  * over NVLink peer memory.  Replaces DistributedDataParallel's all-reduce followed by optimizer.step()
  * (main_mimic.py:44-48, utils/utils.py:179-185, run_epochs.py:130-131).

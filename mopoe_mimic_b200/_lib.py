@@ -40,6 +40,11 @@ class FusionCfg(C.Structure):
                 ('mem_cnt', C.c_int32 * 16), ('mem_idx', (C.c_int32 * 4) * 16), ('mem_end', (C.c_int32 * 4) * 16), ('norm', C.c_float), ('_pad', C.c_float)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [('W', C.c_void_p), ('dst', C.c_void_p * 4), ('A', C.c_int32), ('B', C.c_int32), ('KH', C.c_int32),
+                ('KW', C.c_int32), ('form', C.c_int32), ('bpad', C.c_int32), ('tile0', C.c_int32), ('nx', C.c_int32)]
+
+
 class DpPeers(C.Structure):
     _fields_ = [('grad', C.c_void_p * 16), ('param', C.c_void_p * 16), ('flags', C.c_void_p * 16)]
 
@@ -83,6 +88,8 @@ SIGNATURES = {
     'mopoe_laplace_logprob_bwd': (_I, [_P, _P, _L, _F, _P, _P, _P]),
     'mopoe_categorical_logprob_sum': (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P]),
     'mopoe_categorical_logprob_bwd': (_I, [_P, _P, _L, _I, _P, _P, _P]),
+    'mopoe_pack_job_tiles': (_I, [_I, _I, _I, _I, _I, _I, C.POINTER(C.c_int)]),
+    'mopoe_pack_weights_batched': (_I, [_P, _I, _I, _I, _P]),
     'mopoe_dp_adam_exchange': (_I, [C.POINTER(DpPeers), _P, _P, _P, _P, _L, _I, _I, _P, _P, _F, _F, _F, _F, _P]),
     'mopoe_adam_flat': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P]),
 }

@@ -20,12 +20,11 @@ __device__ __forceinline__ void put(TD* p, float v) {
     if constexpr (sizeof(TD) == 4) *p = v; else *p = __float2bfloat16_rn(v);
 }
 
-// conv-form: grid (ceil(bpad/64), A)
+// conv-form: tile grid (ceil(bpad/64), A)
 template <typename TD>
-__global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict__ W, int A, int B, int T, int bpad,
-                                                        TD* __restrict__ dst) {
-    __shared__ float s[LT][MAXT + 1];
-    const int a = blockIdx.y, b0 = blockIdx.x * LT;
+__device__ __forceinline__ void pack_conv_tile(float (&s)[LT][MAXT + 1], int bx, int by, const float* __restrict__ W, int A,
+                                               int B, int T, int bpad, TD* __restrict__ dst) {
+    const int a = by, b0 = bx * LT;
     const float* src = W + ((long long)a * B + b0) * T;
     const int nb = min(LT, B - b0);                        // may be <= 0 for the zero-padded tail tile
     for (int i = threadIdx.x; i < LT * T; i += 256) {
@@ -38,17 +37,22 @@ __global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict_
         if (b0 + bi < bpad) put(dst + ((long long)a * T + t) * bpad + b0 + bi, s[bi][t]);
     }
 }
+template <typename TD>
+__global__ void __launch_bounds__(256) pack_conv_kernel(const float* __restrict__ W, int A, int B, int T, int bpad,
+                                                        TD* __restrict__ dst) {
+    __shared__ float s[LT][MAXT + 1];
+    pack_conv_tile<TD>(s, blockIdx.x, blockIdx.y, W, A, B, T, bpad, dst);
+}
 
 struct PackDst {
     void* p[4];
 };
-// phase-form (form 1) / full-form (form 2) / transposed 1x1 (form 2 with T = 1): grid (ceil(A/64), B)
+// phase-form (form 1) / full-form (form 2) / transposed 1x1 (form 2 with T = 1): tile grid (ceil(A/64), B)
 template <typename TD>
-__global__ void __launch_bounds__(256) pack_inner_a_kernel(const float* __restrict__ W, int A, int B, int KH, int KW, int form,
-                                                           PackDst dst) {
-    __shared__ float s[LT][MAXT + 1];
+__device__ __forceinline__ void pack_inner_a_tile(float (&s)[LT][MAXT + 1], int bx, int by, const float* __restrict__ W, int A,
+                                                  int B, int KH, int KW, int form, const PackDst& dst) {
     const int T = KH * KW;
-    const int b = blockIdx.y, a0 = blockIdx.x * LT;
+    const int b = by, a0 = bx * LT;
     const int na = min(LT, A - a0);
     for (int i = threadIdx.x; i < LT * T; i += 256) {
         const int ai = i / T, t = i - ai * T;
@@ -74,6 +78,78 @@ __global__ void __launch_bounds__(256) pack_inner_a_kernel(const float* __restri
             put(reinterpret_cast<TD*>(dst.p[ph]) + ((long long)b * nslot + slot) * A + a0 + ai, s[ai][t]);
         }
     }
+}
+template <typename TD>
+__global__ void __launch_bounds__(256) pack_inner_a_kernel(const float* __restrict__ W, int A, int B, int KH, int KW, int form,
+                                                           PackDst dst) {
+    __shared__ float s[LT][MAXT + 1];
+    pack_inner_a_tile<TD>(s, blockIdx.x, blockIdx.y, W, A, B, KH, KW, form, dst);
+}
+
+// Every re-layout of a training step in ONE launch: block -> (job, tile) through the jobs' tile prefix (binary search).
+// A step re-packs ~240 weight tensors after the optimizer update; as separate launches they cost ~1.8 ms of launch
+// latency for ~0.9 GB of traffic.
+constexpr int PACK_TPB = 8;      // consecutive tiles per block: one job look-up (a chain of L2 round trips) per 8 tiles
+template <typename TD>
+__global__ void __launch_bounds__(256) pack_batched_kernel(const mopoe_pack_job_t* __restrict__ jobs, int njobs, int total_tiles) {
+    __shared__ float s[LT][MAXT + 1];
+    __shared__ mopoe_pack_job_t sj;
+    __shared__ int s_idx;
+    const int first = (int)blockIdx.x * PACK_TPB;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = njobs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].tile0 <= first) lo = mid; else hi = mid - 1;
+        }
+        s_idx = lo;
+        sj = jobs[lo];
+    }
+    __syncthreads();
+    for (int k = 0; k < PACK_TPB; ++k) {
+        const int tile = first + k;
+        if (tile >= total_tiles) break;
+        // jobs are sorted by tile0: crossing into the next job is a single step
+        const int next0 = s_idx + 1 < njobs ? jobs[s_idx + 1].tile0 : total_tiles;
+        if (tile >= next0) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_idx += 1;
+                sj = jobs[s_idx];
+            }
+            __syncthreads();
+        }
+        const int local = tile - sj.tile0, bx = local % sj.nx, by = local / sj.nx;
+        const int T = sj.KH * sj.KW;
+        if (sj.form == 0 || sj.form == 3) {
+            pack_conv_tile<TD>(s, bx, by, sj.W, sj.A, sj.B, T, sj.bpad, reinterpret_cast<TD*>(sj.dst[0]));
+        } else {
+            PackDst d;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d.p[i] = sj.dst[i];
+            pack_inner_a_tile<TD>(s, bx, by, sj.W, sj.A, sj.B, sj.KH, sj.KW, sj.form == 1 ? 1 : 2, d);
+        }
+        __syncthreads();                 // the tile buffer is reused by the next iteration
+    }
+}
+extern "C" int mopoe_pack_job_tiles(int A, int B, int KH, int KW, int form, int bpad, int* nx) {
+    if (form == 0 || form == 3) {
+        if (bpad < B) bpad = B;
+        *nx = (bpad + LT - 1) / LT;
+        return *nx * A;
+    }
+    *nx = (A + LT - 1) / LT;
+    return *nx * B;
+}
+extern "C" int mopoe_pack_weights_batched(const mopoe_pack_job_t* jobs_dev, int njobs, int total_tiles, int dst_dtype,
+                                          void* stream) {
+    if (njobs <= 0 || total_tiles <= 0) return 0;
+    MOPOE_REQUIRE(jobs_dev != nullptr, "pack_weights_batched: null job table");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_dtype == MOPOE_F32) pack_batched_kernel<float><<<(unsigned)((total_tiles + PACK_TPB - 1) / PACK_TPB), 256, 0, st>>>(jobs_dev, njobs, total_tiles);
+    else pack_batched_kernel<bf16><<<(unsigned)((total_tiles + PACK_TPB - 1) / PACK_TPB), 256, 0, st>>>(jobs_dev, njobs, total_tiles);
+    MOPOE_CHECK_LAUNCH("pack_weights_batched");
+    return 0;
 }
 
 // form: 0 conv (dsts[0]), 1 phase (dsts[0..3] 2-D / dsts[0..1] 1-D), 2 full (dsts[0]), 3 mat = conv with T=1, 4 matT = full with T=1

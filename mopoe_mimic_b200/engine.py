@@ -79,53 +79,98 @@ class Engine:
         # a separate one-warp-per-channel finalize launch (the lone last block serialises 16 channels), so it stays off.
         self.counters = None
         self._packs = {}
+        self._pack_gen, self._packs_stale, self._pack_table = 0, False, None
         import os
         self.batched = os.environ.get('MOPOE_GEMM_BATCHED', '1') != '0'       # phases of a deconv in one launch
         self.persistent = os.environ.get('MOPOE_GEMM_PERSISTENT', '1') != '0'   # persistent kernel for single GEMMs too
         self.profile = None     # list of (start_event, end_event, flops, kind) when bench.py instruments a step
         self.profile_external = False   # True: events become event-record NODES of a CUDA graph being captured
 
-    # ---- packed-weight cache: each re-layout is computed once per optimizer step (forward and backward share it)
+    # ---- packed-weight cache ---------------------------------------------------------------------------------
+    # Every (weight, form) has a persistent SLOT (destination buffers with fixed addresses).  A slot is valid while its
+    # generation matches the engine's and the tensor's torch version is unchanged.  The first step packs slot by slot
+    # as the layers run; from then on begin_step() re-packs ALL known slots in one batched launch (prepack), so the
+    # forward/backward only ever hit the cache.
+    FORMS = {'conv': 0, 'phase': 1, 'full': 2, 'mat': 3, 'matT': 4}
+
+    def _slot_shapes(self, fcode, A, B, KH, KW, bpad):
+        if fcode == 0:
+            return [(A, KH * KW * bpad)]
+        if fcode == 1:
+            return [(B, 4 * A)] * 4 if KH > 1 else [(B, 2 * A)] * 2
+        if fcode == 2:
+            return [(KH * KW * B, A)]
+        assert KH == 1 and KW == 1
+        return [(A, B)] if fcode == 3 else [(B, A)]
+
     def packed(self, Wg, form, bpad=None):
-        """GEMM-operand re-layout of an fp32 master weight (mopoe_pack_weight), cached until the weights change"""
-        key = (Wg.data_ptr(), Wg._version, form, bpad, self.dtype)
-        hit = self._packs.get(key)
-        if hit is None:
-            W = Wg.detach()
-            assert W.dtype == torch.float32 and W.is_contiguous()
+        """GEMM-operand re-layout of an fp32 master weight, cached until the weights change"""
+        skey = (Wg.data_ptr(), form, bpad, self.dtype)
+        slot = self._packs.get(skey)
+        if slot is not None and slot['gen'] == self._pack_gen and slot['version'] == Wg._version:
+            return slot['out']
+        W = Wg.detach()
+        assert W.dtype == torch.float32 and W.is_contiguous()
+        if slot is None:
             A, B = W.shape[0], W.shape[1]
             KH, KW = (1, 1) if W.dim() == 2 else ((1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3]))
-            code = L.dtype_code(self.dtype)
+            fcode = self.FORMS[form]
+            bp = bpad or B
+            dsts = [torch.empty(sh, dtype=self.dtype, device=self.device) for sh in self._slot_shapes(fcode, A, B, KH, KW, bp)]
+            slot = {'W': Wg, 'dsts': dsts, 'out': dsts if fcode == 1 else dsts[0], 'geo': (A, B, KH, KW, fcode, bp),
+                    'arr': (C.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts]), 'gen': -1, 'version': -1}
+            self._packs[skey] = slot
+            self._pack_table = None                      # the batched job table must be rebuilt
+        A, B, KH, KW, fcode, bp = slot['geo']
+        L.call('mopoe_pack_weight_tiled', L.ptr(W), A, B, KH, KW, fcode, bp, slot['arr'], L.dtype_code(self.dtype),
+               L.stream_ptr())
+        slot['gen'], slot['version'] = self._pack_gen, Wg._version
+        return slot['out']
 
-            def run(fcode, shapes):
-                dsts = [torch.empty(sh, dtype=self.dtype, device=self.device) for sh in shapes]
-                arr = (C.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
-                L.call('mopoe_pack_weight_tiled', L.ptr(W), A, B, KH, KW, fcode, bpad or B, arr, code, L.stream_ptr())
-                return dsts
-            if form == 'conv':
-                hit = run(0, [(A, KH * KW * (bpad or B))])[0]
-            elif form == 'phase':
-                hit = run(1, [(B, 4 * A)] * 4 if KH > 1 else [(B, 2 * A)] * 2)
-            elif form == 'full':
-                hit = run(2, [(KH * KW * B, A)])[0]
-            elif form == 'mat':        # [n, k] from a 1x1 kernel / linear weight [n, k, 1(, 1)]
-                assert KH == 1 and KW == 1
-                hit = run(3, [(A, B)])[0]
-            elif form == 'matT':
-                assert KH == 1 and KW == 1
-                hit = run(4, [(B, A)])[0]
-            else:
-                raise ValueError(form)
-            self._packs[key] = hit
-        return hit
+    def prepack(self):
+        """re-pack every known slot in ONE launch (mopoe_pack_weights_batched)"""
+        if not self._packs:
+            return
+        if self._pack_table is None and torch.cuda.is_current_stream_capturing():
+            return                       # (the table upload is not capturable: this step packs slot by slot)
+        if self._pack_table is None:
+            self._build_pack_table()
+        tab, njobs, tiles = self._pack_table
+        L.call('mopoe_pack_weights_batched', L.ptr(tab), njobs, tiles, L.dtype_code(self.dtype), L.stream_ptr())
+        for slot in self._packs.values():
+            slot['gen'], slot['version'] = self._pack_gen, slot['W']._version
+
+    def _build_pack_table(self):
+        """device-resident job table of mopoe_pack_weights_batched (one descriptor per slot, sorted by first tile)"""
+        lib = L.load()
+        jobs = (L.PackJob * len(self._packs))()
+        tile = 0
+        for j, slot in zip(jobs, self._packs.values()):
+            A, B, KH, KW, fcode, bp = slot['geo']
+            nx = C.c_int(0)
+            n = lib.mopoe_pack_job_tiles(A, B, KH, KW, fcode, bp, C.byref(nx))
+            j.W = slot['W'].data_ptr()
+            for i, d in enumerate(slot['dsts']):
+                j.dst[i] = d.data_ptr()
+            j.A, j.B, j.KH, j.KW, j.form, j.bpad, j.tile0, j.nx = A, B, KH, KW, fcode, bp, tile, nx.value
+            tile += n
+        raw = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8)
+        self._pack_table = (raw.to(self.device), len(jobs), tile)
 
     def begin_step(self):
-        """same within-step Philox offsets every step; the device-side step counter makes the draws differ"""
+        """same within-step Philox offsets every step; the device-side step counter makes the draws differ.  Weights that
+        changed behind torch's back (flat Adam) are re-packed here in one launch."""
         self.rng_offset = 0
+        if self._packs and self._packs_stale:
+            self.prepack()
+            self._packs_stale = False
 
     def invalidate_packs(self):
         """call after the parameters changed in place behind torch's back (the flat Adam kernel)"""
-        self._packs.clear()
+        self._pack_gen += 1
+        self._packs_stale = True
+        if self._pack_table is None and self._packs and not torch.cuda.is_current_stream_capturing():
+            self._build_pack_table()
 
     # ---- scratch ------------------------------------------------------------------------------------
     def ws64(self, n):
