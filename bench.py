@@ -298,6 +298,14 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except Exception:
             pass
+        traffic, traffic_note = None, None
+        try:       # dram bytes of the step's largest GEMM launch, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_roofline_traffic.json')))
+            traffic = tj['dram_bytes_read'] + tj['dram_bytes_written']
+            traffic_note = ('ncu dram read+write of ONE launch (%s); algorithmic bytes of that launch %.1f MB'
+                            % (tj['kernel'], tj['algorithmic_bytes'] / 1e6))
+        except Exception:
+            pass
         peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
         peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback'
         gemm_ms = sum(p_[0].elapsed_time(p_[1]) for p_ in prof)
@@ -333,7 +341,8 @@ def main():
                         'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h},
                 'gpu_launches': launches,
                 'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                             'frac': achieved / peak_tf, 'traffic': None, 'peak_source': peak_src, 'timing': timing,
+                             'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src,
+                             'timing': timing,
                              'kernel': 'implicit-GEMM conv family (fprop+dgrad+wgrad), %d launches/step' % len(prof),
                              'gemm_ms_per_step': gemm_ms, 'step_tensor_frac': value / world * cfg['gflop'] / 1e3 / peak_tf,
                              'by_kind': {k: {'ms': v[0], 'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else 0.0, 'launches': v[2]}

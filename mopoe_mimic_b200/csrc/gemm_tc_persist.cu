@@ -1,8 +1,8 @@
 // gemm_tc_persist.cu — PERSISTENT, batched tcgen05 implicit-GEMM (fprop / dgrad family).
 //
 // Same math and operand maps as conv_gemm_tc_kernel (gemm_tc.cu), different schedule:
-//   * grid = min(#tiles, #SMs): every CTA loops over tiles (static round-robin, N-tiles innermost so CTAs
-//     running side by side read the same activation rows out of L2);
+//   * grid = min(#tiles, #SMs): every CTA loops over tiles (static round-robin in (m-tile, problem, n-tile) order, so
+//     CTAs running side by side read the same activation rows out of L2 — across n-tiles AND across phases);
 //   * the accumulator is DOUBLE-BUFFERED in TMEM (2 x BN columns): while the 4 epilogue warps drain tile i
 //     (tcgen05.ld -> +bias -> bf16 -> global), the MMA warp already accumulates tile i+1 — the epilogue and the
 //     pipeline fill/drain no longer sit on the tensor pipe's critical path;
@@ -85,9 +85,12 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int prob = tile / p.tiles_per_prob;
-                const int rem = tile - prob * p.tiles_per_prob;
-                const int mt = rem / p.NT, nt = rem - mt * p.NT;
+                // tile order (m-tile, problem, n-tile): the sub-pixel phases of one pixel block run side by side, so
+                // their (overlapping) activation windows are fetched from DRAM once — problem-major order re-read the
+                // whole input per phase (ncu: 568 MB read for a 151 MB operand)
+                const int nt = tile % p.NT;
+                const int tq = tile / p.NT;
+                const int prob = tq % p.nprob, mt = tq / p.nprob;
                 const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
                 const int n0 = nt * p.BN;
                 const CUtensorMap* ma = &maps.a[prob];
@@ -138,9 +141,9 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
-            const int prob = tile / p.tiles_per_prob;
-            const int rem = tile - prob * p.tiles_per_prob;
-            const int mt = rem / p.NT, nt = rem - mt * p.NT;
+            const int nt = tile % p.NT;
+            const int tq = tile / p.NT;
+            const int prob = tq % p.nprob, mt = tq / p.nprob;
             const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
             const int n0 = nt * p.BN;
             const int m0 = t0 * p.BX + i1, m1 = t1 * p.BY + i2, m2 = t2 * p.NB + i4;
