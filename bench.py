@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
-def cpu_reference(args, steps, warmup):
+def cpu_reference(args, steps, warmup, min_seconds=None):
     """The reference's CPU path: its algorithm restated in oracle/ (pure torch CPU ops, same call sites), full
     step = forward + ELBO + backward + Adam, fp32, all host threads, batch `cpu_batch` (a bounded sample of the
     same workload)."""
@@ -108,6 +108,8 @@ def cpu_reference(args, steps, warmup):
     v = {k: torch.zeros_like(p) for k, p in params.items()}
     times = []
     for it in range(warmup + steps):
+        if min_seconds is not None and it >= warmup + 2 and sum(times) >= min_seconds:
+            break                       # bounded sample: ~min_seconds of timed CPU work, at least 2 steps
         t0 = time.perf_counter()
         out = O.step_with_grads(state, batch, fl, masks, eps, uni_masks=uni)
         with torch.no_grad():
@@ -119,15 +121,15 @@ def cpu_reference(args, steps, warmup):
     sec = sum(times) / len(times)
     return {'value': args.cpu_batch / sec, 'unit': 'samples/s', 'cores': cores, 'kind': 'port',
             'sample': '%d timed steps (after %d warm-up) of batch %d, fp32, torch CPU ops, %.2f s/step'
-                      % (steps, warmup, args.cpu_batch, sec)}, sec
+                      % (len(times), warmup, args.cpu_batch, sec)}, sec
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warmup = max(1, min(args.warmup, 1))
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 2))
     cb, sec = cpu_reference(args, steps, warmup)
     line = {'metric': 'train samples/sec (3-modality MoPoE, 128px)', 'value': cb['value'], 'unit': 'samples/s',
             'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
@@ -348,7 +350,7 @@ def main():
                              'by_kind': {k: {'ms': v[0], 'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else 0.0, 'launches': v[2]}
                                          for k, v in by_kind.items()}}}
         if not args.no_cpu_baseline:
-            cb, _ = cpu_reference(args, 2, 1)
+            cb, _ = cpu_reference(args, 12, 1, min_seconds=10.0)
             line['cpu_baseline'] = cb
         print(json.dumps(line))
     if world > 1:
