@@ -49,6 +49,10 @@ def parse():
     ap.add_argument('--dp-exchange', default='peer', choices=['peer', 'nccl'],
                     help='N>1 gradient exchange: fused reduce-scatter+Adam+all-gather kernel over NVLink peer memory '
                          '(default) or bucketed NCCL all-reduce followed by Adam')
+    ap.add_argument('--lr', type=float, default=1e-5,
+                    help='Adam learning rate.  The reference default (1e-3) makes the reference model itself diverge to '
+                         'inf/NaN on the SECOND step with default init on random inputs (checked with the CPU oracle); '
+                         '1e-5 keeps the synthetic run finite.  Throughput does not depend on it')
     ap.add_argument('--config', default='2', choices=sorted(CONFIGS), help='BASELINE.json configuration (default 2)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-batch', type=int, default=16)
@@ -113,7 +117,7 @@ def cpu_reference(args, steps, warmup, min_seconds=None):
         t0 = time.perf_counter()
         out = O.step_with_grads(state, batch, fl, masks, eps, uni_masks=uni)
         with torch.no_grad():
-            O.adam_step(params, out['grads'], m, v, it + 1)
+            O.adam_step(params, out['grads'], m, v, it + 1, lr=args.lr)
             state.update(out['results']['bn_updates'])
         dt = time.perf_counter() - t0
         if it >= warmup:
@@ -159,7 +163,7 @@ def main():
     cfg = CONFIGS[args.config]
     B = args.batch or cfg['batch']
     fl = P.default_flags(device=dev, batch_size=B, compute_dtype=args.dtype, distributed=world > 1, world_size=world,
-                         **cfg['flags'])
+                         initial_learning_rate=args.lr, **cfg['flags'])
     torch.manual_seed(0)
     exp = P.Experiment(fl)
     from mopoe_mimic_b200.dp import FlatGradAllReduce, PeerExchange
@@ -337,11 +341,13 @@ def main():
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
                 'data': 'synthetic',
                 'config': {'workload': cfg['workload'], 'per_gpu_batch': B, 'global_batch': B * world,
-                           'parallelism': 'dp%d' % world + ('' if world == 1 else (' peer-memory fused exchange' if peer else ' nccl all-reduce')), 'cuda_graph': not args.no_graph, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
+                           'parallelism': 'dp%d' % world + ('' if world == 1 else (' peer-memory fused exchange' if peer else ' nccl all-reduce')), 'cuda_graph': not args.no_graph, 'lr': args.lr, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
                 'clocks': sampler.summary(),
                 'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s',
                         'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h},
                 'gpu_launches': launches,
+                'last_step': {'total_loss': float(stats_host[0]), 'joint_divergence': float(stats_host[1]),
+                              'finite': bool(torch.isfinite(stats_host[:d2h // 4]).all())},
                 'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                              'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src,
                              'timing': timing,
