@@ -168,7 +168,21 @@ def main():
     exp = P.Experiment(fl)
     from mopoe_mimic_b200.dp import FlatGradAllReduce, PeerExchange
     peer = world > 1 and args.dp_exchange == 'peer'
-    exp.set_optimizer(exchange=PeerExchange(dev) if peer else None)     # (broadcasts rank 0's parameters)
+    px = None
+    if peer:
+        # every rank must take the same path: agree on whether the NVLink symmetric-memory plumbing came up
+        ok = torch.ones(1, device=dev)
+        try:
+            px = PeerExchange(dev)
+        except Exception as e:       # noqa: BLE001
+            print('rank %d: peer-memory exchange unavailable (%r)' % (rank, e), file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            peer, px = False, None
+            if rank == 0:
+                print('falling back to the NCCL all-reduce exchange on all ranks', file=sys.stderr)
+    exp.set_optimizer(exchange=px)     # (a PeerExchange broadcasts rank 0's parameters)
     vae = exp.mm_vae
     vae.train()
     if world > 1 and not peer:
