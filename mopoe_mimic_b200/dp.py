@@ -72,6 +72,11 @@ class PeerExchange:
             raise RuntimeError('PeerExchange supports up to 16 ranks on one NVLink domain')
         self.params = self.grads = self.flags = self.state = self.peers = None
         self.grad_scale = 1.0 / self.world
+        # fail HERE (before the model's buffers are moved) if the platform has no symmetric-memory / P2P support
+        probe = symm.empty(64, dtype=torch.float32, device=device)
+        h = symm.rendezvous(probe, group=self.group)
+        if len(h.buffer_ptrs) != self.world or not all(h.buffer_ptrs):
+            raise RuntimeError('symmetric-memory rendezvous did not yield a peer address for every rank')
 
     def alloc(self, total):
         self.params = self.symm.empty(total, dtype=torch.float32, device=self.device)
