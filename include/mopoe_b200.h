@@ -185,7 +185,8 @@ int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, const float*
  * All tensors fp32.  mu/logvar: M pointers to [B, D].  Subset s has member bitmask members[s] (bit i =
  * modality i, in the caller's modality order).  fuse_mode 0 = product of experts, 1 = mixture (batch-range
  * selection among members, uniform weights).  prior_expert != 0 appends N(0,I) to every product (poe method).
- * stacked[j] (j < S) are the subsets forming the joint mixture; sel_end[j] their exclusive batch-row ends
+ * stacked[j] (j < S) are the subsets forming the joint mixture (-1 = the N(0,I) prior component of jsd mode:
+ * joint mu = logvar = 0, z = eps on its rows); sel_end[j] their exclusive batch-row ends
  * (host-computed with the reference's fp32 floor rule).
  * Outputs: sub_mu/sub_lv [nsub, B, D]; joint_mu/joint_lv/z [B, D]; kl[nsub] = KL(subset || N(0,I)) / norm;
  * nan_flag[0] != 0 when an encoder mean/logvar is NaN (utils.check_latents, utils/utils.py:201-208).
@@ -242,6 +243,16 @@ int mopoe_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, flo
 
 int mopoe_adam_flat_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* coef,
                         float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ---- alpha-JSD divergence with a dynamic prior (jsd mode) -----------------------------------------
+ * BaseMMVae.divergence_dynamic_prior (utils/BaseMMVae.py:87-99) -> calc_alphaJSD_modalities (mm_div.py:67-87):
+ * dynamic prior = alpha_poe of the K stacked experts (mm_div.py:20-32; the N(0,I) prior is passed as one of them),
+ * kl[k] = KL(expert k || dynamic prior) / norm (kl_div.py:11-13).  mu / logvar: K device pointers to [B, D] fp32; alpha: K
+ * HOST floats; ws: K*B doubles.  bwd: d_kl[K] (device) -> d_mu[k], d_lv[k] ([B, D] each, overwritten). */
+int mopoe_jsd_divergence_fwd(int K, int B, int D, const float* const* mu, const float* const* logvar, const float* alpha,
+                             float norm, float* dyn_mu, float* dyn_lv, float* kl, double* ws, void* stream);
+int mopoe_jsd_divergence_bwd(int K, int B, int D, const float* const* mu, const float* const* logvar, const float* alpha,
+                             float norm, const float* d_kl, float* const* d_mu, float* const* d_lv, void* stream);
 
 /* All weight re-layouts of a step in ONE launch.  jobs_dev: DEVICE array of njobs descriptors (same meaning as the
  * arguments of mopoe_pack_weight_tiled; form 1 fills dst[0..3] / dst[0..1], the others dst[0]); tile0 = index of the

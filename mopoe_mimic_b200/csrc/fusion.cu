@@ -125,6 +125,12 @@ __global__ void __launch_bounds__(FUS_WARPS * 32) fusion_fwd_kernel(FusionDev c,
                 }
             }
         }
+        if (kj < 0) {       // jsd: this batch row belongs to the prior component N(0, I) of the mixture (BaseMMVae.py:180-186)
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(jmu + off) = zero;
+            *reinterpret_cast<float4*>(jlv + off) = zero;
+            *reinterpret_cast<float4*>(z + off) = e4;               // eps * exp(0) + 0
+        }
     }
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
@@ -163,7 +169,7 @@ static int fill_dev(const mopoe_fusion_cfg_t* cfg, FusionDev& d) {
         for (int j = 0; j < MAXM; ++j) { d.mem_end[i][j] = cfg->mem_end[i][j]; d.mem_idx[i][j] = cfg->mem_idx[i][j]; }
     }
     for (int j = 0; j < cfg->S; ++j)
-        MOPOE_REQUIRE(cfg->stacked[j] >= 0 && cfg->stacked[j] < cfg->nsub, "fusion: stacked[%d]=%d", j, cfg->stacked[j]);
+        MOPOE_REQUIRE(cfg->stacked[j] >= -1 && cfg->stacked[j] < cfg->nsub, "fusion: stacked[%d]=%d", j, cfg->stacked[j]);
     return 0;
 }
 
@@ -278,5 +284,141 @@ extern "C" int mopoe_fusion_bwd(const mopoe_fusion_cfg_t* cfg, const float* cons
     fusion_bwd_kernel<<<(cfg->B + FUS_WARPS - 1) / FUS_WARPS, FUS_WARPS * 32, 0, (cudaStream_t)stream>>>(
         d, p, eps, sub_mu, sub_lv, d_z, d_joint_mu, d_joint_lv, d_sub_mu, d_sub_lv, d_kl);
     MOPOE_CHECK_LAUNCH("fusion_bwd");
+    return 0;
+}
+
+// ---- alpha-JSD divergence with a dynamic prior (jsd mode) ----------------------------------------------------------------
+// Reference: BaseMMVae.divergence_dynamic_prior (utils/BaseMMVae.py:87-99) -> calc_alphaJSD_modalities (mm_div.py:67-87)
+// -> alpha_poe (mm_div.py:20-32) + calc_kl_divergence two-Gaussian branch (kl_div.py:11-13).
+//   T_i = 1/(exp(lv_i) + 1e-8);  V = 1/sum_i a_i T_i;  m = V * sum_i a_i mu_i T_i;  L = log V     (the dynamic prior)
+//   kl_k = -0.5 * sum_{b,d} (1 - exp(lv_k)/exp(L) - (mu_k - m)^2/exp(L) + lv_k - L) / norm
+constexpr int JSD_MAXK = 5;
+struct JsdArgs {
+    const float* mu[JSD_MAXK];
+    const float* lv[JSD_MAXK];
+    float* dmu[JSD_MAXK];
+    float* dlv[JSD_MAXK];
+    float alpha[JSD_MAXK];
+    int K, B, D;
+    float inv_norm;
+};
+
+__global__ void __launch_bounds__(FUS_WARPS * 32) jsd_fwd_kernel(JsdArgs a, float* __restrict__ dyn_mu, float* __restrict__ dyn_lv,
+                                                                 double* __restrict__ kl_part) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * FUS_WARPS + (threadIdx.x >> 5);
+    if (b >= a.B) return;
+    float acc[JSD_MAXK];
+#pragma unroll
+    for (int k = 0; k < JSD_MAXK; ++k) acc[k] = 0.f;
+    for (int d = lane; d < a.D; d += 32) {
+        const long long off = (long long)b * a.D + d;
+        float mu[JSD_MAXK], lv[JSD_MAXK];
+        float S = 0.f, N = 0.f;
+#pragma unroll
+        for (int k = 0; k < JSD_MAXK; ++k)
+            if (k < a.K) {
+                mu[k] = a.mu[k][off];
+                lv[k] = a.lv[k][off];
+                const float T = 1.f / (expf(lv[k]) + POE_EPS);
+                S += a.alpha[k] * T;                       // torch.sum(dim=0): stacking order
+                N += a.alpha[k] * mu[k] * T;
+            }
+        const float V = 1.f / S, m = V * N, Lg = logf(V), eL = expf(Lg);
+        dyn_mu[off] = m;
+        dyn_lv[off] = Lg;
+#pragma unroll
+        for (int k = 0; k < JSD_MAXK; ++k)
+            if (k < a.K) {
+                const float dm = mu[k] - m;
+                acc[k] += 1.f - expf(lv[k]) / eL - dm * dm / eL + lv[k] - Lg;
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < JSD_MAXK; ++k)
+        if (k < a.K) {
+            const double v = warp_sum((double)acc[k]);
+            if (lane == 0) kl_part[(long long)k * a.B + b] = v;
+        }
+}
+
+__global__ void __launch_bounds__(FUS_WARPS * 32) jsd_bwd_kernel(JsdArgs a, const float* __restrict__ d_kl) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * FUS_WARPS + (threadIdx.x >> 5);
+    if (b >= a.B) return;
+    float ck[JSD_MAXK];
+#pragma unroll
+    for (int k = 0; k < JSD_MAXK; ++k) ck[k] = k < a.K ? d_kl[k] * a.inv_norm : 0.f;
+    for (int d = lane; d < a.D; d += 32) {
+        const long long off = (long long)b * a.D + d;
+        float mu[JSD_MAXK], ev[JSD_MAXK], T[JSD_MAXK];
+        float S = 0.f, N = 0.f;
+#pragma unroll
+        for (int k = 0; k < JSD_MAXK; ++k)
+            if (k < a.K) {
+                mu[k] = a.mu[k][off];
+                ev[k] = expf(a.lv[k][off]);
+                T[k] = 1.f / (ev[k] + POE_EPS);
+                S += a.alpha[k] * T[k];
+                N += a.alpha[k] * mu[k] * T[k];
+            }
+        const float V = 1.f / S, m = V * N, iV = S;
+        // J = sum_k ck * KL_k:  gradients through the dynamic prior (m, V) and the direct terms
+        float Gm = 0.f, GV = 0.f;
+#pragma unroll
+        for (int k = 0; k < JSD_MAXK; ++k)
+            if (k < a.K) {
+                const float dm = mu[k] - m;
+                Gm += ck[k] * (-dm * iV);
+                GV += ck[k] * (-0.5f) * (ev[k] * iV * iV + dm * dm * iV * iV - iV);
+            }
+#pragma unroll
+        for (int k = 0; k < JSD_MAXK; ++k)
+            if (k < a.K) {
+                const float dm = mu[k] - m;
+                const float g_mu = ck[k] * dm * iV + Gm * V * a.alpha[k] * T[k];
+                const float dT = Gm * a.alpha[k] * V * dm - GV * a.alpha[k] * V * V;
+                const float g_lv = 0.5f * ck[k] * (ev[k] * iV - 1.f) + dT * (-T[k] * T[k] * ev[k]);
+                a.dmu[k][off] = g_mu;
+                a.dlv[k][off] = g_lv;
+            }
+    }
+}
+
+static int fill_jsd(int K, int B, int D, const float* const* mu, const float* const* logvar, const float* alpha, float norm,
+                    JsdArgs& a) {
+    MOPOE_REQUIRE(K >= 1 && K <= JSD_MAXK, "jsd_divergence: K=%d (max %d)", K, JSD_MAXK);
+    MOPOE_REQUIRE(B >= 1 && D >= 1 && norm > 0.f, "jsd_divergence: bad sizes");
+    a = JsdArgs{};
+    a.K = K; a.B = B; a.D = D; a.inv_norm = 1.f / norm;
+    for (int k = 0; k < K; ++k) {
+        MOPOE_REQUIRE(mu[k] && logvar[k], "jsd_divergence: null expert %d", k);
+        a.mu[k] = mu[k]; a.lv[k] = logvar[k]; a.alpha[k] = alpha[k];
+    }
+    return 0;
+}
+extern "C" int mopoe_jsd_divergence_fwd(int K, int B, int D, const float* const* mu, const float* const* logvar,
+                                        const float* alpha, float norm, float* dyn_mu, float* dyn_lv, float* kl, double* ws,
+                                        void* stream) {
+    JsdArgs a;
+    if (fill_jsd(K, B, D, mu, logvar, alpha, norm, a)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    jsd_fwd_kernel<<<(B + FUS_WARPS - 1) / FUS_WARPS, FUS_WARPS * 32, 0, st>>>(a, dyn_mu, dyn_lv, ws);
+    MOPOE_CHECK_LAUNCH("jsd_divergence_fwd");
+    fusion_kl_finalize<<<K, 32, 0, st>>>(ws, B, K, a.inv_norm, kl);
+    MOPOE_CHECK_LAUNCH("jsd_kl_finalize");
+    return 0;
+}
+extern "C" int mopoe_jsd_divergence_bwd(int K, int B, int D, const float* const* mu, const float* const* logvar,
+                                        const float* alpha, float norm, const float* d_kl, float* const* d_mu,
+                                        float* const* d_lv, void* stream) {
+    JsdArgs a;
+    if (fill_jsd(K, B, D, mu, logvar, alpha, norm, a)) return 1;
+    for (int k = 0; k < K; ++k) {
+        MOPOE_REQUIRE(d_mu[k] && d_lv[k], "jsd_divergence_bwd: null gradient buffer %d", k);
+        a.dmu[k] = d_mu[k]; a.dlv[k] = d_lv[k];
+    }
+    jsd_bwd_kernel<<<(B + FUS_WARPS - 1) / FUS_WARPS, FUS_WARPS * 32, 0, (cudaStream_t)stream>>>(a, d_kl);
+    MOPOE_CHECK_LAUNCH("jsd_divergence_bwd");
     return 0;
 }

@@ -67,6 +67,8 @@ class FusionPlan:
             stacked = [i for i, mem in enumerate(members) if len(mem) == len(self.mods)]
         else:
             stacked = list(range(len(members)))
+        if method == 'jsd':
+            stacked = stacked + [-1]          # the prior N(0, I) is one more mixture component (BaseMMVae.py:180-186)
         self.stacked = stacked
         self.B, self.D = B, D
         cfg = L.FusionCfg()
@@ -100,6 +102,41 @@ class FusionPlan:
 def _ptr_array(tensors):
     arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
     return arr
+
+
+class JsdDivergenceFn(torch.autograd.Function):
+    """(mu_1..mu_K, lv_1..lv_K) -> (kl [K], dyn_mu [B,D], dyn_lv [B,D]): alpha-JSD terms against the dynamic prior
+    (mopoe_jsd_divergence_fwd / _bwd; mm_div.calc_alphaJSD_modalities).  alpha: K python floats."""
+
+    @staticmethod
+    def forward(ctx, eng, alpha, norm, *mulv):
+        K = len(mulv) // 2
+        mus = [t.contiguous().float() for t in mulv[:K]]
+        lvs = [t.contiguous().float() for t in mulv[K:]]
+        B, D = mus[0].shape
+        dev = mus[0].device
+        kl = torch.empty(K, device=dev)
+        dyn_mu, dyn_lv = torch.empty(B, D, device=dev), torch.empty(B, D, device=dev)
+        al = (C.c_float * K)(*[float(a) for a in alpha])
+        L.call('mopoe_jsd_divergence_fwd', K, B, D, _ptr_array(mus), _ptr_array(lvs), al, float(norm), L.ptr(dyn_mu),
+               L.ptr(dyn_lv), L.ptr(kl), L.ptr(eng.ws64(K * B)), L.stream_ptr())
+        ctx.alpha, ctx.norm, ctx.K = [float(a) for a in alpha], float(norm), K
+        ctx.save_for_backward(*mus, *lvs)
+        ctx.mark_non_differentiable(dyn_mu, dyn_lv)
+        return kl, dyn_mu, dyn_lv
+
+    @staticmethod
+    def backward(ctx, d_kl, _dm, _dl):
+        K = ctx.K
+        mulv = ctx.saved_tensors
+        mus, lvs = mulv[:K], mulv[K:]
+        B, D = mus[0].shape
+        dmu = [torch.empty_like(t) for t in mus]
+        dlv = [torch.empty_like(t) for t in lvs]
+        al = (C.c_float * K)(*ctx.alpha)
+        L.call('mopoe_jsd_divergence_bwd', K, B, D, _ptr_array(mus), _ptr_array(lvs), al, ctx.norm,
+               L.ptr(d_kl.contiguous().float()), _ptr_array(dmu), _ptr_array(dlv), L.stream_ptr())
+        return (None, None, None, *dmu, *dlv)
 
 
 class FusionFn(torch.autograd.Function):

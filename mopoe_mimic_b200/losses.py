@@ -12,9 +12,10 @@ from .fusion import FusionFn, FusionPlan
 
 def calc_kl_divergence(mu0, logvar0, mu1=None, logvar1=None, norm_value=None):
     """kl_div.calc_kl_divergence (evaluation/divergence_measures/kl_div.py:8-16), prior branch, through the
-    fusion kernel's KL reduction.  (The two-Gaussian branch is only used by the jsd path — not built.)"""
+    fusion kernel's KL reduction.  (The two-Gaussian branch is only used inside calc_alphaJSD_modalities, which the jsd path
+    runs fused — mopoe_jsd_divergence_fwd / BaseMMVae.divergence_dynamic_prior — so it is not exposed separately.)"""
     if mu1 is not None or logvar1 is not None:
-        raise NotImplementedError('KL between two Gaussians is only needed by the jsd path (SURVEY.md N4)')
+        raise NotImplementedError('KL between two Gaussians: use mm_vae.divergence_dynamic_prior (the fused jsd divergence)')
     from .engine import Engine
     B, D = mu0.shape
     plan = FusionPlan(['e0'], ['e0'], ['e0'], [['e0']], 'moe', B, D, float(norm_value) if norm_value else 1.0)

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .fusion import FusionFn, FusionPlan, selection_ends, set_subsets, uniform_weights  # noqa: F401
+from .fusion import FusionFn, FusionPlan, JsdDivergenceFn, selection_ends, set_subsets, uniform_weights  # noqa: F401
 from .modalities import CategoricalLikelihood, LaplaceLikelihood
 from .networks import Runtime
 
@@ -51,15 +51,15 @@ class BaseMMVae(nn.Module):
         w = torch.tensor(list(self.flags.alpha_modalities), dtype=torch.float32)
         self.weights = reweight_weights(w)
         self.method = method_of(self.flags)
-        if self.method == 'jsd':
-            raise NotImplementedError('the jsd dynamic prior is outside the built scope (SURVEY.md §8 a22 / N4)')
-        if self.method == 'moe':
+        self.calc_joint_divergence = self.divergence_static_prior
+        if self.method in ('moe', 'jsd'):
             self.modality_fusion, self.fusion_condition = self.moe_fusion, self.fusion_condition_moe
+            if self.method == 'jsd':
+                self.calc_joint_divergence = self.divergence_dynamic_prior
         elif self.method == 'poe':
             self.modality_fusion, self.fusion_condition = self.poe_fusion, self.fusion_condition_poe
         else:
             self.modality_fusion, self.fusion_condition = self.poe_fusion, self.fusion_condition_joint
-        self.calc_joint_divergence = self.divergence_static_prior
 
     def fusion_condition_moe(self, subset, input_batch=None):
         return len(subset) == 1
@@ -138,6 +138,30 @@ class BaseMMVae(nn.Module):
         klds = torch.cat(klds)
         return {'joint_divergence': (w * klds).sum(dim=0), 'individual_divs': klds, 'dyn_prior': None}
 
+    def divergence_dynamic_prior(self, mus, logvars, weights=None):
+        """alpha-JSD against the dynamic prior alpha_poe(weights, mus, logvars)  (BaseMMVae.py:87-99, mm_div.py:67-87).
+        mus / logvars: [K, B, D] (jsd mode stacks the unimodal posteriors and the N(0,I) prior); the weights are used
+        as given (no re-normalisation), exactly as the reference does."""
+        if weights is None:
+            weights = self.weights
+        K = mus.shape[0]
+        if K > 5:
+            raise NotImplementedError('divergence_dynamic_prior takes at most 5 stacked experts')
+        w_host = [float(x) for x in torch.as_tensor(weights, dtype=torch.float32).cpu()] if not getattr(
+            weights, 'is_cuda', False) else self._weights_host(weights)
+        kl, dyn_mu, dyn_lv = JsdDivergenceFn.apply(self._eng(mus.device), tuple(w_host), float(self.flags.batch_size),
+                                                   *[mus[k] for k in range(K)], *[logvars[k] for k in range(K)])
+        w_dev = torch.as_tensor(weights, dtype=torch.float32).to(mus.device)
+        return {'joint_divergence': (w_dev * kl).sum(dim=0), 'individual_divs': kl, 'dyn_prior': [dyn_mu, dyn_lv]}
+
+    def _weights_host(self, weights):
+        """host copy of a (small) device weight vector, cached by identity: keeps the step free of D2H syncs"""
+        cache = self.__dict__.setdefault('_w_host_cache', {})
+        key = (weights.data_ptr(), weights._version)
+        if key not in cache:
+            cache[key] = [float(x) for x in weights.detach().float().cpu()]
+        return cache[key]
+
     # ---- inference (BaseMMVae.py:139-196) ---------------------------------------------------------------------------
     def inference(self, input_batch, num_samples=None):
         enc_mods = self.encode(input_batch)
@@ -153,7 +177,12 @@ class BaseMMVae(nn.Module):
         latents = {'modalities': enc_mods}
         distr_subsets = OrderedDict((k, [sub_mu[i], sub_lv[i]]) for i, k in enumerate(plan.keys))
         st = plan.stacked
-        if st == list(range(len(plan.keys))):
+        if self.method == 'jsd':             # unimodal posteriors + one zero row for the prior component
+            uni = st[:-1]
+            zrow = torch.zeros(1, B, self.flags.class_dim, device=first.device)
+            latents['mus'] = torch.cat((sub_mu[uni[0]:uni[-1] + 1] if uni == list(range(uni[0], uni[-1] + 1)) else sub_mu[uni], zrow))
+            latents['logvars'] = torch.cat((sub_lv[uni[0]:uni[-1] + 1] if uni == list(range(uni[0], uni[-1] + 1)) else sub_lv[uni], zrow))
+        elif st == list(range(len(plan.keys))):
             latents['mus'], latents['logvars'] = sub_mu, sub_lv
         else:
             latents['mus'] = sub_mu[st[0]:st[-1] + 1] if st == list(range(st[0], st[-1] + 1)) else sub_mu[st]
@@ -166,7 +195,10 @@ class BaseMMVae(nn.Module):
         # fused by-products (private): reparameterised sample, per-subset KLs, NaN flag
         latents['_z'] = z
         latents['_klds'] = OrderedDict((k, kl[i]) for i, k in enumerate(plan.keys))
-        latents['_kl_stacked'] = kl[st[0]:st[-1] + 1] if st == list(range(st[0], st[-1] + 1)) else kl[st]
+        if self.method != 'jsd':
+            latents['_kl_stacked'] = kl[st[0]:st[-1] + 1] if st == list(range(st[0], st[-1] + 1)) else kl[st]
+        else:
+            plan.weights_host = [float(x) for x in plan.weights]
         latents['_nan_flag'] = nan_flag
         return latents
 
@@ -244,11 +276,21 @@ class MMVaeMimic(BaseMMVae):
             self.rt.injected_masks, self.rt.injected_eps = self.rt.schedule.pop(0)
         latents = self.inference(input_batch)
         results = {'latents': latents}
-        w = reweight_weights(latents['weights'])
-        klds = latents['_kl_stacked']
-        results['joint_divergence'] = (w * klds).sum(dim=0)
-        results['individual_divs'] = klds
-        results['dyn_prior'] = None
+        if self.method == 'jsd':
+            mus_st, lvs_st = latents['mus'], latents['logvars']
+            K = mus_st.shape[0]
+            w_host = [1.0 / K] * K       # latents['weights'] = (1 / float(K)) * ones(K), used un-normalised (:187, mm_div.py:86)
+            kl, dyn_mu, dyn_lv = JsdDivergenceFn.apply(self._eng(mus_st.device), tuple(w_host), float(self.flags.batch_size),
+                                                       *[mus_st[k] for k in range(K)], *[lvs_st[k] for k in range(K)])
+            results['joint_divergence'] = (latents['weights'] * kl).sum(dim=0)
+            results['individual_divs'] = kl
+            results['dyn_prior'] = [dyn_mu, dyn_lv]
+        else:
+            w = reweight_weights(latents['weights'])
+            klds = latents['_kl_stacked']
+            results['joint_divergence'] = (w * klds).sum(dim=0)
+            results['individual_divs'] = klds
+            results['dyn_prior'] = None
         results['group_distr'] = latents['joint']
         class_embeddings = latents['_z']
         results_rec = {}

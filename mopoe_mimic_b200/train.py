@@ -42,6 +42,7 @@ def default_flags(**kw):
     m = f.pop('method', None)
     if m is not None:
         f['modality_moe'], f['modality_poe'], f['joint_elbo'] = m == 'moe', m == 'poe', m == 'joint_elbo'
+        f['modality_jsd'] = m == 'jsd'
     return SimpleNamespace(**f)
 
 

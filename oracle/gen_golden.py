@@ -57,7 +57,7 @@ def ref_flags(fl):
         image_channels=fl.image_channels, DIM_img=fl.DIM_img, DIM_text=fl.DIM_text, text_encoding='char',
         len_sequence=fl.len_sequence, num_features=fl.num_features, alphabet='x' * fl.num_features,
         feature_extractor_img='resnet', factorized_representation=False, style_pa_dim=0, style_lat_dim=0,
-        style_text_dim=0, modality_moe=(m == 'moe'), modality_jsd=False, modality_poe=(m == 'poe'),
+        style_text_dim=0, modality_moe=(m == 'moe'), modality_jsd=(m == 'jsd'), modality_poe=(m == 'poe'),
         joint_elbo=(m == 'joint_elbo'), poe_unimodal_elbos=True, alpha_modalities=list(fl.alpha_modalities),
         beta=fl.beta, beta_style=fl.beta_style, beta_content=fl.beta_content, dataset='testing',
         distributed=False, world_size=1, text_gen_lastlayer='softmax')
@@ -182,6 +182,8 @@ CASES = OrderedDict([
     ('small_tri_256_joint', dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=64, img_size=256)),
     ('small_tri_64_joint', dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=16, img_size=64)),
     ('small_tri_joint_ragged', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, actual_batch=5)),
+    ('small_tri_jsd', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, method='jsd')),
+    ('small_patext_jsd', dict(batch_size=9, DIM_img=16, DIM_text=16, class_dim=32, mods=('PA', 'text'), method='jsd')),
 ])
 
 

@@ -458,7 +458,7 @@ def kl_to_standard_normal(mu, logvar, norm_value):
 
 
 def inference(enc_mods, flags, present):
-    """BaseMMVae.inference (utils/BaseMMVae.py:139-196) for methods moe / poe / joint_elbo.
+    """BaseMMVae.inference (utils/BaseMMVae.py:139-196) for methods moe / jsd / poe / joint_elbo.
     enc_mods: name -> (mu, logvar); present: modality names in the input batch (dict order)."""
     method = flags.method
     subsets = subset_keys(flags.mods)
@@ -477,8 +477,8 @@ def inference(enc_mods, flags, present):
             w = torch.full((mu_s.shape[0],), 1.0 / mu_s.shape[0])
             s_mu, s_lv = mixture_component_selection(mu_s, lv_s, w)
         distr[key] = (s_mu, s_lv)
-        if method == 'moe':
-            cond = len(members) == 1                  # fusion_condition_moe  :130-131
+        if method in ('moe', 'jsd'):
+            cond = len(members) == 1                  # fusion_condition_moe  :130-131 (jsd uses it too, :58-61)
         elif method == 'poe':
             cond = len(members) == len(present)       # fusion_condition_poe  :133-134
         else:
@@ -487,10 +487,29 @@ def inference(enc_mods, flags, present):
             mus.append(s_mu)
             logvars.append(s_lv)
     mus, logvars = torch.stack(mus), torch.stack(logvars)
+    if method == 'jsd':                    # the prior N(0, I) joins the mixture as one more component (:180-186)
+        zrow = torch.zeros_like(mus[:1])
+        mus, logvars = torch.cat((mus, zrow)), torch.cat((logvars, zrow))
     S = mus.shape[0]
     weights = torch.full((S,), 1.0 / S, dtype=torch.float32)
     j_mu, j_lv = mixture_component_selection(mus, logvars, weights)
     return dict(modalities=enc_mods, mus=mus, logvars=logvars, weights=weights, joint=(j_mu, j_lv), subsets=distr)
+
+
+def alpha_poe(alpha, mu, logvar):
+    """mm_div.alpha_poe (mm_div.py:20-32): weighted product of experts = the jsd dynamic prior.  mu, logvar [K,B,D]."""
+    var = torch.exp(logvar) + POE_EPS
+    a = alpha.to(mu.dtype).unsqueeze(-1).unsqueeze(-1)
+    T = 1 / var
+    pd_var = 1.0 / torch.sum(a * T, dim=0)
+    pd_mu = pd_var * torch.sum(a * mu * T, dim=0)
+    return pd_mu, torch.log(pd_var)
+
+
+def kl_between(mu0, logvar0, mu1, logvar1, norm_value):
+    """kl_div.calc_kl_divergence, two-Gaussian branch (kl_div.py:11-13)."""
+    return -0.5 * torch.sum(1 - logvar0.exp() / logvar1.exp() - (mu0 - mu1).pow(2) / logvar1.exp()
+                            + logvar0 - logvar1) / float(norm_value)
 
 
 def laplace_log_prob_sum(loc, target):
@@ -524,9 +543,19 @@ def forward(state, batch, flags, masks=None, eps=None, train=True, present=None)
     # calc_group_divergence_moe (mm_div.py:90-110): the reference collects the per-subset KLs in
     # `torch.zeros(num_mods)` -- an FP32 tensor whatever the model dtype -- and the weights are FP32 too
     # (BaseMMVae.py:187), so joint_divergence is an fp32 quantity even in an fp64 run.
-    w = lat['weights'] / lat['weights'].sum()
-    klds_ind = torch.stack([kl_to_standard_normal(lat['mus'][k], lat['logvars'][k], flags.batch_size)
-                            for k in range(lat['mus'].shape[0])]).to(torch.float32)
+    dyn_prior = None
+    if flags.method == 'jsd':
+        # divergence_dynamic_prior (BaseMMVae.py:87-99) -> calc_alphaJSD_modalities (mm_div.py:67-87) with the weights
+        # forward() passes: latents['weights'] (uniform 1/(M+1), NOT re-normalised, alpha_modalities is not used here)
+        w = lat['weights']
+        a_mu, a_lv = alpha_poe(w, lat['mus'], lat['logvars'])
+        klds_ind = torch.stack([kl_between(lat['mus'][k], lat['logvars'][k], a_mu, a_lv, flags.batch_size)
+                                for k in range(lat['mus'].shape[0])]).to(torch.float32)
+        dyn_prior = (a_mu, a_lv)
+    else:
+        w = lat['weights'] / lat['weights'].sum()
+        klds_ind = torch.stack([kl_to_standard_normal(lat['mus'][k], lat['logvars'][k], flags.batch_size)
+                                for k in range(lat['mus'].shape[0])]).to(torch.float32)
     joint_div = (w * klds_ind).sum()
     j_mu, j_lv = lat['joint']
     if eps is None:
@@ -538,7 +567,7 @@ def forward(state, batch, flags, masks=None, eps=None, train=True, present=None)
             rec[m] = decoder_text(ctx, flags, DEC_NAME[m], z)
         else:
             rec[m] = decoder_img(ctx, flags, DEC_NAME[m], z)
-    return dict(latents=lat, joint_divergence=joint_div, individual_divs=klds_ind, z=z, rec=rec,
+    return dict(latents=lat, joint_divergence=joint_div, individual_divs=klds_ind, dyn_prior=dyn_prior, z=z, rec=rec,
                 bn_updates=ctx.bn_updates)
 
 
@@ -556,7 +585,7 @@ def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks
         log_probs[m] = -lp / Bn
         weighted = weighted + flags.rec_weights[m] * log_probs[m]
     klds = OrderedDict((k, kl_to_standard_normal(mu, lv, Bn)) for k, (mu, lv) in res['latents']['subsets'].items())
-    if flags.method in ('moe', 'joint_elbo'):
+    if flags.method in ('moe', 'jsd', 'joint_elbo'):
         total = weighted + flags.beta * (flags.beta_style * 0.0 + flags.beta_content * res['joint_divergence'])
     elif flags.method == 'poe':
         total = weighted + flags.beta * flags.beta_content * res['joint_divergence']   # calc_elbo 'joint'

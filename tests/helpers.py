@@ -132,6 +132,11 @@ def compare_step(orc, out, grads, state_after=None):
         errs['sub_mu.' + k] = rel_err(plat['subsets'][k][0], mu)
         errs['sub_lv.' + k] = rel_err(plat['subsets'][k][1], lv)
     errs['joint_mu'] = rel_err(plat['joint'][0], olat['joint'][0])
+    errs['mus'] = rel_err(plat['mus'], olat['mus'])
+    errs['ind_divs'] = rel_err(out['results']['individual_divs'], orc['results']['individual_divs'])
+    if orc['results'].get('dyn_prior') is not None:
+        errs['dyn_mu'] = rel_err(out['results']['dyn_prior'][0], orc['results']['dyn_prior'][0])
+        errs['dyn_lv'] = rel_err(out['results']['dyn_prior'][1], orc['results']['dyn_prior'][1])
     errs['z'] = rel_err(plat['_z'], orc['results']['z'])
     for m, r in orc['results']['rec'].items():
         pr = out['results']['rec'][m]

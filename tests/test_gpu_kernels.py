@@ -85,6 +85,39 @@ def test_fusion_gradients_vs_oracle():
             torch.testing.assert_close(gl[i].grad.cpu(), cl[i].grad, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize('K,B,D', [(4, 16, 32), (3, 9, 64), (5, 7, 20)])
+def test_jsd_divergence_forward_backward_vs_oracle(K, B, D):
+    """mopoe_jsd_divergence_fwd/_bwd against the oracle's alpha_poe + two-Gaussian KL (mm_div.py:20-32,67-87) evaluated
+    in fp64 with torch autograd: per-expert KLs, the dynamic prior, and the gradients of a weighted sum of the KLs."""
+    from mopoe_mimic_b200.engine import Engine
+    from mopoe_mimic_b200.fusion import JsdDivergenceFn
+    g = torch.Generator(device='cpu').manual_seed(K * 100 + B)
+    mus = torch.randn(K, B, D, generator=g)
+    lvs = torch.randn(K, B, D, generator=g) * 0.7
+    mus[-1].zero_()
+    lvs[-1].zero_()                                   # the prior expert of jsd mode
+    alpha = torch.rand(K, generator=g) + 0.2
+    alpha = (alpha / alpha.sum()).float()
+    cw = torch.randn(K, generator=g)
+    norm = 11.0
+    m64, l64 = mus.double().requires_grad_(True), lvs.double().requires_grad_(True)
+    a_mu, a_lv = O.alpha_poe(alpha, m64, l64)
+    kl_ref = torch.stack([O.kl_between(m64[k], l64[k], a_mu, a_lv, norm) for k in range(K)])
+    (kl_ref * cw.double()).sum().backward()
+    eng = Engine('cuda', torch.float32)
+    md = [mus[k].cuda().requires_grad_(True) for k in range(K)]
+    ld = [lvs[k].cuda().requires_grad_(True) for k in range(K)]
+    kl, dyn_mu, dyn_lv = JsdDivergenceFn.apply(eng, tuple(float(a) for a in alpha), norm, *md, *ld)
+    (kl * cw.cuda()).sum().backward()
+    assert torch.allclose(kl.cpu().double(), kl_ref.detach(), rtol=2e-5, atol=1e-6)
+    assert torch.allclose(dyn_mu.cpu().double(), a_mu.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(dyn_lv.cpu().double(), a_lv.detach(), rtol=1e-5, atol=1e-6)
+    gs = float(m64.grad.abs().max())
+    for k in range(K):
+        assert float((md[k].grad.cpu().double() - m64.grad[k]).abs().max()) < 2e-5 * gs + 1e-7, k
+        assert float((ld[k].grad.cpu().double() - l64.grad[k]).abs().max()) < 2e-5 * max(gs, float(l64.grad.abs().max())) + 1e-7, k
+
+
 def test_fusion_nan_flag():
     mods, B, D = ('PA', 'text'), 8, 32
     mus = [torch.zeros(B, D) for _ in mods]

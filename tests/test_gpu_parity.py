@@ -29,6 +29,8 @@ CASES = {
     'patext_joint': dict(SMALL, mods=('PA', 'text')),
     'patext_moe': dict(SMALL, mods=('PA', 'text'), method='moe'),
     'patext_poe': dict(SMALL, mods=('PA', 'text'), method='poe', batch_size=5),
+    'tri_jsd': dict(SMALL, method='jsd'),
+    'patext_jsd': dict(SMALL, mods=('PA', 'text'), method='jsd', batch_size=9),
     'tri_64px': dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=16, img_size=64),
     'tri_256px': dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=16, img_size=256),     # stride-4 stage (config 4)
 }
@@ -55,7 +57,7 @@ def test_fp32_step_matches_oracle(name):
     assert g[-1] < 5e-2, errs['_worst_grad']
 
 
-@pytest.mark.parametrize('name', ['tri_joint', 'tri_moe', 'patext_joint', 'tri_64px', 'tri_256px'])
+@pytest.mark.parametrize('name', ['tri_joint', 'tri_moe', 'tri_jsd', 'patext_joint', 'tri_64px', 'tri_256px'])
 def test_fp32_gradients_of_smooth_loss_match_oracle(name):
     """Every conv / deconv / BN / dropout / fusion backward kernel, compared tightly: same graph, smooth loss."""
     kw = CASES[name]
@@ -98,7 +100,8 @@ def test_fp32_ragged_last_batch():
 
 
 GOLDEN_SMALL = ['small_tri_joint', 'small_tri_moe', 'small_tri_poe', 'small_patext_joint', 'small_patext_moe',
-                'small_patext_poe', 'small_tri_64_joint', 'small_tri_256_joint', 'small_tri_joint_ragged']
+                'small_patext_poe', 'small_tri_64_joint', 'small_tri_256_joint', 'small_tri_joint_ragged', 'small_tri_jsd',
+                'small_patext_jsd']
 
 
 @pytest.mark.parametrize('fixture', GOLDEN_SMALL)
