@@ -64,12 +64,24 @@ def calc_klds(exp, result):
 
 
 def calc_klds_style(exp, result):
-    """losses.py:34-42 — style latents are not built (all BASELINE configs use style_dim = 0)."""
-    return {}
+    """losses.py:34-42: KL(style posterior || N(0,I)) / batch_size for every '<modality>_style' entry.  The fused
+    style-reparameterisation launch of forward() already produced them (latents['_klds_style'])."""
+    latents = result['latents']
+    fused = latents.get('_klds_style')
+    klds = {}
+    for key, val in latents['modalities'].items():
+        if key.endswith('style') and val[0] is not None:
+            klds[key] = fused[key] if fused is not None and key in fused else \
+                calc_kl_divergence(val[0], val[1], norm_value=exp.flags.batch_size)
+    return klds
 
 
 def calc_style_kld(exp, klds):
-    return 0.0
+    """losses.py:45-51"""
+    weighted_klds = 0.0
+    for m_key in exp.modalities.keys():
+        weighted_klds = weighted_klds + exp.style_weights[m_key] * klds[m_key + '_style']
+    return weighted_klds
 
 
 def calc_elbo(exp, modality, recs, klds):
@@ -102,6 +114,6 @@ def calc_poe_loss(exp, mods, group_divergence, klds, klds_style, batch_d, mm_vae
 
 def calc_joint_elbo_loss(exp, klds_style, group_divergence, beta_style, beta_content, weighted_log_prob, beta):
     """losses.py:80-89."""
-    kld_style = 0.0
+    kld_style = calc_style_kld(exp, klds_style) if getattr(exp.flags, 'factorized_representation', False) else 0.0
     kld_weighted = beta_style * kld_style + beta_content * group_divergence
     return 1.0 * weighted_log_prob + beta * kld_weighted

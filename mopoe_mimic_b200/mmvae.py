@@ -255,25 +255,42 @@ class MMVaeMimic(BaseMMVae):
         for m in self.modalities:
             if m in input_batch:
                 L.require_cuda(input_batch[m])
-                latents[m] = list(getattr(self, ENC_NAME[m])(input_batch[m])[:2])
+                out = getattr(self, ENC_NAME[m])(input_batch[m])
+                if len(out) == 4:                  # VAEtrimodalMimic.encode:64-93: content first, style after
+                    latents[m + '_style'] = list(out[2:])
+                latents[m] = list(out[:2])
             else:
                 latents[m + '_style'] = [None, None]
                 latents[m] = [None, None]
         return latents
 
-    def _decode(self, m_key, z):
+    def _style_sample(self, m_key, s_mu, s_lv):
+        """reparameterised style latent and its KL to N(0,I) / batch_size in ONE launch: the fusion kernel on a single
+        expert (identity subset) yields z = eps * exp(logvar / 2) + mu and the KL reduction (utils.py:45-48, kl_div.py:8-16)"""
+        B, Ds = s_mu.shape
+        key = ('style', Ds, B)
+        if key not in self._plans:
+            self._plans[key] = FusionPlan(['e0'], ['e0'], ['e0'], [['e0']], 'moe', B, Ds, self.flags.batch_size)
+        es = self.rt.injected_eps_style
+        eps = es[m_key] if es is not None else torch.randn(B, Ds, device=s_mu.device)
+        out = FusionFn.apply(self._plans[key], self._eng(s_mu.device), eps, s_mu, s_lv)
+        return out[4], out[5][0]
+
+    def _decode(self, m_key, z, z_style=None):
         eng = self._eng(z.device)
         dec = getattr(self, DEC_NAME[m_key])
         if m_key == 'text':
-            return CategoricalLikelihood(scores=dec(None, z)[0], eng=eng)
-        loc, scale = dec(None, z)
+            return CategoricalLikelihood(scores=dec(z_style, z)[0], eng=eng)
+        loc, scale = dec(z_style, z)
         return LaplaceLikelihood(loc, scale, eng=eng, scale_value=0.75)   # ConvNetworksImgMimic.py:54
 
     def forward(self, input_batch):
         """VAEtrimodalMimic.forward:31-62; absent modalities are skipped in the decode loop (the intended
         behaviour for calc_poe_loss — the shipped reference raises KeyError there)."""
         if self.rt.schedule:
-            self.rt.injected_masks, self.rt.injected_eps = self.rt.schedule.pop(0)
+            item = self.rt.schedule.pop(0)
+            self.rt.injected_masks, self.rt.injected_eps = item[0], item[1]
+            self.rt.injected_eps_style = item[2] if len(item) > 2 else None
         latents = self.inference(input_batch)
         results = {'latents': latents}
         if self.method == 'jsd':
@@ -294,14 +311,27 @@ class MMVaeMimic(BaseMMVae):
         results['group_distr'] = latents['joint']
         class_embeddings = latents['_z']
         results_rec = {}
+        factorized = bool(getattr(self.flags, 'factorized_representation', False))
+        if factorized:
+            latents['_klds_style'] = {}
         for m_key in self.modalities:
             if m_key in input_batch and input_batch[m_key] is not None:
-                results_rec[m_key] = self._decode(m_key, class_embeddings)
+                s_emb = None
+                if factorized:          # VAEtrimodalMimic.forward:49-51: s_emb = reparameterize(style mu, logvar)
+                    s_mu, s_lv = latents['modalities'][m_key + '_style']
+                    s_emb, kl_s = self._style_sample(m_key, s_mu, s_lv)
+                    latents['_klds_style'][m_key + '_style'] = kl_s
+                results_rec[m_key] = self._decode(m_key, class_embeddings, s_emb)
         results['rec'] = results_rec
         return results
 
     def get_random_styles(self, num_samples):
-        return {m: None for m in self.modalities}
+        """VAEtrimodalMimic.get_random_styles:95-110"""
+        if not getattr(self.flags, 'factorized_representation', False):
+            return {m: None for m in self.modalities}
+        dims = {'PA': self.flags.style_pa_dim, 'Lateral': self.flags.style_lat_dim, 'text': self.flags.style_text_dim}
+        dev = next(self.parameters()).device
+        return {m: torch.randn(num_samples, dims[m], device=dev) for m in self.modalities}
 
     def get_random_style_dists(self, num_samples):
         dev = next(self.parameters()).device
@@ -310,7 +340,8 @@ class MMVaeMimic(BaseMMVae):
 
     def generate_sufficient_statistics_from_latents(self, latents):
         content = latents['content']
-        return {m: self._decode(m, content) for m in self.modalities}
+        style = latents.get('style') or {}
+        return {m: self._decode(m, content, style.get(m)) for m in self.modalities}
 
     def save_networks(self):
         names = {'PA': ('encoder_save_m1', 'decoder_save_m1'), 'Lateral': ('encoder_save_m2', 'decoder_save_m2'),

@@ -36,7 +36,8 @@ class Runtime:
         self.engine = None
         self.injected_masks = None    # dict name -> uint8 keep-mask in our layout ([B,C] 2-D, [B,L,C] 1-D)
         self.injected_eps = None      # [B, class_dim] fp32
-        self.schedule = None          # optional list of (masks, eps), one per model forward call (poe passes)
+        self.injected_eps_style = None   # modality -> [B, style_dim] fp32 (factorized representation)
+        self.schedule = None          # optional list of (masks, eps[, eps_style]), one per model forward call (poe passes)
         self.seed = None
 
     def eng(self, device):
@@ -172,10 +173,12 @@ class FeatureExtractorImg(nn.Module):
 class LinearFeatureCompressor(nn.Module):
     def __init__(self, in_channels, out_channels_style, out_channels_content):
         super().__init__()
-        if out_channels_style:
-            raise NotImplementedError('factorized (style) latents are outside the built scope (SURVEY.md N4)')
-        self.style_mu = None
-        self.style_logvar = None
+        if out_channels_style:                 # registered FIRST, as in the reference (state_dict order)
+            self.style_mu = _Params((out_channels_style, in_channels), out_channels_style)
+            self.style_logvar = _Params((out_channels_style, in_channels), out_channels_style)
+        else:
+            self.style_mu = None
+            self.style_logvar = None
         self.content_mu = _Params((out_channels_content, in_channels), out_channels_content)
         self.content_logvar = _Params((out_channels_content, in_channels), out_channels_content)
 
@@ -210,6 +213,10 @@ class EncoderImg(_Net):
         lv = LinearFn.apply(h, fc.content_logvar.weight, fc.content_logvar.bias, eng, B, 0, 2, False)
         if train:
             self._bump()
+        if fc.style_mu is not None:            # content first, style after (ConvNetworksImgMimic.py:31-33)
+            smu = LinearFn.apply(h, fc.style_mu.weight, fc.style_mu.bias, eng, B, 0, 2, False)
+            slv = LinearFn.apply(h, fc.style_logvar.weight, fc.style_logvar.bias, eng, B, 0, 2, False)
+            return mu, lv, smu, slv
         return mu, lv
 
 
@@ -238,14 +245,13 @@ class DecoderImg(_Net):
 
     def __init__(self, flags, style_dim=0):
         super().__init__(flags)
-        if style_dim:
-            raise NotImplementedError('factorized (style) latents are outside the built scope (SURVEY.md N4)')
         self.feature_generator = _Params((5 * flags.DIM_img, style_dim + flags.class_dim), 5 * flags.DIM_img)
         self.img_generator = DataGeneratorImg(flags)
         self.register_buffer('_scale', torch.tensor(0.75), persistent=False)
 
     def forward(self, z_style, z_content):
-        z = z_content
+        # factorized representation: z = cat(style, content) (ConvNetworksImgMimic.py:47-48, ConvNetworksTextMimic.py:52-55)
+        z = z_content if z_style is None else torch.cat((z_style, z_content), dim=1)
         L.require_cuda(z)
         rt, gen = self.rt, self.img_generator
         eng = rt.eng(z.device)
@@ -315,6 +321,10 @@ class EncoderText(_Net):
         lv = LinearFn.apply(h, fc.content_logvar.weight, fc.content_logvar.bias, eng, B, 0, 1, False)
         if train:
             self._bump()
+        if fc.style_mu is not None:
+            smu = LinearFn.apply(h, fc.style_mu.weight, fc.style_mu.bias, eng, B, 0, 1, False)
+            slv = LinearFn.apply(h, fc.style_logvar.weight, fc.style_logvar.bias, eng, B, 0, 1, False)
+            return mu, lv, smu, slv
         return mu, lv
 
 
@@ -344,13 +354,12 @@ class DecoderText(_Net):
         super().__init__(flags)
         if flags.text_encoding != 'char':
             raise NotImplementedError('word encoding is outside the built scope (SURVEY.md N4)')
-        if style_dim:
-            raise NotImplementedError('factorized (style) latents are outside the built scope (SURVEY.md N4)')
         self.feature_generator = _Params((5 * flags.DIM_text, style_dim + flags.class_dim), 5 * flags.DIM_text)
         self.text_generator = DataGeneratorText(flags)
 
     def forward(self, z_style, z_content):
-        z = z_content
+        # factorized representation: z = cat(style, content) (ConvNetworksImgMimic.py:47-48, ConvNetworksTextMimic.py:52-55)
+        z = z_content if z_style is None else torch.cat((z_style, z_content), dim=1)
         L.require_cuda(z)
         rt, gen = self.rt, self.text_generator
         eng = rt.eng(z.device)

@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 from . import _lib as L
 from .fusion import set_subsets
-from .losses import calc_joint_elbo_loss, calc_klds, calc_log_probs, calc_poe_loss
+from .losses import calc_joint_elbo_loss, calc_klds, calc_klds_style, calc_log_probs, calc_poe_loss
 from .mmvae import MMVaeMimic, VAEtrimodalMimic
 from .modalities import MimicLateral, MimicPA, MimicText
 from .networks import DecoderImg, DecoderText, EncoderImg, EncoderText
@@ -63,13 +63,16 @@ class Experiment:
         """experiment.py:80-92 — dict order PA, Lateral, text"""
         fl = self.flags
         mods = OrderedDict()
+        fz = bool(getattr(fl, 'factorized_representation', False))      # style latents only when factorized
+        sd = {'PA': fl.style_pa_dim if fz else 0, 'Lateral': fl.style_lat_dim if fz else 0,
+              'text': fl.style_text_dim if fz else 0}
         for m in getattr(fl, 'mods', ('PA', 'Lateral', 'text')):
             if m == 'PA':
-                mods[m] = MimicPA(EncoderImg(fl, 0), DecoderImg(fl, 0), fl)
+                mods[m] = MimicPA(EncoderImg(fl, sd['PA']), DecoderImg(fl, sd['PA']), fl)
             elif m == 'Lateral':
-                mods[m] = MimicLateral(EncoderImg(fl, 0), DecoderImg(fl, 0), fl)
+                mods[m] = MimicLateral(EncoderImg(fl, sd['Lateral']), DecoderImg(fl, sd['Lateral']), fl)
             elif m == 'text':
-                mods[m] = MimicText(EncoderText(fl, 0), DecoderText(fl, 0), fl.len_sequence, None, None, fl)
+                mods[m] = MimicText(EncoderText(fl, sd['text']), DecoderText(fl, sd['text']), fl.len_sequence, None, None, fl)
             else:
                 raise ValueError(m)
         return mods
@@ -144,10 +147,13 @@ def basic_routine_epoch(exp, batch):
     log_probs, weighted_log_prob = calc_log_probs(exp, results, batch)
     group_divergence = results['joint_divergence']
     klds = calc_klds(exp, results)
+    klds_style = calc_klds_style(exp, results) if getattr(flags, 'factorized_representation', False) else None
     if flags.modality_jsd or flags.modality_moe or flags.joint_elbo:
-        total_loss = calc_joint_elbo_loss(exp, None, group_divergence, flags.beta_style, flags.beta_content,
+        total_loss = calc_joint_elbo_loss(exp, klds_style, group_divergence, flags.beta_style, flags.beta_content,
                                           weighted_log_prob, flags.beta)
     elif flags.modality_poe:
+        if klds_style is not None:
+            raise NotImplementedError('poe with a factorized representation is not built (SURVEY.md N4)')
         total_loss = calc_poe_loss(exp, exp.modalities, group_divergence, klds, None, batch_d, mm_vae, log_probs)
     else:
         raise ValueError('no fusion method selected')

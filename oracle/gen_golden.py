@@ -47,7 +47,7 @@ def import_reference():
     return SimpleNamespace(**locals())
 
 
-CURRENT = {'masks': None, 'eps': None, 'calls': 0, 'noise': None}
+CURRENT = {'masks': None, 'eps': None, 'calls': 0, 'noise': None, 'eps_style': None, 'style_calls': 0}
 
 
 def ref_flags(fl):
@@ -56,8 +56,9 @@ def ref_flags(fl):
         device=torch.device('cpu'), batch_size=fl.batch_size, class_dim=fl.class_dim, img_size=fl.img_size,
         image_channels=fl.image_channels, DIM_img=fl.DIM_img, DIM_text=fl.DIM_text, text_encoding='char',
         len_sequence=fl.len_sequence, num_features=fl.num_features, alphabet='x' * fl.num_features,
-        feature_extractor_img='resnet', factorized_representation=False, style_pa_dim=0, style_lat_dim=0,
-        style_text_dim=0, modality_moe=(m == 'moe'), modality_jsd=(m == 'jsd'), modality_poe=(m == 'poe'),
+        feature_extractor_img='resnet', factorized_representation=O.factorized(fl),
+        style_pa_dim=O.style_dim(fl, 'PA'), style_lat_dim=O.style_dim(fl, 'Lateral'),
+        style_text_dim=O.style_dim(fl, 'text'), modality_moe=(m == 'moe'), modality_jsd=(m == 'jsd'), modality_poe=(m == 'poe'),
         joint_elbo=(m == 'joint_elbo'), poe_unimodal_elbos=True, alpha_modalities=list(fl.alpha_modalities),
         beta=fl.beta, beta_style=fl.beta_style, beta_content=fl.beta_content, dataset='testing',
         distributed=False, world_size=1, text_gen_lastlayer='softmax')
@@ -68,15 +69,16 @@ def build_reference_model(R, fl, state):
     mods = OrderedDict()
     for m in fl.mods:            # experiment.py:80-92: dict order PA, Lateral, text
         if m == 'PA':
-            mods[m] = R.MimicPA(R.EncoderImg(rf, 0), R.DecoderImg(rf, 0), rf)
+            mods[m] = R.MimicPA(R.EncoderImg(rf, rf.style_pa_dim), R.DecoderImg(rf, rf.style_pa_dim), rf)
         elif m == 'Lateral':
-            mods[m] = R.MimicLateral(R.EncoderImg(rf, 0), R.DecoderImg(rf, 0), rf)
+            mods[m] = R.MimicLateral(R.EncoderImg(rf, rf.style_lat_dim), R.DecoderImg(rf, rf.style_lat_dim), rf)
         else:
-            mods[m] = R.MimicText(R.EncoderText(rf, 0), R.DecoderText(rf, 0), rf.len_sequence, None, None, rf)
+            mods[m] = R.MimicText(R.EncoderText(rf, rf.style_text_dim), R.DecoderText(rf, rf.style_text_dim),
+                                  rf.len_sequence, None, None, rf)
     exp = SimpleNamespace(flags=rf, modalities=mods)
     exp.subsets = R.BaseExperiment.set_subsets(exp)
     exp.rec_weights = dict(fl.rec_weights)
-    exp.style_weights = {m: 1.0 for m in fl.mods}
+    exp.style_weights = dict(fl.style_weights)
 
     class GenericMMVae(R.BaseMMVae):
         """~30-line shim: VAEtrimodalMimic.forward:31-62 / encode:64-93 generalised to any
@@ -141,7 +143,14 @@ def build_reference_model(R, fl, state):
     for name, mod in vae.named_modules():
         if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
             mod.forward = (lambda x, n=name, md=mod: x * CURRENT['masks'][n] * 2.0 if md.training else x)
-    R.U.reparameterize = lambda mu, logvar: CURRENT['eps'] * torch.exp(0.5 * logvar) + mu
+    def reparameterize(mu, logvar):
+        # VAEtrimodalMimic.forward: the content sample first, then one style sample per modality in self.modalities order
+        if CURRENT['eps_style'] is not None and mu.shape[1] != fl.class_dim:
+            m = list(fl.mods)[CURRENT['style_calls'] % len(fl.mods)]
+            CURRENT['style_calls'] += 1
+            return CURRENT['eps_style'][m] * torch.exp(0.5 * logvar) + mu
+        return CURRENT['eps'] * torch.exp(0.5 * logvar) + mu
+    R.U.reparameterize = reparameterize
     exp.mm_vae = vae
     return exp
 
@@ -153,7 +162,8 @@ def reference_step(R, exp, batch):
     log_probs, weighted = R.losses.calc_log_probs(exp, results, (batch, None))
     klds = R.losses.calc_klds(exp, results)
     if fl.modality_moe or fl.joint_elbo or fl.modality_jsd:
-        total = R.losses.calc_joint_elbo_loss(exp, None, results['joint_divergence'], fl.beta_style,
+        klds_style = R.losses.calc_klds_style(exp, results) if fl.factorized_representation else None
+        total = R.losses.calc_joint_elbo_loss(exp, klds_style, results['joint_divergence'], fl.beta_style,
                                               fl.beta_content, weighted, fl.beta)
     else:
         total = R.losses.calc_poe_loss(exp, exp.modalities, results['joint_divergence'], klds, None, batch,
@@ -182,6 +192,8 @@ CASES = OrderedDict([
     ('small_tri_256_joint', dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=64, img_size=256)),
     ('small_tri_64_joint', dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=16, img_size=64)),
     ('small_tri_joint_ragged', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, actual_batch=5)),
+    ('small_tri_style', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32,
+                            style_dims={'PA': 8, 'Lateral': 16, 'text': 24})),
     ('small_tri_jsd', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, method='jsd')),
     ('small_patext_jsd', dict(batch_size=9, DIM_img=16, DIM_text=16, class_dim=32, mods=('PA', 'text'), method='jsd')),
 ])
@@ -199,8 +211,9 @@ def run_case(R, name, kw, outdir):
     batch = O.make_batch(fl, seed=1, dtype=dt, batch=B)
     noise = [O.make_noise(fl, seed=2 + i, dtype=dt, batch=B) for i in range(1 + len(fl.mods))]
     t0 = time.time()
+    eps_style = O.make_style_noise(fl, seed=2, dtype=dt, batch=B)
     # ---- reference
-    CURRENT.update(calls=0, noise=noise)
+    CURRENT.update(calls=0, noise=noise, eps_style=eps_style, style_calls=0)
     exp = build_reference_model(R, fl, state)
     exp.mm_vae.train()
     out = reference_step(R, exp, OrderedDict(batch))
@@ -212,7 +225,7 @@ def run_case(R, name, kw, outdir):
     # ---- oracle on the same data
     st2 = OrderedDict((k, v.clone()) for k, v in state.items())
     uni = {m: noise[1 + i] for i, m in enumerate(fl.mods)}
-    orc = O.step_with_grads_full(st2, batch, fl, noise[0][0], noise[0][1], uni_masks=uni)
+    orc = O.step_with_grads_full(st2, batch, fl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=eps_style)
     t2 = time.time()
 
     def rel(a, b):

@@ -42,9 +42,20 @@ def default_flags(**kw):
              method='joint_elbo', mods=('PA', 'Lateral', 'text'),
              beta=5.0, beta_style=1.0, beta_content=1.0,
              rec_weights={'PA': 0.33, 'Lateral': 0.33, 'text': 0.33},
-             alpha_modalities=[0.25, 0.25, 0.25, 0.25])
+             alpha_modalities=[0.25, 0.25, 0.25, 0.25],
+             # factorized representation (flags.py: factorized_representation, style_{pa,lat,text}_dim): modality-specific
+             # style latents next to the shared content latent; style_weights = experiment.py's beta_m*_style (1.0)
+             style_dims={'PA': 0, 'Lateral': 0, 'text': 0}, style_weights={'PA': 1.0, 'Lateral': 1.0, 'text': 1.0})
     f.update(kw)
     return SimpleNamespace(**f)
+
+
+def style_dim(flags, m):
+    return int(getattr(flags, 'style_dims', {}).get(m, 0))
+
+
+def factorized(flags):
+    return any(style_dim(flags, m) > 0 for m in flags.mods)
 
 
 # --------------------------------------------------------------------------------------
@@ -145,6 +156,11 @@ def param_spec(flags):
             for i, (ci, co, k, s, p) in enumerate(img_encoder_blocks(flags)):
                 _block_spec(spec, e + '.feature_extractor.resblock_%d.0' % (i + 1), ci, co, k, 2, False, False,
                             'downsample')
+        sd = style_dim(flags, m)
+        if sd:                                    # FeatureCompressor.py:11-16: style heads are registered first
+            for head in ('style_mu', 'style_logvar'):
+                spec[e + '.feature_compressor.%s.weight' % head] = (sd, 5 * d)
+                spec[e + '.feature_compressor.%s.bias' % head] = (sd,)
         for head in ('content_mu', 'content_logvar'):
             spec[e + '.feature_compressor.%s.weight' % head] = (D, 5 * d)
             spec[e + '.feature_compressor.%s.bias' % head] = (D,)
@@ -152,7 +168,7 @@ def param_spec(flags):
         dn = DEC_NAME[m]
         if m == 'text':
             d = flags.DIM_text
-            spec[dn + '.feature_generator.weight'] = (5 * d, D)
+            spec[dn + '.feature_generator.weight'] = (5 * d, style_dim(flags, m) + D)
             spec[dn + '.feature_generator.bias'] = (5 * d,)
             for i, (ci, co, k, s, p) in enumerate(text_decoder_blocks(flags)):
                 _block_spec(spec, dn + '.text_generator.resblock_%d.0' % (i + 1), ci, co, k, 1, True, True,
@@ -161,7 +177,7 @@ def param_spec(flags):
             spec[dn + '.text_generator.conv2.bias'] = (flags.num_features,)
         else:
             d = flags.DIM_img
-            spec[dn + '.feature_generator.weight'] = (5 * d, D)
+            spec[dn + '.feature_generator.weight'] = (5 * d, style_dim(flags, m) + D)
             spec[dn + '.feature_generator.bias'] = (5 * d,)
             blocks = img_decoder_blocks(flags)
             for i, (ci, co, k, s, p) in enumerate(blocks):
@@ -213,7 +229,8 @@ _spec_cache = {}
 
 
 def param_spec_cached(flags):
-    key = (flags.class_dim, flags.img_size, flags.DIM_img, flags.DIM_text, tuple(flags.mods), flags.num_features)
+    key = (flags.class_dim, flags.img_size, flags.DIM_img, flags.DIM_text, tuple(flags.mods), flags.num_features,
+           tuple(style_dim(flags, m) for m in flags.mods))
     if key not in _spec_cache:
         _spec_cache[key] = param_spec(flags)
     return _spec_cache[key]
@@ -287,6 +304,20 @@ def make_noise(flags, seed=2, dtype=torch.float32, batch=None):
     return masks, eps
 
 
+def make_style_noise(flags, seed=2, dtype=torch.float32, batch=None):
+    """reparameterisation eps of the style latents: modality -> [B, style_dim] (None when not factorized)"""
+    if not factorized(flags):
+        return None
+    B = batch or flags.batch_size
+    out = OrderedDict()
+    for m in flags.mods:
+        sd = style_dim(flags, m)
+        u1 = seeded_uniform('eps_style.u1.' + m, seed, (B, sd)).clamp_min(1e-12)
+        u2 = seeded_uniform('eps_style.u2.' + m, seed, (B, sd))
+        out[m] = (torch.sqrt(-2.0 * torch.log(u1)) * torch.cos(2.0 * math.pi * u2)).to(dtype)
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # networks
 # --------------------------------------------------------------------------------------
@@ -348,6 +379,20 @@ def _res_block(ctx, p, x, k, stride, pad, nd, transposed):
     return RES_A * res + RES_B * out
 
 
+def _compress(s, e, f):
+    """LinearFeatureCompressor.forward (FeatureCompressor.py:21-28); the encoders return content first, style after
+    (ConvNetworksImgMimic.py:29-36)"""
+    mu = F.linear(f, s[e + '.feature_compressor.content_mu.weight'], s[e + '.feature_compressor.content_mu.bias'])
+    lv = F.linear(f, s[e + '.feature_compressor.content_logvar.weight'],
+                  s[e + '.feature_compressor.content_logvar.bias'])
+    if e + '.feature_compressor.style_mu.weight' in s:
+        smu = F.linear(f, s[e + '.feature_compressor.style_mu.weight'], s[e + '.feature_compressor.style_mu.bias'])
+        slv = F.linear(f, s[e + '.feature_compressor.style_logvar.weight'],
+                       s[e + '.feature_compressor.style_logvar.bias'])
+        return mu, lv, smu, slv
+    return mu, lv
+
+
 def encoder_img(ctx, flags, e, x):
     """EncoderImg.forward (ConvNetworksImgMimic.py:29-36) -> FeatureExtractorImg.forward
     (FeatureExtractorImg.py:61-81) -> LinearFeatureCompressor.forward (FeatureCompressor.py:21-28)."""
@@ -355,11 +400,7 @@ def encoder_img(ctx, flags, e, x):
     h = F.conv2d(x, s[e + '.feature_extractor.conv1.weight'], None, stride=2, padding=1)
     for i, (ci, co, k, st, p) in enumerate(img_encoder_blocks(flags)):
         h = _res_block(ctx, e + '.feature_extractor.resblock_%d.0' % (i + 1), h, k, st, p, 2, False)
-    f = h.reshape(h.shape[0], -1)
-    mu = F.linear(f, s[e + '.feature_compressor.content_mu.weight'], s[e + '.feature_compressor.content_mu.bias'])
-    lv = F.linear(f, s[e + '.feature_compressor.content_logvar.weight'],
-                  s[e + '.feature_compressor.content_logvar.bias'])
-    return mu, lv
+    return _compress(s, e, h.reshape(h.shape[0], -1))
 
 
 def encoder_text(ctx, flags, e, x):
@@ -370,11 +411,7 @@ def encoder_text(ctx, flags, e, x):
                  s[e + '.feature_extractor.conv1.bias'], stride=2, padding=1)
     for i, (ci, co, k, st, p) in enumerate(text_encoder_blocks(flags)):
         h = _res_block(ctx, e + '.feature_extractor.resblock_%d.0' % (i + 1), h, k, st, p, 1, False)
-    f = h.reshape(h.shape[0], -1)
-    mu = F.linear(f, s[e + '.feature_compressor.content_mu.weight'], s[e + '.feature_compressor.content_mu.bias'])
-    lv = F.linear(f, s[e + '.feature_compressor.content_logvar.weight'],
-                  s[e + '.feature_compressor.content_logvar.bias'])
-    return mu, lv
+    return _compress(s, e, h.reshape(h.shape[0], -1))
 
 
 def decoder_img(ctx, flags, d, z):
@@ -528,7 +565,7 @@ def categorical_log_prob_sum(logits, target):
     return ln.gather(-1, idx.unsqueeze(-1)).sum()
 
 
-def forward(state, batch, flags, masks=None, eps=None, train=True, present=None):
+def forward(state, batch, flags, masks=None, eps=None, train=True, present=None, eps_style=None):
     """VAEtrimodalMimic.forward (networks/VAEtrimodalMimic.py:31-62), tolerant of missing modalities
     in the decode loop (the intended behaviour for calc_poe_loss)."""
     ctx = _Ctx(state, masks or {}, train)
@@ -539,7 +576,10 @@ def forward(state, batch, flags, masks=None, eps=None, train=True, present=None)
             enc[m] = encoder_text(ctx, flags, ENC_NAME[m], batch[m])
         else:
             enc[m] = encoder_img(ctx, flags, ENC_NAME[m], batch[m])
+    styles = OrderedDict((m, tuple(v[2:])) for m, v in enc.items() if len(v) == 4)     # VAEtrimodalMimic.encode:64-93
+    enc = OrderedDict((m, tuple(v[:2])) for m, v in enc.items())
     lat = inference(enc, flags, present)
+    lat['styles'] = styles
     # calc_group_divergence_moe (mm_div.py:90-110): the reference collects the per-subset KLs in
     # `torch.zeros(num_mods)` -- an FP32 tensor whatever the model dtype -- and the weights are FP32 too
     # (BaseMMVae.py:187), so joint_divergence is an fp32 quantity even in an fp64 run.
@@ -563,18 +603,23 @@ def forward(state, batch, flags, masks=None, eps=None, train=True, present=None)
     z = eps * torch.exp(0.5 * j_lv) + j_mu   # utils.reparameterize (utils/utils.py:45-48)
     rec = OrderedDict()
     for m in present:
+        zm = z
+        if m in styles:                   # VAEtrimodalMimic.forward:49-51 + DecoderImg.forward:47-48: cat(style, content)
+            s_mu, s_lv = styles[m]
+            e_s = eps_style[m] if eps_style is not None else torch.zeros_like(s_mu)
+            zm = torch.cat((e_s * torch.exp(0.5 * s_lv) + s_mu, z), dim=1)
         if m == 'text':
-            rec[m] = decoder_text(ctx, flags, DEC_NAME[m], z)
+            rec[m] = decoder_text(ctx, flags, DEC_NAME[m], zm)
         else:
-            rec[m] = decoder_img(ctx, flags, DEC_NAME[m], z)
+            rec[m] = decoder_img(ctx, flags, DEC_NAME[m], zm)
     return dict(latents=lat, joint_divergence=joint_div, individual_divs=klds_ind, dyn_prior=dyn_prior, z=z, rec=rec,
                 bn_updates=ctx.bn_updates)
 
 
-def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks=None):
+def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks=None, eps_style=None):
     """run_epochs.basic_routine_epoch (run_epochs.py:52-96): forward, calc_log_probs (losses.py:6-21),
     calc_klds (:24-31), calc_joint_elbo_loss (:80-89) or calc_poe_loss (:54-77, intended semantics)."""
-    res = forward(state, batch, flags, masks, eps, train)
+    res = forward(state, batch, flags, masks, eps, train, eps_style=eps_style)
     Bn = float(flags.batch_size)
     log_probs, weighted = OrderedDict(), 0.0
     for m in flags.mods:
@@ -585,9 +630,14 @@ def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks
         log_probs[m] = -lp / Bn
         weighted = weighted + flags.rec_weights[m] * log_probs[m]
     klds = OrderedDict((k, kl_to_standard_normal(mu, lv, Bn)) for k, (mu, lv) in res['latents']['subsets'].items())
+    # calc_klds_style (losses.py:34-42) + calc_style_kld (:45-51)
+    klds_style = OrderedDict((m + '_style', kl_to_standard_normal(mu, lv, Bn)) for m, (mu, lv) in res['latents']['styles'].items())
+    kld_style = sum(flags.style_weights[m] * klds_style[m + '_style'] for m in flags.mods) if klds_style else 0.0
     if flags.method in ('moe', 'jsd', 'joint_elbo'):
-        total = weighted + flags.beta * (flags.beta_style * 0.0 + flags.beta_content * res['joint_divergence'])
+        total = weighted + flags.beta * (flags.beta_style * kld_style + flags.beta_content * res['joint_divergence'])
     elif flags.method == 'poe':
+        if klds_style:
+            raise NotImplementedError('poe with a factorized representation')
         total = weighted + flags.beta * flags.beta_content * res['joint_divergence']   # calc_elbo 'joint'
         state2 = dict(state)              # the unimodal passes see the BN buffers the joint pass updated
         state2.update(res['bn_updates'])
@@ -600,16 +650,17 @@ def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks
                 res['bn_updates'][k] = v
     else:
         raise NotImplementedError(flags.method)
-    return dict(results=res, log_probs=log_probs, klds=klds, total_loss=total, weighted_log_prob=weighted)
+    return dict(results=res, log_probs=log_probs, klds=klds, klds_style=klds_style, total_loss=total,
+                weighted_log_prob=weighted)
 
 
-def step_with_grads(state, batch, flags, masks=None, eps=None, uni_masks=None):
+def step_with_grads(state, batch, flags, masks=None, eps=None, uni_masks=None, eps_style=None):
     """One train-mode step: losses + d(total_loss)/d(param) for every float parameter."""
     params = {k: v for k, v in state.items() if v.is_floating_point() and 'running_' not in k}
     for v in params.values():
         v.requires_grad_(True)
         v.grad = None
-    out = step_losses(state, batch, flags, masks, eps, True, uni_masks=uni_masks)
+    out = step_losses(state, batch, flags, masks, eps, True, uni_masks=uni_masks, eps_style=eps_style)
     out['total_loss'].backward()
     grads = OrderedDict((k, v.grad.detach().clone()) for k, v in params.items())
     for v in params.values():

@@ -21,7 +21,9 @@ def product_flags(ofl, compute_dtype, device='cuda'):
     return P.default_flags(device=torch.device(device), batch_size=ofl.batch_size, class_dim=ofl.class_dim,
                            img_size=ofl.img_size, DIM_img=ofl.DIM_img, DIM_text=ofl.DIM_text,
                            len_sequence=ofl.len_sequence, num_features=ofl.num_features, method=ofl.method,
-                           mods=tuple(ofl.mods), beta=ofl.beta, compute_dtype=compute_dtype)
+                           mods=tuple(ofl.mods), beta=ofl.beta, compute_dtype=compute_dtype,
+                           factorized_representation=O.factorized(ofl), style_pa_dim=O.style_dim(ofl, 'PA'),
+                           style_lat_dim=O.style_dim(ofl, 'Lateral'), style_text_dim=O.style_dim(ofl, 'text'))
 
 
 def masks_to_product(masks, device):
@@ -41,13 +43,14 @@ def make_case(kw, actual_batch=None, dtype=torch.float32, seeds=(0, 1, 2)):
     state = O.make_state(ofl, seeds[0], dtype)
     batch = O.make_batch(ofl, seeds[1], dtype, B)
     noise = [O.make_noise(ofl, seeds[2] + i, dtype, B) for i in range(1 + len(ofl.mods))]
+    ofl.eps_style = O.make_style_noise(ofl, seeds[2], dtype, B)        # None unless the case is factorized
     return ofl, state, batch, noise
 
 
 def run_oracle(ofl, state, batch, noise):
     st = OrderedDict((k, v.clone()) for k, v in state.items())
     uni = {m: noise[1 + i] for i, m in enumerate(ofl.mods)}
-    return O.step_with_grads(st, batch, ofl, noise[0][0], noise[0][1], uni_masks=uni)
+    return O.step_with_grads(st, batch, ofl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=getattr(ofl, 'eps_style', None))
 
 
 def run_product(ofl, state, batch, noise, compute_dtype):
@@ -59,7 +62,9 @@ def run_product(ofl, state, batch, noise, compute_dtype):
     exp.set_optimizer()        # flattens params/grads
     vae.train()
     dev = fl.device
-    vae.rt.schedule = [(masks_to_product(m, dev), e.float().to(dev)) for m, e in noise]
+    es = getattr(ofl, 'eps_style', None)
+    es = {m: v.float().to(dev) for m, v in es.items()} if es is not None else None
+    vae.rt.schedule = [(masks_to_product(m, dev), e.float().to(dev), es) for m, e in noise]
     b = OrderedDict((k, v.float().to(dev)) for k, v in batch.items())
     out = P.basic_routine_epoch(exp, (b, None))
     exp.optimizer.zero_grad()
@@ -83,7 +88,9 @@ def smooth_grads(ofl, state, batch, noise, compute_dtype):
             v.requires_grad_(True)
         b = OrderedDict((k, v.to(dt)) for k, v in batch.items())
         masks = {k: v.to(dt) for k, v in noise[0][0].items()}
-        res = O.forward(st, b, ofl, masks, noise[0][1].to(dt), True)
+        es = getattr(ofl, 'eps_style', None)
+        res = O.forward(st, b, ofl, masks, noise[0][1].to(dt), True,
+                        eps_style={m: v.to(dt) for m, v in es.items()} if es is not None else None)
         loss = sum((r ** 2).mean() for r in res['rec'].values()) * 100.0 + 5.0 * res['joint_divergence']
         loss.backward()
         return loss, OrderedDict((k, v.grad.detach().clone()) for k, v in params.items())
@@ -97,7 +104,9 @@ def smooth_grads(ofl, state, batch, noise, compute_dtype):
     exp.set_optimizer()
     vae.train()
     dev = fl.device
-    vae.rt.schedule = [(masks_to_product(noise[0][0], dev), noise[0][1].float().to(dev))]
+    es = getattr(ofl, 'eps_style', None)
+    es = {m: v.float().to(dev) for m, v in es.items()} if es is not None else None
+    vae.rt.schedule = [(masks_to_product(noise[0][0], dev), noise[0][1].float().to(dev), es)]
     out = vae(OrderedDict((k, v.float().to(dev)) for k, v in batch.items()))
     recs = []
     for m, r in out['rec'].items():
@@ -132,6 +141,9 @@ def compare_step(orc, out, grads, state_after=None):
         errs['sub_mu.' + k] = rel_err(plat['subsets'][k][0], mu)
         errs['sub_lv.' + k] = rel_err(plat['subsets'][k][1], lv)
     errs['joint_mu'] = rel_err(plat['joint'][0], olat['joint'][0])
+    for m, (smu, slv) in olat.get('styles', {}).items():
+        errs['style_mu.' + m] = rel_err(plat['modalities'][m + '_style'][0], smu)
+        errs['style_lv.' + m] = rel_err(plat['modalities'][m + '_style'][1], slv)
     errs['mus'] = rel_err(plat['mus'], olat['mus'])
     errs['ind_divs'] = rel_err(out['results']['individual_divs'], orc['results']['individual_divs'])
     if orc['results'].get('dyn_prior') is not None:

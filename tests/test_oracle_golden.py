@@ -25,7 +25,8 @@ def run_oracle(fx, dtype=torch.float64):
     batch = O.make_batch(fl, fx['seeds']['batch'], dtype, B)
     noise = [O.make_noise(fl, fx['seeds']['noise'] + i, dtype, B) for i in range(1 + len(fl.mods))]
     uni = {m: noise[1 + i] for i, m in enumerate(fl.mods)}
-    return fl, st, O.step_with_grads(st, batch, fl, noise[0][0], noise[0][1], uni_masks=uni)
+    es = O.make_style_noise(fl, fx['seeds']['noise'], dtype, B)
+    return fl, st, O.step_with_grads(st, batch, fl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=es)
 
 
 def check_checksum(t, cs, rtol, scale=0.0):
