@@ -181,3 +181,36 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in line['config']
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in _lib.py must have the same size and field offsets as the structs of include/mopoe_b200.h
+    (compiled here with gcc): a silent mismatch would corrupt every call through the ABI."""
+    import ctypes as C
+    from mopoe_mimic_b200 import _lib as L
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [('mopoe_view_t', L.View, ['ptr', 'dtype', 'B', 'C', 'ph', 'sB', 'sW']),
+             ('mopoe_window_t', L.Window, ['a', 'E0', 'R', 'KW', 'a_off', 'sAr']),
+             ('mopoe_rows_t', L.Rows, ['d', 'N', 'd_off', 's2']),
+             ('mopoe_fusion_cfg_t', L.FusionCfg, ['M', 'fuse_mode', 'members', 'stacked', 'sel_end', 'mem_cnt', 'mem_idx',
+                                                  'mem_end', 'norm']),
+             ('mopoe_pack_job_t', L.PackJob, ['W', 'dst', 'A', 'bpad', 'tile0', 'nx']),
+             ('mopoe_dp_peers_t', L.DpPeers, ['grad', 'param', 'flags'])]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "mopoe_b200.h"', 'int main(void) {']
+    for cname, _, fields in pairs:
+        src.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for f in fields:
+            src.append('  printf(" %%zu", offsetof(%s, %s));' % (cname, f))
+        src.append('  printf("\\n");')
+    src += ['  return 0;', '}']
+    cfile = tmp_path / 'abi.c'
+    cfile.write_text('\n'.join(src))
+    exe = tmp_path / 'abi'
+    subprocess.run(['gcc', '-I', os.path.join(root, 'include'), str(cfile), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    for line, (cname, ct, fields) in zip(out, pairs):
+        parts = line.split()
+        assert parts[0] == cname
+        assert int(parts[1]) == C.sizeof(ct), (cname, parts[1], C.sizeof(ct))
+        for f, off in zip(fields, parts[2:]):
+            assert int(off) == getattr(ct, f).offset, (cname, f, off, getattr(ct, f).offset)
