@@ -173,8 +173,11 @@ int mopoe_conv3x3s2_c1_fwd(const float* x, const float* w, int B, int H, int W, 
 int mopoe_conv3x3s2_c1_wgrad(const float* x, const mopoe_view_t* dy, int B, int H, int W, float* dw,
                              int accumulate, double* ws, int nchunk, void* stream);
 /* last deconv nn.ConvTranspose2d(C, 1, 3, stride 2, pad 1, output_padding 1) (DataGeneratorImg.py:84-90)
- * x view [B, H, W, C]; w fp32 [C,1,3,3]; out fp32 [B,1,2H,2W]. */
-int mopoe_deconv3x3s2_c1_fwd(const mopoe_view_t* x, const float* w, const float* bias, float* out, void* stream);
+ * x view [B, H, W, C]; w fp32 [C,1,3,3]; out fp32 [B,1,2H,2W].  ws (mopoe_deconv3x3s2_c1_fwd_ws bytes, 16-B aligned):
+ * per-pixel tap products of the two-phase form; ws == NULL selects the single-kernel form. */
+size_t mopoe_deconv3x3s2_c1_fwd_ws(const mopoe_view_t* x);
+int mopoe_deconv3x3s2_c1_fwd(const mopoe_view_t* x, const float* w, const float* bias, float* out, void* ws,
+                             size_t ws_bytes, void* stream);
 /* given dout fp32 [B,1,2H,2W]: dx view, dw fp32 [C,1,3,3], dbias[1]. ws: nchunk*(9*C+1) doubles. */
 int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, const float* dout, const mopoe_view_t* dx,
                              float* dw, float* dbias, int accumulate, double* ws, int nchunk, void* stream);

@@ -80,7 +80,8 @@ SIGNATURES = {
     'mopoe_adam_flat_dev': (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),
     'mopoe_conv3x3s2_c1_fwd': (_I, [_P, _P, _I, _I, _I, _V, _P]),
     'mopoe_conv3x3s2_c1_wgrad': (_I, [_P, _V, _I, _I, _I, _P, _I, _P, _I, _P]),
-    'mopoe_deconv3x3s2_c1_fwd': (_I, [_V, _P, _P, _P, _P]),
+    'mopoe_deconv3x3s2_c1_fwd_ws': (_S, [_V]),
+    'mopoe_deconv3x3s2_c1_fwd': (_I, [_V, _P, _P, _P, _P, _S, _P]),
     'mopoe_deconv3x3s2_c1_bwd': (_I, [_V, _P, _P, _V, _P, _P, _I, _P, _I, _P]),
     'mopoe_fusion_fwd': (_I, [C.POINTER(FusionCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mopoe_fusion_bwd': (_I, [C.POINTER(FusionCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

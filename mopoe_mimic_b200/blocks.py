@@ -288,7 +288,10 @@ class ImgLastFn(torch.autograd.Function):
         Cc = w.shape[0]
         x = Act.like(x_t, B, H, W, Cc)
         out = eng.f32(B, 1, 2 * H, 2 * W)
-        L.call('mopoe_deconv3x3s2_c1_fwd', C.byref(x.view()), L.ptr(w), L.ptr(bias), L.ptr(out), L.stream_ptr())
+        nbytes = L.load().mopoe_deconv3x3s2_c1_fwd_ws(C.byref(x.view()))
+        ws = eng.wsf(nbytes)
+        L.call('mopoe_deconv3x3s2_c1_fwd', C.byref(x.view()), L.ptr(w), L.ptr(bias), L.ptr(out), L.ptr(ws), nbytes,
+               L.stream_ptr())
         ctx.save_for_backward(x_t, w)
         ctx.eng, ctx.geo = eng, (B, H, W)
         return out

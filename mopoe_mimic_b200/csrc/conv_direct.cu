@@ -316,18 +316,131 @@ __global__ void __launch_bounds__(256) deconv3x3s2_c1_fwd_kernel(DView<const T> 
         }
     }
 }
-extern "C" int mopoe_deconv3x3s2_c1_fwd(const mopoe_view_t* x, const float* w, const float* bias, float* out,
-                                        void* stream) {
-    MOPOE_REQUIRE(x->C % 4 == 0, "deconv3x3s2_c1_fwd: C=%d", x->C);
-    long long quads = (long long)x->B * x->H * x->W;
-    long long blocks = ceil_div64(quads, 8 * 8);          // ~8 quads per warp
-    if (blocks > 148 * 32) blocks = 148 * 32;
+// Two-phase form of the same layer (the default): phase A computes, for every INPUT pixel, the 9 channel dot products
+//   p[k] = sum_c x[b,t,s,c] * w[c,k]      (one thread per pixel walking its 256 contiguous bytes; the [C][9] filter is
+// read from shared memory as warp-wide broadcasts; 2 pixels per thread share each filter read; packed FFMA2)
+// and phase B assembles each 2x2 output quad from the taps of its (up to) 4 source pixels.  Every activation byte is
+// read exactly once and there is no cross-lane reduction: the warp-per-quad kernel above spends its time in a 7-deep
+// shuffle chain and 4x neighbour re-reads (0.47 ms for a 268 MB input; HBM floor 0.05 ms).
+constexpr int TAPS_STRIDE = 12;      // 9 taps padded to 3 float4
+template <typename T>
+__global__ void __launch_bounds__(128) deconv_taps_kernel(DView<const T> x, const float* __restrict__ w,
+                                                          float* __restrict__ taps, long long pixels) {
+    extern __shared__ float wsm[];                   // [C][12]
+    const int C = x.C;
+    for (int i = threadIdx.x; i < C * TAPS_STRIDE; i += 128) {
+        const int c = i / TAPS_STRIDE, k = i - c * TAPS_STRIDE;
+        wsm[i] = k < 9 ? w[c * 9 + k] : 0.f;
+    }
+    __syncthreads();
+    const long long half = (pixels + 1) / 2;
+    for (long long p0 = (long long)blockIdx.x * 128 + threadIdx.x; p0 < half; p0 += (long long)gridDim.x * 128) {
+        const long long p1 = p0 + half;
+        const bool has1 = p1 < pixels;
+        const T* xp[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long pp = u == 0 ? p0 : (has1 ? p1 : p0);
+            const int s_ = (int)(pp % x.W);
+            const long long t2 = pp / x.W;
+            const int t_ = (int)(t2 % x.H), b_ = (int)(t2 / x.H);
+            xp[u] = x.p + (long long)b_ * x.sB + (long long)t_ * x.sH + (long long)s_ * x.sW;
+        }
+        float2 acc[2][5];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc[u][k] = make_float2(0.f, 0.f);
+        for (int c0 = 0; c0 < C; c0 += CV8) {
+            float xv[2][CV8];
+            ld8<T>(xp[0] + c0, xv[0]);
+            ld8<T>(xp[1] + c0, xv[1]);
+#pragma unroll
+            for (int i = 0; i < CV8; ++i) {
+                const float4 wa = *reinterpret_cast<const float4*>(wsm + (c0 + i) * TAPS_STRIDE);
+                const float4 wb = *reinterpret_cast<const float4*>(wsm + (c0 + i) * TAPS_STRIDE + 4);
+                const float4 wc = *reinterpret_cast<const float4*>(wsm + (c0 + i) * TAPS_STRIDE + 8);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float2 xx = make_float2(xv[u][i], xv[u][i]);
+                    acc[u][0] = __ffma2_rn(xx, make_float2(wa.x, wa.y), acc[u][0]);
+                    acc[u][1] = __ffma2_rn(xx, make_float2(wa.z, wa.w), acc[u][1]);
+                    acc[u][2] = __ffma2_rn(xx, make_float2(wb.x, wb.y), acc[u][2]);
+                    acc[u][3] = __ffma2_rn(xx, make_float2(wb.z, wb.w), acc[u][3]);
+                    acc[u][4] = __ffma2_rn(xx, make_float2(wc.x, wc.y), acc[u][4]);     // wc.y is the zero pad
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has1) break;
+            float4* o = reinterpret_cast<float4*>(taps + (u == 0 ? p0 : p1) * TAPS_STRIDE);
+            o[0] = make_float4(acc[u][0].x, acc[u][0].y, acc[u][1].x, acc[u][1].y);
+            o[1] = make_float4(acc[u][2].x, acc[u][2].y, acc[u][3].x, acc[u][3].y);
+            o[2] = make_float4(acc[u][4].x, 0.f, 0.f, 0.f);
+        }
+    }
+}
+// out(2t,2s) = p11(t,s);  out(2t,2s+1) = p12(t,s) + p10(t,s+1);  out(2t+1,2s) = p21(t,s) + p01(t+1,s);
+// out(2t+1,2s+1) = p22(t,s) + p20(t,s+1) + p02(t+1,s) + p00(t+1,s+1)        (p_kykx = taps[ky*3+kx])
+__global__ void __launch_bounds__(256) deconv_assemble_kernel(const float* __restrict__ taps, const float* __restrict__ bias,
+                                                              float* __restrict__ out, int H, int W, long long quads) {
+    const float bb = bias[0];
+    for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < quads; q += (long long)gridDim.x * 256) {
+        const int s = (int)(q % W);
+        const long long t2 = q / W;
+        const int t = (int)(t2 % H);
+        const long long b = t2 / H;
+        const bool rs = s + 1 < W, dn = t + 1 < H;
+        const float* p = taps + q * TAPS_STRIDE;
+        const float* pr = p + TAPS_STRIDE;
+        const float* pd = p + (long long)W * TAPS_STRIDE;
+        const float4 a0 = *reinterpret_cast<const float4*>(p), a1 = *reinterpret_cast<const float4*>(p + 4);
+        const float a8 = p[8];
+        float o00 = a1.x, o01 = a1.y, o10 = a1.w, o11 = a8;        // p11, p12, p21, p22
+        if (rs) { o01 += pr[3]; o11 += pr[6]; }                    // p10, p20 of (t, s+1)
+        if (dn) { o10 += pd[1]; o11 += pd[2]; }                    // p01, p02 of (t+1, s)
+        if (rs && dn) o11 += pd[TAPS_STRIDE];                      // p00 of (t+1, s+1)
+        (void)a0;
+        const int OW = 2 * W;
+        float* ob = out + (b * 2 * H + 2 * t) * OW + 2 * s;
+        *reinterpret_cast<float2*>(ob) = make_float2(o00 + bb, o01 + bb);
+        *reinterpret_cast<float2*>(ob + OW) = make_float2(o10 + bb, o11 + bb);
+    }
+}
+extern "C" size_t mopoe_deconv3x3s2_c1_fwd_ws(const mopoe_view_t* x) {
+    return (size_t)x->B * x->H * x->W * TAPS_STRIDE * sizeof(float);
+}
+extern "C" int mopoe_deconv3x3s2_c1_fwd(const mopoe_view_t* x, const float* w, const float* bias, float* out, void* ws,
+                                        size_t ws_bytes, void* stream) {
+    MOPOE_REQUIRE(x->C % CV8 == 0, "deconv3x3s2_c1_fwd: C=%d", x->C);
+    const long long quads = (long long)x->B * x->H * x->W;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ws == nullptr) {                 // no workspace: single-kernel warp-per-quad form
+        long long blocks = ceil_div64(quads, 8 * 8);
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        if (blocks < 1) blocks = 1;
+        MOPOE_DISPATCH_T(x->dtype, T, {
+            deconv3x3s2_c1_fwd_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(make_dview<const T>(x), w, bias, out, quads);
+        });
+        MOPOE_CHECK_LAUNCH("deconv3x3s2_c1_fwd");
+        return 0;
+    }
+    MOPOE_REQUIRE(ws_bytes >= mopoe_deconv3x3s2_c1_fwd_ws(x), "deconv3x3s2_c1_fwd: workspace %zu too small", ws_bytes);
+    MOPOE_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 15) == 0, "deconv3x3s2_c1_fwd: unaligned workspace");
+    long long blocks = ceil_div64((quads + 1) / 2, 128);
+    if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
+    const size_t smem = (size_t)x->C * TAPS_STRIDE * sizeof(float);
+    MOPOE_REQUIRE(smem <= 48 * 1024, "deconv3x3s2_c1_fwd: C=%d too large for the filter stage", x->C);
     MOPOE_DISPATCH_T(x->dtype, T, {
-        deconv3x3s2_c1_fwd_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(make_dview<const T>(x), w, bias, out,
-                                                                                        quads);
+        deconv_taps_kernel<T><<<(unsigned)blocks, 128, smem, st>>>(make_dview<const T>(x), w, (float*)ws, quads);
     });
-    MOPOE_CHECK_LAUNCH("deconv3x3s2_c1_fwd");
+    MOPOE_CHECK_LAUNCH("deconv_taps");
+    long long b2 = ceil_div64(quads, 256);
+    if (b2 > 148 * 16) b2 = 148 * 16;
+    deconv_assemble_kernel<<<(unsigned)b2, 256, 0, st>>>((const float*)ws, bias, out, x->H, x->W, quads);
+    MOPOE_CHECK_LAUNCH("deconv_assemble");
     return 0;
 }
 

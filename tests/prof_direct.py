@@ -45,7 +45,10 @@ def main():
     xa = Act(torch.randn(B, H // 2, H // 2, Cc, device='cuda', dtype=dt), B, H // 2, H // 2, Cc, 0, 0)
     bias = torch.zeros(1, device='cuda')
     out = torch.empty(B, 1, H, H, device='cuda')
-    ms = timeit(lambda: L.call('mopoe_deconv3x3s2_c1_fwd', C.byref(xa.view()), L.ptr(w), L.ptr(bias), L.ptr(out), L.stream_ptr()))
+    nb = L.load().mopoe_deconv3x3s2_c1_fwd_ws(C.byref(xa.view()))
+    wsd = eng.wsf(nb)
+    ms = timeit(lambda: L.call('mopoe_deconv3x3s2_c1_fwd', C.byref(xa.view()), L.ptr(w), L.ptr(bias), L.ptr(out), L.ptr(wsd), nb,
+                               L.stream_ptr()))
     print('deconv3x3s2_c1_fwd %.3f ms  (reads %.0f MB -> %.0f GB/s)' % (ms, mb, mb / ms))
     dx = Act.empty(B, H // 2, H // 2, Cc, 0, 0, dt, 'cuda')
     db = torch.zeros(1, device='cuda')
