@@ -76,6 +76,31 @@ __device__ __forceinline__ void fma_taps(const float (&tap)[9], const float (&w)
     for (int j = 0; j < 4; ++j) { o[2 * j] = acc[j].x; o[2 * j + 1] = acc[j].y; }
 }
 
+// 8 consecutive channels kept packed between the load and the use
+template <typename T>
+struct Packed8;
+template <>
+struct Packed8<bf16> {
+    uint4 v;
+    __device__ __forceinline__ void load(const bf16* p) { v = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void unpack(float (&o)[8]) const {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+};
+template <>
+struct Packed8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float* p) {
+        a = reinterpret_cast<const float4*>(p)[0];
+        b = reinterpret_cast<const float4*>(p)[1];
+    }
+    __device__ __forceinline__ void unpack(float (&o)[8]) const {
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+    }
+};
+
 // stage w[C][9] -> smem [9][C]
 __device__ __forceinline__ void stage_filter(const float* __restrict__ w, float* ws, int C) {
     for (int i = threadIdx.x + threadIdx.y * blockDim.x; i < 9 * C; i += blockDim.x * blockDim.y) {
@@ -165,39 +190,45 @@ __global__ void __launch_bounds__(256, 2) tap_grad_kernel(DView<const T> v, cons
 #pragma unroll
         for (int i = 0; i < CV8; ++i) acc[t][i] = 0.f;
     if (cvalid) {
-        constexpr int U = 2;                             // rows in flight per thread: the pass is latency-bound
+        // The pass is latency-bound: what matters is bytes in flight per SM.  The activation octets of U rows are
+        // prefetched PACKED (4 registers each for bf16) before the first use; the 9 scalar taps of a row are L1 hits and
+        // are loaded just in time, so they do not occupy registers while the activation loads are outstanding.
+        constexpr int U = sizeof(T) == 2 ? 8 : 4;
         for (unsigned r0 = row_begin + ty; r0 < row_end; r0 += U * gstride) {
-            float g[U][CV8], sv[U][9];
+            Packed8<T> g[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const unsigned r = r0 + u * gstride;
-                const bool ok = r < row_end;
-                const unsigned rr = ok ? r : 0u;
-                int px = (int)(rr % (unsigned)v.W);
-                unsigned t2 = rr / (unsigned)v.W;
-                int py = (int)(t2 % (unsigned)v.H);
-                int b = (int)(t2 / (unsigned)v.H);
-                if (ok) {
-                    ld8<T>(v.p + (long long)b * v.sB + (long long)py * v.sH + (long long)px * v.sW + c, g[u]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < CV8; ++i) g[u][i] = 0.f;
+                if (r < row_end) {
+                    unsigned px, t2, py, b;
+                    v.fW.divmod(r, t2, px);
+                    v.fH.divmod(t2, b, py);
+                    g[u].load(v.p + (long long)b * v.sB + (long long)py * v.sH + (long long)px * v.sW + c);
                 }
-                load_taps(s + (long long)b * SH * SW, SW, py, px, sv[u]);      // (row 0 when !ok: g is zero there)
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u)
+            for (int u = 0; u < U; ++u) {
+                const unsigned r = r0 + u * gstride;
+                if (r < row_end) {
+                    unsigned px, t2, py, b;
+                    v.fW.divmod(r, t2, px);
+                    v.fH.divmod(t2, b, py);
+                    float sv[9], gf[CV8];
+                    load_taps(s + (long long)b * SH * SW, SW, (int)py, (int)px, sv);
+                    g[u].unpack(gf);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const float2 tv = make_float2(sv[u][t], sv[u][t]);
+                    for (int t = 0; t < 9; ++t) {
+                        const float2 tv = make_float2(sv[t], sv[t]);
 #pragma unroll
-                    for (int j = 0; j < CV8 / 2; ++j) {
-                        const float2 r = __ffma2_rn(make_float2(g[u][2 * j], g[u][2 * j + 1]), tv,
-                                                    make_float2(acc[t][2 * j], acc[t][2 * j + 1]));
-                        acc[t][2 * j] = r.x;
-                        acc[t][2 * j + 1] = r.y;
+                        for (int j = 0; j < CV8 / 2; ++j) {
+                            const float2 rr = __ffma2_rn(make_float2(gf[2 * j], gf[2 * j + 1]), tv,
+                                                         make_float2(acc[t][2 * j], acc[t][2 * j + 1]));
+                            acc[t][2 * j] = rr.x;
+                            acc[t][2 * j + 1] = rr.y;
+                        }
                     }
                 }
+            }
         }
     }
     // rows per thread <= rpc/16 (a few hundred): fp32 strip sums, combined across the 16 row lanes in fp64
