@@ -71,8 +71,8 @@ class Engine:
             raise RuntimeError('mopoe_mimic_b200 needs a CUDA device (sm_100a); no CPU fallback exists')
         self.dtype = dtype
         self.impl = impl
-        self._ws64 = None
-        self._wsf = None
+        self._ws64 = {}      # scratch per CUDA stream: the modality branches run concurrently on their own streams
+        self._wsf = {}
         self.rng_offset = 0
         self.rng_step = torch.zeros(1, dtype=torch.int64, device=self.device)
         # arrival counters for the library's fused-finalize path (last block finalises).  Measured SLOWER on B200 than
@@ -174,15 +174,19 @@ class Engine:
 
     # ---- scratch ------------------------------------------------------------------------------------
     def ws64(self, n):
-        if self._ws64 is None or self._ws64.numel() < n:
-            self._ws64 = torch.empty(max(n, 1 << 16), dtype=torch.float64, device=self.device)
-        return self._ws64
+        key = torch.cuda.current_stream().cuda_stream
+        buf = self._ws64.get(key)
+        if buf is None or buf.numel() < n:
+            buf = self._ws64[key] = torch.empty(max(n, 1 << 16), dtype=torch.float64, device=self.device)
+        return buf
 
     def wsf(self, nbytes):
         n = (nbytes + 3) // 4
-        if self._wsf is None or self._wsf.numel() < n:
-            self._wsf = torch.empty(max(n, 1 << 20), dtype=torch.float32, device=self.device)
-        return self._wsf
+        key = torch.cuda.current_stream().cuda_stream
+        buf = self._wsf.get(key)
+        if buf is None or buf.numel() < n:
+            buf = self._wsf[key] = torch.empty(max(n, 1 << 20), dtype=torch.float32, device=self.device)
+        return buf
 
     @staticmethod
     def nchunk(rows, C_, per=1):

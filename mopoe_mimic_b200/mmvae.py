@@ -250,12 +250,62 @@ class MMVaeMimic(BaseMMVae):
                 object.__setattr__(net, 'prefix', nm)
         self.to(flags.device)
 
+    # ---- modality branches on their own CUDA streams ---------------------------------------------------------------
+    # The encoders (and the decoders) of the modalities are independent until the fusion (the loss).  Their deep stages
+    # are chains of tiny launches that leave most of the 148 SMs idle, so each branch runs on its own stream: the big
+    # kernels of one branch fill the gaps of the others.  Autograd replays every backward node on its forward stream, so
+    # the backward pass overlaps the same way; under CUDA-graph capture the branches become parallel graph branches.
+    def _branches(self, names, fn):
+        """run fn(name) for every name, name i > 0 on side stream i; returns {name: result}; joined on return"""
+        import os
+        cur = torch.cuda.current_stream()
+        if len(names) <= 1 or os.environ.get('MOPOE_BRANCH_STREAMS', '1') == '0':
+            return {n: fn(n) for n in names}
+        side = self.__dict__.setdefault('_side_streams', [])
+        while len(side) < len(names) - 1:
+            side.append(torch.cuda.Stream())
+        out = {}
+        for i, n in enumerate(names):
+            if i == 0:
+                continue
+            st = side[i - 1]
+            st.wait_stream(cur)                       # fork: everything enqueued so far (inputs, packed weights) is visible
+            with torch.cuda.stream(st):
+                out[n] = fn(n)
+        out[names[0]] = fn(names[0])                  # the first branch stays on the ambient stream
+        for i in range(1, len(names)):
+            cur.wait_stream(side[i - 1])              # join
+        return out
+
+    def join_branches(self):
+        """make the ambient stream wait for every branch stream (after backward: kernels of our autograd nodes write
+        parameter gradients on the branch streams without an AccumulateGrad node the engine would sync on)"""
+        cur = torch.cuda.current_stream()
+        for st in self.__dict__.get('_side_streams', []):
+            cur.wait_stream(st)
+
+    @staticmethod
+    def _touch(stream, *tensors):
+        """tensors allocated on one stream and consumed on another: tell the caching allocator"""
+        for t in tensors:
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(stream)
+
     def encode(self, input_batch):
         latents = {}
+        present = [m for m in self.modalities if m in input_batch]
+        cur = torch.cuda.current_stream()
+
+        def run(m):
+            L.require_cuda(input_batch[m])
+            self._touch(torch.cuda.current_stream(), input_batch[m])
+            out = getattr(self, ENC_NAME[m])(input_batch[m])
+            self._touch(cur, *out)
+            return out
+        outs = self._branches(present, run)
         for m in self.modalities:
             if m in input_batch:
-                L.require_cuda(input_batch[m])
-                out = getattr(self, ENC_NAME[m])(input_batch[m])
+                out = outs[m]
                 if len(out) == 4:                  # VAEtrimodalMimic.encode:64-93: content first, style after
                     latents[m + '_style'] = list(out[2:])
                 latents[m] = list(out[:2])
@@ -314,14 +364,25 @@ class MMVaeMimic(BaseMMVae):
         factorized = bool(getattr(self.flags, 'factorized_representation', False))
         if factorized:
             latents['_klds_style'] = {}
+        cur = torch.cuda.current_stream()
+
+        def run(m_key):
+            s_emb, kl_s = None, None
+            self._touch(torch.cuda.current_stream(), class_embeddings)
+            if factorized:              # VAEtrimodalMimic.forward:49-51: s_emb = reparameterize(style mu, logvar)
+                s_mu, s_lv = latents['modalities'][m_key + '_style']
+                self._touch(torch.cuda.current_stream(), s_mu, s_lv)
+                s_emb, kl_s = self._style_sample(m_key, s_mu, s_lv)
+                self._touch(cur, kl_s)
+            rec = self._decode(m_key, class_embeddings, s_emb)
+            self._touch(cur, rec._scores if m_key == 'text' else rec.loc)
+            return rec, kl_s
+        decs = self._branches([m for m in self.modalities if m in input_batch and input_batch[m] is not None], run)
         for m_key in self.modalities:
-            if m_key in input_batch and input_batch[m_key] is not None:
-                s_emb = None
-                if factorized:          # VAEtrimodalMimic.forward:49-51: s_emb = reparameterize(style mu, logvar)
-                    s_mu, s_lv = latents['modalities'][m_key + '_style']
-                    s_emb, kl_s = self._style_sample(m_key, s_mu, s_lv)
+            if m_key in decs:
+                results_rec[m_key], kl_s = decs[m_key]
+                if factorized:
                     latents['_klds_style'][m_key + '_style'] = kl_s
-                results_rec[m_key] = self._decode(m_key, class_embeddings, s_emb)
         results['rec'] = results_rec
         return results
 

@@ -168,6 +168,8 @@ def forward_backward(exp, batch):
     out = basic_routine_epoch(exp, batch)
     exp.optimizer.zero_grad()
     out['total_loss'].backward()
+    if hasattr(exp.mm_vae, 'join_branches'):
+        exp.mm_vae.join_branches()
     return out
 
 
