@@ -265,6 +265,7 @@ class MMVaeMimic(BaseMMVae):
         while len(side) < len(names) - 1:
             side.append(torch.cuda.Stream())
         out = {}
+        self.__dict__['_side_used'] = max(self.__dict__.get('_side_used', 0), len(names) - 1)
         for i, n in enumerate(names):
             if i == 0:
                 continue
@@ -281,8 +282,11 @@ class MMVaeMimic(BaseMMVae):
         """make the ambient stream wait for every branch stream (after backward: kernels of our autograd nodes write
         parameter gradients on the branch streams without an AccumulateGrad node the engine would sync on)"""
         cur = torch.cuda.current_stream()
-        for st in self.__dict__.get('_side_streams', []):
+        # only streams forked since the last join: waiting on an idle stream from a CAPTURING stream invalidates the capture
+        used = self.__dict__.get('_side_used', 0)
+        for st in self.__dict__.get('_side_streams', [])[:used]:
             cur.wait_stream(st)
+        self.__dict__['_side_used'] = 0
 
     @staticmethod
     def _touch(stream, *tensors):
