@@ -214,3 +214,38 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert int(parts[1]) == C.sizeof(ct), (cname, parts[1], C.sizeof(ct))
         for f, off in zip(fields, parts[2:]):
             assert int(off) == getattr(ct, f).offset, (cname, f, off, getattr(ct, f).offset)
+
+
+def test_jsd_plan_has_a_prior_component_and_exact_ranges():
+    """jsd mode: the joint mixture has M+1 components (unimodal posteriors + the N(0,I) prior, BaseMMVae.py:180-186); the
+    host plan marks the prior with -1 and its batch-row ranges equal the oracle's selection bounds bit for bit."""
+    from mopoe_mimic_b200.fusion import FusionPlan
+    from oracle import mopoe_oracle as O
+    for mods, B in ((('PA', 'Lateral', 'text'), 256), (('PA', 'text'), 9), (('PA', 'Lateral', 'text'), 17)):
+        keys = list(O.subset_keys(mods).keys())
+        members = [sorted(k.split('_')) if k else [] for k in keys]
+        plan = FusionPlan(list(mods), list(mods), keys, members, 'jsd', B, 32, B)
+        uni = [i for i, k in enumerate(plan.keys) if '_' not in k]
+        assert plan.stacked == uni + [-1]
+        assert plan.cfg.S == len(mods) + 1 and plan.cfg.fuse_mode == 1 and plan.cfg.prior_expert == 0
+        _, ends = O.selection_bounds(B, [1.0 / (len(mods) + 1)] * (len(mods) + 1))
+        assert [plan.cfg.sel_end[j] for j in range(plan.cfg.S)] == ends == plan.sel_end
+        assert [plan.cfg.stacked[j] for j in range(plan.cfg.S)] == plan.stacked
+
+
+def test_peer_exchange_slices_cover_the_buffer():
+    """owner slices of the fused exchange kernel: contiguous, float4-aligned, covering every element exactly once
+    (the same formula as dp_adam_exchange_kernel: per = ceil(n/4 / world) float4s)"""
+    from mopoe_mimic_b200.dp import PeerExchange
+
+    class _Stub:
+        slice_bounds = PeerExchange.slice_bounds
+
+        def __init__(self, n, world):
+            self.params = torch.empty(n)
+            self.world = world
+    for n, world in ((153067136, 8), (3145920, 2), (1024, 16), (64, 3), (4, 8)):
+        b = _Stub(n, world).slice_bounds()
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+        for (s0, e0), (s1, e1) in zip(b, b[1:]):
+            assert e0 == s1 and s0 % 4 == 0 and e0 % 4 == 0 and s0 <= e0
