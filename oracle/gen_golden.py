@@ -54,7 +54,8 @@ def ref_flags(fl):
     m = fl.method
     return SimpleNamespace(
         device=torch.device('cpu'), batch_size=fl.batch_size, class_dim=fl.class_dim, img_size=fl.img_size,
-        image_channels=fl.image_channels, DIM_img=fl.DIM_img, DIM_text=fl.DIM_text, text_encoding='char',
+        image_channels=fl.image_channels, DIM_img=fl.DIM_img, DIM_text=fl.DIM_text,
+        text_encoding=getattr(fl, 'text_encoding', 'char'), vocab_size=getattr(fl, 'vocab_size', 0),
         len_sequence=fl.len_sequence, num_features=fl.num_features, alphabet='x' * fl.num_features,
         feature_extractor_img='resnet', factorized_representation=O.factorized(fl),
         style_pa_dim=O.style_dim(fl, 'PA'), style_lat_dim=O.style_dim(fl, 'Lateral'),
@@ -194,6 +195,8 @@ CASES = OrderedDict([
     ('small_tri_joint_ragged', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, actual_batch=5)),
     ('small_tri_style', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32,
                             style_dims={'PA': 8, 'Lateral': 16, 'text': 24})),
+    ('small_tri_word', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, text_encoding='word', vocab_size=48,
+                           len_sequence=128)),
     ('small_tri_jsd', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, method='jsd')),
     ('small_patext_jsd', dict(batch_size=9, DIM_img=16, DIM_text=16, class_dim=32, mods=('PA', 'text'), method='jsd')),
 ])

@@ -38,7 +38,7 @@ POE_EPS = 1e-8         # evaluation/divergence_measures/mm_div.py:10
 def default_flags(**kw):
     """Flag fields the hot path reads; defaults = utils/flags.py, BaseFlags.py."""
     f = dict(batch_size=16, class_dim=128, img_size=128, image_channels=1, DIM_img=128, DIM_text=128,
-             text_encoding='char', len_sequence=1024, num_features=71,
+             text_encoding='char', len_sequence=1024, num_features=71, vocab_size=0,
              method='joint_elbo', mods=('PA', 'Lateral', 'text'),
              beta=5.0, beta_style=1.0, beta_content=1.0,
              rec_weights={'PA': 0.33, 'Lateral': 0.33, 'text': 0.33},
@@ -95,16 +95,35 @@ def text_encoder_blocks(flags):
     return [(ci, co, 4, 2, 1 if i < 7 else 0) for i, (ci, co) in enumerate(chans)]
 
 
+def is_word(flags):
+    return getattr(flags, 'text_encoding', 'char') == 'word'
+
+
+def text_encoder_blocks_used(flags):
+    """word encoding (word_encoding/mmvae_text_enc.py:76-79): resblock_7/8 are constructed but only RUN when
+    len_sequence > 500; the char encoder always runs all 8"""
+    blocks = text_encoder_blocks(flags)
+    return blocks[:6] if (is_word(flags) and flags.len_sequence <= 500) else blocks
+
+
 def text_decoder_blocks(flags):
     """char_encoding/DataGeneratorText.py:28-43."""
     d = flags.DIM_text
     chans = [(5 * d, 5 * d), (5 * d, 5 * d), (5 * d, 5 * d), (5 * d, 4 * d), (4 * d, 4 * d), (4 * d, 3 * d),
              (3 * d, 2 * d), (2 * d, d)]
+    if is_word(flags) and flags.len_sequence == 128:     # word_encoding/DataGeneratorText.py:58-65
+        chans = chans[:5] + [(4 * d, d)]
+    elif is_word(flags) and flags.len_sequence < 512:
+        raise NotImplementedError('word decoder: len_sequence %d' % flags.len_sequence)
     return [(ci, co, 4, 1 if i == 0 else 2, 0 if i == 0 else 1) for i, (ci, co) in enumerate(chans)]
 
 
 ENC_NAME = {'PA': 'encoder_pa', 'Lateral': 'encoder_lat', 'text': 'encoder_text'}
 DEC_NAME = {'PA': 'decoder_pa', 'Lateral': 'decoder_lat', 'text': 'decoder_text'}
+
+
+def text_dec_block_name(flags, i):
+    return ('.text_generator.generator.%d.0' % i) if is_word(flags) else ('.text_generator.resblock_%d.0' % (i + 1))
 
 
 def _bn_spec(spec, p, c):
@@ -145,7 +164,11 @@ def param_spec(flags):
         e = ENC_NAME[m]
         if m == 'text':
             d = flags.DIM_text
-            spec[e + '.feature_extractor.conv1.weight'] = (d, flags.num_features, 4)
+            if is_word(flags):       # word_encoding/mmvae_text_enc.py:27-30: Embedding(vocab, DIM, padding_idx=0), Conv1d(DIM, DIM)
+                spec[e + '.feature_extractor.embedding.weight'] = (flags.vocab_size, d)
+                spec[e + '.feature_extractor.conv1.weight'] = (d, d, 4)
+            else:
+                spec[e + '.feature_extractor.conv1.weight'] = (d, flags.num_features, 4)
             spec[e + '.feature_extractor.conv1.bias'] = (d,)
             for i, (ci, co, k, s, p) in enumerate(text_encoder_blocks(flags)):
                 _block_spec(spec, e + '.feature_extractor.resblock_%d.0' % (i + 1), ci, co, k, 1, False, True,
@@ -170,11 +193,19 @@ def param_spec(flags):
             d = flags.DIM_text
             spec[dn + '.feature_generator.weight'] = (5 * d, style_dim(flags, m) + D)
             spec[dn + '.feature_generator.bias'] = (5 * d,)
-            for i, (ci, co, k, s, p) in enumerate(text_decoder_blocks(flags)):
-                _block_spec(spec, dn + '.text_generator.resblock_%d.0' % (i + 1), ci, co, k, 1, True, True,
-                            'upsample')
-            spec[dn + '.text_generator.conv2.weight'] = (d, flags.num_features, 4)
-            spec[dn + '.text_generator.conv2.bias'] = (flags.num_features,)
+            blocks = text_decoder_blocks(flags)
+            for i, (ci, co, k, s, p) in enumerate(blocks):
+                _block_spec(spec, dn + text_dec_block_name(flags, i), ci, co, k, 1, True, True, 'upsample')
+            if is_word(flags):       # word_encoding/DataGeneratorText.py:49-65: the modules live in one nn.Sequential
+                last = dn + '.text_generator.generator.%d' % len(blocks)
+                if flags.len_sequence == 128:
+                    spec[last + '.weight'] = (flags.vocab_size, d, 1)            # nn.Conv1d(DIM, vocab, 1)
+                else:
+                    spec[last + '.weight'] = (d, flags.vocab_size, 4)            # nn.ConvTranspose1d(DIM, vocab, 4, 2, 1)
+                spec[last + '.bias'] = (flags.vocab_size,)
+            else:
+                spec[dn + '.text_generator.conv2.weight'] = (d, flags.num_features, 4)
+                spec[dn + '.text_generator.conv2.bias'] = (flags.num_features,)
         else:
             d = flags.DIM_img
             spec[dn + '.feature_generator.weight'] = (5 * d, style_dim(flags, m) + D)
@@ -210,6 +241,11 @@ def make_state(flags, seed=0, dtype=torch.float32):
             st[name] = torch.zeros(shape, dtype=dtype)
         elif name.endswith('running_var'):
             st[name] = torch.ones(shape, dtype=dtype)
+        elif name.endswith('embedding.weight'):
+            # nn.Embedding default init is N(0, 1) with the padding_idx row zeroed; a seeded uniform of the same scale
+            w = seeded_uniform(name, seed, shape, -1.7, 1.7, dtype)
+            w[0].zero_()
+            st[name] = w
         elif len(shape) == 1 and ('.bn' in name or 'sample.1.' in name):
             if name.endswith('weight'):
                 st[name] = seeded_uniform(name, seed, shape, 0.8, 1.2, dtype)
@@ -230,7 +266,8 @@ _spec_cache = {}
 
 def param_spec_cached(flags):
     key = (flags.class_dim, flags.img_size, flags.DIM_img, flags.DIM_text, tuple(flags.mods), flags.num_features,
-           tuple(style_dim(flags, m) for m in flags.mods))
+           tuple(style_dim(flags, m) for m in flags.mods), getattr(flags, 'text_encoding', 'char'),
+           getattr(flags, 'vocab_size', 0), flags.len_sequence)
     if key not in _spec_cache:
         _spec_cache[key] = param_spec(flags)
     return _spec_cache[key]
@@ -243,9 +280,11 @@ def make_batch(flags, seed=1, dtype=torch.float32, batch=None):
     out = OrderedDict()
     for m in flags.mods:
         if m == 'text':
-            idx = (seeded_uniform('text', seed, (B, flags.len_sequence)) * flags.num_features).long()
-            idx.clamp_(0, flags.num_features - 1)
-            out[m] = F.one_hot(idx, flags.num_features).to(dtype)
+            nf = flags.vocab_size if is_word(flags) else flags.num_features
+            idx = (seeded_uniform('text', seed, (B, flags.len_sequence)) * nf).long()
+            idx.clamp_(0, nf - 1)
+            # word encoding ships token indices [B, L] (0 = padding), char encoding one-hot rows [B, L, 71]
+            out[m] = idx.to(dtype) if is_word(flags) else F.one_hot(idx, flags.num_features).to(dtype)
         else:
             out[m] = seeded_uniform(m, seed, (B, flags.image_channels, flags.img_size, flags.img_size), dtype=dtype)
     return out
@@ -261,7 +300,7 @@ def dropout_sites(flags, batch=None):
         e = ENC_NAME[m] + '.feature_extractor.resblock_%d.0'
         if m == 'text':
             L = flags.len_sequence // 2
-            for i, (ci, co, k, s, p) in enumerate(text_encoder_blocks(flags)):
+            for i, (ci, co, k, s, p) in enumerate(text_encoder_blocks_used(flags)):
                 sites[(e % (i + 1)) + '.dropout1'] = (B, ci, L)
                 L = (L + 2 * p - k) // s + 1
                 sites[(e % (i + 1)) + '.dropout2'] = (B, co, L)
@@ -272,12 +311,12 @@ def dropout_sites(flags, batch=None):
 
     def dec(m):
         if m == 'text':
-            dn = DEC_NAME[m] + '.text_generator.resblock_%d.0'
             L = 1
             for i, (ci, co, k, s, p) in enumerate(text_decoder_blocks(flags)):
-                sites[(dn % (i + 1)) + '.dropout1'] = (B, ci, L)
+                dn = DEC_NAME[m] + text_dec_block_name(flags, i)
+                sites[dn + '.dropout1'] = (B, ci, L)
                 L = (L - 1) * s - 2 * p + k
-                sites[(dn % (i + 1)) + '.dropout2'] = (B, co, L)
+                sites[dn + '.dropout2'] = (B, co, L)
         else:
             dn = DEC_NAME[m] + '.img_generator.generator.%d.0'
             for i, (ci, co, k, s, p) in enumerate(img_decoder_blocks(flags)):
@@ -407,9 +446,11 @@ def encoder_text(ctx, flags, e, x):
     """EncoderText.forward (ConvNetworksTextMimic.py:23-36) -> FeatureExtractorText.forward
     (char_encoding/FeatureExtractorText.py:58-81).  x: [B, L, num_features]."""
     s = ctx.s
+    if is_word(flags):      # word_encoding/mmvae_text_enc.py:69-71: embedding(x.long()) (padding_idx only affects the gradient)
+        x = F.embedding(x.long(), s[e + '.feature_extractor.embedding.weight'], padding_idx=0)
     h = F.conv1d(x.transpose(-2, -1), s[e + '.feature_extractor.conv1.weight'],
                  s[e + '.feature_extractor.conv1.bias'], stride=2, padding=1)
-    for i, (ci, co, k, st, p) in enumerate(text_encoder_blocks(flags)):
+    for i, (ci, co, k, st, p) in enumerate(text_encoder_blocks_used(flags)):
         h = _res_block(ctx, e + '.feature_extractor.resblock_%d.0' % (i + 1), h, k, st, p, 1, False)
     return _compress(s, e, h.reshape(h.shape[0], -1))
 
@@ -433,10 +474,18 @@ def decoder_text(ctx, flags, d, z):
     (char_encoding/DataGeneratorText.py:53-76).  Returns log-softmaxed logits [B, L, num_features]."""
     s = ctx.s
     h = F.linear(z, s[d + '.feature_generator.weight'], s[d + '.feature_generator.bias']).unsqueeze(-1)
-    for i, (ci, co, k, st, p) in enumerate(text_decoder_blocks(flags)):
-        h = _res_block(ctx, d + '.text_generator.resblock_%d.0' % (i + 1), h, k, st, p, 1, True)
-    h = F.conv_transpose1d(h, s[d + '.text_generator.conv2.weight'], s[d + '.text_generator.conv2.bias'],
-                           stride=2, padding=1)
+    blocks = text_decoder_blocks(flags)
+    for i, (ci, co, k, st, p) in enumerate(blocks):
+        h = _res_block(ctx, d + text_dec_block_name(flags, i), h, k, st, p, 1, True)
+    if is_word(flags):
+        last = d + '.text_generator.generator.%d' % len(blocks)
+        if flags.len_sequence == 128:
+            h = F.conv1d(h, s[last + '.weight'], s[last + '.bias'])
+        else:
+            h = F.conv_transpose1d(h, s[last + '.weight'], s[last + '.bias'], stride=2, padding=1)
+    else:
+        h = F.conv_transpose1d(h, s[d + '.text_generator.conv2.weight'], s[d + '.text_generator.conv2.bias'],
+                               stride=2, padding=1)
     return F.log_softmax(h, dim=1).transpose(-2, -1)
 
 
@@ -561,7 +610,8 @@ def categorical_log_prob_sum(logits, target):
     """dist.OneHotCategorical(logits=logits).log_prob(target).sum(): logits are re-normalised
     (idempotent after the decoder's LogSoftmax) and indexed by argmax(target)."""
     ln = logits - logits.logsumexp(dim=-1, keepdim=True)
-    idx = target.max(-1)[1]
+    # word encoding: the target holds token indices and MimicText.calc_log_prob one-hot encodes it (MimicText.py:37-40)
+    idx = target.long() if target.dim() == logits.dim() - 1 else target.max(-1)[1]
     return ln.gather(-1, idx.unsqueeze(-1)).sum()
 
 
@@ -662,7 +712,8 @@ def step_with_grads(state, batch, flags, masks=None, eps=None, uni_masks=None, e
         v.grad = None
     out = step_losses(state, batch, flags, masks, eps, True, uni_masks=uni_masks, eps_style=eps_style)
     out['total_loss'].backward()
-    grads = OrderedDict((k, v.grad.detach().clone()) for k, v in params.items())
+    # (parameters the step never touches — the word encoder's resblock_7/8 at len_sequence <= 500 — have no gradient)
+    grads = OrderedDict((k, v.grad.detach().clone()) for k, v in params.items() if v.grad is not None)
     for v in params.values():
         v.requires_grad_(False)
         v.grad = None
@@ -679,6 +730,8 @@ def adam_step(params, grads, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     bc1 = 1 - b1 ** step
     bc2 = 1 - b2 ** step
     for k in params:
+        if k not in grads:            # never used in the step (no gradient): torch.optim.Adam skips it too
+            continue
         g = grads[k]
         m[k].mul_(b1).add_(g, alpha=1 - b1)
         v[k].mul_(b2).addcmul_(g, g, value=1 - b2)
