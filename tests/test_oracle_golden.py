@@ -89,7 +89,10 @@ def test_oracle_matches_reference_golden(golden_dir, name):
     for k, cs in fx['grads'].items():
         check_checksum(out['grads'][k], cs, 1e-8, scale=1e-6 * fx['grad_scale'])
     for k, cs in fx['bn'].items():
-        check_checksum(out['results']['bn_updates'][k], cs, rt)
+        if k in out['results']['bn_updates']:      # (BN layers the step never runs keep their initial statistics)
+            check_checksum(out['results']['bn_updates'][k], cs, rt)
+        else:
+            check_checksum(st[k], cs, rt)
 
 
 def test_oracle_fp32_close_to_fp64_reference(golden_dir):
