@@ -257,6 +257,11 @@ int mopoe_jsd_divergence_fwd(int K, int B, int D, const float* const* mu, const 
 int mopoe_jsd_divergence_bwd(int K, int B, int D, const float* const* mu, const float* const* logvar, const float* alpha,
                              float norm, const float* d_kl, float* const* d_mu, float* const* d_lv, void* stream);
 
+/* Token indices (fp32 values, as the reference ships them; clamped to [0, V)) -> one-hot rows [rows, Vp] (Vp >= V,
+ * multiple of 8) in MOPOE_F32 / MOPOE_BF16, plus the int32 indices: nn.Embedding (word_encoding/mmvae_text_enc.py:27-28,69)
+ * becomes a GEMM of these rows with the embedding matrix, its gradient the matching weight-gradient GEMM. */
+int mopoe_onehot(const float* idx, int64_t rows, int V, int Vp, void* out, int out_dtype, int32_t* idx_out, void* stream);
+
 /* All weight re-layouts of a step in ONE launch.  jobs_dev: DEVICE array of njobs descriptors (same meaning as the
  * arguments of mopoe_pack_weight_tiled; form 1 fills dst[0..3] / dst[0..1], the others dst[0]); tile0 = index of the
  * job's first tile in the launch grid and nx = its tile-grid width, both from mopoe_pack_job_tiles (which returns the

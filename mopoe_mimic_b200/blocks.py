@@ -343,7 +343,60 @@ class TextStemFn(torch.autograd.Function):
         g = eng.wgrad_down(xin, 4, 2, 1, dy)                   # [Cc, 4*Fp]
         dw = g.view(Cc, 4, Fp)[:, :, :Fq].permute(0, 2, 1).contiguous()
         db = eng.colsum(dy)
-        return None, dw, db, None, None
+        dx = None
+        if ctx.needs_input_grad[0]:            # word encoding: x is the embedded token sequence
+            if Fp != Fq or out_pad < 1:
+                raise NotImplementedError('input gradient of the text stem needs a feature count that is a multiple of 16')
+            dxa = eng.gemm_up(dy, eng.packed(w, 'phase'), None, Fq, out_dtype=torch.float32)     # [B, 1, Lq, Fq] fp32
+            dx = dxa.t.view(B, Lq, Fq)
+        return dx, dw, db, None, None
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """nn.Embedding(vocab, D, padding_idx=0) on token indices [B, L] (shipped as floats, as the reference does) -> fp32
+    [B, L, D]  (word_encoding/mmvae_text_enc.py:27-28,69).  The look-up is the GEMM onehot[B*L, V] x E[V, D] and its
+    gradient the matching weight-gradient GEMM — the same tcgen05 / SIMT kernels as every other layer; the padding row
+    receives no gradient."""
+
+    @staticmethod
+    def forward(ctx, idx_f, E, eng):
+        B, Lq = idx_f.shape
+        V, D = E.shape
+        Vp = (V + 63) // 64 * 64
+        rows = B * Lq
+        oh = torch.empty(rows, Vp, dtype=eng.dtype, device=eng.device)
+        L.call('mopoe_onehot', L.ptr(idx_f.contiguous().float()), rows, V, Vp, L.ptr(oh), L.dtype_code(eng.dtype), None,
+               L.stream_ptr())
+        xa = Act(oh, rows, 1, 1, Vp, 0, 0)
+        # GEMM operand [n = D, k = Vp] = E^T (zero columns for the vocabulary padding); V x D is tiny, torch re-lays it out
+        w_op = torch.zeros(D, Vp, dtype=eng.dtype, device=eng.device)
+        w_op[:, :V] = E.detach().t().to(eng.dtype)
+        impl, eng.impl = eng.impl, L.IMPL_SIMT            # (shapes like N = 16 are outside what the tcgen05 path is tested on)
+        try:
+            out = eng.gemm_rows(xa, w_op, None, D, out_dtype=torch.float32)
+        finally:
+            eng.impl = impl
+        ctx.save_for_backward(oh, E)
+        ctx.eng, ctx.geo = eng, (B, Lq, V, Vp, D)
+        return out.t.view(B, Lq, D)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        oh, E = ctx.saved_tensors
+        eng = ctx.eng
+        B, Lq, V, Vp, D = ctx.geo
+        rows = B * Lq
+        dy = Act(d_out.contiguous().to(eng.dtype).view(rows, 1, 1, D), rows, 1, 1, D, 0, 0)
+        xa = Act(oh, rows, 1, 1, Vp, 0, 0)
+        # dE[v, d] = sum_rows onehot[row, v] * d_out[row, d]:  wgrad with the one-hot rows as "dY" and d_out as the window
+        impl, eng.impl = eng.impl, L.IMPL_SIMT
+        try:
+            g = eng.wgrad_rows(dy, xa)                          # [Vp, D] fp32
+        finally:
+            eng.impl = impl
+        dE = g[:V].clone()
+        dE[0].zero_()                                           # padding_idx = 0
+        return None, dE, None
 
 
 class LinearFn(torch.autograd.Function):
@@ -451,19 +504,24 @@ class LaplaceLogProbSumFn(torch.autograd.Function):
 
 
 class CategoricalLogProbSumFn(torch.autograd.Function):
-    """scores: pre-softmax [B, L, V]; target: one-hot [B, L, V]."""
+    """scores: pre-softmax [B, L, V]; target: one-hot [B, L, V], or token indices [B, L] (word encoding)."""
 
     @staticmethod
     def forward(ctx, scores, target, eng):
         scores = scores.contiguous()
-        target = target.contiguous().float()
         V = scores.shape[-1]
         rows = scores.numel() // V
         nc = int(min(148 * 8, max(1, rows // 64)))
         out = eng.f32(1)
-        idx = torch.empty(rows, dtype=torch.int32, device=scores.device)
-        L.call('mopoe_categorical_logprob_sum', L.ptr(scores), L.ptr(target), None, rows, V, None, L.ptr(idx),
-               L.ptr(out), L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
+        if target.dim() == scores.dim() - 1:            # indices (MimicText.calc_log_prob one-hot encodes them, :37-40)
+            idx = target.contiguous().reshape(-1).to(torch.int32)
+            L.call('mopoe_categorical_logprob_sum', L.ptr(scores), None, L.ptr(idx), rows, V, None, None,
+                   L.ptr(out), L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
+        else:
+            target = target.contiguous().float()
+            idx = torch.empty(rows, dtype=torch.int32, device=scores.device)
+            L.call('mopoe_categorical_logprob_sum', L.ptr(scores), L.ptr(target), None, rows, V, None, L.ptr(idx),
+                   L.ptr(out), L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
         ctx.save_for_backward(scores, idx)
         return out.view(())
 

@@ -1045,6 +1045,38 @@ extern "C" int mopoe_dropout_mask(uint8_t* mask, int64_t n, uint64_t seed, uint6
     return 0;
 }
 
+// ---- token indices -> one-hot rows (word-encoded text) ------------------------------------------------------------------
+// nn.Embedding as a GEMM operand (word_encoding/mmvae_text_enc.py:27-28,69): out[row, v] = (v == idx[row]), rows of Vp
+// (>= V, multiple of 8) elements in the activation dtype; idx_out receives the integer indices.
+template <typename T>
+__global__ void __launch_bounds__(256) onehot_kernel(const float* __restrict__ idx, long long rows, int V, int Vp,
+                                                     T* __restrict__ out, int* __restrict__ idx_out) {
+    const long long total = rows * (Vp / 8);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long row = i / (Vp / 8);
+        const int v0 = (int)(i - row * (Vp / 8)) * 8;
+        int id = (int)idx[row];
+        id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+        if (v0 == 0 && idx_out) idx_out[row] = id;
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = (v0 + k == id) ? 1.f : 0.f;
+        st8v<T>(out + row * Vp + v0, o);
+    }
+}
+extern "C" int mopoe_onehot(const float* idx, int64_t rows, int V, int Vp, void* out, int out_dtype, int32_t* idx_out,
+                            void* stream) {
+    MOPOE_REQUIRE(rows > 0 && V >= 1 && Vp >= V && Vp % 8 == 0, "onehot: rows=%lld V=%d Vp=%d", (long long)rows, V, Vp);
+    long long blocks = ceil_div64(rows * (Vp / 8), 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (out_dtype == MOPOE_F32)
+        onehot_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(idx, rows, V, Vp, (float*)out, idx_out);
+    else
+        onehot_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(idx, rows, V, Vp, (bf16*)out, idx_out);
+    MOPOE_CHECK_LAUNCH("onehot");
+    return 0;
+}
+
 // ---- flat Adam -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n4,

@@ -181,15 +181,94 @@ __global__ void __launch_bounds__(256) categorical_fwd_kernel(const float* __res
         part[blockIdx.x] = s;
     }
 }
+// Vocabulary-sized rows (word-encoded text, V in the thousands): the same arithmetic with the row re-read from L1/L2 in
+// lane-strided passes instead of held in registers (same per-lane summation order as the register version).
+__global__ void __launch_bounds__(256) categorical_fwd_big_kernel(const float* __restrict__ y, const float* __restrict__ target,
+                                                                  const int* __restrict__ idx_in, long long rows, int V,
+                                                                  float* __restrict__ logits_out, int* __restrict__ idx_out,
+                                                                  double* __restrict__ part) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (long long row = (long long)blockIdx.x * 8 + wib; row < rows; row += (long long)gridDim.x * 8) {
+        const float* yr = y + row * V;
+        float mx = -INFINITY;
+        for (int k = lane; k < V; k += 32) mx = fmaxf(mx, yr[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+        for (int k = lane; k < V; k += 32) se += expf(yr[k] - mx);
+        se = warp_sum(se);
+        const float lse = mx + logf(se);
+        int id;
+        if (target) {
+            const float* tr = target + row * V;
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int k = lane; k < V; k += 32) {
+                const float t = tr[k];
+                if (t > best) { best = t; bi = k; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            id = bi;
+        } else {
+            id = idx_in[row];
+        }
+        if (idx_out && lane == 0) idx_out[row] = id;
+        if (logits_out)
+            for (int k = lane; k < V; k += 32) logits_out[row * V + k] = yr[k] - lse;
+        // OneHotCategorical(logits=l).log_prob renormalises l again (idempotent up to rounding): emulate it
+        const float mx2 = mx - lse;
+        float se2 = 0.f;
+        for (int k = lane; k < V; k += 32) se2 += expf((yr[k] - lse) - mx2);
+        se2 = warp_sum(se2);
+        const float lse2 = mx2 + logf(se2);
+        if (lane == 0) acc += (double)((yr[id] - lse) - lse2);
+    }
+    __shared__ double sm[8];
+    if (lane == 0) sm[wib] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sm[i];
+        part[blockIdx.x] = s;
+    }
+}
+__global__ void __launch_bounds__(256) categorical_bwd_big_kernel(const float* __restrict__ y, const int* __restrict__ idx,
+                                                                  long long rows, int V, const float* __restrict__ gout,
+                                                                  float* __restrict__ dy) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const float g = gout[0];
+    for (long long row = (long long)blockIdx.x * 8 + wib; row < rows; row += (long long)gridDim.x * 8) {
+        const float* yr = y + row * V;
+        float mx = -INFINITY;
+        for (int k = lane; k < V; k += 32) mx = fmaxf(mx, yr[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
+        for (int k = lane; k < V; k += 32) se += expf(yr[k] - mx);
+        se = warp_sum(se);
+        const float inv = 1.f / se;
+        const int id = idx[row];
+        for (int k = lane; k < V; k += 32) dy[row * V + k] = g * ((k == id ? 1.f : 0.f) - expf(yr[k] - mx) * inv);
+    }
+}
 extern "C" int mopoe_categorical_logprob_sum(const float* y, const float* target, const int32_t* idx, int64_t rows,
                                              int V, float* logits_out, int32_t* idx_out, float* out, double* ws,
                                              int nchunk, void* stream) {
-    MOPOE_REQUIRE(V >= 1 && V <= 32 * CAT_MAXV_PER_LANE, "categorical: V=%d unsupported (max %d)", V,
-                  32 * CAT_MAXV_PER_LANE);
+    MOPOE_REQUIRE(V >= 1, "categorical: V=%d", V);
     MOPOE_REQUIRE(target || idx, "categorical: need target or idx");
     MOPOE_REQUIRE(nchunk >= 1 && nchunk <= 65535, "categorical: nchunk=%d", nchunk);
     cudaStream_t st = (cudaStream_t)stream;
-    categorical_fwd_kernel<<<nchunk, 256, 0, st>>>(y, target, idx, rows, V, logits_out, idx_out, ws);
+    if (V <= 32 * CAT_MAXV_PER_LANE)
+        categorical_fwd_kernel<<<nchunk, 256, 0, st>>>(y, target, idx, rows, V, logits_out, idx_out, ws);
+    else
+        categorical_fwd_big_kernel<<<nchunk, 256, 0, st>>>(y, target, idx, rows, V, logits_out, idx_out, ws);
     MOPOE_CHECK_LAUNCH("categorical_fwd");
     final_sum_kernel<<<1, 32, 0, st>>>(ws, nchunk, out, 1.f);
     MOPOE_CHECK_LAUNCH("categorical_final");
@@ -227,11 +306,14 @@ __global__ void __launch_bounds__(256) categorical_bwd_kernel(const float* __res
 }
 extern "C" int mopoe_categorical_logprob_bwd(const float* y, const int32_t* idx, int64_t rows, int V,
                                              const float* gout, float* dy, void* stream) {
-    MOPOE_REQUIRE(V >= 1 && V <= 32 * CAT_MAXV_PER_LANE, "categorical: V=%d unsupported", V);
+    MOPOE_REQUIRE(V >= 1, "categorical: V=%d", V);
     long long blocks = ceil_div64(rows, 8);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    categorical_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, idx, rows, V, gout, dy);
+    if (V <= 32 * CAT_MAXV_PER_LANE)
+        categorical_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, idx, rows, V, gout, dy);
+    else
+        categorical_bwd_big_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, idx, rows, V, gout, dy);
     MOPOE_CHECK_LAUNCH("categorical_bwd");
     return 0;
 }

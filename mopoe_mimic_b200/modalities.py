@@ -65,7 +65,8 @@ class CategoricalLikelihood:
         return self.probs
 
     def log_prob(self, value):
-        idx = value.max(-1)[1]
+        # one-hot rows [.., V], or token indices [..] (word encoding: MimicText.calc_log_prob one-hot encodes them, :37-40)
+        idx = value.long() if value.dim() == self.logits.dim() - 1 else value.max(-1)[1]
         return self.logits.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
 
     def log_prob_sum(self, value):
@@ -124,8 +125,10 @@ class MimicText(Modality):
         if args.text_encoding == 'char':
             self.alphabet = getattr(args, 'alphabet', None)
             self.data_size = torch.Size((args.num_features, len_sequence))
+        elif args.text_encoding == 'word':
+            self.data_size = torch.Size((args.vocab_size, len_sequence))
         else:
-            raise NotImplementedError('word encoding is outside the built scope (SURVEY.md N4)')
+            raise NotImplementedError('text_encoding %r' % args.text_encoding)
         self.plot_img_size = plotImgSize
         self.font = font
         self.gen_quality_eval = False

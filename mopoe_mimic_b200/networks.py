@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .blocks import (BN_EPS, BlockRun, BlockSpec, ImgLastFn, ImgStemFn, LinearFn, ResBlockFn, TextLastFn,
+from .blocks import (BN_EPS, BlockRun, BlockSpec, EmbeddingFn, ImgLastFn, ImgStemFn, LinearFn, ResBlockFn, TextLastFn,
                      TextStemFn, _pads)
 from .engine import Engine
 
@@ -291,14 +291,35 @@ class FeatureExtractorText(nn.Module):
             setattr(self, 'resblock_%d' % (i + 1), nn.Sequential(ResBlock(sp)))
 
 
+class FeatureExtractorTextWord(nn.Module):
+    """word_encoding/mmvae_text_enc.py:22-85: Embedding(vocab, DIM, padding_idx=0) -> Conv1d(DIM, DIM, 4, 2, 1) -> the same
+    8 residual blocks as the char extractor, of which only the first 6 RUN when len_sequence <= 500."""
+
+    def __init__(self, flags):
+        super().__init__()
+        d = flags.DIM_text
+        self.embedding = _Params((flags.vocab_size, d))
+        with torch.no_grad():                                   # nn.Embedding init: N(0, 1), padding row zero
+            self.embedding.weight.normal_(0.0, 1.0)
+            self.embedding.weight[0].zero_()
+        self.conv1 = _Params((d, d, 4), d)
+        chans = [(d, 2 * d), (2 * d, 3 * d), (3 * d, 4 * d), (4 * d, 4 * d), (4 * d, 4 * d), (4 * d, 5 * d),
+                 (5 * d, 5 * d), (5 * d, 5 * d)]
+        self.specs = []
+        for i, (ci, co) in enumerate(chans):
+            sp = BlockSpec('resblock_%d' % (i + 1), 1, ci, co, 4, 2, 1 if i < 7 else 0, False, RES_A, RES_B)
+            self.specs.append(sp)
+            setattr(self, 'resblock_%d' % (i + 1), nn.Sequential(ResBlock(sp)))
+        self.used = 8 if flags.len_sequence > 500 else 6
+
+
 class EncoderText(_Net):
     """EncoderText(flags, style_dim)(x_text [B, L, num_features]) -> (mu, logvar)  (ConvNetworksTextMimic.py:11-36)"""
 
     def __init__(self, flags, style_dim=0):
         super().__init__(flags)
-        if flags.text_encoding != 'char':
-            raise NotImplementedError('word encoding is outside the built scope (SURVEY.md N4)')
-        self.feature_extractor = FeatureExtractorText(flags)
+        self.word = flags.text_encoding == 'word'
+        self.feature_extractor = FeatureExtractorTextWord(flags) if self.word else FeatureExtractorText(flags)
         self.feature_compressor = LinearFeatureCompressor(5 * flags.DIM_text, style_dim, flags.class_dim)
 
     def forward(self, x_text):
@@ -306,8 +327,10 @@ class EncoderText(_Net):
         rt, fe = self.rt, self.feature_extractor
         eng = rt.eng(x_text.device)
         train = self.training
+        if self.word:               # token indices [B, L] -> embedded sequence [B, L, DIM] (fp32, differentiable)
+            x_text = EmbeddingFn.apply(x_text, fe.embedding.weight, eng)
         B, Lq, _ = x_text.shape
-        specs = fe.specs
+        specs = fe.specs[:fe.used] if self.word else fe.specs
         ins, outs = _chain_pads(specs, 0)
         h = TextStemFn.apply(x_text, fe.conv1.weight, fe.conv1.bias, eng, ins[0])
         H, W = 1, Lq // 2
@@ -343,6 +366,37 @@ class DataGeneratorText(nn.Module):
         self.conv2 = _Params((d, flags.num_features, 4), flags.num_features)
 
 
+class DataGeneratorTextWord(nn.Module):
+    """word_encoding/DataGeneratorText.py:29-98: one nn.Sequential `generator` of transposed residual blocks, then
+    ConvTranspose1d(DIM, vocab, 4, 2, 1) (len_sequence >= 512) or Conv1d(DIM, vocab, 1) (len_sequence == 128); the
+    LogSoftmax module (no parameters) lives in the likelihood kernel."""
+
+    def __init__(self, flags):
+        super().__init__()
+        d = flags.DIM_text
+        chans = [(5 * d, 5 * d), (5 * d, 5 * d), (5 * d, 5 * d), (5 * d, 4 * d), (4 * d, 4 * d)]
+        if flags.len_sequence >= 512:
+            chans += [(4 * d, 3 * d), (3 * d, 2 * d), (2 * d, d)]
+        elif flags.len_sequence == 128:
+            chans += [(4 * d, d)]
+        else:
+            raise NotImplementedError('The output shapes of this network will not work for len_sequence: %d' % flags.len_sequence)
+        self.specs, mods = [], []
+        for i, (ci, co) in enumerate(chans):
+            sp = BlockSpec(str(i), 1, ci, co, 4, 1 if i == 0 else 2, 0 if i == 0 else 1, True, RES_A, RES_B)
+            self.specs.append(sp)
+            mods.append(nn.Sequential(ResBlock(sp)))
+        self.pointwise_last = flags.len_sequence == 128
+        if self.pointwise_last and flags.vocab_size % 8 != 0:
+            raise NotImplementedError('the pointwise vocabulary head needs vocab_size %% 8 == 0 (got %d): pad the vocabulary'
+                                      % flags.vocab_size)
+        if self.pointwise_last:
+            mods.append(_Params((flags.vocab_size, d, 1), flags.vocab_size))        # nn.Conv1d(DIM, vocab, 1)
+        else:
+            mods.append(_Params((d, flags.vocab_size, 4), flags.vocab_size))        # nn.ConvTranspose1d(DIM, vocab, 4, 2, 1)
+        self.generator = nn.Sequential(*mods)
+
+
 class DecoderText(_Net):
     """DecoderText(flags, style_dim)(z_style, z_content) -> [text_hat [B, L, num_features]]  (ConvNetworksTextMimic.py:39-68).
 
@@ -352,10 +406,9 @@ class DecoderText(_Net):
 
     def __init__(self, flags, style_dim=0):
         super().__init__(flags)
-        if flags.text_encoding != 'char':
-            raise NotImplementedError('word encoding is outside the built scope (SURVEY.md N4)')
+        self.word = flags.text_encoding == 'word'
         self.feature_generator = _Params((5 * flags.DIM_text, style_dim + flags.class_dim), 5 * flags.DIM_text)
-        self.text_generator = DataGeneratorText(flags)
+        self.text_generator = DataGeneratorTextWord(flags) if self.word else DataGeneratorText(flags)
 
     def forward(self, z_style, z_content):
         # factorized representation: z = cat(style, content) (ConvNetworksImgMimic.py:47-48, ConvNetworksTextMimic.py:52-55)
@@ -368,13 +421,25 @@ class DecoderText(_Net):
         fg = self.feature_generator
         h = LinearFn.apply(z, fg.weight, fg.bias, eng, B, None, 1, True)
         specs = gen.specs
-        ins, outs = _chain_pads(specs, 1)
+        last_pad = 0 if (self.word and gen.pointwise_last) else 1        # a 1x1 conv needs no border on its input
+        ins, outs = _chain_pads(specs, last_pad)
         H, W = 1, 1
         for i, sp in enumerate(specs):
-            blk = getattr(gen, sp.name)[0]
-            h = blk.run(rt, eng, h, B, H, W, ins[i], outs[i], train, '%s.text_generator.%s.0' % (self.prefix, sp.name))
+            if self.word:
+                blk, pname = gen.generator[i][0], '%s.text_generator.generator.%d.0' % (self.prefix, i)
+            else:
+                blk, pname = getattr(gen, sp.name)[0], '%s.text_generator.%s.0' % (self.prefix, sp.name)
+            h = blk.run(rt, eng, h, B, H, W, ins[i], outs[i], train, pname)
             H, W = sp.out_hw(H, W)
-        scores = TextLastFn.apply(h, gen.conv2.weight, gen.conv2.bias, eng, B, W, 1)
+        if self.word and gen.pointwise_last:
+            last = gen.generator[len(specs)]
+            V = last.weight.shape[0]
+            scores = LinearFn.apply(h, last.weight.view(V, -1), last.bias, eng, B * W, 0, 1, False).view(B, W, V)
+        elif self.word:
+            last = gen.generator[len(specs)]
+            scores = TextLastFn.apply(h, last.weight, last.bias, eng, B, W, 1)
+        else:
+            scores = TextLastFn.apply(h, gen.conv2.weight, gen.conv2.bias, eng, B, W, 1)
         if train:
             self._bump()
         return [scores]

@@ -29,7 +29,7 @@ def default_flags(**kw):
     """The ~30 flag fields the hot path reads, with the reference's defaults (utils/flags.py, BaseFlags.py)."""
     f = dict(device=torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu'),
              batch_size=16, class_dim=128, img_size=128, image_channels=1, DIM_img=128, DIM_text=128,
-             text_encoding='char', len_sequence=1024, num_features=71, alphabet='x' * 71,
+             text_encoding='char', len_sequence=1024, num_features=71, alphabet='x' * 71, vocab_size=0,
              feature_extractor_img='resnet', factorized_representation=False,
              style_pa_dim=0, style_lat_dim=0, style_text_dim=0,
              modality_moe=False, modality_jsd=False, modality_poe=False, joint_elbo=True, poe_unimodal_elbos=True,

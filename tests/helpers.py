@@ -22,6 +22,7 @@ def product_flags(ofl, compute_dtype, device='cuda'):
                            img_size=ofl.img_size, DIM_img=ofl.DIM_img, DIM_text=ofl.DIM_text,
                            len_sequence=ofl.len_sequence, num_features=ofl.num_features, method=ofl.method,
                            mods=tuple(ofl.mods), beta=ofl.beta, compute_dtype=compute_dtype,
+                           text_encoding=getattr(ofl, 'text_encoding', 'char'), vocab_size=getattr(ofl, 'vocab_size', 0),
                            factorized_representation=O.factorized(ofl), style_pa_dim=O.style_dim(ofl, 'PA'),
                            style_lat_dim=O.style_dim(ofl, 'Lateral'), style_text_dim=O.style_dim(ofl, 'text'))
 
@@ -93,7 +94,8 @@ def smooth_grads(ofl, state, batch, noise, compute_dtype):
                         eps_style={m: v.to(dt) for m, v in es.items()} if es is not None else None)
         loss = sum((r ** 2).mean() for r in res['rec'].values()) * 100.0 + 5.0 * res['joint_divergence']
         loss.backward()
-        return loss, OrderedDict((k, v.grad.detach().clone()) for k, v in params.items())
+        # (parameters the step never runs — the word encoder's resblock_7/8 at len_sequence <= 500 — have no gradient)
+        return loss, OrderedDict((k, v.grad.detach().clone()) for k, v in params.items() if v.grad is not None)
     loss_o, g_o = oracle_grads(torch.float32)
     _, g_o64 = oracle_grads(torch.float64)        # truth: the same fp32-rounded inputs evaluated in fp64
     smooth_grads.truth = g_o64

@@ -249,3 +249,17 @@ def test_peer_exchange_slices_cover_the_buffer():
         assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
         for (s0, e0), (s1, e1) in zip(b, b[1:]):
             assert e0 == s1 and s0 % 4 == 0 and e0 % 4 == 0 and s0 <= e0
+
+
+def test_word_encoding_state_dict_matches_the_reference_layout():
+    """word-encoded text (Embedding + Conv1d stem + 8 constructed / 6 used blocks; one nn.Sequential generator with a
+    pointwise vocabulary head at len_sequence 128): names, order and shapes equal the oracle's spec, which is pinned
+    against the reference's own state_dict (oracle/gen_golden.py asserts key order on the live model)."""
+    import mopoe_mimic_b200 as P
+    from oracle import mopoe_oracle as O
+    for L_ in (128, 512):
+        kw = dict(batch_size=4, DIM_img=8, DIM_text=16, class_dim=16, text_encoding='word', vocab_size=48, len_sequence=L_)
+        spec = O.param_spec(O.default_flags(**kw))
+        exp = P.Experiment(P.default_flags(device=torch.device('cpu'), **kw))
+        sd = exp.mm_vae.state_dict()
+        assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s_)) for k, s_ in spec.items()]

@@ -144,7 +144,7 @@ def test_laplace_logprob_sum_and_grad(n):
     torch.testing.assert_close(l.grad.cpu(), (ref_loc.grad * 0.33).float(), rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize('rows,V', [(1, 71), (1024, 71), (16 * 1024, 71), (333, 5), (64, 256)])
+@pytest.mark.parametrize('rows,V', [(1, 71), (1024, 71), (16 * 1024, 71), (333, 5), (64, 256), (77, 257), (512, 2900)])
 def test_categorical_logprob_sum_and_grad(rows, V):
     from mopoe_mimic_b200.blocks import CategoricalLogProbSumFn, log_softmax_rows
     g = torch.Generator().manual_seed(rows + V)
@@ -161,6 +161,9 @@ def test_categorical_logprob_sum_and_grad(rows, V):
     torch.testing.assert_close(yc.grad.cpu(), yr.grad.float(), rtol=1e-4, atol=1e-6)
     ls = log_softmax_rows(y.cuda(), _eng())
     torch.testing.assert_close(ls.cpu(), torch.log_softmax(y, -1), rtol=1e-5, atol=1e-5)
+    # token-index targets (word encoding) must give the same value as the one-hot rows
+    out_i = CategoricalLogProbSumFn.apply(y.cuda().view(1, rows, V), idx.float().cuda().view(1, rows), _eng())
+    assert abs(float(out_i) - float(out)) <= 1e-6 * abs(float(out)) + 1e-6
 
 
 def test_flat_adam_matches_oracle_adam():

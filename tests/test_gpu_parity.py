@@ -30,6 +30,9 @@ CASES = {
     'patext_moe': dict(SMALL, mods=('PA', 'text'), method='moe'),
     'patext_poe': dict(SMALL, mods=('PA', 'text'), method='poe', batch_size=5),
     'tri_jsd': dict(SMALL, method='jsd'),
+    'tri_word': dict(SMALL, text_encoding='word', vocab_size=48, len_sequence=128),      # Embedding + 6 blocks, V = 48
+    'tri_word_bigvocab': dict(batch_size=4, DIM_img=16, DIM_text=16, class_dim=32, text_encoding='word', vocab_size=304,
+                              len_sequence=128),                                         # V > 256: looped categorical kernels
     'tri_style': dict(SMALL, style_dims={'PA': 8, 'Lateral': 16, 'text': 24}),      # factorized representation
     'tri_style_moe': dict(SMALL, method='moe', style_dims={'PA': 8, 'Lateral': 8, 'text': 8}),
     'patext_jsd': dict(SMALL, mods=('PA', 'text'), method='jsd', batch_size=9),
@@ -59,7 +62,7 @@ def test_fp32_step_matches_oracle(name):
     assert g[-1] < 5e-2, errs['_worst_grad']
 
 
-@pytest.mark.parametrize('name', ['tri_joint', 'tri_moe', 'tri_jsd', 'tri_style', 'patext_joint', 'tri_64px', 'tri_256px'])
+@pytest.mark.parametrize('name', ['tri_joint', 'tri_moe', 'tri_jsd', 'tri_style', 'tri_word', 'patext_joint', 'tri_64px', 'tri_256px'])
 def test_fp32_gradients_of_smooth_loss_match_oracle(name):
     """Every conv / deconv / BN / dropout / fusion backward kernel, compared tightly: same graph, smooth loss."""
     kw = CASES[name]
@@ -103,7 +106,7 @@ def test_fp32_ragged_last_batch():
 
 GOLDEN_SMALL = ['small_tri_joint', 'small_tri_moe', 'small_tri_poe', 'small_patext_joint', 'small_patext_moe',
                 'small_patext_poe', 'small_tri_64_joint', 'small_tri_256_joint', 'small_tri_joint_ragged', 'small_tri_jsd',
-                'small_patext_jsd', 'small_tri_style']
+                'small_patext_jsd', 'small_tri_style', 'small_tri_word']
 
 
 @pytest.mark.parametrize('fixture', GOLDEN_SMALL)
