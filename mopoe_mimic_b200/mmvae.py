@@ -451,3 +451,13 @@ class VAEtrimodalMimic(MMVaeMimic):
         if list(modalities.keys()) != ['PA', 'Lateral', 'text']:
             raise ValueError('VAEtrimodalMimic needs modalities PA, Lateral, text (in this order)')
         super().__init__(flags, modalities, subsets)
+
+
+class VAETextMimic(MMVaeMimic):
+    """The text-only VAE of the reference (networks/VAEtrimodalMimic.py:166-256): the same inference / forward / generate
+    path with the single modality 'text' (one subset, so every fusion mode degenerates to that posterior)."""
+
+    def __init__(self, flags, modalities, subsets):
+        if list(modalities.keys()) != ['text']:
+            raise ValueError('VAETextMimic needs exactly the modality text')
+        super().__init__(flags, modalities, subsets)

@@ -12,6 +12,7 @@ import torch.distributed as dist
 from . import _lib as L
 from .fusion import set_subsets
 from .losses import calc_joint_elbo_loss, calc_klds, calc_klds_style, calc_log_probs, calc_poe_loss
+from .mmvae import VAETextMimic  # noqa: F401
 from .mmvae import MMVaeMimic, VAEtrimodalMimic
 from .modalities import MimicLateral, MimicPA, MimicText
 from .networks import DecoderImg, DecoderText, EncoderImg, EncoderText
@@ -80,6 +81,8 @@ class Experiment:
     def set_model(self):
         if list(self.modalities.keys()) == ['PA', 'Lateral', 'text']:
             return VAEtrimodalMimic(self.flags, self.modalities, self.subsets)
+        if list(self.modalities.keys()) == ['text']:
+            return VAETextMimic(self.flags, self.modalities, self.subsets)
         return MMVaeMimic(self.flags, self.modalities, self.subsets)
 
     def set_optimizer(self, exchange=None):

@@ -257,7 +257,7 @@ def test_word_encoding_state_dict_matches_the_reference_layout():
     against the reference's own state_dict (oracle/gen_golden.py asserts key order on the live model)."""
     import mopoe_mimic_b200 as P
     from oracle import mopoe_oracle as O
-    for L_ in (128, 512):
+    for L_ in (128, 1024):
         kw = dict(batch_size=4, DIM_img=8, DIM_text=16, class_dim=16, text_encoding='word', vocab_size=48, len_sequence=L_)
         spec = O.param_spec(O.default_flags(**kw))
         exp = P.Experiment(P.default_flags(device=torch.device('cpu'), **kw))

@@ -30,6 +30,8 @@ CASES = {
     'patext_moe': dict(SMALL, mods=('PA', 'text'), method='moe'),
     'patext_poe': dict(SMALL, mods=('PA', 'text'), method='poe', batch_size=5),
     'tri_jsd': dict(SMALL, method='jsd'),
+    'text_only': dict(SMALL, mods=('text',)),                    # VAETextMimic
+    'text_only_word_moe': dict(SMALL, mods=('text',), method='moe', text_encoding='word', vocab_size=64, len_sequence=1024),
     'tri_word': dict(SMALL, text_encoding='word', vocab_size=48, len_sequence=128),      # Embedding + 6 blocks, V = 48
     'tri_word_bigvocab': dict(batch_size=4, DIM_img=16, DIM_text=16, class_dim=32, text_encoding='word', vocab_size=304,
                               len_sequence=128),                                         # V > 256: looped categorical kernels
