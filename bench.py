@@ -53,6 +53,9 @@ def parse():
                     help='Adam learning rate.  The reference default (1e-3) makes the reference model itself diverge to '
                          'inf/NaN on the SECOND step with default init on random inputs (checked with the CPU oracle); '
                          '1e-5 keeps the synthetic run finite.  Throughput does not depend on it')
+    ap.add_argument('--text-wire', default='onehot', choices=['onehot', 'uint8'],
+                    help='host format of the char text in the e2e leg: the reference\'s fp32 one-hot rows [B,1024,71] '
+                         '(default) or one byte per token, expanded on the device (SURVEY N3)')
     ap.add_argument('--config', default='2', choices=sorted(CONFIGS), help='BASELINE.json configuration (default 2)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-batch', type=int, default=16)
@@ -196,6 +199,10 @@ def main():
             'text': torch.nn.functional.one_hot(torch.randint(0, 71, (B, 1024), generator=g), 71).float().pin_memory()}
     host = {k: v for k, v in host.items() if k in fl.mods}
     resident = {k: v.to(dev) for k, v in host.items()}
+    if args.text_wire == 'uint8' and 'text' in host:
+        if args.no_graph:
+            raise SystemExit('--text-wire uint8 needs the graphed step (the expansion kernel fills its static input)')
+        host['text'] = host['text'].argmax(-1).to(torch.uint8).pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
     ar = FlatGradAllReduce() if (world > 1 and not peer) else None      # bucketed NCCL all-reduce of the flat gradients
@@ -367,7 +374,7 @@ def main():
                 'data': 'synthetic',
                 'config': {'workload': cfg['workload'], 'per_gpu_batch': B, 'global_batch': B * world,
                            'parallelism': 'dp%d' % world + ('' if world == 1 else (' peer-memory fused exchange' if peer else ' nccl all-reduce')), 'cuda_graph': not args.no_graph, 'lr': args.lr,
-                           'branch_streams': os.environ.get('MOPOE_BRANCH_STREAMS', '1') != '0', 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
+                           'branch_streams': os.environ.get('MOPOE_BRANCH_STREAMS', '1') != '0', 'text_wire': args.text_wire, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
                 'clocks': sampler.summary(),
                 'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s',
                         'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h},

@@ -261,6 +261,9 @@ int mopoe_jsd_divergence_bwd(int K, int B, int D, const float* const* mu, const 
  * multiple of 8) in MOPOE_F32 / MOPOE_BF16, plus the int32 indices: nn.Embedding (word_encoding/mmvae_text_enc.py:27-28,69)
  * becomes a GEMM of these rows with the embedding matrix, its gradient the matching weight-gradient GEMM. */
 int mopoe_onehot(const float* idx, int64_t rows, int V, int Vp, void* out, int out_dtype, int32_t* idx_out, void* stream);
+/* uint8 character indices [rows] -> fp32 one-hot rows [rows, V] (V <= 256): the device side of the 1-byte-per-token wire
+ * format; the reference builds these rows on the host (dataio/MimicDataset.py:92-96, utils/text.py:13-34). */
+int mopoe_onehot_u8(const uint8_t* idx, int64_t rows, int V, float* out, void* stream);
 
 /* All weight re-layouts of a step in ONE launch.  jobs_dev: DEVICE array of njobs descriptors (same meaning as the
  * arguments of mopoe_pack_weight_tiled; form 1 fills dst[0..3] / dst[0..1], the others dst[0]); tile0 = index of the

@@ -1077,6 +1077,25 @@ extern "C" int mopoe_onehot(const float* idx, int64_t rows, int V, int Vp, void*
     return 0;
 }
 
+// Character indices shipped as one byte per token (SURVEY N3 wire format: 1 KB instead of 291 KB per report) -> the fp32
+// one-hot rows [rows, V] the text encoder consumes (dataio/MimicDataset.py:92-96 builds them on the host in the reference).
+__global__ void __launch_bounds__(256) onehot_u8_kernel(const uint8_t* __restrict__ idx, long long rows, int V,
+                                                        float* __restrict__ out) {
+    const long long total = rows * V;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long row = i / V;
+        out[i] = ((int)(i - row * V) == (int)idx[row]) ? 1.f : 0.f;
+    }
+}
+extern "C" int mopoe_onehot_u8(const uint8_t* idx, int64_t rows, int V, float* out, void* stream) {
+    MOPOE_REQUIRE(rows > 0 && V >= 1 && V <= 256, "onehot_u8: rows=%lld V=%d", (long long)rows, V);
+    long long blocks = ceil_div64(rows * V, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    onehot_u8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(idx, rows, V, out);
+    MOPOE_CHECK_LAUNCH("onehot_u8");
+    return 0;
+}
+
 // ---- flat Adam -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n4,

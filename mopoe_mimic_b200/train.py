@@ -230,27 +230,46 @@ class GraphedTrainStep:
         self.keys = (['total_loss', 'joint_divergence'] + ['kld.' + k for k in out['klds']]
                      + ['log_prob.' + k for k in out['log_probs']])
 
+    def _is_wire_text(self, batch):
+        """char text shipped as uint8 indices [B, L] instead of fp32 one-hot rows [B, L, 71]"""
+        t = batch.get('text')
+        return t is not None and t.dtype == torch.uint8 and t.dim() == 2 and self.static['text'].dim() == 3
+
+    def _expand_text(self, idx_dev):
+        st = self.static['text']
+        L.call('mopoe_onehot_u8', L.ptr(idx_dev), idx_dev.numel(), st.shape[-1], L.ptr(st), L.stream_ptr())
+
     def _stage_host_batch(self, batch):
         """Host (pinned) batch -> one of two device staging sets on a COPY stream, so the H2D transfer of step i+1
         runs under step i's graph instead of in front of its own (the loader side of run_epochs.py:61-62)."""
+        wire = self._is_wire_text(batch)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
             self._staging = [{k: torch.empty_like(t) for k, t in self.static.items()} for _ in range(2)]
             self._staged = [torch.cuda.Event(), torch.cuda.Event()]
             self._consumed = [None, None]
             self._slot = 0
+        if wire and 'text_u8' not in self._staging[0]:
+            for sset in self._staging:
+                sset['text_u8'] = torch.empty(self.static['text'].shape[:2], dtype=torch.uint8, device=self.static['text'].device)
         i = self._slot
         self._slot ^= 1
         cs, cur = self._copy_stream, torch.cuda.current_stream()
         if self._consumed[i] is not None:
             cs.wait_event(self._consumed[i])          # the step that last read this staging set has copied it out
         with torch.cuda.stream(cs):
-            for k, t in self._staging[i].items():
-                t.copy_(batch[k], non_blocking=True)
+            for k in self.static:
+                if k == 'text' and wire:
+                    self._staging[i]['text_u8'].copy_(batch['text'], non_blocking=True)
+                else:
+                    self._staging[i][k].copy_(batch[k], non_blocking=True)
             self._staged[i].record(cs)
         cur.wait_event(self._staged[i])
         for k, t in self.static.items():
-            t.copy_(self._staging[i][k], non_blocking=True)
+            if k == 'text' and wire:
+                self._expand_text(self._staging[i]['text_u8'])
+            else:
+                t.copy_(self._staging[i][k], non_blocking=True)
         if self._consumed[i] is None:
             self._consumed[i] = torch.cuda.Event()
         self._consumed[i].record(cur)
@@ -259,8 +278,12 @@ class GraphedTrainStep:
         if all(not batch[k].is_cuda for k in self.static):
             self._stage_host_batch(batch)
         else:
+            wire = self._is_wire_text(batch)
             for k, t in self.static.items():
-                t.copy_(batch[k], non_blocking=True)
+                if k == 'text' and wire:
+                    self._expand_text(batch['text'].contiguous())
+                else:
+                    t.copy_(batch[k], non_blocking=True)
         self.graph.replay()
         if self.graph_b is not None:
             self.allreduce(self.exp.mm_vae.flat_grads)

@@ -294,6 +294,34 @@ def test_graphed_step_pipelined_host_batches():
     assert len(set(seqs[0])) == len(seqs[0])
 
 
+def test_graphed_step_uint8_text_wire_format():
+    """char text shipped as one byte per token ([B, L] uint8 indices, expanded to one-hot rows on the device) must give
+    exactly the losses of the reference format (fp32 one-hot rows [B, L, 71]) — from pinned host memory and from device."""
+    import mopoe_mimic_b200 as P
+    kw = dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32)
+    ofl = O.default_flags(**kw)
+    state = O.make_state(ofl, 0, torch.float32)
+    host = [{k: v.pin_memory() for k, v in O.make_batch(ofl, 20 + i, torch.float32).items()} for i in range(4)]
+    wire = [dict(b, text=b['text'].argmax(-1).to(torch.uint8).pin_memory()) for b in host]
+    seqs = []
+    for mode in ('onehot', 'uint8_host', 'uint8_device'):
+        exp = P.Experiment(P.default_flags(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, compute_dtype='fp32'))
+        exp.mm_vae.load_state_dict(state)
+        exp.set_optimizer()
+        exp.mm_vae.train()
+        exp.mm_vae.rt.seed = 7
+        exp.mm_vae.rt.injected_eps = torch.zeros(8, 32, device='cuda')
+        gs = P.GraphedTrainStep(exp, {k: v.cuda() for k, v in host[0].items()}, warmup=1)
+        outs = []
+        for b, w in zip(host, wire):
+            feed = b if mode == 'onehot' else (w if mode == 'uint8_host' else {k: v.cuda() for k, v in w.items()})
+            outs.append(gs(feed)[:1].clone())
+        torch.cuda.synchronize()
+        seqs.append([float(o) for o in outs])
+    assert seqs[0] == seqs[1] == seqs[2]
+    assert len(set(seqs[0])) == len(seqs[0])
+
+
 @pytest.mark.parametrize('B,S', [(256, 7), (1024, 7), (2048, 7), (128, 3), (64, 7)])
 def test_full_size_selection_ranges(B, S):
     """BASELINE.json batch sizes: k * floor(B/S) boundaries, identical to the oracle's."""
