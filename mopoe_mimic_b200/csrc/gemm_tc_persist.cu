@@ -201,6 +201,18 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+// experimental 256 x BN tile variant (gemm_tc_persist2.cu): only with MOPOE_GEMM_BM256=1
+int mopoe_conv_gemm_tc_batched_bm256(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                                     const mopoe_rows_t* D, void* stream);
+static int bm256_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_GEMM_BM256");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
 static bool g_persist_attr_set = false;
 static int g_num_sms = 0;
 
@@ -209,6 +221,18 @@ int mopoe_conv_gemm_tc_batched(int nprob, const mopoe_window_t* A, const void* c
                                const mopoe_rows_t* D, void* stream) {
     MOPOE_REQUIRE(nprob >= 1 && nprob <= TCP_MAXP, "conv_gemm_tc_batched: nprob=%d", nprob);
     if (!mopoe_tc_init_state()) MOPOE_FAIL("conv_gemm_tc_batched: tcgen05 path unavailable on this device");
+    if (bm256_enabled()) {
+        bool same = true;
+        for (int i = 1; i < nprob; ++i)
+            same = same && A[i].E0 == A[0].E0 && A[i].E1 == A[0].E1 && A[i].E2 == A[0].E2 && A[i].R == A[0].R &&
+                   A[i].KW == A[0].KW && D[i].N == D[0].N && D[i].s0 == D[0].s0 && D[i].s1 == D[0].s1 &&
+                   D[i].s2 == D[0].s2 && D[i].d == D[0].d && D[i].d_dtype == D[0].d_dtype;
+        if (same) {
+            const int rc = mopoe_conv_gemm_tc_batched_bm256(nprob, A, Wp, bias, D, stream);
+            if (rc == 2) return 0;
+            if (rc == 1) return 1;
+        }
+    }
     TcPersistParams p;
     p.E0 = A[0].E0; p.E1 = A[0].E1; p.E2 = A[0].E2; p.R = A[0].R; p.KW = A[0].KW; p.N = D[0].N;
     for (int i = 1; i < nprob; ++i) {
