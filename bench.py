@@ -6,8 +6,9 @@
         bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...      # the CPU oracle port of the reference step on the host cores
 
-One "step" = forward (3 encoders, fused MoPoE, 3 decoders, likelihoods) + ELBO + backward + gradient all-reduce
-(N > 1) + Adam on a synthetic batch: configs[1] of BASELINE.json (PA+Lateral+text, 128 px, 1024x71 char text,
+One "step" = forward (3 encoders, fused MoPoE, 3 decoders, likelihoods) + ELBO + backward + gradient exchange and Adam
+(N > 1: ONE fused reduce-scatter + Adam + all-gather kernel over NVLink peer memory, or --dp-exchange nccl) on a
+synthetic batch: configs[1] of BASELINE.json (PA+Lateral+text, 128 px, 1024x71 char text,
 class_dim 128, per-GPU batch 256, bf16 storage / fp32 accumulation).  Weak scaling: per-GPU batch is fixed.
 Prints ONE JSON line on rank 0.
 """
