@@ -197,6 +197,11 @@ CASES = OrderedDict([
                             style_dims={'PA': 8, 'Lateral': 16, 'text': 24})),
     ('small_tri_word', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, text_encoding='word', vocab_size=48,
                            len_sequence=128)),
+    # combinations (pins for the oracle; GPU parity cases for them are next-round work)
+    ('small_tri_jsd_style', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, method='jsd',
+                                style_dims={'PA': 8, 'Lateral': 8, 'text': 16})),
+    ('small_tri_word_style_moe', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, method='moe', text_encoding='word',
+                                     vocab_size=48, len_sequence=128, style_dims={'PA': 8, 'Lateral': 8, 'text': 8})),
     ('small_tri_jsd', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, method='jsd')),
     ('small_patext_jsd', dict(batch_size=9, DIM_img=16, DIM_text=16, class_dim=32, mods=('PA', 'text'), method='jsd')),
 ])
