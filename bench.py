@@ -63,6 +63,14 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='launch every kernel from the host instead of replaying the captured CUDA graph')
     ap.add_argument('--profile-kernels', action='store_true', help='print per-op-class device time of one step')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: the per-GPU batch is fixed (default, the config\'s); strong: --global-batch is split over the '
+                         'ranks (BASELINE config 3: global 2048 -> 1024 / 512 / 256 per GPU at 2 / 4 / 8 GPUs)')
+    ap.add_argument('--global-batch', type=int, default=2048, help='global batch of --scaling strong')
+    ap.add_argument('--cpu-kind', default='auto', choices=['auto', 'reference', 'port'],
+                    help='CPU baseline: the unmodified reference vendored under baseline/_ref (auto: when present and the '
+                         'config is the tri-modal joint_elbo one) or the oracle port')
+    ap.add_argument('--no-dp-check', action='store_true', help='N > 1: skip the exchange-vs-all-reduce parity step')
     return ap.parse_args()
 
 
@@ -99,10 +107,29 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_reference(args, steps, warmup, min_seconds=None):
-    """The reference's CPU path: its algorithm restated in oracle/ (pure torch CPU ops, same call sites), full
-    step = forward + ELBO + backward + Adam, fp32, all host threads, batch `cpu_batch` (a bounded sample of the
-    same workload)."""
+    """The reference's CPU path on the host cores: full step = forward + ELBO + backward + Adam, fp32, all host threads,
+    batch `cpu_batch` (a bounded sample of the same workload).  kind "reference": the UNMODIFIED reference modules
+    vendored under baseline/_ref (baseline/reference_step.py); kind "port": its algorithm restated in oracle/ (pure torch
+    CPU ops, same call sites) — used when the vendored tree is absent or the config needs the oracle's model shim
+    (PA+text / poe: the shipped VAEtrimodalMimic cannot run them)."""
     import torch
+    cfg_flags = CONFIGS[args.config]['flags']
+    native = not any(k in cfg_flags for k in ('mods', 'method'))
+    if args.cpu_kind != 'port' and native:
+        try:
+            from baseline import reference_step as RS
+            if RS.available():
+                sec, n, cores, loss = RS.timed_run(args.cpu_batch, args.lr, steps, warmup, min_seconds,
+                                                   img_size=cfg_flags.get('img_size', 128), class_dim=cfg_flags.get('class_dim', 128))
+                return {'value': args.cpu_batch / sec, 'unit': 'samples/s', 'cores': cores, 'kind': 'reference',
+                        'sample': '%d timed steps (after %d warm-up) of batch %d, fp32, the unmodified reference '
+                                  '(baseline/_ref) on torch CPU, %.2f s/step' % (n, warmup, args.cpu_batch, sec)}, sec
+            if args.cpu_kind == 'reference':
+                raise RuntimeError('baseline/_ref is missing: run __graft_entry__.build() where /root/reference exists')
+        except Exception as e:      # noqa: BLE001
+            if args.cpu_kind == 'reference':
+                raise
+            print('reference arm: vendored reference unavailable (%r); timing the oracle port' % (e,), file=sys.stderr)
     from oracle import mopoe_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -143,10 +170,49 @@ def run_reference(args):
             'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
             'config': {'workload': CONFIGS[args.config]['workload'], 'per_gpu_batch': args.cpu_batch,
-                       'note': 'CPU oracle port of the reference step'},
+                       'note': 'the reference step on the host CPU (%s)' % cb['kind']},
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
+
+
+def run_dp_check(exp, px_obj, world, rank, dev):
+    """DP parity where the driver can see it (the -m gpu pytest is skipped on a 1-GPU box): ONE more optimizer step on
+    the gradients the last timed step left in the flat buffers, done twice — by the fused peer-memory exchange kernel
+    on the live buffers, and by the path it replaces (NCCL all-reduce of the gradients, then the flat Adam kernel with
+    grad_scale = 1/world) on clones — plus a check that all replicas hold bit-identical parameters afterwards."""
+    import torch
+    import torch.distributed as dist
+    from mopoe_mimic_b200 import _lib as L
+    opt = exp.optimizer
+    vae = exp.mm_vae
+    torch.cuda.synchronize()
+    dist.barrier()
+    px_obj.gather_moments(opt.m, opt.v)                 # owner-sharded moments -> full tensors on every rank
+    eng = vae.rt.engine
+    L.call('mopoe_step_advance', L.ptr(eng.rng_step), L.ptr(opt.step_t), L.ptr(opt.coef), float(opt.lr),
+           float(opt.betas[0]), float(opt.betas[1]), L.stream_ptr())
+    p_ref, m_ref, v_ref = opt.p.clone(), opt.m.clone(), opt.v.clone()
+    g_sum = opt.g.clone()
+    dist.all_reduce(g_sum)
+    L.call('mopoe_adam_flat_dev', L.ptr(p_ref), L.ptr(g_sum), L.ptr(m_ref), L.ptr(v_ref), p_ref.numel(), L.ptr(opt.coef),
+           float(opt.betas[0]), float(opt.betas[1]), float(opt.eps), 1.0 / world, L.stream_ptr())
+    px_obj.adam_step(opt.m, opt.v, opt.coef, opt.betas, opt.eps)
+    eng.invalidate_packs()
+    torch.cuda.synchronize()
+    err = (opt.p - p_ref).abs().max().reshape(1).double()
+    scale = p_ref.abs().max().reshape(1).double()
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    hi, lo = opt.p.clone(), opt.p.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    spread = (hi - lo).abs().max().reshape(1).double()
+    px_obj.check()
+    del p_ref, m_ref, v_ref, g_sum, hi, lo
+    return {'what': 'one step: fused peer-memory exchange kernel vs NCCL all-reduce + flat Adam (grad_scale 1/world)',
+            'max_abs_err': float(err), 'param_abs_max': float(scale),
+            'params_equal_across_ranks': bool(float(spread) == 0.0), 'max_param_spread_across_ranks': float(spread),
+            'world': world, 'multicast': bool(getattr(px_obj, 'multicast', False))}
 
 
 def main():
@@ -166,32 +232,34 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     cfg = CONFIGS[args.config]
     B = args.batch or cfg['batch']
+    if args.scaling == 'strong':
+        if args.global_batch % world:
+            raise SystemExit('--global-batch %d does not divide over %d ranks' % (args.global_batch, world))
+        B = args.global_batch // world
     fl = P.default_flags(device=dev, batch_size=B, compute_dtype=args.dtype, distributed=world > 1, world_size=world,
                          initial_learning_rate=args.lr, **cfg['flags'])
     torch.manual_seed(0)
     exp = P.Experiment(fl)
     from mopoe_mimic_b200.dp import FlatGradAllReduce, PeerExchange
     peer = world > 1 and args.dp_exchange == 'peer'
-    px = None
+    px_obj = None
     if peer:
         # every rank must take the same path: agree on whether the NVLink symmetric-memory plumbing came up
         ok = torch.ones(1, device=dev)
         try:
-            px = PeerExchange(dev)
+            px_obj = PeerExchange(dev)
         except Exception as e:       # noqa: BLE001
             print('rank %d: peer-memory exchange unavailable (%r)' % (rank, e), file=sys.stderr)
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if float(ok) == 0.0:
-            peer, px = False, None
+            peer, px_obj = False, None
             if rank == 0:
                 print('falling back to the NCCL all-reduce exchange on all ranks', file=sys.stderr)
-    exp.set_optimizer(exchange=px)     # (a PeerExchange broadcasts rank 0's parameters)
+    exp.set_optimizer(exchange=px_obj)     # (a PeerExchange broadcasts rank 0's parameters)
     vae = exp.mm_vae
     vae.train()
-    if world > 1 and not peer:
-        dist.broadcast(vae.flat_params, 0)
-        exp.optimizer.grad_scale = 1.0 / world
+    # (NCCL path: train_step / GraphedTrainStep attach the all-reduce — rank-0 parameter broadcast + 1/world gradient scale)
     # synthetic inputs of the reference's shapes (dataio/MimicDataset.py:414-428), true one-hot text
     g = torch.Generator(device='cpu').manual_seed(1 + rank)
     px = fl.img_size
@@ -284,15 +352,18 @@ def main():
     ms_e2e = f0.elapsed_time(f1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    # roofline of the dominant kernel family (implicit-GEMM convs): one instrumented step with a CUDA event pair
-    # around every GEMM launch.  The events are captured INTO a copy of the step graph (event-record nodes), so the
-    # durations are the kernels' own in-step durations — bracketing eager launches instead also counts the host's
-    # enqueue latency between the event and the kernel, which is comparable to these 20-100 us kernels.
-    eng = vae.rt.engine
+    # Rooflines: one instrumented step with a CUDA event pair around EVERY C-ABI call (mopoe_mimic_b200/_lib.call), each
+    # annotated by its caller with the algorithmic work of the launch (GEMM flops; bytes of the HBM-bound passes).  The
+    # events are captured INTO a copy of the step graph (event-record nodes), so the durations are the kernels' own
+    # in-step durations — bracketing eager launches instead also counts the host's enqueue latency between the event and
+    # the kernel, which is comparable to these 5-100 us kernels.
     prof, timing = None, None
+    dp_check = None
+    if world > 1 and peer and not args.no_dp_check:
+        dp_check = run_dp_check(exp, px_obj, world, rank, dev)
     if not args.no_graph:
         try:
-            eng.profile, eng.profile_external = [], True
+            L.PROFILE, L.PROFILE_EXTERNAL = [], True
             saved_dataset, fl.dataset = fl.dataset, 'testing'
             g2 = torch.cuda.CUDAGraph()
             # the instrumented copy runs the modality branches on ONE stream: an event pair around a kernel that shares
@@ -302,17 +373,19 @@ def main():
             try:
                 with torch.cuda.graph(g2, pool=gstep.graph.pool()):
                     P.forward_backward(exp, (dict(gstep.static), None))
+                    if world == 1:
+                        exp.optimizer.step()
             finally:
                 if saved_env is None:
                     os.environ.pop('MOPOE_BRANCH_STREAMS', None)
                 else:
                     os.environ['MOPOE_BRANCH_STREAMS'] = saved_env
             fl.dataset = saved_dataset
-            prof = eng.profile
+            prof = L.PROFILE
             for _ in range(3):
                 g2.replay()
             torch.cuda.synchronize()
-            _ = [p_[0].elapsed_time(p_[1]) for p_ in prof[:2]]
+            _ = [p_['a'].elapsed_time(p_['b']) for p_ in prof[:2]]
             timing = ('CUDA event pairs captured as nodes of a single-stream copy of the step graph (in-step kernel '
                       'durations; the timed step itself overlaps the modality branches on 3 streams)')
         except Exception as e:       # noqa: BLE001
@@ -320,13 +393,17 @@ def main():
             prof = None
             torch.cuda.synchronize()
         finally:
-            eng.profile, eng.profile_external = None, False
+            L.PROFILE, L.PROFILE_EXTERNAL = None, False
     if prof is None:
-        eng.profile = []
-        P.train_step(exp, (dict(resident), None), ar)          # eager: includes host enqueue latency per launch
-        torch.cuda.synchronize()
-        prof, eng.profile = eng.profile, None
+        L.PROFILE = []
+        try:
+            P.forward_backward(exp, (dict(resident), None))          # eager: includes host enqueue latency per launch
+            torch.cuda.synchronize()
+        finally:
+            prof, L.PROFILE = L.PROFILE, None
         timing = 'CUDA event pairs around eager launches (includes host enqueue latency)'
+    for p_ in prof:
+        p_['ms'] = p_['a'].elapsed_time(p_['b'])
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,37 +418,68 @@ def main():
         try:       # dram bytes of the step's largest GEMM launch, from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_roofline_traffic.json')))
             traffic = tj['dram_bytes_read'] + tj['dram_bytes_written']
-            traffic_note = ('ncu dram read+write of ONE launch (%s); algorithmic bytes of that launch %.1f MB'
+            traffic_note = ('NOT measured in this run: ncu --set full dram read+write of ONE launch (%s) from the committed '
+                            'capture profiles/r1_ncu_gemm_persist.txt; algorithmic bytes of that launch %.1f MB'
                             % (tj['kernel'], tj['algorithmic_bytes'] / 1e6))
         except Exception:
             pass
         peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
         peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback'
-        gemm_ms = sum(p_[0].elapsed_time(p_[1]) for p_ in prof)
-        gemm_flop = sum(p_[2] for p_ in prof)
+        gprof = [p_ for p_ in prof if p_.get('flops')]
+        gemm_ms = sum(p_['ms'] for p_ in gprof)
+        gemm_flop = sum(p_['flops'] for p_ in gprof)
         by_kind = {}
-        for a, b, f, kind, _tag in prof:
-            d = by_kind.setdefault(kind, [0.0, 0.0, 0])
-            d[0] += a.elapsed_time(b)
-            d[1] += f
+        for p_ in gprof:
+            d = by_kind.setdefault(p_['kind'], [0.0, 0.0, 0])
+            d[0] += p_['ms']
+            d[1] += p_['flops']
             d[2] += 1
         achieved = gemm_flop / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        # HBM side (north_star items 2-3): algorithmic bytes of every fusion / likelihood / BatchNorm / Adam launch of the
+        # step divided by its in-step duration, per kernel class, against the measured copy bandwidth
+        peak_hbm = peaks.get('hbm_gbs', 6550.0)
+        hbm = {}
+        for p_ in prof:
+            if p_.get('bytes'):
+                d = hbm.setdefault(p_['kind'], [0.0, 0.0, 0])
+                d[0] += p_['ms']
+                d[1] += p_['bytes']
+                d[2] += 1
+        roofline_hbm = {'peak': peak_hbm, 'unit': 'GB/s', 'peak_source': 'measured (MEASURED_PEAKS.json hbm_gbs)' if peaks else 'fallback',
+                        'note': 'achieved = algorithmic bytes (SURVEY.md 8d) / in-step launch time; the fusion kernels move '
+                                '<5 MB per launch and are launch-latency-bound by construction',
+                        'classes': {k: {'ms': v[0], 'MB': v[1] / 1e6, 'launches': v[2],
+                                        'achieved': (v[1] / 1e9) / (v[0] * 1e-3) if v[0] > 0 else 0.0,
+                                        'frac': ((v[1] / 1e9) / (v[0] * 1e-3) / peak_hbm) if v[0] > 0 else 0.0}
+                                    for k, v in sorted(hbm.items())}}
+        tot_ms = sum(v[0] for v in hbm.values())
+        tot_b = sum(v[1] for v in hbm.values())
+        roofline_hbm['all'] = {'ms': tot_ms, 'MB': tot_b / 1e6, 'achieved': (tot_b / 1e9) / (tot_ms * 1e-3) if tot_ms else 0.0,
+                               'frac': (tot_b / 1e9) / (tot_ms * 1e-3) / peak_hbm if tot_ms else 0.0}
         if os.environ.get('MOPOE_BENCH_SHAPES'):       # developer aid: GEMM time per problem shape
             agg = {}
-            for a, b, f, kind, tag in prof:
-                d = agg.setdefault(tag, [0.0, 0.0, 0])
-                d[0] += a.elapsed_time(b)
-                d[1] += f
+            for p_ in gprof:
+                d = agg.setdefault(p_.get('tag'), [0.0, 0.0, 0])
+                d[0] += p_['ms']
+                d[1] += p_['flops']
                 d[2] += 1
             for tag, d in sorted(agg.items(), key=lambda kv: -kv[1][0]):
                 print('%-46s n=%3d %8.3f ms %7.1f TF/s' % (tag, d[2], d[0], d[1] / d[0] / 1e9), file=sys.stderr)
+            other = {}
+            for p_ in prof:
+                if not p_.get('flops'):
+                    d = other.setdefault(p_['name'], [0.0, 0])
+                    d[0] += p_['ms']
+                    d[1] += 1
+            for name, d in sorted(other.items(), key=lambda kv: -kv[1][0]):
+                print('%-46s n=%3d %8.3f ms' % (name, d[1], d[0]), file=sys.stderr)
         value = world * B * args.steps / (ms * 1e-3)
         metric = 'train samples/sec (3-modality MoPoE, 128px)'
         if args.config != '2':
             metric = 'train samples/sec (BASELINE config %s)' % args.config
         line = {'metric': metric, 'value': value, 'unit': 'samples/s',
                 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
-                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype,
+                'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': args.dtype,
                 'data': 'synthetic',
                 'config': {'workload': cfg['workload'], 'per_gpu_batch': B, 'global_batch': B * world,
                            'parallelism': 'dp%d' % world + ('' if world == 1 else (' peer-memory fused exchange' if peer else ' nccl all-reduce')), 'cuda_graph': not args.no_graph, 'lr': args.lr,
@@ -385,10 +493,13 @@ def main():
                 'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                              'frac': achieved / peak_tf, 'traffic': traffic, 'traffic_note': traffic_note, 'peak_source': peak_src,
                              'timing': timing,
-                             'kernel': 'implicit-GEMM conv family (fprop+dgrad+wgrad), %d launches/step' % len(prof),
+                             'kernel': 'implicit-GEMM conv family (fprop+dgrad+wgrad), %d launches/step' % len(gprof),
                              'gemm_ms_per_step': gemm_ms, 'step_tensor_frac': value / world * cfg['gflop'] / 1e3 / peak_tf,
                              'by_kind': {k: {'ms': v[0], 'tflops': (v[1] / (v[0] * 1e-3) / 1e12) if v[0] > 0 else 0.0, 'launches': v[2]}
-                                         for k, v in by_kind.items()}}}
+                                         for k, v in by_kind.items()}},
+                'roofline_hbm': roofline_hbm}
+        if dp_check is not None:
+            line['dp_check'] = dp_check
         if not args.no_cpu_baseline:
             cb, _ = cpu_reference(args, 12, 1, min_seconds=10.0)
             line['cpu_baseline'] = cb

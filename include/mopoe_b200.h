@@ -226,16 +226,24 @@ int mopoe_laplace_logprob_sum(const float* loc, const float* x, int64_t n, float
 /* dloc_i = (*gout) * sign(x_i - loc_i) / scale   (gradient of the log-prob sum; gout on device) */
 int mopoe_laplace_logprob_bwd(const float* loc, const float* x, int64_t n, float scale, const float* gout,
                               float* dloc, void* stream);
+/* out_i = -(log(2*scale) + |x_i - loc_i| / scale): the elementwise density the evaluation callers reduce per sample
+ * (utils/likelihood.py:120-121) */
+int mopoe_laplace_logprob_elem(const float* loc, const float* x, int64_t n, float scale, float* out, void* stream);
 /* LogSoftmax(dim=vocab) of the text decoder (char_encoding/DataGeneratorText.py:51,75) fused with
  * OneHotCategorical(logits).log_prob(target).sum() (modalities/utils.py:7-8, MimicText.py:37-40).
- * y: pre-softmax [rows, V] fp32 (rows = B*L); target: one-hot(ish) fp32 [rows, V] (argmax taken) or NULL
- * with idx int32 [rows].  logits_out [rows, V] = log_softmax(y) (may be NULL); idx_out (may be NULL)
- * receives the argmax; out[0] = sum_rows logits[row, idx]. */
+ * y: pre-softmax [rows, V] fp32 (rows = B*L); target: ONE-HOT fp32 [rows, V] (the argmax is taken, first maximum wins:
+ * rows that are not strictly one-hot — all-zero or soft targets — deviate from OneHotCategorical.log_prob's
+ * sum(target * logits); the reference's data is always one-hot) or NULL with idx int32 [rows].  logits_out [rows, V] =
+ * log_softmax(y) (may be NULL); idx_out (may be NULL) receives the argmax; lse_out (may be NULL) the row logsumexp
+ * for the flat backward — filled only when mopoe_categorical_has_lse(y, target, V) is 1 (V <= 256, 16-byte aligned
+ * buffers: the staged-row kernel), NaN otherwise; out[0] = sum_rows logits[row, idx]. */
 int mopoe_categorical_logprob_sum(const float* y, const float* target, const int32_t* idx, int64_t rows,
-                                  int V, float* logits_out, int32_t* idx_out, float* out, double* ws,
+                                  int V, float* logits_out, int32_t* idx_out, float* lse_out, float* out, double* ws,
                                   int nchunk, void* stream);
-/* dy[row, v] = (*gout) * (onehot(idx)[v] - softmax(y)[row, v]) + dlogits-path (NULL) */
-int mopoe_categorical_logprob_bwd(const float* y, const int32_t* idx, int64_t rows, int V,
+int mopoe_categorical_has_lse(const float* y, const float* target, int V);
+/* dy[row, v] = (*gout) * (onehot(idx)[v] - softmax(y)[row, v]).  lse: the row logsumexp saved by the forward (one flat
+ * elementwise pass) or NULL (the row softmax is recomputed). */
+int mopoe_categorical_logprob_bwd(const float* y, const int32_t* idx, const float* lse, int64_t rows, int V,
                                   const float* gout, float* dy, void* stream);
 
 /* ---- optimizer: torch.optim.Adam defaults (experiment.py:171-178) over the FLAT
@@ -285,9 +293,11 @@ int mopoe_pack_weights_batched(const mopoe_pack_job_t* jobs_dev, int njobs, int 
  * buffer, its flat parameter buffer and its flag array (>= 2*world uint32, zero-initialised before the first call).
  * Rank `rank` sums slice [rank*ceil(n/4/world)*4, ...) of all gradient buffers in rank order, multiplies by grad_scale,
  * applies Adam (moments m, v: local, only the own slice is touched) and stores the new parameters into every rank's
- * parameter buffer.  state: 2 local uint32 {epoch (initialise to 1), 0}.  coef as mopoe_adam_flat_dev.  Every rank
- * must enqueue the same sequence of calls; the kernel completes only when all peers are done with this rank's
- * buffers.  CUDA-graph capturable (nothing step-dependent is a launch argument).
+ * parameter buffer.  state: 4 local uint32 {epoch (initialise to 1), 0, error, 0}.  coef as mopoe_adam_flat_dev.  Every
+ * rank must enqueue the same sequence of calls; the kernel completes only when all peers are done with this rank's
+ * buffers.  CUDA-graph capturable (nothing step-dependent is a launch argument).  The flag waits are bounded by
+ * MOPOE_DP_TIMEOUT_S seconds (environment, default 600, 0 = unbounded); an expired wait never traps: it stores
+ * 1 + 16*barrier + missing_rank into state[2] and returns, and the caller must treat the step as failed.
  * mc_grad / mc_param (both or neither): NVSwitch multicast addresses of the gradient / parameter buffers.  When given,
  * the sum is formed inside the switch (multimem.ld_reduce) and the parameters are broadcast by it (multimem.st); the
  * summation order is then the switch's, not rank order. */

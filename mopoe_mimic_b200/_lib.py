@@ -87,8 +87,10 @@ SIGNATURES = {
     'mopoe_fusion_bwd': (_I, [C.POINTER(FusionCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mopoe_laplace_logprob_sum': (_I, [_P, _P, _L, _F, _P, _P, _I, _P]),
     'mopoe_laplace_logprob_bwd': (_I, [_P, _P, _L, _F, _P, _P, _P]),
-    'mopoe_categorical_logprob_sum': (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P]),
-    'mopoe_categorical_logprob_bwd': (_I, [_P, _P, _L, _I, _P, _P, _P]),
+    'mopoe_laplace_logprob_elem': (_I, [_P, _P, _L, _F, _P, _P]),
+    'mopoe_categorical_logprob_sum': (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _P, _I, _P]),
+    'mopoe_categorical_has_lse': (_I, [_P, _P, _I]),
+    'mopoe_categorical_logprob_bwd': (_I, [_P, _P, _P, _L, _I, _P, _P, _P]),
     'mopoe_jsd_divergence_fwd': (_I, [_I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P, _P]),
     'mopoe_jsd_divergence_bwd': (_I, [_I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P]),
     'mopoe_onehot': (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
@@ -118,11 +120,38 @@ def load():
     return _lib
 
 
+# bench.py's per-call device timing: when PROFILE is a list, every call is bracketed by a CUDA event pair on the current
+# stream and appended as a dict(name, a, b, + the annotation set by annotate() just before the call: kind / flops / bytes /
+# tag).  PROFILE_EXTERNAL: create the events as `external` so that they become event-record NODES of a graph being captured.
+PROFILE = None
+PROFILE_EXTERNAL = False
+_ANNOT = None
+
+
+def annotate(**kw):
+    """algorithmic work of the NEXT call (consumed by it): kind=..., flops=..., bytes=..., tag=..."""
+    global _ANNOT
+    if PROFILE is not None:
+        _ANNOT = kw
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; raise RuntimeError(mopoe_last_error()) on failure."""
-    global LAUNCHES
+    global LAUNCHES, _ANNOT
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if PROFILE is not None:
+        ext = {'external': True} if PROFILE_EXTERNAL else {}
+        a, b = torch.cuda.Event(enable_timing=True, **ext), torch.cuda.Event(enable_timing=True, **ext)
+        a.record()
+        rc = getattr(lib, name)(*args)
+        b.record()
+        rec = {'name': name, 'a': a, 'b': b}
+        if _ANNOT:
+            rec.update(_ANNOT)
+        _ANNOT = None
+        PROFILE.append(rec)
+    else:
+        rc = getattr(lib, name)(*args)
     LAUNCHES += 1
     if rc != 0:
         raise RuntimeError('%s failed: %s' % (name, lib.mopoe_last_error().decode()))

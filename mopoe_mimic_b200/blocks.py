@@ -488,6 +488,7 @@ class LaplaceLogProbSumFn(torch.autograd.Function):
         n = loc.numel()
         nc = int(min(148 * 8, max(1, n // 4096)))
         out = eng.f32(1)
+        L.annotate(kind='laplace_nll', bytes=8 * n)            # loc + target, fp32
         L.call('mopoe_laplace_logprob_sum', L.ptr(loc), L.ptr(target), n, float(scale), L.ptr(out),
                L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
         ctx.save_for_backward(loc, target)
@@ -498,13 +499,18 @@ class LaplaceLogProbSumFn(torch.autograd.Function):
     def backward(ctx, g):
         loc, target = ctx.saved_tensors
         dloc = torch.empty_like(loc)
+        # SURVEY.md §8d counts forward + gradient as 3 passes (loc, target, dloc); the backward re-reads loc and target
+        L.annotate(kind='laplace_nll', bytes=4 * loc.numel())
         L.call('mopoe_laplace_logprob_bwd', L.ptr(loc), L.ptr(target), loc.numel(), ctx.scale,
                L.ptr(g.contiguous().float()), L.ptr(dloc), L.stream_ptr())
         return dloc, None, None, None
 
 
 class CategoricalLogProbSumFn(torch.autograd.Function):
-    """scores: pre-softmax [B, L, V]; target: one-hot [B, L, V], or token indices [B, L] (word encoding)."""
+    """scores: pre-softmax [B, L, V]; target: one-hot [B, L, V], or token indices [B, L] (word encoding).
+
+    Precondition (as in the reference's data): target rows are strictly one-hot.  The kernel gathers at argmax(target);
+    OneHotCategorical.log_prob computes sum(target * logits), which differs for all-zero or soft rows."""
 
     @staticmethod
     def forward(ctx, scores, target, eng):
@@ -513,26 +519,42 @@ class CategoricalLogProbSumFn(torch.autograd.Function):
         rows = scores.numel() // V
         nc = int(min(148 * 8, max(1, rows // 64)))
         out = eng.f32(1)
+        lib = L.load()
         if target.dim() == scores.dim() - 1:            # indices (MimicText.calc_log_prob one-hot encodes them, :37-40)
             idx = target.contiguous().reshape(-1).to(torch.int32)
-            L.call('mopoe_categorical_logprob_sum', L.ptr(scores), None, L.ptr(idx), rows, V, None, None,
-                   L.ptr(out), L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
+            tgt, idx_in, idx_out = None, idx, None
         else:
-            target = target.contiguous().float()
+            tgt = target.contiguous().float()
             idx = torch.empty(rows, dtype=torch.int32, device=scores.device)
-            L.call('mopoe_categorical_logprob_sum', L.ptr(scores), L.ptr(target), None, rows, V, None, L.ptr(idx),
-                   L.ptr(out), L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
-        ctx.save_for_backward(scores, idx)
+            idx_in, idx_out = None, idx
+        lse = eng.f32(rows) if lib.mopoe_categorical_has_lse(L.ptr(scores), L.ptr(tgt), V) else None
+        L.annotate(kind='categorical_nll', bytes=4 * rows * (V * (2 if tgt is not None else 1) + (1 if tgt is None else 0)))
+        L.call('mopoe_categorical_logprob_sum', L.ptr(scores), L.ptr(tgt), L.ptr(idx_in), rows, V, None, L.ptr(idx_out),
+               L.ptr(lse), L.ptr(out), L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
+        ctx.has_lse = lse is not None
+        ctx.save_for_backward(scores, idx, *([lse] if lse is not None else []))
         return out.view(())
 
     @staticmethod
     def backward(ctx, g):
-        scores, idx = ctx.saved_tensors
+        scores, idx = ctx.saved_tensors[:2]
+        lse = ctx.saved_tensors[2] if ctx.has_lse else None
         V = scores.shape[-1]
         d = torch.empty_like(scores)
-        L.call('mopoe_categorical_logprob_bwd', L.ptr(scores), L.ptr(idx), scores.numel() // V, V,
+        L.annotate(kind='categorical_nll', bytes=4 * scores.numel())      # the gradient write (3 passes in all)
+        L.call('mopoe_categorical_logprob_bwd', L.ptr(scores), L.ptr(idx), L.ptr(lse), scores.numel() // V, V,
                L.ptr(g.contiguous().float()), L.ptr(d), L.stream_ptr())
         return d, None, None
+
+
+def laplace_log_prob(loc, value, scale, eng):
+    """elementwise Laplace(loc, scale).log_prob(value) (no grad; the evaluation callers' `.log_prob`)"""
+    loc = loc.detach().contiguous().float()
+    value = value.detach().float().expand_as(loc).contiguous()
+    L.require_cuda(loc, value)
+    out = torch.empty_like(loc)
+    L.call('mopoe_laplace_logprob_elem', L.ptr(loc), L.ptr(value), loc.numel(), float(scale), L.ptr(out), L.stream_ptr())
+    return out
 
 
 def log_softmax_rows(scores, eng):
@@ -544,6 +566,6 @@ def log_softmax_rows(scores, eng):
     idx = torch.zeros(rows, dtype=torch.int32, device=scores.device)
     dummy = eng.f32(1)
     nc = int(min(148 * 8, max(1, rows // 64)))
-    L.call('mopoe_categorical_logprob_sum', L.ptr(scores), None, L.ptr(idx), rows, V, L.ptr(out), None, L.ptr(dummy),
+    L.call('mopoe_categorical_logprob_sum', L.ptr(scores), None, L.ptr(idx), rows, V, L.ptr(out), None, None, L.ptr(dummy),
            L.ptr(eng.ws64(nc)), nc, L.stream_ptr())
     return out

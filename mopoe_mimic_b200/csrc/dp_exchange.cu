@@ -15,13 +15,16 @@
 //   flags[r]         = epoch : rank r's gradients are final (its backward finished — stream order)
 //   flags[world + r] = epoch : rank r has finished READING my gradients and WRITING my parameters
 // The kernel does not complete before all peers have signalled the second flag, so whatever follows it in the stream
-// (the next step's zero_grad / forward) is safe.  Waits are bounded: a missing peer traps instead of hanging the GPU.
+// (the next step's zero_grad / forward) is safe.  Waits are bounded by a CONFIGURABLE window (MOPOE_DP_TIMEOUT_S, default
+// 600 s, 0 = wait forever): ranks may legitimately arrive far apart (rank-0-only evaluation / checkpointing, a loader
+// stall), so the default is in NCCL-watchdog territory.  A wait that does expire does NOT trap (that would poison the
+// CUDA context of every waiting rank): it records the missing flag in state[2], stops waiting, and the host raises from
+// PeerExchange.check() — the step's numbers are garbage but the process can still report and shut down cleanly.
 #include "common.cuh"
 
 constexpr int DPX_MAX_WORLD = 16;
 constexpr int DPX_THREADS = 256;
 constexpr int DPX_UNROLL = 4;
-constexpr unsigned long long DPX_TIMEOUT_NS = 30ull * 1000ull * 1000ull * 1000ull;
 
 struct DpxPeers {
     const float* grad[DPX_MAX_WORLD];
@@ -64,14 +67,16 @@ __device__ __forceinline__ void mc_st(float4* mc, const float4& v) {
 }
 
 // threads [0, world) of the block poll one flag each until it reaches `epoch`
-__device__ __forceinline__ void wait_flags(const unsigned int* flags, int world, unsigned int epoch) {
+__device__ __forceinline__ void wait_flags(const unsigned int* flags, int world, unsigned int epoch,
+                                           unsigned long long timeout_ns, unsigned int* state, int which) {
     if ((int)threadIdx.x < world) {
         const unsigned long long t0 = globaltimer_ns();
         while ((int)(ld_acquire_sys(flags + threadIdx.x) - epoch) < 0) {
             __nanosleep(64);
-            if (globaltimer_ns() - t0 > DPX_TIMEOUT_NS) {
-                printf("mopoe dp exchange: rank flag %d never reached epoch %u (peer missing?)\n", (int)threadIdx.x, epoch);
-                __trap();
+            if (timeout_ns && globaltimer_ns() - t0 > timeout_ns) {
+                // error flag for the host (PeerExchange.check): 1 + barrier * 16 + the rank that never arrived
+                atomicCAS(state + 2, 0u, 1u + (unsigned)which * 16u + threadIdx.x);
+                break;
             }
         }
     }
@@ -83,13 +88,13 @@ __global__ void __launch_bounds__(DPX_THREADS)
 dp_adam_exchange_kernel(const DpxPeers peers, const float* __restrict__ mc_grad, float* __restrict__ mc_param,
                         float* __restrict__ m, float* __restrict__ v, long long n4, int rank,
                         int world, unsigned int* state, const float* __restrict__ coef, float b1, float b2, float eps,
-                        float gscale) {
+                        float gscale, unsigned long long timeout_ns) {
     __shared__ int s_last;
     const unsigned int epoch = *reinterpret_cast<volatile unsigned int*>(state);
     unsigned int* const myflags = peers.flags[rank];
     // ---- barrier 1: everybody's gradients are final ---------------------------------------------------------------
     if (blockIdx.x == 0 && (int)threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, epoch);
-    wait_flags(myflags, world, epoch);
+    wait_flags(myflags, world, epoch, timeout_ns, state, 0);
 
     const float lr_c = coef[0], inv_sqrt_bc2 = coef[1];
     const long long per = (n4 + world - 1) / world;
@@ -161,7 +166,7 @@ dp_adam_exchange_kernel(const DpxPeers peers, const float* __restrict__ mc_grad,
     __syncthreads();
     if (s_last) {
         if ((int)threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + world + rank, epoch);
-        wait_flags(myflags + world, world, epoch);
+        wait_flags(myflags + world, world, epoch, timeout_ns, state, 1);
         if (threadIdx.x == 0) {
             state[1] = 0;
             *reinterpret_cast<volatile unsigned int*>(state) = epoch + 1;
@@ -193,12 +198,19 @@ extern "C" int mopoe_dp_adam_exchange(const mopoe_dp_peers_t* peers, const float
     if (blocks < 1) blocks = 1;
     MOPOE_REQUIRE((mc_grad == nullptr) == (mc_param == nullptr), "dp_adam_exchange: give both multicast addresses or neither");
     MOPOE_REQUIRE((((uintptr_t)mc_grad | (uintptr_t)mc_param) & 15) == 0, "dp_adam_exchange: unaligned multicast address");
+    static long long timeout_s = -1;
+    if (timeout_s < 0) {
+        const char* e = getenv("MOPOE_DP_TIMEOUT_S");
+        timeout_s = e ? atoll(e) : 600;
+        if (timeout_s < 0) timeout_s = 0;
+    }
+    const unsigned long long timeout_ns = (unsigned long long)timeout_s * 1000000000ull;
     if (mc_grad)
         dp_adam_exchange_kernel<true><<<(unsigned)blocks, DPX_THREADS, 0, (cudaStream_t)stream>>>(
-            pk, mc_grad, mc_param, m, v, n4, rank, world, state, coef, beta1, beta2, eps, grad_scale);
+            pk, mc_grad, mc_param, m, v, n4, rank, world, state, coef, beta1, beta2, eps, grad_scale, timeout_ns);
     else
         dp_adam_exchange_kernel<false><<<(unsigned)blocks, DPX_THREADS, 0, (cudaStream_t)stream>>>(
-            pk, nullptr, nullptr, m, v, n4, rank, world, state, coef, beta1, beta2, eps, grad_scale);
+            pk, nullptr, nullptr, m, v, n4, rank, world, state, coef, beta1, beta2, eps, grad_scale, timeout_ns);
     MOPOE_CHECK_LAUNCH("dp_adam_exchange");
     return 0;
 }

@@ -107,7 +107,7 @@ class PeerExchange:
             use = False
         self.multicast = use
         self.mc_grad, self.mc_param = (hg.multicast_ptr + og, hp.multicast_ptr + op) if use else (0, 0)
-        self.state = torch.tensor([1, 0], dtype=torch.int32, device=self.device)
+        self.state = torch.tensor([1, 0, 0, 0], dtype=torch.int32, device=self.device)   # epoch, arrivals, error, -
         dist.broadcast(self.params, 0, group=self.group)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)          # every rank's flags are zeroed and mapped before the first kernel
@@ -119,6 +119,17 @@ class PeerExchange:
                L.ptr(m), L.ptr(v), self.params.numel(), self.rank,
                self.world, L.ptr(self.state), L.ptr(coef), float(betas[0]), float(betas[1]), float(eps),
                float(self.grad_scale), L.stream_ptr())
+
+    def check(self):
+        """Raise if a flag barrier of the exchange kernel gave up waiting (one device->host read; call it where the step's
+        statistics are read anyway).  All ranks must reach the exchange within MOPOE_DP_TIMEOUT_S (default 600 s, 0 = no
+        limit) of each other; put a dist.barrier() after rank-asymmetric work (rank-0 evaluation, checkpointing) so the
+        skew is absorbed on the host rather than inside the kernel."""
+        err = int(self.state[2].item())
+        if err:
+            err -= 1
+            raise RuntimeError('peer exchange: rank %d never reached barrier %d within MOPOE_DP_TIMEOUT_S on rank %d'
+                               % (err % 16, err // 16, self.rank))
 
     def slice_bounds(self):
         n4 = self.params.numel() // 4

@@ -83,8 +83,6 @@ class Engine:
         import os
         self.batched = os.environ.get('MOPOE_GEMM_BATCHED', '1') != '0'       # phases of a deconv in one launch
         self.persistent = os.environ.get('MOPOE_GEMM_PERSISTENT', '1') != '0'   # persistent kernel for single GEMMs too
-        self.profile = None     # list of (start_event, end_event, flops, kind) when bench.py instruments a step
-        self.profile_external = False   # True: events become event-record NODES of a CUDA graph being captured
 
     # ---- packed-weight cache ---------------------------------------------------------------------------------
     # Every (weight, form) has a persistent SLOT (destination buffers with fixed addresses).  A slot is valid while its
@@ -203,16 +201,19 @@ class Engine:
         nc = self.nchunk(rows, x.C)
         ws = self.ws64(2 * nc * x.C)
         stats = self.f32(2, x.C)
+        self._bytes('bn_stats', x, 1)
         L.call('mopoe_bn_stats', C.byref(x.view()), L.ptr(mask), mode, L.ptr(ws), nc, eps, momentum,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(rmean), L.ptr(rvar), L.ptr(self.counters), L.stream_ptr())
         return stats
 
     def bn_apply(self, x, mask, mode, stats, gamma, beta, relu, out):
+        self._bytes('bn_apply', x, 2)
         L.call('mopoe_bn_apply', C.byref(x.view()), L.ptr(mask), mode, L.ptr(stats[0]), L.ptr(stats[1]),
                L.ptr(gamma), L.ptr(beta), int(relu), C.byref(out.view()), L.stream_ptr())
         return out
 
     def combine(self, r, stats, gamma, beta, c, mask, mode, a, b, out):
+        self._bytes('combine', r, 3)
         L.call('mopoe_combine', C.byref(r.view()), L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(beta),
                C.byref(c.view()), L.ptr(mask), mode, float(a), float(b), C.byref(out.view()), L.stream_ptr())
         return out
@@ -226,10 +227,12 @@ class Engine:
         sums = self.f32(2, x.C)
         gv = C.byref(gate.view()) if gate is not None else None
         gg = gb = None      # reserved gate-recompute operands of the C ABI (not compiled in)
+        self._bytes('bn_bwd_reduce', x, 3 if gate is not None else 2)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(sums),
                gg, gb, L.ptr(self.counters), L.stream_ptr())
         av = C.byref(addend.view()) if addend is not None else None
+        self._bytes('bn_bwd_apply', x, 3 + (gate is not None) + (addend is not None))
         L.call('mopoe_bn_bwd_apply', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), av, C.byref(out.view()), gb, L.stream_ptr())
         return out
@@ -240,9 +243,11 @@ class Engine:
         nc = self.nchunk(rows, r.C)
         ws = self.ws64(2 * nc * r.C)
         sums = self.f32(2, r.C)
+        self._bytes('bn_bwd_reduce', r, 2)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), None, float(a), C.byref(r.view()), None, L.MASK_NONE,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(sums),
                None, None, L.ptr(self.counters), L.stream_ptr())
+        self._bytes('combine_bwd_apply', r, 4)
         L.call('mopoe_combine_bwd_apply', C.byref(dy.view()), float(a), C.byref(r.view()), L.ptr(stats[0]),
                L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), L.ptr(mask2), mode2, float(b), C.byref(dr.view()),
                C.byref(dc.view()), L.stream_ptr())
@@ -275,16 +280,17 @@ class Engine:
         return m
 
     # ---- implicit-GEMM problem builders -------------------------------------------------------------------
-    def _timed(self, kind, flops, fn, tag=None):
-        if self.profile is None:
-            return fn()
-        ext = {'external': True} if self.profile_external else {}
-        a, b = torch.cuda.Event(enable_timing=True, **ext), torch.cuda.Event(enable_timing=True, **ext)
-        a.record()
-        r = fn()
-        b.record()
-        self.profile.append((a, b, flops, kind, tag))
-        return r
+    @staticmethod
+    def _timed(kind, flops, fn, tag=None):
+        """annotate the C call fn() makes with its algorithmic work (bench.py's per-call timing lives in _lib.call)"""
+        L.annotate(kind=kind, flops=flops, tag=tag)
+        return fn()
+
+    @staticmethod
+    def _bytes(kind, v, passes, extra=0):
+        """annotate the next call as an HBM pass: `passes` reads/writes of the interior of activation `v`"""
+        if L.PROFILE is not None:
+            L.annotate(kind=kind, bytes=passes * v.B * v.H * v.W * v.C * v.t.element_size() + extra)
 
     def _gemm(self, win, wp, bias, rows):
         self._gemm_batched([win], [wp], bias, [rows])

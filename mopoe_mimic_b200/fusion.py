@@ -156,6 +156,8 @@ class FusionFn(torch.autograd.Function):
         nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         eps = eps.contiguous().float()
         mu_p, lv_p = _ptr_array(mus), _ptr_array(lvs)
+        # algorithmic bytes: read 2 M D + eps D, write subsets 2 nsub D + joint 2 D + z D, fp32
+        L.annotate(kind='fusion_fwd', bytes=4 * B * D * (2 * len(mus) + 1 + 2 * ns + 3))
         L.call('mopoe_fusion_fwd', C.byref(plan.cfg), mu_p, lv_p, L.ptr(eps), L.ptr(sub_mu), L.ptr(sub_lv), L.ptr(jmu),
                L.ptr(jlv), L.ptr(z), L.ptr(kl), L.ptr(nan_flag), L.ptr(eng.ws64(ns * B)), L.stream_ptr())
         ctx.plan, ctx.eng = plan, eng
@@ -176,6 +178,8 @@ class FusionFn(torch.autograd.Function):
         d_smu, d_slv, d_jmu, d_jlv, d_z, d_kl = map(c, (d_smu, d_slv, d_jmu, d_jlv, d_z, d_kl))
         dmu = [torch.empty_like(t) for t in mus]
         dlv = [torch.empty_like(t) for t in lvs]
+        # read d_z + the experts' 2 M D, write their gradients 2 M D (the saved subset tensors come out of L2 at these sizes)
+        L.annotate(kind='fusion_bwd', bytes=4 * plan.B * plan.D * (1 + 4 * M))
         L.call('mopoe_fusion_bwd', C.byref(plan.cfg), _ptr_array(mus), _ptr_array(lvs), L.ptr(eps), L.ptr(sub_mu),
                L.ptr(sub_lv), L.ptr(d_z), L.ptr(d_jmu), L.ptr(d_jlv), L.ptr(d_smu), L.ptr(d_slv), L.ptr(d_kl),
                _ptr_array(dmu), _ptr_array(dlv), L.stream_ptr())

@@ -207,7 +207,9 @@ class BaseMMVae(nn.Module):
         if num_samples is None:
             num_samples = self.flags.batch_size
         dev = next(self.parameters()).device
-        z_class = torch.randn(num_samples, self.flags.class_dim, device=dev)
+        # drawn from the CPU generator and moved, as the reference does (VAEtrimodalMimic.py:127-135): the same
+        # torch.manual_seed gives the same samples on both implementations
+        z_class = torch.randn(num_samples, self.flags.class_dim).to(dev)
         random_latents = {'content': z_class, 'style': self.get_random_styles(num_samples)}
         return self.generate_from_latents(random_latents)
 
@@ -256,26 +258,36 @@ class MMVaeMimic(BaseMMVae):
     # kernels of one branch fill the gaps of the others.  Autograd replays every backward node on its forward stream, so
     # the backward pass overlaps the same way; under CUDA-graph capture the branches become parallel graph branches.
     def _branches(self, names, fn):
-        """run fn(name) for every name, name i > 0 on side stream i; returns {name: result}; joined on return"""
+        """run fn(name) for every modality name on ITS stream; returns {name: result}; joined on return.
+
+        The stream is a fixed property of the modality (position in self.modalities: 0 -> the ambient stream, i -> side
+        stream i-1), not of the call: poe's unimodal passes (losses.calc_poe_loss) therefore run on the stream that also ran
+        the modality's branch of the joint pass, and — autograd replays backward nodes on their forward streams — the two
+        passes' read-modify-write accumulations into the SAME flat gradient slots are ordered by the stream instead of
+        racing as parallel branches of the captured graph."""
         import os
         cur = torch.cuda.current_stream()
-        if len(names) <= 1 or os.environ.get('MOPOE_BRANCH_STREAMS', '1') == '0':
+        if self.num_modalities <= 1 or os.environ.get('MOPOE_BRANCH_STREAMS', '1') == '0':
             return {n: fn(n) for n in names}
+        order = list(self.modalities.keys())
         side = self.__dict__.setdefault('_side_streams', [])
-        while len(side) < len(names) - 1:
+        while len(side) < len(order) - 1:
             side.append(torch.cuda.Stream())
         out = {}
-        self.__dict__['_side_used'] = max(self.__dict__.get('_side_used', 0), len(names) - 1)
-        for i, n in enumerate(names):
+        used = [order.index(n) for n in names]
+        self.__dict__.setdefault('_side_used', set()).update(i for i in used if i > 0)
+        for n, i in zip(names, used):
             if i == 0:
                 continue
             st = side[i - 1]
             st.wait_stream(cur)                       # fork: everything enqueued so far (inputs, packed weights) is visible
             with torch.cuda.stream(st):
                 out[n] = fn(n)
-        out[names[0]] = fn(names[0])                  # the first branch stays on the ambient stream
-        for i in range(1, len(names)):
-            cur.wait_stream(side[i - 1])              # join
+        if order[0] in names:
+            out[order[0]] = fn(order[0])              # the first modality stays on the ambient stream
+        for i in used:
+            if i > 0:
+                cur.wait_stream(side[i - 1])          # join
         return out
 
     def join_branches(self):
@@ -283,10 +295,10 @@ class MMVaeMimic(BaseMMVae):
         parameter gradients on the branch streams without an AccumulateGrad node the engine would sync on)"""
         cur = torch.cuda.current_stream()
         # only streams forked since the last join: waiting on an idle stream from a CAPTURING stream invalidates the capture
-        used = self.__dict__.get('_side_used', 0)
-        for st in self.__dict__.get('_side_streams', [])[:used]:
-            cur.wait_stream(st)
-        self.__dict__['_side_used'] = 0
+        side = self.__dict__.get('_side_streams', [])
+        for i in sorted(self.__dict__.get('_side_used', ())):
+            cur.wait_stream(side[i - 1])
+        self.__dict__['_side_used'] = set()
 
     @staticmethod
     def _touch(stream, *tensors):
@@ -396,11 +408,14 @@ class MMVaeMimic(BaseMMVae):
             return {m: None for m in self.modalities}
         dims = {'PA': self.flags.style_pa_dim, 'Lateral': self.flags.style_lat_dim, 'text': self.flags.style_text_dim}
         dev = next(self.parameters()).device
-        return {m: torch.randn(num_samples, dims[m], device=dev) for m in self.modalities}
+        return {m: torch.randn(num_samples, dims[m]).to(dev) for m in self.modalities}       # CPU generator, as the reference
 
     def get_random_style_dists(self, num_samples):
+        """VAEtrimodalMimic.get_random_style_dists:109-125: N(0, I) style posteriors [zeros(n, style_dim)] * 2 — the
+        flags' style dims are used whether or not the representation is factorized, as in the reference"""
+        dims = {'PA': self.flags.style_pa_dim, 'Lateral': self.flags.style_lat_dim, 'text': self.flags.style_text_dim}
         dev = next(self.parameters()).device
-        return {m: [torch.zeros(num_samples, 0, device=dev), torch.zeros(num_samples, 0, device=dev)]
+        return {m: [torch.zeros(num_samples, dims[m], device=dev), torch.zeros(num_samples, dims[m], device=dev)]
                 for m in self.modalities}
 
     def generate_sufficient_statistics_from_latents(self, latents):

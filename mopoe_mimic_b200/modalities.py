@@ -9,7 +9,14 @@ import math
 
 import torch
 
-from .blocks import CategoricalLogProbSumFn, LaplaceLogProbSumFn, log_softmax_rows
+from .blocks import CategoricalLogProbSumFn, LaplaceLogProbSumFn, laplace_log_prob, log_softmax_rows
+
+
+def _need_engine(eng, what):
+    if eng is None:
+        raise RuntimeError('%s needs the CUDA engine (likelihood objects are built by the model\'s decoders); there is no '
+                           'torch / CPU fallback' % what)
+    return eng
 
 
 class LaplaceLikelihood:
@@ -23,24 +30,25 @@ class LaplaceLikelihood:
         elif not torch.is_tensor(scale):
             self._scale_f = float(scale)
         else:
-            self._scale_f = float(scale) if scale.numel() == 1 and not scale.is_cuda else None
+            self._scale_f = float(scale)          # one device->host read (foreign callers only; the model passes scale_value)
 
     @property
     def mean(self):
         return self.loc
 
     def log_prob(self, value):
-        # elementwise (evaluation callers only): -log(2b) - |x - loc| / b
-        return -torch.log(2 * self.scale) - torch.abs(value - self.loc) / self.scale
+        """elementwise -log(2b) - |x - loc| / b, shape of loc (the evaluation callers reduce it per sample:
+        utils/likelihood.py:120-121); `value` broadcasts over leading dims of loc as in torch.distributions"""
+        return laplace_log_prob(self.loc, value, self._scale_f, _need_engine(self._eng, 'LaplaceLikelihood.log_prob'))
 
     def log_prob_sum(self, value):
-        if self._eng is None or self._scale_f is None:
-            return self.log_prob(value).sum()
-        return LaplaceLogProbSumFn.apply(self.loc, value, self._scale_f, self._eng)
+        return LaplaceLogProbSumFn.apply(self.loc, value, self._scale_f, _need_engine(self._eng, 'LaplaceLikelihood.log_prob_sum'))
 
 
 class CategoricalLikelihood:
-    """dist.OneHotCategorical(logits=...) stand-in built from the decoder's PRE-softmax scores [B, L, V]."""
+    """dist.OneHotCategorical(logits=...) stand-in built from the decoder's PRE-softmax scores [B, L, V].
+
+    Targets must be strictly one-hot rows (or token indices): see blocks.CategoricalLogProbSumFn."""
 
     def __init__(self, logits=None, scores=None, eng=None):
         self._scores = scores if scores is not None else logits
@@ -50,10 +58,7 @@ class CategoricalLikelihood:
     @property
     def logits(self):
         if self._logits is None:
-            if self._eng is not None:
-                self._logits = log_softmax_rows(self._scores, self._eng)
-            else:
-                self._logits = self._scores - self._scores.logsumexp(-1, keepdim=True)
+            self._logits = log_softmax_rows(self._scores, _need_engine(self._eng, 'CategoricalLikelihood.logits'))
         return self._logits
 
     @property
@@ -70,9 +75,7 @@ class CategoricalLikelihood:
         return self.logits.gather(-1, idx.unsqueeze(-1)).squeeze(-1)
 
     def log_prob_sum(self, value):
-        if self._eng is None:
-            return self.log_prob(value).sum()
-        return CategoricalLogProbSumFn.apply(self._scores, value, self._eng)
+        return CategoricalLogProbSumFn.apply(self._scores, value, _need_engine(self._eng, 'CategoricalLikelihood.log_prob_sum'))
 
 
 def get_likelihood(name):

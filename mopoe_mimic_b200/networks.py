@@ -414,6 +414,15 @@ class DecoderText(_Net):
         # factorized representation: z = cat(style, content) (ConvNetworksImgMimic.py:47-48, ConvNetworksTextMimic.py:52-55)
         z = z_content if z_style is None else torch.cat((z_style, z_content), dim=1)
         L.require_cuda(z)
+        # "predict in batches to spare GPU memory" (ConvNetworksTextMimic.py:59-64): more rows than flags.batch_size (the
+        # importance-sampled likelihood decodes B*K rows) are decoded in batch_size chunks and concatenated; in train
+        # mode the BatchNorm statistics are then per chunk, exactly as in the reference
+        nb = int(self.flags.batch_size)
+        if z.shape[0] > nb:
+            return [torch.cat([self._decode_rows(z[i:i + nb]) for i in range(0, z.shape[0], nb)])]
+        return [self._decode_rows(z)]
+
+    def _decode_rows(self, z):
         rt, gen = self.rt, self.text_generator
         eng = rt.eng(z.device)
         train = self.training
@@ -442,4 +451,4 @@ class DecoderText(_Net):
             scores = TextLastFn.apply(h, gen.conv2.weight, gen.conv2.bias, eng, B, W, 1)
         if train:
             self._bump()
-        return [scores]
+        return scores

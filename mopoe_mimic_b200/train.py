@@ -125,12 +125,18 @@ class FlatAdam:
 
     def step(self):
         eng = self.model.rt.eng(self.p.device)
+        # the backward kernels of the modality branches accumulate straight into the flat gradient views on their own
+        # streams and return None to autograd (no AccumulateGrad node orders them): the reference loop
+        # `loss.backward(); optimizer.step()` must therefore join the branches before anything reads flat_grads
+        if hasattr(self.model, 'join_branches'):
+            self.model.join_branches()
         L.call('mopoe_step_advance', L.ptr(eng.rng_step), L.ptr(self.step_t), L.ptr(self.coef), float(self.lr),
                float(self.betas[0]), float(self.betas[1]), L.stream_ptr())
         if self.exchange is not None:
             # reduce-scatter + Adam + all-gather in one kernel over peer memory; moments of a slice live on its owner
             self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps)
         else:
+            L.annotate(kind='adam', bytes=28 * self.p.numel())       # p, g, m, v read; p, m, v written (fp32)
             L.call('mopoe_adam_flat_dev', L.ptr(self.p), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.p.numel(),
                    L.ptr(self.coef), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.grad_scale),
                    L.stream_ptr())
@@ -141,6 +147,9 @@ def basic_routine_epoch(exp, batch):
     """run_epochs.basic_routine_epoch:52-96.  One device->host read (the NaN flag) instead of nine."""
     flags = exp.flags
     mm_vae = exp.mm_vae
+    eng = mm_vae.rt.engine
+    if eng is not None:
+        eng.begin_step()             # same Philox offsets every step; weights changed by the flat Adam are re-packed in one launch
     batch_d = batch[0]
     for m_key in batch_d.keys():
         batch_d[m_key] = batch_d[m_key].to(flags.device, non_blocking=True)
@@ -165,9 +174,6 @@ def basic_routine_epoch(exp, batch):
 
 def forward_backward(exp, batch):
     """forward + ELBO + zero_grad + backward (everything of the step before the gradient exchange)"""
-    eng = exp.mm_vae.rt.engine
-    if eng is not None:
-        eng.begin_step()
     out = basic_routine_epoch(exp, batch)
     exp.optimizer.zero_grad()
     out['total_loss'].backward()
@@ -176,8 +182,21 @@ def forward_backward(exp, batch):
     return out
 
 
+def attach_allreduce(exp, allreduce):
+    """What wrapping the model in DistributedDataParallel does in the reference (utils/utils.py:179-185): rank 0's
+    parameters go to every rank once, and the optimizer divides the summed gradients by the world size (DDP's mean).
+    Idempotent; called by train_step / GraphedTrainStep whenever an all-reduce is passed."""
+    if allreduce is None or getattr(allreduce, '_attached_to', None) is exp.optimizer:
+        return
+    from .dp import broadcast_flat
+    exp.optimizer.grad_scale = float(allreduce.grad_scale)
+    broadcast_flat(exp.mm_vae.flat_params, 0, getattr(allreduce, 'group', None))
+    allreduce._attached_to = exp.optimizer
+
+
 def train_step(exp, batch, allreduce=None):
     """run_epochs.train:118-131 for one batch: forward + loss, zero_grad, backward, (DP all-reduce), Adam."""
+    attach_allreduce(exp, allreduce)
     out = forward_backward(exp, batch)
     if allreduce is not None:
         allreduce(exp.mm_vae.flat_grads)
@@ -200,6 +219,7 @@ class GraphedTrainStep:
         dev = flags.device
         self.exp = exp
         self.allreduce = allreduce
+        attach_allreduce(exp, allreduce)
         self._copy_stream = None
         self.static = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in example_batch.items()}
         for k, v in example_batch.items():

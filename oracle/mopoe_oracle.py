@@ -737,3 +737,73 @@ def adam_step(params, grads, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
         v[k].mul_(b2).addcmul_(g, g, value=1 - b2)
         denom = (v[k].sqrt() / math.sqrt(bc2)).add_(eps)
         params[k].addcdiv_(m[k], denom, value=-lr / bc1)
+
+
+# --------------------------------------------------------------------------------------
+# evaluation path: decode from latents, per-sample log-probs, importance-sampled likelihoods
+# --------------------------------------------------------------------------------------
+def decode(state, flags, z, z_style=None, train=False):
+    """VAEtrimodalMimic.generate_sufficient_statistics_from_latents (networks/VAEtrimodalMimic.py:143-152): every decoder on
+    the same content rows (cat(style, content) when factorized).  Returns modality -> Laplace loc / log-softmaxed logits.
+    (The reference decodes text in flags.batch_size chunks, ConvNetworksTextMimic.py:59-64 — a no-op for the values in
+    eval mode, where BatchNorm reads its running statistics.)"""
+    ctx = _Ctx(state, {}, train)
+    out = OrderedDict()
+    for m in flags.mods:
+        zm = z if not (z_style and z_style.get(m) is not None) else torch.cat((z_style[m], z), dim=1)
+        out[m] = decoder_text(ctx, flags, DEC_NAME[m], zm) if m == 'text' else decoder_img(ctx, flags, DEC_NAME[m], zm)
+    return out
+
+
+def likelihood_mean(m, dec_out):
+    """`.mean` of the likelihood object (BaseMMVae.generate_from_latents:210-216): Laplace loc, categorical probabilities"""
+    return dec_out.exp() if m == 'text' else dec_out
+
+
+def log_prob_rows(m, dec_out, x):
+    """likelihood.log_prob(x).view(rows, -1).sum(dim=1)  (utils/likelihood.py:120-121, :187)"""
+    rows = x.shape[0]
+    if m == 'text':
+        ln = dec_out - dec_out.logsumexp(dim=-1, keepdim=True)
+        lp = ln.gather(-1, x.max(-1)[1].unsqueeze(-1)).squeeze(-1)
+    else:
+        b = LAPLACE_SCALE
+        log2b = float(torch.log(torch.tensor(2 * b, dtype=torch.float32)))
+        lp = -log2b - (x - dec_out).abs() / b
+    return lp.reshape(rows, -1).sum(dim=1)
+
+
+def _gaussian_log_pdf(x, mu, logvar):
+    """utils/likelihood.py:54-66"""
+    log2pi = float(math.log(2.0 * math.pi))
+    return torch.sum(-0.5 * log2pi - logvar / 2. - torch.pow(x - mu, 2) / (2. * torch.exp(logvar)), dim=1)
+
+
+def _log_mean_exp(x, dim=1):
+    """utils/likelihood.py:39-51"""
+    m = torch.max(x, dim=dim, keepdim=True)[0]
+    return m + torch.log(torch.mean(torch.exp(x - m), dim=dim, keepdim=True))
+
+
+def importance_likelihoods(flags, K, dec, batch, z, mu, lv):
+    """calc_log_likelihood_batch without style latents (evaluation/eval_metrics/likelihood.py:17-93): per-modality
+    log_marginal_estimate (utils/likelihood.py:82-141) and log_joint_estimate (:144-220) with a static N(0, I) prior.
+    dec: decode() output on the K*B rows z (sample-major: row k*B + b); mu, lv: the conditioning subset's posterior [B, D]."""
+    B = flags.batch_size
+    mu_r = mu.unsqueeze(0).repeat(K, 1, 1).view(K * B, -1)
+    lv_r = lv.unsqueeze(0).repeat(K, 1, 1).view(K * B, -1)
+    log_q = _gaussian_log_pdf(z, mu_r, lv_r)
+    log_p = _gaussian_log_pdf(z, torch.zeros_like(z), torch.zeros_like(z))      # unit_gaussian_log_pdf (:69-79)
+    out, rows = OrderedDict(), []
+    for m in flags.mods:
+        x = batch[m]
+        xr = x.unsqueeze(0).repeat(K, *([1] * x.dim())).view(K * B, *x.shape[1:])
+        lp = log_prob_rows(m, dec[m], xr)
+        rows.append(lp)
+        lw = (lp + log_p - log_q).view(B, K)          # the reference views the sample-major rows as (batch, samples)
+        out[m] = torch.mean(_log_mean_exp(lw, dim=1))
+    # log_joint_estimate collects the per-modality rows in `torch.zeros(num_mods, B*K)` — an FP32 tensor whatever the model
+    # dtype (utils/likelihood.py:183-188) — and sums over modalities there: an fp32 quantity even in an fp64 run
+    lw = (torch.stack(rows).to(torch.float32).sum(0) + log_p - log_q).view(B, K)
+    out['joint'] = torch.mean(_log_mean_exp(lw, dim=1))
+    return out

@@ -164,3 +164,63 @@ def compare_step(orc, out, grads, state_after=None):
             worst = (e, k)
     errs['_worst_grad'] = worst
     return errs
+
+
+# ---- per-tensor gradient comparison (bf16 parity) --------------------------------------------------------------------------
+ZERO_GRAD_SUFFIXES = ('downsample.0.bias', 'upsample.0.bias')      # conv bias feeding a train-mode BatchNorm: analytically 0
+
+
+def grad_table(g_test, g_ref):
+    """per parameter tensor: relative L2 error, max-abs error / max-abs value, cosine, and the tensor's share of the whole
+    gradient's L2 norm (tensors that carry ~nothing of the gradient are rounding noise in ANY implementation)"""
+    tot = sum(float(r.double().norm()) ** 2 for r in g_ref.values()) ** 0.5
+    rows = []
+    for k, r in g_ref.items():
+        t, r = g_test[k].double().reshape(-1), r.double().reshape(-1)
+        nr, nt = float(r.norm()), float(t.norm())
+        rows.append(dict(name=k, numel=r.numel(), share=nr / max(tot, 1e-300),
+                         rel_l2=float((t - r).norm()) / max(nr, 1e-300),
+                         max_rel=float((t - r).abs().max()) / max(float(r.abs().max()), 1e-300),
+                         cos=float(t @ r) / max(nt * nr, 1e-300)))
+    return rows
+
+
+def device_noise(ofl, B, seed, device='cuda'):
+    """dropout keep-masks in the PRODUCT's layouts (uint8 [B,C] for Dropout2d, [B,L,C] for Dropout) and eps, generated on
+    the device — for comparisons between two product runs at sizes where the CPU mask generator is too slow"""
+    g = torch.Generator(device=device).manual_seed(seed)
+    masks = {}
+    for name, shape in O.dropout_sites(ofl, B).items():
+        if len(shape) == 4:
+            masks[name] = (torch.rand(shape[0], shape[1], device=device, generator=g) < 0.5).to(torch.uint8)
+        else:
+            masks[name] = (torch.rand(shape[0], shape[2], shape[1], device=device, generator=g) < 0.5).to(torch.uint8)
+    eps = torch.randn(B, ofl.class_dim, device=device, generator=g)
+    return masks, eps
+
+
+def run_product_device_noise(ofl, state, batch_dev, noise_dev, compute_dtype, loss='elbo'):
+    """one product step (forward + loss + backward) with device-resident inputs / injected noise -> (out, grads on device)"""
+    import mopoe_mimic_b200 as P
+    fl = product_flags(ofl, compute_dtype)
+    exp = P.Experiment(fl)
+    vae = exp.mm_vae
+    vae.load_state_dict({k: v.float() for k, v in state.items()})
+    exp.set_optimizer()
+    vae.train()
+    vae.rt.schedule = [(dict(noise_dev[0]), noise_dev[1], None)]
+    b = OrderedDict((k, v.clone()) for k, v in batch_dev.items())
+    if loss == 'elbo':
+        out = P.basic_routine_epoch(exp, (b, None))
+        lossv = out['total_loss']
+    else:
+        res = vae(b)
+        recs = [torch.log_softmax(r._scores, -1) if m == 'text' else r.loc for m, r in res['rec'].items()]
+        lossv = sum((r ** 2).mean() for r in recs) * 100.0 + 5.0 * res['joint_divergence']
+        out = {'total_loss': lossv, 'results': res}
+    exp.optimizer.zero_grad()
+    lossv.backward()
+    vae.join_branches()
+    torch.cuda.synchronize()
+    grads = OrderedDict((k, p.grad.detach().clone()) for k, p in vae.named_parameters())
+    return out, grads

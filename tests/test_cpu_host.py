@@ -143,6 +143,18 @@ assert torch.allclose(flat[3:], torch.full((n - 3,), (1.0 + world) / 2))
 p = torch.full((10,), float(rank))
 broadcast_flat(p, 0)
 assert float(p.sum()) == 0.0
+# what train_step / GraphedTrainStep do when handed an all-reduce (the reference wraps the model in DDP): the optimizer
+# takes the 1/world gradient scale and every rank starts from rank 0's parameters
+from types import SimpleNamespace
+from mopoe_mimic_b200.train import attach_allreduce
+opt = SimpleNamespace(grad_scale=1.0)
+exp = SimpleNamespace(optimizer=opt, mm_vae=SimpleNamespace(flat_params=torch.full((6,), float(rank + 1))))
+ar2 = FlatGradAllReduce()
+attach_allreduce(exp, ar2)
+assert opt.grad_scale == 1.0 / world and float(exp.mm_vae.flat_params.sum()) == 6.0
+exp.mm_vae.flat_params.add_(rank)            # idempotent: a second attach must not broadcast again
+attach_allreduce(exp, ar2)
+assert float(exp.mm_vae.flat_params[0]) == 1.0 + rank
 dist.destroy_process_group()
 print('rank', rank, 'ok')
 '''
@@ -170,15 +182,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
-                        '--cpu-batch', '2'], capture_output=True, text=True, timeout=600, cwd=root)
-    assert r.returncode == 0, r.stderr[-2000:]
-    line = json.loads(r.stdout.strip().splitlines()[-1])
+    have_ref = os.path.isdir(os.path.join(root, 'baseline', '_ref', 'mimic', 'networks'))
+    for kind in (['reference'] if have_ref else []) + ['port']:
+        r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1',
+                            '--cpu-batch', '2', '--cpu-kind', kind], capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode == 0, r.stderr[-2000:]
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        assert line['cpu_baseline']['kind'] == kind
     for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
               'vs_baseline', 'dtype', 'data', 'config', 'impl', 'cpu_baseline', 'e2e'):
         assert k in line, k
     assert line['impl'] == 'reference' and line['unit'] == 'samples/s' and line['value'] > 0
-    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['cpu_baseline']['cores'] >= 1
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
     assert 'workload' in line['config']
 

@@ -144,7 +144,8 @@ def test_laplace_logprob_sum_and_grad(n):
     torch.testing.assert_close(l.grad.cpu(), (ref_loc.grad * 0.33).float(), rtol=1e-6, atol=0)
 
 
-@pytest.mark.parametrize('rows,V', [(1, 71), (1024, 71), (16 * 1024, 71), (333, 5), (64, 256), (77, 257), (512, 2900)])
+@pytest.mark.parametrize('rows,V', [(1, 71), (1024, 71), (16 * 1024, 71), (333, 5), (64, 256), (77, 257), (512, 2900),
+                                     (130, 71), (256 * 1024, 71), (4099, 12)])
 def test_categorical_logprob_sum_and_grad(rows, V):
     from mopoe_mimic_b200.blocks import CategoricalLogProbSumFn, log_softmax_rows
     g = torch.Generator().manual_seed(rows + V)

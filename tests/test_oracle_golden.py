@@ -102,3 +102,40 @@ def test_oracle_fp32_close_to_fp64_reference(golden_dir):
     assert abs(float(out['total_loss']) - fx['total_loss']) <= 1e-5 * abs(fx['total_loss'])
     for k, v in fx['klds'].items():
         assert abs(float(out['klds'][k]) - v) <= 1e-4 * abs(v)
+
+
+def test_eval_path_oracle_matches_reference_fixture(golden_dir):
+    """N2: eval-mode inference (full / partial batches), decode on B*K rows, per-sample log-probs, importance-sampled
+    likelihoods and cond_generation of the oracle against the reference outputs in eval_tri.pt (fp64)."""
+    from oracle import gen_golden_eval as GE
+    fx = torch.load(os.path.join(golden_dir, 'eval_tri.pt'), weights_only=False)
+    fl = O.default_flags(**fx['flags'])
+    dt = torch.float64
+    st = GE.eval_state(fl, dt)
+    batch = O.make_batch(fl, seed=1, dtype=dt)
+    noise = GE.eval_noise(fl, dt)
+    K, B = fx['k_imp'], fl.batch_size
+    with torch.no_grad():
+        res = O.forward(st, batch, fl, None, None, train=False)
+        for k, (mu, lv) in fx['subsets'].items():
+            assert float((res['latents']['subsets'][k][0] - mu).abs().max()) < 1e-10
+            assert float((res['latents']['subsets'][k][1] - lv).abs().max()) < 1e-10
+        for tag, p in fx['partial'].items():
+            o = O.forward(st, {m: batch[m][:p['rows']] for m in p['mods']}, fl, None, None, train=False, present=list(p['mods']))
+            assert list(o['latents']['subsets'].keys()) == list(p['subsets'].keys())
+            for k, (mu, lv) in p['subsets'].items():
+                assert float((o['latents']['subsets'][k][0] - mu).abs().max()) < 1e-10, (tag, k)
+            assert float((o['latents']['joint'][1] - p['joint'][1]).abs().max()) < 1e-10
+        for s_key, d in fx['lhood'].items():
+            mu, lv = fx['subsets'][s_key]
+            z = (noise['eps_imp'] * torch.exp(0.5 * lv.unsqueeze(0)) + mu.unsqueeze(0)).view(K * B, -1)
+            dec = O.decode(st, fl, z)
+            ll = O.importance_likelihoods(fl, K, dec, batch, z, mu, lv)
+            for k, v in d['ll'].items():
+                assert abs(float(ll[k]) - v) <= 1e-10 * abs(v), (s_key, k)
+            for m in fl.mods:
+                cs = d['mean'][m]
+                assert abs(float(O.likelihood_mean(m, dec[m]).double().norm()) - cs['l2']) <= 1e-10 * cs['l2']
+        mu, lv = fx['subsets']['Lateral_PA_text']
+        z = noise['eps_cg'] * torch.exp(0.5 * lv) + mu
+        assert float((O.decode(st, fl, z)['PA'] - fx['cond_gen_pa_full']).abs().max()) < 1e-10
