@@ -1,0 +1,107 @@
+"""bf16 — the benchmarked dtype — against the fp32 oracle, PER TENSOR (north_star: "rtol 1e-2 for bf16 paths").
+
+What holds at 1e-2 and is asserted at 1e-2: the loss, every KLD and every log-prob.  Latents and reconstructions are
+asserted at 3e-2 (bf16 has 8 mantissa bits; a dozen stored activations deep the max-abs error of a latent is 1.0-1.6e-2).
+
+What provably cannot hold at 1e-2 and is asserted at a MEASURED bound: per-tensor parameter gradients.  The residual
+blocks gate with ReLU after BatchNorm; a 1e-2 forward perturbation moves ~0.4 % of the pre-activations across zero, and
+every flipped gate adds or removes that element's full contribution: relative L2 error of a gradient tensor ~ sqrt(p_flip)
+= 3-10 %, largest on the main branch (conv1 / bn1, two gates deep) and smallest on the linear shortcut path.  This is a
+property of bf16 storage, not of these kernels: the CPU oracle run under torch.autocast(bfloat16) — the library's own bf16
+kernels on the reference's op sequence — shows the same profile (tools/bf16_autocast_floor.py: median 6.2 %, carrying
+tensors <= 14.5 %, min cosine 0.989 at the smoke size; ours: 5.9 %, 13.8 %, 0.990).  Bounds below = measured on B200
+(tools/bf16_parity.py, profiles/r2_bf16_parity.txt) with ~1.5x head-room; conv biases that feed a train-mode BatchNorm
+have an analytically zero gradient (pure rounding noise in any implementation) and are skipped.
+"""
+import os
+from collections import OrderedDict
+
+import pytest
+import torch
+
+from oracle import mopoe_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+MID = dict(batch_size=16, DIM_img=64, DIM_text=64, class_dim=64)
+CASES = {
+    'mid_moe': dict(MID, method='moe'),
+    'mid_poe': dict(MID, method='poe', batch_size=12),
+    'mid_patext': dict(MID, mods=('PA', 'text')),
+    'mid_256px': dict(batch_size=8, DIM_img=32, DIM_text=32, class_dim=64, img_size=256),
+    'cfg1': dict(batch_size=16),                      # BASELINE.json configs[0]: full-size model, B = 16
+}
+# tensor kinds by their position in the block (last two name components)
+MAIN_BRANCH = ('conv1.weight', 'conv1.bias', 'bn1.weight', 'bn1.bias', 'bn2.bias')
+
+
+def check_gradients(rows, carry_rel, carry_cos, median_all, what):
+    rows = [r for r in rows if not r['name'].endswith(H.ZERO_GRAD_SUFFIXES)]
+    carrying = [r for r in rows if r['share'] > 1e-3]           # tensors holding > 0.1 % of the gradient's L2 norm
+    assert len(carrying) >= 80, (what, len(carrying))
+    worst = max(carrying, key=lambda r: r['rel_l2'])
+    assert worst['rel_l2'] < carry_rel, (what, worst)
+    wc = min(carrying, key=lambda r: r['cos'])
+    assert wc['cos'] > carry_cos, (what, wc)
+    rl = sorted(r['rel_l2'] for r in rows if r['share'] > 1e-4)
+    assert rl[len(rl) // 2] < median_all, (what, rl[len(rl) // 2])
+    # the linear shortcut path and conv2 see no extra gate: tighter than the main branch
+    lin = sorted(r['rel_l2'] for r in carrying if not r['name'].endswith(MAIN_BRANCH))
+    assert lin[len(lin) // 2] < 0.07, (what, 'shortcut/conv2 median', lin[len(lin) // 2])
+    # whole-gradient direction
+    return worst, rl[len(rl) // 2]
+
+
+def global_cosine(g_test, g_ref):
+    dot = nt = nr = 0.0
+    for k, r in g_ref.items():
+        a, b = g_test[k].double().reshape(-1), r.double().reshape(-1)
+        dot += float(a @ b)
+        nt += float(a @ a)
+        nr += float(b @ b)
+    return dot / (nt ** 0.5 * nr ** 0.5)
+
+
+@pytest.mark.parametrize('name', sorted(CASES))
+def test_bf16_step_per_tensor_vs_fp32_oracle(name):
+    ofl, state, batch, noise = H.make_case(CASES[name])
+    orc = H.run_oracle(ofl, state, batch, noise)
+    exp, out, grads = H.run_product(ofl, state, batch, noise, 'bf16')
+    errs = H.compare_step(orc, out, grads)
+    # north_star tolerance where it holds: loss terms at 1e-2
+    assert errs['total_loss'] < 1e-2 and errs['joint_div'] < 1e-2
+    for k, v in errs.items():
+        if k.startswith(('kld.', 'logp.')):
+            assert v < 1e-2, (k, v)
+        if k.startswith(('enc_', 'sub_', 'joint_mu', 'mus', 'z', 'rec.')):
+            assert v < 3e-2, (k, v)
+    assert list(out['results']['latents']['subsets'].keys()) == list(orc['results']['latents']['subsets'].keys())
+    check_gradients(H.grad_table(grads, orc['grads']), carry_rel=0.22, carry_cos=0.975, median_all=0.11, what=name)
+    assert global_cosine(grads, orc['grads']) > 0.995
+
+
+def test_bf16_vs_fp32_product_at_config2():
+    """BASELINE.json configs[1] — the benchmarked size (B = 256, DIM 128, class_dim 128): the bf16 product against the fp32
+    validation-mode product (itself pinned to the oracle at rtol 1e-5) on the same weights, inputs, dropout masks and eps."""
+    B = 256
+    ofl = H.oracle_flags(batch_size=B)
+    state = O.make_state(ofl, 0, torch.float32)
+    batch = OrderedDict((k, v.cuda()) for k, v in O.make_batch(ofl, 1, torch.float32).items())
+    noise = H.device_noise(ofl, B, 2)
+    o32, g32 = H.run_product_device_noise(ofl, state, batch, noise, 'fp32')
+    o16, g16 = H.run_product_device_noise(ofl, state, batch, noise, 'bf16')
+    l32, l16 = float(o32['total_loss']), float(o16['total_loss'])
+    assert abs(l32 - l16) < 1e-2 * abs(l32)
+    for k in o32['klds']:
+        assert abs(float(o32['klds'][k]) - float(o16['klds'][k])) < 1e-2 * abs(float(o32['klds'][k])), k
+    for k in o32['log_probs']:
+        assert abs(float(o32['log_probs'][k]) - float(o16['log_probs'][k])) < 1e-2 * abs(float(o32['log_probs'][k])), k
+    lat32, lat16 = o32['results']['latents'], o16['results']['latents']
+    for k in lat32['subsets']:
+        assert H.rel_err(lat16['subsets'][k][0], lat32['subsets'][k][0]) < 3e-2, k
+        assert H.rel_err(lat16['subsets'][k][1], lat32['subsets'][k][1]) < 3e-2, k
+    g32c = OrderedDict((k, v.cpu()) for k, v in g32.items())
+    g16c = OrderedDict((k, v.cpu()) for k, v in g16.items())
+    check_gradients(H.grad_table(g16c, g32c), carry_rel=0.16, carry_cos=0.985, median_all=0.08, what='cfg2')
+    assert global_cosine(g16c, g32c) > 0.997
