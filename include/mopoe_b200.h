@@ -84,6 +84,30 @@ int mopoe_conv_gemm(const mopoe_window_t* A, const void* Wp, const float* bias, 
 int mopoe_conv_gemm_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
                             const mopoe_rows_t* D, int impl, void* stream);
 
+/* The same launch with the training-mode BatchNorm STATISTICS of its output fused into the epilogue: the GEMM that
+ * produces a tensor also produces the per-channel mean / 1/sqrt(var + eps) the following nn.BatchNorm needs
+ * (ResidualBlocks.py:84-97: conv1 -> dropout1 -> bn2, and shortcut conv -> BatchNorm), and updates the running statistics
+ * (momentum, unbiased variance) — instead of a separate reduction pass over the activation.  `out` describes the whole
+ * tensor the launch writes (all problems together cover every pixel once); mask / mask_mode: the dropout keep-mask that
+ * sits between the GEMM and the BatchNorm (statistics of x * 2 * mask).  The statistics are those of the STORED (bf16-
+ * rounded) values.  ws: >= max(2 * nchunk, 8 * #SMs) * out.C doubles.  When the fused epilogue does not apply (fp32 /
+ * SIMT path, unaligned rows, masked multi-problem launches) the library runs mopoe_bn_stats itself: same results. */
+typedef struct {
+    mopoe_view_t out;
+    const uint8_t* mask;
+    int32_t mask_mode;
+    int32_t nchunk;
+    double* ws;
+    int64_t ws_doubles;
+    float eps, momentum;
+    float* mean;
+    float* invstd;
+    float* running_mean;
+    float* running_var;
+} mopoe_bn_req_t;
+int mopoe_conv_gemm_bn(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias, const mopoe_rows_t* D,
+                       int impl, const mopoe_bn_req_t* bn, void* stream);
+
 /* dWp[n, r*KW + k] (+)= sum_m dY[m, n] * A[m,r,k]   (fp32 output).  `ws` holds split partials
  * (ws_bytes from mopoe_conv_wgrad_ws); replaces the weight-gradient half of autograd's conv backward
  * (run_epochs.py:130 total_loss.backward()). */

@@ -40,6 +40,12 @@ class FusionCfg(C.Structure):
                 ('mem_cnt', C.c_int32 * 16), ('mem_idx', (C.c_int32 * 4) * 16), ('mem_end', (C.c_int32 * 4) * 16), ('norm', C.c_float), ('_pad', C.c_float)]
 
 
+class BnReq(C.Structure):
+    _fields_ = [('out', View), ('mask', C.c_void_p), ('mask_mode', C.c_int32), ('nchunk', C.c_int32), ('ws', C.c_void_p),
+                ('ws_doubles', C.c_int64), ('eps', C.c_float), ('momentum', C.c_float), ('mean', C.c_void_p),
+                ('invstd', C.c_void_p), ('running_mean', C.c_void_p), ('running_var', C.c_void_p)]
+
+
 class PackJob(C.Structure):
     _fields_ = [('W', C.c_void_p), ('dst', C.c_void_p * 4), ('A', C.c_int32), ('B', C.c_int32), ('KH', C.c_int32),
                 ('KW', C.c_int32), ('form', C.c_int32), ('bpad', C.c_int32), ('tile0', C.c_int32), ('nx', C.c_int32)]
@@ -60,6 +66,7 @@ SIGNATURES = {
     'mopoe_tc_wgrad_built': (_I, []),
     'mopoe_conv_gemm': (_I, [_W, _P, _P, _R, _I, _P]),
     'mopoe_conv_gemm_batched': (_I, [_I, _W, _P, _P, _R, _I, _P]),
+    'mopoe_conv_gemm_bn': (_I, [_I, _W, _P, _P, _R, _I, C.POINTER(BnReq), _P]),
     'mopoe_conv_wgrad_ws': (_S, [_W, _R, _I]),
     'mopoe_conv_wgrad': (_I, [_W, _R, _P, _I, _P, _S, _I, _P]),
     'mopoe_colsum': (_I, [_V, _P, _I, _P, _I, _P, _P]),

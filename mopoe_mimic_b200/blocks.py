@@ -72,20 +72,24 @@ def _eval_stats(rm, rv):
     return torch.stack((rm, torch.rsqrt(rv + BN_EPS)))
 
 
-def _main_fwd(eng, spec, x, Wg, bias, dtype):
-    """conv2 / shortcut forward by geometry kind -> plain Act"""
+def _main_fwd(eng, spec, x, Wg, bias, dtype, bn=None):
+    """conv2 / shortcut forward by geometry kind -> plain Act; bn = (mask, mode, running_mean, running_var): also the
+    training-mode BatchNorm statistics of the result -> (Act, stats)"""
     if spec.kind == 'S' and not spec.transposed:
-        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 1, spec.cout)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 1, spec.cout, bn=bn)
     if spec.kind == 'S':
-        return eng.gemm_up(x, eng.packed(Wg, "phase"), bias, spec.cout)
+        return eng.gemm_up(x, eng.packed(Wg, "phase"), bias, spec.cout, bn=bn)
     if spec.kind == 'Z':
-        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 0, spec.cout)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 0, spec.cout, bn=bn)
     if spec.kind == 'Q':
-        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 4, 1, spec.cout)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 4, 1, spec.cout, bn=bn)
     taps = 4 ** spec.nd if spec.nd == 2 else 4                     # 'U'
     bb = bias.repeat(taps) if bias is not None else None
     oh, ow = spec.out_hw(x.H, x.W)
-    return eng.gemm_rows(x, eng.packed(Wg, "full"), bb, taps * spec.cout, out_shape=(x.B, oh, ow, spec.cout))
+    out = eng.gemm_rows(x, eng.packed(Wg, "full"), bb, taps * spec.cout, out_shape=(x.B, oh, ow, spec.cout))
+    if bn is None:
+        return out
+    return out, eng.bn_stats(out, bn[0], bn[1], bn[2], bn[3])       # GEMM columns are (tap, channel) here: separate pass
 
 
 def _main_dgrad(eng, spec, dout, Wg, dtype, H, W):
@@ -143,16 +147,22 @@ class ResBlockFn(torch.autograd.Function):
                           Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device))
         # conv1 (1x1)
         w1f = eng.packed(P['conv1.weight'], 'matT' if sp.transposed else 'mat')
-        hh = eng.gemm_rows(a1, w1f, P.get('conv1.bias'), sp.cin)
+        # (training: the statistics of dropout1(conv1(.)) for bn2 come out of the GEMM's epilogue)
+        if run.train:
+            hh, st2 = eng.gemm_rows(a1, w1f, P.get('conv1.bias'), sp.cin, bn=(m1, mode) + tuple(bufs['bn2']))
+        else:
+            hh, st2 = eng.gemm_rows(a1, w1f, P.get('conv1.bias'), sp.cin), _eval_stats(*bufs['bn2'])
         # dropout1 -> bn2 -> relu  (written with the border conv2 needs)
-        st2 = eng.bn_stats(hh, m1, mode, *bufs['bn2']) if run.train else _eval_stats(*bufs['bn2'])
         pph, ppw = _pads(sp.nd, sp.needs_pad)
         a2 = eng.bn_apply(hh, m1, mode, st2, P['bn2.weight'], P['bn2.bias'], True,
                           Act.empty(B, H, W, sp.cin, pph, ppw, dt, eng.device))
         # conv2 and shortcut conv
         c = _main_fwd(eng, sp, a2, P['conv2.weight'], P.get('conv2.bias'), dt)
-        r = _main_fwd(eng, sp, x, P[short + '.0.weight'], P[short + '.0.bias'], dt)
-        st3 = eng.bn_stats(r, None, L.MASK_NONE, *bufs['short']) if run.train else _eval_stats(*bufs['short'])
+        if run.train:
+            r, st3 = _main_fwd(eng, sp, x, P[short + '.0.weight'], P[short + '.0.bias'], dt,
+                               bn=(None, L.MASK_NONE) + tuple(bufs['short']))
+        else:
+            r, st3 = _main_fwd(eng, sp, x, P[short + '.0.weight'], P[short + '.0.bias'], dt), _eval_stats(*bufs['short'])
         oph, opw = _pads(sp.nd, run.out_pad)
         y = eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b,
                         Act.empty(B, r.H, r.W, sp.cout, oph, opw, dt, eng.device))

@@ -440,6 +440,14 @@ extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int ma
     return 0;
 }
 
+int mopoe_bn_finalize_launch(const double* ws, int nchunk, int C, double count, float eps, float momentum, float* mean,
+                             float* invstd, float* rmean, float* rvar, void* stream) {
+    bn_finalize_kernel<<<(C + FIN_CH - 1) / FIN_CH, 256, 0, (cudaStream_t)stream>>>(ws, nchunk, C, count, eps, momentum, mean,
+                                                                                   invstd, rmean, rvar);
+    MOPOE_CHECK_LAUNCH("bn_finalize");
+    return 0;
+}
+
 extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, int* counters,
                             void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -63,3 +63,47 @@ extern "C" int mopoe_conv_wgrad_param(const mopoe_window_t* A, const mopoe_rows_
     if (impl != 1 && mopoe_tc_wgrad_eligible(A, dY)) return mopoe_conv_wgrad_tc(A, dY, grad, accumulate, ws, ws_bytes, stream, fin);
     return mopoe_conv_wgrad_simt(A, dY, grad, accumulate, ws, ws_bytes, stream, fin);
 }
+
+// ---- fprop with the output's BatchNorm statistics fused into the epilogue ------------------------------------------------
+struct TcStatsReq {
+    double* ws;
+    size_t ws_doubles;
+    const uint8_t* mask;
+    int mask_mode;
+    int rows_per_b;
+    int* nchunk_out;
+};
+int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                                  const mopoe_rows_t* D, const TcStatsReq* stats, void* stream);
+int mopoe_bn_finalize_launch(const double* ws, int nchunk, int C, double count, float eps, float momentum, float* mean,
+                             float* invstd, float* rmean, float* rvar, void* stream);
+
+extern "C" int mopoe_conv_gemm_bn(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                                  const mopoe_rows_t* D, int impl, const mopoe_bn_req_t* bn, void* stream) {
+    MOPOE_REQUIRE(nprob >= 1 && nprob <= 4, "conv_gemm_bn: nprob=%d (1..4)", nprob);
+    MOPOE_REQUIRE(bn && bn->ws && bn->mean && bn->invstd, "conv_gemm_bn: null statistics request");
+    MOPOE_REQUIRE(bn->out.C == D[0].N, "conv_gemm_bn: the output view has %d channels, the GEMM %d columns", bn->out.C, D[0].N);
+    bool tc = impl != 1;
+    for (int i = 0; i < nprob && tc; ++i) tc = mopoe_tc_fwd_eligible(&A[i], &D[i]) != 0;
+    if (impl == 2 && !tc) MOPOE_FAIL("conv_gemm_bn: tcgen05 path forced but problem not eligible");
+    int fused_chunks = 0;
+    if (tc) {
+        TcStatsReq req;
+        req.ws = bn->ws;
+        req.ws_doubles = (size_t)bn->ws_doubles;
+        req.mask = bn->mask;
+        req.mask_mode = bn->mask_mode;
+        req.rows_per_b = (A[0].E2 > 1 || A[0].E1 > 1) ? A[0].E0 * A[0].E1 : bn->out.H * bn->out.W;
+        req.nchunk_out = &fused_chunks;
+        if (mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, bias, D, &req, stream)) return 1;
+    } else {
+        for (int i = 0; i < nprob; ++i)
+            if (mopoe_conv_gemm_simt(&A[i], Wp[i], bias, &D[i], stream)) return 1;
+    }
+    if (fused_chunks > 0)
+        return mopoe_bn_finalize_launch(bn->ws, fused_chunks, bn->out.C, (double)bn->out.B * bn->out.H * bn->out.W, bn->eps,
+                                        bn->momentum, bn->mean, bn->invstd, bn->running_mean, bn->running_var, stream);
+    MOPOE_REQUIRE((long long)2 * bn->nchunk * bn->out.C <= bn->ws_doubles, "conv_gemm_bn: workspace too small for the fallback reduction");
+    return mopoe_bn_stats(&bn->out, bn->mask, bn->mask_mode, bn->ws, bn->nchunk, bn->eps, bn->momentum, bn->mean, bn->invstd,
+                          bn->running_mean, bn->running_var, nullptr, stream);
+}

@@ -9,6 +9,16 @@
 //   * up to 4 problems of identical shape in ONE launch: the sub-pixel phases of a stride-2 transposed conv
 //     (and of a conv's dgrad) share (M, N, K) and differ only in window origin, weights and output origin,
 //     so they become one grid instead of four quarter-size launches.
+//   * bf16 outputs leave through a TMA-STORE epilogue (template flag TMA_EPI): 64-column groups of the accumulator are read
+//     with one batch of tcgen05.ld (no wait per 16 columns), cast, written into a 128-byte-swizzled shared-memory staging
+//     tile and stored by ONE cp.async.bulk.tensor per group (two staging tiles alternate).  The register epilogue wrote
+//     32 B per lane to 32 different rows per instruction (4x the LSU wavefronts of a row-contiguous store) and was the
+//     bottleneck of every short-K layer (K = 512: 9,000 cycles per tile against 2,048 of MMA).
+//   * fused BatchNorm statistics (TcStats): while a group sits in the staging tile, each epilogue warp sums its own 32 rows
+//     column-wise (per-channel sum and sum of squares of the bf16-ROUNDED, dropout-masked values — what the consuming BN
+//     reads), accumulates per CTA in shared memory and writes fixed-order partials for bn_finalize_kernel: the separate
+//     statistics pass over the activation (reduce_rows_kernel<.,0>: 1.35 ms / step) disappears for conv1 -> bn2 and
+//     shortcut conv -> BN.  Deterministic: fixed tile -> CTA assignment, no atomics.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -27,6 +37,13 @@ constexpr int TCP_MAXP = 4;
 struct TcMaps {
     CUtensorMap a[TCP_MAXP];
     CUtensorMap b[TCP_MAXP];
+    CUtensorMap d[TCP_MAXP];      // output maps (n, m0, m1, m2) of the TMA-store epilogue
+};
+struct TcStats {
+    double* ws;                   // [gridDim.x * 4][2][N] partial (sum, sum of squares); NULL: no statistics
+    const uint8_t* mask;          // dropout keep-mask applied between this GEMM and the BatchNorm (x * 2 * mask)
+    int mask_mode;                // MOPOE_MASK_NONE / _BC ([B, N]) / _ELEM ([rows, N])
+    int rows_per_b;               // flat output rows per sample (MASK_BC: sample = flat row / rows_per_b)
 };
 struct TcPersistParams {
     int E0, E1, E2, BX, BY, NB, T0, T1, T2;
@@ -37,8 +54,14 @@ struct TcPersistParams {
     void* d;
     int d_is_bf16;
     const float* bias;
+    int nacc;                     // NT * BN: columns of the per-CTA statistics accumulators
+    TcStats st;
 };
 
+constexpr int EPI_BAR = 1;        // named barrier of the 4 epilogue warps
+constexpr uint32_t STG_BYTES = 128 * 128;   // one staging tile: 128 rows x 64 bf16, SWIZZLE_128B
+
+template <bool TMA_EPI>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersistParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -47,12 +70,17 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     uint8_t* const gen = smem_raw + (base - raw);
     const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)p.BN * 128;
     const uint32_t stage_bytes = a_bytes + b_bytes;
-    const uint32_t hdr = base + (uint32_t)p.stages * stage_bytes;
+    // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | statistics accumulators] | header
+    const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;
+    const uint32_t acc_bytes = (TMA_EPI && p.st.ws) ? (uint32_t)(8 * p.nacc) * 4u : 0u;
+    const uint32_t extra = TMA_EPI ? 2 * STG_BYTES + acc_bytes : 0u;
+    float* const sacc = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + 2 * STG_BYTES);
+    const uint32_t hdr = stg0 + extra;
     // header: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
     const uint32_t full0 = hdr, empty0 = hdr + 8u * p.stages, tfull0 = hdr + 16u * p.stages, tempty0 = tfull0 + 16,
                    tmem_slot = tempty0 + 16;
     volatile uint32_t* tmem_slot_gen =
-        reinterpret_cast<volatile uint32_t*>(gen + (size_t)p.stages * stage_bytes + 16 * p.stages + 32);
+        reinterpret_cast<volatile uint32_t*>(gen + (size_t)p.stages * stage_bytes + extra + 16 * p.stages + 32);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kpw = p.KW >> 6;
@@ -62,6 +90,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         for (int i = 0; i < p.nprob; ++i) {
             prefetch_tmap(&maps.a[i]);
             prefetch_tmap(&maps.b[i]);
+            if (TMA_EPI) prefetch_tmap(&maps.d[i]);
         }
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full0 + 8 * s, 1);
@@ -132,6 +161,122 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                 umma_commit(tfull0 + 8 * acc);
             }
         }
+    } else if constexpr (TMA_EPI) {
+        // ===== TMA-store epilogue (bf16 output, BN % 64 == 0): 4 warps, warp q owns TMEM lanes / tile rows [32q, 32q+32) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool leader = threadIdx.x == 64;                     // issues the bulk stores of this CTA
+        const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
+        const bool stats = p.st.ws != nullptr;
+        if (stats) {
+            for (int i = threadIdx.x - 64; i < 8 * p.nacc; i += 128) sacc[i] = 0.f;
+            named_bar_sync(EPI_BAR, 128);
+        }
+        const uint32_t swz = (uint32_t)(row & 7);
+        int iter = 0;
+        uint32_t sbuf = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
+            const int nt = tile % p.NT;
+            const int tq = tile / p.NT;
+            const int prob = tq % p.nprob, mt = tq / p.nprob;
+            const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
+            const int n0 = nt * p.BN;
+            const int m0 = t0 * p.BX + i1, m1 = t1 * p.BY + i2, m2 = t2 * p.NB + i4;
+            const bool rvalid = m0 < p.E0 && m1 < p.E1 && m2 < p.E2;
+            const unsigned flat = (unsigned)((m2 * p.E1 + m1) * p.E0 + m0);        // flat output row (host checks < 2^31)
+            const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+            const int ngroups = p.BN >> 6;
+            for (int g = 0; g < ngroups; ++g) {
+                const int c0 = n0 + g * 64;
+                uint32_t r0[32], r1[32];
+                tmem_ld32_nowait(t_addr + (uint32_t)(g * 64), r0);
+                tmem_ld32_nowait(t_addr + (uint32_t)(g * 64 + 32), r1);
+                tmem_ld_wait();
+                if (g == ngroups - 1) {
+                    // every TMEM read of this accumulator buffer is complete: hand it back before the stores
+                    fence_before();
+                    mbar_arrive(tempty0 + 8 * acc);
+                }
+                uint32_t w[32];                                     // 64 bf16, packed
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float a0 = __uint_as_float(r0[2 * j]), a1 = __uint_as_float(r0[2 * j + 1]);
+                    float b0 = __uint_as_float(r1[2 * j]), b1 = __uint_as_float(r1[2 * j + 1]);
+                    if (p.bias) {
+                        const int ca = c0 + 2 * j, cb = c0 + 32 + 2 * j;
+                        if (ca < p.N) a0 += __ldg(p.bias + ca);
+                        if (ca + 1 < p.N) a1 += __ldg(p.bias + ca + 1);
+                        if (cb < p.N) b0 += __ldg(p.bias + cb);
+                        if (cb + 1 < p.N) b1 += __ldg(p.bias + cb + 1);
+                    }
+                    __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
+                    w[j] = *reinterpret_cast<uint32_t*>(&ha);
+                    w[16 + j] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+                // the staging tile we are about to overwrite: its previous bulk store must have finished READING it
+                if (leader) bulk_wait_read<1>();
+                named_bar_sync(EPI_BAR, 128);
+                const uint32_t stg = stg0 + sbuf * STG_BYTES;
+                const uint32_t rbase = stg + (uint32_t)row * 128u;
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)                      // 16-byte chunk ch of the row -> swizzled slot
+                    st_shared_v4(rbase + ((((uint32_t)ch) ^ swz) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+                fence_proxy_async_smem();
+                if (stats) {
+                    // column sums over THIS warp's 32 rows (written by this warp: a warp-level sync suffices).  Lane l
+                    // owns columns c0 + 2l, c0 + 2l + 1: one 128-byte row per step, conflict-free.
+                    __syncwarp();
+                    const int cn = c0 + 2 * lane;
+                    const bool cvalid = cn < p.N;
+                    const uint32_t jchunk = (uint32_t)lane >> 2, wsel = ((uint32_t)lane & 3u) << 2;
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                    const unsigned myb = p.st.mask_mode == MOPOE_MASK_BC ? flat / (unsigned)p.st.rows_per_b : flat;
+#pragma unroll 4
+                    for (int i = 0; i < 32; ++i) {
+                        const unsigned rb = __shfl_sync(0xffffffffu, myb, i);
+                        if (!((vmask >> i) & 1u)) continue;
+                        const uint32_t rr = (uint32_t)(q * 32 + i);
+                        const uint32_t word = ld_shared_b32(stg + rr * 128u + ((jchunk ^ (rr & 7u)) << 4) + wsel);
+                        float x0 = __uint_as_float(word << 16), x1 = __uint_as_float(word & 0xffff0000u);
+                        if (p.st.mask_mode != MOPOE_MASK_NONE && cvalid) {
+                            const unsigned short mk = *reinterpret_cast<const unsigned short*>(p.st.mask + (size_t)rb * p.N + cn);
+                            x0 = (mk & 0xffu) ? 2.f * x0 : 0.f;
+                            x1 = (mk & 0xff00u) ? 2.f * x1 : 0.f;
+                        }
+                        s0 += x0;
+                        s1 += x1;
+                        q0 = fmaf(x0, x0, q0);
+                        q1 = fmaf(x1, x1, q1);
+                    }
+                    if (cvalid) {
+                        float* a = sacc + (size_t)(q * 2) * p.nacc + cn;           // exclusive owner of these entries
+                        a[0] += s0;
+                        a[1] += s1;
+                        a[p.nacc] += q0;
+                        a[p.nacc + 1] += q1;
+                    }
+                }
+                named_bar_sync(EPI_BAR, 128);                       // all 128 rows are in the staging tile and fenced
+                if (leader) {
+                    tma_store_4d(&maps.d[prob], stg, c0, t0 * p.BX, t1 * p.BY, t2 * p.NB);
+                    bulk_commit();
+                }
+                sbuf ^= 1u;
+            }
+        }
+        if (leader) bulk_wait<0>();                                 // the last stores have landed before the CTA exits
+        if (stats) {
+            named_bar_sync(EPI_BAR, 128);
+            for (int i = threadIdx.x - 64; i < 8 * p.N; i += 128) {
+                const int n = i % p.N, k = i / p.N;                 // k = q * 2 + which
+                p.st.ws[((size_t)blockIdx.x * 8 + k) * p.N + n] = (double)sacc[(size_t)k * p.nacc + n];
+            }
+        }
     } else {
         // ===== epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====
         const int q = warp & 3;
@@ -195,7 +340,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             fence_before();
             mbar_arrive(tempty0 + 8 * acc);
         }
-    }
+        }
     fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
@@ -216,12 +361,34 @@ static int bm256_enabled() {
 static bool g_persist_attr_set = false;
 static int g_num_sms = 0;
 
-// nprob problems of identical (E0,E1,E2,R,KW,N, output strides): window base / weights / output origin differ
-int mopoe_conv_gemm_tc_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
-                               const mopoe_rows_t* D, void* stream) {
+static int tma_epi_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_GEMM_TMA_EPI");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
+// Fused BatchNorm statistics request of mopoe_conv_gemm_tc_batched_ex (host side of TcStats)
+struct TcStatsReq {
+    double* ws;              // >= 8 * #SMs * N doubles
+    size_t ws_doubles;
+    const uint8_t* mask;
+    int mask_mode;
+    int rows_per_b;
+    int* nchunk_out;         // number of [2][N] partial slabs written (for bn_finalize_kernel)
+};
+
+// nprob problems of identical (E0,E1,E2,R,KW,N, output strides): window base / weights / output origin differ.
+// stats != NULL: fuse the output's per-channel statistics when the TMA-store epilogue applies; *stats->nchunk_out = 0
+// tells the caller that they were NOT produced (it then runs the separate statistics pass).
+int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                                  const mopoe_rows_t* D, const TcStatsReq* stats, void* stream) {
     MOPOE_REQUIRE(nprob >= 1 && nprob <= TCP_MAXP, "conv_gemm_tc_batched: nprob=%d", nprob);
     if (!mopoe_tc_init_state()) MOPOE_FAIL("conv_gemm_tc_batched: tcgen05 path unavailable on this device");
-    if (bm256_enabled()) {
+    if (stats && stats->nchunk_out) *stats->nchunk_out = 0;
+    if (bm256_enabled() && !stats) {
         bool same = true;
         for (int i = 1; i < nprob; ++i)
             same = same && A[i].E0 == A[0].E0 && A[i].E1 == A[0].E1 && A[i].E2 == A[0].E2 && A[i].R == A[0].R &&
@@ -244,23 +411,61 @@ int mopoe_conv_gemm_tc_batched(int nprob, const mopoe_window_t* A, const void* c
     mopoe_tc_tile_split(p.E0, p.E1, 128, p.BX, p.BY, p.NB);
     p.T0 = (p.E0 + p.BX - 1) / p.BX; p.T1 = (p.E1 + p.BY - 1) / p.BY; p.T2 = (p.E2 + p.NB - 1) / p.NB;
     p.BN = mopoe_tc_pick_bn(p.N);
+    // wide layers whose best tile is not a multiple of 64 columns (N = 640 -> 160): take 128 so that the TMA-store epilogue
+    // (64-column groups) and the fused statistics apply
+    if (tma_epi_enabled() && D[0].d_dtype == MOPOE_BF16 && p.N > 256 && p.BN % 64 != 0) p.BN = 128;
     p.NT = (p.N + p.BN - 1) / p.BN;
+    p.nacc = p.NT * p.BN;
     int cols = 2 * p.BN, pc = 32;
     while (pc < cols) pc <<= 1;
     MOPOE_REQUIRE(pc <= 512, "conv_gemm_tc_batched: BN=%d needs %d TMEM columns", p.BN, pc);
     p.tmem_cols = pc;
-    const int stage_bytes = 128 * 128 + p.BN * 128;
-    const int hdr_bytes = 16 * 8 + 48 + 64;
-    int stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes) / stage_bytes;
-    if (stages > 8) stages = 8;
-    MOPOE_REQUIRE(stages >= 2, "conv_gemm_tc_batched: no room for 2 stages (BN=%d)", p.BN);
-    p.stages = stages;
     p.nprob = nprob;
     p.tiles_per_prob = p.T0 * p.T1 * p.T2 * p.NT;
     p.total_tiles = p.tiles_per_prob * nprob;
     p.s0 = D[0].s0; p.s1 = D[0].s1; p.s2 = D[0].s2; p.d = D[0].d;
     p.d_is_bf16 = D[0].d_dtype == MOPOE_BF16;
     p.bias = bias;
+    p.st.ws = nullptr; p.st.mask = nullptr; p.st.mask_mode = MOPOE_MASK_NONE; p.st.rows_per_b = 1;
+    if (!g_persist_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+        g_persist_attr_set = true;
+    }
+    const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+    // TMA-store epilogue: bf16 rows whose strides / origins are 16-byte aligned, 64-column groups
+    bool tma_epi = tma_epi_enabled() && p.d_is_bf16 && p.BN % 64 == 0 && p.N % 8 == 0 && p.s0 % 8 == 0 && p.s1 % 8 == 0 &&
+                   p.s2 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 &&
+                   (long long)p.E0 * p.E1 * p.E2 < (1ll << 31);
+    for (int i = 0; i < nprob && tma_epi; ++i) tma_epi = D[i].d_off % 8 == 0;
+    bool fuse_stats = false;
+    if (stats && tma_epi && stats->ws && (size_t)grid * 8 * p.N <= stats->ws_doubles &&
+        (stats->mask_mode == MOPOE_MASK_NONE || (nprob == 1 && stats->mask && p.N % 2 == 0))) {
+        fuse_stats = true;
+        p.st.ws = stats->ws;
+        p.st.mask = stats->mask_mode == MOPOE_MASK_NONE ? nullptr : stats->mask;
+        p.st.mask_mode = stats->mask_mode;
+        p.st.rows_per_b = stats->rows_per_b > 0 ? stats->rows_per_b : 1;
+    }
+    const int stage_bytes = 128 * 128 + p.BN * 128;
+    const int hdr_bytes = 16 * 8 + 48 + 64;
+    const int extra = tma_epi ? 2 * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) : 0;
+    int stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes - extra) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2 && tma_epi) {                  // (never with the model's shapes) fall back to the register epilogue
+        tma_epi = fuse_stats = false;
+        p.st.ws = nullptr;
+        stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes) / stage_bytes;
+        if (stages > 8) stages = 8;
+    }
+    MOPOE_REQUIRE(stages >= 2, "conv_gemm_tc_batched: no room for 2 stages (BN=%d)", p.BN);
+    p.stages = stages;
     TcMaps maps;
     for (int i = 0; i < nprob; ++i) {
         p.d_off[i] = D[i].d_off;
@@ -274,20 +479,27 @@ int mopoe_conv_gemm_tc_batched(int nprob, const mopoe_window_t* A, const void* c
         const uint64_t strb[2] = {1, K};
         const uint32_t boxb[2] = {64, (uint32_t)p.BN};
         if (mopoe_tc_encode(&maps.b[i], Wp[i], 2, dimsb, strb, boxb, "conv_gemm_tc(B)")) return 1;
+        if (tma_epi) {
+            const uint64_t dimsd[4] = {(uint64_t)p.N, (uint64_t)p.E0, (uint64_t)p.E1, (uint64_t)p.E2};
+            const uint64_t strd[4] = {1, (uint64_t)p.s0, (uint64_t)p.s1, (uint64_t)p.s2};
+            const uint32_t boxd[4] = {64, (uint32_t)p.BX, (uint32_t)p.BY, (uint32_t)p.NB};
+            if (mopoe_tc_encode(&maps.d[i], reinterpret_cast<const bf16*>(p.d) + D[i].d_off, 4, dimsd, strd, boxd, "conv_gemm_tc(D)"))
+                return 1;
+        }
     }
     for (int i = nprob; i < TCP_MAXP; ++i) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
-    if (!g_persist_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
-        if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-        g_persist_attr_set = true;
-    }
-    const int smem = 1024 + stages * stage_bytes + hdr_bytes;
-    const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
-    conv_gemm_tc_persist_kernel<<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    if (!tma_epi) memset(maps.d, 0, sizeof(maps.d));
+    else for (int i = nprob; i < TCP_MAXP; ++i) maps.d[i] = maps.d[0];
+    const int smem = 1024 + stages * stage_bytes + extra + hdr_bytes;
+    if (tma_epi)
+        conv_gemm_tc_persist_kernel<true><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    else
+        conv_gemm_tc_persist_kernel<false><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
     MOPOE_CHECK_LAUNCH("conv_gemm_tc_persist");
+    if (fuse_stats && stats->nchunk_out) *stats->nchunk_out = grid * 4;
     return 0;
+}
+int mopoe_conv_gemm_tc_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                               const mopoe_rows_t* D, void* stream) {
+    return mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, bias, D, nullptr, stream);
 }

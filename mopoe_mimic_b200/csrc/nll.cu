@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) categorical_bwd_big_kernel(const float* _
 // odd V, at worst 2-way otherwise).  No shuffles, ~12 instructions per element; the warp-per-row kernel above spent ~35
 // shuffles and 6 dependent global loads per row and reached 0.15 of the HBM roofline.  The forward also stores the row's
 // logsumexp, so the backward is a flat elementwise pass (one read of the scores, one write of the gradient).
-constexpr int CAT_RB_THREADS = 128;
+constexpr int CAT_RB_THREADS = 64;      // rows (= threads) per block: 36 KB of staging at V = 71 -> 6 blocks per SM
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256) categorical_bwd_flat_kernel(const float* 
 }
 
 static int cat_rows_per_block(int V) {
-    int rb = (96 * 1024 / 8) / V;                  // scores + target chunk <= 96 KB: >= 2 blocks per SM
+    int rb = (96 * 1024 / 8) / V;                  // scores + target chunk <= 96 KB
     if (rb > CAT_RB_THREADS) rb = CAT_RB_THREADS;
     return rb / 4 * 4;
 }
@@ -425,7 +425,7 @@ extern "C" int mopoe_categorical_logprob_sum(const float* y, const float* target
         const size_t smem = (size_t)RB * V * sizeof(float) * (target ? 2 : 1);
         int bps = (int)((200 * 1024) / (smem + 1024));
         if (bps < 1) bps = 1;
-        if (bps > 8) bps = 8;
+        if (bps > 12) bps = 12;
         long long grid = (long long)148 * bps;
         if (grid > nchunks) grid = nchunks;
         if (grid > nchunk) grid = nchunk;

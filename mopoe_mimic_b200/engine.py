@@ -83,6 +83,7 @@ class Engine:
         import os
         self.batched = os.environ.get('MOPOE_GEMM_BATCHED', '1') != '0'       # phases of a deconv in one launch
         self.persistent = os.environ.get('MOPOE_GEMM_PERSISTENT', '1') != '0'   # persistent kernel for single GEMMs too
+        self.fuse_stats = os.environ.get('MOPOE_FUSE_BN_STATS', '1') != '0'     # BatchNorm statistics in the GEMM epilogue
 
     # ---- packed-weight cache ---------------------------------------------------------------------------------
     # Every (weight, form) has a persistent SLOT (destination buffers with fixed addresses).  A slot is valid while its
@@ -292,15 +293,48 @@ class Engine:
         if L.PROFILE is not None:
             L.annotate(kind=kind, bytes=passes * v.B * v.H * v.W * v.C * v.t.element_size() + extra)
 
-    def _gemm(self, win, wp, bias, rows):
-        self._gemm_batched([win], [wp], bias, [rows])
+    def _gemm(self, win, wp, bias, rows, bn=None, out=None):
+        return self._gemm_batched([win], [wp], bias, [rows], bn, out)
 
-    def _gemm_batched(self, wins, wps, bias, rows_list):
-        """up to 4 same-shape problems in ONE launch (persistent tcgen05 kernel when eligible)"""
+    def _bn_request(self, out, bn):
+        """mopoe_bn_req_t for a GEMM whose output `out` feeds a training-mode BatchNorm; bn = (mask, mode, rmean, rvar)"""
+        mask, mode, rmean, rvar = bn
+        rows = out.B * out.H * out.W
+        nc = self.nchunk(rows, out.C)
+        nd = max(2 * nc, 8 * 160) * out.C
+        ws = self.ws64(nd)
+        stats = self.f32(2, out.C)
+        req = L.BnReq()
+        req.out = out.view()
+        req.mask, req.mask_mode, req.nchunk = (mask.data_ptr() if mask is not None else None), mode, nc
+        req.ws, req.ws_doubles = ws.data_ptr(), ws.numel()
+        req.eps, req.momentum = 1e-5, 0.1
+        req.mean, req.invstd = stats[0].data_ptr(), stats[1].data_ptr()
+        req.running_mean = rmean.data_ptr() if rmean is not None else None
+        req.running_var = rvar.data_ptr() if rvar is not None else None
+        return req, stats, (ws, mask, rmean, rvar)
+
+    def _gemm_batched(self, wins, wps, bias, rows_list, bn=None, out=None):
+        """up to 4 same-shape problems in ONE launch (persistent tcgen05 kernel when eligible).  bn = (mask, mode,
+        running_mean, running_var): also produce the training-mode BatchNorm statistics of the output `out` (fused into
+        the GEMM epilogue where the library can); returns them as a [2, C] tensor (mean, 1/sqrt(var + eps))."""
         n = len(wins)
         for wp in wps:
             assert wp.is_contiguous() and wp.dtype == self._win_dtype(wins[0])
         flops = sum(2.0 * w.E0 * w.E1 * w.E2 * r.N * w.R * w.KW for w, r in zip(wins, rows_list))
+        if bn is not None and not self.fuse_stats:
+            self._gemm_batched(wins, wps, bias, rows_list)
+            return self.bn_stats(out, bn[0], bn[1], bn[2], bn[3])
+        if bn is not None:
+            req, stats, keep = self._bn_request(out, bn)
+            WA = (L.Window * n)(*wins)
+            RA = (L.Rows * n)(*rows_list)
+            PA = (C.c_void_p * n)(*[wp.data_ptr() for wp in wps])
+            w0 = wins[0]
+            self._timed('fprop/dgrad', flops, lambda: L.call('mopoe_conv_gemm_bn', n, WA, PA, L.ptr(bias), RA, self.impl,
+                                                             C.byref(req), L.stream_ptr()),
+                        'x%d+bn M=%dx%dx%d N=%d K=%dx%d' % (n, w0.E2, w0.E1, w0.E0, rows_list[0].N, w0.R, w0.KW))
+            return stats
         if self.batched and (n > 1 or self.persistent):
             WA = (L.Window * n)(*wins)
             RA = (L.Rows * n)(*rows_list)
@@ -372,20 +406,20 @@ class Engine:
         return L.Rows(act.t.data_ptr(), L.dtype_code(act.dtype), N or act.C, act.origin(), act.C,
                       act.Ws * act.C, act.Hs * act.Ws * act.C)
 
-    def gemm_down(self, x, wc, bias, k, s, p, n, out_dtype=None, out=None):
+    def gemm_down(self, x, wc, bias, k, s, p, n, out_dtype=None, out=None, bn=None):
         win, OH, OW = self.win_down(x, k, s, p)
         if out is None:
             out = Act.empty(x.B, OH, OW, n, 0, 0, out_dtype or x.dtype, self.device)
         assert (out.B, out.H, out.W, out.C) == (x.B, OH, OW, n)
-        self._gemm(win, wc, bias, self.rows_of(out))
-        return out
+        st = self._gemm(win, wc, bias, self.rows_of(out), bn, out)
+        return out if bn is None else (out, st)
 
     def wgrad_down(self, xwin, k, s, p, yrows):
         win, OH, OW = self.win_down(xwin, k, s, p)
         assert (yrows.H, yrows.W, yrows.B) == (OH, OW, xwin.B), ((yrows.H, yrows.W), (OH, OW))
         return self._wgrad(win, self.rows_of(yrows), yrows.C, win.R * win.KW)
 
-    def gemm_up(self, x, wph, bias, n, out_dtype=None):
+    def gemm_up(self, x, wph, bias, n, out_dtype=None, bn=None):
         """stride-2 k4 p1 transposed conv as 2^nd sub-pixel phase GEMMs (x must carry a border >= 1)"""
         Cc = x.C
         assert x.pw >= 1 and (x.H == 1 or x.ph >= 1)
@@ -396,8 +430,8 @@ class Engine:
                 wins.append(L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, 1, x.B, 1, 2 * Cc, 0,
                                      (x.pw - 1 + px) * Cc, Cc, 0, x.Ws * Cc, 0))
                 rows_l.append(L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, px * n, 2 * n, 0, 2 * x.W * n))
-            self._gemm_batched(wins, list(wph), bias, rows_l)
-            return out
+            st = self._gemm_batched(wins, list(wph), bias, rows_l, bn, out)
+            return out if bn is None else (out, st)
         out = Act.empty(x.B, 2 * x.H, 2 * x.W, n, 0, 0, out_dtype or x.dtype, self.device)
         OW = 2 * x.W
         wins, rows_l = [], []
@@ -408,8 +442,8 @@ class Engine:
                                      a_off, Cc, x.Ws * Cc, x.Hs * x.Ws * Cc, x.Ws * Cc))
                 rows_l.append(L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, (py * OW + px) * n, 2 * n,
                                      2 * OW * n, 2 * x.H * OW * n))
-        self._gemm_batched(wins, list(wph), bias, rows_l)
-        return out
+        st = self._gemm_batched(wins, list(wph), bias, rows_l, bn, out)
+        return out if bn is None else (out, st)
 
     def gemm_unfold(self, dy, wfull, n, H, W, k, p):
         """input gradient of a conv whose stride equals its kernel (the 256-px stage: k4 s4 p1, FeatureExtractorImg.py
@@ -432,7 +466,7 @@ class Engine:
         self._gemm_batched(wins, wps, None, rows_l)
         return out
 
-    def gemm_rows(self, x, w, bias, n, out_shape=None, out_dtype=None):
+    def gemm_rows(self, x, w, bias, n, out_shape=None, out_dtype=None, bn=None):
         """pointwise GEMM over the interior pixels of x: out[m, n] = sum_c x[m, c] w[n, c] (+bias)"""
         Cc = x.C
         if x.ph == 0 and x.pw == 0:
@@ -447,8 +481,9 @@ class Engine:
             rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, 0, n, 0, 0)
         else:
             rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, 0, n, x.W * n, x.H * x.W * n)
-        self._gemm(win, w, bias, rows)
-        return out
+        assert bn is None or out_shape is None, 'fused statistics need GEMM columns == output channels'
+        st = self._gemm(win, w, bias, rows, bn, out)
+        return out if bn is None else (out, st)
 
     def wgrad_rows_param(self, x, dy, param):
         """param.grad[n, c] += sum_m dy[m, n] x[m, c] (a 1x1 conv / linear weight [n, c, 1..]); False if the parameter

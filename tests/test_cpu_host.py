@@ -210,7 +210,9 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
              ('mopoe_fusion_cfg_t', L.FusionCfg, ['M', 'fuse_mode', 'members', 'stacked', 'sel_end', 'mem_cnt', 'mem_idx',
                                                   'mem_end', 'norm']),
              ('mopoe_pack_job_t', L.PackJob, ['W', 'dst', 'A', 'bpad', 'tile0', 'nx']),
-             ('mopoe_dp_peers_t', L.DpPeers, ['grad', 'param', 'flags'])]
+             ('mopoe_dp_peers_t', L.DpPeers, ['grad', 'param', 'flags']),
+             ('mopoe_bn_req_t', L.BnReq, ['out', 'mask', 'mask_mode', 'nchunk', 'ws', 'ws_doubles', 'eps', 'momentum', 'mean',
+                                          'running_var'])]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "mopoe_b200.h"', 'int main(void) {']
     for cname, _, fields in pairs:
         src.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))

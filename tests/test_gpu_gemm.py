@@ -132,3 +132,69 @@ def test_valid_4to1_and_1to4(impl, dtype):
     out2 = eng.gemm_rows(za, full_form(wt.cuda(), dtype), None, 16 * co, out_shape=(B, 4, 4, co))
     torch.cuda.synchronize()
     assert (_to_nchw(out2, 2) - ref2).abs().max() <= tol * ref2.abs().max()
+
+
+BN_CASES = [
+    # (kind, nd, B, Cin, Cout, spatial, mask)
+    ('rows', 2, 4, 128, 128, 16, 'bc'),          # conv1 of a 2-D block: Dropout2d mask [B, C]
+    ('rows', 2, 3, 64, 256, 7, 'bc'),            # ragged: 147 rows, not a multiple of the 128-row tile
+    ('rows', 1, 4, 128, 384, 100, 'elem'),       # conv1 of a 1-D block: elementwise mask [B, L, C]; BN = 192
+    ('rows', 2, 2, 64, 640, 4, 'bc'),            # wide layer: 5 n-tiles of 128
+    ('rows', 2, 2, 64, 96, 8, 'bc'),             # BN = 96: register epilogue + separate statistics pass inside the library
+    ('down', 2, 4, 64, 128, 16, None),           # shortcut conv k4 s2 p1
+    ('down', 1, 3, 64, 512, 64, None),
+    ('up', 2, 4, 128, 64, 8, None),              # shortcut deconv: 4 sub-pixel phases in one launch
+    ('up', 1, 5, 64, 256, 32, None),             # 2 phases
+]
+
+
+@pytest.mark.parametrize('impl,dtype', [('tc', torch.bfloat16), ('simt', torch.float32)])
+@pytest.mark.parametrize('kind,nd,B,ci,co,sp,mask', BN_CASES)
+def test_gemm_with_fused_batchnorm_statistics(impl, dtype, kind, nd, B, ci, co, sp, mask):
+    """mopoe_conv_gemm_bn: the GEMM output must equal the plain launch bit for bit, and the statistics must equal the
+    separate reduction pass over the stored output (the path it replaces) and torch's own batch statistics."""
+    from mopoe_mimic_b200 import _lib as L
+    from mopoe_mimic_b200.engine import conv_form, phase_form
+    eng = _eng(dtype, impl)
+    shp = (B, ci, sp) if nd == 1 else (B, ci, sp, sp)
+    x = _rand(shp, 21, 1.0, dtype)
+    bias = _rand((co,), 23, 0.5).cuda()
+    g = torch.Generator().manual_seed(24)
+    rm0, rv0 = torch.randn(co, generator=g), torch.rand(co, generator=g) + 0.5
+
+    def run(bn):
+        if kind == 'rows':
+            w = _rand((co, ci), 22, 0.05, dtype).to(dtype).cuda().contiguous()
+            return eng.gemm_rows(_act(x, 0, dtype, nd), w, bias, co, bn=bn)
+        if kind == 'down':
+            w = _rand((co, ci, 4) if nd == 1 else (co, ci, 4, 4), 22, 0.05, dtype)
+            return eng.gemm_down(_act(x, 1, dtype, nd), conv_form(w.cuda(), dtype), bias, 4, 2, 1, co, bn=bn)
+        w = _rand((ci, co, 4) if nd == 1 else (ci, co, 4, 4), 22, 0.05, dtype)
+        return eng.gemm_up(_act(x, 1, dtype, nd), phase_form(w.cuda(), dtype), bias, co, bn=bn)
+    plain = run(None)
+    rows = plain.B * plain.H * plain.W
+    mk, mode = None, L.MASK_NONE
+    if mask == 'bc':
+        mk, mode = (torch.rand(B * co, generator=g) < 0.5).to(torch.uint8).cuda(), L.MASK_BC
+    elif mask == 'elem':
+        mk, mode = (torch.rand(rows * co, generator=g) < 0.5).to(torch.uint8).cuda(), L.MASK_ELEM
+    rm, rv = rm0.clone().cuda(), rv0.clone().cuda()
+    out, st = run((mk, mode, rm, rv))
+    torch.cuda.synchronize()
+    assert torch.equal(out.t, plain.t)
+    # the path it replaces: the separate statistics pass over the stored output
+    rm2, rv2 = rm0.clone().cuda(), rv0.clone().cuda()
+    st_ref = eng.bn_stats(plain, mk, mode, rm2, rv2)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(st, st_ref, rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(rm, rm2, rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(rv, rv2, rtol=2e-5, atol=2e-6)
+    # and torch's definition (biased variance for the normalisation, eps 1e-5)
+    v = plain.interior().double().reshape(rows, co)
+    if mask == 'bc':
+        v = (v.view(B, -1, co) * (2.0 * mk.view(B, 1, co).double())).reshape(rows, co)
+    elif mask == 'elem':
+        v = v * (2.0 * mk.view(rows, co).double())
+    mean, var = v.mean(0), v.var(0, unbiased=False)
+    torch.testing.assert_close(st[0].double(), mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(st[1].double(), 1.0 / torch.sqrt(var + 1e-5), rtol=1e-4, atol=1e-5)
