@@ -299,8 +299,8 @@ int mopoe_onehot_u8(const uint8_t* idx, int64_t rows, int V, float* out, void* s
 
 /* All weight re-layouts of a step in ONE launch.  jobs_dev: DEVICE array of njobs descriptors (same meaning as the
  * arguments of mopoe_pack_weight_tiled; form 1 fills dst[0..3] / dst[0..1], the others dst[0]); tile0 = index of the
- * job's first tile in the launch grid and nx = its tile-grid width, both from mopoe_pack_job_tiles (which returns the
- * job's tile count).  total_tiles = sum of the tile counts.  Replaces nothing in the reference (torch.nn consumes its
+ * job's first tile (a run of 256 work items = one thread block) in the launch grid; mopoe_pack_job_tiles returns the
+ * job's tile count (nx: unused, set to 0).  Jobs must be sorted by tile0.  total_tiles = sum of the tile counts.  Replaces nothing in the reference (torch.nn consumes its
  * fp32 weights in place); it exists because the tcgen05 kernels want K-major bf16 operands. */
 typedef struct {
     const float* W;

@@ -73,8 +73,10 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | statistics accumulators] | header
     const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;
     const uint32_t acc_bytes = (TMA_EPI && p.st.ws) ? (uint32_t)(8 * p.nacc) * 4u : 0u;
-    const uint32_t extra = TMA_EPI ? 2 * STG_BYTES + acc_bytes : 0u;
+    const uint32_t bias_bytes = (TMA_EPI && p.bias) ? (uint32_t)p.nacc * 4u : 0u;
+    const uint32_t extra = TMA_EPI ? 2 * STG_BYTES + acc_bytes + bias_bytes : 0u;
     float* const sacc = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + 2 * STG_BYTES);
+    const float* const sbias = reinterpret_cast<const float*>(gen + (size_t)p.stages * stage_bytes + 2 * STG_BYTES + acc_bytes);
     const uint32_t hdr = stg0 + extra;
     // header: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
     const uint32_t full0 = hdr, empty0 = hdr + 8u * p.stages, tfull0 = hdr + 16u * p.stages, tempty0 = tfull0 + 16,
@@ -168,10 +170,11 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         const bool leader = threadIdx.x == 64;                     // issues the bulk stores of this CTA
         const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
         const bool stats = p.st.ws != nullptr;
-        if (stats) {
+        if (stats)
             for (int i = threadIdx.x - 64; i < 8 * p.nacc; i += 128) sacc[i] = 0.f;
-            named_bar_sync(EPI_BAR, 128);
-        }
+        if (p.bias)                                                // the bias row, zero-padded to the tile grid
+            for (int i = threadIdx.x - 64; i < p.nacc; i += 128) const_cast<float*>(sbias)[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
+        if (stats || p.bias) named_bar_sync(EPI_BAR, 128);
         const uint32_t swz = (uint32_t)(row & 7);
         int iter = 0;
         uint32_t sbuf = 0;
@@ -187,6 +190,21 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             const bool rvalid = m0 < p.E0 && m1 < p.E1 && m2 < p.E2;
             const unsigned flat = (unsigned)((m2 * p.E1 + m1) * p.E0 + m0);        // flat output row (host checks < 2^31)
             const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
+            // row key of the dropout mask: sample index (Dropout2d mask [B, N]) or flat row (elementwise mask [rows, N])
+            const unsigned mykey = p.st.mask_mode == MOPOE_MASK_BC ? flat / (unsigned)p.st.rows_per_b : flat;
+            const unsigned key_lo = __shfl_sync(0xffffffffu, mykey, 0), key_hi = __shfl_sync(0xffffffffu, mykey, 31);
+            // Dropout2d mask, all 32 rows of the warp in one sample: ONE mask value per column — fetched here, before the
+            // wait for the accumulator, so that its L2 round trip is off the epilogue's critical path
+            const bool warp_mask = stats && p.st.mask_mode == MOPOE_MASK_BC && key_lo == key_hi;
+            unsigned long long mkw = 0ull;                        // 4 groups x 16 bits
+            if (warp_mask) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int cn = n0 + g * 64 + 2 * lane;
+                    if (g * 64 < p.BN && cn < p.N)
+                        mkw |= (unsigned long long)*reinterpret_cast<const unsigned short*>(p.st.mask + (size_t)key_lo * p.N + cn) << (16 * g);
+                }
+            }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -203,20 +221,29 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     mbar_arrive(tempty0 + 8 * acc);
                 }
                 uint32_t w[32];                                     // 64 bf16, packed
+                if (p.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(sbias + c0);     // broadcast reads
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float a0 = __uint_as_float(r0[2 * j]), a1 = __uint_as_float(r0[2 * j + 1]);
-                    float b0 = __uint_as_float(r1[2 * j]), b1 = __uint_as_float(r1[2 * j + 1]);
-                    if (p.bias) {
-                        const int ca = c0 + 2 * j, cb = c0 + 32 + 2 * j;
-                        if (ca < p.N) a0 += __ldg(p.bias + ca);
-                        if (ca + 1 < p.N) a1 += __ldg(p.bias + ca + 1);
-                        if (cb < p.N) b0 += __ldg(p.bias + cb);
-                        if (cb + 1 < p.N) b1 += __ldg(p.bias + cb + 1);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 ba = b4[j], bb = b4[8 + j];
+                        __nv_bfloat162 h;
+                        h = __floats2bfloat162_rn(__uint_as_float(r0[4 * j]) + ba.x, __uint_as_float(r0[4 * j + 1]) + ba.y);
+                        w[2 * j] = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(__uint_as_float(r0[4 * j + 2]) + ba.z, __uint_as_float(r0[4 * j + 3]) + ba.w);
+                        w[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(__uint_as_float(r1[4 * j]) + bb.x, __uint_as_float(r1[4 * j + 1]) + bb.y);
+                        w[16 + 2 * j] = *reinterpret_cast<uint32_t*>(&h);
+                        h = __floats2bfloat162_rn(__uint_as_float(r1[4 * j + 2]) + bb.z, __uint_as_float(r1[4 * j + 3]) + bb.w);
+                        w[16 + 2 * j + 1] = *reinterpret_cast<uint32_t*>(&h);
                     }
-                    __nv_bfloat162 ha = __floats2bfloat162_rn(a0, a1), hb = __floats2bfloat162_rn(b0, b1);
-                    w[j] = *reinterpret_cast<uint32_t*>(&ha);
-                    w[16 + j] = *reinterpret_cast<uint32_t*>(&hb);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat162 ha = __floats2bfloat162_rn(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+                        __nv_bfloat162 hb = __floats2bfloat162_rn(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+                        w[j] = *reinterpret_cast<uint32_t*>(&ha);
+                        w[16 + j] = *reinterpret_cast<uint32_t*>(&hb);
+                    }
                 }
                 // the staging tile we are about to overwrite: its previous bulk store must have finished READING it
                 if (leader) bulk_wait_read<1>();
@@ -228,30 +255,54 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     st_shared_v4(rbase + ((((uint32_t)ch) ^ swz) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
                 fence_proxy_async_smem();
                 if (stats) {
-                    // column sums over THIS warp's 32 rows (written by this warp: a warp-level sync suffices).  Lane l
-                    // owns columns c0 + 2l, c0 + 2l + 1: one 128-byte row per step, conflict-free.
+                    // Column sums over THIS warp's 32 rows (written by this warp: a warp-level sync suffices).  Lane l owns
+                    // columns c0 + 2l, c0 + 2l + 1: one 128-byte row per load, conflict-free.  All 32 loads are issued
+                    // before the first use (a dependent load -> add chain per row is pure latency with 4 warps per SM).
                     __syncwarp();
                     const int cn = c0 + 2 * lane;
                     const bool cvalid = cn < p.N;
                     const uint32_t jchunk = (uint32_t)lane >> 2, wsel = ((uint32_t)lane & 3u) << 2;
-                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                    const unsigned myb = p.st.mask_mode == MOPOE_MASK_BC ? flat / (unsigned)p.st.rows_per_b : flat;
-#pragma unroll 4
-                    for (int i = 0; i < 32; ++i) {
-                        const unsigned rb = __shfl_sync(0xffffffffu, myb, i);
-                        if (!((vmask >> i) & 1u)) continue;
-                        const uint32_t rr = (uint32_t)(q * 32 + i);
-                        const uint32_t word = ld_shared_b32(stg + rr * 128u + ((jchunk ^ (rr & 7u)) << 4) + wsel);
-                        float x0 = __uint_as_float(word << 16), x1 = __uint_as_float(word & 0xffff0000u);
-                        if (p.st.mask_mode != MOPOE_MASK_NONE && cvalid) {
-                            const unsigned short mk = *reinterpret_cast<const unsigned short*>(p.st.mask + (size_t)rb * p.N + cn);
-                            x0 = (mk & 0xffu) ? 2.f * x0 : 0.f;
-                            x1 = (mk & 0xff00u) ? 2.f * x1 : 0.f;
+                    const uint32_t lbase = stg + (uint32_t)(q * 32) * 128u + wsel;
+                    // dropout mask between this GEMM and the BatchNorm: per row (elementwise mask, or a Dropout2d mask when
+                    // the warp's rows span several samples) — global loads issued ahead of the shared-memory reads
+                    const bool row_masks = p.st.mask_mode == MOPOE_MASK_ELEM || (p.st.mask_mode == MOPOE_MASK_BC && key_lo != key_hi);
+                    unsigned short mk[32];
+                    if (row_masks) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const unsigned key = __shfl_sync(0xffffffffu, mykey, i);
+                            mk[i] = (cvalid && ((vmask >> i) & 1u))
+                                        ? *reinterpret_cast<const unsigned short*>(p.st.mask + (size_t)key * p.N + cn) : (unsigned short)0;
                         }
-                        s0 += x0;
-                        s1 += x1;
-                        q0 = fmaf(x0, x0, q0);
-                        q1 = fmaf(x1, x1, q1);
+                    }
+                    uint32_t wv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) wv[i] = ld_shared_b32(lbase + (uint32_t)i * 128u + ((jchunk ^ (uint32_t)(i & 7)) << 4));
+                    float sa0 = 0.f, sa1 = 0.f, qa0 = 0.f, qa1 = 0.f, sb0 = 0.f, sb1 = 0.f, qb0 = 0.f, qb1 = 0.f;
+                    if (row_masks) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float x0 = __uint_as_float(wv[i] << 16), x1 = __uint_as_float(wv[i] & 0xffff0000u);
+                            x0 = (mk[i] & 0xffu) ? 2.f * x0 : 0.f;
+                            x1 = (mk[i] & 0xff00u) ? 2.f * x1 : 0.f;
+                            if (i & 1) { sb0 += x0; sb1 += x1; qb0 = fmaf(x0, x0, qb0); qb1 = fmaf(x1, x1, qb1); }
+                            else { sa0 += x0; sa1 += x1; qa0 = fmaf(x0, x0, qa0); qa1 = fmaf(x1, x1, qa1); }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            float x0 = __uint_as_float(wv[i] << 16), x1 = __uint_as_float(wv[i] & 0xffff0000u);
+                            if (vmask != 0xffffffffu && !((vmask >> i) & 1u)) x0 = x1 = 0.f;       // tile overhang rows
+                            if (i & 1) { sb0 += x0; sb1 += x1; qb0 = fmaf(x0, x0, qb0); qb1 = fmaf(x1, x1, qb1); }
+                            else { sa0 += x0; sa1 += x1; qa0 = fmaf(x0, x0, qa0); qa1 = fmaf(x1, x1, qa1); }
+                        }
+                    }
+                    float s0 = sa0 + sb0, s1 = sa1 + sb1, q0 = qa0 + qb0, q1 = qa1 + qb1;
+                    if (warp_mask) {
+                        const unsigned mk = (unsigned)(mkw >> (16 * (g & 3))) & 0xffffu;
+                        const float f0 = (mk & 0xffu) ? 2.f : 0.f, f1 = (mk & 0xff00u) ? 2.f : 0.f;
+                        s0 *= f0; q0 *= f0 * f0;
+                        s1 *= f1; q1 *= f1 * f1;
                     }
                     if (cvalid) {
                         float* a = sacc + (size_t)(q * 2) * p.nacc + cn;           // exclusive owner of these entries
@@ -346,18 +397,6 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
-// experimental 256 x BN tile variant (gemm_tc_persist2.cu): only with MOPOE_GEMM_BM256=1
-int mopoe_conv_gemm_tc_batched_bm256(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
-                                     const mopoe_rows_t* D, void* stream);
-static int bm256_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("MOPOE_GEMM_BM256");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v;
-}
-
 static bool g_persist_attr_set = false;
 static int g_num_sms = 0;
 
@@ -388,18 +427,6 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     MOPOE_REQUIRE(nprob >= 1 && nprob <= TCP_MAXP, "conv_gemm_tc_batched: nprob=%d", nprob);
     if (!mopoe_tc_init_state()) MOPOE_FAIL("conv_gemm_tc_batched: tcgen05 path unavailable on this device");
     if (stats && stats->nchunk_out) *stats->nchunk_out = 0;
-    if (bm256_enabled() && !stats) {
-        bool same = true;
-        for (int i = 1; i < nprob; ++i)
-            same = same && A[i].E0 == A[0].E0 && A[i].E1 == A[0].E1 && A[i].E2 == A[0].E2 && A[i].R == A[0].R &&
-                   A[i].KW == A[0].KW && D[i].N == D[0].N && D[i].s0 == D[0].s0 && D[i].s1 == D[0].s1 &&
-                   D[i].s2 == D[0].s2 && D[i].d == D[0].d && D[i].d_dtype == D[0].d_dtype;
-        if (same) {
-            const int rc = mopoe_conv_gemm_tc_batched_bm256(nprob, A, Wp, bias, D, stream);
-            if (rc == 2) return 0;
-            if (rc == 1) return 1;
-        }
-    }
     TcPersistParams p;
     p.E0 = A[0].E0; p.E1 = A[0].E1; p.E2 = A[0].E2; p.R = A[0].R; p.KW = A[0].KW; p.N = D[0].N;
     for (int i = 1; i < nprob; ++i) {
@@ -455,7 +482,7 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     }
     const int stage_bytes = 128 * 128 + p.BN * 128;
     const int hdr_bytes = 16 * 8 + 48 + 64;
-    const int extra = tma_epi ? 2 * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) : 0;
+    const int extra = tma_epi ? 2 * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) + (bias ? 4 * p.nacc : 0) : 0;
     int stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes - extra) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2 && tma_epi) {                  // (never with the model's shapes) fall back to the register epilogue

@@ -86,68 +86,127 @@ __global__ void __launch_bounds__(256) pack_inner_a_kernel(const float* __restri
     pack_inner_a_tile<TD>(s, blockIdx.x, blockIdx.y, W, A, B, KH, KW, form, dst);
 }
 
-// Every re-layout of a training step in ONE launch: block -> (job, tile) through the jobs' tile prefix (binary search).
-// A step re-packs ~240 weight tensors after the optimizer update; as separate launches they cost ~1.8 ms of launch
-// latency for ~0.9 GB of traffic.
-constexpr int PACK_TPB = 8;      // consecutive tiles per block: one job look-up (a chain of L2 round trips) per 8 tiles
+// Every re-layout of a training step in ONE launch.  Thread-per-item, no shared memory, no barriers: an item is
+//   conv / mat  (form 0, 3): (a, b-octet, tap)      -> 8 scalar loads W[a][b0..b0+7][t]  -> ONE 16-byte store dst[a][t][b0..]
+//   phase / full / matT (1, 2, 4): (a-hexadecad, b, tap) -> 16 scalar loads W[a0..a0+15][b][t] -> 32 contiguous bytes of dst
+// with the tap index fastest across the lanes, so that every load instruction of a warp reads whole 32-byte sectors
+// (phase / full: 128 contiguous bytes) and every store writes whole sectors.  All 8 / 16 loads of a thread are
+// independent: the kernel is limited by bytes in flight, not by a load -> barrier -> store round trip per 4-KB tile as
+// the shared-memory version was (1.58 ms per step for 1.2 GB = 0.12 of the HBM roofline).
+constexpr int PACK_ITEMS_PER_TILE = 256;
+
 template <typename TD>
-__global__ void __launch_bounds__(256) pack_batched_kernel(const mopoe_pack_job_t* __restrict__ jobs, int njobs, int total_tiles) {
-    __shared__ float s[LT][MAXT + 1];
+__device__ __forceinline__ void store8(TD* p, const float (&v)[8]) {
+    if constexpr (sizeof(TD) == 2) {
+        uint4 t;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = t;
+    } else {
+        reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+template <typename TD>
+__device__ __forceinline__ void pack_item(const mopoe_pack_job_t& j, long long item) {
+    const int A = j.A, B = j.B, T = j.KH * j.KW;
+    const float* __restrict__ W = reinterpret_cast<const float*>(j.W);
+    if (j.form == 0 || j.form == 3) {
+        const int OB = (j.bpad + 7) / 8;
+        const long long total = (long long)A * OB * T;
+        if (item >= total) return;
+        const int t = (int)(item % T);
+        const long long q = item / T;
+        const int ob = (int)(q % OB), a = (int)(q / OB);
+        const int b0 = ob * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (b0 + i < B) ? __ldg(W + ((long long)a * B + b0 + i) * T + t) : 0.f;
+        TD* d = reinterpret_cast<TD*>(j.dst[0]) + ((long long)a * T + t) * j.bpad + b0;
+        if (b0 + 8 <= j.bpad && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+            store8<TD>(d, v);
+        } else {
+            for (int i = 0; i < 8 && b0 + i < j.bpad; ++i) put(d + i, v[i]);
+        }
+        return;
+    }
+    const int OA = (A + 15) / 16;
+    const long long total = (long long)OA * B * T;
+    if (item >= total) return;
+    const int t = (int)(item % T);
+    const long long q = item / T;
+    const int b = (int)(q % B), a0 = (int)(q / B) * 16;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (a0 + i < A) ? __ldg(W + ((long long)(a0 + i) * B + b) * T + t) : 0.f;
+    TD* d;
+    if (j.form == 1) {
+        // tap (ky,kx) belongs to phase (py,px) at window slot (r,kxi):  KT[p][slot] = tap,  KT = ((3,1),(2,0))
+        const int ky = t / j.KW, kx = t - ky * j.KW;
+        const int px = (kx == 3 || kx == 1) ? 0 : 1, kxi = (kx == 3 || kx == 2) ? 0 : 1;
+        int ph = px, slot = kxi, nslot = 2;
+        if (j.KH > 1) {
+            const int py = (ky == 3 || ky == 1) ? 0 : 1, r = (ky == 3 || ky == 2) ? 0 : 1;
+            ph = py * 2 + px;
+            slot = r * 2 + kxi;
+            nslot = 4;
+        }
+        d = reinterpret_cast<TD*>(j.dst[ph]) + ((long long)b * nslot + slot) * A + a0;
+    } else {
+        d = reinterpret_cast<TD*>(j.dst[0]) + ((long long)t * B + b) * A + a0;
+    }
+    if (a0 + 16 <= A && (reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        float lo[8], hi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { lo[i] = v[i]; hi[i] = v[8 + i]; }
+        store8<TD>(d, lo);
+        store8<TD>(d + 8, hi);
+    } else {
+        for (int i = 0; i < 16 && a0 + i < A; ++i) put(d + i, v[i]);
+    }
+}
+
+template <typename TD>
+__global__ void __launch_bounds__(PACK_ITEMS_PER_TILE) pack_batched_kernel(const mopoe_pack_job_t* __restrict__ jobs, int njobs,
+                                                                           int total_tiles) {
     __shared__ mopoe_pack_job_t sj;
-    __shared__ int s_idx;
-    const int first = (int)blockIdx.x * PACK_TPB;
-    if (threadIdx.x == 0) {
+    const int tile = (int)blockIdx.x;
+    if (threadIdx.x == 0) {                       // jobs are sorted by their first tile
         int lo = 0, hi = njobs - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (jobs[mid].tile0 <= first) lo = mid; else hi = mid - 1;
+            if (jobs[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
         }
-        s_idx = lo;
         sj = jobs[lo];
     }
     __syncthreads();
-    for (int k = 0; k < PACK_TPB; ++k) {
-        const int tile = first + k;
-        if (tile >= total_tiles) break;
-        // jobs are sorted by tile0: crossing into the next job is a single step
-        const int next0 = s_idx + 1 < njobs ? jobs[s_idx + 1].tile0 : total_tiles;
-        if (tile >= next0) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                s_idx += 1;
-                sj = jobs[s_idx];
-            }
-            __syncthreads();
-        }
-        const int local = tile - sj.tile0, bx = local % sj.nx, by = local / sj.nx;
-        const int T = sj.KH * sj.KW;
-        if (sj.form == 0 || sj.form == 3) {
-            pack_conv_tile<TD>(s, bx, by, sj.W, sj.A, sj.B, T, sj.bpad, reinterpret_cast<TD*>(sj.dst[0]));
-        } else {
-            PackDst d;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d.p[i] = sj.dst[i];
-            pack_inner_a_tile<TD>(s, bx, by, sj.W, sj.A, sj.B, sj.KH, sj.KW, sj.form == 1 ? 1 : 2, d);
-        }
-        __syncthreads();                 // the tile buffer is reused by the next iteration
-    }
+    pack_item<TD>(sj, (long long)(tile - sj.tile0) * PACK_ITEMS_PER_TILE + threadIdx.x);
 }
-extern "C" int mopoe_pack_job_tiles(int A, int B, int KH, int KW, int form, int bpad, int* nx) {
+template <typename TD>
+__global__ void __launch_bounds__(PACK_ITEMS_PER_TILE) pack_single_kernel(const mopoe_pack_job_t j) {
+    pack_item<TD>(j, (long long)blockIdx.x * PACK_ITEMS_PER_TILE + threadIdx.x);
+}
+static long long pack_job_items(int A, int B, int KH, int KW, int form, int bpad) {
+    const long long T = (long long)KH * KW;
     if (form == 0 || form == 3) {
         if (bpad < B) bpad = B;
-        *nx = (bpad + LT - 1) / LT;
-        return *nx * A;
+        return (long long)A * ((bpad + 7) / 8) * T;
     }
-    *nx = (A + LT - 1) / LT;
-    return *nx * B;
+    return (long long)((A + 15) / 16) * B * T;
+}
+extern "C" int mopoe_pack_job_tiles(int A, int B, int KH, int KW, int form, int bpad, int* nx) {
+    if (nx) *nx = 0;                              // (tiles are flat runs of 256 items; kept for ABI compatibility)
+    return (int)((pack_job_items(A, B, KH, KW, form, bpad) + PACK_ITEMS_PER_TILE - 1) / PACK_ITEMS_PER_TILE);
 }
 extern "C" int mopoe_pack_weights_batched(const mopoe_pack_job_t* jobs_dev, int njobs, int total_tiles, int dst_dtype,
                                           void* stream) {
     if (njobs <= 0 || total_tiles <= 0) return 0;
     MOPOE_REQUIRE(jobs_dev != nullptr, "pack_weights_batched: null job table");
     cudaStream_t st = (cudaStream_t)stream;
-    if (dst_dtype == MOPOE_F32) pack_batched_kernel<float><<<(unsigned)((total_tiles + PACK_TPB - 1) / PACK_TPB), 256, 0, st>>>(jobs_dev, njobs, total_tiles);
-    else pack_batched_kernel<bf16><<<(unsigned)((total_tiles + PACK_TPB - 1) / PACK_TPB), 256, 0, st>>>(jobs_dev, njobs, total_tiles);
+    if (dst_dtype == MOPOE_F32) pack_batched_kernel<float><<<(unsigned)total_tiles, PACK_ITEMS_PER_TILE, 0, st>>>(jobs_dev, njobs, total_tiles);
+    else pack_batched_kernel<bf16><<<(unsigned)total_tiles, PACK_ITEMS_PER_TILE, 0, st>>>(jobs_dev, njobs, total_tiles);
     MOPOE_CHECK_LAUNCH("pack_weights_batched");
     return 0;
 }
@@ -157,24 +216,21 @@ extern "C" int mopoe_pack_weight_tiled(const float* W, int A, int B, int KH, int
                                        int dst_dtype, void* stream) {
     const int T = KH * KW;
     MOPOE_REQUIRE(T >= 1 && T <= MAXT, "pack_weight: taps=%d", T);
+    MOPOE_REQUIRE(form >= 0 && form <= 4, "pack_weight: bad form %d", form);
+    MOPOE_REQUIRE(form != 1 || KW == 4, "pack_weight: phase form needs a 4-tap kernel");
+    MOPOE_REQUIRE(!(form == 3 || form == 4) || T == 1, "pack_weight: mat forms need a 1x1 kernel");
+    mopoe_pack_job_t j = {};
+    j.W = W;
+    const int n = form == 1 ? (KH > 1 ? 4 : 2) : 1;
+    for (int i = 0; i < n; ++i) j.dst[i] = dsts[i];
+    j.A = A; j.B = B; j.KH = KH; j.KW = KW;
+    j.form = form == 4 ? 2 : form;                 // matT = full-form with one tap
+    j.bpad = bpad < B ? B : bpad;
+    const long long items = pack_job_items(A, B, KH, KW, form, bpad);
+    const unsigned grid = (unsigned)((items + PACK_ITEMS_PER_TILE - 1) / PACK_ITEMS_PER_TILE);
     cudaStream_t st = (cudaStream_t)stream;
-    if (form == 0 || form == 3) {
-        if (bpad < B) bpad = B;
-        dim3 grid((bpad + LT - 1) / LT, A);
-        if (dst_dtype == MOPOE_F32) pack_conv_kernel<float><<<grid, 256, 0, st>>>(W, A, B, T, bpad, (float*)dsts[0]);
-        else pack_conv_kernel<bf16><<<grid, 256, 0, st>>>(W, A, B, T, bpad, (bf16*)dsts[0]);
-    } else if (form == 1 || form == 2 || form == 4) {
-        MOPOE_REQUIRE(form != 1 || KW == 4, "pack_weight: phase form needs a 4-tap kernel");
-        PackDst d = {};
-        const int n = form == 1 ? (KH > 1 ? 4 : 2) : 1;
-        for (int i = 0; i < n; ++i) d.p[i] = dsts[i];
-        dim3 grid((A + LT - 1) / LT, B);
-        const int f = form == 1 ? 1 : 2;
-        if (dst_dtype == MOPOE_F32) pack_inner_a_kernel<float><<<grid, 256, 0, st>>>(W, A, B, KH, KW, f, d);
-        else pack_inner_a_kernel<bf16><<<grid, 256, 0, st>>>(W, A, B, KH, KW, f, d);
-    } else {
-        MOPOE_FAIL("pack_weight: bad form %d", form);
-    }
+    if (dst_dtype == MOPOE_F32) pack_single_kernel<float><<<grid, PACK_ITEMS_PER_TILE, 0, st>>>(j);
+    else pack_single_kernel<bf16><<<grid, PACK_ITEMS_PER_TILE, 0, st>>>(j);
     MOPOE_CHECK_LAUNCH("pack_weight_tiled");
     return 0;
 }

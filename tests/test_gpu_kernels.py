@@ -330,3 +330,49 @@ def test_full_size_selection_ranges(B, S):
     ends = selection_ends(B, uniform_weights(S))
     assert ends == O.selection_bounds(B, [1.0 / S] * S)[1]
     assert ends[:-1] == [(k + 1) * (B // S) for k in range(S - 1)] and ends[-1] == B
+
+
+@pytest.mark.parametrize('dtype', [torch.bfloat16, torch.float32])
+def test_weight_relayout_kernels_match_the_index_maps(dtype):
+    """mopoe_pack_weight_tiled (per slot) and mopoe_pack_weights_batched (all slots of a step in one launch) against the
+    torch re-layouts of engine.py (conv_form / phase_form / full_form, themselves checked against conv identities on the
+    CPU): bit-exact, for every weight geometry of the model incl. the channel-padded text stem and odd vocabulary sizes."""
+    from mopoe_mimic_b200.engine import Engine, conv_form, full_form, phase_form
+    eng = Engine('cuda', dtype)
+    g = torch.Generator().manual_seed(5)
+    cases = [((256, 128, 4, 4), 'conv', None), ((128, 256, 4, 4), 'phase', None), ((640, 512, 4, 4), 'full', None),
+             ((128, 71, 4), 'conv', 80), ((128, 71, 4), 'phase', None), ((384, 256, 4), 'conv', None),
+             ((256, 384, 4), 'phase', None), ((640, 640, 4), 'full', None), ((128, 128, 1, 1), 'mat', None),
+             ((128, 128, 1, 1), 'matT', None), ((304, 128), 'mat', None), ((2900, 16), 'matT', None), ((40, 24, 4, 4), 'full', None),
+             ((72, 24, 4), 'phase', None)]
+    weights = [torch.randn(shape, generator=g).cuda() for shape, _, _ in cases]
+
+    def reference(W, form, bpad):
+        if form == 'conv':
+            if bpad:
+                Wp = torch.zeros(W.shape[0], bpad, *W.shape[2:], device=W.device)
+                Wp[:, :W.shape[1]] = W
+                W = Wp
+            return [conv_form(W, dtype)]
+        if form == 'phase':
+            return phase_form(W, dtype)
+        if form == 'full':
+            return [full_form(W, dtype)]
+        W2 = W.reshape(W.shape[0], W.shape[1])
+        return [(W2 if form == 'mat' else W2.t()).to(dtype).contiguous()]
+
+    def check(tag):
+        for W, (shape, form, bpad) in zip(weights, cases):
+            got = eng.packed(W, form, bpad=bpad)
+            got = list(got) if isinstance(got, (list, tuple)) else [got]
+            ref = reference(W, form, bpad)
+            assert len(got) == len(ref)
+            for a, b in zip(got, ref):
+                assert a.shape == b.shape and torch.equal(a, b), (tag, shape, form)
+    check('per-slot')                       # first use packs slot by slot (mopoe_pack_weight_tiled)
+    for W in weights:                       # the optimizer changed the weights behind torch's back ...
+        W.mul_(1.5).add_(0.25)
+    eng.invalidate_packs()
+    eng.begin_step()                        # ... one batched launch re-packs every known slot
+    torch.cuda.synchronize()
+    check('batched')
