@@ -57,6 +57,9 @@ def parse():
     ap.add_argument('--text-wire', default='onehot', choices=['onehot', 'uint8'],
                     help='host format of the char text in the e2e leg: the reference\'s fp32 one-hot rows [B,1024,71] '
                          '(default) or one byte per token, expanded on the device (SURVEY N3)')
+    ap.add_argument('--image-wire', default='fp32', choices=['fp32', 'uint8'],
+                    help='host format of the images in the e2e leg: the reference\'s fp32 in [0,1] (default) or 8-bit pixels, '
+                         'ToTensor() evaluated on the device (SURVEY N3)')
     ap.add_argument('--config', default='2', choices=sorted(CONFIGS), help='BASELINE.json configuration (default 2)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--cpu-batch', type=int, default=16)
@@ -272,6 +275,13 @@ def main():
         if args.no_graph:
             raise SystemExit('--text-wire uint8 needs the graphed step (the expansion kernel fills its static input)')
         host['text'] = host['text'].argmax(-1).to(torch.uint8).pin_memory()
+    if args.image_wire == 'uint8':
+        if args.no_graph:
+            raise SystemExit('--image-wire uint8 needs the graphed step (the expansion kernel fills its static input)')
+        for k in ('PA', 'Lateral'):
+            if k in host:
+                host[k] = (host[k] * 255.0).round().to(torch.uint8).pin_memory()
+                resident[k] = (host[k].float() / 255.0).to(dev)         # the same pixel values the device expansion yields
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
 
     ar = FlatGradAllReduce() if (world > 1 and not peer) else None      # bucketed NCCL all-reduce of the flat gradients
@@ -483,7 +493,7 @@ def main():
                 'data': 'synthetic',
                 'config': {'workload': cfg['workload'], 'per_gpu_batch': B, 'global_batch': B * world,
                            'parallelism': 'dp%d' % world + ('' if world == 1 else (' peer-memory fused exchange' if peer else ' nccl all-reduce')), 'cuda_graph': not args.no_graph, 'lr': args.lr,
-                           'branch_streams': os.environ.get('MOPOE_BRANCH_STREAMS', '1') != '0', 'text_wire': args.text_wire, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
+                           'branch_streams': os.environ.get('MOPOE_BRANCH_STREAMS', '1') != '0', 'text_wire': args.text_wire, 'image_wire': args.image_wire, 'l2': 'inputs+activations per step >> 126 MB L2 (no flush needed)'},
                 'clocks': sampler.summary(),
                 'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s',
                         'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h},

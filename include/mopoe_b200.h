@@ -296,6 +296,9 @@ int mopoe_onehot(const float* idx, int64_t rows, int V, int Vp, void* out, int o
 /* uint8 character indices [rows] -> fp32 one-hot rows [rows, V] (V <= 256): the device side of the 1-byte-per-token wire
  * format; the reference builds these rows on the host (dataio/MimicDataset.py:92-96, utils/text.py:13-34). */
 int mopoe_onehot_u8(const uint8_t* idx, int64_t rows, int V, float* out, void* stream);
+/* 8-bit images on the wire: dst[i] = float(src[i]) / 255 — torchvision ToTensor(), which the reference's loader
+ * applies on the host (dataio/MimicDataset.py), evaluated on the device: 1 byte per pixel crosses PCIe instead of 4. */
+int mopoe_u8_to_unit(const uint8_t* src, int64_t n, float* dst, void* stream);
 
 /* All weight re-layouts of a step in ONE launch.  jobs_dev: DEVICE array of njobs descriptors (same meaning as the
  * arguments of mopoe_pack_weight_tiled; form 1 fills dst[0..3] / dst[0..1], the others dst[0]); tile0 = index of the

@@ -1104,6 +1104,33 @@ extern "C" int mopoe_onehot_u8(const uint8_t* idx, int64_t rows, int V, float* o
     return 0;
 }
 
+// 8-bit images on the wire: out = float(u8) / 255 — exactly torchvision's ToTensor() (the reference's loader,
+// dataio/MimicDataset.py) evaluated on the device, so the host ships 1 byte per pixel instead of 4
+__global__ void __launch_bounds__(256) u8_to_unit_kernel(const uint8_t* __restrict__ src, long long n, float* __restrict__ dst) {
+    const long long n16 = n >> 4;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n16; i += (long long)gridDim.x * 256) {
+        const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + i);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            reinterpret_cast<float4*>(dst)[i * 4 + k] =
+                make_float4((float)(w[k] & 0xffu) / 255.f, (float)((w[k] >> 8) & 0xffu) / 255.f,
+                            (float)((w[k] >> 16) & 0xffu) / 255.f, (float)(w[k] >> 24) / 255.f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (long long i = n16 << 4; i < n; ++i) dst[i] = (float)src[i] / 255.f;
+}
+extern "C" int mopoe_u8_to_unit(const uint8_t* src, int64_t n, float* dst, void* stream) {
+    if (n <= 0) return 0;
+    MOPOE_REQUIRE((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "u8_to_unit: unaligned buffers");
+    long long blocks = ceil_div64(n >> 4, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    u8_to_unit_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, n, dst);
+    MOPOE_CHECK_LAUNCH("u8_to_unit");
+    return 0;
+}
+
 // ---- flat Adam -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n4,

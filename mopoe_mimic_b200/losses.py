@@ -85,28 +85,37 @@ def calc_style_kld(exp, klds):
 
 
 def calc_elbo(exp, modality, recs, klds):
-    """utils.calc_elbo (utils/utils.py:105-127) without style terms (factorized_representation is False)."""
+    """utils.calc_elbo (utils/utils.py:105-127): klds = {'content': ..., 'style': {m: ...}}"""
     flags = exp.flags
+    s_weights = exp.style_weights
     kld_content = klds['content']
     if modality == 'joint':
+        w_style_kld = 0.0
         rec_error = 0.0
         for m_key in exp.modalities:
-            rec_error += exp.rec_weights[m_key] * recs[m_key]
+            w_style_kld = w_style_kld + s_weights[m_key] * klds['style'][m_key]
+            rec_error = rec_error + exp.rec_weights[m_key] * recs[m_key]
+        kld_style = w_style_kld
     else:
+        kld_style = s_weights[modality] * klds['style'][modality]
         rec_error = 1.0 * recs[modality]
-    div = flags.beta_content * kld_content + flags.beta_style * 0.0
+    div = flags.beta_content * kld_content + flags.beta_style * kld_style
     return rec_error + flags.beta * div
 
 
 def calc_poe_loss(exp, mods, group_divergence, klds, klds_style, batch_d, mm_vae, log_probs):
-    """losses.py:54-77: one unimodal forward pass per modality + the joint ELBO."""
+    """losses.py:54-77: one unimodal forward pass per modality + the joint ELBO.  With a factorized representation the
+    style KLs of the JOINT pass enter every ELBO (the unimodal passes only contribute their reconstruction terms)."""
     klds_joint = {'content': group_divergence, 'style': {}}
+    factorized = bool(getattr(exp.flags, 'factorized_representation', False))
     elbos = {}
     for m_key in mods.keys():
         mod = mods[m_key]
+        kld_style_m = klds_style[m_key + '_style'] if factorized else 0.0
+        klds_joint['style'][m_key] = kld_style_m
         r_mod = mm_vae({m_key: batch_d[m_key]})
         log_prob_mod = -mod.calc_log_prob(r_mod['rec'][m_key], batch_d[m_key], exp.flags.batch_size)
-        klds_mod = {'content': klds[m_key], 'style': {m_key: 0.0}}
+        klds_mod = {'content': klds[m_key], 'style': {m_key: kld_style_m}}
         elbos[m_key] = calc_elbo(exp, m_key, {m_key: log_prob_mod}, klds_mod)
     elbos['joint'] = calc_elbo(exp, 'joint', log_probs, klds_joint)
     return sum(elbos.values())

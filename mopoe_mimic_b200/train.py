@@ -164,9 +164,7 @@ def basic_routine_epoch(exp, batch):
         total_loss = calc_joint_elbo_loss(exp, klds_style, group_divergence, flags.beta_style, flags.beta_content,
                                           weighted_log_prob, flags.beta)
     elif flags.modality_poe:
-        if klds_style is not None:
-            raise NotImplementedError('poe with a factorized representation is not built (SURVEY.md N4)')
-        total_loss = calc_poe_loss(exp, exp.modalities, group_divergence, klds, None, batch_d, mm_vae, log_probs)
+        total_loss = calc_poe_loss(exp, exp.modalities, group_divergence, klds, klds_style, batch_d, mm_vae, log_probs)
     else:
         raise ValueError('no fusion method selected')
     return {'results': results, 'log_probs': log_probs, 'total_loss': total_loss, 'klds': klds}
@@ -250,44 +248,53 @@ class GraphedTrainStep:
         self.keys = (['total_loss', 'joint_divergence'] + ['kld.' + k for k in out['klds']]
                      + ['log_prob.' + k for k in out['log_probs']])
 
-    def _is_wire_text(self, batch):
-        """char text shipped as uint8 indices [B, L] instead of fp32 one-hot rows [B, L, 71]"""
-        t = batch.get('text')
-        return t is not None and t.dtype == torch.uint8 and t.dim() == 2 and self.static['text'].dim() == 3
+    def _wire(self, batch, k):
+        """compact wire format of input k, expanded on the device into the fp32 static input the model reads:
+        'text_u8'  char text as one byte per token [B, L]   (instead of fp32 one-hot rows [B, L, 71]: 1 KB vs 291 KB / report)
+        'img_u8'   8-bit image [B, 1, px, px]                (instead of fp32 in [0, 1]: ToTensor() runs on the device)"""
+        t, st = batch[k], self.static[k]
+        if t.dtype != torch.uint8:
+            return None
+        if k == 'text' and t.dim() == 2 and st.dim() == 3:
+            return 'text_u8'
+        if k != 'text' and tuple(t.shape) == tuple(st.shape):
+            return 'img_u8'
+        raise ValueError('uint8 input %r of shape %s does not match the model input %s' % (k, tuple(t.shape), tuple(st.shape)))
 
-    def _expand_text(self, idx_dev):
-        st = self.static['text']
-        L.call('mopoe_onehot_u8', L.ptr(idx_dev), idx_dev.numel(), st.shape[-1], L.ptr(st), L.stream_ptr())
+    def _expand(self, k, kind, src_dev):
+        st = self.static[k]
+        if kind == 'text_u8':
+            L.call('mopoe_onehot_u8', L.ptr(src_dev), src_dev.numel(), st.shape[-1], L.ptr(st), L.stream_ptr())
+        else:
+            L.call('mopoe_u8_to_unit', L.ptr(src_dev), src_dev.numel(), L.ptr(st), L.stream_ptr())
 
     def _stage_host_batch(self, batch):
         """Host (pinned) batch -> one of two device staging sets on a COPY stream, so the H2D transfer of step i+1
         runs under step i's graph instead of in front of its own (the loader side of run_epochs.py:61-62)."""
-        wire = self._is_wire_text(batch)
+        kinds = {k: self._wire(batch, k) for k in self.static}
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
             self._staging = [{k: torch.empty_like(t) for k, t in self.static.items()} for _ in range(2)]
             self._staged = [torch.cuda.Event(), torch.cuda.Event()]
             self._consumed = [None, None]
             self._slot = 0
-        if wire and 'text_u8' not in self._staging[0]:
-            for sset in self._staging:
-                sset['text_u8'] = torch.empty(self.static['text'].shape[:2], dtype=torch.uint8, device=self.static['text'].device)
+        for k, kind in kinds.items():
+            if kind is not None and (k, kind) not in self._staging[0]:
+                for sset in self._staging:
+                    sset[(k, kind)] = torch.empty(batch[k].shape, dtype=torch.uint8, device=self.static[k].device)
         i = self._slot
         self._slot ^= 1
         cs, cur = self._copy_stream, torch.cuda.current_stream()
         if self._consumed[i] is not None:
             cs.wait_event(self._consumed[i])          # the step that last read this staging set has copied it out
         with torch.cuda.stream(cs):
-            for k in self.static:
-                if k == 'text' and wire:
-                    self._staging[i]['text_u8'].copy_(batch['text'], non_blocking=True)
-                else:
-                    self._staging[i][k].copy_(batch[k], non_blocking=True)
+            for k, kind in kinds.items():
+                self._staging[i][k if kind is None else (k, kind)].copy_(batch[k], non_blocking=True)
             self._staged[i].record(cs)
         cur.wait_event(self._staged[i])
         for k, t in self.static.items():
-            if k == 'text' and wire:
-                self._expand_text(self._staging[i]['text_u8'])
+            if kinds[k] is not None:
+                self._expand(k, kinds[k], self._staging[i][(k, kinds[k])])
             else:
                 t.copy_(self._staging[i][k], non_blocking=True)
         if self._consumed[i] is None:
@@ -298,10 +305,10 @@ class GraphedTrainStep:
         if all(not batch[k].is_cuda for k in self.static):
             self._stage_host_batch(batch)
         else:
-            wire = self._is_wire_text(batch)
             for k, t in self.static.items():
-                if k == 'text' and wire:
-                    self._expand_text(batch['text'].contiguous())
+                kind = self._wire(batch, k)
+                if kind is not None:
+                    self._expand(k, kind, batch[k].contiguous())
                 else:
                     t.copy_(batch[k], non_blocking=True)
         self.graph.replay()

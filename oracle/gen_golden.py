@@ -47,7 +47,8 @@ def import_reference():
     return SimpleNamespace(**locals())
 
 
-CURRENT = {'masks': None, 'eps': None, 'calls': 0, 'noise': None, 'eps_style': None, 'style_calls': 0}
+CURRENT = {'masks': None, 'eps': None, 'calls': 0, 'noise': None, 'eps_style': None, 'style_calls': 0,
+           'eps_style_list': None, 'eps_style_pass': None, 'style_mod': None}
 
 
 def ref_flags(fl):
@@ -93,12 +94,20 @@ def build_reference_model(R, fl, state):
                 setattr(self, O.DEC_NAME[m], mod.decoder)
 
         def encode(self, input_batch):
-            return {m: list(getattr(self, O.ENC_NAME[m])(input_batch[m])[:2]) for m in self.modalities
-                    if m in input_batch}
+            lat = {}
+            for m in self.modalities:           # VAEtrimodalMimic.encode:64-93: content first, style after
+                if m in input_batch:
+                    out = getattr(self, O.ENC_NAME[m])(input_batch[m])
+                    lat[m] = list(out[:2])
+                    if len(out) == 4:
+                        lat[m + '_style'] = list(out[2:])
+            return lat
 
         def forward(self, input_batch):
             noise = CURRENT['noise'][CURRENT['calls']]
             CURRENT['masks'], CURRENT['eps'] = noise
+            if CURRENT['eps_style_list'] is not None:
+                CURRENT['eps_style_pass'] = CURRENT['eps_style_list'][CURRENT['calls']]
             CURRENT['calls'] += 1
             latents = self.inference(input_batch)
             results = {'latents': latents}
@@ -110,10 +119,15 @@ def build_reference_model(R, fl, state):
             for m, mod in self.modalities.items():
                 if m in input_batch:
                     dec = getattr(self, O.DEC_NAME[m])
+                    s_emb = None
+                    if self.flags.factorized_representation:       # VAEtrimodalMimic.forward:49-51
+                        s_mu, s_logvar = latents['modalities'][m + '_style']
+                        CURRENT['style_mod'] = m
+                        s_emb = R.U.reparameterize(mu=s_mu, logvar=s_logvar)
                     if m == 'text':
-                        rec[m] = mod.likelihood(logits=dec(None, z)[0])
+                        rec[m] = mod.likelihood(logits=dec(s_emb, z)[0])
                     else:
-                        rec[m] = mod.likelihood(*dec(None, z))
+                        rec[m] = mod.likelihood(*dec(s_emb, z))
             results['rec'] = rec
             return results
 
@@ -145,6 +159,9 @@ def build_reference_model(R, fl, state):
         if isinstance(mod, (torch.nn.Dropout, torch.nn.Dropout2d)):
             mod.forward = (lambda x, n=name, md=mod: x * CURRENT['masks'][n] * 2.0 if md.training else x)
     def reparameterize(mu, logvar):
+        if CURRENT['style_mod'] is not None:        # the shim's style sample of modality `style_mod` in the current pass
+            m, CURRENT['style_mod'] = CURRENT['style_mod'], None
+            return CURRENT['eps_style_pass'][m] * torch.exp(0.5 * logvar) + mu
         # VAEtrimodalMimic.forward: the content sample first, then one style sample per modality in self.modalities order
         if CURRENT['eps_style'] is not None and mu.shape[1] != fl.class_dim:
             m = list(fl.mods)[CURRENT['style_calls'] % len(fl.mods)]
@@ -167,7 +184,8 @@ def reference_step(R, exp, batch):
         total = R.losses.calc_joint_elbo_loss(exp, klds_style, results['joint_divergence'], fl.beta_style,
                                               fl.beta_content, weighted, fl.beta)
     else:
-        total = R.losses.calc_poe_loss(exp, exp.modalities, results['joint_divergence'], klds, None, batch,
+        klds_style = R.losses.calc_klds_style(exp, results) if fl.factorized_representation else None
+        total = R.losses.calc_poe_loss(exp, exp.modalities, results['joint_divergence'], klds, klds_style, batch,
                                        exp.mm_vae, log_probs)
     return dict(results=results, log_probs=log_probs, klds=klds, total_loss=total)
 
@@ -202,6 +220,8 @@ CASES = OrderedDict([
                                 style_dims={'PA': 8, 'Lateral': 8, 'text': 16})),
     ('small_tri_word_style_moe', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, method='moe', text_encoding='word',
                                      vocab_size=48, len_sequence=128, style_dims={'PA': 8, 'Lateral': 8, 'text': 8})),
+    ('small_tri_poe_style', dict(batch_size=6, DIM_img=16, DIM_text=16, class_dim=32, method='poe',
+                                style_dims={'PA': 8, 'Lateral': 8, 'text': 16})),
     ('small_tri_jsd', dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, method='jsd')),
     ('small_patext_jsd', dict(batch_size=9, DIM_img=16, DIM_text=16, class_dim=32, mods=('PA', 'text'), method='jsd')),
 ])
@@ -220,8 +240,11 @@ def run_case(R, name, kw, outdir):
     noise = [O.make_noise(fl, seed=2 + i, dtype=dt, batch=B) for i in range(1 + len(fl.mods))]
     t0 = time.time()
     eps_style = O.make_style_noise(fl, seed=2, dtype=dt, batch=B)
+    uni_es = ({m: O.make_style_noise(fl, seed=3 + i, dtype=dt, batch=B) for i, m in enumerate(fl.mods)}
+              if eps_style is not None else None)
     # ---- reference
-    CURRENT.update(calls=0, noise=noise, eps_style=eps_style, style_calls=0)
+    CURRENT.update(calls=0, noise=noise, eps_style=eps_style, style_calls=0, style_mod=None, eps_style_pass=eps_style,
+                   eps_style_list=([eps_style] + [uni_es[m] for m in fl.mods]) if uni_es is not None else None)
     exp = build_reference_model(R, fl, state)
     exp.mm_vae.train()
     out = reference_step(R, exp, OrderedDict(batch))
@@ -233,7 +256,8 @@ def run_case(R, name, kw, outdir):
     # ---- oracle on the same data
     st2 = OrderedDict((k, v.clone()) for k, v in state.items())
     uni = {m: noise[1 + i] for i, m in enumerate(fl.mods)}
-    orc = O.step_with_grads_full(st2, batch, fl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=eps_style)
+    orc = O.step_with_grads_full(st2, batch, fl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=eps_style,
+                                 uni_eps_style=uni_es)
     t2 = time.time()
 
     def rel(a, b):

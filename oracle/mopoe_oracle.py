@@ -666,7 +666,7 @@ def forward(state, batch, flags, masks=None, eps=None, train=True, present=None,
                 bn_updates=ctx.bn_updates)
 
 
-def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks=None, eps_style=None):
+def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks=None, eps_style=None, uni_eps_style=None):
     """run_epochs.basic_routine_epoch (run_epochs.py:52-96): forward, calc_log_probs (losses.py:6-21),
     calc_klds (:24-31), calc_joint_elbo_loss (:80-89) or calc_poe_loss (:54-77, intended semantics)."""
     res = forward(state, batch, flags, masks, eps, train, eps_style=eps_style)
@@ -686,16 +686,18 @@ def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks
     if flags.method in ('moe', 'jsd', 'joint_elbo'):
         total = weighted + flags.beta * (flags.beta_style * kld_style + flags.beta_content * res['joint_divergence'])
     elif flags.method == 'poe':
-        if klds_style:
-            raise NotImplementedError('poe with a factorized representation')
-        total = weighted + flags.beta * flags.beta_content * res['joint_divergence']   # calc_elbo 'joint'
+        # calc_poe_loss (losses.py:54-77) + utils.calc_elbo (utils/utils.py:105-127): the style KLs of the JOINT pass enter
+        # the joint ELBO (weighted sum) and every unimodal ELBO (the modality's own)
+        total = weighted + flags.beta * (flags.beta_content * res['joint_divergence'] + flags.beta_style * kld_style)
         state2 = dict(state)              # the unimodal passes see the BN buffers the joint pass updated
         state2.update(res['bn_updates'])
         for i, m in enumerate(flags.mods):
             um, ue = (uni_masks or {}).get(m, (masks, eps))
-            r_m = forward(state2, {m: batch[m]}, flags, um, ue, train, present=[m])
+            es_m = (uni_eps_style or {}).get(m, eps_style)
+            r_m = forward(state2, {m: batch[m]}, flags, um, ue, train, present=[m], eps_style=es_m)
             lp = (categorical_log_prob_sum if m == 'text' else laplace_log_prob_sum)(r_m['rec'][m], batch[m])
-            total = total + (-lp / Bn) + flags.beta * flags.beta_content * klds[m]     # calc_elbo modality
+            ks_m = flags.style_weights[m] * klds_style[m + '_style'] if klds_style else 0.0
+            total = total + (-lp / Bn) + flags.beta * (flags.beta_content * klds[m] + flags.beta_style * ks_m)   # calc_elbo modality
             for k, v in r_m['bn_updates'].items():
                 res['bn_updates'][k] = v
     else:
@@ -704,13 +706,13 @@ def step_losses(state, batch, flags, masks=None, eps=None, train=True, uni_masks
                 weighted_log_prob=weighted)
 
 
-def step_with_grads(state, batch, flags, masks=None, eps=None, uni_masks=None, eps_style=None):
+def step_with_grads(state, batch, flags, masks=None, eps=None, uni_masks=None, eps_style=None, uni_eps_style=None):
     """One train-mode step: losses + d(total_loss)/d(param) for every float parameter."""
     params = {k: v for k, v in state.items() if v.is_floating_point() and 'running_' not in k}
     for v in params.values():
         v.requires_grad_(True)
         v.grad = None
-    out = step_losses(state, batch, flags, masks, eps, True, uni_masks=uni_masks, eps_style=eps_style)
+    out = step_losses(state, batch, flags, masks, eps, True, uni_masks=uni_masks, eps_style=eps_style, uni_eps_style=uni_eps_style)
     out['total_loss'].backward()
     # (parameters the step never touches — the word encoder's resblock_7/8 at len_sequence <= 500 — have no gradient)
     grads = OrderedDict((k, v.grad.detach().clone()) for k, v in params.items() if v.grad is not None)

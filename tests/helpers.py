@@ -45,13 +45,17 @@ def make_case(kw, actual_batch=None, dtype=torch.float32, seeds=(0, 1, 2)):
     batch = O.make_batch(ofl, seeds[1], dtype, B)
     noise = [O.make_noise(ofl, seeds[2] + i, dtype, B) for i in range(1 + len(ofl.mods))]
     ofl.eps_style = O.make_style_noise(ofl, seeds[2], dtype, B)        # None unless the case is factorized
+    # poe: every unimodal pass reparameterises its own style latent
+    ofl.eps_style_uni = ({m: O.make_style_noise(ofl, seeds[2] + 1 + i, dtype, B) for i, m in enumerate(ofl.mods)}
+                         if ofl.eps_style is not None else None)
     return ofl, state, batch, noise
 
 
 def run_oracle(ofl, state, batch, noise):
     st = OrderedDict((k, v.clone()) for k, v in state.items())
     uni = {m: noise[1 + i] for i, m in enumerate(ofl.mods)}
-    return O.step_with_grads(st, batch, ofl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=getattr(ofl, 'eps_style', None))
+    return O.step_with_grads(st, batch, ofl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=getattr(ofl, 'eps_style', None),
+                             uni_eps_style=getattr(ofl, 'eps_style_uni', None))
 
 
 def run_product(ofl, state, batch, noise, compute_dtype):
@@ -65,7 +69,9 @@ def run_product(ofl, state, batch, noise, compute_dtype):
     dev = fl.device
     es = getattr(ofl, 'eps_style', None)
     es = {m: v.float().to(dev) for m, v in es.items()} if es is not None else None
-    vae.rt.schedule = [(masks_to_product(m, dev), e.float().to(dev), es) for m, e in noise]
+    esu = getattr(ofl, 'eps_style_uni', None)
+    per_pass = [es] + [({k: v.float().to(dev) for k, v in esu[m].items()} if esu is not None else es) for m in ofl.mods]
+    vae.rt.schedule = [(masks_to_product(m, dev), e.float().to(dev), per_pass[i]) for i, (m, e) in enumerate(noise)]
     b = OrderedDict((k, v.float().to(dev)) for k, v in batch.items())
     out = P.basic_routine_epoch(exp, (b, None))
     exp.optimizer.zero_grad()

@@ -323,6 +323,43 @@ def test_graphed_step_uint8_text_wire_format():
     assert len(set(seqs[0])) == len(seqs[0])
 
 
+def test_graphed_step_uint8_image_wire_format():
+    """8-bit images on the wire ([B, 1, px, px] uint8; ToTensor() = x / 255 evaluated on the device, 1/4 of the H2D bytes)
+    give exactly the losses of the reference format (fp32 in [0, 1], divided on the host) — host and device feeds, together
+    with the uint8 text wire."""
+    import mopoe_mimic_b200 as P
+    kw = dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32)
+    ofl = O.default_flags(**kw)
+    state = O.make_state(ofl, 0, torch.float32)
+    g = torch.Generator().manual_seed(31)
+    wire, host = [], []
+    for i in range(4):
+        b = O.make_batch(ofl, 40 + i, torch.float32)
+        w = {'PA': torch.randint(0, 256, (8, 1, 128, 128), generator=g, dtype=torch.uint8).pin_memory(),
+             'Lateral': torch.randint(0, 256, (8, 1, 128, 128), generator=g, dtype=torch.uint8).pin_memory(),
+             'text': b['text'].argmax(-1).to(torch.uint8).pin_memory()}
+        wire.append(w)
+        host.append({'PA': (w['PA'].float() / 255.0).pin_memory(), 'Lateral': (w['Lateral'].float() / 255.0).pin_memory(),
+                     'text': b['text'].pin_memory()})
+    seqs = []
+    for mode in ('fp32', 'uint8_host', 'uint8_device'):
+        exp = P.Experiment(P.default_flags(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32, compute_dtype='fp32'))
+        exp.mm_vae.load_state_dict(state)
+        exp.set_optimizer()
+        exp.mm_vae.train()
+        exp.mm_vae.rt.seed = 7
+        exp.mm_vae.rt.injected_eps = torch.zeros(8, 32, device='cuda')
+        gs = P.GraphedTrainStep(exp, {k: v.cuda() for k, v in host[0].items()}, warmup=1)
+        outs = []
+        for b, w in zip(host, wire):
+            feed = b if mode == 'fp32' else (w if mode == 'uint8_host' else {k: v.cuda() for k, v in w.items()})
+            outs.append(gs(feed)[:1].clone())
+        torch.cuda.synchronize()
+        seqs.append([float(o) for o in outs])
+    assert seqs[0] == seqs[1] == seqs[2]
+    assert len(set(seqs[0])) == len(seqs[0])
+
+
 @pytest.mark.parametrize('B,S', [(256, 7), (1024, 7), (2048, 7), (128, 3), (64, 7)])
 def test_full_size_selection_ranges(B, S):
     """BASELINE.json batch sizes: k * floor(B/S) boundaries, identical to the oracle's."""

@@ -37,6 +37,7 @@ CASES = {
                               len_sequence=128),                                         # V > 256: looped categorical kernels
     'tri_style': dict(SMALL, style_dims={'PA': 8, 'Lateral': 16, 'text': 24}),      # factorized representation
     'tri_style_moe': dict(SMALL, method='moe', style_dims={'PA': 8, 'Lateral': 8, 'text': 8}),
+    'tri_style_poe': dict(SMALL, method='poe', batch_size=6, style_dims={'PA': 8, 'Lateral': 8, 'text': 16}),   # losses.py:58-72
     'patext_jsd': dict(SMALL, mods=('PA', 'text'), method='jsd', batch_size=9),
     'tri_64px': dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=16, img_size=64),
     'tri_256px': dict(batch_size=4, DIM_img=8, DIM_text=8, class_dim=16, img_size=256),     # stride-4 stage (config 4)
@@ -108,7 +109,7 @@ def test_fp32_ragged_last_batch():
 
 GOLDEN_SMALL = ['small_tri_joint', 'small_tri_moe', 'small_tri_poe', 'small_patext_joint', 'small_patext_moe',
                 'small_patext_poe', 'small_tri_64_joint', 'small_tri_256_joint', 'small_tri_joint_ragged', 'small_tri_jsd',
-                'small_patext_jsd', 'small_tri_style', 'small_tri_word']
+                'small_patext_jsd', 'small_tri_style', 'small_tri_word', 'small_tri_poe_style']
 
 
 @pytest.mark.parametrize('fixture', GOLDEN_SMALL)

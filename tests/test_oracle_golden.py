@@ -26,7 +26,8 @@ def run_oracle(fx, dtype=torch.float64):
     noise = [O.make_noise(fl, fx['seeds']['noise'] + i, dtype, B) for i in range(1 + len(fl.mods))]
     uni = {m: noise[1 + i] for i, m in enumerate(fl.mods)}
     es = O.make_style_noise(fl, fx['seeds']['noise'], dtype, B)
-    return fl, st, O.step_with_grads(st, batch, fl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=es)
+    ues = {m: O.make_style_noise(fl, fx['seeds']['noise'] + 1 + i, dtype, B) for i, m in enumerate(fl.mods)} if es is not None else None
+    return fl, st, O.step_with_grads(st, batch, fl, noise[0][0], noise[0][1], uni_masks=uni, eps_style=es, uni_eps_style=ues)
 
 
 def check_checksum(t, cs, rtol, scale=0.0):
