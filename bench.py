@@ -200,7 +200,7 @@ def run_dp_check(exp, px_obj, world, rank, dev):
     dist.all_reduce(g_sum)
     L.call('mopoe_adam_flat_dev', L.ptr(p_ref), L.ptr(g_sum), L.ptr(m_ref), L.ptr(v_ref), p_ref.numel(), L.ptr(opt.coef),
            float(opt.betas[0]), float(opt.betas[1]), float(opt.eps), 1.0 / world, L.stream_ptr())
-    px_obj.adam_step(opt.m, opt.v, opt.coef, opt.betas, opt.eps)
+    px_obj.adam_step_all(opt.m, opt.v, opt.coef, opt.betas, opt.eps)
     eng.invalidate_packs()
     torch.cuda.synchronize()
     err = (opt.p - p_ref).abs().max().reshape(1).double()
@@ -215,7 +215,8 @@ def run_dp_check(exp, px_obj, world, rank, dev):
     return {'what': 'one step: fused peer-memory exchange kernel vs NCCL all-reduce + flat Adam (grad_scale 1/world)',
             'max_abs_err': float(err), 'param_abs_max': float(scale),
             'params_equal_across_ranks': bool(float(spread) == 0.0), 'max_param_spread_across_ranks': float(spread),
-            'world': world, 'multicast': bool(getattr(px_obj, 'multicast', False))}
+            'world': world, 'multicast': bool(getattr(px_obj, 'multicast', False)),
+            'buckets': [(b['lo'], b['hi']) for b in px_obj.buckets] if px_obj.buckets else None}
 
 
 def main():

@@ -336,6 +336,13 @@ typedef struct {
 int mopoe_dp_adam_exchange(const mopoe_dp_peers_t* peers, const float* mc_grad, float* mc_param, float* m, float* v,
                            int64_t n, int rank, int world, uint32_t* state, const float* coef, float beta1,
                            float beta2, float eps, float grad_scale, void* stream);
+/* The same on at most max_blocks thread blocks (0 = no limit).  A training step exchanges its gradients in BUCKETS — the
+ * decoders' slice of the flat buffers as soon as the decoders' backward pass is done, under the encoders' backward (DDP's
+ * bucketed overlap, run_epochs.py:245-247); every bucket is one call on its own sub-range (pointers offset by the bucket's
+ * start), with its own flags / state, and the overlapped one runs on a small grid. */
+int mopoe_dp_adam_exchange_ex(const mopoe_dp_peers_t* peers, const float* mc_grad, float* mc_param, float* m, float* v,
+                              int64_t n, int rank, int world, uint32_t* state, const float* coef, float beta1,
+                              float beta2, float eps, float grad_scale, int max_blocks, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,7 @@ SIGNATURES = {
     'mopoe_pack_job_tiles': (_I, [_I, _I, _I, _I, _I, _I, C.POINTER(C.c_int)]),
     'mopoe_pack_weights_batched': (_I, [_P, _I, _I, _I, _P]),
     'mopoe_dp_adam_exchange': (_I, [C.POINTER(DpPeers), _P, _P, _P, _P, _L, _I, _I, _P, _P, _F, _F, _F, _F, _P]),
+    'mopoe_dp_adam_exchange_ex': (_I, [C.POINTER(DpPeers), _P, _P, _P, _P, _L, _I, _I, _P, _P, _F, _F, _F, _F, _I, _P]),
     'mopoe_adam_flat': (_I, [_P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _P]),
 }
 

@@ -174,9 +174,9 @@ dp_adam_exchange_kernel(const DpxPeers peers, const float* __restrict__ mc_grad,
     }
 }
 
-extern "C" int mopoe_dp_adam_exchange(const mopoe_dp_peers_t* peers, const float* mc_grad, float* mc_param, float* m, float* v,
-                                      int64_t n, int rank, int world, uint32_t* state, const float* coef, float beta1,
-                                      float beta2, float eps, float grad_scale, void* stream) {
+extern "C" int mopoe_dp_adam_exchange_ex(const mopoe_dp_peers_t* peers, const float* mc_grad, float* mc_param, float* m, float* v,
+                                         int64_t n, int rank, int world, uint32_t* state, const float* coef, float beta1,
+                                         float beta2, float eps, float grad_scale, int max_blocks, void* stream) {
     MOPOE_REQUIRE(peers && m && v && state && coef, "dp_adam_exchange: null argument");
     MOPOE_REQUIRE(world >= 1 && world <= DPX_MAX_WORLD && rank >= 0 && rank < world, "dp_adam_exchange: rank %d / world %d", rank,
                   world);
@@ -195,6 +195,9 @@ extern "C" int mopoe_dp_adam_exchange(const mopoe_dp_peers_t* peers, const float
     const long long n4 = n / 4, per = (n4 + world - 1) / world;
     long long blocks = (per + DPX_THREADS * DPX_UNROLL - 1) / (DPX_THREADS * DPX_UNROLL);
     if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+    // a bucket exchanged UNDER the rest of the backward pass runs on a small grid: it has milliseconds to hide in and
+    // must not take the SMs away from the kernels it overlaps with
+    if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     MOPOE_REQUIRE((mc_grad == nullptr) == (mc_param == nullptr), "dp_adam_exchange: give both multicast addresses or neither");
     MOPOE_REQUIRE((((uintptr_t)mc_grad | (uintptr_t)mc_param) & 15) == 0, "dp_adam_exchange: unaligned multicast address");
@@ -213,4 +216,11 @@ extern "C" int mopoe_dp_adam_exchange(const mopoe_dp_peers_t* peers, const float
             pk, nullptr, nullptr, m, v, n4, rank, world, state, coef, beta1, beta2, eps, grad_scale, timeout_ns);
     MOPOE_CHECK_LAUNCH("dp_adam_exchange");
     return 0;
+}
+
+extern "C" int mopoe_dp_adam_exchange(const mopoe_dp_peers_t* peers, const float* mc_grad, float* mc_param, float* m, float* v,
+                                      int64_t n, int rank, int world, uint32_t* state, const float* coef, float beta1,
+                                      float beta2, float eps, float grad_scale, void* stream) {
+    return mopoe_dp_adam_exchange_ex(peers, mc_grad, mc_param, m, v, n, rank, world, state, coef, beta1, beta2, eps, grad_scale, 0,
+                                     stream);
 }

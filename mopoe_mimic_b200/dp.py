@@ -56,6 +56,8 @@ class PeerExchange:
     the whole DP step stays ONE CUDA graph.  Adam moments are owner-sharded (ZeRO-1 style): `gather_moments()`
     assembles the full tensors for a checkpoint."""
 
+    MAX_BUCKETS = 8
+
     def __init__(self, device, group=None, multicast=None):
         """multicast: None = use NVSwitch multicast (NVLS) when the symmetric allocation has it and world > 2
         (MOPOE_DP_MULTICAST=0/1 overrides); True / False force it."""
@@ -81,7 +83,7 @@ class PeerExchange:
     def alloc(self, total):
         self.params = self.symm.empty(total, dtype=torch.float32, device=self.device)
         self.grads = self.symm.empty(total, dtype=torch.float32, device=self.device)
-        self.flags = self.symm.empty(64, dtype=torch.int32, device=self.device)
+        self.flags = self.symm.empty(self.MAX_BUCKETS * 32, dtype=torch.int32, device=self.device)
         self.flags.zero_()
         return self.params, self.grads
 
@@ -108,40 +110,86 @@ class PeerExchange:
         self.multicast = use
         self.mc_grad, self.mc_param = (hg.multicast_ptr + og, hp.multicast_ptr + op) if use else (0, 0)
         self.state = torch.tensor([1, 0, 0, 0], dtype=torch.int32, device=self.device)   # epoch, arrivals, error, -
+        self._bases = ([hg.buffer_ptrs[r] + og for r in range(self.world)], [hp.buffer_ptrs[r] + op for r in range(self.world)],
+                       [hf.buffer_ptrs[r] + of for r in range(self.world)])
+        self.buckets = None
         dist.broadcast(self.params, 0, group=self.group)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)          # every rank's flags are zeroed and mapped before the first kernel
 
-    def adam_step(self, m, v, coef, betas, eps):
+    def set_buckets(self, bounds):
+        """Split the exchange into buckets: [(lo, hi), ...] element ranges (multiples of 4) covering the flat buffers, in the
+        order their gradients become final during backward.  Every bucket is exchanged by its own launch on its own
+        sub-range (reduce-scatter + Adam + all-gather of THAT range over all ranks), with its own flag slots / epoch state,
+        so a bucket can run under the rest of the backward pass (the reference's DDP overlaps its buckets the same way)."""
+        from . import _lib as L
+        assert self.peers is not None, 'connect() first'
+        assert 1 <= len(bounds) <= self.MAX_BUCKETS
+        covered = sorted(bounds)
+        assert covered[0][0] == 0 and covered[-1][1] == self.params.numel() and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        gb, pb, fb = self._bases
+        self.buckets = []
+        for k, (lo, hi) in enumerate(bounds):
+            assert lo % 4 == 0 and hi % 4 == 0 and hi > lo
+            pk = L.DpPeers()
+            for r in range(self.world):
+                pk.grad[r], pk.param[r], pk.flags[r] = gb[r] + 4 * lo, pb[r] + 4 * lo, fb[r] + 4 * 32 * k
+            self.buckets.append(dict(lo=lo, hi=hi, peers=pk,
+                                     mc_grad=self.mc_grad + 4 * lo if self.multicast else 0,
+                                     mc_param=self.mc_param + 4 * lo if self.multicast else 0,
+                                     state=torch.tensor([1, 0, 0, 0], dtype=torch.int32, device=self.device)))
+
+    def adam_step(self, m, v, coef, betas, eps, bucket=None, max_blocks=0):
+        """the whole buffer (bucket None; only valid while no buckets are set) or one bucket"""
         import ctypes as C
         from . import _lib as L
-        L.call('mopoe_dp_adam_exchange', C.byref(self.peers), C.c_void_p(self.mc_grad), C.c_void_p(self.mc_param),
-               L.ptr(m), L.ptr(v), self.params.numel(), self.rank,
-               self.world, L.ptr(self.state), L.ptr(coef), float(betas[0]), float(betas[1]), float(eps),
-               float(self.grad_scale), L.stream_ptr())
+        if bucket is None:
+            assert self.buckets is None, 'the exchange is bucketed: use adam_step_all() or pass a bucket index'
+            L.call('mopoe_dp_adam_exchange', C.byref(self.peers), C.c_void_p(self.mc_grad), C.c_void_p(self.mc_param),
+                   L.ptr(m), L.ptr(v), self.params.numel(), self.rank,
+                   self.world, L.ptr(self.state), L.ptr(coef), float(betas[0]), float(betas[1]), float(eps),
+                   float(self.grad_scale), L.stream_ptr())
+            return
+        b = self.buckets[bucket]
+        lo, hi = b['lo'], b['hi']
+        L.call('mopoe_dp_adam_exchange_ex', C.byref(b['peers']), C.c_void_p(b['mc_grad']), C.c_void_p(b['mc_param']),
+               L.ptr(m[lo:hi]), L.ptr(v[lo:hi]), hi - lo, self.rank, self.world, L.ptr(b['state']), L.ptr(coef),
+               float(betas[0]), float(betas[1]), float(eps), float(self.grad_scale), int(max_blocks), L.stream_ptr())
+
+    def adam_step_all(self, m, v, coef, betas, eps):
+        """every bucket (or the whole buffer) back to back on the current stream"""
+        if self.buckets is None:
+            return self.adam_step(m, v, coef, betas, eps)
+        for k in range(len(self.buckets)):
+            self.adam_step(m, v, coef, betas, eps, bucket=k)
 
     def check(self):
         """Raise if a flag barrier of the exchange kernel gave up waiting (one device->host read; call it where the step's
         statistics are read anyway).  All ranks must reach the exchange within MOPOE_DP_TIMEOUT_S (default 600 s, 0 = no
         limit) of each other; put a dist.barrier() after rank-asymmetric work (rank-0 evaluation, checkpointing) so the
         skew is absorbed on the host rather than inside the kernel."""
-        err = int(self.state[2].item())
+        errs = [int(self.state[2].item())] + [int(b['state'][2].item()) for b in (self.buckets or [])]
+        err = max(errs)
         if err:
             err -= 1
             raise RuntimeError('peer exchange: rank %d never reached barrier %d within MOPOE_DP_TIMEOUT_S on rank %d'
                                % (err % 16, err // 16, self.rank))
 
-    def slice_bounds(self):
-        n4 = self.params.numel() // 4
+    def slice_bounds(self, lo=0, hi=None):
+        """owner slices of the range [lo, hi) (default: the whole buffer): rank r owns the r-th run of ceil(n/4/world) float4s"""
+        hi = self.params.numel() if hi is None else hi
+        n4 = (hi - lo) // 4
         per = (n4 + self.world - 1) // self.world
-        return [(min(n4, r * per) * 4, min(n4, (r + 1) * per) * 4) for r in range(self.world)]
+        return [(lo + min(n4, r * per) * 4, lo + min(n4, (r + 1) * per) * 4) for r in range(self.world)]
 
     def gather_moments(self, m, v):
         """full Adam moments on every rank (for optimizer checkpoints): each slice comes from its owner"""
-        for r, (s, e) in enumerate(self.slice_bounds()):
-            if e > s:
-                dist.broadcast(m[s:e], r, group=self.group)
-                dist.broadcast(v[s:e], r, group=self.group)
+        ranges = [(b['lo'], b['hi']) for b in self.buckets] if getattr(self, 'buckets', None) else [(0, self.params.numel())]
+        for lo, hi in ranges:
+            for r, (s, e) in enumerate(self.slice_bounds(lo, hi)):
+                if e > s:
+                    dist.broadcast(m[s:e], r, group=self.group)
+                    dist.broadcast(v[s:e], r, group=self.group)
         return m, v
 
 

@@ -235,6 +235,24 @@ def reparameterize(mu, logvar):
     return torch.randn_like(std).mul(std).add(mu)
 
 
+class _GradReady(torch.autograd.Function):
+    """identity on the latent sample fed to every decoder; its backward runs once ALL decoders have produced their input
+    gradient — i.e. every decoder parameter gradient of the step is final (each decoder's backward kernels are queued
+    on its stream before the kernel that produces dz) — and fires rt.on_decoders_done (the bucketed gradient exchange)"""
+
+    @staticmethod
+    def forward(ctx, z, rt):
+        ctx.rt = rt
+        return z.view_as(z)
+
+    @staticmethod
+    def backward(ctx, g):
+        cb = getattr(ctx.rt, 'on_decoders_done', None)
+        if cb is not None:
+            cb()
+        return g, None
+
+
 class MMVaeMimic(BaseMMVae):
     """Any non-empty subset of {PA, Lateral, text}; VAEtrimodalMimic is the 3-modality instance."""
 
@@ -376,6 +394,9 @@ class MMVaeMimic(BaseMMVae):
             results['dyn_prior'] = None
         results['group_distr'] = latents['joint']
         class_embeddings = latents['_z']
+        if (getattr(self.rt, 'on_decoders_done', None) is not None and torch.is_grad_enabled() and class_embeddings.requires_grad
+                and len(input_batch) == self.num_modalities):
+            class_embeddings = _GradReady.apply(class_embeddings, self.rt)
         results_rec = {}
         factorized = bool(getattr(self.flags, 'factorized_representation', False))
         if factorized:
@@ -450,6 +471,7 @@ class MMVaeMimic(BaseMMVae):
         else:
             flat = torch.zeros(total, dtype=torch.float32, device=dev)
             flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        object.__setattr__(self, 'flat_offsets', {name: off for (name, _), off in zip(self.named_parameters(), offs)})
         for p, off in zip(params, offs):
             n = p.numel()
             flat[off:off + n].copy_(p.data.reshape(-1))

@@ -39,6 +39,7 @@ class Runtime:
         self.injected_eps_style = None   # modality -> [B, style_dim] fp32 (factorized representation)
         self.schedule = None          # optional list of (masks, eps[, eps_style]), one per model forward call (poe passes)
         self.seed = None
+        self.on_decoders_done = None  # callback fired in backward once every decoder gradient is final (bucketed DP exchange)
 
     def eng(self, device):
         if self.engine is None:

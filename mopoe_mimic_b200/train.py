@@ -115,6 +115,46 @@ class FlatAdam:
         # step count and bias-correction coefficients live on the device: the step stays CUDA-graph capturable
         self.step_t = torch.zeros(1, dtype=torch.int32, device=dev)
         self.coef = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._advanced = False
+        self._xs = None
+        self._setup_buckets()
+
+    def _setup_buckets(self):
+        """Data-parallel overlap (north_star item 4): the decoders' gradients are final long before the encoders' backward
+        ends, so their slice of the flat buffers is exchanged (reduce-scatter + Adam + all-gather) on a side stream UNDER
+        the encoders' backward; only the encoders' bucket runs after it.  Needs the decoders' parameters to form the
+        contiguous tail of the flat buffer (registration order: encoders, then decoders).  poe's unimodal passes revisit
+        the decoders, so poe keeps the single exchange.  MOPOE_DP_BUCKETS=0 disables it."""
+        import os
+        ex, model = self.exchange, self.model
+        if ex is None or os.environ.get('MOPOE_DP_BUCKETS', '1') == '0' or getattr(model, 'method', None) == 'poe':
+            return
+        offs = getattr(model, 'flat_offsets', None)
+        if not offs:
+            return
+        dec = [o for n, o in offs.items() if n.startswith('decoder_')]
+        enc = [o for n, o in offs.items() if not n.startswith('decoder_')]
+        if not dec or not enc or max(enc) > min(dec):
+            return
+        cut = min(dec)
+        ex.set_buckets([(cut, self.p.numel()), (0, cut)])          # launch order: decoders first
+        self._xs = torch.cuda.Stream()
+        self.side_blocks = int(os.environ.get('MOPOE_DPX_SIDE_BLOCKS', '64'))
+        model.rt.on_decoders_done = self.begin_exchange
+
+    def _advance(self, eng):
+        L.call('mopoe_step_advance', L.ptr(eng.rng_step), L.ptr(self.step_t), L.ptr(self.coef), float(self.lr),
+               float(self.betas[0]), float(self.betas[1]), L.stream_ptr())
+        self._advanced = True
+
+    def begin_exchange(self):
+        """fired from backward when every decoder gradient is final: exchange the decoders' bucket on the side stream"""
+        eng = self.model.rt.eng(self.p.device)
+        cur = torch.cuda.current_stream()
+        self._xs.wait_stream(cur)
+        with torch.cuda.stream(self._xs):
+            self._advance(eng)
+            self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps, bucket=0, max_blocks=self.side_blocks)
 
     @property
     def step_count(self):
@@ -130,9 +170,16 @@ class FlatAdam:
         # `loss.backward(); optimizer.step()` must therefore join the branches before anything reads flat_grads
         if hasattr(self.model, 'join_branches'):
             self.model.join_branches()
-        L.call('mopoe_step_advance', L.ptr(eng.rng_step), L.ptr(self.step_t), L.ptr(self.coef), float(self.lr),
-               float(self.betas[0]), float(self.betas[1]), L.stream_ptr())
-        if self.exchange is not None:
+        if self._advanced:              # bucketed exchange: the decoders' bucket is already in flight on the side stream
+            torch.cuda.current_stream().wait_stream(self._xs)
+        else:
+            self._advance(eng)
+        started, self._advanced = self._advanced, False
+        if self.exchange is not None and self.exchange.buckets is not None:
+            if not started:             # (a step whose backward did not fire the hook: exchange every bucket here)
+                self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps, bucket=0)
+            self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps, bucket=1)
+        elif self.exchange is not None:
             # reduce-scatter + Adam + all-gather in one kernel over peer memory; moments of a slice live on its owner
             self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps)
         else:

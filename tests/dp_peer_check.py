@@ -21,7 +21,78 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     for mc in (False, True):
         run(mc)
+    run_buckets()
     dist.destroy_process_group()
+
+
+def run_buckets():
+    """the bucketed exchange (decoders' slice first on a side stream with a small grid, then the rest): same parameters
+    and moments as NCCL all-reduce + Adam over the whole buffer, eagerly and from a CUDA graph with the first bucket on a
+    forked stream (as FlatAdam.begin_exchange / step do inside the training-step graph)"""
+    from mopoe_mimic_b200 import _lib as L
+    from mopoe_mimic_b200.dp import PeerExchange
+    world, rank = int(os.environ['WORLD_SIZE']), int(os.environ['RANK'])
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    n = (5 << 20) + 448
+    cut = (3 << 20) + 64
+    px = PeerExchange(dev)
+    params, grads = px.alloc(n)
+    params.copy_(torch.randn(n, generator=torch.Generator(device='cpu').manual_seed(1)))
+    px.connect()
+    px.set_buckets([(cut, n), (0, cut)])
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    p_ref, m_ref, v_ref = params.clone(), m.clone(), v.clone()
+    coef = torch.zeros(2, device=dev)
+    b1, b2, eps, lr = 0.9, 0.999, 1e-8, 1e-3
+    gr = torch.Generator(device='cpu').manual_seed(200 + rank)
+    step_grads = [torch.randn(n, generator=gr).to(dev) * (1 + rank) for _ in range(5)]
+    tol = 0.0 if world == 2 else 2e-5
+    xs = torch.cuda.Stream()
+
+    def set_coef(t):
+        coef.copy_(torch.tensor([lr / (1 - b1 ** t), 1.0 / (1 - b2 ** t) ** 0.5]))
+
+    def exchange():
+        cur = torch.cuda.current_stream()
+        xs.wait_stream(cur)
+        with torch.cuda.stream(xs):
+            px.adam_step(m, v, coef, (b1, b2), eps, bucket=0, max_blocks=16)
+        cur.wait_stream(xs)
+        px.adam_step(m, v, coef, (b1, b2), eps, bucket=1)
+
+    def check(tag, t):
+        gs = step_grads[t].clone()
+        dist.all_reduce(gs)
+        L.call('mopoe_adam_flat_dev', L.ptr(p_ref), L.ptr(gs), L.ptr(m_ref), L.ptr(v_ref), n, L.ptr(coef), b1, b2, eps,
+               1.0 / world, L.stream_ptr())
+        torch.cuda.synchronize()
+        err = float((params - p_ref).abs().max())
+        assert err <= tol, '%s: rank %d param err %.3e' % (tag, rank, err)
+    for t in range(2):
+        set_coef(t + 1)
+        grads.copy_(step_grads[t])
+        exchange()
+        check('bucketed eager step %d' % t, t)
+    static_g = torch.zeros(n, device=dev)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        grads.copy_(static_g)
+        exchange()
+    for t in range(2, 5):
+        set_coef(t + 1)
+        static_g.copy_(step_grads[t])
+        graph.replay()
+        check('bucketed graph step %d' % t, t)
+    px.gather_moments(m, v)
+    px.check()
+    torch.cuda.synchronize()
+    assert float((m - m_ref).abs().max()) <= tol and float((v - v_ref).abs().max()) <= tol
+    dist.barrier()
+    if rank == 0:
+        print('dp_peer_check buckets PASS world=%d' % world, flush=True)
 
 
 def run(multicast):

@@ -198,3 +198,27 @@ def test_gemm_with_fused_batchnorm_statistics(impl, dtype, kind, nd, B, ci, co, 
     mean, var = v.mean(0), v.var(0, unbiased=False)
     torch.testing.assert_close(st[0].double(), mean, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(st[1].double(), 1.0 / torch.sqrt(var + 1e-5), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('B,ci,co,sp', [(3, 64, 128, 10), (2, 64, 256, 16), (5, 128, 640, 6)])
+def test_tma_store_epilogue_writes_nothing_outside_its_rows(B, ci, co, sp):
+    """Guard-band check of the TMA-store epilogue (compute-sanitizer is closed on this pool): the GEMM writes the interior of
+    a BORDERED output carved out of a larger sentinel-filled buffer; ragged tiles (B * OH * OW not a multiple of 128), the
+    border pixels and the guard bands before / after the tensor must keep the sentinel."""
+    from mopoe_mimic_b200.engine import Act, conv_form
+    eng = _eng(torch.bfloat16, 'tc')
+    x = _rand((B, ci, sp, sp), 31, 1.0, torch.bfloat16)
+    w = _rand((co, ci, 4, 4), 32, 0.05, torch.bfloat16)
+    ref = F.conv2d(x, w, None, stride=2, padding=1)
+    OH = sp // 2
+    guard = 4096
+    n = B * (OH + 2) * (OH + 2) * co
+    buf = torch.full((guard + n + guard,), 7.0, dtype=torch.bfloat16, device='cuda')
+    out = Act(buf[guard:guard + n].view(B, OH + 2, OH + 2, co), B, OH, OH, co, 1, 1)
+    eng.gemm_down(_act(x, 1, torch.bfloat16, 2), conv_form(w.cuda(), torch.bfloat16), None, 4, 2, 1, co, out=out)
+    torch.cuda.synchronize()
+    assert (_to_nchw(out, 2) - ref).abs().max() <= 1.5e-2 * ref.abs().max()
+    assert bool((buf[:guard] == 7.0).all()) and bool((buf[guard + n:] == 7.0).all())
+    full = out.t.clone()
+    full[:, 1:1 + OH, 1:1 + OH, :] = 7.0
+    assert bool((full == 7.0).all())          # the zero border of the output tensor was not touched

@@ -1,0 +1,18 @@
+#!/bin/bash
+# 2-GPU call: DP parity tests (fused exchange, bucketed overlap), weak-scaling bench with dp_check, BASELINE config 3 @ 2 GPUs
+mkdir -p gpurun_out
+N=${1:-2}
+timeout 600 python -m pytest tests/test_gpu_dp.py -q -x > gpurun_out/r2_dp_pytest_n$N.log 2>&1; echo "dp pytest exit $?" >> gpurun_out/r2_dp_pytest_n$N.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+DP_PEER_TIME=1 timeout 300 $TR --master-port 29511 tests/dp_peer_check.py > gpurun_out/r2_dp_peer_time_n$N.log 2>&1
+timeout 600 $TR --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_weak_n$N.log 2> gpurun_out/r2_bench_weak_n$N.err; echo "exit $?" >> gpurun_out/r2_bench_weak_n$N.err
+MOPOE_DP_BUCKETS=0 timeout 600 $TR --master-port 29513 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_weak_nobuckets_n$N.log 2> gpurun_out/r2_bench_weak_nobuckets_n$N.err
+timeout 600 $TR --master-port 29514 bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline --scaling strong --global-batch 2048 > gpurun_out/r2_bench_cfg3_n$N.log 2> gpurun_out/r2_bench_cfg3_n$N.err; echo "exit $?" >> gpurun_out/r2_bench_cfg3_n$N.err
+tail -n 4 gpurun_out/r2_dp_pytest_n$N.log gpurun_out/r2_dp_peer_time_n$N.log gpurun_out/r2_bench_weak_n$N.err gpurun_out/r2_bench_cfg3_n$N.err
+for f in r2_bench_weak_n$N r2_bench_weak_nobuckets_n$N r2_bench_cfg3_n$N; do python - <<PY
+import json
+for l in open('gpurun_out/$f.log'):
+    if l.startswith('{'):
+        d=json.loads(l); print('$f', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), d.get('dp_check'))
+PY
+done
