@@ -372,6 +372,8 @@ def main():
     dp_check = None
     if world > 1 and peer and not args.no_dp_check:
         dp_check = run_dp_check(exp, px_obj, world, rank, dev)
+    # (the instrumented copy stops after backward at N > 1: no bucket of the gradient exchange may be forked from it)
+    saved_hook, vae.rt.on_decoders_done = vae.rt.on_decoders_done, None
     if not args.no_graph:
         try:
             L.PROFILE, L.PROFILE_EXTERNAL = [], True
@@ -413,6 +415,7 @@ def main():
         finally:
             prof, L.PROFILE = L.PROFILE, None
         timing = 'CUDA event pairs around eager launches (includes host enqueue latency)'
+    vae.rt.on_decoders_done = saved_hook
     for p_ in prof:
         p_['ms'] = p_['a'].elapsed_time(p_['b'])
     t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
