@@ -127,7 +127,8 @@ class FlatAdam:
         the decoders, so poe keeps the single exchange.  MOPOE_DP_BUCKETS=0 disables it."""
         import os
         ex, model = self.exchange, self.model
-        if ex is None or os.environ.get('MOPOE_DP_BUCKETS', '1') == '0' or getattr(model, 'method', None) == 'poe':
+        self.cut = None
+        if os.environ.get('MOPOE_DP_BUCKETS', '1') == '0' or getattr(model, 'method', None) == 'poe' or not self.p.is_cuda:
             return
         offs = getattr(model, 'flat_offsets', None)
         if not offs:
@@ -137,7 +138,9 @@ class FlatAdam:
         if not dec or not enc or max(enc) > min(dec):
             return
         cut = min(dec)
-        ex.set_buckets([(cut, self.p.numel()), (0, cut)])          # launch order: decoders first
+        self.cut = cut                                             # single GPU: the same split for the plain Adam kernel
+        if ex is not None:
+            ex.set_buckets([(cut, self.p.numel()), (0, cut)])      # launch order: decoders first
         self._xs = torch.cuda.Stream()
         self.side_blocks = int(os.environ.get('MOPOE_DPX_SIDE_BLOCKS', '64'))
         model.rt.on_decoders_done = self.begin_exchange
@@ -154,7 +157,16 @@ class FlatAdam:
         self._xs.wait_stream(cur)
         with torch.cuda.stream(self._xs):
             self._advance(eng)
-            self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps, bucket=0, max_blocks=self.side_blocks)
+            if self.exchange is not None:
+                self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps, bucket=0, max_blocks=self.side_blocks)
+            else:
+                self._adam_range(self.cut, self.p.numel())
+
+    def _adam_range(self, lo, hi):
+        L.annotate(kind='adam', bytes=28 * (hi - lo))            # p, g, m, v read; p, m, v written (fp32)
+        L.call('mopoe_adam_flat_dev', L.ptr(self.p[lo:hi]), L.ptr(self.g[lo:hi]), L.ptr(self.m[lo:hi]), L.ptr(self.v[lo:hi]),
+               hi - lo, L.ptr(self.coef), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.grad_scale),
+               L.stream_ptr())
 
     @property
     def step_count(self):
@@ -182,11 +194,10 @@ class FlatAdam:
         elif self.exchange is not None:
             # reduce-scatter + Adam + all-gather in one kernel over peer memory; moments of a slice live on its owner
             self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps)
+        elif started:                   # single GPU: the decoders' Adam already ran under the encoders' backward
+            self._adam_range(0, self.cut)
         else:
-            L.annotate(kind='adam', bytes=28 * self.p.numel())       # p, g, m, v read; p, m, v written (fp32)
-            L.call('mopoe_adam_flat_dev', L.ptr(self.p), L.ptr(self.g), L.ptr(self.m), L.ptr(self.v), self.p.numel(),
-                   L.ptr(self.coef), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.grad_scale),
-                   L.stream_ptr())
+            self._adam_range(0, self.p.numel())
         eng.invalidate_packs()      # the kernel rewrote the weights in place: packed copies are stale
 
 
@@ -234,6 +245,11 @@ def attach_allreduce(exp, allreduce):
     if allreduce is None or getattr(allreduce, '_attached_to', None) is exp.optimizer:
         return
     from .dp import broadcast_flat
+    # the gradients are only final after the all-reduce that runs between backward and step(): no part of the optimizer
+    # may start from inside backward (the single-GPU / peer-exchange overlap of FlatAdam)
+    rt = getattr(exp.mm_vae, 'rt', None)
+    if rt is not None:
+        rt.on_decoders_done = None
     exp.optimizer.grad_scale = float(allreduce.grad_scale)
     broadcast_flat(exp.mm_vae.flat_params, 0, getattr(allreduce, 'group', None))
     allreduce._attached_to = exp.optimizer
