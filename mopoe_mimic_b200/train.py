@@ -182,11 +182,12 @@ class FlatAdam:
         # `loss.backward(); optimizer.step()` must therefore join the branches before anything reads flat_grads
         if hasattr(self.model, 'join_branches'):
             self.model.join_branches()
-        if self._advanced:              # bucketed exchange: the decoders' bucket is already in flight on the side stream
+        started = self._advanced        # the decoders' bucket was started from inside backward (begin_exchange)
+        if started:
             torch.cuda.current_stream().wait_stream(self._xs)
         else:
             self._advance(eng)
-        started, self._advanced = self._advanced, False
+        self._advanced = False
         if self.exchange is not None and self.exchange.buckets is not None:
             if not started:             # (a step whose backward did not fire the hook: exchange every bucket here)
                 self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps, bucket=0)

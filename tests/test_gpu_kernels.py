@@ -236,6 +236,37 @@ def test_graphed_step_equals_eager_steps():
     assert losses[0][1] != losses[0][0]
 
 
+@pytest.mark.parametrize('method', ['joint_elbo', 'poe'])
+def test_optimizer_under_backward_equals_the_serial_step(method):
+    """FlatAdam starts the decoders' range from inside backward (side stream, under the encoders' backward) and finishes the
+    encoders' range in step(): the parameters after two steps must be the SAME BITS as with the whole update after backward
+    (hook removed).  poe keeps the serial update (its unimodal passes revisit the decoders) and must simply step."""
+    import mopoe_mimic_b200 as P
+    kw = dict(batch_size=8, DIM_img=16, DIM_text=16, class_dim=32)
+    ofl = O.default_flags(**kw)
+    state = O.make_state(ofl, 0, torch.float32)
+    batch = {k: v.cuda() for k, v in O.make_batch(ofl, 1, torch.float32).items()}
+    finals = []
+    for overlap in (True, False):
+        exp = P.Experiment(P.default_flags(compute_dtype='fp32', initial_learning_rate=1e-4, method=method, **kw))
+        exp.mm_vae.load_state_dict(state)
+        exp.set_optimizer()
+        exp.mm_vae.train()
+        exp.mm_vae.rt.seed = 99
+        exp.mm_vae.rt.injected_eps = torch.zeros(8, 32, device='cuda')
+        assert (exp.mm_vae.rt.on_decoders_done is not None) == (method != 'poe')
+        if not overlap:
+            exp.mm_vae.rt.on_decoders_done = None
+        init = exp.mm_vae.flat_params.clone()
+        for _ in range(2):
+            out = P.train_step(exp, (dict(batch), None))
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(out['total_loss'])) and exp.optimizer.step_count == 2
+        assert not torch.equal(init, exp.mm_vae.flat_params)
+        finals.append(exp.mm_vae.flat_params.clone())
+    assert torch.equal(finals[0], finals[1])
+
+
 def test_full_size_bf16_step_is_bitwise_reproducible():
     """BASELINE config 2 at its full size (tri-modal, 128 px, batch 256, bf16): every reduction in the step is a fixed-
     order two-stage sum (no atomics), so two runs from the same state give the SAME BITS — loss terms, all 153 M
