@@ -205,6 +205,11 @@ int mopoe_deconv3x3s2_c1_fwd(const mopoe_view_t* x, const float* w, const float*
 /* given dout fp32 [B,1,2H,2W]: dx view, dw fp32 [C,1,3,3], dbias[1]. ws: nchunk*(9*C+1) doubles. */
 int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, const float* dout, const mopoe_view_t* dx,
                              float* dw, float* dbias, int accumulate, double* ws, int nchunk, void* stream);
+/* 3x3 / stride-2 / pad-1 patches of a single-channel fp32 image [B, SH, SW] as a bf16 matrix [B*(SH/2)*(SW/2), 16]
+ * (column t = ky*3 + kx, columns 9..15 zero).  The weight gradients of the two single-channel layers are then
+ * mopoe_conv_wgrad launches (activation = window operand, patches = 16-wide row operand); mopoe_deconv3x3s2_c1_bwd accepts
+ * dw = NULL for that case. */
+int mopoe_im2col3x3s2(const float* src, int B, int SH, int SW, void* out_bf16, void* stream);
 
 /* ---- fused MoPoE kernel (north_star item 2) --------------------------------------------------------
  * BaseMMVae.inference (utils/BaseMMVae.py:139-196) + poe (mm_div.py:10-17) + mixture_component_selection

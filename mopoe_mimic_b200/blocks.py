@@ -261,6 +261,25 @@ class ResBlockFn(torch.autograd.Function):
 
 
 # ---- stems and heads ------------------------------------------------------------------------------------------
+def _tc_taps(eng, act):
+    """the tap gradients of the single-channel layers run as tcgen05 weight-gradient GEMMs in bf16 mode"""
+    import os
+    return (act.dtype == torch.bfloat16 and eng.impl != L.IMPL_SIMT and act.C % 64 == 0
+            and os.environ.get('MOPOE_TC_TAPS', '1') != '0')
+
+
+def _tap_grad_tc(eng, img, B, SH, SW, act):
+    """dW[c, t] = sum_m act[m, c] * patches(img)[m, t]: the 3x3/s2 patches of the fp32 image [B, SH, SW] as a bf16 [M, 16]
+    matrix (mopoe_im2col3x3s2), then ONE weight-gradient GEMM with the 128-channel activation as the window operand.
+    Returns [C, 9] fp32."""
+    OH, OW = SH // 2, SW // 2
+    pt = torch.empty(B * OH * OW, 16, dtype=torch.bfloat16, device=eng.device)
+    L.call('mopoe_im2col3x3s2', L.ptr(img), B, SH, SW, L.ptr(pt), L.stream_ptr())
+    g = eng.wgrad_rows(act, Act(pt, B, OH, OW, 16, 0, 0))          # [16, C]
+    return g[:9].t().contiguous()
+
+
+
 class ImgStemFn(torch.autograd.Function):
     """nn.Conv2d(1, C, 3, 2, 1, bias=False) on the NCHW fp32 image (FeatureExtractorImg.py:29-34, :72)."""
 
@@ -282,6 +301,8 @@ class ImgStemFn(torch.autograd.Function):
         B, _, H, W = x.shape
         Cc = w.shape[0]
         dy = Act.like(dy_t.contiguous(), B, H // 2, W // 2, Cc, ctx.out_pad, ctx.out_pad)
+        if _tc_taps(eng, dy):
+            return None, _tap_grad_tc(eng, x, B, H, W, dy).view_as(w), None, None
         nc = eng.nchunk(B * (H // 2) * (W // 2), Cc)
         ws = eng.ws64(nc * 9 * Cc)
         dw = eng.f32(*w.shape)
@@ -316,9 +337,14 @@ class ImgLastFn(torch.autograd.Function):
         dx = Act.empty(B, H, W, Cc, 0, 0, x_t.dtype, eng.device)
         nc = eng.nchunk(B * H * W, Cc)
         ws = eng.ws64(nc * (9 * Cc + 1))
-        dw, db = eng.f32(*w.shape), eng.f32(1)
-        L.call('mopoe_deconv3x3s2_c1_bwd', C.byref(x.view()), L.ptr(w), L.ptr(dout.contiguous()), C.byref(dx.view()),
+        db = eng.f32(1)
+        dout = dout.contiguous()
+        tc = _tc_taps(eng, x)
+        dw = None if tc else eng.f32(*w.shape)
+        L.call('mopoe_deconv3x3s2_c1_bwd', C.byref(x.view()), L.ptr(w), L.ptr(dout), C.byref(dx.view()),
                L.ptr(dw), L.ptr(db), 0, L.ptr(ws), nc, L.stream_ptr())
+        if tc:
+            dw = _tap_grad_tc(eng, dout, B, 2 * H, 2 * W, x).view_as(w)
         return dx.t.view_as(x_t), dw, db, None, None, None, None
 
 

@@ -549,15 +549,58 @@ extern "C" int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, c
     MOPOE_DISPATCH_T(x->dtype, T, {
         deconv3x3s2_c1_dx_kernel<T><<<(unsigned)min((long long)ceil_div64(total, 256), 148ll * 16), 256, 9 * x->C * sizeof(float), st>>>(
             dout, w, make_dview<T>(dx), total);
-        tap_grad_kernel<T, false><<<grid, block, 0, st>>>(make_dview<const T>(x), dout, 2 * x->H, 2 * x->W, ws, nchunk);
+        if (dw) tap_grad_kernel<T, false><<<grid, block, 0, st>>>(make_dview<const T>(x), dout, 2 * x->H, 2 * x->W, ws, nchunk);
     });
     MOPOE_CHECK_LAUNCH("deconv3x3s2_c1_bwd");
-    tap_finalize_kernel<<<(x->C * 9 + 7) / 8, 256, 0, st>>>(ws, nchunk, 9, x->C, dw, accumulate);
-    MOPOE_CHECK_LAUNCH("tap_finalize");
+    if (dw) {          // (NULL: the caller forms the tap gradient as a tcgen05 weight-gradient GEMM over mopoe_im2col3x3s2)
+        tap_finalize_kernel<<<(x->C * 9 + 7) / 8, 256, 0, st>>>(ws, nchunk, 9, x->C, dw, accumulate);
+        MOPOE_CHECK_LAUNCH("tap_finalize");
+    }
     double* part = ws + (long long)nchunk * 9 * x->C;
     long long n = (long long)x->B * 4 * x->H * x->W;
     sum_partial_kernel<<<nchunk, 256, 0, st>>>(dout, n, part);
     sum_final_kernel<<<1, 32, 0, st>>>(part, nchunk, dbias, accumulate);
     MOPOE_CHECK_LAUNCH("dbias");
+    return 0;
+}
+
+// ---- 3x3 / stride-2 / pad-1 patches of a single-channel image as a 16-column bf16 matrix ------------------------------
+// out[(b, oy, ox)][t = ky*3 + kx] = src[b, 2*oy - 1 + ky, 2*ox - 1 + kx]  (0 outside the image, 0 for t >= 9).
+// With it the two single-channel weight gradients are ordinary weight-gradient GEMMs on the tensor cores:
+//   first conv  (FeatureExtractorImg.py:29-34):  dW[c, t] = sum_m dY[m, c] * patches(x)[m, t]
+//   last deconv (DataGeneratorImg.py:84-90):      dW[c, t] = sum_m  X[m, c] * patches(dOut)[m, t]
+// i.e. mopoe_conv_wgrad with the 128-channel activation as the window operand and the patches as the 16-wide row operand —
+// one streaming read of the activation at tensor-core speed instead of the register-blocked CUDA-core reduction
+// (tap_grad_kernel: 235 us per launch against a 45 us HBM floor).
+__global__ void __launch_bounds__(256) im2col3x3s2_kernel(const float* __restrict__ src, int SH, int SW, long long pixels,
+                                                          bf16* __restrict__ out) {
+    const int OW = SW / 2, OH = SH / 2;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < pixels; p += (long long)gridDim.x * 256) {
+        const int ox = (int)(p % OW);
+        const long long t2 = p / OW;
+        const int oy = (int)(t2 % OH);
+        const long long b = t2 / OH;
+        float t[9];
+        load_taps(src + b * SH * SW, SW, oy, ox, t);
+        uint4 lo, hi;
+        __nv_bfloat162 h;
+        h = __floats2bfloat162_rn(t[0], t[1]); lo.x = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(t[2], t[3]); lo.y = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(t[4], t[5]); lo.z = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(t[6], t[7]); lo.w = *reinterpret_cast<uint32_t*>(&h);
+        h = __floats2bfloat162_rn(t[8], 0.f); hi.x = *reinterpret_cast<uint32_t*>(&h);
+        hi.y = hi.z = hi.w = 0u;
+        reinterpret_cast<uint4*>(out + p * 16)[0] = lo;
+        reinterpret_cast<uint4*>(out + p * 16)[1] = hi;
+    }
+}
+extern "C" int mopoe_im2col3x3s2(const float* src, int B, int SH, int SW, void* out_bf16, void* stream) {
+    MOPOE_REQUIRE(B > 0 && SH > 0 && SW > 0 && SH % 2 == 0 && SW % 2 == 0, "im2col3x3s2: bad shape [%d,%d,%d]", B, SH, SW);
+    MOPOE_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, "im2col3x3s2: unaligned output");
+    const long long pixels = (long long)B * (SH / 2) * (SW / 2);
+    long long blocks = ceil_div64(pixels, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    im2col3x3s2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, SH, SW, pixels, reinterpret_cast<bf16*>(out_bf16));
+    MOPOE_CHECK_LAUNCH("im2col3x3s2");
     return 0;
 }

@@ -578,7 +578,7 @@ extern "C" int mopoe_tc_wgrad_built(void) { return 1; }
 int mopoe_tc_wgrad_eligible(const mopoe_window_t* A, const mopoe_rows_t* dY) {
     if (!tc_init()) return 0;
     if (A->a_dtype != MOPOE_BF16 || dY->d_dtype != MOPOE_BF16) return 0;
-    if (A->KW % 64 != 0 || dY->N < 64 || dY->N % 8 != 0) return 0;
+    if (A->KW % 64 != 0 || dY->N < 16 || dY->N % 8 != 0) return 0;     // (narrow dY: TMA zero-fills the rest of the 128-row tile)
     if ((A->sA0 % 8) || (A->sA1 % 8) || (A->sA2 % 8) || (A->sAr % 8) || (A->a_off % 8)) return 0;
     if ((dY->s0 % 8) || (dY->s1 % 8) || (dY->s2 % 8) || (dY->d_off % 8)) return 0;
     if ((reinterpret_cast<uintptr_t>(A->a) & 15) || (reinterpret_cast<uintptr_t>(dY->d) & 15)) return 0;
@@ -630,7 +630,9 @@ static void wg_plan(const mopoe_window_t* A, const mopoe_rows_t* dY, TcWgParams&
         const double t_kb = 0.14 * (double)(p.BNJ / 64) + 0.05, t_item = 0.6;
         double best_t = 1e30;
         Z = 1;
-        for (int z = 1; z <= 64 && z <= p.TM; ++z) {
+        // few output tiles (the 16 x 128 tap gradients of the single-channel layers): allow one split per SM
+        const int zmax = tiles_out <= 2 ? 148 : 64;
+        for (int z = 1; z <= zmax && z <= p.TM; ++z) {
             const int mps = (p.TM + z - 1) / z;
             const int zz = (p.TM + mps - 1) / mps;
             if (zz != z) continue;
