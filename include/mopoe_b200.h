@@ -208,8 +208,16 @@ int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, const float*
 /* 3x3 / stride-2 / pad-1 patches of a single-channel fp32 image [B, SH, SW] as a bf16 matrix [B*(SH/2)*(SW/2), 16]
  * (column t = ky*3 + kx, columns 9..15 zero).  The weight gradients of the two single-channel layers are then
  * mopoe_conv_wgrad launches (activation = window operand, patches = 16-wide row operand); mopoe_deconv3x3s2_c1_bwd accepts
- * dw = NULL for that case. */
-int mopoe_im2col3x3s2(const float* src, int B, int SH, int SW, void* out_bf16, void* stream);
+ * dw = NULL and dx = NULL for these cases. */
+int mopoe_im2col3x3s2(const float* src, int B, int SH, int SW, int cols, void* out_bf16, void* stream);
+/* (cols: 16, or 64 = one k-block of the tcgen05 GEMMs — the patches are then also the A operand of the layer itself:
+ * first conv forward and last deconv input gradient are out[m, c] = sum_t patches[m, t] * w[c, t], mopoe_conv_gemm launches.)
+ * The last deconv's forward as a GEMM: taps[m, t] = sum_c x[m, c] * w[c, t] (16 zero-padded filter rows, fp32 [M, stride])
+ * followed by the assembly of the 2x2 output quads (+ bias): */
+int mopoe_deconv3x3s2_c1_assemble(const float* taps, int stride, const float* bias, float* out, int B, int H, int W,
+                                  void* stream);
+/* zero the border of a bordered channels-last activation whose producer wrote only the interior (a GEMM) */
+int mopoe_zero_border(const mopoe_view_t* v, void* stream);
 
 /* ---- fused MoPoE kernel (north_star item 2) --------------------------------------------------------
  * BaseMMVae.inference (utils/BaseMMVae.py:139-196) + poe (mm_div.py:10-17) + mixture_component_selection

@@ -90,7 +90,9 @@ SIGNATURES = {
     'mopoe_deconv3x3s2_c1_fwd_ws': (_S, [_V]),
     'mopoe_deconv3x3s2_c1_fwd': (_I, [_V, _P, _P, _P, _P, _S, _P]),
     'mopoe_deconv3x3s2_c1_bwd': (_I, [_V, _P, _P, _V, _P, _P, _I, _P, _I, _P]),
-    'mopoe_im2col3x3s2': (_I, [_P, _I, _I, _I, _P, _P]),
+    'mopoe_im2col3x3s2': (_I, [_P, _I, _I, _I, _I, _P, _P]),
+    'mopoe_deconv3x3s2_c1_assemble': (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
+    'mopoe_zero_border': (_I, [_V, _P]),
     'mopoe_fusion_fwd': (_I, [C.POINTER(FusionCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mopoe_fusion_bwd': (_I, [C.POINTER(FusionCfg), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'mopoe_laplace_logprob_sum': (_I, [_P, _P, _L, _F, _P, _P, _I, _P]),

@@ -268,20 +268,26 @@ def _tc_taps(eng, act):
             and os.environ.get('MOPOE_TC_TAPS', '1') != '0')
 
 
-def _tap_grad_tc(eng, img, B, SH, SW, act):
-    """dW[c, t] = sum_m act[m, c] * patches(img)[m, t]: the 3x3/s2 patches of the fp32 image [B, SH, SW] as a bf16 [M, 16]
-    matrix (mopoe_im2col3x3s2), then ONE weight-gradient GEMM with the 128-channel activation as the window operand.
-    Returns [C, 9] fp32."""
-    OH, OW = SH // 2, SW // 2
-    pt = torch.empty(B * OH * OW, 16, dtype=torch.bfloat16, device=eng.device)
-    L.call('mopoe_im2col3x3s2', L.ptr(img), B, SH, SW, L.ptr(pt), L.stream_ptr())
-    g = eng.wgrad_rows(act, Act(pt, B, OH, OW, 16, 0, 0))          # [16, C]
+PATCH_COLS = 64        # 9 taps zero-padded to one 64-element k-block of the tcgen05 GEMMs
+
+
+def _patches(eng, img, B, SH, SW):
+    """3x3 / stride-2 / pad-1 patches of the fp32 image [B, SH, SW] as a bf16 activation [B, SH/2, SW/2, 64] (columns 9.. zero)"""
+    pt = torch.empty(B * (SH // 2) * (SW // 2), PATCH_COLS, dtype=torch.bfloat16, device=eng.device)
+    L.call('mopoe_im2col3x3s2', L.ptr(img), B, SH, SW, PATCH_COLS, L.ptr(pt), L.stream_ptr())
+    return Act(pt, B, SH // 2, SW // 2, PATCH_COLS, 0, 0)
+
+
+def _tap_grad_tc(eng, patches, act):
+    """dW[c, t] = sum_m act[m, c] * patches[m, t]: ONE weight-gradient GEMM with the 128-channel activation as the window
+    operand and the first 16 patch columns as the row operand.  Returns [C, 9] fp32."""
+    g = eng.wgrad_rows(act, patches, n=16)          # [16, C]
     return g[:9].t().contiguous()
 
 
-
 class ImgStemFn(torch.autograd.Function):
-    """nn.Conv2d(1, C, 3, 2, 1, bias=False) on the NCHW fp32 image (FeatureExtractorImg.py:29-34, :72)."""
+    """nn.Conv2d(1, C, 3, 2, 1, bias=False) on the NCHW fp32 image (FeatureExtractorImg.py:29-34, :72).  bf16 mode: the
+    3x3 patches become a [M, 64] bf16 operand and the layer — forward and weight gradient — runs on the tensor cores."""
 
     @staticmethod
     def forward(ctx, x, w, eng, out_pad):
@@ -289,20 +295,29 @@ class ImgStemFn(torch.autograd.Function):
         Cc = w.shape[0]
         x = x.contiguous().float()
         y = Act.empty(B, H // 2, W // 2, Cc, out_pad, out_pad, eng.dtype, eng.device)
-        L.call('mopoe_conv3x3s2_c1_fwd', L.ptr(x), L.ptr(w), B, H, W, C.byref(y.view()), L.stream_ptr())
-        ctx.save_for_backward(x, w)
-        ctx.eng, ctx.out_pad = eng, out_pad
+        if _tc_taps(eng, y):
+            pt = _patches(eng, x, B, H, W)
+            eng.zero_border(y)
+            eng.gemm_rows(pt, eng.packed(w.view(Cc, 9), 'mat', bpad=PATCH_COLS), None, Cc, out=y)
+            ctx.save_for_backward(pt.t, w)
+            ctx.tc = True
+        else:
+            L.call('mopoe_conv3x3s2_c1_fwd', L.ptr(x), L.ptr(w), B, H, W, C.byref(y.view()), L.stream_ptr())
+            ctx.save_for_backward(x, w)
+            ctx.tc = False
+        ctx.eng, ctx.out_pad, ctx.geo = eng, out_pad, (B, H, W)
         return y.t
 
     @staticmethod
     def backward(ctx, dy_t):
         x, w = ctx.saved_tensors
         eng = ctx.eng
-        B, _, H, W = x.shape
+        B, H, W = ctx.geo
         Cc = w.shape[0]
         dy = Act.like(dy_t.contiguous(), B, H // 2, W // 2, Cc, ctx.out_pad, ctx.out_pad)
-        if _tc_taps(eng, dy):
-            return None, _tap_grad_tc(eng, x, B, H, W, dy).view_as(w), None, None
+        if ctx.tc:
+            pt = Act(x, B, H // 2, W // 2, PATCH_COLS, 0, 0)
+            return None, _tap_grad_tc(eng, pt, dy).view_as(w), None, None
         nc = eng.nchunk(B * (H // 2) * (W // 2), Cc)
         ws = eng.ws64(nc * 9 * Cc)
         dw = eng.f32(*w.shape)
@@ -312,17 +327,23 @@ class ImgStemFn(torch.autograd.Function):
 
 
 class ImgLastFn(torch.autograd.Function):
-    """nn.ConvTranspose2d(C, 1, 3, 2, 1, output_padding=1) -> fp32 NCHW loc (DataGeneratorImg.py:84-90)."""
+    """nn.ConvTranspose2d(C, 1, 3, 2, 1, output_padding=1) -> fp32 NCHW loc (DataGeneratorImg.py:84-90).  bf16 mode: the
+    9 tap products per input pixel are a [M, C] x [C, 16] GEMM (then the 2x2 quads are assembled); the input gradient is
+    patches(dout) [M, 64] x [64, C] and the weight gradient a 16-wide wgrad — all three on the tensor cores."""
 
     @staticmethod
     def forward(ctx, x_t, w, bias, eng, B, H, W):
         Cc = w.shape[0]
         x = Act.like(x_t, B, H, W, Cc)
         out = eng.f32(B, 1, 2 * H, 2 * W)
-        nbytes = L.load().mopoe_deconv3x3s2_c1_fwd_ws(C.byref(x.view()))
-        ws = eng.wsf(nbytes)
-        L.call('mopoe_deconv3x3s2_c1_fwd', C.byref(x.view()), L.ptr(w), L.ptr(bias), L.ptr(out), L.ptr(ws), nbytes,
-               L.stream_ptr())
+        if _tc_taps(eng, x):
+            taps = eng.gemm_rows(x, eng.packed(w.view(Cc, 9), 'matT', bpad=16), None, 16, out_dtype=torch.float32)
+            L.call('mopoe_deconv3x3s2_c1_assemble', L.ptr(taps.t), 16, L.ptr(bias), L.ptr(out), B, H, W, L.stream_ptr())
+        else:
+            nbytes = L.load().mopoe_deconv3x3s2_c1_fwd_ws(C.byref(x.view()))
+            ws = eng.wsf(nbytes)
+            L.call('mopoe_deconv3x3s2_c1_fwd', C.byref(x.view()), L.ptr(w), L.ptr(bias), L.ptr(out), L.ptr(ws), nbytes,
+                   L.stream_ptr())
         ctx.save_for_backward(x_t, w)
         ctx.eng, ctx.geo = eng, (B, H, W)
         return out
@@ -334,17 +355,21 @@ class ImgLastFn(torch.autograd.Function):
         B, H, W = ctx.geo
         Cc = w.shape[0]
         x = Act.like(x_t, B, H, W, Cc)
-        dx = Act.empty(B, H, W, Cc, 0, 0, x_t.dtype, eng.device)
         nc = eng.nchunk(B * H * W, Cc)
         ws = eng.ws64(nc * (9 * Cc + 1))
         db = eng.f32(1)
         dout = dout.contiguous()
-        tc = _tc_taps(eng, x)
-        dw = None if tc else eng.f32(*w.shape)
-        L.call('mopoe_deconv3x3s2_c1_bwd', C.byref(x.view()), L.ptr(w), L.ptr(dout), C.byref(dx.view()),
-               L.ptr(dw), L.ptr(db), 0, L.ptr(ws), nc, L.stream_ptr())
-        if tc:
-            dw = _tap_grad_tc(eng, dout, B, 2 * H, 2 * W, x).view_as(w)
+        if _tc_taps(eng, x):
+            pt = _patches(eng, dout, B, 2 * H, 2 * W)
+            dx = eng.gemm_rows(pt, eng.packed(w.view(Cc, 9), 'mat', bpad=PATCH_COLS), None, Cc)
+            dw = _tap_grad_tc(eng, pt, x).view_as(w)
+            L.call('mopoe_deconv3x3s2_c1_bwd', C.byref(x.view()), L.ptr(w), L.ptr(dout), None, None, L.ptr(db), 0,
+                   L.ptr(ws), nc, L.stream_ptr())                    # (only the bias gradient is left to this call)
+        else:
+            dx = Act.empty(B, H, W, Cc, 0, 0, x_t.dtype, eng.device)
+            dw = eng.f32(*w.shape)
+            L.call('mopoe_deconv3x3s2_c1_bwd', C.byref(x.view()), L.ptr(w), L.ptr(dout), C.byref(dx.view()),
+                   L.ptr(dw), L.ptr(db), 0, L.ptr(ws), nc, L.stream_ptr())
         return dx.t.view_as(x_t), dw, db, None, None, None, None
 
 

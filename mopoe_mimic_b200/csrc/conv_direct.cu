@@ -415,7 +415,8 @@ __global__ void __launch_bounds__(128) deconv_taps_kernel(DView<const T> x, cons
 // out(2t,2s) = p11(t,s);  out(2t,2s+1) = p12(t,s) + p10(t,s+1);  out(2t+1,2s) = p21(t,s) + p01(t+1,s);
 // out(2t+1,2s+1) = p22(t,s) + p20(t,s+1) + p02(t+1,s) + p00(t+1,s+1)        (p_kykx = taps[ky*3+kx])
 __global__ void __launch_bounds__(256) deconv_assemble_kernel(const float* __restrict__ taps, const float* __restrict__ bias,
-                                                              float* __restrict__ out, int H, int W, long long quads) {
+                                                              float* __restrict__ out, int H, int W, long long quads,
+                                                              int TS) {                  // TS: floats per pixel in `taps`
     const float bb = bias[0];
     for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < quads; q += (long long)gridDim.x * 256) {
         const int s = (int)(q % W);
@@ -423,15 +424,15 @@ __global__ void __launch_bounds__(256) deconv_assemble_kernel(const float* __res
         const int t = (int)(t2 % H);
         const long long b = t2 / H;
         const bool rs = s + 1 < W, dn = t + 1 < H;
-        const float* p = taps + q * TAPS_STRIDE;
-        const float* pr = p + TAPS_STRIDE;
-        const float* pd = p + (long long)W * TAPS_STRIDE;
+        const float* p = taps + q * TS;
+        const float* pr = p + TS;
+        const float* pd = p + (long long)W * TS;
         const float4 a0 = *reinterpret_cast<const float4*>(p), a1 = *reinterpret_cast<const float4*>(p + 4);
         const float a8 = p[8];
         float o00 = a1.x, o01 = a1.y, o10 = a1.w, o11 = a8;        // p11, p12, p21, p22
         if (rs) { o01 += pr[3]; o11 += pr[6]; }                    // p10, p20 of (t, s+1)
         if (dn) { o10 += pd[1]; o11 += pd[2]; }                    // p01, p02 of (t+1, s)
-        if (rs && dn) o11 += pd[TAPS_STRIDE];                      // p00 of (t+1, s+1)
+        if (rs && dn) o11 += pd[TS];                               // p00 of (t+1, s+1)
         (void)a0;
         const int OW = 2 * W;
         float* ob = out + (b * 2 * H + 2 * t) * OW + 2 * s;
@@ -470,7 +471,20 @@ extern "C" int mopoe_deconv3x3s2_c1_fwd(const mopoe_view_t* x, const float* w, c
     MOPOE_CHECK_LAUNCH("deconv_taps");
     long long b2 = ceil_div64(quads, 256);
     if (b2 > 148 * 16) b2 = 148 * 16;
-    deconv_assemble_kernel<<<(unsigned)b2, 256, 0, st>>>((const float*)ws, bias, out, x->H, x->W, quads);
+    deconv_assemble_kernel<<<(unsigned)b2, 256, 0, st>>>((const float*)ws, bias, out, x->H, x->W, quads, TAPS_STRIDE);
+    MOPOE_CHECK_LAUNCH("deconv_assemble");
+    return 0;
+}
+
+// the assembly half alone: the 9 tap products per input pixel come from a tensor-core GEMM ([M, C] x [C, 16] -> taps
+// [M, stride] fp32, mopoe_conv_gemm with the 16-row zero-padded filter) instead of deconv_taps_kernel
+extern "C" int mopoe_deconv3x3s2_c1_assemble(const float* taps, int stride, const float* bias, float* out, int B, int H, int W,
+                                             void* stream) {
+    MOPOE_REQUIRE(stride >= 9 && stride % 4 == 0 && (reinterpret_cast<uintptr_t>(taps) & 15) == 0, "deconv_assemble: stride=%d", stride);
+    const long long quads = (long long)B * H * W;
+    long long b2 = ceil_div64(quads, 256);
+    if (b2 > 148 * 16) b2 = 148 * 16;
+    deconv_assemble_kernel<<<(unsigned)b2, 256, 0, (cudaStream_t)stream>>>(taps, bias, out, H, W, quads, stride);
     MOPOE_CHECK_LAUNCH("deconv_assemble");
     return 0;
 }
@@ -541,13 +555,14 @@ __global__ void sum_final_kernel(const double* part, int n, float* out, int accu
 }
 extern "C" int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, const float* dout, const mopoe_view_t* dx,
                                         float* dw, float* dbias, int accumulate, double* ws, int nchunk, void* stream) {
-    MOPOE_REQUIRE(x->C % CV8 == 0 && dx->C == x->C && dx->B == x->B && dx->H == x->H && dx->W == x->W &&
-                      dx->dtype == x->dtype, "deconv3x3s2_c1_bwd: bad views");
+    MOPOE_REQUIRE(x->C % CV8 == 0 && (!dx || (dx->C == x->C && dx->B == x->B && dx->H == x->H && dx->W == x->W &&
+                                              dx->dtype == x->dtype)), "deconv3x3s2_c1_bwd: bad views");
     cudaStream_t st = (cudaStream_t)stream;
-    long long total = (long long)dx->B * (dx->H + 2 * dx->ph) * (dx->W + 2 * dx->pw) * (dx->C / CV8);
+    const long long total = dx ? (long long)dx->B * (dx->H + 2 * dx->ph) * (dx->W + 2 * dx->pw) * (dx->C / CV8) : 0;
     dim3 block(16, 16), grid((x->C + 127) / 128, nchunk);
     MOPOE_DISPATCH_T(x->dtype, T, {
-        deconv3x3s2_c1_dx_kernel<T><<<(unsigned)min((long long)ceil_div64(total, 256), 148ll * 16), 256, 9 * x->C * sizeof(float), st>>>(
+        // (dx == NULL: the caller forms it as a tensor-core GEMM over mopoe_im2col3x3s2 patches of dout)
+        if (dx) deconv3x3s2_c1_dx_kernel<T><<<(unsigned)min((long long)ceil_div64(total, 256), 148ll * 16), 256, 9 * x->C * sizeof(float), st>>>(
             dout, w, make_dview<T>(dx), total);
         if (dw) tap_grad_kernel<T, false><<<grid, block, 0, st>>>(make_dview<const T>(x), dout, 2 * x->H, 2 * x->W, ws, nchunk);
     });
@@ -573,7 +588,7 @@ extern "C" int mopoe_deconv3x3s2_c1_bwd(const mopoe_view_t* x, const float* w, c
 // one streaming read of the activation at tensor-core speed instead of the register-blocked CUDA-core reduction
 // (tap_grad_kernel: 235 us per launch against a 45 us HBM floor).
 __global__ void __launch_bounds__(256) im2col3x3s2_kernel(const float* __restrict__ src, int SH, int SW, long long pixels,
-                                                          bf16* __restrict__ out) {
+                                                          int cols, bf16* __restrict__ out) {
     const int OW = SW / 2, OH = SH / 2;
     for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < pixels; p += (long long)gridDim.x * 256) {
         const int ox = (int)(p % OW);
@@ -590,17 +605,20 @@ __global__ void __launch_bounds__(256) im2col3x3s2_kernel(const float* __restric
         h = __floats2bfloat162_rn(t[6], t[7]); lo.w = *reinterpret_cast<uint32_t*>(&h);
         h = __floats2bfloat162_rn(t[8], 0.f); hi.x = *reinterpret_cast<uint32_t*>(&h);
         hi.y = hi.z = hi.w = 0u;
-        reinterpret_cast<uint4*>(out + p * 16)[0] = lo;
-        reinterpret_cast<uint4*>(out + p * 16)[1] = hi;
+        uint4* o = reinterpret_cast<uint4*>(out + p * cols);
+        o[0] = lo;
+        o[1] = hi;
+        for (int k = 2; k < cols / 8; ++k) o[k] = make_uint4(0u, 0u, 0u, 0u);      // K padded to the GEMM's 64-element k-block
     }
 }
-extern "C" int mopoe_im2col3x3s2(const float* src, int B, int SH, int SW, void* out_bf16, void* stream) {
+extern "C" int mopoe_im2col3x3s2(const float* src, int B, int SH, int SW, int cols, void* out_bf16, void* stream) {
     MOPOE_REQUIRE(B > 0 && SH > 0 && SW > 0 && SH % 2 == 0 && SW % 2 == 0, "im2col3x3s2: bad shape [%d,%d,%d]", B, SH, SW);
+    MOPOE_REQUIRE(cols >= 16 && cols % 8 == 0, "im2col3x3s2: cols=%d (>= 16, multiple of 8)", cols);
     MOPOE_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, "im2col3x3s2: unaligned output");
     const long long pixels = (long long)B * (SH / 2) * (SW / 2);
     long long blocks = ceil_div64(pixels, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    im2col3x3s2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, SH, SW, pixels, reinterpret_cast<bf16*>(out_bf16));
+    im2col3x3s2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, SH, SW, pixels, cols, reinterpret_cast<bf16*>(out_bf16));
     MOPOE_CHECK_LAUNCH("im2col3x3s2");
     return 0;
 }

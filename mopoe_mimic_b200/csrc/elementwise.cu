@@ -963,6 +963,41 @@ extern "C" int mopoe_scale_mask(const mopoe_view_t* dy, const uint8_t* mask, int
     return 0;
 }
 
+// ---- zero border of a bordered activation (producers that only write the interior: GEMM outputs) ---------------------
+template <typename T>
+__global__ void __launch_bounds__(256) zero_border_kernel(DView<T> o, long long total) {
+    const int Ws = o.W + 2 * o.pw, Hs = o.H + 2 * o.ph;
+    const int CV = o.C / VEC;
+    // border pixels per image: the ph top / bottom rows (full width) + the pw left / right columns of the H middle rows
+    const int per = 2 * o.ph * Ws + 2 * o.pw * o.H;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int cv = (int)(i % CV);
+        const long long q = i / CV;
+        const int k = (int)(q % per);
+        const long long b = q / per;
+        int hs, ws;
+        if (k < o.ph * Ws) { hs = k / Ws; ws = k - hs * Ws; }
+        else if (k < 2 * o.ph * Ws) { const int k2 = k - o.ph * Ws; hs = o.ph + o.H + k2 / Ws; ws = k2 % Ws; }
+        else { const int k2 = k - 2 * o.ph * Ws; hs = o.ph + k2 / (2 * o.pw); const int j = k2 % (2 * o.pw); ws = j < o.pw ? j : o.W + j; }
+        const float z[VEC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        st8v<T>(o.p + b * o.sB + (long long)(hs - o.ph) * o.sH + (long long)(ws - o.pw) * o.sW + cv * VEC, z);
+        (void)Hs;
+    }
+}
+extern "C" int mopoe_zero_border(const mopoe_view_t* v, void* stream) {
+    MOPOE_REQUIRE(v->C % VEC == 0, "zero_border: C=%d", v->C);
+    if (v->ph == 0 && v->pw == 0) return 0;
+    const long long per = 2ll * v->ph * (v->W + 2 * v->pw) + 2ll * v->pw * v->H;
+    const long long total = (long long)v->B * per * (v->C / VEC);
+    long long blocks = ceil_div64(total, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    MOPOE_DISPATCH_T(v->dtype, T, {
+        zero_border_kernel<T><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(make_dview<T>(v), total);
+    });
+    MOPOE_CHECK_LAUNCH("zero_border");
+    return 0;
+}
+
 // ---- layout / dtype conversion ------------------------------------------------------------------------
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(EW_THREADS) convert_kernel(DView<const TS> s, int src_nchw, DView<TD> d,

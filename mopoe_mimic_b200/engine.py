@@ -100,7 +100,8 @@ class Engine:
         if fcode == 2:
             return [(KH * KW * B, A)]
         assert KH == 1 and KW == 1
-        return [(A, B)] if fcode == 3 else [(B, A)]
+        # (bpad: zero-padded k-columns of a 'mat' operand / zero-padded rows of a 'matT' operand)
+        return [(A, bpad)] if fcode == 3 else [(max(B, bpad), A)]
 
     def packed(self, Wg, form, bpad=None):
         """GEMM-operand re-layout of an fp32 master weight, cached until the weights change"""
@@ -115,7 +116,8 @@ class Engine:
             KH, KW = (1, 1) if W.dim() == 2 else ((1, W.shape[2]) if W.dim() == 3 else (W.shape[2], W.shape[3]))
             fcode = self.FORMS[form]
             bp = bpad or B
-            dsts = [torch.empty(sh, dtype=self.dtype, device=self.device) for sh in self._slot_shapes(fcode, A, B, KH, KW, bp)]
+            alloc = torch.zeros if (fcode == 4 and bp > B) else torch.empty      # (padded matT rows are never written: stay 0)
+            dsts = [alloc(sh, dtype=self.dtype, device=self.device) for sh in self._slot_shapes(fcode, A, B, KH, KW, bp)]
             slot = {'W': Wg, 'dsts': dsts, 'out': dsts if fcode == 1 else dsts[0], 'geo': (A, B, KH, KW, fcode, bp),
                     'arr': (C.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts]), 'gen': -1, 'version': -1}
             self._packs[skey] = slot
@@ -466,19 +468,26 @@ class Engine:
         self._gemm_batched(wins, wps, None, rows_l)
         return out
 
-    def gemm_rows(self, x, w, bias, n, out_shape=None, out_dtype=None, bn=None):
-        """pointwise GEMM over the interior pixels of x: out[m, n] = sum_c x[m, c] w[n, c] (+bias)"""
+    def gemm_rows(self, x, w, bias, n, out_shape=None, out_dtype=None, bn=None, out=None):
+        """pointwise GEMM over the interior pixels of x: out[m, n] = sum_c x[m, c] w[n, c] (+bias).  out: an existing
+        (possibly bordered) activation to write the interior of."""
         Cc = x.C
-        if x.ph == 0 and x.pw == 0:
+        flat = x.ph == 0 and x.pw == 0 and (out is None or (out.ph == 0 and out.pw == 0))
+        if flat:
             win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.B * x.H * x.W, 1, 1, 1, Cc, 0, 0, Cc, 0, 0, 0)
         else:
             win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 1, Cc, 0, x.origin(), Cc,
                            x.Ws * Cc, x.Hs * x.Ws * Cc, 0)
         B, H, W = out_shape[:3] if out_shape else (x.B, x.H, x.W)
         nn_ = out_shape[3] if out_shape else n
-        out = Act.empty(B, H, W, nn_, 0, 0, out_dtype or x.dtype, self.device)
-        if x.ph == 0 and x.pw == 0:
+        if out is None:
+            out = Act.empty(B, H, W, nn_, 0, 0, out_dtype or x.dtype, self.device)
+        else:
+            assert out_shape is None and (out.B, out.H, out.W, out.C) == (x.B, x.H, x.W, n)
+        if flat:
             rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, 0, n, 0, 0)
+        elif out.ph or out.pw:
+            rows = self.rows_of(out)
         else:
             rows = L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, 0, n, x.W * n, x.H * x.W * n)
         assert bn is None or out_shape is None, 'fused statistics need GEMM columns == output channels'
@@ -494,13 +503,17 @@ class Engine:
         assert (x.B, x.H, x.W) == (dy.B, dy.H, dy.W) and tuple(param.shape[:2]) == (dy.C, Cc)
         return self._wgrad_param(win, self.rows_of(dy), param, 1, Cc)
 
-    def wgrad_rows(self, x, dy):
-        """dW[n, c] = sum_m dy[m, n] x[m, c] over interior pixels (both any padding)"""
+    def wgrad_rows(self, x, dy, n=None):
+        """dW[n, c] = sum_m dy[m, n] x[m, c] over interior pixels (both any padding); n: only the first n columns of dy"""
         Cc = x.C
         win = L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 1, Cc, 0, x.origin(), Cc,
                        x.Ws * Cc, x.Hs * x.Ws * Cc, 0)
         assert (x.B, x.H, x.W) == (dy.B, dy.H, dy.W)
-        return self._wgrad(win, self.rows_of(dy), dy.C, Cc)
+        return self._wgrad(win, self.rows_of(dy, N=n), n or dy.C, Cc)
+
+    def zero_border(self, act):
+        L.call('mopoe_zero_border', C.byref(act.view()), L.stream_ptr())
+        return act
 
 
 # ---- weight packing (tiny torch re-layouts of the fp32 master weights) ------------------------------------
