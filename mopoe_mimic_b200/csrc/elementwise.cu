@@ -97,6 +97,14 @@ __device__ __forceinline__ void ldmask8(const uint8_t* m, int mode, int bc_idx, 
     }
 }
 
+__device__ __forceinline__ void mask8(const uint2& t, float (&o)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o[i] = ((t.x >> (8 * i)) & 0xffu) ? 2.f : 0.f;
+        o[4 + i] = ((t.y >> (8 * i)) & 0xffu) ? 2.f : 0.f;
+    }
+}
+
 // y = v * sc + sh  ==  gamma * (v - mean) * invstd + beta.  ONE definition shared by the forward apply kernel and
 // the backward kernels that RECOMPUTE the ReLU gate from x instead of re-reading the activation: identical
 // instruction sequence -> bit-identical sign decisions.
@@ -170,6 +178,12 @@ __device__ __forceinline__ Pos decode_pixel(const DView<T>& o, unsigned pos, int
 // block = (16 channel-octet lanes, 16 row lanes); grid = (ceil(C/128), nchunk)
 enum { RED_STATS = 0, RED_BNBWD = 1, RED_COLSUM = 2 };
 constexpr int RED_ROWS = 16;
+#ifndef RED_U_BWD
+#define RED_U_BWD 4
+#endif
+#ifndef RED_U_ONE
+#define RED_U_ONE 4
+#endif
 
 // Fused finalize: the LAST block of a channel group to finish (a self-resetting arrival counter) sums the per-chunk
 // partials in a FIXED lane-strided order — so which block happens to be last does not change a single bit — and
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(DView<const T> x, DVie
         ld8f(invstd + c, is);
     }
     if (cvalid) {
-        constexpr int U = 4;                  // row groups in flight per thread
+        constexpr int U = MODE == RED_BNBWD ? RED_U_BWD : RED_U_ONE;      // row groups in flight per thread
         for (unsigned rb = blockIdx.y * RED_ROWS + ty; rb < r1; rb += U * gstride) {
             // issue all loads of the U row groups first (kept PACKED: 4 registers per bf16 octet), unpack at use
             Raw8<T> xr[U], gr[U], tr[U];
@@ -483,6 +497,313 @@ extern "C" int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* g
     return 0;
 }
 
+// =====================================================================================================================
+// Row-wise streaming passes (default; MOPOE_EW_ROWS=0 selects the per-octet kernels below).
+//
+// ncu of the per-octet kernels (profiles/r2_ncu_elementwise.txt): ~125 instructions and ONE 16-byte load in flight per
+// thread and item, 1.2 eligible warps per scheduler, 66 % of the cycles stalled on that load -> 4.3 TB/s where a plain
+// copy moves 6.2.  Here a thread owns one octet COLUMN (8 channels of one pixel column of the storage row) of U
+// consecutive storage rows of the output: the (batch, row) decode is one division per row, the column / channel decode
+// one per thread, the per-channel coefficients are loaded once per thread, and all U x (operands) 16-byte loads are
+// issued before the first use.
+struct RowGeo {
+    unsigned NRG, RS, RO;          // row groups, storage rows (B * Hs), octets per storage row (Ws * C/8)
+    int Hs, H, ph, o_lo, o_hi, W;  // interior octets of a row: [o_lo, o_hi)
+    FastDiv fRO, fHs, fCV;
+};
+static int make_rowgeo(const mopoe_view_t* out, int U, RowGeo& g, unsigned& blocks) {
+    const int CV = out->C / VEC;
+    g.Hs = out->H + 2 * out->ph;
+    g.H = out->H; g.ph = out->ph; g.W = out->W;
+    g.RS = (unsigned)out->B * g.Hs;
+    g.RO = (unsigned)(out->W + 2 * out->pw) * CV;
+    g.o_lo = out->pw * CV;
+    g.o_hi = (out->pw + out->W) * CV;
+    g.NRG = (g.RS + U - 1) / U;
+    g.fRO = FastDiv(g.RO); g.fHs = FastDiv((unsigned)g.Hs); g.fCV = FastDiv((unsigned)CV);
+    const long long threads = (long long)g.NRG * g.RO;
+    MOPOE_REQUIRE(threads > 0 && threads < (1ll << 31), "elementwise: %lld work items do not fit 32-bit indexing", threads);
+    blocks = (unsigned)ceil_div64(threads, EW_THREADS);
+    return 0;
+}
+static bool rows_ok(const mopoe_view_t* v) { return v->sW == v->C && v->C % VEC == 0; }
+static int ew_rows() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_EW_ROWS");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+// per-thread decode shared by the row kernels
+struct RowThread {
+    unsigned rg, o;
+    int c, coff;
+    bool col_in;
+};
+__device__ __forceinline__ bool row_thread(const RowGeo& g, RowThread& t) {
+    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
+    g.fRO.divmod(idx, t.rg, t.o);
+    if (t.rg >= g.NRG) return false;
+    unsigned wq, cv;
+    g.fCV.divmod(t.o, wq, cv);
+    t.c = (int)cv * VEC;
+    t.col_in = (int)t.o >= g.o_lo && (int)t.o < g.o_hi;
+    t.coff = ((int)t.o - g.o_lo) * VEC;
+    return true;
+}
+// storage row rs -> (b, h); returns "row exists"
+__device__ __forceinline__ bool row_decode(const RowGeo& g, unsigned rs, int& b, int& h) {
+    unsigned bb, hs;
+    g.fHs.divmod(rs, bb, hs);
+    b = (int)bb;
+    h = (int)hs - g.ph;
+    return rs < g.RS;
+}
+template <typename T>
+__device__ __forceinline__ void store_raw(T* p, const float (&o)[8]) { st8v<T>(p, o); }
+
+template <typename T, int U>
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_rows_kernel(const RowGeo g, DView<const T> x, const uint8_t* mask,
+                                                                   int mask_mode, const float* mean, const float* invstd,
+                                                                   const float* gamma, const float* beta, int relu,
+                                                                   DView<T> out) {
+    RowThread t;
+    if (!row_thread(g, t)) return;
+    Raw8<T> xr[U];
+    uint2 mr[U];
+    bool valid[U], in[U];
+    int ooff[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        int b, h;
+        valid[u] = row_decode(g, t.rg * U + u, b, h);
+        in[u] = valid[u] && t.col_in && h >= 0 && h < g.H;
+        ooff[u] = b * (int)out.sB + h * (int)out.sH + t.coff;
+        if (in[u]) {
+            xr[u].load(x.p + (b * (int)x.sB + h * (int)x.sH + t.coff));
+            if (mask_mode != MOPOE_MASK_NONE)
+                mr[u] = *reinterpret_cast<const uint2*>(
+                    mask + (mask_mode == MOPOE_MASK_BC ? b * x.C + t.c : (b * g.H + h) * (g.W * x.C) + t.coff));
+        }
+    }
+    float sc[VEC], sh[VEC];
+    {
+        float mu[VEC], is[VEC], ga[VEC], be[VEC];
+        ld8f(mean + t.c, mu); ld8f(invstd + t.c, is); ld8f(gamma + t.c, ga); ld8f(beta + t.c, be);
+        bn_affine(mu, is, ga, be, sc, sh);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+        if (in[u]) {
+            float xv[VEC];
+            xr[u].unpack(xv);
+            if (mask_mode != MOPOE_MASK_NONE) {
+                float mk[VEC];
+                mask8(mr[u], mk);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) xv[i] *= mk[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) xv[i] *= 1.f;
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float y = bn_eval(xv[i], sc[i], sh[i]);
+                o[i] = (relu && y < 0.f) ? 0.f : y;
+            }
+        }
+        st8v<T>(out.p + ooff[u], o);
+    }
+}
+
+template <typename T, int U>
+__global__ void __launch_bounds__(EW_THREADS) combine_rows_kernel(const RowGeo g, DView<const T> r, const float* mean,
+                                                                  const float* invstd, const float* gamma, const float* beta,
+                                                                  DView<const T> cc, const uint8_t* mask, int mask_mode, float a,
+                                                                  float bcoef, DView<T> out) {
+    RowThread t;
+    if (!row_thread(g, t)) return;
+    Raw8<T> rr[U], cr[U];
+    uint2 mr[U];
+    bool valid[U], in[U];
+    int ooff[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        int b, h;
+        valid[u] = row_decode(g, t.rg * U + u, b, h);
+        in[u] = valid[u] && t.col_in && h >= 0 && h < g.H;
+        ooff[u] = b * (int)out.sB + h * (int)out.sH + t.coff;
+        if (in[u]) {
+            rr[u].load(r.p + (b * (int)r.sB + h * (int)r.sH + t.coff));
+            cr[u].load(cc.p + (b * (int)cc.sB + h * (int)cc.sH + t.coff));
+            if (mask_mode != MOPOE_MASK_NONE)
+                mr[u] = *reinterpret_cast<const uint2*>(
+                    mask + (mask_mode == MOPOE_MASK_BC ? b * r.C + t.c : (b * g.H + h) * (g.W * r.C) + t.coff));
+        }
+    }
+    float sc[VEC], sh[VEC];                    // a * BN(r) = r * sc + sh
+    {
+        float mu[VEC], is[VEC], ga[VEC], be[VEC];
+        ld8f(mean + t.c, mu); ld8f(invstd + t.c, is); ld8f(gamma + t.c, ga); ld8f(beta + t.c, be);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { sc[i] = a * is[i] * ga[i]; sh[i] = a * be[i] - mu[i] * sc[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+        if (in[u]) {
+            float rv[VEC], cv[VEC], mk[VEC];
+            rr[u].unpack(rv);
+            cr[u].unpack(cv);
+            if (mask_mode != MOPOE_MASK_NONE) {
+                mask8(mr[u], mk);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) mk[i] = 1.f;
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = fmaf(rv[i], sc[i], sh[i]) + bcoef * (cv[i] * mk[i]);
+        }
+        st8v<T>(out.p + ooff[u], o);
+    }
+}
+
+// BN(+ReLU gate, +dropout, +addend, + second output) backward apply, row-wise.  Same arithmetic, operation for operation,
+// as bn_bwd_apply_oneshot_kernel (coefficients k1 / ca / cb, fmaf nesting) -> bit-identical results.
+template <typename T, int U, bool GATE, bool ADD, bool OUT2>
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_rows_kernel(
+    const RowGeo g, DView<const T> dy, DView<const T> gate, float gscale, DView<const T> x, const uint8_t* mask, int mask_mode,
+    const float* mean, const float* invstd, const float* gamma, const float* sums, float inv_cnt, DView<const T> addend,
+    DView<T> out, DView<T> out2, const uint8_t* mask2, int mask2_mode, float scale2) {
+    RowThread t;
+    if (!row_thread(g, t)) return;
+    const int C = x.C;
+    Raw8<T> gR[U], tR[U], xR[U], aR[U];
+    uint2 mR[U], m2R[U];
+    bool valid[U], in[U];
+    int ooff[U], o2off[U];
+    const bool masked = mask_mode != MOPOE_MASK_NONE, masked2 = OUT2 && mask2_mode != MOPOE_MASK_NONE;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        int b, h;
+        valid[u] = row_decode(g, t.rg * U + u, b, h);
+        in[u] = valid[u] && t.col_in && h >= 0 && h < g.H;
+        ooff[u] = b * (int)out.sB + h * (int)out.sH + t.coff;
+        if (OUT2) o2off[u] = b * (int)out2.sB + h * (int)out2.sH + t.coff;
+        if (in[u]) {
+            gR[u].load(dy.p + (b * (int)dy.sB + h * (int)dy.sH + t.coff));
+            if (GATE) tR[u].load(gate.p + (b * (int)gate.sB + h * (int)gate.sH + t.coff));
+            xR[u].load(x.p + (b * (int)x.sB + h * (int)x.sH + t.coff));
+            if (ADD) aR[u].load(addend.p + (b * (int)addend.sB + h * (int)addend.sH + t.coff));
+            const int bc = b * C + t.c, el = (b * g.H + h) * (g.W * C) + t.coff;
+            if (masked) mR[u] = *reinterpret_cast<const uint2*>(mask + (mask_mode == MOPOE_MASK_BC ? bc : el));
+            if (masked2) m2R[u] = *reinterpret_cast<const uint2*>(mask2 + (mask2_mode == MOPOE_MASK_BC ? bc : el));
+        }
+    }
+    float k1[VEC], ca[VEC], cb[VEC];
+    {
+        float mu[VEC], is[VEC], ga[VEC], sg[VEC], sgx[VEC];
+        ld8f(mean + t.c, mu); ld8f(invstd + t.c, is); ld8f(gamma + t.c, ga); ld8f(sums + t.c, sg); ld8f(sums + C + t.c, sgx);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            k1[i] = ga[i] * is[i];
+            const float mg = sg[i] * inv_cnt, mgx = sgx[i] * inv_cnt;
+            ca[i] = -k1[i] * is[i] * mgx;
+            cb[i] = k1[i] * (mu[i] * is[i] * mgx - mg);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (!valid[u]) continue;
+        float o[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) o[i] = 0.f;
+        if (!in[u]) {
+            st8v<T>(out.p + ooff[u], o);
+            if (OUT2) st8v<T>(out2.p + o2off[u], o);
+            continue;
+        }
+        float gv[VEC], v[VEC];
+        gR[u].unpack(gv);
+        xR[u].unpack(v);
+        if (OUT2) {
+            float o2[VEC], mk2[VEC];
+            if (masked2) {
+                mask8(m2R[u], mk2);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) mk2[i] = 1.f;
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o2[i] = scale2 * gv[i] * mk2[i];
+            st8v<T>(out2.p + o2off[u], o2);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) gv[i] *= gscale;
+        if (GATE) {
+            float gt[VEC];
+            tR[u].unpack(gt);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i)
+                if (!(gt[i] > 0.f)) gv[i] = 0.f;
+        }
+        if (masked) {
+            float mk[VEC];
+            mask8(mR[u], mk);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = fmaf(k1[i], gv[i], fmaf(ca[i], v[i] * mk[i], cb[i])) * mk[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] = fmaf(k1[i], gv[i], fmaf(ca[i], v[i], cb[i]));
+        }
+        if (ADD) {
+            float ad[VEC];
+            aR[u].unpack(ad);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) o[i] += ad[i];
+        }
+        st8v<T>(out.p + ooff[u], o);
+    }
+}
+#ifndef BWD_ROWS_U
+#define BWD_ROWS_U 2
+#endif
+#ifndef FWD_ROWS_U
+#define FWD_ROWS_U 4
+#endif
+template <typename T>
+static int launch_bwd_rows(const mopoe_view_t* outv, cudaStream_t st, DView<const T> dy, DView<const T> gate, bool has_gate,
+                           float gscale, DView<const T> x, const uint8_t* mask, int mask_mode, const float* mean,
+                           const float* invstd, const float* gamma, const float* sums, float inv_cnt, DView<const T> addend,
+                           bool has_add, DView<T> out, DView<T> out2, bool has_out2, const uint8_t* mask2, int mask2_mode,
+                           float scale2) {
+    RowGeo g;
+    unsigned blocks;
+    constexpr int U = BWD_ROWS_U;
+    if (make_rowgeo(outv, U, g, blocks)) return 1;
+#define MOPOE_RW(G, A, O)                                                                                                      \
+    bn_bwd_apply_rows_kernel<T, U, G, A, O><<<blocks, EW_THREADS, 0, st>>>(g, dy, gate, gscale, x, mask, mask_mode, mean, invstd, \
+                                                                          gamma, sums, inv_cnt, addend, out, out2, mask2,        \
+                                                                          mask2_mode, scale2)
+    if (has_out2) {
+        if (has_gate) { if (has_add) MOPOE_RW(true, true, true); else MOPOE_RW(true, false, true); }
+        else { if (has_add) MOPOE_RW(false, true, true); else MOPOE_RW(false, false, true); }
+    } else {
+        if (has_gate) { if (has_add) MOPOE_RW(true, true, false); else MOPOE_RW(true, false, false); }
+        else { if (has_add) MOPOE_RW(false, true, false); else MOPOE_RW(false, false, false); }
+    }
+#undef MOPOE_RW
+    return 0;
+}
+
 // ---- forward apply kernels ----------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(DView<const T> x, const uint8_t* mask, int mask_mode,
@@ -524,6 +845,17 @@ extern "C" int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int ma
                               const mopoe_view_t* out, void* stream) {
     if (check_same(x, out, "bn_apply")) return 1;
     MOPOE_REQUIRE(x->C % VEC == 0, "bn_apply: C=%d", x->C);
+    if (ew_rows() && rows_ok(x) && rows_ok(out)) {
+        RowGeo g;
+        unsigned blocks;
+        if (make_rowgeo(out, FWD_ROWS_U, g, blocks)) return 1;
+        MOPOE_DISPATCH_T(x->dtype, T, {
+            bn_apply_rows_kernel<T, FWD_ROWS_U><<<blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(
+                g, make_dview<const T>(x), mask, mask_mode, mean, invstd, gamma, beta, relu, make_dview<T>(out));
+        });
+        MOPOE_CHECK_LAUNCH("bn_apply_rows");
+        return 0;
+    }
     MOPOE_DISPATCH_T(x->dtype, T, {
         DView<T> ov = make_dview<T>(out);
         unsigned grid, stride;
@@ -576,6 +908,18 @@ extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const flo
                              float b, const mopoe_view_t* out, void* stream) {
     if (check_same(r, out, "combine(out)") || check_same(r, c, "combine(c)")) return 1;
     MOPOE_REQUIRE(r->C % VEC == 0, "combine: C=%d", r->C);
+    if (ew_rows() && rows_ok(r) && rows_ok(c) && rows_ok(out)) {
+        RowGeo g;
+        unsigned blocks;
+        if (make_rowgeo(out, FWD_ROWS_U, g, blocks)) return 1;
+        MOPOE_DISPATCH_T(r->dtype, T, {
+            combine_rows_kernel<T, FWD_ROWS_U><<<blocks, EW_THREADS, 0, (cudaStream_t)stream>>>(
+                g, make_dview<const T>(r), mean, invstd, gamma, beta, make_dview<const T>(c), mask, mask_mode, a, b,
+                make_dview<T>(out));
+        });
+        MOPOE_CHECK_LAUNCH("combine_rows");
+        return 0;
+    }
     MOPOE_DISPATCH_T(r->dtype, T, {
         DView<T> ov = make_dview<T>(out);
         unsigned grid, stride;
@@ -592,13 +936,6 @@ extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const flo
 // ---- backward apply kernels ---------------------------------------------------------------------------
 // out  = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend,  g = gscale * dy * [gate > 0]
 // out2 = scale2 * dy * 2mask2   (optional second output sharing the read of dy: the dropout2 branch of a block)
-__device__ __forceinline__ void mask8(const uint2& t, float (&o)[8]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        o[i] = ((t.x >> (8 * i)) & 0xffu) ? 2.f : 0.f;
-        o[4 + i] = ((t.y >> (8 * i)) & 0xffu) ? 2.f : 0.f;
-    }
-}
 // These passes are LATENCY-bound, not issue-bound (ncu: 39 % issue slots, long-scoreboard stalls, 115 registers -> 2
 // blocks/SM): what sets their speed is the number of bytes in flight per SM.  So: operands stay PACKED between load and
 // use (4 registers per bf16 octet), the loads of U pixels are issued before the first use, the per-channel terms are
@@ -892,7 +1229,15 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
         const long long total = storage_threads(ov);
         if (apply_grid(total, x->C, grid, stride)) return 1;
         const int os = ew_oneshot();
-        if (os) {
+        const bool rw = ew_rows() && rows_ok(x) && rows_ok(dy) && rows_ok(out) && (!gate || rows_ok(gate)) &&
+                        (!addend || rows_ok(addend)) && (!out2 || rows_ok(out2));
+        if (rw) {
+            if (launch_bwd_rows<T>(out, (cudaStream_t)stream, make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv,
+                                   gate != nullptr, gscale, xv, mask, mask_mode, mean, invstd, gamma, sums, inv_cnt,
+                                   addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,
+                                   out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2))
+                return 1;
+        } else if (os) {
             launch_oneshot<T>(total, (cudaStream_t)stream, make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv,
                               gate != nullptr, gscale, xv, mask, mask_mode, mean, invstd, gamma, sums, inv_cnt,
                               addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,

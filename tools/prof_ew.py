@@ -49,6 +49,8 @@ def main():
     print('bn_bwd bn1 (reduce 3R, apply 4R 1W) %.3f ms  %.0f GB/s' % (ms, 8 * nb / ms))
     ms = timeit(lambda: eng.bn_bwd(dy, a1, 1.0, x, mask, L.MASK_BC, stats, gamma, dg, db, None, out))
     print('bn_bwd bn2 (reduce 3R, apply 3R 1W) %.3f ms  %.0f GB/s' % (ms, 7 * nb / ms))
+    ms = timeit(lambda: eng.combine(a1, stats, gamma, beta, dy, mask, L.MASK_BC, 2.0, 0.3, out))
+    print('combine (2R 1W)                 %.3f ms  %.0f GB/s' % (ms, 3 * nb / ms))
     dr, dc = act(1), act(1)
     t1, t2, t3 = a1.t, dy.t, dxs.t
     ms = timeit(lambda: t1.copy_(t2))
