@@ -25,6 +25,28 @@ extern "C" int mopoe_version(void) { return 101; }
 constexpr int VEC = 8;
 constexpr int EW_THREADS = 256;
 
+// shared-memory-staged persistent variants (stream.cu): 0 launched, 1 error, -1 shape not eligible
+int mopoe_staged_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean, const float* invstd,
+                          const float* gamma, const float* beta, int relu, const mopoe_view_t* out, cudaStream_t st);
+int mopoe_staged_combine(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                         const mopoe_view_t* c, const uint8_t* mask, int mask_mode, float a, float b, const mopoe_view_t* out,
+                         cudaStream_t st);
+int mopoe_staged_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const mopoe_view_t* x,
+                              const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, const float* gamma,
+                              const float* sums, const mopoe_view_t* addend, const mopoe_view_t* out, const mopoe_view_t* out2,
+                              const uint8_t* mask2, int mask2_mode, float scale2, cudaStream_t st);
+int mopoe_staged_reduce(int mode, const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
+                        const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, double* ws, int nchunk_cap,
+                        int* nchunk_used, cudaStream_t st);
+static int ew_staged() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_EW_STAGED");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+
 static int check_same(const mopoe_view_t* a, const mopoe_view_t* b, const char* what) {
     if (a->B != b->B || a->H != b->H || a->W != b->W || a->C != b->C || a->dtype != b->dtype)
         MOPOE_FAIL("%s: view mismatch [%d,%d,%d,%d]/%d vs [%d,%d,%d,%d]/%d", what, a->B, a->H, a->W, a->C,
@@ -436,6 +458,20 @@ static int launch_reduce(const mopoe_view_t* x, const mopoe_view_t* dy, const mo
     return 0;
 }
 
+// staged reduction when eligible (and no fused-finalize counters were asked for), else the register-staged kernel
+template <int MODE>
+static int reduce_any(const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const uint8_t* mask,
+                      int mask_mode, const float* mean, const float* invstd, double* ws, int nchunk, int* used, cudaStream_t st,
+                      const FinArgs& fin, const float* ggamma = nullptr, const float* gbeta = nullptr) {
+    *used = nchunk;
+    if (ew_staged() && !fin.counter && !ggamma && !gbeta && x->C % VEC == 0) {
+        const int r = mopoe_staged_reduce(MODE, x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, used, st);
+        if (r >= 0) return r;
+        *used = nchunk;
+    }
+    return launch_reduce<MODE>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st, fin, ggamma, gbeta);
+}
+
 extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, double* ws, int nchunk,
                               float eps, float momentum, float* mean, float* invstd, float* running_mean,
                               float* running_var, int* counters, void* stream) {
@@ -445,7 +481,7 @@ extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int ma
     fin.count = (double)x->B * x->H * x->W;
     fin.eps = eps; fin.momentum = momentum;
     fin.mean = mean; fin.invstd = invstd; fin.rmean = running_mean; fin.rvar = running_var;
-    if (launch_reduce<RED_STATS>(x, nullptr, nullptr, 1.f, mask, mask_mode, nullptr, nullptr, ws, nchunk, st, fin)) return 1;
+    if (reduce_any<RED_STATS>(x, nullptr, nullptr, 1.f, mask, mask_mode, nullptr, nullptr, ws, nchunk, &nchunk, st, fin)) return 1;
     if (!counters) {
         bn_finalize_kernel<<<(x->C + FIN_CH - 1) / FIN_CH, 256, 0, st>>>(ws, nchunk, x->C, fin.count, eps, momentum, mean, invstd,
                                                           running_mean, running_var);
@@ -468,7 +504,7 @@ extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, d
     FinArgs fin = {};
     fin.counter = counters;
     fin.out0 = out; fin.accumulate = accumulate;
-    if (launch_reduce<RED_COLSUM>(v, nullptr, nullptr, 1.f, nullptr, MOPOE_MASK_NONE, nullptr, nullptr, ws, nchunk, st, fin))
+    if (reduce_any<RED_COLSUM>(v, nullptr, nullptr, 1.f, nullptr, MOPOE_MASK_NONE, nullptr, nullptr, ws, nchunk, &nchunk, st, fin))
         return 1;
     if (!counters) {
         sums_finalize_kernel<<<(v->C + FIN_CH - 1) / FIN_CH, 256, 0, st>>>(ws, nchunk, v->C, out, nullptr, accumulate, nullptr);
@@ -488,7 +524,7 @@ extern "C" int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* g
     FinArgs fin = {};
     fin.counter = counters;
     fin.out0 = dbeta; fin.out1 = dgamma; fin.sums = sums; fin.accumulate = accumulate;
-    if (launch_reduce<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st, fin, gate_gamma, gate_beta))
+    if (reduce_any<RED_BNBWD>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, &nchunk, st, fin, gate_gamma, gate_beta))
         return 1;
     if (!counters) {
         sums_finalize_kernel<<<(x->C + FIN_CH - 1) / FIN_CH, 256, 0, st>>>(ws, nchunk, x->C, dbeta, dgamma, accumulate, sums);
@@ -845,6 +881,10 @@ extern "C" int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int ma
                               const mopoe_view_t* out, void* stream) {
     if (check_same(x, out, "bn_apply")) return 1;
     MOPOE_REQUIRE(x->C % VEC == 0, "bn_apply: C=%d", x->C);
+    if (ew_staged()) {
+        const int r = mopoe_staged_bn_apply(x, mask, mask_mode, mean, invstd, gamma, beta, relu, out, (cudaStream_t)stream);
+        if (r >= 0) return r;
+    }
     if (ew_rows() && rows_ok(x) && rows_ok(out)) {
         RowGeo g;
         unsigned blocks;
@@ -908,6 +948,10 @@ extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const flo
                              float b, const mopoe_view_t* out, void* stream) {
     if (check_same(r, out, "combine(out)") || check_same(r, c, "combine(c)")) return 1;
     MOPOE_REQUIRE(r->C % VEC == 0, "combine: C=%d", r->C);
+    if (ew_staged()) {
+        const int rc = mopoe_staged_combine(r, mean, invstd, gamma, beta, c, mask, mask_mode, a, b, out, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
+    }
     if (ew_rows() && rows_ok(r) && rows_ok(c) && rows_ok(out)) {
         RowGeo g;
         unsigned blocks;
@@ -1222,6 +1266,11 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
     }
     MOPOE_REQUIRE(x->C % VEC == 0, "bn_bwd_apply: C=%d", x->C);
     float inv_cnt = 1.f / ((float)x->B * (float)x->H * (float)x->W);
+    if (ew_staged()) {
+        const int r = mopoe_staged_bn_bwd_apply(dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, sums, addend, out, out2,
+                                                mask2, mask2_mode, scale2, (cudaStream_t)stream);
+        if (r >= 0) return r;
+    }
     MOPOE_DISPATCH_T(x->dtype, T, {
         DView<T> ov = make_dview<T>(out);
         DView<const T> xv = make_dview<const T>(x);
