@@ -145,6 +145,13 @@ int mopoe_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, co
 int mopoe_combine(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma,
                   const float* beta, const mopoe_view_t* c, const uint8_t* mask, int mask_mode,
                   float a, float b, const mopoe_view_t* out, void* stream);
+/* mopoe_combine + the training-mode BatchNorm statistics of `out` (mean, 1/sqrt(var+eps), running statistics): the bn1 of the
+ * NEXT residual block reads exactly this tensor (ResidualBlocks.py:84-86), so its statistics pass folds into this one.
+ * Statistics are those of the STORED (storage-dtype-rounded) values.  ws: 2*nchunk*C doubles. */
+int mopoe_combine_bn(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma,
+                     const float* beta, const mopoe_view_t* c, const uint8_t* mask, int mask_mode, float a, float b,
+                     const mopoe_view_t* out, double* ws, int nchunk, float eps, float momentum, float* out_mean,
+                     float* out_invstd, float* running_mean, float* running_var, void* stream);
 /* BN backward, reduction half: g = gscale * dy * [gate > 0];  xhat = (x*2mask - mean)*invstd;
  * dbeta (+)= sum g, dgamma (+)= sum g*xhat, sums[0:C] = sum g, sums[C:2C] = sum g*xhat.
  * The ReLU gate is read from `gate` (the saved activation) or absent (NULL).  gate_gamma / gate_beta are reserved

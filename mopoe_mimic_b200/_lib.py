@@ -73,6 +73,7 @@ SIGNATURES = {
     'mopoe_bn_stats': (_I, [_V, _P, _I, _P, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
     'mopoe_bn_apply': (_I, [_V, _P, _I, _P, _P, _P, _P, _I, _V, _P]),
     'mopoe_combine': (_I, [_V, _P, _P, _P, _P, _V, _P, _I, _F, _F, _V, _P]),
+    'mopoe_combine_bn': (_I, [_V, _P, _P, _P, _P, _V, _P, _I, _F, _F, _V, _P, _I, _F, _F, _P, _P, _P, _P, _P]),
     'mopoe_bn_bwd_reduce': (_I, [_V, _V, _F, _V, _P, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
     'mopoe_bn_bwd_apply': (_I, [_V, _V, _F, _V, _P, _I, _P, _P, _P, _P, _V, _V, _P, _P]),
     'mopoe_combine_bwd_apply': (_I, [_V, _F, _V, _P, _P, _P, _P, _P, _I, _F, _V, _V, _P]),

@@ -62,6 +62,11 @@ class BlockRun:
         self.in_pad, self.out_pad, self.train = in_pad, out_pad, train
         self.buffers = buffers          # dict: 'bn1'/'bn2'/'short' -> (running_mean, running_var)
         self.masks = masks              # (mask1, mask2) uint8 tensors or None
+        # hand-off between consecutive blocks of a chain (training): this block's bn1 statistics as produced by the
+        # previous block's combine pass / the buffers of the next block's bn1, whose statistics this block then produces
+        self.in_stats = None
+        self.next_bn = None
+        self.out_stats = None
 
 
 def _pads(nd, p):
@@ -142,7 +147,12 @@ class ResBlockFn(torch.autograd.Function):
         m1, m2 = run.masks if run.train else (None, None)
         bufs = run.buffers
         # bn1 -> relu
-        st1 = eng.bn_stats(x, None, L.MASK_NONE, *bufs['bn1']) if run.train else _eval_stats(*bufs['bn1'])
+        if not run.train:
+            st1 = _eval_stats(*bufs['bn1'])
+        elif run.in_stats is not None:
+            st1 = run.in_stats           # (the previous block's combine pass produced them, running statistics included)
+        else:
+            st1 = eng.bn_stats(x, None, L.MASK_NONE, *bufs['bn1'])
         a1 = eng.bn_apply(x, None, L.MASK_NONE, st1, P['bn1.weight'], P['bn1.bias'], True,
                           Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device))
         # conv1 (1x1)
@@ -164,8 +174,12 @@ class ResBlockFn(torch.autograd.Function):
         else:
             r, st3 = _main_fwd(eng, sp, x, P[short + '.0.weight'], P[short + '.0.bias'], dt), _eval_stats(*bufs['short'])
         oph, opw = _pads(sp.nd, run.out_pad)
-        y = eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b,
-                        Act.empty(B, r.H, r.W, sp.cout, oph, opw, dt, eng.device))
+        y = Act.empty(B, r.H, r.W, sp.cout, oph, opw, dt, eng.device)
+        if run.train and run.next_bn is not None and eng.fuse_next_stats:
+            y, run.out_stats = eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b, y,
+                                           bn=run.next_bn)
+        else:
+            eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b, y)
         ctx.run = run
         ctx.geo = (r.H, r.W)
         ctx.save_for_backward(x_t, a1.t, hh.t, a2.t, r.t, st1, st2, st3, *params)

@@ -30,7 +30,7 @@ int mopoe_staged_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_m
                           const float* gamma, const float* beta, int relu, const mopoe_view_t* out, cudaStream_t st);
 int mopoe_staged_combine(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma, const float* beta,
                          const mopoe_view_t* c, const uint8_t* mask, int mask_mode, float a, float b, const mopoe_view_t* out,
-                         cudaStream_t st);
+                         double* ws, int nchunk_cap, int* nchunk_used, cudaStream_t st);
 int mopoe_staged_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const mopoe_view_t* x,
                               const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, const float* gamma,
                               const float* sums, const mopoe_view_t* addend, const mopoe_view_t* out, const mopoe_view_t* out2,
@@ -949,7 +949,8 @@ extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const flo
     if (check_same(r, out, "combine(out)") || check_same(r, c, "combine(c)")) return 1;
     MOPOE_REQUIRE(r->C % VEC == 0, "combine: C=%d", r->C);
     if (ew_staged()) {
-        const int rc = mopoe_staged_combine(r, mean, invstd, gamma, beta, c, mask, mask_mode, a, b, out, (cudaStream_t)stream);
+        const int rc = mopoe_staged_combine(r, mean, invstd, gamma, beta, c, mask, mask_mode, a, b, out, nullptr, 0, nullptr,
+                                            (cudaStream_t)stream);
         if (rc >= 0) return rc;
     }
     if (ew_rows() && rows_ok(r) && rows_ok(c) && rows_ok(out)) {
@@ -975,6 +976,32 @@ extern "C" int mopoe_combine(const mopoe_view_t* r, const float* mean, const flo
     });
     MOPOE_CHECK_LAUNCH("combine");
     return 0;
+}
+
+// combine + the training-mode BatchNorm statistics of its output (the NEXT block's bn1: ResidualBlocks.py:84-86 applied to
+// the previous block's `out`), in the same pass over the data when the staged kernel applies; else combine, then mopoe_bn_stats.
+extern "C" int mopoe_combine_bn(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma,
+                                const float* beta, const mopoe_view_t* c, const uint8_t* mask, int mask_mode, float a, float b,
+                                const mopoe_view_t* out, double* ws, int nchunk, float eps, float momentum, float* out_mean,
+                                float* out_invstd, float* running_mean, float* running_var, void* stream) {
+    if (check_same(r, out, "combine_bn(out)") || check_same(r, c, "combine_bn(c)")) return 1;
+    MOPOE_REQUIRE(r->C % VEC == 0 && ws && nchunk >= 1, "combine_bn: C=%d / workspace", r->C);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ew_staged()) {
+        int used = 0;
+        const int rc = mopoe_staged_combine(r, mean, invstd, gamma, beta, c, mask, mask_mode, a, b, out, ws, nchunk, &used, st);
+        if (rc > 0) return 1;
+        if (rc == 0) {
+            const double count = (double)r->B * r->H * r->W;
+            bn_finalize_kernel<<<(r->C + FIN_CH - 1) / FIN_CH, 256, 0, st>>>(ws, used, r->C, count, eps, momentum, out_mean, out_invstd,
+                                                                           running_mean, running_var);
+            MOPOE_CHECK_LAUNCH("combine_bn_finalize");
+            return 0;
+        }
+    }
+    if (mopoe_combine(r, mean, invstd, gamma, beta, c, mask, mask_mode, a, b, out, stream)) return 1;
+    return mopoe_bn_stats(out, nullptr, MOPOE_MASK_NONE, ws, nchunk, eps, momentum, out_mean, out_invstd, running_mean, running_var,
+                          nullptr, stream);
 }
 
 // ---- backward apply kernels ---------------------------------------------------------------------------

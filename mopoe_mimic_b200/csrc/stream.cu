@@ -61,6 +61,7 @@ struct StreamGeo {
     int PP, CH, IO, KC;            // pixels / octets per sub-chunk (CH = PP * CV <= 256), octets per item, items per row
     unsigned items;
     int stages;
+    int reverse;                   // walk the items from the END of the tensors (see st_reverse())
     unsigned op_bytes;             // bytes of one operand slot of a stage
     FastDiv fKC, fH, fCV;
 };
@@ -142,6 +143,7 @@ struct Item {
 };
 __device__ __forceinline__ Item decode_item(const StreamGeo& g, unsigned item) {
     unsigned row, k, b, h;
+    if (g.reverse) item = g.items - 1u - item;
     g.fKC.divmod(item, row, k);
     g.fH.divmod(row, b, h);
     Item it;
@@ -343,8 +345,8 @@ struct ApplyBody {            // out = act(gamma * (x*2mask - mean) * invstd + b
     }
 };
 
-template <typename T>
-struct CombineBody {          // out = a * BN(r) + b * (c * 2mask)
+template <typename T, bool STATS>
+struct CombineBody {          // out = a * BN(r) + b * (c * 2mask)   [+ per-channel sum / sum of squares of the STORED out]
     static constexpr int KS = ks_for<T>(ST_K2);
     typedef MaskPre<KS> Pre;
     StreamGeo g;
@@ -353,13 +355,18 @@ struct CombineBody {          // out = a * BN(r) + b * (c * 2mask)
     float a, bcoef;
     SOut out;
     float sc[VEC], sh[VEC];
+    float f0[VEC], f1[VEC];
     int c;
     __device__ __forceinline__ void init(int c_) {
         c = c_;
         float mu[VEC], is[VEC], ga[VEC], be[VEC];
         ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(beta + c, be);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { sc[i] = a * is[i] * ga[i]; sh[i] = a * be[i] - mu[i] * sc[i]; }
+        for (int i = 0; i < VEC; ++i) {
+            sc[i] = a * is[i] * ga[i];
+            sh[i] = a * be[i] - mu[i] * sc[i];
+            f0[i] = f1[i] = 0.f;
+        }
     }
     __device__ __forceinline__ Pre prefetch(const Item& it, int tid) const { return mask_fetch<KS>(mk, g, it, tid, c); }
     __device__ __forceinline__ void item(const Item& it, int tid, const Oct<T> (&raw)[KS][2], const Pre& pre) {
@@ -376,6 +383,15 @@ struct CombineBody {          // out = a * BN(r) + b * (c * 2mask)
 #pragma unroll
             for (int i = 0; i < VEC; ++i) o[i] = fmaf(rv[i], sc[i], sh[i]) + bcoef * (cv[i] * m[i]);
             st8<T>(orow + j * g.CH * VEC, o);
+            if (STATS) {
+                // the statistics the NEXT block's bn1 needs are those of the values it will read: rounded to the storage type
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float v = sizeof(T) == 2 ? __bfloat162float(__float2bfloat16_rn(o[i])) : o[i];
+                    f0[i] += v;
+                    f1[i] = fmaf(v, v, f1[i]);
+                }
+            }
         }
     }
 };
@@ -531,13 +547,38 @@ __global__ void __launch_bounds__(ST_THREADS, 2) staged_bn_apply_kernel(const SO
     stream_pipeline<T, 1>(body.g, ops, smem, body);
     if (threadIdx.x < ST_CONSUMERS) zero_border<T>(body.out, body.g, threadIdx.x);
 }
-template <typename T>
-__global__ void __launch_bounds__(ST_THREADS, 2) staged_combine_kernel(const SOp r, const SOp c, const CombineBody<T> body_in) {
+// per-CTA partial sums of the consumers' fp32 strips: ws[(blockIdx.x * 2 + which) * C + channel], fp64; every CTA writes all
+// 2*C entries.  Threads that share a channel octet (the PP pixel lanes of a sub-chunk) are summed in lane order: fixed order.
+__device__ __forceinline__ void block_sums(const StreamGeo& g, uint8_t* smem, int c, const float (&f0)[VEC], const float (&f1)[VEC],
+                                           double* ws) {
+    __syncthreads();                                   // every stage has been consumed: reuse the data area
+    float* red = reinterpret_cast<float*>(smem + ST_HDR);           // [2][PP][C]
+    const int tid = threadIdx.x;
+    if (tid < g.CH) {
+        const int p = tid / g.CV;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            red[(0 * g.PP + p) * g.C + c + i] = f0[i];
+            red[(1 * g.PP + p) * g.C + c + i] = f1[i];
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < 2 * g.C; j += ST_THREADS) {
+        const int which = j / g.C, ch = j - which * g.C;
+        double a = 0.0;
+        for (int p = 0; p < g.PP; ++p) a += (double)red[(which * g.PP + p) * g.C + ch];
+        ws[((long long)blockIdx.x * 2 + which) * g.C + ch] = a;
+    }
+}
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(ST_THREADS, 2) staged_combine_kernel(const SOp r, const SOp c, const CombineBody<T, STATS> body_in,
+                                                                       double* ws) {
     extern __shared__ __align__(128) uint8_t smem[];
-    CombineBody<T> body = body_in;
+    CombineBody<T, STATS> body = body_in;
     const SOp ops[2] = {r, c};
     stream_pipeline<T, 2>(body.g, ops, smem, body);
     if (threadIdx.x < ST_CONSUMERS) zero_border<T>(body.out, body.g, threadIdx.x);
+    if (STATS) block_sums(body.g, smem, body.c, body.f0, body.f1, ws);
 }
 struct SOps4 {
     SOp o[4];
@@ -566,26 +607,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) staged_reduce_kernel(const SOps
 #pragma unroll
     for (int i = 0; i < NOPS; ++i) ops[i] = in.o[i];
     stream_pipeline<T, NOPS>(body.g, ops, smem, body);
-    // block reduction over the PP pixel lanes that share a channel octet: fp32 strips -> fp64 in shared memory
-    __syncthreads();                                   // every stage has been consumed: reuse the data area
-    const StreamGeo& g = body.g;
-    float* red = reinterpret_cast<float*>(smem + ST_HDR);           // [2][PP][C]
-    const int tid = threadIdx.x;
-    if (tid < g.CH) {
-        const int p = tid / g.CV;
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            red[(0 * g.PP + p) * g.C + body.c + i] = body.f0[i];
-            red[(1 * g.PP + p) * g.C + body.c + i] = body.f1[i];
-        }
-    }
-    __syncthreads();
-    for (int j = tid; j < 2 * g.C; j += ST_THREADS) {
-        const int which = j / g.C, ch = j - which * g.C;
-        double a = 0.0;
-        for (int p = 0; p < g.PP; ++p) a += (double)red[(which * g.PP + p) * g.C + ch];
-        ws[((long long)blockIdx.x * 2 + which) * g.C + ch] = a;
-    }
+    block_sums(body.g, smem, body.c, body.f0, body.f1, ws);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------
@@ -597,6 +619,17 @@ int num_sms() {
         if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
     }
     return g_num_sms;
+}
+// The apply-type passes walk their tensors BACKWARDS: the pass that ran just before them (the statistics / sums reduction
+// over the same operands, or the GEMM that produced the input) touched the END of those tensors last, so with a 126 MB L2
+// the first ~100 MB an apply pass asks for are still on chip.  MOPOE_ST_REVERSE=0 restores the forward walk.
+int st_reverse() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_ST_REVERSE");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
 }
 bool view_ok(const mopoe_view_t* v) {
     return v && v->sW == v->C && v->C % VEC == 0 && v->C / VEC <= ST_CONSUMERS && (reinterpret_cast<uintptr_t>(v->ptr) & 15) == 0 &&
@@ -628,6 +661,7 @@ bool make_geo(const mopoe_view_t* v, int esize, int nops, int ks, StreamGeo& g, 
     if (stages > ST_MAX_STAGES) stages = ST_MAX_STAGES;
     if (stages < 2) return false;
     g.stages = stages;
+    g.reverse = 0;
     g.fKC = FastDiv((unsigned)g.KC); g.fH = FastDiv((unsigned)g.H); g.fCV = FastDiv((unsigned)g.CV);
     smem = ST_HDR + (size_t)stages * g.op_bytes * nops;
     if (smem < smem_floor) smem = smem_floor;
@@ -662,6 +696,7 @@ int mopoe_staged_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_m
     size_t smem;
     const int ks = x->dtype == MOPOE_BF16 ? ApplyBody<bf16>::KS : ApplyBody<float>::KS;
     if (!make_geo(out, es, 1, ks, g, grid, smem)) return -1;
+    g.reverse = st_reverse();
     MOPOE_DISPATCH_T(x->dtype, T, {
         ST_ATTR(staged_bn_apply_kernel<T>);
         ApplyBody<T> body;
@@ -673,23 +708,45 @@ int mopoe_staged_bn_apply(const mopoe_view_t* x, const uint8_t* mask, int mask_m
     return 0;
 }
 
+static size_t sums_floor(const mopoe_view_t* v) {
+    const int cv = v->C / VEC;
+    const int pp_max = ST_CONSUMERS / cv > 0 ? ST_CONSUMERS / cv : 1;
+    return ST_HDR + (size_t)2 * pp_max * v->C * sizeof(float);          // block_sums re-uses the data area: [2][PP][C] floats
+}
+// ws != NULL: also the per-channel statistics (sum, sum of squares) of the stored output, as *nchunk_used <= nchunk_cap
+// partial slabs of [2][C] doubles
 int mopoe_staged_combine(const mopoe_view_t* r, const float* mean, const float* invstd, const float* gamma, const float* beta,
                          const mopoe_view_t* c, const uint8_t* mask, int mask_mode, float a, float b, const mopoe_view_t* out,
-                         cudaStream_t st) {
+                         double* ws, int nchunk_cap, int* nchunk_used, cudaStream_t st) {
     if (!view_ok(r) || !view_ok(c) || !view_ok(out)) return -1;
     const int es = r->dtype == MOPOE_BF16 ? 2 : 4;
     StreamGeo g;
     int grid;
     size_t smem;
-    const int ks = r->dtype == MOPOE_BF16 ? CombineBody<bf16>::KS : CombineBody<float>::KS;
-    if (!make_geo(out, es, 2, ks, g, grid, smem)) return -1;
+    const int ks = r->dtype == MOPOE_BF16 ? CombineBody<bf16, false>::KS : CombineBody<float, false>::KS;
+    const size_t floor_bytes = ws ? sums_floor(r) : 0;
+    if (floor_bytes > 100 * 1024) return -1;
+    if (!make_geo(out, es, 2, ks, g, grid, smem, floor_bytes)) return -1;
+    g.reverse = st_reverse();
+    if (ws) {
+        if (nchunk_cap < 1) return -1;
+        if (grid > nchunk_cap) grid = nchunk_cap;
+        *nchunk_used = grid;
+    }
+#define ST_CB(S)                                                                                                                 \
+    do {                                                                                                                         \
+        ST_ATTR((staged_combine_kernel<T, S>));                                                                                  \
+        CombineBody<T, S> body;                                                                                                  \
+        body.g = g; body.mk = MaskRef{mask, mask_mode};                                                                          \
+        body.mean = mean; body.invstd = invstd; body.gamma = gamma; body.beta = beta; body.a = a; body.bcoef = b;                \
+        body.out = sout(out);                                                                                                    \
+        staged_combine_kernel<T, S><<<grid, ST_THREADS, smem, st>>>(sop(r), sop(c), body, ws);                                   \
+    } while (0)
     MOPOE_DISPATCH_T(r->dtype, T, {
-        ST_ATTR(staged_combine_kernel<T>);
-        CombineBody<T> body;
-        body.g = g; body.mk = MaskRef{mask, mask_mode};
-        body.mean = mean; body.invstd = invstd; body.gamma = gamma; body.beta = beta; body.a = a; body.bcoef = b; body.out = sout(out);
-        staged_combine_kernel<T><<<grid, ST_THREADS, smem, st>>>(sop(r), sop(c), body);
+        if (ws) ST_CB(true);
+        else ST_CB(false);
     });
+#undef ST_CB
     MOPOE_CHECK_LAUNCH("staged_combine");
     return 0;
 }
@@ -732,6 +789,7 @@ int mopoe_staged_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, 
     const int kb = nops >= 4 ? ST_K4 : (nops == 3 ? ST_K3 : ST_K2);
     const int ks = x->dtype == MOPOE_BF16 ? ks_for<bf16>(kb) : ks_for<float>(kb);
     if (!make_geo(out, es, nops, ks, g, grid, smem)) return -1;
+    g.reverse = st_reverse();
     const float inv_cnt = 1.f / ((float)x->B * (float)x->H * (float)x->W);
 #define ST_BW(G, A, O)                                                                                                          \
     if (launch_bwd<T, G, A, O>(g, grid, smem, st, dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, sums, inv_cnt, addend, \
@@ -778,9 +836,7 @@ int mopoe_staged_reduce(int mode, const mopoe_view_t* x, const mopoe_view_t* dy,
     StreamGeo g;
     int grid;
     size_t smem;
-    // the block reduction re-uses the data area: [2][PP][C] floats
-    const int pp_max = ST_CONSUMERS / (x->C / VEC) > 0 ? ST_CONSUMERS / (x->C / VEC) : 1;
-    const size_t floor_bytes = ST_HDR + (size_t)2 * pp_max * x->C * sizeof(float);
+    const size_t floor_bytes = sums_floor(x);
     if (floor_bytes > 100 * 1024) return -1;
     const int kb = nops == 1 ? ST_K1 : (nops == 2 ? ST_K2 : ST_K3);
     const int ks = x->dtype == MOPOE_BF16 ? ks_for<bf16>(kb) : ks_for<float>(kb);

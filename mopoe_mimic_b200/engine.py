@@ -84,6 +84,7 @@ class Engine:
         self.batched = os.environ.get('MOPOE_GEMM_BATCHED', '1') != '0'       # phases of a deconv in one launch
         self.persistent = os.environ.get('MOPOE_GEMM_PERSISTENT', '1') != '0'   # persistent kernel for single GEMMs too
         self.fuse_stats = os.environ.get('MOPOE_FUSE_BN_STATS', '1') != '0'     # BatchNorm statistics in the GEMM epilogue
+        self.fuse_next_stats = os.environ.get('MOPOE_FUSE_NEXT_BN_STATS', '1') != '0'   # next block's bn1 statistics in combine
 
     # ---- packed-weight cache ---------------------------------------------------------------------------------
     # Every (weight, form) has a persistent SLOT (destination buffers with fixed addresses).  A slot is valid while its
@@ -215,11 +216,21 @@ class Engine:
                L.ptr(gamma), L.ptr(beta), int(relu), C.byref(out.view()), L.stream_ptr())
         return out
 
-    def combine(self, r, stats, gamma, beta, c, mask, mode, a, b, out):
+    def combine(self, r, stats, gamma, beta, c, mask, mode, a, b, out, bn=None, eps=1e-5, momentum=0.1):
+        """out = a * BN(r) + b * (c * 2mask).  bn = (running_mean, running_var) of the BatchNorm that reads `out` next (the
+        following block's bn1): also return its training-mode statistics [2, C], produced in the same pass"""
         self._bytes('combine', r, 3)
-        L.call('mopoe_combine', C.byref(r.view()), L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(beta),
-               C.byref(c.view()), L.ptr(mask), mode, float(a), float(b), C.byref(out.view()), L.stream_ptr())
-        return out
+        if bn is None:
+            L.call('mopoe_combine', C.byref(r.view()), L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(beta),
+                   C.byref(c.view()), L.ptr(mask), mode, float(a), float(b), C.byref(out.view()), L.stream_ptr())
+            return out
+        nc = self.nchunk(r.B * r.H * r.W, r.C)
+        ws = self.ws64(2 * nc * r.C)
+        st = self.f32(2, r.C)
+        L.call('mopoe_combine_bn', C.byref(r.view()), L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(beta),
+               C.byref(c.view()), L.ptr(mask), mode, float(a), float(b), C.byref(out.view()), L.ptr(ws), nc, eps, momentum,
+               L.ptr(st[0]), L.ptr(st[1]), L.ptr(bn[0]), L.ptr(bn[1]), L.stream_ptr())
+        return out, st
 
     def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out, accumulate=False):
         """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x).  gate = the saved post-ReLU

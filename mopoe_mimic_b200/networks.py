@@ -104,7 +104,9 @@ class ResBlock(nn.Module):
     def bns(self):
         return [self.bn1, self.bn2, self.short()[1]]
 
-    def run(self, rt, eng, x_t, B, H, W, in_pad, out_pad, train, prefix):
+    def run(self, rt, eng, x_t, B, H, W, in_pad, out_pad, train, prefix, chain=None, next_blk=None):
+        """chain: a dict shared by the consecutive blocks of one network call.  In training the block's combine pass also
+        produces the batch statistics of next_blk.bn1 (which reads this block's output) and hands them over through it."""
         sp = self.spec
         masks = None
         if train:
@@ -121,7 +123,16 @@ class ResBlock(nn.Module):
         named = dict(self.named_parameters())
         params = [named[n] for n in sp.param_names()]
         run.param_objs = dict(zip(sp.param_names(), params))     # the Parameter objects (their .grad is the flat view)
-        return ResBlockFn.apply(x_t, run, *params)
+        if train and chain is not None:
+            prev = chain.pop('stats', None)
+            if prev is not None and prev[0] == x_t.data_ptr():
+                run.in_stats = prev[1]
+            if next_blk is not None:
+                run.next_bn = (next_blk.bn1.running_mean, next_blk.bn1.running_var)
+        y = ResBlockFn.apply(x_t, run, *params)
+        if run.out_stats is not None:
+            chain['stats'] = (y.data_ptr(), run.out_stats)
+        return y
 
 
 def _chain_pads(specs, last_pad):
@@ -204,9 +215,10 @@ class EncoderImg(_Net):
         ins, outs = _chain_pads(specs, 0)
         h = ImgStemFn.apply(x_img, fe.conv1.weight, eng, ins[0])
         H, W = H // 2, W // 2
+        blks, chain = [getattr(fe, sp.name)[0] for sp in specs], {}
         for i, sp in enumerate(specs):
-            blk = getattr(fe, sp.name)[0]
-            h = blk.run(rt, eng, h, B, H, W, ins[i], outs[i], train, '%s.feature_extractor.%s.0' % (self.prefix, sp.name))
+            h = blks[i].run(rt, eng, h, B, H, W, ins[i], outs[i], train, '%s.feature_extractor.%s.0' % (self.prefix, sp.name),
+                            chain, blks[i + 1] if i + 1 < len(blks) else None)
             H, W = sp.out_hw(H, W)
         assert H == 1 and W == 1, 'feature extractor must end at 1x1 (got %dx%d)' % (H, W)
         fc = self.feature_compressor
@@ -265,10 +277,10 @@ class DecoderImg(_Net):
         if ins[0]:
             raise AssertionError('first decoder block takes an unbordered 1x1 input')
         H = W = 1
+        blks, chain = [gen.generator[i][0] for i in range(len(specs))], {}
         for i, sp in enumerate(specs):
-            blk = gen.generator[i][0]
-            h = blk.run(rt, eng, h, B, H, W, ins[i], outs[i], train,
-                        '%s.img_generator.generator.%d.0' % (self.prefix, i))
+            h = blks[i].run(rt, eng, h, B, H, W, ins[i], outs[i], train,
+                            '%s.img_generator.generator.%d.0' % (self.prefix, i), chain, blks[i + 1] if i + 1 < len(blks) else None)
             H, W = sp.out_hw(H, W)
         last = gen.generator[len(specs)]
         img = ImgLastFn.apply(h, last.weight, last.bias, eng, B, H, W)
@@ -335,9 +347,10 @@ class EncoderText(_Net):
         ins, outs = _chain_pads(specs, 0)
         h = TextStemFn.apply(x_text, fe.conv1.weight, fe.conv1.bias, eng, ins[0])
         H, W = 1, Lq // 2
+        blks, chain = [getattr(fe, sp.name)[0] for sp in specs], {}
         for i, sp in enumerate(specs):
-            blk = getattr(fe, sp.name)[0]
-            h = blk.run(rt, eng, h, B, H, W, ins[i], outs[i], train, '%s.feature_extractor.%s.0' % (self.prefix, sp.name))
+            h = blks[i].run(rt, eng, h, B, H, W, ins[i], outs[i], train, '%s.feature_extractor.%s.0' % (self.prefix, sp.name),
+                            chain, blks[i + 1] if i + 1 < len(blks) else None)
             H, W = sp.out_hw(H, W)
         assert W == 1, 'text feature extractor must end at length 1 (got %d)' % W
         fc = self.feature_compressor
@@ -434,12 +447,15 @@ class DecoderText(_Net):
         last_pad = 0 if (self.word and gen.pointwise_last) else 1        # a 1x1 conv needs no border on its input
         ins, outs = _chain_pads(specs, last_pad)
         H, W = 1, 1
+        if self.word:
+            blks = [gen.generator[i][0] for i in range(len(specs))]
+            names = ['%s.text_generator.generator.%d.0' % (self.prefix, i) for i in range(len(specs))]
+        else:
+            blks = [getattr(gen, sp.name)[0] for sp in specs]
+            names = ['%s.text_generator.%s.0' % (self.prefix, sp.name) for sp in specs]
+        chain = {}
         for i, sp in enumerate(specs):
-            if self.word:
-                blk, pname = gen.generator[i][0], '%s.text_generator.generator.%d.0' % (self.prefix, i)
-            else:
-                blk, pname = getattr(gen, sp.name)[0], '%s.text_generator.%s.0' % (self.prefix, sp.name)
-            h = blk.run(rt, eng, h, B, H, W, ins[i], outs[i], train, pname)
+            h = blks[i].run(rt, eng, h, B, H, W, ins[i], outs[i], train, names[i], chain, blks[i + 1] if i + 1 < len(blks) else None)
             H, W = sp.out_hw(H, W)
         if self.word and gen.pointwise_last:
             last = gen.generator[len(specs)]

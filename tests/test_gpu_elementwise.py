@@ -157,6 +157,19 @@ def test_combine_and_its_backward(dtype, B, H, W, Cc, nd):
     rt, at = _tol(dtype)
     assert torch.allclose(y.interior().double(), ref, rtol=rt, atol=at * 3)
     assert _border_is_zero(y)
+    # combine + the statistics of its (stored) output for the next block's bn1, in one pass
+    y2 = _out(B, H, W, Cc, pho, pwo, dtype)
+    rm, rv = torch.zeros(Cc, device='cuda'), torch.ones(Cc, device='cuda')
+    _, st_next = eng.combine(r, st, gamma, beta, c, m, mode, 2.0, 0.3, y2, bn=(rm, rv))
+    torch.cuda.synchronize()
+    assert torch.equal(y2.t, y.t)
+    yv = y.interior().double()
+    n = B * H * W
+    mean, var = yv.mean(dim=(0, 1, 2)), yv.var(dim=(0, 1, 2), unbiased=False)
+    assert torch.allclose(st_next[0].double(), mean, rtol=1e-5, atol=2e-6)
+    assert torch.allclose(st_next[1].double(), 1.0 / torch.sqrt(var + EPS), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rm.double(), 0.1 * mean, rtol=1e-5, atol=2e-6)
+    assert torch.allclose(rv.double(), 0.9 + 0.1 * (var * n / (n - 1) if n > 1 else var), rtol=1e-5, atol=1e-6)
     # backward: dr = BN-backward(a * dy), dc = b * dy * 2mask
     dy64 = _rand((B, H, W, Cc), 8, dtype)
     dy = _act(dy64, pho, pwo, dtype)
