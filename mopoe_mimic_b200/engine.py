@@ -12,6 +12,7 @@ so that  conv k4/s2/p1  = one GEMM over 4-tap row windows of the padded input (c
 and each layer's dgrad is the other kind; wgrad always produces conv-form.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -161,8 +162,10 @@ class Engine:
 
     def begin_step(self):
         """same within-step Philox offsets every step; the device-side step counter makes the draws differ.  Weights that
-        changed behind torch's back (flat Adam) are re-packed here in one launch."""
+        changed behind torch's back (flat Adam) are re-packed here in one launch, and all dropout keep-masks of the step
+        (72 at the bench configuration) are drawn by ONE launch once the previous step has shown which are needed."""
         self.rng_offset = 0
+        self._masks_begin()
         if self._packs and self._packs_stale:
             self.prepack()
             self._packs_stale = False
@@ -286,11 +289,47 @@ class Engine:
         L.call('mopoe_convert', C.byref(src_view), int(nchw), C.byref(dst.view()), L.stream_ptr())
         return dst
 
+    # ---- dropout keep-masks --------------------------------------------------------------------------------
+    # Mask k of a step covers the Philox counter blocks [off_k, off_k + ceil(n_k / 128)) (128 mask bytes per counter), so
+    # the masks of a whole step are ONE contiguous stream: a single launch over a buffer that lays them out at 128-byte
+    # boundaries draws exactly the bytes the per-mask launches would.  The sizes are learnt from the previous step; a
+    # step that asks for anything else (eval pass, another fusion method) falls back to per-mask launches and re-learns.
+    def _masks_begin(self):
+        rec = getattr(self, '_mask_rec', None)
+        if rec:                                   # what the last step drew becomes the plan
+            self._mask_plan = (self._mask_seed, tuple(rec))
+        self._mask_rec, self._mask_seed = [], None
+        self._mask_buf, self._mask_pos = None, 0
+        plan = getattr(self, '_mask_plan', None)
+        if plan is None or os.environ.get('MOPOE_BATCHED_MASKS', '1') == '0':
+            return
+        seed, sizes = plan
+        total = sum((n + 127) // 128 for n in sizes) * 128
+        self._mask_buf = torch.empty(total, dtype=torch.uint8, device=self.device)
+        L.call('mopoe_dropout_mask', L.ptr(self._mask_buf), total, int(seed) & (2 ** 64 - 1), 0, L.ptr(self.rng_step),
+               L.stream_ptr())
+
     def dropout_mask(self, n, seed):
+        if getattr(self, '_mask_rec', None) is None:
+            self._mask_rec, self._mask_seed, self._mask_buf, self._mask_pos = [], None, None, 0
+        if self._mask_seed is None:
+            self._mask_seed = seed
+        self._mask_rec.append(n)
+        blocks = (n + 127) // 128
+        buf = self._mask_buf
+        if buf is not None:
+            pseed, sizes = self._mask_plan
+            k = self._mask_pos
+            if k < len(sizes) and sizes[k] == n and pseed == seed and self.rng_offset * 128 + n <= buf.numel():
+                m = buf[self.rng_offset * 128:self.rng_offset * 128 + n]
+                self._mask_pos += 1
+                self.rng_offset += blocks
+                return m
+            self._mask_buf = None                 # the step departs from the plan: per-mask launches from here on
         m = torch.empty(n, dtype=torch.uint8, device=self.device)
         L.call('mopoe_dropout_mask', L.ptr(m), n, int(seed) & (2 ** 64 - 1), self.rng_offset, L.ptr(self.rng_step),
                L.stream_ptr())
-        self.rng_offset += (n + 127) // 128
+        self.rng_offset += blocks
         return m
 
     # ---- implicit-GEMM problem builders -------------------------------------------------------------------
