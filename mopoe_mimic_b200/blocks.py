@@ -229,6 +229,18 @@ class ResBlockFn(torch.autograd.Function):
                 return None
             return eng.colsum(act)
 
+        # weight gradients (and the bias column sums) that accumulate straight into the flat gradient run on the side
+        # stream of this branch (Engine.wgrad_side): nothing in this backward chain reads them
+        flat = all(grad_slot(po[n]) is not None for n in sp.param_names())
+
+        def deferred(fn, *operands):
+            side = eng.wgrad_side() if flat else None
+            if side is None:
+                return fn()
+            eng.wgrad_keep(*[o.t for o in operands])
+            with torch.cuda.stream(side):
+                return fn()
+
         # y = a*BN3(r) + b*(c*2m2)
         dg, db, acc = bn_slots(short + '.1')
         dr, dc = eng.combine_bwd(dy, sp.a, r, st3, P[short + '.1.weight'], dg, db,
@@ -236,7 +248,7 @@ class ResBlockFn(torch.autograd.Function):
                                  Act.empty(B, OH, OW, sp.cout, bph, bpw, dt, eng.device), accumulate=acc)
         # shortcut conv
         Ws_ = P[short + '.0.weight']
-        G[short + '.0.weight'] = _main_wgrad(eng, sp, x, dr, po[short + '.0.weight'])
+        G[short + '.0.weight'] = deferred(lambda: _main_wgrad(eng, sp, x, dr, po[short + '.0.weight']), x, dr)
         # the shortcut bias feeds a train-mode BatchNorm: its gradient sum(dr) is analytically zero (BN backward
         # output sums to zero per channel); the reference only accumulates rounding noise there
         G[short + '.0.bias'] = None if grad_slot(po[short + '.0.bias']) is not None else \
@@ -244,9 +256,9 @@ class ResBlockFn(torch.autograd.Function):
         dxs = _main_dgrad(eng, sp, dr, Ws_, dt, H, W)
         # conv2
         W2 = P['conv2.weight']
-        G['conv2.weight'] = _main_wgrad(eng, sp, a2, dc, po['conv2.weight'])
+        G['conv2.weight'] = deferred(lambda: _main_wgrad(eng, sp, a2, dc, po['conv2.weight']), a2, dc)
         if sp.inner_bias:
-            G['conv2.bias'] = bias_grad('conv2.bias', dc)
+            G['conv2.bias'] = deferred(lambda: bias_grad('conv2.bias', dc), dc)
         da2 = _main_dgrad(eng, sp, dc, W2, dt, H, W)
         # relu, bn2, dropout1
         # (recomputing the ReLU gate from hh instead of re-reading a2 was measured SLOWER on B200: these passes are
@@ -256,14 +268,15 @@ class ResBlockFn(torch.autograd.Function):
                         Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device), accumulate=acc)
         # conv1 (1x1): weight [n_out, c_in, 1..] (conv) or [c_in, n_out, 1..] (transposed conv)
         w1p = po['conv1.weight']
-        done = eng.wgrad_rows_param(dh, a1, w1p) if sp.transposed else eng.wgrad_rows_param(a1, dh, w1p)
+        done = deferred(lambda: eng.wgrad_rows_param(dh, a1, w1p) if sp.transposed else eng.wgrad_rows_param(a1, dh, w1p),
+                        a1, dh)
         if done:
             G['conv1.weight'] = None
         else:
             g1 = eng.wgrad_rows(a1, dh)                               # [n_out, c_in]
             G['conv1.weight'] = (g1.t() if sp.transposed else g1).reshape(P['conv1.weight'].shape)
         if sp.inner_bias:
-            G['conv1.bias'] = bias_grad('conv1.bias', dh)
+            G['conv1.bias'] = deferred(lambda: bias_grad('conv1.bias', dh), dh)
         w1b = eng.packed(P['conv1.weight'], 'mat' if sp.transposed else 'matT')   # [c_in, n_out]
         da1 = eng.gemm_rows(dh, w1b, None, sp.cin)
         # relu, bn1 (+ the shortcut's input gradient)

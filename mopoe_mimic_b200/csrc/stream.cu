@@ -380,8 +380,13 @@ struct CombineBody {          // out = a * BN(r) + b * (c * 2mask)   [+ per-chan
             raw[j][0].unpack(rv);
             raw[j][1].unpack(cv);
             if (mk.mode == MOPOE_MASK_ELEM) mask_mul<KS>(mk, pre, j, m);
+            if (mk.mode == MOPOE_MASK_NONE) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) o[i] = fmaf(rv[i], sc[i], sh[i]) + bcoef * (cv[i] * m[i]);
+                for (int i = 0; i < VEC; ++i) o[i] = fmaf(rv[i], sc[i], sh[i]) + bcoef * cv[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) o[i] = fmaf(rv[i], sc[i], sh[i]) + bcoef * (cv[i] * m[i]);
+            }
             st8<T>(orow + j * g.CH * VEC, o);
             if (STATS) {
                 // the statistics the NEXT block's bn1 needs are those of the values it will read: rounded to the storage type
@@ -512,11 +517,19 @@ struct ReduceBody {
             raw[j][0].unpack(xv);
             if (mk.mode == MOPOE_MASK_ELEM) mask_mul<KS>(mk, pre, j, m);
             if (MODE == 0) {
+                if (mk.mode == MOPOE_MASK_NONE) {            // (the pass is instruction-bound: no multiply by 1)
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    const float v = xv[i] * m[i];
-                    f0[i] += v;
-                    f1[i] = fmaf(v, v, f1[i]);
+                    for (int i = 0; i < VEC; ++i) {
+                        f0[i] += xv[i];
+                        f1[i] = fmaf(xv[i], xv[i], f1[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const float v = xv[i] * m[i];
+                        f0[i] += v;
+                        f1[i] = fmaf(v, v, f1[i]);
+                    }
                 }
             } else if (MODE == 2) {
 #pragma unroll
@@ -525,13 +538,24 @@ struct ReduceBody {
                 float gv[VEC], gt[VEC];
                 raw[j][1].unpack(gv);
                 if (GATE) raw[j][NOPS - 1].unpack(gt);
+                if (mk.mode == MOPOE_MASK_NONE) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) {
-                    float gg = gscale * gv[i];
-                    if (GATE && !(gt[i] > 0.f)) gg = 0.f;
-                    const float xh = (xv[i] * m[i] - mu[i]) * is[i];
-                    f0[i] += gg;
-                    f1[i] = fmaf(gg, xh, f1[i]);
+                    for (int i = 0; i < VEC; ++i) {
+                        float gg = gscale * gv[i];
+                        if (GATE && !(gt[i] > 0.f)) gg = 0.f;
+                        const float xh = (xv[i] - mu[i]) * is[i];
+                        f0[i] += gg;
+                        f1[i] = fmaf(gg, xh, f1[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        float gg = gscale * gv[i];
+                        if (GATE && !(gt[i] > 0.f)) gg = 0.f;
+                        const float xh = (xv[i] * m[i] - mu[i]) * is[i];
+                        f0[i] += gg;
+                        f1[i] = fmaf(gg, xh, f1[i]);
+                    }
                 }
             }
         }

@@ -86,6 +86,8 @@ class Engine:
         self.persistent = os.environ.get('MOPOE_GEMM_PERSISTENT', '1') != '0'   # persistent kernel for single GEMMs too
         self.fuse_stats = os.environ.get('MOPOE_FUSE_BN_STATS', '1') != '0'     # BatchNorm statistics in the GEMM epilogue
         self.fuse_next_stats = os.environ.get('MOPOE_FUSE_NEXT_BN_STATS', '1') != '0'   # next block's bn1 statistics in combine
+        self.wgrad_streams = os.environ.get('MOPOE_WGRAD_STREAMS', '0') != '0'          # weight gradients on side streams (opt-in: measured +-0.1 ms)
+        self._wg_streams, self._wg_used, self._wg_keep = {}, set(), []
 
     # ---- packed-weight cache ---------------------------------------------------------------------------------
     # Every (weight, form) has a persistent SLOT (destination buffers with fixed addresses).  A slot is valid while its
@@ -288,6 +290,41 @@ class Engine:
     def convert(self, src_view, nchw, dst):
         L.call('mopoe_convert', C.byref(src_view), int(nchw), C.byref(dst.view()), L.stream_ptr())
         return dst
+
+    # ---- weight-gradient side streams ------------------------------------------------------------------------
+    # A block's weight gradients feed nothing but the optimizer, while its input gradients sit on the critical chain
+    # dgrad -> BN sums -> finalize -> BN apply -> dgrad ...  In the deep stages that chain is a string of 5-us launches on a
+    # handful of SMs and the weight-gradient GEMMs (large weights there) are the bulk of the work: they go to a side stream
+    # of the branch stream they were issued from and overlap the chain.  The side streams are joined before anything
+    # reads the flat gradient (FlatAdam.step / the decoders' bucket), and the operands of the deferred kernels are kept
+    # alive until then (the caching allocator would otherwise hand their memory to the branch stream's next tensors).
+    def wgrad_side(self):
+        """the side stream paired with the current stream, forked at this point (None: disabled / gradients not flat)"""
+        if not self.wgrad_streams or os.environ.get('MOPOE_BRANCH_STREAMS', '1') == '0':      # (bench.py flips it at run time)
+            return None
+        cur = torch.cuda.current_stream()
+        key = cur.cuda_stream
+        st = self._wg_streams.get(key)
+        if st is None:
+            st = self._wg_streams[key] = torch.cuda.Stream()
+        st.wait_stream(cur)
+        self._wg_used.add(key)
+        return st
+
+    def wgrad_keep(self, *tensors):
+        self._wg_keep.extend(tensors)
+
+    def join_wgrad_sides(self, final=True):
+        """make the current stream wait for every weight-gradient side stream used since the last final join.  final:
+        the caller is the step's last join (everything later is ordered behind the current stream): the operands kept
+        alive for the deferred kernels may go.  A non-final join (the decoders' optimizer bucket, itself on a side stream)
+        must keep them: the branch streams do not wait here and would reuse the memory."""
+        cur = torch.cuda.current_stream()
+        for key in sorted(self._wg_used):
+            cur.wait_stream(self._wg_streams[key])
+        if final:
+            self._wg_used = set()
+            self._wg_keep = []
 
     # ---- dropout keep-masks --------------------------------------------------------------------------------
     # Mask k of a step covers the Philox counter blocks [off_k, off_k + ceil(n_k / 128)) (128 mask bytes per counter), so

@@ -317,6 +317,8 @@ class MMVaeMimic(BaseMMVae):
         for i in sorted(self.__dict__.get('_side_used', ())):
             cur.wait_stream(side[i - 1])
         self.__dict__['_side_used'] = set()
+        if self.rt.engine is not None:
+            self.rt.engine.join_wgrad_sides()      # the weight-gradient side streams of the branches
 
     @staticmethod
     def _touch(stream, *tensors):

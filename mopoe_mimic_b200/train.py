@@ -156,6 +156,7 @@ class FlatAdam:
         cur = torch.cuda.current_stream()
         self._xs.wait_stream(cur)
         with torch.cuda.stream(self._xs):
+            eng.join_wgrad_sides(final=False)       # the decoders' weight gradients were accumulated on side streams
             self._advance(eng)
             if self.exchange is not None:
                 self.exchange.adam_step(self.m, self.v, self.coef, self.betas, self.eps, bucket=0, max_blocks=self.side_blocks)
