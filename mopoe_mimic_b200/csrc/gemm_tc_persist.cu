@@ -30,7 +30,7 @@ int mopoe_tc_init_state();
 void mopoe_tc_tile_split(int E0, int E1, int rows, int& BX, int& BY, int& NB);
 int mopoe_tc_pick_bn(int N);
 
-constexpr int TCP_THREADS = 192;
+constexpr int TCP_THREADS = 320;      // TMA warp, MMA warp, 4 epilogue warps, 4 statistics warps
 constexpr int TCP_SMEM_LIMIT = 232448;
 constexpr int TCP_MAXP = 4;
 
@@ -59,6 +59,12 @@ struct TcPersistParams {
 };
 
 constexpr int EPI_BAR = 1;        // named barrier of the 4 epilogue warps
+constexpr int STG_FULL_BAR = 2;   // +buffer: staging tile written (128 epilogue threads arrive, 128 statistics threads wait)
+constexpr int STG_FREE_BAR = 4;   // +buffer: statistics warps are done reading it (they arrive, the epilogue threads wait)
+constexpr int STAT_BAR = 6;       // the 4 statistics warps among themselves
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 constexpr uint32_t STG_BYTES = 128 * 128;   // one staging tile: 128 rows x 64 bf16, SWIZZLE_128B
 
 template <bool TMA_EPI>
@@ -163,18 +169,16 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                 umma_commit(tfull0 + 8 * acc);
             }
         }
-    } else if constexpr (TMA_EPI) {
+    } else if (TMA_EPI && warp < 6) {
         // ===== TMA-store epilogue (bf16 output, BN % 64 == 0): 4 warps, warp q owns TMEM lanes / tile rows [32q, 32q+32) =====
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const bool leader = threadIdx.x == 64;                     // issues the bulk stores of this CTA
-        const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
         const bool stats = p.st.ws != nullptr;
-        if (stats)
-            for (int i = threadIdx.x - 64; i < 8 * p.nacc; i += 128) sacc[i] = 0.f;
-        if (p.bias)                                                // the bias row, zero-padded to the tile grid
+        if (p.bias) {                                              // the bias row, zero-padded to the tile grid
             for (int i = threadIdx.x - 64; i < p.nacc; i += 128) const_cast<float*>(sbias)[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
-        if (stats || p.bias) named_bar_sync(EPI_BAR, 128);
+            named_bar_sync(EPI_BAR, 128);
+        }
         const uint32_t swz = (uint32_t)(row & 7);
         int iter = 0;
         uint32_t sbuf = 0;
@@ -186,25 +190,6 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             const int prob = tq % p.nprob, mt = tq / p.nprob;
             const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
             const int n0 = nt * p.BN;
-            const int m0 = t0 * p.BX + i1, m1 = t1 * p.BY + i2, m2 = t2 * p.NB + i4;
-            const bool rvalid = m0 < p.E0 && m1 < p.E1 && m2 < p.E2;
-            const unsigned flat = (unsigned)((m2 * p.E1 + m1) * p.E0 + m0);        // flat output row (host checks < 2^31)
-            const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
-            // row key of the dropout mask: sample index (Dropout2d mask [B, N]) or flat row (elementwise mask [rows, N])
-            const unsigned mykey = p.st.mask_mode == MOPOE_MASK_BC ? flat / (unsigned)p.st.rows_per_b : flat;
-            const unsigned key_lo = __shfl_sync(0xffffffffu, mykey, 0), key_hi = __shfl_sync(0xffffffffu, mykey, 31);
-            // Dropout2d mask, all 32 rows of the warp in one sample: ONE mask value per column — fetched here, before the
-            // wait for the accumulator, so that its L2 round trip is off the epilogue's critical path
-            const bool warp_mask = stats && p.st.mask_mode == MOPOE_MASK_BC && key_lo == key_hi;
-            unsigned long long mkw = 0ull;                        // 4 groups x 16 bits
-            if (warp_mask) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int cn = n0 + g * 64 + 2 * lane;
-                    if (g * 64 < p.BN && cn < p.N)
-                        mkw |= (unsigned long long)*reinterpret_cast<const unsigned short*>(p.st.mask + (size_t)key_lo * p.N + cn) << (16 * g);
-                }
-            }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -245,8 +230,10 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                         w[16 + j] = *reinterpret_cast<uint32_t*>(&hb);
                     }
                 }
-                // the staging tile we are about to overwrite: its previous bulk store must have finished READING it
+                // the staging tile we are about to overwrite: its previous bulk store must have finished READING it, and the
+                // statistics warps must be done with it
                 if (leader) bulk_wait_read<1>();
+                if (stats) named_bar_sync(STG_FREE_BAR + (int)sbuf, 256);
                 named_bar_sync(EPI_BAR, 128);
                 const uint32_t stg = stg0 + sbuf * STG_BYTES;
                 const uint32_t rbase = stg + (uint32_t)row * 128u;
@@ -254,17 +241,71 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                 for (int ch = 0; ch < 8; ++ch)                      // 16-byte chunk ch of the row -> swizzled slot
                     st_shared_v4(rbase + ((((uint32_t)ch) ^ swz) << 4), w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
                 fence_proxy_async_smem();
-                if (stats) {
-                    // Column sums over THIS warp's 32 rows (written by this warp: a warp-level sync suffices).  Lane l owns
-                    // columns c0 + 2l, c0 + 2l + 1: one 128-byte row per load, conflict-free.  All 32 loads are issued
-                    // before the first use (a dependent load -> add chain per row is pure latency with 4 warps per SM).
-                    __syncwarp();
+                if (stats) named_bar_arrive(STG_FULL_BAR + (int)sbuf, 256);   // the statistics warps may read the tile
+                named_bar_sync(EPI_BAR, 128);                       // all 128 rows are in the staging tile and fenced
+                if (leader) {
+                    tma_store_4d(&maps.d[prob], stg, c0, t0 * p.BX, t1 * p.BY, t2 * p.NB);
+                    bulk_commit();
+                }
+                sbuf ^= 1u;
+            }
+        }
+        if (leader) bulk_wait<0>();                                 // the last stores have landed before the CTA exits
+        if (stats) {                                                // drain: pairs with the statistics warps' last arrivals
+            named_bar_sync(STG_FREE_BAR, 256);
+            named_bar_sync(STG_FREE_BAR + 1, 256);
+        }
+    } else if (TMA_EPI) {
+        // ===== statistics warps (fused BatchNorm statistics): warp q sums rows [32q, 32q+32) of every staged 128 x 64 tile
+        // column-wise while the epilogue warps already convert the next group.  (Round 2, first cut: the epilogue warps did
+        // this themselves — on short-K layers, where the epilogue is the critical path, it doubled the kernel: 158 us against
+        // 87 for the M = 1M 1x1 layer.)
+        const bool stats = p.st.ws != nullptr;
+        if (stats) {
+            const int q = warp - 6;
+            const int row = q * 32 + lane;
+            const int st_tid = threadIdx.x - 192;
+            const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
+            for (int i = st_tid; i < 8 * p.nacc; i += 128) sacc[i] = 0.f;
+            named_bar_sync(STAT_BAR, 128);
+            named_bar_arrive(STG_FREE_BAR, 256);                    // both staging tiles start out free
+            named_bar_arrive(STG_FREE_BAR + 1, 256);
+            uint32_t sbuf = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.NT;
+                const int tq = tile / p.NT;
+                const int mt = tq / p.nprob;
+                const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
+                const int n0 = nt * p.BN;
+                const int m0 = t0 * p.BX + i1, m1 = t1 * p.BY + i2, m2 = t2 * p.NB + i4;
+                const bool rvalid = m0 < p.E0 && m1 < p.E1 && m2 < p.E2;
+                const unsigned flat = (unsigned)((m2 * p.E1 + m1) * p.E0 + m0);        // flat output row (host checks < 2^31)
+                const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
+                // row key of the dropout mask: sample index (Dropout2d mask [B, N]) or flat row (elementwise mask [rows, N])
+                const unsigned mykey = p.st.mask_mode == MOPOE_MASK_BC ? flat / (unsigned)p.st.rows_per_b : flat;
+                const unsigned key_lo = __shfl_sync(0xffffffffu, mykey, 0), key_hi = __shfl_sync(0xffffffffu, mykey, 31);
+                // Dropout2d mask, all 32 rows of the warp in one sample: ONE mask value per column
+                const bool warp_mask = p.st.mask_mode == MOPOE_MASK_BC && key_lo == key_hi;
+                unsigned long long mkw = 0ull;                        // 4 groups x 16 bits
+                if (warp_mask) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int cn = n0 + g * 64 + 2 * lane;
+                        if (g * 64 < p.BN && cn < p.N)
+                            mkw |= (unsigned long long)*reinterpret_cast<const unsigned short*>(p.st.mask + (size_t)key_lo * p.N + cn) << (16 * g);
+                    }
+                }
+                const int ngroups = p.BN >> 6;
+                for (int g = 0; g < ngroups; ++g) {
+                    const int c0 = n0 + g * 64;
+                    const uint32_t stg = stg0 + sbuf * STG_BYTES;
+                    // Lane l owns columns c0 + 2l, c0 + 2l + 1: one 128-byte row per load, conflict-free.
                     const int cn = c0 + 2 * lane;
                     const bool cvalid = cn < p.N;
                     const uint32_t jchunk = (uint32_t)lane >> 2, wsel = ((uint32_t)lane & 3u) << 2;
                     const uint32_t lbase = stg + (uint32_t)(q * 32) * 128u + wsel;
                     // dropout mask between this GEMM and the BatchNorm: per row (elementwise mask, or a Dropout2d mask when
-                    // the warp's rows span several samples) — global loads issued ahead of the shared-memory reads
+                    // the warp's rows span several samples) — global loads issued ahead of the wait for the tile
                     const bool row_masks = p.st.mask_mode == MOPOE_MASK_ELEM || (p.st.mask_mode == MOPOE_MASK_BC && key_lo != key_hi);
                     unsigned short mk[32];
                     if (row_masks) {
@@ -275,6 +316,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                                         ? *reinterpret_cast<const unsigned short*>(p.st.mask + (size_t)key * p.N + cn) : (unsigned short)0;
                         }
                     }
+                    named_bar_sync(STG_FULL_BAR + (int)sbuf, 256);      // the epilogue warps have written (and fenced) the tile
                     uint32_t wv[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) wv[i] = ld_shared_b32(lbase + (uint32_t)i * 128u + ((jchunk ^ (uint32_t)(i & 7)) << 4));
@@ -297,10 +339,12 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                             else { sa0 += x0; sa1 += x1; qa0 = fmaf(x0, x0, qa0); qa1 = fmaf(x1, x1, qa1); }
                         }
                     }
+                    // (the values are in registers: the tile may be overwritten)
+                    named_bar_arrive(STG_FREE_BAR + (int)sbuf, 256);
                     float s0 = sa0 + sb0, s1 = sa1 + sb1, q0 = qa0 + qb0, q1 = qa1 + qb1;
                     if (warp_mask) {
-                        const unsigned mk = (unsigned)(mkw >> (16 * (g & 3))) & 0xffffu;
-                        const float f0 = (mk & 0xffu) ? 2.f : 0.f, f1 = (mk & 0xff00u) ? 2.f : 0.f;
+                        const unsigned mkv = (unsigned)(mkw >> (16 * (g & 3))) & 0xffffu;
+                        const float f0 = (mkv & 0xffu) ? 2.f : 0.f, f1 = (mkv & 0xff00u) ? 2.f : 0.f;
                         s0 *= f0; q0 *= f0 * f0;
                         s1 *= f1; q1 *= f1 * f1;
                     }
@@ -311,24 +355,16 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                         a[p.nacc] += q0;
                         a[p.nacc + 1] += q1;
                     }
+                    sbuf ^= 1u;
                 }
-                named_bar_sync(EPI_BAR, 128);                       // all 128 rows are in the staging tile and fenced
-                if (leader) {
-                    tma_store_4d(&maps.d[prob], stg, c0, t0 * p.BX, t1 * p.BY, t2 * p.NB);
-                    bulk_commit();
-                }
-                sbuf ^= 1u;
             }
-        }
-        if (leader) bulk_wait<0>();                                 // the last stores have landed before the CTA exits
-        if (stats) {
-            named_bar_sync(EPI_BAR, 128);
-            for (int i = threadIdx.x - 64; i < 8 * p.N; i += 128) {
+            named_bar_sync(STAT_BAR, 128);
+            for (int i = st_tid; i < 8 * p.N; i += 128) {
                 const int n = i % p.N, k = i / p.N;                 // k = q * 2 + which
                 p.st.ws[((size_t)blockIdx.x * 8 + k) * p.N + n] = (double)sacc[(size_t)k * p.nacc + n];
             }
         }
-    } else {
+    } else if (warp < 6) {
         // ===== epilogue: 4 warps, warp q owns TMEM lanes [32q, 32q+32) =====
         const int q = warp & 3;
         const int row = q * 32 + lane;
