@@ -67,14 +67,23 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 }
 constexpr uint32_t STG_BYTES = 128 * 128;   // one staging tile: 128 rows x 64 bf16, SWIZZLE_128B
 
-template <bool TMA_EPI>
+// PAIR: the kernel runs as clusters of 2 CTAs (one TPC) that execute ONE 256 x BN tcgen05.mma.cta_group::2 per k-step: CTA r
+// holds the 128 rows of ITS m-tile (2*mp + r) and columns [r*BN/2, (r+1)*BN/2) of the weight tile, the leader (r = 0)
+// issues the MMAs, each CTA's TMEM receives the 128 x BN accumulator of its own rows.  Why: the single-CTA kernel is bound by
+// the SM's operand fill — ncu: 65-67 B/clk/SM of L2->shared traffic on the 128 x 256 layers (75 % tensor pipe), 57 B/clk on
+// the 128 x 128 layers (47 %): a CTA moves 48 KB per 128x256x64 k-step (85 flop/B).  A pair moves 32 KB per CTA for the same
+// math (128 flop/B); N = 128 layers 24 KB instead of 32 (85 instead of 64 flop/B).
+template <bool TMA_EPI, bool PAIR>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersistParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* const gen = smem_raw + (base - raw);
-    const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)p.BN * 128;
+    const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)p.BN * (PAIR ? 64 : 128);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t stage_bytes = a_bytes + b_bytes;
     // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | statistics accumulators] | header
     const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;
@@ -106,13 +115,17 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull0 + 8 * s, 1);
-            mbar_init(tempty0 + 8 * s, 128);
+            mbar_init(tempty0 + 8 * s, PAIR ? 2 : 128);           // pair: one (remote) arrival per CTA, at the leader
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols);
+        else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
     fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();                                  // the peer's barriers exist before anything signals them
+    else __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -121,13 +134,14 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             // ===== TMA producer =====
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const uint32_t full_leader0 = PAIR ? mapa_shared(full0, 0) : full0;     // pair: bytes are counted at the leader
+            for (int tile = tile_first; tile < p.total_tiles; tile += tile_step) {
                 // tile order (m-tile, problem, n-tile): the sub-pixel phases of one pixel block run side by side, so
                 // their (overlapping) activation windows are fetched from DRAM once — problem-major order re-read the
                 // whole input per phase (ncu: 568 MB read for a 151 MB operand)
                 const int nt = tile % p.NT;
                 const int tq = tile / p.NT;
-                const int prob = tq % p.nprob, mt = tq / p.nprob;
+                const int prob = tq % p.nprob, mt = PAIR ? 2 * (tq / p.nprob) + (int)rank : tq / p.nprob;
                 const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
                 const int n0 = nt * p.BN;
                 const CUtensorMap* ma = &maps.a[prob];
@@ -136,21 +150,27 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     const int r = it / kpw, kc = it - r * kpw;
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
-                    mbar_expect_tx(full0 + 8 * stage, stage_bytes);
-                    tma_load_5d(sa, ma, full0 + 8 * stage, kc * 64, t0 * p.BX, t1 * p.BY, r, t2 * p.NB);
-                    tma_load_2d(sb, mb, full0 + 8 * stage, r * p.KW + kc * 64, n0);
+                    if (PAIR) {
+                        if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * stage_bytes);
+                        tma_load_5d_2cta(sa, ma, full_leader0 + 8 * stage, kc * 64, t0 * p.BX, t1 * p.BY, r, t2 * p.NB);
+                        tma_load_2d_2cta(sb, mb, full_leader0 + 8 * stage, r * p.KW + kc * 64, n0 + (int)rank * (p.BN >> 1));
+                    } else {
+                        mbar_expect_tx(full0 + 8 * stage, stage_bytes);
+                        tma_load_5d(sa, ma, full0 + 8 * stage, kc * 64, t0 * p.BX, t1 * p.BY, r, t2 * p.NB);
+                        tma_load_2d(sb, mb, full0 + 8 * stage, r * p.KW + kc * 64, n0);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
-            const uint32_t idesc = make_idesc_bf16(128, p.BN, 0, 0);
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (pair: the leader CTA only) =====
+            const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+            for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);      // epilogue has drained this accumulator buffer
@@ -161,12 +181,19 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     fence_after();
                     const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
                     const uint64_t da = smem_desc_sw128(sa, 0, 1024), db = smem_desc_sw128(sb, 0, 1024);
+                    if (PAIR) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
-                    umma_commit(empty0 + 8 * stage);
+                        for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                        umma_commit_2cta(empty0 + 8 * stage, 3);             // frees the stage in BOTH CTAs
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                        umma_commit(empty0 + 8 * stage);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull0 + 8 * acc);
+                if (PAIR) umma_commit_2cta(tfull0 + 8 * acc, 3);             // both CTAs' epilogues
+                else umma_commit(tfull0 + 8 * acc);
             }
         }
     } else if (TMA_EPI && warp < 6) {
@@ -182,12 +209,13 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         const uint32_t swz = (uint32_t)(row & 7);
         int iter = 0;
         uint32_t sbuf = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+        const uint32_t tempty_leader0 = PAIR ? mapa_shared(tempty0, 0) : tempty0;
+        for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
             const int nt = tile % p.NT;
             const int tq = tile / p.NT;
-            const int prob = tq % p.nprob, mt = tq / p.nprob;
+            const int prob = tq % p.nprob, mt = PAIR ? 2 * (tq / p.nprob) + (int)rank : tq / p.nprob;
             const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
             const int n0 = nt * p.BN;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
@@ -203,7 +231,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                 if (g == ngroups - 1) {
                     // every TMEM read of this accumulator buffer is complete: hand it back before the stores
                     fence_before();
-                    mbar_arrive(tempty0 + 8 * acc);
+                    if (!PAIR) mbar_arrive(tempty0 + 8 * acc);
                 }
                 uint32_t w[32];                                     // 64 bf16, packed
                 if (p.bias) {
@@ -235,6 +263,8 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                 if (leader) bulk_wait_read<1>();
                 if (stats) named_bar_sync(STG_FREE_BAR + (int)sbuf, 256);
                 named_bar_sync(EPI_BAR, 128);
+                // pair: all 128 threads of this CTA are past their last TMEM load: ONE arrival at the leader's barrier
+                if (PAIR && g == ngroups - 1 && leader) mbar_arrive_cluster(tempty_leader0 + 8 * acc);
                 const uint32_t stg = stg0 + sbuf * STG_BYTES;
                 const uint32_t rbase = stg + (uint32_t)row * 128u;
 #pragma unroll
@@ -271,10 +301,10 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             named_bar_arrive(STG_FREE_BAR, 256);                    // both staging tiles start out free
             named_bar_arrive(STG_FREE_BAR + 1, 256);
             uint32_t sbuf = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < p.total_tiles; tile += tile_step) {
                 const int nt = tile % p.NT;
                 const int tq = tile / p.NT;
-                const int mt = tq / p.nprob;
+                const int mt = PAIR ? 2 * (tq / p.nprob) + (int)rank : tq / p.nprob;
                 const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
                 const int n0 = nt * p.BN;
                 const int m0 = t0 * p.BX + i1, m1 = t1 * p.BY + i2, m2 = t2 * p.NB + i4;
@@ -370,7 +400,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         const int row = q * 32 + lane;
         const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
         int iter = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++iter) {
+        for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
             const int nt = tile % p.NT;
@@ -429,13 +459,26 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         }
         }
     fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (PAIR) {
+        cluster_sync_all();                    // no remote arrival / pair MMA may still target a CTA that tears down
+        if (warp == 1) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
 }
 
 static bool g_persist_attr_set = false;
 static int g_num_sms = 0;
 
+static int pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_GEMM_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
 static int tma_epi_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -491,9 +534,11 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     p.bias = bias;
     p.st.ws = nullptr; p.st.mask = nullptr; p.st.mask_mode = MOPOE_MASK_NONE; p.st.rows_per_b = 1;
     if (!g_persist_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+            e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
         if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         int dev = 0;
         cudaGetDevice(&dev);
@@ -501,7 +546,7 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         if (g_num_sms <= 0) g_num_sms = 148;
         g_persist_attr_set = true;
     }
-    const int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
+    int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
     // TMA-store epilogue: bf16 rows whose strides / origins are 16-byte aligned, 64-column groups
     bool tma_epi = tma_epi_enabled() && p.d_is_bf16 && p.BN % 64 == 0 && p.N % 8 == 0 && p.s0 % 8 == 0 && p.s1 % 8 == 0 &&
                    p.s2 % 8 == 0 && (reinterpret_cast<uintptr_t>(p.d) & 15) == 0 &&
@@ -516,7 +561,24 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         p.st.mask_mode = stats->mask_mode;
         p.st.rows_per_b = stats->rows_per_b > 0 ? stats->rows_per_b : 1;
     }
-    const int stage_bytes = 128 * 128 + p.BN * 128;
+    // CTA pairs (cta_group::2) when the TMA-store epilogue applies and there is at least a full wave of single-CTA tiles
+    const int m_tiles = p.T0 * p.T1 * p.T2;
+    // ... and the tile is wide: measured, N = 128 layers gain nothing from the pair (906 vs 925 TFLOP/s — whatever bounds
+    // them, it is not the operand fill), N >= 192 layers gain 10-15 % (1441 -> 1605, 1213 -> 1403 TFLOP/s)
+    static int pair_min_bn = -1;
+    if (pair_min_bn < 0) {
+        const char* e = getenv("MOPOE_GEMM_PAIR_MIN_BN");
+        pair_min_bn = e ? atoi(e) : 192;
+    }
+    const bool pair = pair_enabled() && tma_epi && p.BN % 64 == 0 && p.BN >= pair_min_bn && p.total_tiles >= g_num_sms &&
+                      g_num_sms % 2 == 0;
+    if (pair) {
+        p.total_tiles = ((m_tiles + 1) / 2) * nprob * p.NT;          // pair tiles: two consecutive m-tiles x one n-tile
+        const int clusters = p.total_tiles < g_num_sms / 2 ? p.total_tiles : g_num_sms / 2;
+        grid = 2 * clusters;
+        if (stats && stats->ws && (size_t)grid * 8 * p.N > stats->ws_doubles) { fuse_stats = false; p.st.ws = nullptr; }
+    }
+    const int stage_bytes = 128 * 128 + p.BN * (pair ? 64 : 128);
     const int hdr_bytes = 16 * 8 + 48 + 64;
     const int extra = tma_epi ? 2 * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) + (bias ? 4 * p.nacc : 0) : 0;
     int stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes - extra) / stage_bytes;
@@ -540,7 +602,7 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         const uint64_t K = (uint64_t)A[i].R * A[i].KW;
         const uint64_t dimsb[2] = {K, (uint64_t)p.N};
         const uint64_t strb[2] = {1, K};
-        const uint32_t boxb[2] = {64, (uint32_t)p.BN};
+        const uint32_t boxb[2] = {64, (uint32_t)(pair ? p.BN / 2 : p.BN)};
         if (mopoe_tc_encode(&maps.b[i], Wp[i], 2, dimsb, strb, boxb, "conv_gemm_tc(B)")) return 1;
         if (tma_epi) {
             const uint64_t dimsd[4] = {(uint64_t)p.N, (uint64_t)p.E0, (uint64_t)p.E1, (uint64_t)p.E2};
@@ -554,10 +616,23 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     if (!tma_epi) memset(maps.d, 0, sizeof(maps.d));
     else for (int i = nprob; i < TCP_MAXP; ++i) maps.d[i] = maps.d[0];
     const int smem = 1024 + stages * stage_bytes + extra + hdr_bytes;
-    if (tma_epi)
-        conv_gemm_tc_persist_kernel<true><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(TCP_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true>, maps, p);
+        if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc_pair: launch: %s", cudaGetErrorString(e));
+    } else if (tma_epi)
+        conv_gemm_tc_persist_kernel<true, false><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
     else
-        conv_gemm_tc_persist_kernel<false><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+        conv_gemm_tc_persist_kernel<false, false><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
     MOPOE_CHECK_LAUNCH("conv_gemm_tc_persist");
     if (fuse_stats && stats->nchunk_out) *stats->nchunk_out = grid * 4;
     return 0;

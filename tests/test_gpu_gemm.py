@@ -51,6 +51,11 @@ CASES = [
     (1, 4, 64, 128, 64),
     (1, 2, 128, 96, 512),
     (2, 5, 128, 640, 8),
+    # >= 148 output tiles: the CTA-pair kernel (tcgen05.mma.cta_group::2, 256-row MMAs over two SMs)
+    (2, 32, 64, 128, 64),        # 256 m-tiles x 1 n-tile (fprop), 4 phases x 1024 m-tiles (dgrad)
+    (2, 31, 64, 256, 40),        # 155 m-tiles: ODD -> the last pair's second CTA works on an out-of-range tile
+    (1, 64, 64, 128, 1024),      # 1-D
+    (2, 9, 128, 384, 32),        # BN = 192: 96 weight columns per CTA
 ]
 
 
@@ -145,6 +150,12 @@ BN_CASES = [
     ('down', 1, 3, 64, 512, 64, None),
     ('up', 2, 4, 128, 64, 8, None),              # shortcut deconv: 4 sub-pixel phases in one launch
     ('up', 1, 5, 64, 256, 32, None),             # 2 phases
+    # CTA-pair kernel (>= 148 tiles)
+    ('rows', 2, 20, 128, 128, 32, 'bc'),         # 160 m-tiles, Dropout2d mask
+    ('rows', 1, 21, 128, 256, 1000, 'elem'),     # 165 m-tiles (odd pairs), elementwise mask
+    ('down', 2, 19, 64, 256, 64, None),          # 152 m-tiles
+    ('up', 2, 10, 128, 64, 16, None),            # 4 phases x 20 m-tiles x 1 n-tile = 80 ... below the threshold: single-CTA path
+    ('up', 2, 40, 128, 128, 16, None),           # 4 phases x 80 m-tiles = 320 tiles
 ]
 
 
