@@ -430,10 +430,10 @@ def main():
             pass
         traffic, traffic_note = None, None
         try:       # dram bytes of the step's largest GEMM launch, from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_roofline_traffic.json')))
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_roofline_traffic.json')))
             traffic = tj['dram_bytes_read'] + tj['dram_bytes_written']
             traffic_note = ('NOT measured in this run: ncu --set full dram read+write of ONE launch (%s) from the committed '
-                            'capture profiles/r1_ncu_gemm_persist.txt; algorithmic bytes of that launch %.1f MB'
+                            'capture profiles/r2_ncu_gemm.txt; algorithmic bytes of that launch %.1f MB'
                             % (tj['kernel'], tj['algorithmic_bytes'] / 1e6))
         except Exception:
             pass
