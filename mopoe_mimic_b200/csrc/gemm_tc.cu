@@ -310,7 +310,8 @@ struct TcWgParams {
     long long K;                      // R*KW
     float* out;                       // dWp (Z == 1) or workspace [Z][N][K]
     int accumulate;
-    int NTN, tiles_out, items;        // persistent schedule: n-tiles, output tiles, tiles_out * Z work items
+    int NTN, tiles_out, items;        // persistent schedule: n-tiles (pair: n-tile PAIRS), output tiles, tiles_out * Z work items
+    int pair;                         // host only: CTA-pair kernel
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -434,6 +435,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 // the MMAs of item i+1 and the TMEM allocation / barrier set-up is paid once per SM instead of once per tile.
 // Items are ordered split-major: the CTAs running side by side work on the SAME pixel range, so the dY / window
 // tiles they share come out of L2.
+// PAIR: clusters of 2 CTAs run one 256 x BNJ tcgen05.mma.cta_group::2 per step: CTA r holds the dY tile of ITS n-tile
+// (2*np + r) and window columns [r*BNJ/2, (r+1)*BNJ/2) — 32 KB per CTA and k-step instead of 48 (ncu: the single-CTA kernel
+// sits at 51 B/clk/SM of operand fill with the tensor pipe 58 % active).
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapY,
                              const TcWgParams p) {
@@ -441,7 +446,11 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* const gen = smem_raw + (base - raw);
-    const uint32_t y_bytes = 2 * WG_BKM * 128, a_bytes = (uint32_t)(p.BNJ / 64) * WG_BKM * 128;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int item_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int item_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int nqd = PAIR ? p.BNJ / 128 : p.BNJ / 64;          // 64-column window chunks this CTA loads per stage
+    const uint32_t y_bytes = 2 * WG_BKM * 128, a_bytes = (uint32_t)nqd * WG_BKM * 128;
     const uint32_t stage_bytes = y_bytes + a_bytes;
     const uint32_t hdr = base + (uint32_t)p.stages * stage_bytes;
     // header: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
@@ -461,13 +470,17 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull0 + 8 * s, 1);
-            mbar_init(tempty0 + 8 * s, 128);
+            mbar_init(tempty0 + 8 * s, PAIR ? 2 : 128);           // pair: one (remote) arrival per CTA, at the leader
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_2cta(tmem_slot, (uint32_t)p.tmem_cols);
+        else tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    }
     fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -475,32 +488,43 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+            const uint32_t full_leader0 = PAIR ? mapa_shared(full0, 0) : full0;
+            for (int item = item_first; item < p.items; item += item_step) {
                 const int z = item / p.tiles_out, tile = item - z * p.tiles_out;
-                const int jt = tile / p.NTN, nt = tile - jt * p.NTN;
+                const int jt = tile / p.NTN, nt = PAIR ? 2 * (tile - jt * p.NTN) + (int)rank : tile - jt * p.NTN;
                 const int r = jt / p.JT, j0 = (jt - r * p.JT) * p.BNJ, n0 = nt * 128;
                 const int mt_begin = z * p.m_per_split, mt_end = min(p.TM, mt_begin + p.m_per_split);
                 for (int mt = mt_begin; mt < mt_end; ++mt) {
                     const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sy = base + stage * stage_bytes, sa = sy + y_bytes;
-                    const uint32_t bar = full0 + 8 * stage;
-                    mbar_expect_tx(bar, stage_bytes);
-                    tma_load_4d(sy, &mapY, bar, n0, t0 * p.bx, t1 * p.by, t2 * p.nb);
-                    tma_load_4d(sy + WG_BKM * 128, &mapY, bar, n0 + 64, t0 * p.bx, t1 * p.by, t2 * p.nb);
-                    for (int qd = 0; qd < p.BNJ / 64; ++qd)
-                        tma_load_5d(sa + qd * WG_BKM * 128, &mapA, bar, j0 + 64 * qd, t0 * p.bx, t1 * p.by, r, t2 * p.nb);
+                    if (PAIR) {
+                        const uint32_t bar = full_leader0 + 8 * stage;
+                        if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * stage_bytes);
+                        tma_load_4d_2cta(sy, &mapY, bar, n0, t0 * p.bx, t1 * p.by, t2 * p.nb);
+                        tma_load_4d_2cta(sy + WG_BKM * 128, &mapY, bar, n0 + 64, t0 * p.bx, t1 * p.by, t2 * p.nb);
+                        for (int qd = 0; qd < nqd; ++qd)
+                            tma_load_5d_2cta(sa + qd * WG_BKM * 128, &mapA, bar, j0 + (int)rank * (p.BNJ >> 1) + 64 * qd, t0 * p.bx,
+                                             t1 * p.by, r, t2 * p.nb);
+                    } else {
+                        const uint32_t bar = full0 + 8 * stage;
+                        mbar_expect_tx(bar, stage_bytes);
+                        tma_load_4d(sy, &mapY, bar, n0, t0 * p.bx, t1 * p.by, t2 * p.nb);
+                        tma_load_4d(sy + WG_BKM * 128, &mapY, bar, n0 + 64, t0 * p.bx, t1 * p.by, t2 * p.nb);
+                        for (int qd = 0; qd < nqd; ++qd)
+                            tma_load_5d(sa + qd * WG_BKM * 128, &mapA, bar, j0 + 64 * qd, t0 * p.bx, t1 * p.by, r, t2 * p.nb);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, p.BNJ, 1, 1);      // both operands MN-major
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BNJ, 1, 1);      // both operands MN-major
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++iter) {
+            for (int item = item_first; item < p.items; item += item_step, ++iter) {
                 const int z = item / p.tiles_out;
                 const int mt_begin = z * p.m_per_split, mt_end = min(p.TM, mt_begin + p.m_per_split);
                 const int nkb = mt_end - mt_begin;
@@ -514,22 +538,31 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
                     fence_after();
                     const uint32_t sy = base + stage * stage_bytes, sa = sy + y_bytes;
                     const uint64_t dy = smem_desc_sw128(sy, WG_BKM * 128, 1024), da = smem_desc_sw128(sa, WG_BKM * 128, 1024);
+                    if (PAIR) {
 #pragma unroll
-                    for (int k = 0; k < WG_BKM / 16; ++k)
-                        umma_bf16(d_tmem, dy + 128 * k, da + 128 * k, idesc, (it | k) != 0);
-                    umma_commit(empty0 + 8 * stage);
+                        for (int k = 0; k < WG_BKM / 16; ++k)
+                            umma_bf16_2cta(d_tmem, dy + 128 * k, da + 128 * k, idesc, (it | k) != 0);
+                        umma_commit_2cta(empty0 + 8 * stage, 3);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < WG_BKM / 16; ++k)
+                            umma_bf16(d_tmem, dy + 128 * k, da + 128 * k, idesc, (it | k) != 0);
+                        umma_commit(empty0 + 8 * stage);
+                    }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull0 + 8 * acc);
+                if (PAIR) umma_commit_2cta(tfull0 + 8 * acc, 3);
+                else umma_commit(tfull0 + 8 * acc);
             }
         }
     } else {
         const int q = warp & 3;
         const bool direct_acc = p.Z == 1 && p.accumulate;
+        const uint32_t tempty_leader0 = PAIR ? mapa_shared(tempty0, 0) : tempty0;
         int iter = 0;
-        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++iter) {
+        for (int item = item_first; item < p.items; item += item_step, ++iter) {
             const int z = item / p.tiles_out, tile = item - z * p.tiles_out;
-            const int jt = tile / p.NTN, nt = tile - jt * p.NTN;
+            const int jt = tile / p.NTN, nt = PAIR ? 2 * (tile - jt * p.NTN) + (int)rank : tile - jt * p.NTN;
             const int r = jt / p.JT, j0 = (jt - r * p.JT) * p.BNJ;
             const int n = nt * 128 + q * 32 + lane;
             const int acc = iter & 1;
@@ -561,12 +594,22 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
                 }
             }
             fence_before();
-            mbar_arrive(tempty0 + 8 * acc);
+            if (PAIR) {
+                named_bar_sync(1, 128);                                  // all 4 epilogue warps of this CTA have drained
+                if (threadIdx.x == 64) mbar_arrive_cluster(tempty_leader0 + 8 * acc);
+            } else {
+                mbar_arrive(tempty0 + 8 * acc);
+            }
         }
     }
     fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (PAIR) {
+        cluster_sync_all();
+        if (warp == 1) tmem_dealloc_2cta(tmem_base, (uint32_t)p.tmem_cols);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
 }
 
 void mopoe_split_reduce_launch(const float* ws, int Z, long long n, float* out, int accumulate, cudaStream_t st);
@@ -610,7 +653,17 @@ static void wg_plan(const mopoe_window_t* A, const mopoe_rows_t* dY, TcWgParams&
     p.BNJ = best;
     p.JT = (p.KW + p.BNJ - 1) / p.BNJ;
     p.tmem_cols = pow2_ceil(p.BNJ < 32 ? 32 : p.BNJ);
-    const int tiles_out = p.R * p.JT * ((p.N + 127) / 128);
+    // CTA pairs: two n-tiles of one window tile per cluster.  Only for an EVEN number of n-tiles (an odd count would spend a
+    // whole tile of MMAs on out-of-range rows: N = 384 -> 4 tiles for 3) and 128-column halves of the window tile.
+    const int ntn_single = (p.N + 127) / 128;
+    static int wg_pair = -1;
+    if (wg_pair < 0) {
+        const char* e = getenv("MOPOE_WGRAD_PAIR");
+        wg_pair = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.pair = wg_pair && wg_persistent() && ntn_single % 2 == 0 && p.BNJ % 128 == 0;
+    const int units = p.pair ? 74 : 148;               // concurrent work items: SMs, or SM pairs
+    const int tiles_out = p.R * p.JT * (p.pair ? ntn_single / 2 : ntn_single);
     // split count: fill the 148 SMs in whole waves (a 2.05-wave grid wastes a third of its time in the tail) while
     // keeping >= 8 pixel blocks per CTA and the partials workspace bounded
     const long long ws_cap = 1ll << 29;              // 512 MB of partials at most
@@ -619,9 +672,9 @@ static void wg_plan(const mopoe_window_t* A, const mopoe_rows_t* dY, TcWgParams&
     for (int z = 1; z <= 64 && z <= p.TM; ++z) {
         if (z > 1 && (p.TM / z < 8 || (long long)z * p.N * p.K * 4 > ws_cap)) break;
         const long long items = (long long)tiles_out * z;
-        const long long waves = (items + 147) / 148;
+        const long long waves = (items + units - 1) / units;
         if (waves > 4 && z > 1) break;
-        const double eff = (double)items / (double)(waves * 148);
+        const double eff = (double)items / (double)(waves * units);
         if (eff > best_eff + 0.02) { best_eff = eff; Z = z; }
     }
     if (wg_persistent()) {
@@ -631,24 +684,36 @@ static void wg_plan(const mopoe_window_t* A, const mopoe_rows_t* dY, TcWgParams&
         double best_t = 1e30;
         Z = 1;
         // few output tiles (the 16 x 128 tap gradients of the single-channel layers): allow one split per SM
-        const int zmax = tiles_out <= 2 ? 148 : 64;
+        const int zmax = tiles_out <= 2 ? units : 64;
         for (int z = 1; z <= zmax && z <= p.TM; ++z) {
             const int mps = (p.TM + z - 1) / z;
             const int zz = (p.TM + mps - 1) / mps;
             if (zz != z) continue;
             if (z > 1 && (mps < 4 || (long long)z * p.N * p.K * 4 > ws_cap)) break;
             const long long items = (long long)tiles_out * z;
-            const double t = (double)((items + 147) / 148) * (mps * t_kb + t_item) + (z > 1 ? (double)z : 0.5) * p.N * (double)p.K * 8.0 / 5.0e6;
+            const double t = (double)((items + units - 1) / units) * (mps * t_kb + t_item) + (z > 1 ? (double)z : 0.5) * p.N * (double)p.K * 8.0 / 5.0e6;
             if (t < best_t * 0.98) { best_t = t; Z = z; }
         }
     }
     p.m_per_split = (p.TM + Z - 1) / Z;
     p.Z = (p.TM + p.m_per_split - 1) / p.m_per_split;
-    p.NTN = (p.N + 127) / 128;
+    p.NTN = p.pair ? ntn_single / 2 : ntn_single;
     p.tiles_out = tiles_out;
     p.items = tiles_out * p.Z;
+    if (p.pair && p.items < units / 2) {          // too little work for 74 pairs: plan again for single CTAs
+        static thread_local bool again = false;
+        if (!again) {
+            again = true;
+            const int saved = wg_pair;
+            wg_pair = 0;
+            wg_plan(A, dY, p);
+            wg_pair = saved;
+            again = false;
+            return;
+        }
+    }
     if (wg_persistent()) p.tmem_cols = pow2_ceil(2 * p.BNJ < 32 ? 32 : 2 * p.BNJ);
-    const int stage_bytes = 2 * WG_BKM * 128 + (p.BNJ / 64) * WG_BKM * 128;
+    const int stage_bytes = 2 * WG_BKM * 128 + (p.pair ? p.BNJ / 128 : p.BNJ / 64) * WG_BKM * 128;
     int stages = (SMEM_LIMIT - 1024 - 256) / stage_bytes;
     if (stages > 8) stages = 8;
     p.stages = stages;
@@ -686,7 +751,7 @@ int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* 
         const uint32_t box[4] = {64, (uint32_t)p.bx, (uint32_t)p.by, (uint32_t)p.nb};
         if (encode_map(&mapY, reinterpret_cast<const bf16*>(dY->d) + dY->d_off, 4, dims, str, box, "conv_wgrad_tc(dY)")) return 1;
     }
-    const int stage_bytes = 2 * WG_BKM * 128 + (p.BNJ / 64) * WG_BKM * 128;
+    const int stage_bytes = 2 * WG_BKM * 128 + (p.pair ? p.BNJ / 128 : p.BNJ / 64) * WG_BKM * 128;
     const int smem = 1024 + p.stages * stage_bytes + 256;
     if (!g_wg_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
@@ -698,15 +763,33 @@ int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* 
         static bool attr_p = false;
         static int num_sms = 148;
         if (!attr_p) {
-            cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+            cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(conv_wgrad_tc_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
             if (e != cudaSuccess) MOPOE_FAIL("conv_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             int dev = 0;
             cudaGetDevice(&dev);
             if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
             attr_p = true;
         }
-        const int grid = p.items < num_sms ? p.items : num_sms;
-        conv_wgrad_tc_persist_kernel<<<grid, TC_THREADS, smem, st>>>(mapA, mapY, p);
+        if (p.pair) {
+            const int clusters = p.items < num_sms / 2 ? p.items : num_sms / 2;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(2 * clusters));
+            cfg.blockDim = dim3(TC_THREADS);
+            cfg.dynamicSmemBytes = (size_t)smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cudaError_t e = cudaLaunchKernelEx(&cfg, conv_wgrad_tc_persist_kernel<true>, mapA, mapY, p);
+            if (e != cudaSuccess) MOPOE_FAIL("conv_wgrad_tc_pair: launch: %s", cudaGetErrorString(e));
+        } else {
+            const int grid = p.items < num_sms ? p.items : num_sms;
+            conv_wgrad_tc_persist_kernel<false><<<grid, TC_THREADS, smem, st>>>(mapA, mapY, p);
+        }
         MOPOE_CHECK_LAUNCH("conv_wgrad_tc_persist");
     } else {
         dim3 grid((unsigned)(p.R * p.JT), (unsigned)((p.N + 127) / 128), (unsigned)p.Z);

@@ -56,6 +56,7 @@ CASES = [
     (2, 31, 64, 256, 40),        # 155 m-tiles: ODD -> the last pair's second CTA works on an out-of-range tile
     (1, 64, 64, 128, 1024),      # 1-D
     (2, 9, 128, 384, 32),        # BN = 192: 96 weight columns per CTA
+    (2, 16, 128, 512, 16),       # wgrad: 4 n-tiles -> 2 n-tile pairs per window tile (CTA-pair weight-gradient kernel)
 ]
 
 
