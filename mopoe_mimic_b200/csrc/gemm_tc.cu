@@ -485,7 +485,8 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
     const uint32_t tmem_base = *tmem_slot_gen;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
+            // (whole warp converged, one elected lane issues: see tc::elect_one)
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t full_leader0 = PAIR ? mapa_shared(full0, 0) : full0;
@@ -498,7 +499,8 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
                     const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sy = base + stage * stage_bytes, sa = sy + y_bytes;
-                    if (PAIR) {
+                    if (!elect_one()) {
+                    } else if (PAIR) {
                         const uint32_t bar = full_leader0 + 8 * stage;
                         if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * stage_bytes);
                         tma_load_4d_2cta(sy, &mapY, bar, n0, t0 * p.bx, t1 * p.by, t2 * p.nb);
@@ -514,12 +516,13 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
                         for (int qd = 0; qd < nqd; ++qd)
                             tma_load_5d(sa + qd * WG_BKM * 128, &mapA, bar, j0 + 64 * qd, t0 * p.bx, t1 * p.by, r, t2 * p.nb);
                     }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
             const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BNJ, 1, 1);      // both operands MN-major
             int stage = 0;
             uint32_t phase = 0;
@@ -538,7 +541,8 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
                     fence_after();
                     const uint32_t sy = base + stage * stage_bytes, sa = sy + y_bytes;
                     const uint64_t dy = smem_desc_sw128(sy, WG_BKM * 128, 1024), da = smem_desc_sw128(sa, WG_BKM * 128, 1024);
-                    if (PAIR) {
+                    if (!elect_one()) {
+                    } else if (PAIR) {
 #pragma unroll
                         for (int k = 0; k < WG_BKM / 16; ++k)
                             umma_bf16_2cta(d_tmem, dy + 128 * k, da + 128 * k, idesc, (it | k) != 0);
@@ -549,10 +553,14 @@ conv_wgrad_tc_persist_kernel(const __grid_constant__ CUtensorMap mapA, const __g
                             umma_bf16(d_tmem, dy + 128 * k, da + 128 * k, idesc, (it | k) != 0);
                         umma_commit(empty0 + 8 * stage);
                     }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                if (PAIR) umma_commit_2cta(tfull0 + 8 * acc, 3);
-                else umma_commit(tfull0 + 8 * acc);
+                if (elect_one()) {
+                    if (PAIR) umma_commit_2cta(tfull0 + 8 * acc, 3);
+                    else umma_commit(tfull0 + 8 * acc);
+                }
+                __syncwarp();
             }
         }
     } else {

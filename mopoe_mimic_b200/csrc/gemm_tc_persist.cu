@@ -130,8 +130,8 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     const uint32_t tmem_base = *tmem_slot_gen;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
+        {
+            // ===== TMA producer (whole warp converged; one elected lane issues) =====
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t full_leader0 = PAIR ? mapa_shared(full0, 0) : full0;     // pair: bytes are counted at the leader
@@ -150,22 +150,25 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     const int r = it / kpw, kc = it - r * kpw;
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
-                    if (PAIR) {
-                        if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * stage_bytes);
-                        tma_load_5d_2cta(sa, ma, full_leader0 + 8 * stage, kc * 64, t0 * p.BX, t1 * p.BY, r, t2 * p.NB);
-                        tma_load_2d_2cta(sb, mb, full_leader0 + 8 * stage, r * p.KW + kc * 64, n0 + (int)rank * (p.BN >> 1));
-                    } else {
-                        mbar_expect_tx(full0 + 8 * stage, stage_bytes);
-                        tma_load_5d(sa, ma, full0 + 8 * stage, kc * 64, t0 * p.BX, t1 * p.BY, r, t2 * p.NB);
-                        tma_load_2d(sb, mb, full0 + 8 * stage, r * p.KW + kc * 64, n0);
+                    if (elect_one()) {
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * stage_bytes);
+                            tma_load_5d_2cta(sa, ma, full_leader0 + 8 * stage, kc * 64, t0 * p.BX, t1 * p.BY, r, t2 * p.NB);
+                            tma_load_2d_2cta(sb, mb, full_leader0 + 8 * stage, r * p.KW + kc * 64, n0 + (int)rank * (p.BN >> 1));
+                        } else {
+                            mbar_expect_tx(full0 + 8 * stage, stage_bytes);
+                            tma_load_5d(sa, ma, full0 + 8 * stage, kc * 64, t0 * p.BX, t1 * p.BY, r, t2 * p.NB);
+                            tma_load_2d(sb, mb, full0 + 8 * stage, r * p.KW + kc * 64, n0);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // ===== MMA issuer (pair: the leader CTA only) =====
+        if (rank == 0) {
+            // ===== MMA issuer (pair: the leader CTA only); whole warp converged, one elected lane issues =====
             const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -181,19 +184,25 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     fence_after();
                     const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
                     const uint64_t da = smem_desc_sw128(sa, 0, 1024), db = smem_desc_sw128(sb, 0, 1024);
-                    if (PAIR) {
+                    if (elect_one()) {
+                        if (PAIR) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
-                        umma_commit_2cta(empty0 + 8 * stage, 3);             // frees the stage in BOTH CTAs
-                    } else {
+                            for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                            umma_commit_2cta(empty0 + 8 * stage, 3);             // frees the stage in BOTH CTAs
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
-                        umma_commit(empty0 + 8 * stage);
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                            umma_commit(empty0 + 8 * stage);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                if (PAIR) umma_commit_2cta(tfull0 + 8 * acc, 3);             // both CTAs' epilogues
-                else umma_commit(tfull0 + 8 * acc);
+                if (elect_one()) {
+                    if (PAIR) umma_commit_2cta(tfull0 + 8 * acc, 3);             // both CTAs' epilogues
+                    else umma_commit(tfull0 + 8 * acc);
+                }
+                __syncwarp();
             }
         }
     } else if (TMA_EPI && warp < 6) {

@@ -37,6 +37,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// one lane of a CONVERGED warp.  The producer / MMA warps run their loops with all 32 lanes (barrier polls included) and
+// only ISSUE under elect_one(): every operand is then computed in warp-uniform code and lives in uniform registers.
+// Issuing from inside an `if (lane == 0)` region made the compiler wrap each tcgen05.mma / TMA instruction in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall (~95 dependent instructions per k-step by a single thread: 400-550 cycles,
+// more than the 256 cycles of MMA a 128x128 k-step holds — what kept the N = 128 layers at 45 % tensor-pipe active).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
