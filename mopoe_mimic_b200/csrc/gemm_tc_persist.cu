@@ -579,8 +579,11 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         const char* e = getenv("MOPOE_GEMM_PAIR_MIN_BN");
         pair_min_bn = e ? atoi(e) : 192;
     }
-    const bool pair = pair_enabled() && tma_epi && p.BN % 64 == 0 && p.BN >= pair_min_bn && p.total_tiles >= g_num_sms &&
-                      g_num_sms % 2 == 0;
+    // ... and the reduction is long: a 1x1 conv (K = 256-512: 4-8 k-steps per tile) is bound by its epilogue and the
+    // HBM, and pays for the pair's per-tile handshakes (x1 M=262144 N=256 K=256: 117 us paired, 93 us single)
+    const int nkb = p.R * (p.KW >> 6);
+    const bool pair = pair_enabled() && tma_epi && p.BN % 64 == 0 && p.BN >= pair_min_bn && nkb >= 12 &&
+                      p.total_tiles >= g_num_sms && g_num_sms % 2 == 0;
     if (pair) {
         p.total_tiles = ((m_tiles + 1) / 2) * nprob * p.NT;          // pair tiles: two consecutive m-tiles x one n-tile
         const int clusters = p.total_tiles < g_num_sms / 2 ? p.total_tiles : g_num_sms / 2;
