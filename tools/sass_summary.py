@@ -9,7 +9,7 @@ from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'mopoe_mimic_b200', 'libmopoe_b200.so')
-OPS = ['UTCHMMA', 'UTCQMMA', 'LDTM', 'STTM', 'UTCBAR', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'SYNCS', 'HMMA', 'FFMA', 'LDGSTS', 'RED', 'MULTIMEM']
+OPS = ['UTCHMMA', 'UTCQMMA', 'LDTM', 'STTM', 'UTCBAR', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'ELECT', 'SYNCS', 'HMMA', 'FFMA', 'LDGSTS', 'RED', 'MULTIMEM']
 
 
 def main():
