@@ -154,9 +154,10 @@ int mopoe_combine_bn(const mopoe_view_t* r, const float* mean, const float* invs
                      float* out_invstd, float* running_mean, float* running_var, void* stream);
 /* BN backward, reduction half: g = gscale * dy * [gate > 0];  xhat = (x*2mask - mean)*invstd;
  * dbeta (+)= sum g, dgamma (+)= sum g*xhat, sums[0:C] = sum g, sums[C:2C] = sum g*xhat.
- * The ReLU gate is read from `gate` (the saved activation) or absent (NULL).  gate_gamma / gate_beta are reserved
- * (must be NULL): recomputing the gate from x was measured slower than re-reading the bf16 activation on B200 —
- * these passes are issue-bound, not DRAM-bound. */
+ * The ReLU gate is read from `gate` (the saved activation) or absent (NULL).  gate_gamma / gate_beta (optional): the
+ * affine parameters of THIS BatchNorm when `gate` = relu(gamma*xhat + beta) is its own output — with bf16 storage the
+ * library may then recover xhat = (gate - beta)/gamma where the gate is open instead of reading x (a third less
+ * traffic; channels with |beta| > 4|gamma| or gamma == 0 read x as before).  NULL: always read x. */
 int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                         const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
                         const float* mean, const float* invstd, double* ws, int nchunk,

@@ -265,7 +265,7 @@ class ResBlockFn(torch.autograd.Function):
         #  issue-bound, not DRAM-bound)
         dg, db, acc = bn_slots('bn2')
         dh = eng.bn_bwd(da2, a2, 1.0, hh, m1, mode, st2, P['bn2.weight'], dg, db, None,
-                        Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device), accumulate=acc)
+                        Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device), accumulate=acc, beta=P['bn2.bias'])
         # conv1 (1x1): weight [n_out, c_in, 1..] (conv) or [c_in, n_out, 1..] (transposed conv)
         w1p = po['conv1.weight']
         done = deferred(lambda: eng.wgrad_rows_param(dh, a1, w1p) if sp.transposed else eng.wgrad_rows_param(a1, dh, w1p),
@@ -282,7 +282,7 @@ class ResBlockFn(torch.autograd.Function):
         # relu, bn1 (+ the shortcut's input gradient)
         dg, db, acc = bn_slots('bn1')
         dx = eng.bn_bwd(da1, a1, 1.0, x, None, L.MASK_NONE, st1, P['bn1.weight'], dg, db, dxs,
-                        Act.empty(B, H, W, sp.cin, iph, ipw, dt, eng.device), accumulate=acc)
+                        Act.empty(B, H, W, sp.cin, iph, ipw, dt, eng.device), accumulate=acc, beta=P['bn1.bias'])
         grads = [G[n] for n in sp.param_names()]
         return (dx.t.view_as(x_t), None, *grads)
 

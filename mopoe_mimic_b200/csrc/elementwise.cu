@@ -37,7 +37,7 @@ int mopoe_staged_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, 
                               const uint8_t* mask2, int mask2_mode, float scale2, cudaStream_t st);
 int mopoe_staged_reduce(int mode, const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                         const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, double* ws, int nchunk_cap,
-                        int* nchunk_used, cudaStream_t st);
+                        int* nchunk_used, const float* gate_gamma, const float* gate_beta, cudaStream_t st);
 static int ew_staged() {
     static int v = -1;
     if (v < 0) {
@@ -464,12 +464,12 @@ static int reduce_any(const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe
                       int mask_mode, const float* mean, const float* invstd, double* ws, int nchunk, int* used, cudaStream_t st,
                       const FinArgs& fin, const float* ggamma = nullptr, const float* gbeta = nullptr) {
     *used = nchunk;
-    if (ew_staged() && !fin.counter && !ggamma && !gbeta && x->C % VEC == 0) {
-        const int r = mopoe_staged_reduce(MODE, x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, used, st);
+    if (ew_staged() && !fin.counter && x->C % VEC == 0) {
+        const int r = mopoe_staged_reduce(MODE, x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, used, ggamma, gbeta, st);
         if (r >= 0) return r;
         *used = nchunk;
     }
-    return launch_reduce<MODE>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st, fin, ggamma, gbeta);
+    return launch_reduce<MODE>(x, dy, gate, gscale, mask, mask_mode, mean, invstd, ws, nchunk, st, fin);   // (reads x: exact)
 }
 
 extern "C" int mopoe_bn_stats(const mopoe_view_t* x, const uint8_t* mask, int mask_mode, double* ws, int nchunk,
