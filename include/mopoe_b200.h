@@ -155,15 +155,16 @@ int mopoe_combine_bn(const mopoe_view_t* r, const float* mean, const float* invs
 /* BN backward, reduction half: g = gscale * dy * [gate > 0];  xhat = (x*2mask - mean)*invstd;
  * dbeta (+)= sum g, dgamma (+)= sum g*xhat, sums[0:C] = sum g, sums[C:2C] = sum g*xhat.
  * The ReLU gate is read from `gate` (the saved activation) or absent (NULL).  gate_gamma / gate_beta (optional): the
- * affine parameters of THIS BatchNorm when `gate` = relu(gamma*xhat + beta) is its own output — with bf16 storage the
- * library may then recover xhat = (gate - beta)/gamma where the gate is open instead of reading x (a third less
- * traffic; channels with |beta| > 4|gamma| or gamma == 0 read x as before).  NULL: always read x. */
+ * affine parameters of THIS BatchNorm when `gate` = relu(gamma*xhat + beta) is its own output — the library may then
+ * RECOMPUTE the gate from x with the forward pass's own instruction sequence (bit-identical decisions) instead of reading
+ * the activation: a third less traffic, same result.  NULL: always read `gate`. */
 int mopoe_bn_bwd_reduce(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                         const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
                         const float* mean, const float* invstd, double* ws, int nchunk,
                         float* dgamma, float* dbeta, int accumulate, float* sums,
                         const float* gate_gamma, const float* gate_beta, int* counters, void* stream);
-/* BN backward, apply half: out = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend. */
+/* BN backward, apply half: out = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend.
+ * gate_beta (optional, with `gate`): the BatchNorm's bias -> the gate may be recomputed from x (see above). */
 int mopoe_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                        const mopoe_view_t* x, const uint8_t* mask, int mask_mode,
                        const float* mean, const float* invstd, const float* gamma, const float* sums,

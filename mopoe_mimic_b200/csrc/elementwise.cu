@@ -34,7 +34,7 @@ int mopoe_staged_combine(const mopoe_view_t* r, const float* mean, const float* 
 int mopoe_staged_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const mopoe_view_t* x,
                               const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, const float* gamma,
                               const float* sums, const mopoe_view_t* addend, const mopoe_view_t* out, const mopoe_view_t* out2,
-                              const uint8_t* mask2, int mask2_mode, float scale2, cudaStream_t st);
+                              const uint8_t* mask2, int mask2_mode, float scale2, const float* gate_beta, cudaStream_t st);
 int mopoe_staged_reduce(int mode, const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                         const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, double* ws, int nchunk_cap,
                         int* nchunk_used, const float* gate_gamma, const float* gate_beta, cudaStream_t st);
@@ -133,12 +133,12 @@ __device__ __forceinline__ void mask8(const uint2& t, float (&o)[8]) {
 __device__ __forceinline__ void bn_affine(const float (&mu)[8], const float (&is)[8], const float (&ga)[8],
                                           const float (&be)[8], float (&sc)[8], float (&sh)[8]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        sc[i] = is[i] * ga[i];
-        sh[i] = be[i] - mu[i] * sc[i];
+    for (int i = 0; i < 8; ++i) {                      // explicit intrinsics: identical in every kernel (stream.cu affine8)
+        sc[i] = __fmul_rn(is[i], ga[i]);
+        sh[i] = __fmaf_rn(-mu[i], sc[i], be[i]);
     }
 }
-__device__ __forceinline__ float bn_eval(float v, float sc, float sh) { return fmaf(v, sc, sh); }
+__device__ __forceinline__ float bn_eval(float v, float sc, float sh) { return __fmaf_rn(v, sc, sh); }
 
 // position of a flat thread index over the STORAGE (interior + zero border) of an output view
 struct Pos {
@@ -1284,7 +1284,7 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
                              const mopoe_view_t* out2, const uint8_t* mask2, int mask2_mode, float scale2, void* stream,
                              const float* gate_beta = nullptr) {
     if (check_same(x, dy, "bn_bwd_apply(dy)") || check_same(x, out, "bn_bwd_apply(out)")) return 1;
-    MOPOE_REQUIRE(gate_beta == nullptr, "bn_bwd_apply: gate recompute is not compiled in; pass the gate view");
+    MOPOE_REQUIRE(gate_beta == nullptr || gate, "bn_bwd_apply: pass the gate view as well (the register-staged kernels read it)");
     if (gate && check_same(x, gate, "bn_bwd_apply(gate)")) return 1;
     if (addend && check_same(x, addend, "bn_bwd_apply(addend)")) return 1;
     if (out2) {
@@ -1295,7 +1295,7 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
     float inv_cnt = 1.f / ((float)x->B * (float)x->H * (float)x->W);
     if (ew_staged()) {
         const int r = mopoe_staged_bn_bwd_apply(dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, sums, addend, out, out2,
-                                                mask2, mask2_mode, scale2, (cudaStream_t)stream);
+                                                mask2, mask2_mode, scale2, gate_beta, (cudaStream_t)stream);
         if (r >= 0) return r;
     }
     MOPOE_DISPATCH_T(x->dtype, T, {
@@ -1322,7 +1322,7 @@ static int bn_bwd_apply_impl(const mopoe_view_t* dy, const mopoe_view_t* gate, f
         bn_bwd_apply_kernel<T><<<grid, EW_THREADS, 0, (cudaStream_t)stream>>>(
             make_dview<const T>(dy), gate ? make_dview<const T>(gate) : xv, gate ? 1 : 0, gscale, xv, mask, mask_mode,
             mean, invstd, gamma, sums, inv_cnt, addend ? make_dview<const T>(addend) : xv, addend != nullptr, ov,
-            out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2, gate_beta, (unsigned)total, stride);
+            out2 ? make_dview<T>(out2) : ov, out2 != nullptr, mask2, mask2_mode, scale2, nullptr, (unsigned)total, stride);
     });
     MOPOE_CHECK_LAUNCH("bn_bwd_apply");
     return 0;

@@ -136,6 +136,23 @@ __device__ __forceinline__ void mask8(const uint2& t, float (&o)[8]) {
     }
 }
 
+// y = v * sc + sh == gamma * (v - mean) * invstd + beta, evaluated with ONE instruction sequence everywhere (forward apply,
+// backward gate recompute): sc = invstd * gamma, sh = fma(-mean, sc, beta), y = fma(v, sc, sh) — explicit fma intrinsics, so
+// that no contraction choice of the compiler can make two kernels disagree on a sign.
+__device__ __forceinline__ void affine8(const float (&mu)[8], const float (&is)[8], const float (&ga)[8], const float (&be)[8],
+                                        float (&sc)[8], float (&sh)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = __fmul_rn(is[i], ga[i]);
+        sh[i] = __fmaf_rn(-mu[i], sc[i], be[i]);
+    }
+}
+// the stored activation relu(y) is > 0  <=>  y rounds to a non-zero value of the storage type
+template <typename T>
+__device__ __forceinline__ bool gate_open(float y) {
+    return sizeof(T) == 2 ? y > 0x1p-134f : y > 0.f;       // bf16: half of the smallest subnormal rounds to zero (ties to even)
+}
+
 struct Item {
     int b, h, k;          // batch, image row, chunk
     int noct;             // octets in this item
@@ -305,11 +322,7 @@ struct ApplyBody {            // out = act(gamma * (x*2mask - mean) * invstd + b
         c = c_;
         float mu[VEC], is[VEC], ga[VEC], be[VEC];
         ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(beta + c, be);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {            // same sequence as bn_affine (elementwise.cu)
-            sc[i] = is[i] * ga[i];
-            sh[i] = be[i] - mu[i] * sc[i];
-        }
+        affine8(mu, is, ga, be, sc, sh);           // same sequence as bn_affine (elementwise.cu)
     }
     __device__ __forceinline__ Pre prefetch(const Item& it, int tid) const { return mask_fetch<KS>(mk, g, it, tid, c); }
     __device__ __forceinline__ void item(const Item& it, int tid, const Oct<T> (&raw)[KS][1], const Pre& pre) {
@@ -337,7 +350,7 @@ struct ApplyBody {            // out = act(gamma * (x*2mask - mean) * invstd + b
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const float y = fmaf(xv[i], scm[i], sh[i]);
+                const float y = __fmaf_rn(xv[i], scm[i], sh[i]);
                 o[i] = (relu && y < 0.f) ? 0.f : y;
             }
             st8<T>(orow + j * g.CH * VEC, o);
@@ -404,19 +417,20 @@ struct CombineBody {          // out = a * BN(r) + b * (c * 2mask)   [+ per-chan
 // out  = gamma*invstd*(g - sums_g/cnt - xhat*sums_gx/cnt) * 2mask + addend,  g = gscale * dy * [gate > 0]
 // out2 = scale2 * dy * 2mask2
 // operand order: dy, x, [gate], [addend]
-template <typename T, bool GATE, bool ADD, bool OUT2>
+// RECOMP (with GATE): the gate is not a staged operand but recomputed from x (see ReduceRecompBody)
+template <typename T, bool GATE, bool ADD, bool OUT2, bool RECOMP = false>
 struct BwdBody {
-    static constexpr int NOPS = 2 + (GATE ? 1 : 0) + (ADD ? 1 : 0);
+    static constexpr int NOPS = 2 + (GATE && !RECOMP ? 1 : 0) + (ADD ? 1 : 0);
     static constexpr int KS = ks_for<T>(NOPS >= 4 ? ST_K4 : (NOPS == 3 ? ST_K3 : ST_K2));
     struct Pre {
         MaskPre<KS> a, b;
     };
     StreamGeo g;
     MaskRef mk, mk2;
-    const float *mean, *invstd, *gamma, *sums;
+    const float *mean, *invstd, *gamma, *sums, *gate_beta;
     float gscale, inv_cnt, scale2;
     SOut out, out2;
-    float k1[VEC], ca[VEC], cb[VEC];
+    float k1[VEC], ca[VEC], cb[VEC], gsh[VEC];       // (the gate's scale invstd * gamma IS k1)
     int c;
     __device__ __forceinline__ void init(int c_) {
         c = c_;
@@ -424,10 +438,16 @@ struct BwdBody {
         ld8f(mean + c, mu); ld8f(invstd + c, is); ld8f(gamma + c, ga); ld8f(sums + c, sg); ld8f(sums + g.C + c, sgx);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {          // same sequence as the kernels of elementwise.cu
-            k1[i] = ga[i] * is[i];
+            k1[i] = __fmul_rn(is[i], ga[i]);                 // == affine8's sc
             const float mg = sg[i] * inv_cnt, mgx = sgx[i] * inv_cnt;
             ca[i] = -k1[i] * is[i] * mgx;
             cb[i] = k1[i] * (mu[i] * is[i] * mgx - mg);
+        }
+        if (GATE && RECOMP) {
+            float be[VEC];
+            ld8f(gate_beta + c, be);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) gsh[i] = __fmaf_rn(-mu[i], k1[i], be[i]);       // == affine8's sh
         }
     }
     __device__ __forceinline__ Pre prefetch(const Item& it, int tid) const {
@@ -458,15 +478,22 @@ struct BwdBody {
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) gv[i] *= gscale;
-            if (GATE) {
+            if (GATE && !RECOMP) {
                 float gt[VEC];
                 raw[j][2].unpack(gt);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i)
                     if (!(gt[i] > 0.f)) gv[i] = 0.f;
             }
+            if (mk.mode == MOPOE_MASK_ELEM) mask_mul<KS>(mk, pre.a, j, m);
+            if (GATE && RECOMP) {
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float vm = mk.mode != MOPOE_MASK_NONE ? v[i] * m[i] : v[i];
+                    if (!gate_open<T>(__fmaf_rn(vm, k1[i], gsh[i]))) gv[i] = 0.f;
+                }
+            }
             if (mk.mode != MOPOE_MASK_NONE) {
-                if (mk.mode == MOPOE_MASK_ELEM) mask_mul<KS>(mk, pre.a, j, m);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) o[i] = fmaf(k1[i], gv[i], fmaf(ca[i], v[i] * m[i], cb[i])) * m[i];
             } else {
@@ -475,7 +502,7 @@ struct BwdBody {
             }
             if (ADD) {
                 float ad[VEC];
-                raw[j][2 + (GATE ? 1 : 0)].unpack(ad);
+                raw[j][2 + (GATE && !RECOMP ? 1 : 0)].unpack(ad);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) o[i] += ad[i];
             }
@@ -562,16 +589,13 @@ struct ReduceBody {
     }
 };
 
-// BN-backward sums WITHOUT reading the normalised layer's input: where the ReLU gate is open, the saved activation is
-// a = gamma * xhat + beta, so xhat = (a - beta) / gamma; where it is closed, g = 0 and xhat is not needed.  Two staged
-// operands (dy, gate) instead of three: the largest pass of the backward (72 launches, 2.0 ms / step) moves a third
-// less.  Rounding: a carries the storage rounding of the activation (2^-9 relative in bf16), which puts
-// 2^-9 * (|xhat| + |beta / gamma|) on xhat — the same size as the rounding of the stored input on the three-operand
-// path while |beta| <= 4 |gamma|.  A thread whose channel octet violates that (or has gamma == 0) takes the exact path:
-// it loads its input octets (and mask bytes) straight from global memory.  bf16 storage only; fp32 validation mode
-// always runs the three-operand pass.
+// BN-backward sums with the ReLU gate RECOMPUTED from the BatchNorm's input instead of read from the saved activation:
+// gate = [relu(y) stored > 0], y = fma(x * 2mask, sc, sh) — the very instruction sequence of the forward apply pass
+// (affine8 / gate_open), so the decision is bit-identical to the stored activation's sign.  Two staged operands (dy, x)
+// instead of three (dy, x, a): the largest pass of the backward (72 launches) moves a third less, and stays exact.
+// operand order: dy, x
 template <typename T>
-struct ReduceGateBody {
+struct ReduceRecompBody {
     static constexpr int NOPS = 2;
     static constexpr int KS = ks_for<T>(ST_K2);
     typedef MaskPre<KS> Pre;
@@ -579,58 +603,41 @@ struct ReduceGateBody {
     MaskRef mk;
     const float *mean, *invstd, *gamma, *beta;
     float gscale;
-    SOp x;                                     // exact path only
-    float f0[VEC], f1[VEC], rg[VEC], bt[VEC], mu[VEC], is[VEC];
+    float f0[VEC], f1[VEC], sc[VEC], sh[VEC], mu[VEC], is[VEC];
     int c;
-    bool exact;
     __device__ __forceinline__ void init(int c_) {
         c = c_;
-        exact = false;
-        float ga[VEC];
+        float ga[VEC], be[VEC];
         ld8f(gamma + c, ga);
-        ld8f(beta + c, bt);
+        ld8f(beta + c, be);
         ld8f(mean + c, mu);
         ld8f(invstd + c, is);
+        affine8(mu, is, ga, be, sc, sh);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            f0[i] = f1[i] = 0.f;
-            exact = exact || !(fabsf(bt[i]) <= 4.f * fabsf(ga[i])) || ga[i] == 0.f;
-            rg[i] = ga[i] != 0.f ? 1.f / ga[i] : 0.f;
-        }
+        for (int i = 0; i < VEC; ++i) f0[i] = f1[i] = 0.f;
     }
-    __device__ __forceinline__ Pre prefetch(const Item& it, int tid) const {
-        if (exact) return mask_fetch<KS>(mk, g, it, tid, c);
-        Pre p;
-#pragma unroll
-        for (int j = 0; j < KS; ++j) p.m[j] = make_uint2(0, 0);
-        return p;
-    }
+    __device__ __forceinline__ Pre prefetch(const Item& it, int tid) const { return mask_fetch<KS>(mk, g, it, tid, c); }
     __device__ __forceinline__ void item(const Item& it, int tid, const Oct<T> (&raw)[KS][2], const Pre& pre) {
+        float m[VEC];
+        mask_mul<KS>(mk, pre, 0, m);
 #pragma unroll
         for (int j = 0; j < KS; ++j) {
             if (!(tid < g.CH && tid + j * g.CH < it.noct)) continue;
-            float gv[VEC], gt[VEC], xh[VEC];
+            float gv[VEC], xv[VEC];
             raw[j][0].unpack(gv);
-            raw[j][1].unpack(gt);
-            if (!exact) {
+            raw[j][1].unpack(xv);
+            if (mk.mode == MOPOE_MASK_ELEM) mask_mul<KS>(mk, pre, j, m);
+            if (mk.mode != MOPOE_MASK_NONE) {
 #pragma unroll
-                for (int i = 0; i < VEC; ++i) xh[i] = (gt[i] - bt[i]) * rg[i];
-            } else {
-                Oct<T> xo;
-                xo.lds(reinterpret_cast<const uint8_t*>(reinterpret_cast<const T*>(x.p) +
-                                                        ((long long)it.b * x.sB + (long long)it.h * x.sH + it.eoff + (tid + j * g.CH) * VEC)));
-                float xv[VEC], m[VEC];
-                xo.unpack(xv);
-                mask_mul<KS>(mk, pre, j, m);
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) xh[i] = (xv[i] * m[i] - mu[i]) * is[i];
+                for (int i = 0; i < VEC; ++i) xv[i] *= m[i];          // exact (m in {0, 2}): the forward's masked input
             }
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
                 float gg = gscale * gv[i];
-                if (!(gt[i] > 0.f)) gg = 0.f;
+                if (!gate_open<T>(__fmaf_rn(xv[i], sc[i], sh[i]))) gg = 0.f;
+                const float xh = (xv[i] - mu[i]) * is[i];
                 f0[i] += gg;
-                f1[i] = fmaf(gg, xh[i], f1[i]);
+                f1[i] = fmaf(gg, xh, f1[i]);
             }
         }
     }
@@ -681,11 +688,11 @@ __global__ void __launch_bounds__(ST_THREADS, 2) staged_combine_kernel(const SOp
 struct SOps4 {
     SOp o[4];
 };
-template <typename T, bool GATE, bool ADD, bool OUT2>
-__global__ void __launch_bounds__(ST_THREADS, 2) staged_bn_bwd_apply_kernel(const SOps4 in, const BwdBody<T, GATE, ADD, OUT2> body_in) {
+template <typename T, bool GATE, bool ADD, bool OUT2, bool RECOMP>
+__global__ void __launch_bounds__(ST_THREADS, 2) staged_bn_bwd_apply_kernel(const SOps4 in, const BwdBody<T, GATE, ADD, OUT2, RECOMP> body_in) {
     extern __shared__ __align__(128) uint8_t smem[];
-    BwdBody<T, GATE, ADD, OUT2> body = body_in;
-    constexpr int NOPS = BwdBody<T, GATE, ADD, OUT2>::NOPS;
+    BwdBody<T, GATE, ADD, OUT2, RECOMP> body = body_in;
+    constexpr int NOPS = BwdBody<T, GATE, ADD, OUT2, RECOMP>::NOPS;
     SOp ops[NOPS];
 #pragma unroll
     for (int i = 0; i < NOPS; ++i) ops[i] = in.o[i];
@@ -709,11 +716,11 @@ __global__ void __launch_bounds__(ST_THREADS, 2) staged_reduce_kernel(const SOps
 }
 
 template <typename T>
-__global__ void __launch_bounds__(ST_THREADS, 2) staged_reduce_gate_kernel(const SOp dy, const SOp gate, const ReduceGateBody<T> body_in,
-                                                                           double* ws) {
+__global__ void __launch_bounds__(ST_THREADS, 2) staged_reduce_recomp_kernel(const SOp dy, const SOp x, const ReduceRecompBody<T> body_in,
+                                                                             double* ws) {
     extern __shared__ __align__(128) uint8_t smem[];
-    ReduceGateBody<T> body = body_in;
-    const SOp ops[2] = {dy, gate};
+    ReduceRecompBody<T> body = body_in;
+    const SOp ops[2] = {dy, x};
     stream_pipeline<T, 2>(body.g, ops, smem, body);
     block_sums(body.g, smem, body.c, body.f0, body.f1, ws);
 }
@@ -731,10 +738,10 @@ int num_sms() {
 // The apply-type passes walk their tensors BACKWARDS: the pass that ran just before them (the statistics / sums reduction
 // over the same operands, or the GEMM that produced the input) touched the END of those tensors last, so with a 126 MB L2
 // the first ~100 MB an apply pass asks for are still on chip.  MOPOE_ST_REVERSE=0 restores the forward walk.
-int xhat_from_gate() {
+int gate_recompute() {
     static int v = -1;
     if (v < 0) {
-        const char* e = getenv("MOPOE_XHAT_FROM_GATE");
+        const char* e = getenv("MOPOE_GATE_RECOMPUTE");
         v = e ? atoi(e) : 1;
     }
     return v;
@@ -867,13 +874,15 @@ int mopoe_staged_combine(const mopoe_view_t* r, const float* mean, const float* 
     return 0;
 }
 
-template <typename T, bool GATE, bool ADD, bool OUT2>
+template <typename T, bool GATE, bool ADD, bool OUT2, bool RECOMP>
 static int launch_bwd(const StreamGeo& g, int grid, size_t smem, cudaStream_t st, const mopoe_view_t* dy, const mopoe_view_t* gate,
                       float gscale, const mopoe_view_t* x, const uint8_t* mask, int mask_mode, const float* mean,
                       const float* invstd, const float* gamma, const float* sums, float inv_cnt, const mopoe_view_t* addend,
-                      const mopoe_view_t* out, const mopoe_view_t* out2, const uint8_t* mask2, int mask2_mode, float scale2) {
-    ST_ATTR((staged_bn_bwd_apply_kernel<T, GATE, ADD, OUT2>));
-    BwdBody<T, GATE, ADD, OUT2> body;
+                      const mopoe_view_t* out, const mopoe_view_t* out2, const uint8_t* mask2, int mask2_mode, float scale2,
+                      const float* gate_beta) {
+    ST_ATTR((staged_bn_bwd_apply_kernel<T, GATE, ADD, OUT2, RECOMP>));
+    BwdBody<T, GATE, ADD, OUT2, RECOMP> body;
+    body.gate_beta = gate_beta;
     body.g = g; body.mk = MaskRef{mask, mask_mode}; body.mk2 = MaskRef{mask2, mask2_mode};
     body.mean = mean; body.invstd = invstd; body.gamma = gamma; body.sums = sums;
     body.gscale = gscale; body.inv_cnt = inv_cnt; body.scale2 = scale2;
@@ -883,22 +892,23 @@ static int launch_bwd(const StreamGeo& g, int grid, size_t smem, cudaStream_t st
     int n = 0;
     in.o[n++] = sop(dy);
     in.o[n++] = sop(x);
-    if (GATE) in.o[n++] = sop(gate);
+    if (GATE && !RECOMP) in.o[n++] = sop(gate);
     if (ADD) in.o[n++] = sop(addend);
     for (; n < 4; ++n) in.o[n] = sop(x);
-    staged_bn_bwd_apply_kernel<T, GATE, ADD, OUT2><<<grid, ST_THREADS, smem, st>>>(in, body);
+    staged_bn_bwd_apply_kernel<T, GATE, ADD, OUT2, RECOMP><<<grid, ST_THREADS, smem, st>>>(in, body);
     return 0;
 }
 
 int mopoe_staged_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale, const mopoe_view_t* x,
                               const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, const float* gamma,
                               const float* sums, const mopoe_view_t* addend, const mopoe_view_t* out, const mopoe_view_t* out2,
-                              const uint8_t* mask2, int mask2_mode, float scale2, cudaStream_t st) {
+                              const uint8_t* mask2, int mask2_mode, float scale2, const float* gate_beta, cudaStream_t st) {
     if (!view_ok(dy) || !view_ok(x) || !view_ok(out) || (gate && !view_ok(gate)) || (addend && !view_ok(addend)) ||
         (out2 && !view_ok(out2)))
         return -1;
     const int es = x->dtype == MOPOE_BF16 ? 2 : 4;
-    const int nops = 2 + (gate ? 1 : 0) + (addend ? 1 : 0);
+    const bool recomp = gate && gate_beta && !out2 && gate_recompute();      // gate recomputed from x: not a staged operand
+    const int nops = 2 + (gate && !recomp ? 1 : 0) + (addend ? 1 : 0);
     StreamGeo g;
     int grid;
     size_t smem;
@@ -908,11 +918,17 @@ int mopoe_staged_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, 
     g.reverse = st_reverse();
     const float inv_cnt = 1.f / ((float)x->B * (float)x->H * (float)x->W);
 #define ST_BW(G, A, O)                                                                                                          \
-    if (launch_bwd<T, G, A, O>(g, grid, smem, st, dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, sums, inv_cnt, addend, \
-                               out, out2, mask2, mask2_mode, scale2))                                                              \
+    if (launch_bwd<T, G, A, O, false>(g, grid, smem, st, dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, sums, inv_cnt,  \
+                                      addend, out, out2, mask2, mask2_mode, scale2, nullptr))                                      \
+    return 1
+#define ST_BWR(A)                                                                                                               \
+    if (launch_bwd<T, true, A, false, true>(g, grid, smem, st, dy, gate, gscale, x, mask, mask_mode, mean, invstd, gamma, sums,    \
+                                            inv_cnt, addend, out, out2, mask2, mask2_mode, scale2, gate_beta))                     \
     return 1
     MOPOE_DISPATCH_T(x->dtype, T, {
-        if (out2) {
+        if (recomp) {
+            if (addend) { ST_BWR(true); } else { ST_BWR(false); }
+        } else if (out2) {
             if (gate) { if (addend) { ST_BW(true, true, true); } else { ST_BW(true, false, true); } }
             else { if (addend) { ST_BW(false, true, true); } else { ST_BW(false, false, true); } }
         } else {
@@ -921,6 +937,7 @@ int mopoe_staged_bn_bwd_apply(const mopoe_view_t* dy, const mopoe_view_t* gate, 
         }
     });
 #undef ST_BW
+#undef ST_BWR
     MOPOE_CHECK_LAUNCH("staged_bn_bwd_apply");
     return 0;
 }
@@ -943,14 +960,14 @@ static int launch_reduce(const StreamGeo& g, int grid, size_t smem, cudaStream_t
 }
 
 // mode: 0 statistics, 1 BN-backward sums, 2 column sums.  Writes *nchunk_used partial rows into ws (<= nchunk_cap).
-// gate_gamma / gate_beta (mode 1, with a gate, bf16): the gate is relu(gamma * xhat + beta) of THIS BatchNorm -> the
-// two-operand pass (ReduceGateBody)
+// gate_gamma / gate_beta (mode 1, with a gate): the gate is relu(gamma * xhat + beta) of THIS BatchNorm -> the two-operand
+// pass that recomputes it from x (ReduceRecompBody)
 int mopoe_staged_reduce(int mode, const mopoe_view_t* x, const mopoe_view_t* dy, const mopoe_view_t* gate, float gscale,
                         const uint8_t* mask, int mask_mode, const float* mean, const float* invstd, double* ws, int nchunk_cap,
                         int* nchunk_used, const float* gate_gamma, const float* gate_beta, cudaStream_t st) {
     if (!view_ok(x) || (mode == 1 && !view_ok(dy)) || (gate && !view_ok(gate))) return -1;
     const int es = x->dtype == MOPOE_BF16 ? 2 : 4;
-    const bool xg = mode == 1 && gate && gate_gamma && gate_beta && x->dtype == MOPOE_BF16 && xhat_from_gate();
+    const bool xg = mode == 1 && gate && gate_gamma && gate_beta && gate_recompute();
     const int nops = mode == 1 ? (gate && !xg ? 3 : 2) : 1;
     StreamGeo g;
     int grid;
@@ -964,13 +981,14 @@ int mopoe_staged_reduce(int mode, const mopoe_view_t* x, const mopoe_view_t* dy,
     if (grid > nchunk_cap) grid = nchunk_cap;
     *nchunk_used = grid;
     if (xg) {
-        ST_ATTR(staged_reduce_gate_kernel<bf16>);
-        ReduceGateBody<bf16> body;
-        body.g = g; body.mk = MaskRef{mask, mask_mode};
-        body.mean = mean; body.invstd = invstd; body.gamma = gate_gamma; body.beta = gate_beta; body.gscale = gscale;
-        body.x = sop(x);
-        staged_reduce_gate_kernel<bf16><<<grid, ST_THREADS, smem, st>>>(sop(dy), sop(gate), body, ws);
-        MOPOE_CHECK_LAUNCH("staged_reduce_gate");
+        MOPOE_DISPATCH_T(x->dtype, T, {
+            ST_ATTR(staged_reduce_recomp_kernel<T>);
+            ReduceRecompBody<T> body;
+            body.g = g; body.mk = MaskRef{mask, mask_mode};
+            body.mean = mean; body.invstd = invstd; body.gamma = gate_gamma; body.beta = gate_beta; body.gscale = gscale;
+            staged_reduce_recomp_kernel<T><<<grid, ST_THREADS, smem, st>>>(sop(dy), sop(x), body, ws);
+        });
+        MOPOE_CHECK_LAUNCH("staged_reduce_recomp");
         return 0;
     }
 #define ST_RD(M, G)                                                                                                  \

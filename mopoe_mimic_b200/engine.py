@@ -239,22 +239,21 @@ class Engine:
 
     def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out, accumulate=False, beta=None):
         """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x).  gate = the saved post-ReLU
-        activation (None: no ReLU).  beta: the BatchNorm's bias when `gate` is this BatchNorm's own relu output — lets the
-        sums pass recover the normalised input from the gate instead of reading x (bf16 storage)."""
+        activation (None: no ReLU).  beta: the BatchNorm's bias when `gate` is this BatchNorm's own relu output — lets both
+        passes recompute the gate from x (bit-identical) instead of reading the activation."""
         rows = x.B * x.H * x.W
         nc = self.nchunk(rows, x.C)
         ws = self.ws64(2 * nc * x.C)
         sums = self.f32(2, x.C)
         gv = C.byref(gate.view()) if gate is not None else None
-        from_gate = gate is not None and beta is not None and x.dtype == torch.bfloat16
-        gg, gb = (L.ptr(gamma), L.ptr(beta)) if from_gate else (None, None)
-        self._bytes('bn_bwd_reduce', x, (2 if from_gate else 3) if gate is not None else 2)
+        recomp = gate is not None and beta is not None
+        gg, gb = (L.ptr(gamma), L.ptr(beta)) if recomp else (None, None)
+        self._bytes('bn_bwd_reduce', x, (2 if recomp else 3) if gate is not None else 2)
         L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(sums),
                gg, gb, L.ptr(self.counters), L.stream_ptr())
-        gb = None
         av = C.byref(addend.view()) if addend is not None else None
-        self._bytes('bn_bwd_apply', x, 3 + (gate is not None) + (addend is not None))
+        self._bytes('bn_bwd_apply', x, 3 + (gate is not None and not recomp) + (addend is not None))
         L.call('mopoe_bn_bwd_apply', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
                L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(sums), av, C.byref(out.view()), gb, L.stream_ptr())
         return out
