@@ -84,6 +84,15 @@ int mopoe_conv_gemm(const mopoe_window_t* A, const void* Wp, const float* bias, 
 int mopoe_conv_gemm_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
                             const mopoe_rows_t* D, int impl, void* stream);
 
+/* Split-K variant of mopoe_conv_gemm for weight-bound problems — few output tiles and a long reduction (the 4x4 -> 1x1
+ * convolutions at the bottom of the image stacks and their gradients, FeatureExtractorImg.py / DataGeneratorImg.py: M = batch
+ * rows, K = 8192-10240): every SM reduces a slice of K into an fp32 partial tile in `ws`, a finish kernel sums the slices in
+ * a fixed order (deterministic), adds the bias and writes D.  mopoe_conv_gemm_splitk_ws returns the workspace bytes, or 0
+ * when the problem is not of that kind (then use mopoe_conv_gemm). */
+size_t mopoe_conv_gemm_splitk_ws(const mopoe_window_t* A, const mopoe_rows_t* D, int impl);
+int mopoe_conv_gemm_splitk(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* ws,
+                           size_t ws_bytes, int impl, void* stream);
+
 /* The same launch with the training-mode BatchNorm STATISTICS of its output fused into the epilogue: the GEMM that
  * produces a tensor also produces the per-channel mean / 1/sqrt(var + eps) the following nn.BatchNorm needs
  * (ResidualBlocks.py:84-97: conv1 -> dropout1 -> bn2, and shortcut conv -> BatchNorm), and updates the running statistics

@@ -67,6 +67,8 @@ SIGNATURES = {
     'mopoe_conv_gemm': (_I, [_W, _P, _P, _R, _I, _P]),
     'mopoe_conv_gemm_batched': (_I, [_I, _W, _P, _P, _R, _I, _P]),
     'mopoe_conv_gemm_bn': (_I, [_I, _W, _P, _P, _R, _I, C.POINTER(BnReq), _P]),
+    'mopoe_conv_gemm_splitk_ws': (_S, [_W, _R, _I]),
+    'mopoe_conv_gemm_splitk': (_I, [_W, _P, _P, _R, _P, _S, _I, _P]),
     'mopoe_conv_wgrad_ws': (_S, [_W, _R, _I]),
     'mopoe_conv_wgrad': (_I, [_W, _R, _P, _I, _P, _S, _I, _P]),
     'mopoe_colsum': (_I, [_V, _P, _I, _P, _I, _P, _P]),

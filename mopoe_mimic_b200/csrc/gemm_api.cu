@@ -107,3 +107,18 @@ extern "C" int mopoe_conv_gemm_bn(int nprob, const mopoe_window_t* A, const void
     return mopoe_bn_stats(&bn->out, bn->mask, bn->mask_mode, bn->ws, bn->nchunk, bn->eps, bn->momentum, bn->mean, bn->invstd,
                           bn->running_mean, bn->running_var, nullptr, stream);
 }
+
+// ---- split-K for weight-bound problems (few output tiles, long reduction) ------------------------------------------------
+size_t mopoe_conv_gemm_tc_splitk_ws(const mopoe_window_t* A, const mopoe_rows_t* D);
+int mopoe_conv_gemm_tc_splitk(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* ws,
+                              size_t ws_bytes, void* stream);
+extern "C" size_t mopoe_conv_gemm_splitk_ws(const mopoe_window_t* A, const mopoe_rows_t* D, int impl) {
+    if (impl == 1 || !mopoe_tc_fwd_eligible(A, D)) return 0;
+    if (D->d_dtype != MOPOE_BF16 && D->d_dtype != MOPOE_F32) return 0;
+    return mopoe_conv_gemm_tc_splitk_ws(A, D);
+}
+extern "C" int mopoe_conv_gemm_splitk(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* ws,
+                                      size_t ws_bytes, int impl, void* stream) {
+    MOPOE_REQUIRE(impl != 1 && mopoe_tc_fwd_eligible(A, D), "conv_gemm_splitk: tcgen05 path not eligible");
+    return mopoe_conv_gemm_tc_splitk(A, Wp, bias, D, ws, ws_bytes, stream);
+}

@@ -778,6 +778,10 @@ int mopoe_conv_wgrad_tc(const mopoe_window_t* A, const mopoe_rows_t* dY, float* 
             int dev = 0;
             cudaGetDevice(&dev);
             if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+            if (const char* e2 = getenv("MOPOE_GEMM_SMS")) {
+                const int v = atoi(e2);
+                if (v >= 2 && v <= num_sms) num_sms = v & ~1;
+            }
             attr_p = true;
         }
         if (p.pair) {

@@ -56,6 +56,10 @@ struct TcPersistParams {
     const float* bias;
     int nacc;                     // NT * BN: columns of the per-CTA statistics accumulators
     TcStats st;
+    // split-K (register epilogue only): work item = (tile, split); split s reduces k-steps [s*kb_per_split, ...) and
+    // writes an fp32 partial tile at d + s * split_stride.  ksplit == 1: off.
+    int ksplit, kb_per_split;
+    long long split_stride;
 };
 
 constexpr int EPI_BAR = 1;        // named barrier of the 4 epilogue warps
@@ -139,14 +143,16 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                 // tile order (m-tile, problem, n-tile): the sub-pixel phases of one pixel block run side by side, so
                 // their (overlapping) activation windows are fetched from DRAM once — problem-major order re-read the
                 // whole input per phase (ncu: 568 MB read for a 151 MB operand)
-                const int nt = tile % p.NT;
-                const int tq = tile / p.NT;
+                const int sp = tile % p.ksplit, tl = tile / p.ksplit;
+                const int nt = tl % p.NT;
+                const int tq = tl / p.NT;
                 const int prob = tq % p.nprob, mt = PAIR ? 2 * (tq / p.nprob) + (int)rank : tq / p.nprob;
                 const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
                 const int n0 = nt * p.BN;
                 const CUtensorMap* ma = &maps.a[prob];
                 const CUtensorMap* mb = &maps.b[prob];
-                for (int it = 0; it < nkb; ++it) {
+                const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+                for (int it = kb0; it < kb1; ++it) {
                     const int r = it / kpw, kc = it - r * kpw;
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
@@ -179,7 +185,9 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);      // epilogue has drained this accumulator buffer
                 fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-                for (int it = 0; it < nkb; ++it) {
+                const int sp = tile % p.ksplit;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+                for (int it = kb0; it < kb1; ++it) {
                     mbar_wait(full0 + 8 * stage, phase);
                     fence_after();
                     const uint32_t sa = base + stage * stage_bytes, sb = sa + a_bytes;
@@ -187,11 +195,11 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     if (elect_one()) {
                         if (PAIR) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                            for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, ((it - kb0) | k) != 0);
                             umma_commit_2cta(empty0 + 8 * stage, 3);             // frees the stage in BOTH CTAs
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+                            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, ((it - kb0) | k) != 0);
                             umma_commit(empty0 + 8 * stage);
                         }
                     }
@@ -412,14 +420,16 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
-            const int nt = tile % p.NT;
-            const int tq = tile / p.NT;
+            const int sp = tile % p.ksplit, tl = tile / p.ksplit;
+            const int nt = tl % p.NT;
+            const int tq = tl / p.NT;
             const int prob = tq % p.nprob, mt = tq / p.nprob;
             const int t0 = mt % p.T0, t1 = (mt / p.T0) % p.T1, t2 = mt / (p.T0 * p.T1);
             const int n0 = nt * p.BN;
             const int m0 = t0 * p.BX + i1, m1 = t1 * p.BY + i2, m2 = t2 * p.NB + i4;
             const bool rvalid = m0 < p.E0 && m1 < p.E1 && m2 < p.E2;
-            const long long o = p.d_off[prob] + (long long)m0 * p.s0 + (long long)m1 * p.s1 + (long long)m2 * p.s2 + n0;
+            const long long o = p.d_off[prob] + (long long)m0 * p.s0 + (long long)m1 * p.s1 + (long long)m2 * p.s2 + n0 +
+                                (long long)sp * p.split_stride;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -542,6 +552,7 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     p.d_is_bf16 = D[0].d_dtype == MOPOE_BF16;
     p.bias = bias;
     p.st.ws = nullptr; p.st.mask = nullptr; p.st.mask_mode = MOPOE_MASK_NONE; p.st.rows_per_b = 1;
+    p.ksplit = 1; p.kb_per_split = p.R * (p.KW >> 6); p.split_stride = 0;
     if (!g_persist_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
         if (e == cudaSuccess)
@@ -553,6 +564,10 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (g_num_sms <= 0) g_num_sms = 148;
+        if (const char* e = getenv("MOPOE_GEMM_SMS")) {       // experiment: leave SMs to the kernels of the other branches
+            const int v = atoi(e);
+            if (v >= 2 && v <= g_num_sms) g_num_sms = v & ~1;
+        }
         g_persist_attr_set = true;
     }
     int grid = p.total_tiles < g_num_sms ? p.total_tiles : g_num_sms;
@@ -652,4 +667,142 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
 int mopoe_conv_gemm_tc_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
                                const mopoe_rows_t* D, void* stream) {
     return mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, bias, D, nullptr, stream);
+}
+
+// =====================================================================================================================
+// Split-K for weight-bound GEMMs: few output tiles, long reduction (the 4x4 -> 1x1 convs and their gradients at the
+// bottom of the image stacks: M = batch rows, N = 640, K = 8192-10240 — 10 CTAs streaming 10-13 MB of weights at the fill
+// rate of 10 SMs: 40-58 us).  Work items = (tile, split): every SM streams 1/S of the weights into an fp32 partial tile;
+// a finish kernel sums the S partials in a fixed order, adds the bias and writes the output rows.
+// =====================================================================================================================
+struct SplitKPlan {
+    int S, kbps, tiles, nkb, BN;
+    long long rows;
+};
+static bool splitk_plan(const mopoe_window_t* A, const mopoe_rows_t* D, SplitKPlan& q) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        // opt-in: measured on the bench step the split halves these launches (40-58 -> 20 us) and changes nothing in the
+        // step time — on 10 SMs they were running UNDER the other modality branches' kernels anyway
+        const char* e = getenv("MOPOE_GEMM_SPLITK");
+        enabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!enabled || !mopoe_tc_init_state()) return false;
+    int BX, BY, NB;
+    mopoe_tc_tile_split(A->E0, A->E1, 128, BX, BY, NB);
+    const int T0 = (A->E0 + BX - 1) / BX, T1 = (A->E1 + BY - 1) / BY, T2 = (A->E2 + NB - 1) / NB;
+    q.BN = mopoe_tc_pick_bn(D->N);
+    const int NT = (D->N + q.BN - 1) / q.BN;
+    q.tiles = T0 * T1 * T2 * NT;
+    q.nkb = A->R * (A->KW >> 6);
+    q.rows = (long long)A->E0 * A->E1 * A->E2;
+    if (q.tiles > 37 || q.nkb < 32 || D->N % 4 != 0) return false;
+    int S = q.nkb / 8;
+    if (S > 148 / q.tiles) S = 148 / q.tiles;
+    if (S > 32) S = 32;
+    if (S < 2) return false;
+    q.kbps = (q.nkb + S - 1) / S;
+    q.S = (q.nkb + q.kbps - 1) / q.kbps;
+    return q.S >= 2;
+}
+size_t mopoe_conv_gemm_tc_splitk_ws(const mopoe_window_t* A, const mopoe_rows_t* D) {
+    SplitKPlan q;
+    if (!splitk_plan(A, D, q)) return 0;
+    return (size_t)q.S * q.rows * D->N * sizeof(float);
+}
+
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ ws, int S, long long rows, int N, int E0, int E1,
+                                                            const float* __restrict__ bias, void* d, int d_is_bf16, long long d_off,
+                                                            long long s0, long long s1, long long s2) {
+    const int n4 = N >> 2;
+    const long long total = rows * n4;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long m = i / n4;
+        const int n = (int)(i - m * n4) * 4;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < S; ++z) {                                   // fixed order: deterministic
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(ws + ((long long)z * rows + m) * N + n));
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        if (bias) { a.x += bias[n]; a.y += bias[n + 1]; a.z += bias[n + 2]; a.w += bias[n + 3]; }
+        const long long m0 = m % E0, m1 = (m / E0) % E1, m2 = m / ((long long)E0 * E1);
+        const long long o = d_off + m0 * s0 + m1 * s1 + m2 * s2 + n;
+        if (d_is_bf16) {
+            bf16* dp = reinterpret_cast<bf16*>(d) + o;
+            dp[0] = __float2bfloat16_rn(a.x); dp[1] = __float2bfloat16_rn(a.y);
+            dp[2] = __float2bfloat16_rn(a.z); dp[3] = __float2bfloat16_rn(a.w);
+        } else {
+            float* dp = reinterpret_cast<float*>(d) + o;
+            dp[0] = a.x; dp[1] = a.y; dp[2] = a.z; dp[3] = a.w;
+        }
+    }
+}
+
+int mopoe_conv_gemm_tc_splitk(const mopoe_window_t* A, const void* Wp, const float* bias, const mopoe_rows_t* D, void* ws,
+                              size_t ws_bytes, void* stream) {
+    SplitKPlan q;
+    MOPOE_REQUIRE(splitk_plan(A, D, q), "conv_gemm_splitk: problem not eligible (ask mopoe_conv_gemm_splitk_ws first)");
+    MOPOE_REQUIRE(ws && ws_bytes >= (size_t)q.S * q.rows * D->N * sizeof(float), "conv_gemm_splitk: workspace too small");
+    TcPersistParams p;
+    p.E0 = A->E0; p.E1 = A->E1; p.E2 = A->E2; p.R = A->R; p.KW = A->KW; p.N = D->N;
+    mopoe_tc_tile_split(p.E0, p.E1, 128, p.BX, p.BY, p.NB);
+    p.T0 = (p.E0 + p.BX - 1) / p.BX; p.T1 = (p.E1 + p.BY - 1) / p.BY; p.T2 = (p.E2 + p.NB - 1) / p.NB;
+    p.BN = q.BN;
+    p.NT = (p.N + p.BN - 1) / p.BN;
+    p.nacc = p.NT * p.BN;
+    int pc = 32;
+    while (pc < 2 * p.BN) pc <<= 1;
+    MOPOE_REQUIRE(pc <= 512, "conv_gemm_splitk: BN=%d needs %d TMEM columns", p.BN, pc);
+    p.tmem_cols = pc;
+    p.nprob = 1;
+    p.tiles_per_prob = q.tiles;
+    p.total_tiles = q.tiles * q.S;
+    p.ksplit = q.S; p.kb_per_split = q.kbps;
+    p.split_stride = q.rows * p.N;
+    p.d = ws; p.d_is_bf16 = 0; p.bias = nullptr;
+    p.d_off[0] = 0; p.d_off[1] = p.d_off[2] = p.d_off[3] = 0;
+    p.s0 = p.N; p.s1 = (long long)p.E0 * p.N; p.s2 = (long long)p.E0 * p.E1 * p.N;
+    p.st.ws = nullptr; p.st.mask = nullptr; p.st.mask_mode = MOPOE_MASK_NONE; p.st.rows_per_b = 1;
+    if (!g_persist_attr_set) {             // (first GEMM of the process: let the regular entry point set the attributes)
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_splitk: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    const int stage_bytes = 128 * 128 + p.BN * 128;
+    const int hdr_bytes = 16 * 8 + 48 + 64;
+    int stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes) / stage_bytes;
+    if (stages > 8) stages = 8;
+    MOPOE_REQUIRE(stages >= 2, "conv_gemm_splitk: no room for 2 stages (BN=%d)", p.BN);
+    p.stages = stages;
+    TcMaps maps;
+    {
+        const uint64_t dims[5] = {(uint64_t)A->KW, (uint64_t)A->E0, (uint64_t)A->E1, (uint64_t)A->R, (uint64_t)A->E2};
+        const uint64_t str[5] = {1, (uint64_t)A->sA0, (uint64_t)A->sA1, (uint64_t)A->sAr, (uint64_t)A->sA2};
+        const uint32_t box[5] = {64, (uint32_t)p.BX, (uint32_t)p.BY, 1, (uint32_t)p.NB};
+        if (mopoe_tc_encode(&maps.a[0], reinterpret_cast<const bf16*>(A->a) + A->a_off, 5, dims, str, box, "conv_gemm_splitk(A)")) return 1;
+        const uint64_t K = (uint64_t)A->R * A->KW;
+        const uint64_t dimsb[2] = {K, (uint64_t)p.N};
+        const uint64_t strb[2] = {1, K};
+        const uint32_t boxb[2] = {64, (uint32_t)p.BN};
+        if (mopoe_tc_encode(&maps.b[0], Wp, 2, dimsb, strb, boxb, "conv_gemm_splitk(B)")) return 1;
+    }
+    for (int i = 1; i < TCP_MAXP; ++i) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
+    memset(maps.d, 0, sizeof(maps.d));
+    int sms = 148;
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+    const int smem = 1024 + stages * stage_bytes + hdr_bytes;
+    cudaStream_t st = (cudaStream_t)stream;
+    conv_gemm_tc_persist_kernel<false, false><<<grid, TCP_THREADS, smem, st>>>(maps, p);
+    MOPOE_CHECK_LAUNCH("conv_gemm_splitk");
+    const long long total = q.rows * (p.N >> 2);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)ws, q.S, q.rows, p.N, p.E0, p.E1, bias, D->d,
+                                                          D->d_dtype == MOPOE_BF16, D->d_off, D->s0, D->s1, D->s2);
+    MOPOE_CHECK_LAUNCH("splitk_finish");
+    return 0;
 }

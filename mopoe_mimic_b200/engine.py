@@ -413,6 +413,17 @@ class Engine:
         for wp in wps:
             assert wp.is_contiguous() and wp.dtype == self._win_dtype(wins[0])
         flops = sum(2.0 * w.E0 * w.E1 * w.E2 * r.N * w.R * w.KW for w, r in zip(wins, rows_list))
+        if n == 1 and self.impl != L.IMPL_SIMT and wins[0].a_dtype == L.BF16:
+            # weight-bound problem (few tiles, long reduction): split-K over the idle SMs
+            nbytes = L.load().mopoe_conv_gemm_splitk_ws(C.byref(wins[0]), C.byref(rows_list[0]), self.impl)
+            if nbytes:
+                ws = self.wsf(nbytes)
+                w0 = wins[0]
+                self._timed('fprop/dgrad', flops, lambda: L.call('mopoe_conv_gemm_splitk', C.byref(w0), L.ptr(wps[0]), L.ptr(bias),
+                                                                 C.byref(rows_list[0]), L.ptr(ws), nbytes, self.impl,
+                                                                 L.stream_ptr()),
+                            'sk M=%dx%dx%d N=%d K=%dx%d' % (w0.E2, w0.E1, w0.E0, rows_list[0].N, w0.R, w0.KW))
+                return self.bn_stats(out, bn[0], bn[1], bn[2], bn[3]) if bn is not None else None
         if bn is not None and not self.fuse_stats:
             self._gemm_batched(wins, wps, bias, rows_list)
             return self.bn_stats(out, bn[0], bn[1], bn[2], bn[3])

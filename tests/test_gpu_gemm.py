@@ -140,6 +140,48 @@ def test_valid_4to1_and_1to4(impl, dtype):
     assert (_to_nchw(out2, 2) - ref2).abs().max() <= tol * ref2.abs().max()
 
 
+@pytest.mark.parametrize('B,ci,co,bias_on,bn_on', [(256, 512, 640, False, False), (200, 640, 640, True, True), (128, 128, 64, True, False)])
+def test_split_k_weight_bound_gemm(B, ci, co, bias_on, bn_on):
+    """the 4x4 -> 1x1 conv at the bottom of the image encoder (M = batch rows, K = 16 * Cin = 8192-10240): few output tiles,
+    long reduction -> split-K work items + fixed-order finish kernel (mopoe_conv_gemm_splitk); with and without the
+    BatchNorm statistics of the output; the library must also report the path as taken for these shapes."""
+    import ctypes as C
+    import os
+    from mopoe_mimic_b200 import _lib as L
+    from mopoe_mimic_b200.engine import conv_form
+    if os.environ.get('MOPOE_GEMM_SPLITK', '0') != '1':
+        pytest.skip('split-K is opt-in (MOPOE_GEMM_SPLITK=1): no step-time gain measured; run this test with the switch set')
+    dtype = torch.bfloat16
+    eng = _eng(dtype, 'tc')
+    x = _rand((B, ci, 4, 4), 8, 1.0, dtype)
+    w = _rand((co, ci, 4, 4), 9, 0.02, dtype)
+    bias = _rand((co,), 10, 0.5) if bias_on else None
+    ref = F.conv2d(x, w, bias, stride=2, padding=0)
+    xa = _act(x, 1, dtype, 2)
+    win, OH, OW = eng.win_down(xa, 4, 2, 0)
+    from mopoe_mimic_b200.engine import Act
+    probe = Act.empty(B, OH, OW, co, 0, 0, dtype, eng.device)
+    assert L.load().mopoe_conv_gemm_splitk_ws(C.byref(win), C.byref(eng.rows_of(probe)), eng.impl) > 0
+    wc = conv_form(w.cuda(), dtype)
+    bn = None
+    if bn_on:
+        rm, rv = torch.zeros(co, device='cuda'), torch.ones(co, device='cuda')
+        bn = (None, L.MASK_NONE, rm, rv)
+    res = eng.gemm_down(xa, wc, bias.cuda() if bias_on else None, 4, 2, 0, co, bn=bn)
+    out, st = res if bn_on else (res, None)
+    torch.cuda.synchronize()
+    got = _to_nchw(out, 2)
+    assert (got - ref).abs().max() <= 1.5e-2 * ref.abs().max()
+    if bn_on:
+        v = out.interior().double()
+        assert torch.allclose(st[0].double(), v.mean(dim=(0, 1, 2)), rtol=1e-5, atol=1e-5)
+        assert torch.allclose(st[1].double(), 1 / torch.sqrt(v.var(dim=(0, 1, 2), unbiased=False) + 1e-5), rtol=1e-5, atol=1e-5)
+    # deterministic: the finish kernel sums the slices in a fixed order
+    out2 = eng.gemm_down(xa, wc, bias.cuda() if bias_on else None, 4, 2, 0, co)
+    torch.cuda.synchronize()
+    assert torch.equal(out2.t, out.t)
+
+
 BN_CASES = [
     # (kind, nd, B, Cin, Cout, spatial, mask)
     ('rows', 2, 4, 128, 128, 16, 'bc'),          # conv1 of a 2-D block: Dropout2d mask [B, C]
