@@ -300,7 +300,7 @@ def main():
             return st.numel() * 4
     else:
         c0 = L.LAUNCHES
-        gstep = P.GraphedTrainStep(exp, resident, ar)          # 2 eager warm-up steps + 1 captured step
+        gstep = P.GraphedTrainStep(exp, resident, ar, token_indices=(args.text_wire == 'uint8'))   # 2 eager warm-up steps + 1 captured step
         launches_per_step = (L.LAUNCHES - c0) // 3
 
         def step_resident():

@@ -327,6 +327,16 @@ int mopoe_onehot(const float* idx, int64_t rows, int V, int Vp, void* out, int o
 /* uint8 character indices [rows] -> fp32 one-hot rows [rows, V] (V <= 256): the device side of the 1-byte-per-token wire
  * format; the reference builds these rows on the host (dataio/MimicDataset.py:92-96, utils/text.py:13-34). */
 int mopoe_onehot_u8(const uint8_t* idx, int64_t rows, int V, float* out, void* stream);
+/* The first layer of the character-text encoder, nn.Conv1d(V, C, 4, 2, 1) on one-hot rows
+ * (char_encoding/FeatureExtractorText.py:30-31, :71-72), as a GATHER over the byte indices [B, L] of the wire format:
+ *   out[b, l, :] = bias + sum_{t<4, 0 <= 2l-1+t < L} W[:, idx[b, 2l-1+t], t]
+ * table: the layer's weights in full form [(t*V + v), c] in the activation dtype (mopoe_pack_weight_tiled form 2);
+ * out: [B, 1, L/2, C] (bordered allowed; only the interior is written).  An index >= V contributes nothing.
+ * mopoe_text_onehot_act builds the one-hot rows as the bordered, channel-padded activation [B, 1, L, Vp] (border pw, zero
+ * border and zero padding channels included) that the layer's weight-gradient GEMM reads, from the same indices. */
+int mopoe_text_stem_gather_fwd(const uint8_t* idx, int B, int L, int V, const void* table, int dtype, const float* bias,
+                               const mopoe_view_t* out, void* stream);
+int mopoe_text_onehot_act(const uint8_t* idx, int B, int L, int V, const mopoe_view_t* out, void* stream);
 /* 8-bit images on the wire: dst[i] = float(src[i]) / 255 — torchvision ToTensor(), which the reference's loader
  * applies on the host (dataio/MimicDataset.py), evaluated on the device: 1 byte per pixel crosses PCIe instead of 4. */
 int mopoe_u8_to_unit(const uint8_t* src, int64_t n, float* dst, void* stream);

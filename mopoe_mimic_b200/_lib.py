@@ -108,6 +108,8 @@ SIGNATURES = {
     'mopoe_jsd_divergence_bwd': (_I, [_I, _I, _I, _P, _P, _P, _F, _P, _P, _P, _P]),
     'mopoe_onehot': (_I, [_P, _L, _I, _I, _P, _I, _P, _P]),
     'mopoe_onehot_u8': (_I, [_P, _L, _I, _P, _P]),
+    'mopoe_text_stem_gather_fwd': (_I, [_P, _I, _I, _I, _P, _I, _P, _V, _P]),
+    'mopoe_text_onehot_act': (_I, [_P, _I, _I, _I, _V, _P]),
     'mopoe_u8_to_unit': (_I, [_P, _L, _P, _P]),
     'mopoe_pack_job_tiles': (_I, [_I, _I, _I, _I, _I, _I, C.POINTER(C.c_int)]),
     'mopoe_pack_weights_batched': (_I, [_P, _I, _I, _I, _P]),

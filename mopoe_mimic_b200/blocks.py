@@ -8,6 +8,7 @@ Reference graph of one block (networks/ResidualBlocks.py:20-33 / 51-65 / 84-97 /
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -400,15 +401,43 @@ class ImgLastFn(torch.autograd.Function):
         return dx.t.view_as(x_t), dw, db, None, None, None, None
 
 
+def attach_token_indices(onehot, idx):
+    """tell the text encoder that the one-hot rows `onehot` [B, L, V] were expanded from the byte indices `idx` [B, L]
+    (uint8, same device): its first layer then runs as a gather.  The caller guarantees that they agree."""
+    assert idx.dtype == torch.uint8 and idx.is_cuda and tuple(idx.shape) == tuple(onehot.shape[:2])
+    onehot._mopoe_token_idx = idx.contiguous()
+    return onehot
+
+
+def token_indices_of(x):
+    idx = getattr(x, '_mopoe_token_idx', None)
+    if idx is None or not x.is_cuda or idx.device != x.device or tuple(idx.shape) != tuple(x.shape[:2]):
+        return None
+    return idx
+
+
 class TextStemFn(torch.autograd.Function):
     """x.transpose(-2,-1) -> nn.Conv1d(71, C, 4, 2, 1) (char_encoding/FeatureExtractorText.py:30-31, :71-72):
     the [B, L, F] input already IS channels-last; it is copied once into a bordered, channel-padded buffer."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, eng, out_pad):
+    def forward(ctx, x, w, bias, eng, out_pad, idx=None):
         B, Lq, Fq = x.shape
         Cc = w.shape[0]
         Fp = (Fq + 15) // 16 * 16
+        # idx: the one-hot rows came from byte indices that are still on the device (the 1-byte-per-token wire format,
+        # train.GraphedTrainStep(token_indices=True) / attach_token_indices): the layer is a gather of 4 weight columns
+        ctx.gather = (idx is not None and not ctx.needs_input_grad[0] and Lq % 2 == 0 and Cc % 8 == 0 and Fq <= 255
+                      and os.environ.get('MOPOE_TEXT_GATHER', '1') != '0')
+        if ctx.gather:
+            y = Act(torch.zeros((B, 1, Lq // 2 + 2 * out_pad, Cc), dtype=eng.dtype, device=eng.device), B, 1, Lq // 2, Cc,
+                    0, out_pad)
+            table = eng.packed(w, 'full')                          # [(t * V + v), c] in the activation dtype
+            L.call('mopoe_text_stem_gather_fwd', L.ptr(idx), B, Lq, Fq, L.ptr(table), L.dtype_code(eng.dtype), L.ptr(bias),
+                   C.byref(y.view()), L.stream_ptr())
+            ctx.save_for_backward(idx, w)
+            ctx.eng, ctx.geo = eng, (B, Lq, Fq, Fp, out_pad)
+            return y.t
         x = x.contiguous().float()
         xin = Act.empty(B, 1, Lq, Fp, 0, 1, eng.dtype, eng.device)
         src = L.View(x.data_ptr(), L.F32, B, 1, Lq, Fq, 0, 0, 0, Lq * Fq, Lq * Fq, Fq)
@@ -426,8 +455,12 @@ class TextStemFn(torch.autograd.Function):
         eng = ctx.eng
         B, Lq, Fq, Fp, out_pad = ctx.geo
         Cc = w.shape[0]
-        xin = Act.like(xin_t, B, 1, Lq, Fp, 0, 1)
         dy = Act.like(dy_t.contiguous(), B, 1, Lq // 2, Cc, 0, out_pad)
+        if ctx.gather:              # the one-hot rows the weight-gradient GEMM reads: built from the byte indices, here
+            xin = Act.empty(B, 1, Lq, Fp, 0, 1, eng.dtype, eng.device)
+            L.call('mopoe_text_onehot_act', L.ptr(xin_t), B, Lq, Fq, C.byref(xin.view()), L.stream_ptr())
+        else:
+            xin = Act.like(xin_t, B, 1, Lq, Fp, 0, 1)
         g = eng.wgrad_down(xin, 4, 2, 1, dy)                   # [Cc, 4*Fp]
         dw = g.view(Cc, 4, Fp)[:, :, :Fq].permute(0, 2, 1).contiguous()
         db = eng.colsum(dy)
@@ -437,7 +470,7 @@ class TextStemFn(torch.autograd.Function):
                 raise NotImplementedError('input gradient of the text stem needs a feature count that is a multiple of 16')
             dxa = eng.gemm_up(dy, eng.packed(w, 'phase'), None, Fq, out_dtype=torch.float32)     # [B, 1, Lq, Fq] fp32
             dx = dxa.t.view(B, Lq, Fq)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class EmbeddingFn(torch.autograd.Function):

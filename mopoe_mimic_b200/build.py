@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmopoe_b200.so')
-SOURCES = ['elementwise.cu', 'stream.cu', 'fusion.cu', 'nll.cu', 'conv_direct.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gemm_tc_persist.cu', 'layout.cu', 'gemm_api.cu', 'dp_exchange.cu']
+SOURCES = ['elementwise.cu', 'stream.cu', 'text_stem.cu', 'fusion.cu', 'nll.cu', 'conv_direct.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gemm_tc_persist.cu', 'layout.cu', 'gemm_api.cu', 'dp_exchange.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
 

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from .blocks import (BN_EPS, BlockRun, BlockSpec, EmbeddingFn, ImgLastFn, ImgStemFn, LinearFn, ResBlockFn, TextLastFn,
+from .blocks import (BN_EPS, BlockRun, BlockSpec, EmbeddingFn, ImgLastFn, ImgStemFn, LinearFn, ResBlockFn, TextLastFn, token_indices_of,
                      TextStemFn, _pads)
 from .engine import Engine
 
@@ -345,7 +345,7 @@ class EncoderText(_Net):
         B, Lq, _ = x_text.shape
         specs = fe.specs[:fe.used] if self.word else fe.specs
         ins, outs = _chain_pads(specs, 0)
-        h = TextStemFn.apply(x_text, fe.conv1.weight, fe.conv1.bias, eng, ins[0])
+        h = TextStemFn.apply(x_text, fe.conv1.weight, fe.conv1.bias, eng, ins[0], None if self.word else token_indices_of(x_text))
         H, W = 1, Lq // 2
         blks, chain = [getattr(fe, sp.name)[0] for sp in specs], {}
         for i, sp in enumerate(specs):

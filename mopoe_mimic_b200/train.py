@@ -277,7 +277,10 @@ class GraphedTrainStep:
     batch is copied into static input buffers, and the scalars the reference logs come back as one packed vector.
     The NaN-in-latent guard (utils.check_latents) is read from `nan_flag` after the replay instead of mid-step."""
 
-    def __init__(self, exp, example_batch, allreduce=None, warmup=2):
+    def __init__(self, exp, example_batch, allreduce=None, warmup=2, token_indices=False):
+        """token_indices: keep the byte indices of the character text in a static device buffer next to the one-hot rows
+        and run the text encoder's first layer as a gather over them (meant for the 1-byte-per-token wire
+        format — one-hot float batches still work: their indices are recovered with an argmax per call)."""
         flags = exp.flags
         dev = flags.device
         self.exp = exp
@@ -287,6 +290,11 @@ class GraphedTrainStep:
         self.static = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in example_batch.items()}
         for k, v in example_batch.items():
             self.static[k].copy_(v)
+        self.static_idx = None
+        if token_indices and 'text' in self.static and self.static['text'].dim() == 3 and self.static['text'].shape[-1] <= 255:
+            from .blocks import attach_token_indices
+            self.static_idx = self.static['text'].argmax(dim=-1).to(torch.uint8)
+            attach_token_indices(self.static['text'], self.static_idx)
         saved_dataset = flags.dataset
         flags.dataset = 'testing'            # no mid-step .item() while capturing; the flag is checked after replay
         cur = torch.cuda.current_stream()
@@ -330,6 +338,8 @@ class GraphedTrainStep:
         st = self.static[k]
         if kind == 'text_u8':
             L.call('mopoe_onehot_u8', L.ptr(src_dev), src_dev.numel(), st.shape[-1], L.ptr(st), L.stream_ptr())
+            if self.static_idx is not None:
+                self.static_idx.copy_(src_dev.view_as(self.static_idx), non_blocking=True)
         else:
             L.call('mopoe_u8_to_unit', L.ptr(src_dev), src_dev.numel(), L.ptr(st), L.stream_ptr())
 
@@ -362,6 +372,8 @@ class GraphedTrainStep:
                 self._expand(k, kinds[k], self._staging[i][(k, kinds[k])])
             else:
                 t.copy_(self._staging[i][k], non_blocking=True)
+                if k == 'text' and self.static_idx is not None:
+                    self.static_idx.copy_(t.argmax(dim=-1))
         if self._consumed[i] is None:
             self._consumed[i] = torch.cuda.Event()
         self._consumed[i].record(cur)
@@ -376,6 +388,8 @@ class GraphedTrainStep:
                     self._expand(k, kind, batch[k].contiguous())
                 else:
                     t.copy_(batch[k], non_blocking=True)
+                    if k == 'text' and self.static_idx is not None:
+                        self.static_idx.copy_(t.argmax(dim=-1))
         self.graph.replay()
         if self.graph_b is not None:
             self.allreduce(self.exp.mm_vae.flat_grads)

@@ -354,6 +354,43 @@ def test_graphed_step_uint8_text_wire_format():
     assert len(set(seqs[0])) == len(seqs[0])
 
 
+@pytest.mark.parametrize('cd,dim_text,rel', [('fp32', 32, 2e-6), ('bf16', 64, 2e-3)])
+def test_text_stem_as_a_gather_over_the_byte_indices(cd, dim_text, rel):
+    """GraphedTrainStep(token_indices=True): the first layer of the character-text encoder, Conv1d(71, C, 4, 2, 1) on
+    one-hot rows (char_encoding/FeatureExtractorText.py:30-31), runs as a gather of 4 weight columns over the byte indices
+    of the wire format; its weight gradient stays a GEMM over one-hot rows rebuilt from the indices.  Several steps (so that the weight
+    gradient acts through Adam) must track the one-hot GEMM path; a one-hot float feed must work too (argmax)."""
+    import mopoe_mimic_b200 as P
+    kw = dict(batch_size=8, DIM_img=16, DIM_text=dim_text, class_dim=32)
+    ofl = O.default_flags(**kw)
+    state = O.make_state(ofl, 0, torch.float32)
+    host = [O.make_batch(ofl, 20 + i, torch.float32) for i in range(4)]
+    wire = [dict(b, text=b['text'].argmax(-1).to(torch.uint8)) for b in host]
+    seqs = {}
+    for mode in ('gemm', 'gather_u8', 'gather_float'):
+        exp = P.Experiment(P.default_flags(compute_dtype=cd, **kw))
+        exp.mm_vae.load_state_dict(state)
+        exp.set_optimizer()
+        exp.mm_vae.train()
+        exp.mm_vae.rt.seed = 7
+        exp.mm_vae.rt.injected_eps = torch.zeros(8, 32, device='cuda')
+        gs = P.GraphedTrainStep(exp, {k: v.cuda() for k, v in host[0].items()}, warmup=1, token_indices=mode != 'gemm')
+        outs = []
+        for b, w in zip(host, wire):
+            feed = {k: v.cuda() for k, v in (w if mode == 'gather_u8' else b).items()}
+            outs.append(gs(feed)[:1].clone())
+        torch.cuda.synchronize()
+        seqs[mode] = [float(o) for o in outs]
+        w1 = exp.mm_vae.encoder_text.feature_extractor.conv1.weight.detach().clone()
+        seqs[mode + '.w'] = w1
+    assert seqs['gather_u8'] == seqs['gather_float']
+    assert seqs['gather_u8'] == pytest.approx(seqs['gemm'], rel=rel)
+    # the stem's own weights after 4 Adam steps: the scatter gradient equals the GEMM gradient
+    dw = (seqs['gather_u8.w'] - seqs['gemm.w']).abs().max()
+    moved = (seqs['gemm.w'] - state['encoder_text.feature_extractor.conv1.weight'].cuda()).abs().max()
+    assert float(moved) > 0 and float(dw) <= (5e-3 if cd == 'fp32' else 0.2) * float(moved)
+
+
 def test_graphed_step_uint8_image_wire_format():
     """8-bit images on the wire ([B, 1, px, px] uint8; ToTensor() = x / 255 evaluated on the device, 1/4 of the H2D bytes)
     give exactly the losses of the reference format (fp32 in [0, 1], divided on the host) — host and device feeds, together
