@@ -19,6 +19,8 @@
 //     reads), accumulates per CTA in shared memory and writes fixed-order partials for bn_finalize_kernel: the separate
 //     statistics pass over the activation (reduce_rows_kernel<.,0>: 1.35 ms / step) disappears for conv1 -> bn2 and
 //     shortcut conv -> BN.  Deterministic: fixed tile -> CTA assignment, no atomics.
+#include <math.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -538,7 +540,21 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     p.BN = mopoe_tc_pick_bn(p.N);
     // wide layers whose best tile is not a multiple of 64 columns (N = 640 -> 160): take 128 so that the TMA-store epilogue
     // (64-column groups) and the fused statistics apply
-    if (tma_epi_enabled() && D[0].d_dtype == MOPOE_BF16 && p.N > 256 && p.BN % 64 != 0) p.BN = 128;
+    if (tma_epi_enabled() && D[0].d_dtype == MOPOE_BF16 && p.N > 256 && p.BN % 64 != 0) {
+        // N = 640: choose among the 64-column multiples by a wave-aware cost: tiles are dealt to 148 SMs in whole waves, a
+        // tile's k-step costs max(MMA cycles, operand fill at ~55 B/clk/SM) (profiles/r2_ncu_gemm.txt).  M = 4096 rows
+        // (32 m-tiles): 128 columns -> 160 tiles = 2 waves; 192 -> 128 tiles = 1 wave, 37 % less time despite 17 % padding.
+        const long long mt = (long long)p.T0 * p.T1 * p.T2 * nprob;
+        int best = 128;
+        double best_cost = 1e30;
+        for (int bn : {128, 192, 256}) {
+            const long long tiles = mt * ((p.N + bn - 1) / bn);
+            const double kstep = fmax(2.0 * bn, (16384.0 + 128.0 * bn) / 55.0);
+            const double cost = (double)((tiles + 147) / 148) * kstep;
+            if (cost < best_cost * 0.97) { best_cost = cost; best = bn; }
+        }
+        p.BN = best;
+    }
     p.NT = (p.N + p.BN - 1) / p.BN;
     p.nacc = p.NT * p.BN;
     int cols = 2 * p.BN, pc = 32;

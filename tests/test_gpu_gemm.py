@@ -57,6 +57,7 @@ CASES = [
     (1, 64, 64, 128, 1024),      # 1-D
     (2, 9, 128, 384, 32),        # BN = 192: 96 weight columns per CTA
     (2, 16, 128, 512, 16),       # wgrad: 4 n-tiles -> 2 n-tile pairs per window tile (CTA-pair weight-gradient kernel)
+    (2, 256, 64, 640, 8),        # N = 640 at M = 4096 rows: 192-column tiles (one wave of 128 tiles), last tile overhangs N
 ]
 
 
