@@ -117,6 +117,33 @@ typedef struct {
 int mopoe_conv_gemm_bn(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias, const mopoe_rows_t* D,
                        int impl, const mopoe_bn_req_t* bn, void* stream);
 
+/* The same launch with the block's RESIDUAL COMBINE fused into the epilogue: the GEMM is the block's conv2
+ * (ResidualBlocks.py:92-93 `out = self.conv2(out); out = self.dropout2(out)`), and instead of its result it stores the
+ * block output `self.a * residual + self.b * out` (ResidualBlocks.py:94-96) with the shortcut's BatchNorm folded in:
+ *     D[m, n] = a * BN(r[m, n]) + b * ((acc[m, n] + bias[n]) * 2mask)      (mask_mode NONE: no factor 2, no mask)
+ * acc is the fp32 accumulator: the conv2 result never goes through HBM (mopoe_conv_gemm + mopoe_combine write it, read it
+ * back, and launch twice).  r: one row addressing per problem over the shortcut branch (bf16, N columns), same geometry as
+ * D.  mask: MOPOE_MASK_BC = [E2, N] keep-bytes (Dropout2d, E2 the batch), MOPOE_MASK_ELEM = one byte per element of r,
+ * laid out like r.  bn (may be NULL): also the training-mode statistics of the STORED output — the next block's bn1 —
+ * with bn->mask_mode == MOPOE_MASK_NONE.  The caller zeroes the border of D's activation (mopoe_zero_border).
+ * mopoe_conv_gemm_res_eligible answers 1 when this epilogue applies (tcgen05 path, bf16, N % 64 == 0, 16-byte aligned rows,
+ * MOPOE_GEMM_RES != 0); otherwise the caller runs mopoe_conv_gemm(_batched) + mopoe_combine(_bn); mopoe_conv_gemm_res fails
+ * on a problem that is not eligible. */
+typedef struct {
+    const mopoe_rows_t* r;
+    const float* mean;
+    const float* invstd;
+    const float* gamma;
+    const float* beta;
+    float a, b;
+    const uint8_t* mask;
+    int32_t mask_mode;
+} mopoe_res_req_t;
+int mopoe_conv_gemm_res_eligible(int nprob, const mopoe_window_t* A, const float* bias, const mopoe_rows_t* D, int impl,
+                                 const mopoe_res_req_t* res, const mopoe_bn_req_t* bn);
+int mopoe_conv_gemm_res(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias, const mopoe_rows_t* D,
+                        int impl, const mopoe_res_req_t* res, const mopoe_bn_req_t* bn, void* stream);
+
 /* dWp[n, r*KW + k] (+)= sum_m dY[m, n] * A[m,r,k]   (fp32 output).  `ws` holds split partials
  * (ws_bytes from mopoe_conv_wgrad_ws); replaces the weight-gradient half of autograd's conv backward
  * (run_epochs.py:130 total_loss.backward()). */

@@ -46,6 +46,11 @@ class BnReq(C.Structure):
                 ('invstd', C.c_void_p), ('running_mean', C.c_void_p), ('running_var', C.c_void_p)]
 
 
+class ResReq(C.Structure):
+    _fields_ = [('r', C.POINTER(Rows)), ('mean', C.c_void_p), ('invstd', C.c_void_p), ('gamma', C.c_void_p),
+                ('beta', C.c_void_p), ('a', C.c_float), ('b', C.c_float), ('mask', C.c_void_p), ('mask_mode', C.c_int32)]
+
+
 class PackJob(C.Structure):
     _fields_ = [('W', C.c_void_p), ('dst', C.c_void_p * 4), ('A', C.c_int32), ('B', C.c_int32), ('KH', C.c_int32),
                 ('KW', C.c_int32), ('form', C.c_int32), ('bpad', C.c_int32), ('tile0', C.c_int32), ('nx', C.c_int32)]
@@ -67,6 +72,8 @@ SIGNATURES = {
     'mopoe_conv_gemm': (_I, [_W, _P, _P, _R, _I, _P]),
     'mopoe_conv_gemm_batched': (_I, [_I, _W, _P, _P, _R, _I, _P]),
     'mopoe_conv_gemm_bn': (_I, [_I, _W, _P, _P, _R, _I, C.POINTER(BnReq), _P]),
+    'mopoe_conv_gemm_res_eligible': (_I, [_I, _W, _P, _R, _I, C.POINTER(ResReq), C.POINTER(BnReq)]),
+    'mopoe_conv_gemm_res': (_I, [_I, _W, _P, _P, _R, _I, C.POINTER(ResReq), C.POINTER(BnReq), _P]),
     'mopoe_conv_gemm_splitk_ws': (_S, [_W, _R, _I]),
     'mopoe_conv_gemm_splitk': (_I, [_W, _P, _P, _R, _P, _S, _I, _P]),
     'mopoe_conv_wgrad_ws': (_S, [_W, _R, _I]),

@@ -78,17 +78,20 @@ def _eval_stats(rm, rv):
     return torch.stack((rm, torch.rsqrt(rv + BN_EPS)))
 
 
-def _main_fwd(eng, spec, x, Wg, bias, dtype, bn=None):
+def _main_fwd(eng, spec, x, Wg, bias, dtype, bn=None, res=None, out=None):
     """conv2 / shortcut forward by geometry kind -> plain Act; bn = (mask, mode, running_mean, running_var): also the
-    training-mode BatchNorm statistics of the result -> (Act, stats)"""
+    training-mode BatchNorm statistics of the result -> (Act, stats).  res (with out = the block's output activation): the
+    block's residual combine in the GEMM epilogue, see Engine._gemm_res -> None when that does not apply."""
+    if res is not None and spec.kind == 'U':
+        return None                                                # GEMM columns are (tap, channel): separate combine
     if spec.kind == 'S' and not spec.transposed:
-        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 1, spec.cout, bn=bn)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 1, spec.cout, bn=bn, res=res, out=out)
     if spec.kind == 'S':
-        return eng.gemm_up(x, eng.packed(Wg, "phase"), bias, spec.cout, bn=bn)
+        return eng.gemm_up(x, eng.packed(Wg, "phase"), bias, spec.cout, bn=bn, res=res, out=out)
     if spec.kind == 'Z':
-        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 0, spec.cout, bn=bn)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 2, 0, spec.cout, bn=bn, res=res, out=out)
     if spec.kind == 'Q':
-        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 4, 1, spec.cout, bn=bn)
+        return eng.gemm_down(x, eng.packed(Wg, "conv"), bias, 4, 4, 1, spec.cout, bn=bn, res=res, out=out)
     taps = 4 ** spec.nd if spec.nd == 2 else 4                     # 'U'
     bb = bias.repeat(taps) if bias is not None else None
     oh, ow = spec.out_hw(x.H, x.W)
@@ -167,8 +170,8 @@ class ResBlockFn(torch.autograd.Function):
         pph, ppw = _pads(sp.nd, sp.needs_pad)
         a2 = eng.bn_apply(hh, m1, mode, st2, P['bn2.weight'], P['bn2.bias'], True,
                           Act.empty(B, H, W, sp.cin, pph, ppw, dt, eng.device))
-        # conv2 and shortcut conv
-        c = _main_fwd(eng, sp, a2, P['conv2.weight'], P.get('conv2.bias'), dt)
+        # shortcut conv, then conv2 with the combine y = a * BN3(r) + b * dropout2(conv2) in its epilogue where the
+        # library can (bf16 tcgen05 path), else conv2 -> combine pass
         if run.train:
             r, st3 = _main_fwd(eng, sp, x, P[short + '.0.weight'], P[short + '.0.bias'], dt,
                                bn=(None, L.MASK_NONE) + tuple(bufs['short']))
@@ -176,11 +179,24 @@ class ResBlockFn(torch.autograd.Function):
             r, st3 = _main_fwd(eng, sp, x, P[short + '.0.weight'], P[short + '.0.bias'], dt), _eval_stats(*bufs['short'])
         oph, opw = _pads(sp.nd, run.out_pad)
         y = Act.empty(B, r.H, r.W, sp.cout, oph, opw, dt, eng.device)
-        if run.train and run.next_bn is not None and eng.fuse_next_stats:
-            y, run.out_stats = eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b, y,
-                                           bn=run.next_bn)
+        next_bn = run.next_bn if (run.train and run.next_bn is not None and eng.fuse_next_stats) else None
+        fused = None
+        if run.train and eng.fuse_res and dt == torch.bfloat16:
+            fused = _main_fwd(eng, sp, a2, P['conv2.weight'], P.get('conv2.bias'), dt, out=y,
+                              res=dict(r=r, stats=st3, gamma=P[short + '.1.weight'], beta=P[short + '.1.bias'], a=sp.a, b=sp.b,
+                                       mask=m2, mode=mode, next_bn=next_bn))
+        if fused is not None:
+            if oph or opw:
+                eng.zero_border(y)
+            if next_bn is not None:
+                run.out_stats = fused
         else:
-            eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b, y)
+            c = _main_fwd(eng, sp, a2, P['conv2.weight'], P.get('conv2.bias'), dt)
+            if next_bn is not None:
+                y, run.out_stats = eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b, y,
+                                               bn=next_bn)
+            else:
+                eng.combine(r, st3, P[short + '.1.weight'], P[short + '.1.bias'], c, m2, mode, sp.a, sp.b, y)
         ctx.run = run
         ctx.geo = (r.H, r.W)
         ctx.save_for_backward(x_t, a1.t, hh.t, a2.t, r.t, st1, st2, st3, *params)

@@ -73,8 +73,16 @@ struct TcStatsReq {
     int rows_per_b;
     int* nchunk_out;
 };
+struct TcResReq {
+    const mopoe_rows_t* R;
+    const float *mean, *invstd, *gamma, *beta;
+    float a, b;
+    const uint8_t* mask;
+    int mask_mode;
+    int dry_run;
+};
 int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
-                                  const mopoe_rows_t* D, const TcStatsReq* stats, void* stream);
+                                  const mopoe_rows_t* D, const TcStatsReq* stats, void* stream, const TcResReq* res);
 int mopoe_bn_finalize_launch(const double* ws, int nchunk, int C, double count, float eps, float momentum, float* mean,
                              float* invstd, float* rmean, float* rvar, void* stream);
 
@@ -95,7 +103,7 @@ extern "C" int mopoe_conv_gemm_bn(int nprob, const mopoe_window_t* A, const void
         req.mask_mode = bn->mask_mode;
         req.rows_per_b = (A[0].E2 > 1 || A[0].E1 > 1) ? A[0].E0 * A[0].E1 : bn->out.H * bn->out.W;
         req.nchunk_out = &fused_chunks;
-        if (mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, bias, D, &req, stream)) return 1;
+        if (mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, bias, D, &req, stream, nullptr)) return 1;
     } else {
         for (int i = 0; i < nprob; ++i)
             if (mopoe_conv_gemm_simt(&A[i], Wp[i], bias, &D[i], stream)) return 1;
@@ -106,6 +114,56 @@ extern "C" int mopoe_conv_gemm_bn(int nprob, const mopoe_window_t* A, const void
     MOPOE_REQUIRE((long long)2 * bn->nchunk * bn->out.C <= bn->ws_doubles, "conv_gemm_bn: workspace too small for the fallback reduction");
     return mopoe_bn_stats(&bn->out, bn->mask, bn->mask_mode, bn->ws, bn->nchunk, bn->eps, bn->momentum, bn->mean, bn->invstd,
                           bn->running_mean, bn->running_var, nullptr, stream);
+}
+
+// ---- fprop with the block's residual combine (and the next BatchNorm's statistics) fused into the epilogue -----------------
+static int res_call(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias, const mopoe_rows_t* D, int impl,
+                    const mopoe_res_req_t* res, const mopoe_bn_req_t* bn, int dry, int* fused_chunks, void* stream) {
+    if (impl == 1 || !res || !res->r) return 2;
+    for (int i = 0; i < nprob; ++i)
+        if (!mopoe_tc_fwd_eligible(&A[i], &D[i])) return 2;
+    TcResReq rq;
+    rq.R = res->r;
+    rq.mean = res->mean; rq.invstd = res->invstd; rq.gamma = res->gamma; rq.beta = res->beta;
+    rq.a = res->a; rq.b = res->b;
+    rq.mask = res->mask; rq.mask_mode = res->mask_mode;
+    rq.dry_run = dry;
+    TcStatsReq sq;
+    if (bn) {
+        sq.ws = bn->ws;
+        sq.ws_doubles = (size_t)bn->ws_doubles;
+        sq.mask = nullptr;
+        sq.mask_mode = bn->mask_mode;            // must be MOPOE_MASK_NONE: the next BatchNorm reads the block output as stored
+        sq.rows_per_b = 1;
+        sq.nchunk_out = fused_chunks;
+    }
+    return mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, bias, D, bn ? &sq : nullptr, stream, &rq);
+}
+extern "C" int mopoe_conv_gemm_res_eligible(int nprob, const mopoe_window_t* A, const float* bias, const mopoe_rows_t* D, int impl,
+                                            const mopoe_res_req_t* res, const mopoe_bn_req_t* bn) {
+    if (nprob < 1 || nprob > 4) return 0;
+    int chunks = 0;
+    return res_call(nprob, A, nullptr, bias, D, impl, res, bn, 1, &chunks, nullptr) == 0;
+}
+extern "C" int mopoe_conv_gemm_res(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
+                                   const mopoe_rows_t* D, int impl, const mopoe_res_req_t* res, const mopoe_bn_req_t* bn,
+                                   void* stream) {
+    MOPOE_REQUIRE(nprob >= 1 && nprob <= 4, "conv_gemm_res: nprob=%d (1..4)", nprob);
+    MOPOE_REQUIRE(res && res->r && res->mean && res->invstd && res->gamma && res->beta, "conv_gemm_res: null residual request");
+    if (bn) {
+        MOPOE_REQUIRE(bn->ws && bn->mean && bn->invstd, "conv_gemm_res: null statistics request");
+        MOPOE_REQUIRE(bn->out.C == D[0].N, "conv_gemm_res: the output view has %d channels, the GEMM %d columns", bn->out.C, D[0].N);
+    }
+    int chunks = 0;
+    const int rc = res_call(nprob, A, Wp, bias, D, impl, res, bn, 0, &chunks, stream);
+    if (rc == 2) MOPOE_FAIL("conv_gemm_res: the fused residual epilogue does not apply (ask mopoe_conv_gemm_res_eligible first)");
+    if (rc) return 1;
+    if (bn) {
+        MOPOE_REQUIRE(chunks > 0, "conv_gemm_res: statistics were not produced");
+        return mopoe_bn_finalize_launch(bn->ws, chunks, bn->out.C, (double)bn->out.B * bn->out.H * bn->out.W, bn->eps,
+                                        bn->momentum, bn->mean, bn->invstd, bn->running_mean, bn->running_var, stream);
+    }
+    return 0;
 }
 
 // ---- split-K for weight-bound problems (few output tiles, long reduction) ------------------------------------------------

@@ -40,12 +40,22 @@ struct TcMaps {
     CUtensorMap a[TCP_MAXP];
     CUtensorMap b[TCP_MAXP];
     CUtensorMap d[TCP_MAXP];      // output maps (n, m0, m1, m2) of the TMA-store epilogue
+    CUtensorMap r[TCP_MAXP];      // RES: the shortcut branch's rows, same geometry as d
 };
 struct TcStats {
     double* ws;                   // [gridDim.x * 4][2][N] partial (sum, sum of squares); NULL: no statistics
     const uint8_t* mask;          // dropout keep-mask applied between this GEMM and the BatchNorm (x * 2 * mask)
     int mask_mode;                // MOPOE_MASK_NONE / _BC ([B, N]) / _ELEM ([rows, N])
     int rows_per_b;               // flat output rows per sample (MASK_BC: sample = flat row / rows_per_b)
+};
+// RES: the residual combine of the block fused into the epilogue (ResidualBlocks.py:29-33):
+//   stored = a * BN(r) + b * ((acc + bias) * mask_scale * mask),  acc the fp32 accumulator (never rounded to bf16 in between)
+struct TcRes {
+    const float *mean, *invstd, *gamma, *beta;     // the shortcut's BatchNorm
+    float a, b;
+    const uint8_t* mask;          // dropout keep-mask on the GEMM result; byte address = mask + moff[prob] + m0*ms0 + m1*ms1 + m2*ms2 + n
+    int mask_mode;
+    long long moff[TCP_MAXP], ms0, ms1, ms2;
 };
 struct TcPersistParams {
     int E0, E1, E2, BX, BY, NB, T0, T1, T2;
@@ -62,6 +72,7 @@ struct TcPersistParams {
     // writes an fp32 partial tile at d + s * split_stride.  ksplit == 1: off.
     int ksplit, kb_per_split;
     long long split_stride;
+    TcRes rs;
 };
 
 constexpr int EPI_BAR = 1;        // named barrier of the 4 epilogue warps
@@ -79,9 +90,14 @@ constexpr uint32_t STG_BYTES = 128 * 128;   // one staging tile: 128 rows x 64 b
 // the SM's operand fill — ncu: 65-67 B/clk/SM of L2->shared traffic on the 128 x 256 layers (75 % tensor pipe), 57 B/clk on
 // the 128 x 128 layers (47 %): a CTA moves 48 KB per 128x256x64 k-step (85 flop/B).  A pair moves 32 KB per CTA for the same
 // math (128 flop/B); N = 128 layers 24 KB instead of 32 (85 instead of 64 flop/B).
-template <bool TMA_EPI, bool PAIR>
+// RES (with TMA_EPI): the epilogue also reads the shortcut branch's tile (TMA, double-buffered, one 64-column group ahead)
+// and stores a * BN(r) + b * dropout(acc) — the block's residual combine without the round trip of the conv2 output through
+// HBM (one write + one read of the activation) and without the combine launch.  The statistics warps then sum the COMBINED
+// tile: the statistics of the next block's bn1.
+template <bool TMA_EPI, bool PAIR, bool RES = false>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersistParams p) {
+    static_assert(!RES || TMA_EPI, "the residual epilogue is a TMA-store epilogue");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -91,17 +107,22 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t stage_bytes = a_bytes + b_bytes;
-    // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | statistics accumulators] | header
+    // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | RES: 2 residual tiles |
+    //         statistics accumulators | bias row | RES: coefficient rows (scale, shift)] | header
     const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;
+    const uint32_t tiles_bytes = (RES ? 4u : 2u) * STG_BYTES;
+    const uint32_t res0 = stg0 + 2 * STG_BYTES;
     const uint32_t acc_bytes = (TMA_EPI && p.st.ws) ? (uint32_t)(8 * p.nacc) * 4u : 0u;
     const uint32_t bias_bytes = (TMA_EPI && p.bias) ? (uint32_t)p.nacc * 4u : 0u;
-    const uint32_t extra = TMA_EPI ? 2 * STG_BYTES + acc_bytes + bias_bytes : 0u;
-    float* const sacc = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + 2 * STG_BYTES);
-    const float* const sbias = reinterpret_cast<const float*>(gen + (size_t)p.stages * stage_bytes + 2 * STG_BYTES + acc_bytes);
+    const uint32_t coef_bytes = RES ? (uint32_t)p.nacc * 8u : 0u;
+    const uint32_t extra = TMA_EPI ? tiles_bytes + acc_bytes + bias_bytes + coef_bytes : 0u;
+    float* const sacc = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + tiles_bytes);
+    const float* const sbias = reinterpret_cast<const float*>(gen + (size_t)p.stages * stage_bytes + tiles_bytes + acc_bytes);
+    float* const scoef = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + tiles_bytes + acc_bytes + bias_bytes);
     const uint32_t hdr = stg0 + extra;
-    // header: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+    // header: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem_ptr | res_full[2]
     const uint32_t full0 = hdr, empty0 = hdr + 8u * p.stages, tfull0 = hdr + 16u * p.stages, tempty0 = tfull0 + 16,
-                   tmem_slot = tempty0 + 16;
+                   tmem_slot = tempty0 + 16, resfull0 = tmem_slot + 8;
     volatile uint32_t* tmem_slot_gen =
         reinterpret_cast<volatile uint32_t*>(gen + (size_t)p.stages * stage_bytes + extra + 16 * p.stages + 32);
 
@@ -114,6 +135,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             prefetch_tmap(&maps.a[i]);
             prefetch_tmap(&maps.b[i]);
             if (TMA_EPI) prefetch_tmap(&maps.d[i]);
+            if (RES) prefetch_tmap(&maps.r[i]);
         }
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full0 + 8 * s, 1);
@@ -122,6 +144,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull0 + 8 * s, 1);
             mbar_init(tempty0 + 8 * s, PAIR ? 2 : 128);           // pair: one (remote) arrival per CTA, at the leader
+            if (RES) mbar_init(resfull0 + 8 * s, 1);
         }
         fence_barrier_init();
     }
@@ -221,14 +244,37 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         const int row = q * 32 + lane;
         const bool leader = threadIdx.x == 64;                     // issues the bulk stores of this CTA
         const bool stats = p.st.ws != nullptr;
-        if (p.bias) {                                              // the bias row, zero-padded to the tile grid
+        if (p.bias)                                                // the bias row, zero-padded to the tile grid
             for (int i = threadIdx.x - 64; i < p.nacc; i += 128) const_cast<float*>(sbias)[i] = i < p.N ? __ldg(p.bias + i) : 0.f;
-            named_bar_sync(EPI_BAR, 128);
+        if (RES) {
+            // per-column scale / shift of a * BN(r), the expressions of the stand-alone combine pass (stream.cu CombineBody)
+            for (int i = threadIdx.x - 64; i < p.nacc; i += 128) {
+                float sc = 0.f, sh = 0.f;
+                if (i < p.N) {
+                    sc = p.rs.a * __ldg(p.rs.invstd + i) * __ldg(p.rs.gamma + i);
+                    sh = p.rs.a * __ldg(p.rs.beta + i) - __ldg(p.rs.mean + i) * sc;
+                }
+                scoef[i] = sc;
+                scoef[p.nacc + i] = sh;
+            }
         }
+        if (p.bias || RES) named_bar_sync(EPI_BAR, 128);
         const uint32_t swz = (uint32_t)(row & 7);
         int iter = 0;
         uint32_t sbuf = 0;
         const uint32_t tempty_leader0 = PAIR ? mapa_shared(tempty0, 0) : tempty0;
+        // RES: residual tile ring (2 buffers), filled one 64-column group ahead by the leader thread
+        const int ri1 = row % p.BX, ri2 = (row / p.BX) % p.BY, ri4 = row / (p.BX * p.BY);
+        uint32_t gcount = 0;
+        auto res_issue = [&](int tile_, int g_, uint32_t buf) {
+            const int nt_ = tile_ % p.NT, tq_ = tile_ / p.NT;
+            const int prob_ = tq_ % p.nprob, mt_ = PAIR ? 2 * (tq_ / p.nprob) + (int)rank : tq_ / p.nprob;
+            const int u0 = mt_ % p.T0, u1 = (mt_ / p.T0) % p.T1, u2 = mt_ / (p.T0 * p.T1);
+            mbar_expect_tx(resfull0 + 8 * buf, STG_BYTES);
+            tma_load_4d(res0 + buf * STG_BYTES, &maps.r[prob_], resfull0 + 8 * buf, nt_ * p.BN + g_ * 64, u0 * p.BX, u1 * p.BY,
+                        u2 * p.NB);
+        };
+        if (RES && leader && tile_first < p.total_tiles) res_issue(tile_first, 0, 0u);
         for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
@@ -253,7 +299,64 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     if (!PAIR) mbar_arrive(tempty0 + 8 * acc);
                 }
                 uint32_t w[32];                                     // 64 bf16, packed
-                if (p.bias) {
+                if (RES) {
+                    const uint32_t rbuf = gcount & 1u, rph = (gcount >> 1) & 1u;
+                    if (leader) {
+                        // the NEXT group's residual tile goes into the other buffer: every thread finished reading that one
+                        // before the last barrier of the previous group
+                        int ntile = tile, ng = g + 1;
+                        if (ng == ngroups) { ntile = tile + tile_step; ng = 0; }
+                        if (ntile < p.total_tiles) res_issue(ntile, ng, rbuf ^ 1u);
+                    }
+                    ++gcount;
+                    const int m0 = t0 * p.BX + ri1, m1 = t1 * p.BY + ri2, m2 = t2 * p.NB + ri4;
+                    const bool rvalid = m0 < p.E0 && m1 < p.E1 && m2 < p.E2;
+                    const uint8_t* mrow = nullptr;                  // this row's 64 keep-mask bytes
+                    if (p.rs.mask_mode != MOPOE_MASK_NONE && rvalid)
+                        mrow = p.rs.mask + p.rs.moff[prob] + (long long)m0 * p.rs.ms0 + (long long)m1 * p.rs.ms1 +
+                               (long long)m2 * p.rs.ms2 + c0;
+                    const float mscale = p.rs.mask_mode == MOPOE_MASK_NONE ? 1.f : 2.f;
+                    uint2 mk[8];
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)
+                        mk[ch] = mrow ? __ldg(reinterpret_cast<const uint2*>(mrow) + ch) : make_uint2(0x01010101u, 0x01010101u);
+                    const float4* s4 = reinterpret_cast<const float4*>(scoef + c0);             // broadcast reads
+                    const float4* h4 = reinterpret_cast<const float4*>(scoef + p.nacc + c0);
+                    const float4* b4 = reinterpret_cast<const float4*>(sbias + c0);
+                    const bool has_bias = p.bias != nullptr;
+                    const float bco = p.rs.b;
+                    mbar_wait(resfull0 + 8 * rbuf, rph);
+                    const uint32_t rrow = res0 + rbuf * STG_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t rw[4];
+                        ld_shared_v4(rrow + ((((uint32_t)ch) ^ swz) << 4), rw);
+                        const float4 sA = s4[2 * ch], sB = s4[2 * ch + 1], hA = h4[2 * ch], hB = h4[2 * ch + 1];
+                        const float scv[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
+                        const float shv[8] = {hA.x, hA.y, hA.z, hA.w, hB.x, hB.y, hB.z, hB.w};
+                        float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (has_bias) {
+                            const float4 bA = b4[2 * ch], bB = b4[2 * ch + 1];
+                            bv[0] = bA.x; bv[1] = bA.y; bv[2] = bA.z; bv[3] = bA.w;
+                            bv[4] = bB.x; bv[5] = bB.y; bv[6] = bB.z; bv[7] = bB.w;
+                        }
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t rwv = rw[i >> 1];
+                            const float rv = __uint_as_float((i & 1) ? (rwv & 0xffff0000u) : (rwv << 16));
+                            const float cv = __uint_as_float(ch < 4 ? r0[8 * (ch & 3) + i] : r1[8 * (ch & 3) + i]) + bv[i];
+                            const uint32_t mword = i < 4 ? mk[ch].x : mk[ch].y;
+                            const float mf = ((mword >> (8 * (i & 3))) & 0xffu) ? mscale : 0.f;
+                            o[i] = fmaf(rv, scv[i], shv[i]) + bco * (cv * mf);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+                            w[4 * ch + i] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                    }
+                } else if (p.bias) {
                     const float4* b4 = reinterpret_cast<const float4*>(sbias + c0);     // broadcast reads
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -519,11 +622,30 @@ struct TcStatsReq {
     int* nchunk_out;         // number of [2][N] partial slabs written (for bn_finalize_kernel)
 };
 
+// Residual combine request (host side of TcRes): D is the block's OUTPUT, R the shortcut branch's rows
+struct TcResReq {
+    const mopoe_rows_t* R;   // nprob row addressings of r (bf16, N columns), like D
+    const float *mean, *invstd, *gamma, *beta;
+    float a, b;
+    const uint8_t* mask;     // keep-mask on the GEMM result: MASK_BC [E2, N]; MASK_ELEM: one byte per element of r, laid out like r
+    int mask_mode;
+    int dry_run;             // only answer whether the fused epilogue applies (0) or not (2): nothing is launched
+};
+static int res_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_GEMM_RES");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
 // nprob problems of identical (E0,E1,E2,R,KW,N, output strides): window base / weights / output origin differ.
 // stats != NULL: fuse the output's per-channel statistics when the TMA-store epilogue applies; *stats->nchunk_out = 0
 // tells the caller that they were NOT produced (it then runs the separate statistics pass).
+// res != NULL: fuse the residual combine; returns 2 (nothing launched) when that epilogue does not apply to the problem.
 int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
-                                  const mopoe_rows_t* D, const TcStatsReq* stats, void* stream) {
+                                  const mopoe_rows_t* D, const TcStatsReq* stats, void* stream, const TcResReq* res) {
     MOPOE_REQUIRE(nprob >= 1 && nprob <= TCP_MAXP, "conv_gemm_tc_batched: nprob=%d", nprob);
     if (!mopoe_tc_init_state()) MOPOE_FAIL("conv_gemm_tc_batched: tcgen05 path unavailable on this device");
     if (stats && stats->nchunk_out) *stats->nchunk_out = 0;
@@ -575,6 +697,10 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
             e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
         if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         int dev = 0;
         cudaGetDevice(&dev);
@@ -621,11 +747,33 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         grid = 2 * clusters;
         if (stats && stats->ws && (size_t)grid * 8 * p.N > stats->ws_doubles) { fuse_stats = false; p.st.ws = nullptr; }
     }
+    // residual epilogue: needs the TMA-store epilogue, whole 64-column groups, 16-byte addressable rows of r, 8-byte aligned
+    // mask rows, and (when statistics were asked for) the fused statistics
+    bool fuse_res = false;
+    if (res) {
+        fuse_res = res_enabled() && tma_epi && p.N % 64 == 0 && res->R && res->mean && res->invstd && res->gamma && res->beta &&
+                   (!stats || fuse_stats) && (!stats || stats->mask_mode == MOPOE_MASK_NONE);
+        for (int i = 0; i < nprob && fuse_res; ++i)
+            fuse_res = res->R[i].d_dtype == MOPOE_BF16 && res->R[i].N == p.N && res->R[i].d == res->R[0].d &&
+                       res->R[i].s0 == res->R[0].s0 && res->R[i].s1 == res->R[0].s1 && res->R[i].s2 == res->R[0].s2 &&
+                       res->R[i].s0 % 8 == 0 && res->R[i].s1 % 8 == 0 && res->R[i].s2 % 8 == 0 && res->R[i].d_off % 8 == 0 &&
+                       (reinterpret_cast<uintptr_t>(res->R[i].d) & 15) == 0;
+        if (fuse_res && res->mask_mode != MOPOE_MASK_NONE)
+            fuse_res = res->mask && (reinterpret_cast<uintptr_t>(res->mask) & 7) == 0 &&
+                       (res->mask_mode == MOPOE_MASK_BC || res->mask_mode == MOPOE_MASK_ELEM);
+    }
     const int stage_bytes = 128 * 128 + p.BN * (pair ? 64 : 128);
     const int hdr_bytes = 16 * 8 + 48 + 64;
-    const int extra = tma_epi ? 2 * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) + (bias ? 4 * p.nacc : 0) : 0;
+    const int extra = tma_epi ? (fuse_res ? 4 : 2) * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) + (bias ? 4 * p.nacc : 0) +
+                                    (fuse_res ? 8 * p.nacc : 0)
+                              : 0;
     int stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes - extra) / stage_bytes;
     if (stages > 8) stages = 8;
+    if (res) {
+        if (stages < 3) fuse_res = false;
+        if (res->dry_run) return fuse_res ? 0 : 2;
+        if (!fuse_res) return 2;
+    }
     if (stages < 2 && tma_epi) {                  // (never with the model's shapes) fall back to the register epilogue
         tma_epi = fuse_stats = false;
         p.st.ws = nullptr;
@@ -658,8 +806,32 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     for (int i = nprob; i < TCP_MAXP; ++i) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
     if (!tma_epi) memset(maps.d, 0, sizeof(maps.d));
     else for (int i = nprob; i < TCP_MAXP; ++i) maps.d[i] = maps.d[0];
+    memset(&p.rs, 0, sizeof(p.rs));
+    if (fuse_res) {
+        for (int i = 0; i < nprob; ++i) {
+            const mopoe_rows_t& R = res->R[i];
+            const uint64_t dimsr[4] = {(uint64_t)p.N, (uint64_t)p.E0, (uint64_t)p.E1, (uint64_t)p.E2};
+            const uint64_t strr[4] = {1, (uint64_t)R.s0, (uint64_t)R.s1, (uint64_t)R.s2};
+            const uint32_t boxr[4] = {64, (uint32_t)p.BX, (uint32_t)p.BY, (uint32_t)p.NB};
+            if (mopoe_tc_encode(&maps.r[i], reinterpret_cast<const bf16*>(R.d) + R.d_off, 4, dimsr, strr, boxr, "conv_gemm_tc(R)"))
+                return 1;
+            // elementwise mask: one byte per element of r, same addressing; Dropout2d mask: [E2 = batch, N]
+            p.rs.moff[i] = res->mask_mode == MOPOE_MASK_ELEM ? R.d_off : 0;
+        }
+        for (int i = nprob; i < TCP_MAXP; ++i) { maps.r[i] = maps.r[0]; p.rs.moff[i] = p.rs.moff[0]; }
+        p.rs.mean = res->mean; p.rs.invstd = res->invstd; p.rs.gamma = res->gamma; p.rs.beta = res->beta;
+        p.rs.a = res->a; p.rs.b = res->b;
+        p.rs.mask = res->mask_mode == MOPOE_MASK_NONE ? nullptr : res->mask;
+        p.rs.mask_mode = res->mask_mode;
+        if (res->mask_mode == MOPOE_MASK_ELEM) { p.rs.ms0 = res->R[0].s0; p.rs.ms1 = res->R[0].s1; p.rs.ms2 = res->R[0].s2; }
+        else { p.rs.ms0 = 0; p.rs.ms1 = 0; p.rs.ms2 = p.N; }
+    } else {
+        memset(maps.r, 0, sizeof(maps.r));
+    }
     const int smem = 1024 + stages * stage_bytes + extra + hdr_bytes;
-    if (pair) {
+    if (fuse_res && !pair) {
+        conv_gemm_tc_persist_kernel<true, false, true><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    } else if (pair) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(TCP_THREADS);
@@ -670,7 +842,8 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true>, maps, p);
+        cudaError_t e = fuse_res ? cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true, true>, maps, p)
+                                 : cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true>, maps, p);
         if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc_pair: launch: %s", cudaGetErrorString(e));
     } else if (tma_epi)
         conv_gemm_tc_persist_kernel<true, false><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
@@ -682,7 +855,7 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
 }
 int mopoe_conv_gemm_tc_batched(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
                                const mopoe_rows_t* D, void* stream) {
-    return mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, bias, D, nullptr, stream);
+    return mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, bias, D, nullptr, stream, nullptr);
 }
 
 // =====================================================================================================================
@@ -803,6 +976,8 @@ int mopoe_conv_gemm_tc_splitk(const mopoe_window_t* A, const void* Wp, const flo
     }
     for (int i = 1; i < TCP_MAXP; ++i) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
     memset(maps.d, 0, sizeof(maps.d));
+    memset(maps.r, 0, sizeof(maps.r));
+    memset(&p.rs, 0, sizeof(p.rs));
     int sms = 148;
     {
         int dev = 0;

@@ -86,6 +86,7 @@ class Engine:
         self.persistent = os.environ.get('MOPOE_GEMM_PERSISTENT', '1') != '0'   # persistent kernel for single GEMMs too
         self.fuse_stats = os.environ.get('MOPOE_FUSE_BN_STATS', '1') != '0'     # BatchNorm statistics in the GEMM epilogue
         self.fuse_next_stats = os.environ.get('MOPOE_FUSE_NEXT_BN_STATS', '1') != '0'   # next block's bn1 statistics in combine
+        self.fuse_res = os.environ.get('MOPOE_FUSE_RES', '1') != '0'            # residual combine in conv2's GEMM epilogue
         self.wgrad_streams = os.environ.get('MOPOE_WGRAD_STREAMS', '0') != '0'          # weight gradients on side streams (opt-in: measured +-0.1 ms)
         self._wg_streams, self._wg_used, self._wg_keep = {}, set(), []
 
@@ -384,8 +385,47 @@ class Engine:
         if L.PROFILE is not None:
             L.annotate(kind=kind, bytes=passes * v.B * v.H * v.W * v.C * v.t.element_size() + extra)
 
-    def _gemm(self, win, wp, bias, rows, bn=None, out=None):
+    def _gemm(self, win, wp, bias, rows, bn=None, out=None, res=None):
+        if res is not None:
+            return self._gemm_res([win], [wp], bias, [rows], out, res, [self.rows_of(res['r'])])
         return self._gemm_batched([win], [wp], bias, [rows], bn, out)
+
+    def _gemm_res(self, wins, wps, bias, rows_list, out, res, res_rows):
+        """conv2 of a residual block with the block's combine in the epilogue (mopoe_conv_gemm_res): `out` receives
+        a * BN(r) + b * dropout(conv2) directly.  res: dict(r, stats, gamma, beta, a, b, mask, mode, next_bn).  Returns None
+        when the fused epilogue does not apply (nothing launched; the caller runs GEMM + combine), else the statistics of
+        the next block's bn1 (res['next_bn'] = its running buffers) or True."""
+        n = len(wins)
+        if wins[0].a_dtype != L.BF16 or self.impl == L.IMPL_SIMT or not self.persistent:
+            return None
+        for wp in wps:
+            assert wp.is_contiguous() and wp.dtype == torch.bfloat16
+        r = res['r']
+        assert r.ph == 0 and r.pw == 0 and r.t.is_contiguous() and (r.B, r.H, r.W, r.C) == (out.B, out.H, out.W, out.C)
+        req = L.ResReq()
+        RR = (L.Rows * n)(*res_rows)
+        req.r = RR
+        st = res['stats']
+        req.mean, req.invstd = st[0].data_ptr(), st[1].data_ptr()
+        req.gamma, req.beta = res['gamma'].data_ptr(), res['beta'].data_ptr()
+        req.a, req.b = float(res['a']), float(res['b'])
+        mask = res['mask']
+        req.mask, req.mask_mode = (mask.data_ptr() if mask is not None else None), res['mode']
+        bnreq = stats = keep = None
+        if res.get('next_bn') is not None:
+            bnreq, stats, keep = self._bn_request(out, (None, L.MASK_NONE) + tuple(res['next_bn']))
+        bnp = C.byref(bnreq) if bnreq is not None else None
+        WA = (L.Window * n)(*wins)
+        RA = (L.Rows * n)(*rows_list)
+        if not L.load().mopoe_conv_gemm_res_eligible(n, WA, L.ptr(bias), RA, self.impl, C.byref(req), bnp):
+            return None
+        PA = (C.c_void_p * n)(*[wp.data_ptr() for wp in wps])
+        w0 = wins[0]
+        flops = sum(2.0 * w.E0 * w.E1 * w.E2 * rr.N * w.R * w.KW for w, rr in zip(wins, rows_list))
+        self._timed('fprop/dgrad', flops, lambda: L.call('mopoe_conv_gemm_res', n, WA, PA, L.ptr(bias), RA, self.impl,
+                                                         C.byref(req), bnp, L.stream_ptr()),
+                    'x%d+res M=%dx%dx%d N=%d K=%dx%d' % (n, w0.E2, w0.E1, w0.E0, rows_list[0].N, w0.R, w0.KW))
+        return stats if stats is not None else True
 
     def _bn_request(self, out, bn):
         """mopoe_bn_req_t for a GEMM whose output `out` feeds a training-mode BatchNorm; bn = (mask, mode, rmean, rvar)"""
@@ -508,42 +548,56 @@ class Engine:
         return L.Rows(act.t.data_ptr(), L.dtype_code(act.dtype), N or act.C, act.origin(), act.C,
                       act.Ws * act.C, act.Hs * act.Ws * act.C)
 
-    def gemm_down(self, x, wc, bias, k, s, p, n, out_dtype=None, out=None, bn=None):
+    def gemm_down(self, x, wc, bias, k, s, p, n, out_dtype=None, out=None, bn=None, res=None):
         win, OH, OW = self.win_down(x, k, s, p)
         if out is None:
             out = Act.empty(x.B, OH, OW, n, 0, 0, out_dtype or x.dtype, self.device)
         assert (out.B, out.H, out.W, out.C) == (x.B, OH, OW, n)
+        if res is not None:
+            return self._gemm(win, wc, bias, self.rows_of(out), None, out, res)
         st = self._gemm(win, wc, bias, self.rows_of(out), bn, out)
         return out if bn is None else (out, st)
+
+    @staticmethod
+    def phase_rows(act, n, py, px):
+        """rows of sub-pixel phase (py, px) of a stride-2 deconv's output `act` (any border): pixel (2y+py, 2x+px)"""
+        if act.H == 1:
+            return L.Rows(act.t.data_ptr(), L.dtype_code(act.dtype), n, act.origin() + px * n, 2 * n, 0, act.Ws * n)
+        return L.Rows(act.t.data_ptr(), L.dtype_code(act.dtype), n, act.origin() + (py * act.Ws + px) * n, 2 * n,
+                      2 * act.Ws * n, act.Hs * act.Ws * n)
 
     def wgrad_down(self, xwin, k, s, p, yrows):
         win, OH, OW = self.win_down(xwin, k, s, p)
         assert (yrows.H, yrows.W, yrows.B) == (OH, OW, xwin.B), ((yrows.H, yrows.W), (OH, OW))
         return self._wgrad(win, self.rows_of(yrows), yrows.C, win.R * win.KW)
 
-    def gemm_up(self, x, wph, bias, n, out_dtype=None, bn=None):
-        """stride-2 k4 p1 transposed conv as 2^nd sub-pixel phase GEMMs (x must carry a border >= 1)"""
+    def gemm_up(self, x, wph, bias, n, out_dtype=None, bn=None, out=None, res=None):
+        """stride-2 k4 p1 transposed conv as 2^nd sub-pixel phase GEMMs (x must carry a border >= 1).  out: an existing
+        (possibly bordered) activation to write the interior of.  res: see _gemm_res (returns its result)."""
         Cc = x.C
         assert x.pw >= 1 and (x.H == 1 or x.ph >= 1)
+        if out is None:
+            out = Act.empty(x.B, 1 if x.H == 1 else 2 * x.H, 2 * x.W, n, 0, 0, out_dtype or x.dtype, self.device)
+        assert (out.B, out.H, out.W, out.C) == (x.B, 1 if x.H == 1 else 2 * x.H, 2 * x.W, n)
+        wins, rows_l, res_rows = [], [], []
         if x.H == 1:
-            out = Act.empty(x.B, 1, 2 * x.W, n, 0, 0, out_dtype or x.dtype, self.device)
-            wins, rows_l = [], []
             for px in range(2):
                 wins.append(L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, 1, x.B, 1, 2 * Cc, 0,
                                      (x.pw - 1 + px) * Cc, Cc, 0, x.Ws * Cc, 0))
-                rows_l.append(L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, px * n, 2 * n, 0, 2 * x.W * n))
-            st = self._gemm_batched(wins, list(wph), bias, rows_l, bn, out)
-            return out if bn is None else (out, st)
-        out = Act.empty(x.B, 2 * x.H, 2 * x.W, n, 0, 0, out_dtype or x.dtype, self.device)
-        OW = 2 * x.W
-        wins, rows_l = [], []
-        for py in range(2):
-            for px in range(2):
-                a_off = ((x.ph - 1 + py) * x.Ws + (x.pw - 1 + px)) * Cc
-                wins.append(L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 2, 2 * Cc, 0,
-                                     a_off, Cc, x.Ws * Cc, x.Hs * x.Ws * Cc, x.Ws * Cc))
-                rows_l.append(L.Rows(out.t.data_ptr(), L.dtype_code(out.dtype), n, (py * OW + px) * n, 2 * n,
-                                     2 * OW * n, 2 * x.H * OW * n))
+                rows_l.append(self.phase_rows(out, n, 0, px))
+                if res is not None:
+                    res_rows.append(self.phase_rows(res['r'], n, 0, px))
+        else:
+            for py in range(2):
+                for px in range(2):
+                    a_off = ((x.ph - 1 + py) * x.Ws + (x.pw - 1 + px)) * Cc
+                    wins.append(L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 2, 2 * Cc, 0,
+                                         a_off, Cc, x.Ws * Cc, x.Hs * x.Ws * Cc, x.Ws * Cc))
+                    rows_l.append(self.phase_rows(out, n, py, px))
+                    if res is not None:
+                        res_rows.append(self.phase_rows(res['r'], n, py, px))
+        if res is not None:
+            return self._gemm_res(wins, list(wph), bias, rows_l, out, res, res_rows)
         st = self._gemm_batched(wins, list(wph), bias, rows_l, bn, out)
         return out if bn is None else (out, st)
 

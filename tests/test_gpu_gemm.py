@@ -277,3 +277,114 @@ def test_tma_store_epilogue_writes_nothing_outside_its_rows(B, ci, co, sp):
     full = out.t.clone()
     full[:, 1:1 + OH, 1:1 + OH, :] = 7.0
     assert bool((full == 7.0).all())          # the zero border of the output tensor was not touched
+
+
+RES_CASES = [
+    # (kind, nd, B, ci, co, sp, mask, bias, next_bn, out_pad)
+    ('down', 2, 4, 64, 128, 16, 'bc', False, True, 1),      # conv2 of a 2-D down block, Dropout2d mask, bordered output
+    ('down', 2, 3, 64, 192, 20, 'bc', True, True, 0),       # ragged tiles (300 rows), conv bias, 192-column tile
+    ('down', 2, 5, 128, 640, 8, 'bc', False, False, 1),     # wide layer, no statistics
+    ('down', 1, 3, 64, 256, 200, 'elem', True, True, 1),    # 1-D block: elementwise mask laid out like r
+    ('up', 2, 4, 128, 64, 8, 'bc', False, True, 1),         # deconv block: 4 sub-pixel phases in one launch
+    ('up', 1, 5, 64, 128, 50, 'elem', True, True, 1),       # 1-D deconv: 2 phases, elementwise mask
+    ('up', 2, 3, 64, 128, 6, None, False, True, 0),         # no dropout mask (factor 1)
+    # CTA-pair kernel
+    ('down', 2, 19, 64, 256, 64, 'bc', False, True, 1),     # 152 m-tiles
+    ('down', 2, 31, 64, 256, 40, 'bc', True, True, 1),      # 155 m-tiles: odd -> phantom tile in the last pair
+    ('up', 2, 40, 256, 256, 16, 'bc', False, True, 1),      # 4 phases x 80 m-tiles, 16 k-steps
+    ('down', 1, 64, 64, 256, 1024, 'elem', False, True, 1),
+]
+
+
+@pytest.mark.parametrize('kind,nd,B,ci,co,sp,mask,bias_on,next_bn,out_pad', RES_CASES)
+def test_gemm_with_the_residual_combine_in_its_epilogue(kind, nd, B, ci, co, sp, mask, bias_on, next_bn, out_pad):
+    """mopoe_conv_gemm_res against the two launches it replaces (mopoe_conv_gemm_batched -> mopoe_combine_bn) and against
+    the definition `a * BN(residual) + b * dropout(conv2)` (ResidualBlocks.py:92-96) in fp64 on the same bf16 operands.
+    The fused epilogue combines the fp32 accumulator, the unfused path the bf16-rounded conv result: they agree to bf16
+    rounding, the fused one being the closer to the definition."""
+    from mopoe_mimic_b200 import _lib as L
+    from mopoe_mimic_b200.engine import Act, conv_form, phase_form
+    dtype = torch.bfloat16
+    eng = _eng(dtype, 'tc')
+    shp = (B, ci, sp) if nd == 1 else (B, ci, sp, sp)
+    x = _rand(shp, 41, 1.0, dtype)
+    bias = _rand((co,), 43, 0.5).cuda() if bias_on else None
+    g = torch.Generator().manual_seed(44)
+    if kind == 'down':
+        w = _rand((co, ci, 4) if nd == 1 else (co, ci, 4, 4), 42, 0.05, dtype)
+        wp = conv_form(w.cuda(), dtype)
+        conv = lambda **kw: eng.gemm_down(_act(x, 1, dtype, nd), wp, bias, 4, 2, 1, co, **kw)
+        ref_c = (F.conv1d if nd == 1 else F.conv2d)(x.double(), w.double(), None, stride=2, padding=1)
+    else:
+        w = _rand((ci, co, 4) if nd == 1 else (ci, co, 4, 4), 42, 0.05, dtype)
+        wp = phase_form(w.cuda(), dtype)
+        conv = lambda **kw: eng.gemm_up(_act(x, 1, dtype, nd), wp, bias, co, **kw)
+        ref_c = (F.conv_transpose1d if nd == 1 else F.conv_transpose2d)(x.double(), w.double(), None, stride=2, padding=1)
+    c = conv()                                                   # the unfused conv2 result (bf16)
+    OH, OW = c.H, c.W
+    rows = B * OH * OW
+    r = Act((torch.randn(B, OH, OW, co, generator=g) * 1.5).to(dtype).cuda(), B, OH, OW, co, 0, 0)
+    st3 = torch.stack((torch.randn(co, generator=g) * 0.2, torch.rand(co, generator=g) + 0.5)).cuda()
+    gamma, beta = (torch.rand(co, generator=g) + 0.5).cuda(), (torch.randn(co, generator=g) * 0.3).cuda()
+    a, b = 2.0, 0.3
+    mk, mode = None, L.MASK_NONE
+    if mask == 'bc':
+        mk, mode = (torch.rand(B * co, generator=g) < 0.5).to(torch.uint8).cuda(), L.MASK_BC
+    elif mask == 'elem':
+        mk, mode = (torch.rand(rows * co, generator=g) < 0.5).to(torch.uint8).cuda(), L.MASK_ELEM
+    rm0, rv0 = torch.randn(co, generator=g), torch.rand(co, generator=g) + 0.5
+    ph, pw = (0, out_pad) if nd == 1 else (out_pad, out_pad)
+
+    def sentinel_out():
+        guard = 4096
+        n = B * (OH + 2 * ph) * (OW + 2 * pw) * co
+        buf = torch.full((guard + n + guard,), 7.0, dtype=dtype, device='cuda')
+        return buf, guard, n, Act(buf[guard:guard + n].view(B, OH + 2 * ph, OW + 2 * pw, co), B, OH, OW, co, ph, pw)
+
+    # the path it replaces
+    y_ref = Act.empty(B, OH, OW, co, ph, pw, dtype, 'cuda')
+    rm2, rv2 = rm0.clone().cuda(), rv0.clone().cuda()
+    if next_bn:
+        y_ref, st_ref = eng.combine(r, st3, gamma, beta, c, mk, mode, a, b, y_ref, bn=(rm2, rv2))
+    else:
+        eng.combine(r, st3, gamma, beta, c, mk, mode, a, b, y_ref)
+    # fused
+    buf, guard, n, y = sentinel_out()
+    rm, rv = rm0.clone().cuda(), rv0.clone().cuda()
+    res = dict(r=r, stats=st3, gamma=gamma, beta=beta, a=a, b=b, mask=mk, mode=mode, next_bn=(rm, rv) if next_bn else None)
+    got = conv(out=y, res=res)
+    torch.cuda.synchronize()
+    assert got is not None, 'the fused residual epilogue must apply to this problem'
+    # nothing outside the interior rows was written (border pixels, guard bands)
+    assert bool((buf[:guard] == 7.0).all()) and bool((buf[guard + n:] == 7.0).all())
+    full = y.t.clone()
+    full[:, ph:ph + OH, pw:pw + OW, :] = 7.0
+    assert bool((full == 7.0).all())
+    # the definition, fp64 on the same operands
+    cc = ref_c.permute(0, 2, 3, 1) if nd == 2 else ref_c.permute(0, 2, 1).reshape(B, 1, OW, co)
+    if bias is not None:
+        cc = cc + bias.double().cpu()
+    if mask == 'bc':
+        cc = cc * (2.0 * mk.cpu().view(B, 1, 1, co).double())
+    elif mask == 'elem':
+        cc = cc * (2.0 * mk.cpu().view(B, OH, OW, co).double())
+    mean, invstd = st3[0].double().cpu(), st3[1].double().cpu()
+    bn_r = (r.t.double().cpu() - mean) * invstd * gamma.double().cpu() + beta.double().cpu()
+    want = a * bn_r + b * cc
+    yf, yr = y.interior().double().cpu(), y_ref.interior().double().cpu()
+    scale = want.abs().max()
+    err_fused, err_unfused = (yf - want).abs().max(), (yr - want).abs().max()
+    assert err_fused <= 2.0 ** -8 * scale, (float(err_fused), float(scale))       # one bf16 rounding of the result
+    assert (yf - want).abs().mean() <= 1.02 * (yr - want).abs().mean()
+    assert err_unfused <= 2.0 ** -7 * scale
+    assert (yf - yr).abs().max() <= 2.0 ** -7 * scale
+    if next_bn:
+        # statistics of the STORED output, as the separate pass computes them
+        v = y.interior().double().reshape(rows, co)
+        m_, var = v.mean(0), v.var(0, unbiased=False)
+        torch.testing.assert_close(got[0].double(), m_, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(got[1].double(), 1.0 / torch.sqrt(var + 1e-5), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(got, st_ref, rtol=2e-2, atol=2e-3)             # (of a slightly different tensor)
+        cnt = float(rows)
+        torch.testing.assert_close(rm.double(), 0.9 * rm0.double().cuda() + 0.1 * m_, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(rv.double(), 0.9 * rv0.double().cuda() + 0.1 * var * cnt / (cnt - 1), rtol=1e-4, atol=1e-5)
