@@ -125,7 +125,8 @@ int mopoe_conv_gemm_bn(int nprob, const mopoe_window_t* A, const void* const* Wp
  * back, and launch twice).  r: one row addressing per problem over the shortcut branch (bf16, N columns), same geometry as
  * D.  mask: MOPOE_MASK_BC = [E2, N] keep-bytes (Dropout2d, E2 the batch), MOPOE_MASK_ELEM = one byte per element of r,
  * laid out like r.  bn (may be NULL): also the training-mode statistics of the STORED output — the next block's bn1 —
- * with bn->mask_mode == MOPOE_MASK_NONE.  The caller zeroes the border of D's activation (mopoe_zero_border).
+ * with bn->mask_mode == MOPOE_MASK_NONE.  out (may be NULL): the activation D addresses — the launch then also writes its
+ * zero border (idle warps of the same kernel); with out == NULL the caller runs mopoe_zero_border.
  * mopoe_conv_gemm_res_eligible answers 1 when this epilogue applies (tcgen05 path, bf16, N % 64 == 0, 16-byte aligned rows,
  * MOPOE_GEMM_RES != 0); otherwise the caller runs mopoe_conv_gemm(_batched) + mopoe_combine(_bn); mopoe_conv_gemm_res fails
  * on a problem that is not eligible. */
@@ -138,6 +139,7 @@ typedef struct {
     float a, b;
     const uint8_t* mask;
     int32_t mask_mode;
+    const mopoe_view_t* out;
 } mopoe_res_req_t;
 int mopoe_conv_gemm_res_eligible(int nprob, const mopoe_window_t* A, const float* bias, const mopoe_rows_t* D, int impl,
                                  const mopoe_res_req_t* res, const mopoe_bn_req_t* bn);

@@ -48,7 +48,8 @@ class BnReq(C.Structure):
 
 class ResReq(C.Structure):
     _fields_ = [('r', C.POINTER(Rows)), ('mean', C.c_void_p), ('invstd', C.c_void_p), ('gamma', C.c_void_p),
-                ('beta', C.c_void_p), ('a', C.c_float), ('b', C.c_float), ('mask', C.c_void_p), ('mask_mode', C.c_int32)]
+                ('beta', C.c_void_p), ('a', C.c_float), ('b', C.c_float), ('mask', C.c_void_p), ('mask_mode', C.c_int32),
+                ('out', C.POINTER(View))]
 
 
 class PackJob(C.Structure):

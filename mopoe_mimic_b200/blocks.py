@@ -186,8 +186,6 @@ class ResBlockFn(torch.autograd.Function):
                               res=dict(r=r, stats=st3, gamma=P[short + '.1.weight'], beta=P[short + '.1.bias'], a=sp.a, b=sp.b,
                                        mask=m2, mode=mode, next_bn=next_bn))
         if fused is not None:
-            if oph or opw:
-                eng.zero_border(y)
             if next_bn is not None:
                 run.out_stats = fused
         else:

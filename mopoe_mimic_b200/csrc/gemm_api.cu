@@ -80,6 +80,7 @@ struct TcResReq {
     const uint8_t* mask;
     int mask_mode;
     int dry_run;
+    const mopoe_view_t* out;
 };
 int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
                                   const mopoe_rows_t* D, const TcStatsReq* stats, void* stream, const TcResReq* res);
@@ -128,6 +129,7 @@ static int res_call(int nprob, const mopoe_window_t* A, const void* const* Wp, c
     rq.a = res->a; rq.b = res->b;
     rq.mask = res->mask; rq.mask_mode = res->mask_mode;
     rq.dry_run = dry;
+    rq.out = res->out;
     TcStatsReq sq;
     if (bn) {
         sq.ws = bn->ws;

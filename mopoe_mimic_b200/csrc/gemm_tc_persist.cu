@@ -56,6 +56,10 @@ struct TcRes {
     const uint8_t* mask;          // dropout keep-mask on the GEMM result; byte address = mask + moff[prob] + m0*ms0 + m1*ms1 + m2*ms2 + n
     int mask_mode;
     long long moff[TCP_MAXP], ms0, ms1, ms2;
+    // zero border of the output activation, written by the otherwise idle statistics warps (zb == NULL: none)
+    bf16* zb;                     // interior element (0, 0, 0, 0)
+    int zB, zH, zW, zph, zpw;
+    long long zsB, zsH, zsW;
 };
 struct TcPersistParams {
     int E0, E1, E2, BX, BY, NB, T0, T1, T2;
@@ -413,6 +417,31 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         // this themselves — on short-K layers, where the epilogue is the critical path, it doubled the kernel: 158 us against
         // 87 for the M = 1M 1x1 layer.)
         const bool stats = p.st.ws != nullptr;
+        if (RES && p.rs.zb) {
+            // border pixels per image: the ph top / bottom rows (full width) + the pw left / right columns of the H middle
+            // rows (same enumeration as zero_border_kernel, elementwise.cu); items = (pixel, 16-byte chunk), dealt to all CTAs
+            const int Ws = p.rs.zW + 2 * p.rs.zpw;
+            const int per = 2 * p.rs.zph * Ws + 2 * p.rs.zpw * p.rs.zH;
+            const int cv8 = p.N >> 3;
+            const long long total = (long long)p.rs.zB * per * cv8;
+            for (long long i = (long long)blockIdx.x * 128 + (threadIdx.x - 192); i < total; i += (long long)gridDim.x * 128) {
+                const int cv = (int)(i % cv8);
+                const long long qq = i / cv8;
+                const int k = (int)(qq % per);
+                const long long b = qq / per;
+                int hs, ws;
+                if (k < p.rs.zph * Ws) { hs = k / Ws; ws = k - hs * Ws; }
+                else if (k < 2 * p.rs.zph * Ws) { const int k2 = k - p.rs.zph * Ws; hs = p.rs.zph + p.rs.zH + k2 / Ws; ws = k2 % Ws; }
+                else {
+                    const int k2 = k - 2 * p.rs.zph * Ws;
+                    hs = p.rs.zph + k2 / (2 * p.rs.zpw);
+                    const int j = k2 % (2 * p.rs.zpw);
+                    ws = j < p.rs.zpw ? j : p.rs.zW + j;
+                }
+                bf16* dst = p.rs.zb + b * p.rs.zsB + (long long)(hs - p.rs.zph) * p.rs.zsH + (long long)(ws - p.rs.zpw) * p.rs.zsW + cv * 8;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
         if (stats) {
             const int q = warp - 6;
             const int row = q * 32 + lane;
@@ -630,6 +659,7 @@ struct TcResReq {
     const uint8_t* mask;     // keep-mask on the GEMM result: MASK_BC [E2, N]; MASK_ELEM: one byte per element of r, laid out like r
     int mask_mode;
     int dry_run;             // only answer whether the fused epilogue applies (0) or not (2): nothing is launched
+    const mopoe_view_t* out; // may be NULL; the activation D addresses: the launch also writes its zero border
 };
 static int res_enabled() {
     static int v = -1;
@@ -758,6 +788,9 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
                        res->R[i].s0 == res->R[0].s0 && res->R[i].s1 == res->R[0].s1 && res->R[i].s2 == res->R[0].s2 &&
                        res->R[i].s0 % 8 == 0 && res->R[i].s1 % 8 == 0 && res->R[i].s2 % 8 == 0 && res->R[i].d_off % 8 == 0 &&
                        (reinterpret_cast<uintptr_t>(res->R[i].d) & 15) == 0;
+        if (fuse_res && res->out)
+            fuse_res = res->out->dtype == MOPOE_BF16 && res->out->C == p.N && res->out->sW % 8 == 0 && res->out->sH % 8 == 0 &&
+                       res->out->sB % 8 == 0 && (reinterpret_cast<uintptr_t>(res->out->ptr) & 15) == 0;
         if (fuse_res && res->mask_mode != MOPOE_MASK_NONE)
             fuse_res = res->mask && (reinterpret_cast<uintptr_t>(res->mask) & 7) == 0 &&
                        (res->mask_mode == MOPOE_MASK_BC || res->mask_mode == MOPOE_MASK_ELEM);
@@ -825,6 +858,12 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         p.rs.mask_mode = res->mask_mode;
         if (res->mask_mode == MOPOE_MASK_ELEM) { p.rs.ms0 = res->R[0].s0; p.rs.ms1 = res->R[0].s1; p.rs.ms2 = res->R[0].s2; }
         else { p.rs.ms0 = 0; p.rs.ms1 = 0; p.rs.ms2 = p.N; }
+        if (res->out && (res->out->ph > 0 || res->out->pw > 0)) {
+            const mopoe_view_t* o = res->out;
+            p.rs.zb = reinterpret_cast<bf16*>(o->ptr);
+            p.rs.zB = o->B; p.rs.zH = o->H; p.rs.zW = o->W; p.rs.zph = o->ph; p.rs.zpw = o->pw;
+            p.rs.zsB = o->sB; p.rs.zsH = o->sH; p.rs.zsW = o->sW;
+        }
     } else {
         memset(maps.r, 0, sizeof(maps.r));
     }

@@ -392,7 +392,7 @@ class Engine:
 
     def _gemm_res(self, wins, wps, bias, rows_list, out, res, res_rows):
         """conv2 of a residual block with the block's combine in the epilogue (mopoe_conv_gemm_res): `out` receives
-        a * BN(r) + b * dropout(conv2) directly.  res: dict(r, stats, gamma, beta, a, b, mask, mode, next_bn).  Returns None
+        a * BN(r) + b * dropout(conv2) directly, zero border included.  res: dict(r, stats, gamma, beta, a, b, mask, mode, next_bn).  Returns None
         when the fused epilogue does not apply (nothing launched; the caller runs GEMM + combine), else the statistics of
         the next block's bn1 (res['next_bn'] = its running buffers) or True."""
         n = len(wins)
@@ -411,6 +411,8 @@ class Engine:
         req.a, req.b = float(res['a']), float(res['b'])
         mask = res['mask']
         req.mask, req.mask_mode = (mask.data_ptr() if mask is not None else None), res['mode']
+        oview = out.view()
+        req.out = C.pointer(oview)               # the launch also writes the zero border of `out`
         bnreq = stats = keep = None
         if res.get('next_bn') is not None:
             bnreq, stats, keep = self._bn_request(out, (None, L.MASK_NONE) + tuple(res['next_bn']))

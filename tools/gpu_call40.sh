@@ -1,18 +1,18 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_gemm.py -q --maxfail=20 -k "residual_combine or tma_store or fused_batchnorm" > gpurun_out/r4a_gemm.log 2>&1; echo "gemm exit $?" >> gpurun_out/r4a_gemm.log
-grep -E "^FAILED|passed|failed|exit|^E " gpurun_out/r4a_gemm.log | head -40
+timeout 600 python -m pytest tests/test_gpu_gemm.py -q --maxfail=20 -k "residual_combine or tma_store or fused_batchnorm" > gpurun_out/r4c_gemm.log 2>&1; echo "gemm exit $?" >> gpurun_out/r4c_gemm.log
+grep -E "^FAILED|passed|failed|exit|^E " gpurun_out/r4c_gemm.log | head -40
 for v in fused unfused fused2 unfused2; do
   if [ $v = unfused -o $v = unfused2 ]; then export MOPOE_FUSE_RES=0; fi
-  MOPOE_BENCH_SHAPES=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r4a_bench_$v.log 2> gpurun_out/r4a_shapes_$v.log
+  MOPOE_BENCH_SHAPES=1 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r4c_bench_$v.log 2> gpurun_out/r4c_shapes_$v.log
   echo "bench $v exit $?"
   unset MOPOE_FUSE_RES
   python - <<PY
 import json
-for l in open('gpurun_out/r4a_bench_$v.log'):
+for l in open('gpurun_out/r4c_bench_$v.log'):
     if l.startswith('{'):
         d=json.loads(l); print('$v', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'clk', d['clocks']['sm_mhz'], 'gemm', round(d['roofline']['gemm_ms_per_step'],2), d['last_step']['total_loss'])
 PY
 done
-grep "res" gpurun_out/r4a_shapes_fused.log | head -20
-tail -5 gpurun_out/r4a_shapes_fused.log
+grep "res" gpurun_out/r4c_shapes_fused.log | head -20
+tail -5 gpurun_out/r4c_shapes_fused.log
