@@ -146,6 +146,36 @@ int mopoe_conv_gemm_res_eligible(int nprob, const mopoe_window_t* A, const float
 int mopoe_conv_gemm_res(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias, const mopoe_rows_t* D,
                         int impl, const mopoe_res_req_t* res, const mopoe_bn_req_t* bn, void* stream);
 
+/* The same launch as an INPUT GRADIENT whose result dy feeds a BatchNorm(+ReLU, +dropout) backward (autograd's
+ * conv2 -> relu -> bn2 -> dropout1 chain of ResidualBlocks.py:88-92, run_epochs.py:130 total_loss.backward()): the
+ * statistics warps of the epilogue read the matching tile of the BatchNorm's input x next to every stored tile of dy and
+ * produce the two per-channel sums of the BatchNorm backward — sums[0][n] = sum_m g, sums[1][n] = sum_m g * xhat with
+ * g = dy * [relu(BN(x * 2mask)) > 0] (gate recomputed bit-exactly, as in mopoe_bn_bwd_reduce with gate_gamma / gate_beta) and
+ * xhat = (x * 2mask - mean) * invstd — plus dgamma (+)= sums[1], dbeta (+)= sums[0].  This replaces the mopoe_bn_bwd_reduce
+ * pass (two reads of the activation); mopoe_bn_bwd_apply then runs as usual on the stored dy.  x: one row addressing per
+ * problem over the BatchNorm's input (bf16, N columns), same geometry as D.  mask: MOPOE_MASK_BC [E2, N] for any nprob,
+ * MOPOE_MASK_ELEM ([rows, N] in D's flat row order) for nprob == 1.  ws: >= 8 * #SMs * N doubles.  The sums are those of
+ * the STORED (bf16-rounded) dy.  mopoe_conv_gemm_bnbwd_eligible answers 1 when this epilogue applies (MOPOE_GEMM_BNB != 0). */
+typedef struct {
+    const mopoe_rows_t* x;
+    const uint8_t* mask;
+    int32_t mask_mode;
+    int32_t accumulate;
+    const float* mean;
+    const float* invstd;
+    const float* gamma;
+    const float* beta;
+    double* ws;
+    int64_t ws_doubles;
+    float* dgamma;
+    float* dbeta;
+    float* sums;
+} mopoe_bnbwd_req_t;
+int mopoe_conv_gemm_bnbwd_eligible(int nprob, const mopoe_window_t* A, const mopoe_rows_t* D, int impl,
+                                   const mopoe_bnbwd_req_t* req);
+int mopoe_conv_gemm_bnbwd(int nprob, const mopoe_window_t* A, const void* const* Wp, const mopoe_rows_t* D, int impl,
+                          const mopoe_bnbwd_req_t* req, void* stream);
+
 /* dWp[n, r*KW + k] (+)= sum_m dY[m, n] * A[m,r,k]   (fp32 output).  `ws` holds split partials
  * (ws_bytes from mopoe_conv_wgrad_ws); replaces the weight-gradient half of autograd's conv backward
  * (run_epochs.py:130 total_loss.backward()). */

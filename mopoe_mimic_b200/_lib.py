@@ -52,6 +52,13 @@ class ResReq(C.Structure):
                 ('out', C.POINTER(View))]
 
 
+class BnBwdReq(C.Structure):
+    _fields_ = [('x', C.POINTER(Rows)), ('mask', C.c_void_p), ('mask_mode', C.c_int32), ('accumulate', C.c_int32),
+                ('mean', C.c_void_p), ('invstd', C.c_void_p), ('gamma', C.c_void_p), ('beta', C.c_void_p),
+                ('ws', C.c_void_p), ('ws_doubles', C.c_int64), ('dgamma', C.c_void_p), ('dbeta', C.c_void_p),
+                ('sums', C.c_void_p)]
+
+
 class PackJob(C.Structure):
     _fields_ = [('W', C.c_void_p), ('dst', C.c_void_p * 4), ('A', C.c_int32), ('B', C.c_int32), ('KH', C.c_int32),
                 ('KW', C.c_int32), ('form', C.c_int32), ('bpad', C.c_int32), ('tile0', C.c_int32), ('nx', C.c_int32)]
@@ -75,6 +82,8 @@ SIGNATURES = {
     'mopoe_conv_gemm_bn': (_I, [_I, _W, _P, _P, _R, _I, C.POINTER(BnReq), _P]),
     'mopoe_conv_gemm_res_eligible': (_I, [_I, _W, _P, _R, _I, C.POINTER(ResReq), C.POINTER(BnReq)]),
     'mopoe_conv_gemm_res': (_I, [_I, _W, _P, _P, _R, _I, C.POINTER(ResReq), C.POINTER(BnReq), _P]),
+    'mopoe_conv_gemm_bnbwd_eligible': (_I, [_I, _W, _R, _I, C.POINTER(BnBwdReq)]),
+    'mopoe_conv_gemm_bnbwd': (_I, [_I, _W, _P, _R, _I, C.POINTER(BnBwdReq), _P]),
     'mopoe_conv_gemm_splitk_ws': (_S, [_W, _R, _I]),
     'mopoe_conv_gemm_splitk': (_I, [_W, _P, _P, _R, _P, _S, _I, _P]),
     'mopoe_conv_wgrad_ws': (_S, [_W, _R, _I]),

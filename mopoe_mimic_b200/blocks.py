@@ -101,20 +101,23 @@ def _main_fwd(eng, spec, x, Wg, bias, dtype, bn=None, res=None, out=None):
     return out, eng.bn_stats(out, bn[0], bn[1], bn[2], bn[3])       # GEMM columns are (tap, channel) here: separate pass
 
 
-def _main_dgrad(eng, spec, dout, Wg, dtype, H, W):
-    """d/d(input) of conv2 / shortcut: dout is a bordered Act -> plain Act [B,H,W,cin]"""
+def _main_dgrad(eng, spec, dout, Wg, dtype, H, W, bnb=None):
+    """d/d(input) of conv2 / shortcut: dout is a bordered Act -> plain Act [B,H,W,cin].  bnb (Engine._gemm_bnbwd): the
+    result feeds a BatchNorm backward whose sums the GEMM epilogue can produce -> (Act, sums or None)"""
     if spec.kind == 'S' and not spec.transposed:
-        return eng.gemm_up(dout, eng.packed(Wg, "phase"), None, spec.cin)
+        return eng.gemm_up(dout, eng.packed(Wg, "phase"), None, spec.cin, bnb=bnb)
     if spec.kind == 'S':
-        return eng.gemm_down(dout, eng.packed(Wg, "conv"), None, 4, 2, 1, spec.cin)
+        return eng.gemm_down(dout, eng.packed(Wg, "conv"), None, 4, 2, 1, spec.cin, bnb=bnb)
+    if spec.kind == 'U':
+        return eng.gemm_down(dout, eng.packed(Wg, "conv"), None, 4, 1, 0, spec.cin, bnb=bnb)
     if spec.kind == 'Z':
         taps = 16 if spec.nd == 2 else 4
-        return eng.gemm_rows(dout, eng.packed(Wg, "full"), None, taps * spec.cin, out_shape=(dout.B, H, W, spec.cin))
-    if spec.kind == 'U':
-        return eng.gemm_down(dout, eng.packed(Wg, "conv"), None, 4, 1, 0, spec.cin)
-    if spec.kind == 'Q':
-        return eng.gemm_unfold(dout, eng.packed(Wg, "full"), spec.cin, H, W, 4, 1)
-    raise NotImplementedError('dgrad for block kind %r' % spec.kind)
+        out = eng.gemm_rows(dout, eng.packed(Wg, "full"), None, taps * spec.cin, out_shape=(dout.B, H, W, spec.cin))
+    elif spec.kind == 'Q':
+        out = eng.gemm_unfold(dout, eng.packed(Wg, "full"), spec.cin, H, W, 4, 1)
+    else:
+        raise NotImplementedError('dgrad for block kind %r' % spec.kind)
+    return out if bnb is None else (out, None)
 
 
 def _main_wgrad(eng, spec, xin, dout, param):
@@ -274,13 +277,14 @@ class ResBlockFn(torch.autograd.Function):
         G['conv2.weight'] = deferred(lambda: _main_wgrad(eng, sp, a2, dc, po['conv2.weight']), a2, dc)
         if sp.inner_bias:
             G['conv2.bias'] = deferred(lambda: bias_grad('conv2.bias', dc), dc)
-        da2 = _main_dgrad(eng, sp, dc, W2, dt, H, W)
-        # relu, bn2, dropout1
-        # (recomputing the ReLU gate from hh instead of re-reading a2 was measured SLOWER on B200: these passes are
-        #  issue-bound, not DRAM-bound)
+        # relu, bn2, dropout1: the two per-channel sums of the bn2 backward come out of the conv2 input-gradient GEMM's epilogue
+        # where the library can (bf16 tcgen05 path), else out of a reduction pass over (da2, hh)
         dg, db, acc = bn_slots('bn2')
+        da2, sums2 = _main_dgrad(eng, sp, dc, W2, dt, H, W,
+                                 bnb=dict(x=hh, mask=m1, mode=mode, stats=st2, gamma=P['bn2.weight'], beta=P['bn2.bias'],
+                                          dgamma=dg, dbeta=db, accumulate=acc))
         dh = eng.bn_bwd(da2, a2, 1.0, hh, m1, mode, st2, P['bn2.weight'], dg, db, None,
-                        Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device), accumulate=acc, beta=P['bn2.bias'])
+                        Act.empty(B, H, W, sp.cin, 0, 0, dt, eng.device), accumulate=acc, beta=P['bn2.bias'], sums=sums2)
         # conv1 (1x1): weight [n_out, c_in, 1..] (conv) or [c_in, n_out, 1..] (transposed conv)
         w1p = po['conv1.weight']
         done = deferred(lambda: eng.wgrad_rows_param(dh, a1, w1p) if sp.transposed else eng.wgrad_rows_param(a1, dh, w1p),

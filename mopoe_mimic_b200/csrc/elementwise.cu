@@ -498,6 +498,14 @@ int mopoe_bn_finalize_launch(const double* ws, int nchunk, int C, double count, 
     return 0;
 }
 
+// finalize of BatchNorm-backward partial sums produced elsewhere (the GEMM epilogue, gemm_api.cu): ws = [nchunk][2][C]
+int mopoe_sums_finalize_launch(const double* ws, int nchunk, int C, float* dbeta, float* dgamma, int accumulate, float* sums,
+                               void* stream) {
+    sums_finalize_kernel<<<(C + FIN_CH - 1) / FIN_CH, 256, 0, (cudaStream_t)stream>>>(ws, nchunk, C, dbeta, dgamma, accumulate, sums);
+    MOPOE_CHECK_LAUNCH("bn_bwd_finalize");
+    return 0;
+}
+
 extern "C" int mopoe_colsum(const mopoe_view_t* v, float* out, int accumulate, double* ws, int nchunk, int* counters,
                             void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -81,6 +81,7 @@ struct TcResReq {
     int mask_mode;
     int dry_run;
     const mopoe_view_t* out;
+    int kind;
 };
 int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void* const* Wp, const float* bias,
                                   const mopoe_rows_t* D, const TcStatsReq* stats, void* stream, const TcResReq* res);
@@ -130,6 +131,7 @@ static int res_call(int nprob, const mopoe_window_t* A, const void* const* Wp, c
     rq.mask = res->mask; rq.mask_mode = res->mask_mode;
     rq.dry_run = dry;
     rq.out = res->out;
+    rq.kind = 0;
     TcStatsReq sq;
     if (bn) {
         sq.ws = bn->ws;
@@ -166,6 +168,50 @@ extern "C" int mopoe_conv_gemm_res(int nprob, const mopoe_window_t* A, const voi
                                         bn->momentum, bn->mean, bn->invstd, bn->running_mean, bn->running_var, stream);
     }
     return 0;
+}
+
+// ---- input gradient with the following BatchNorm backward's per-channel sums fused into the epilogue ----------------------
+int mopoe_sums_finalize_launch(const double* ws, int nchunk, int C, float* dbeta, float* dgamma, int accumulate, float* sums,
+                               void* stream);
+static int bnbwd_call(int nprob, const mopoe_window_t* A, const void* const* Wp, const mopoe_rows_t* D, int impl,
+                      const mopoe_bnbwd_req_t* rq_in, int dry, int* fused_chunks, void* stream) {
+    if (impl == 1 || !rq_in || !rq_in->x || !rq_in->ws) return 2;
+    for (int i = 0; i < nprob; ++i)
+        if (!mopoe_tc_fwd_eligible(&A[i], &D[i])) return 2;
+    TcResReq rq;
+    rq.R = rq_in->x;
+    rq.mean = rq_in->mean; rq.invstd = rq_in->invstd; rq.gamma = rq_in->gamma; rq.beta = rq_in->beta;
+    rq.a = rq.b = 0.f;
+    rq.mask = nullptr; rq.mask_mode = MOPOE_MASK_NONE;
+    rq.dry_run = dry;
+    rq.out = nullptr;
+    rq.kind = 1;
+    TcStatsReq sq;
+    sq.ws = rq_in->ws;
+    sq.ws_doubles = (size_t)rq_in->ws_doubles;
+    sq.mask = rq_in->mask;
+    sq.mask_mode = rq_in->mask_mode;
+    sq.rows_per_b = A[0].E0 * A[0].E1;           // Dropout2d mask: sample = E2 index
+    sq.nchunk_out = fused_chunks;
+    return mopoe_conv_gemm_tc_batched_ex(nprob, A, Wp, nullptr, D, &sq, stream, &rq);
+}
+extern "C" int mopoe_conv_gemm_bnbwd_eligible(int nprob, const mopoe_window_t* A, const mopoe_rows_t* D, int impl,
+                                              const mopoe_bnbwd_req_t* req) {
+    if (nprob < 1 || nprob > 4) return 0;
+    int chunks = 0;
+    return bnbwd_call(nprob, A, nullptr, D, impl, req, 1, &chunks, nullptr) == 0;
+}
+extern "C" int mopoe_conv_gemm_bnbwd(int nprob, const mopoe_window_t* A, const void* const* Wp, const mopoe_rows_t* D, int impl,
+                                     const mopoe_bnbwd_req_t* req, void* stream) {
+    MOPOE_REQUIRE(nprob >= 1 && nprob <= 4, "conv_gemm_bnbwd: nprob=%d (1..4)", nprob);
+    MOPOE_REQUIRE(req && req->x && req->mean && req->invstd && req->gamma && req->beta && req->ws && req->sums,
+                  "conv_gemm_bnbwd: null request fields");
+    int chunks = 0;
+    const int rc = bnbwd_call(nprob, A, Wp, D, impl, req, 0, &chunks, stream);
+    if (rc == 2) MOPOE_FAIL("conv_gemm_bnbwd: the fused epilogue does not apply (ask mopoe_conv_gemm_bnbwd_eligible first)");
+    if (rc) return 1;
+    MOPOE_REQUIRE(chunks > 0, "conv_gemm_bnbwd: sums were not produced");
+    return mopoe_sums_finalize_launch(req->ws, chunks, D[0].N, req->dbeta, req->dgamma, req->accumulate, req->sums, stream);
 }
 
 // ---- split-K for weight-bound problems (few output tiles, long reduction) ------------------------------------------------

@@ -98,10 +98,16 @@ constexpr uint32_t STG_BYTES = 128 * 128;   // one staging tile: 128 rows x 64 b
 // and stores a * BN(r) + b * dropout(acc) — the block's residual combine without the round trip of the conv2 output through
 // HBM (one write + one read of the activation) and without the combine launch.  The statistics warps then sum the COMBINED
 // tile: the statistics of the next block's bn1.
-template <bool TMA_EPI, bool PAIR, bool RES = false>
+// BNB (with TMA_EPI): the GEMM is the input gradient that feeds a BatchNorm(+ReLU, +dropout) backward; the statistics warps
+// read, next to every staged output tile dy, the matching tile of the BatchNorm's INPUT x (maps.r; their own 2-buffer TMA
+// ring, two groups ahead) and accumulate the two per-channel sums of the BatchNorm backward, sum(g) and sum(g * xhat) with
+// g = dy * [relu gate recomputed from x] — the reduction pass over (dy, x) that otherwise follows the GEMM.
+template <bool TMA_EPI, bool PAIR, bool RES = false, bool BNB = false>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
 conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersistParams p) {
     static_assert(!RES || TMA_EPI, "the residual epilogue is a TMA-store epilogue");
+    static_assert(!BNB || (TMA_EPI && !RES), "the BatchNorm-backward sums ride on the TMA-store epilogue's statistics warps");
+    constexpr bool AUX = RES || BNB;                               // a second tile stream (maps.r) next to the output's
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -114,11 +120,11 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | RES: 2 residual tiles |
     //         statistics accumulators | bias row | RES: coefficient rows (scale, shift)] | header
     const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;
-    const uint32_t tiles_bytes = (RES ? 4u : 2u) * STG_BYTES;
+    const uint32_t tiles_bytes = (AUX ? 4u : 2u) * STG_BYTES;
     const uint32_t res0 = stg0 + 2 * STG_BYTES;
     const uint32_t acc_bytes = (TMA_EPI && p.st.ws) ? (uint32_t)(8 * p.nacc) * 4u : 0u;
     const uint32_t bias_bytes = (TMA_EPI && p.bias) ? (uint32_t)p.nacc * 4u : 0u;
-    const uint32_t coef_bytes = RES ? (uint32_t)p.nacc * 8u : 0u;
+    const uint32_t coef_bytes = RES ? (uint32_t)p.nacc * 8u : BNB ? (uint32_t)p.nacc * 16u : 0u;
     const uint32_t extra = TMA_EPI ? tiles_bytes + acc_bytes + bias_bytes + coef_bytes : 0u;
     float* const sacc = reinterpret_cast<float*>(gen + (size_t)p.stages * stage_bytes + tiles_bytes);
     const float* const sbias = reinterpret_cast<const float*>(gen + (size_t)p.stages * stage_bytes + tiles_bytes + acc_bytes);
@@ -139,7 +145,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             prefetch_tmap(&maps.a[i]);
             prefetch_tmap(&maps.b[i]);
             if (TMA_EPI) prefetch_tmap(&maps.d[i]);
-            if (RES) prefetch_tmap(&maps.r[i]);
+            if (AUX) prefetch_tmap(&maps.r[i]);
         }
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full0 + 8 * s, 1);
@@ -148,7 +154,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull0 + 8 * s, 1);
             mbar_init(tempty0 + 8 * s, PAIR ? 2 : 128);           // pair: one (remote) arrival per CTA, at the leader
-            if (RES) mbar_init(resfull0 + 8 * s, 1);
+            if (AUX) mbar_init(resfull0 + 8 * s, 1);
         }
         fence_barrier_init();
     }
@@ -448,10 +454,44 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             const int st_tid = threadIdx.x - 192;
             const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
             for (int i = st_tid; i < 8 * p.nacc; i += 128) sacc[i] = 0.f;
+            const int ngroups_c = p.BN >> 6;
+            // BNB: the x tile of linear group G (= tile iteration * groups per tile + group) goes to buffer G & 1
+            auto x_issue = [&](int G) {
+                const int it_ = G / ngroups_c, g_ = G - it_ * ngroups_c;
+                const long long tile_l = (long long)tile_first + (long long)it_ * tile_step;
+                if (tile_l >= p.total_tiles) return;
+                const int tile_ = (int)tile_l;
+                const int nt_ = tile_ % p.NT, tq_ = tile_ / p.NT;
+                const int prob_ = tq_ % p.nprob, mt_ = PAIR ? 2 * (tq_ / p.nprob) + (int)rank : tq_ / p.nprob;
+                const int u0 = mt_ % p.T0, u1 = (mt_ / p.T0) % p.T1, u2 = mt_ / (p.T0 * p.T1);
+                const uint32_t buf = (uint32_t)G & 1u;
+                mbar_expect_tx(resfull0 + 8 * buf, STG_BYTES);
+                tma_load_4d(res0 + buf * STG_BYTES, &maps.r[prob_], resfull0 + 8 * buf, nt_ * p.BN + g_ * 64, u0 * p.BX, u1 * p.BY,
+                            u2 * p.NB);
+            };
+            if (BNB) {
+                // per-column mean, 1/std and the forward's affine (sc, sh) — the SAME instruction sequence as the forward apply
+                // pass (stream.cu affine8), so the recomputed gate is the stored activation's sign bit for bit
+                for (int i = st_tid; i < p.nacc; i += 128) {
+                    float mu = 0.f, is = 0.f, sc = 0.f, sh = 0.f;
+                    if (i < p.N) {
+                        mu = __ldg(p.rs.mean + i);
+                        is = __ldg(p.rs.invstd + i);
+                        sc = __fmul_rn(is, __ldg(p.rs.gamma + i));
+                        sh = __fmaf_rn(-mu, sc, __ldg(p.rs.beta + i));
+                    }
+                    scoef[i] = mu;
+                    scoef[p.nacc + i] = is;
+                    scoef[2 * p.nacc + i] = sc;
+                    scoef[3 * p.nacc + i] = sh;
+                }
+                if (st_tid == 0) { x_issue(0); x_issue(1); }
+            }
             named_bar_sync(STAT_BAR, 128);
             named_bar_arrive(STG_FREE_BAR, 256);                    // both staging tiles start out free
             named_bar_arrive(STG_FREE_BAR + 1, 256);
             uint32_t sbuf = 0;
+            int gcount = 0;
             for (int tile = tile_first; tile < p.total_tiles; tile += tile_step) {
                 const int nt = tile % p.NT;
                 const int tq = tile / p.NT;
@@ -498,6 +538,66 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                         }
                     }
                     named_bar_sync(STG_FULL_BAR + (int)sbuf, 256);      // the epilogue warps have written (and fenced) the tile
+                    if (BNB) {
+                        const uint32_t xb = (uint32_t)gcount & 1u, xph = ((uint32_t)gcount >> 1) & 1u;
+                        mbar_wait(resfull0 + 8 * xb, xph);
+                        const uint32_t xbase = res0 + xb * STG_BYTES + (uint32_t)(q * 32) * 128u + wsel;
+                        const float2 mu2 = *reinterpret_cast<const float2*>(scoef + cn);
+                        const float2 is2 = *reinterpret_cast<const float2*>(scoef + p.nacc + cn);
+                        const float2 sc2 = *reinterpret_cast<const float2*>(scoef + 2 * p.nacc + cn);
+                        const float2 sh2 = *reinterpret_cast<const float2*>(scoef + 3 * p.nacc + cn);
+                        // dropout on x: one factor per column (Dropout2d, warp inside one sample), per row, or none
+                        float wf0 = 1.f, wf1 = 1.f;
+                        if (warp_mask) {
+                            const unsigned mkv = (unsigned)(mkw >> (16 * (g & 3))) & 0xffffu;
+                            wf0 = (mkv & 0xffu) ? 2.f : 0.f;
+                            wf1 = (mkv & 0xff00u) ? 2.f : 0.f;
+                        }
+                        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                        for (int hlf = 0; hlf < 2; ++hlf) {
+                            uint32_t dv[16], xw[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const uint32_t off = (uint32_t)(hlf * 16 + i) * 128u + ((jchunk ^ (uint32_t)(i & 7)) << 4);
+                                dv[i] = ld_shared_b32(lbase + off);
+                                xw[i] = ld_shared_b32(xbase + off);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const int r_ = hlf * 16 + i;
+                                float d0 = __uint_as_float(dv[i] << 16), d1 = __uint_as_float(dv[i] & 0xffff0000u);
+                                float x0 = __uint_as_float(xw[i] << 16), x1 = __uint_as_float(xw[i] & 0xffff0000u);
+                                if (row_masks) {
+                                    x0 *= (mk[r_] & 0xffu) ? 2.f : 0.f;           // exact: the forward's masked input
+                                    x1 *= (mk[r_] & 0xff00u) ? 2.f : 0.f;
+                                } else if (warp_mask) {
+                                    x0 *= wf0;
+                                    x1 *= wf1;
+                                }
+                                if (vmask != 0xffffffffu && !((vmask >> r_) & 1u)) d0 = d1 = 0.f;   // tile overhang rows
+                                // relu gate: the stored activation is > 0  <=>  y rounds to a non-zero bf16 (stream.cu gate_open)
+                                if (!(__fmaf_rn(x0, sc2.x, sh2.x) > 0x1p-134f)) d0 = 0.f;
+                                if (!(__fmaf_rn(x1, sc2.y, sh2.y) > 0x1p-134f)) d1 = 0.f;
+                                const float xh0 = (x0 - mu2.x) * is2.x, xh1 = (x1 - mu2.y) * is2.y;
+                                s0 += d0; s1 += d1;
+                                q0 = fmaf(d0, xh0, q0); q1 = fmaf(d1, xh1, q1);
+                            }
+                        }
+                        named_bar_arrive(STG_FREE_BAR + (int)sbuf, 256);
+                        named_bar_sync(STAT_BAR, 128);                  // every statistics thread has read this x tile
+                        if (st_tid == 0) x_issue(gcount + 2);
+                        ++gcount;
+                        if (cvalid) {
+                            float* a = sacc + (size_t)(q * 2) * p.nacc + cn;           // exclusive owner of these entries
+                            a[0] += s0;
+                            a[1] += s1;
+                            a[p.nacc] += q0;
+                            a[p.nacc + 1] += q1;
+                        }
+                        sbuf ^= 1u;
+                        continue;
+                    }
                     uint32_t wv[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) wv[i] = ld_shared_b32(lbase + (uint32_t)i * 128u + ((jchunk ^ (uint32_t)(i & 7)) << 4));
@@ -660,7 +760,18 @@ struct TcResReq {
     int mask_mode;
     int dry_run;             // only answer whether the fused epilogue applies (0) or not (2): nothing is launched
     const mopoe_view_t* out; // may be NULL; the activation D addresses: the launch also writes its zero border
+    int kind;                // 0: residual combine (above).  1: BatchNorm-backward sums — R addresses the BatchNorm's input x,
+                             // mean / invstd / gamma / beta are that BatchNorm's, the dropout mask on x travels in the
+                             // statistics request (TcStatsReq), which is mandatory; a, b, mask, out are unused
 };
+static int bnb_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MOPOE_GEMM_BNB");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
 static int res_enabled() {
     static int v = -1;
     if (v < 0) {
@@ -731,6 +842,10 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
             e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv_gemm_tc_persist_kernel<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_LIMIT);
         if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc_batched: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         int dev = 0;
         cudaGetDevice(&dev);
@@ -749,8 +864,12 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
                    (long long)p.E0 * p.E1 * p.E2 < (1ll << 31);
     for (int i = 0; i < nprob && tma_epi; ++i) tma_epi = D[i].d_off % 8 == 0;
     bool fuse_stats = false;
+    const bool bnb = res && res->kind == 1;
+    // (BatchNorm-backward sums: a Dropout2d mask is keyed by the sample = E2 index, which holds for every phase problem)
+    const bool bc_by_sample = bnb && stats && stats->mask_mode == MOPOE_MASK_BC && stats->mask && p.N % 2 == 0 &&
+                              stats->rows_per_b == p.E0 * p.E1;
     if (stats && tma_epi && stats->ws && (size_t)grid * 8 * p.N <= stats->ws_doubles &&
-        (stats->mask_mode == MOPOE_MASK_NONE || (nprob == 1 && stats->mask && p.N % 2 == 0))) {
+        (stats->mask_mode == MOPOE_MASK_NONE || (nprob == 1 && stats->mask && p.N % 2 == 0) || bc_by_sample)) {
         fuse_stats = true;
         p.st.ws = stats->ws;
         p.st.mask = stats->mask_mode == MOPOE_MASK_NONE ? nullptr : stats->mask;
@@ -781,24 +900,24 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     // mask rows, and (when statistics were asked for) the fused statistics
     bool fuse_res = false;
     if (res) {
-        fuse_res = res_enabled() && tma_epi && p.N % 64 == 0 && res->R && res->mean && res->invstd && res->gamma && res->beta &&
-                   (!stats || fuse_stats) && (!stats || stats->mask_mode == MOPOE_MASK_NONE);
+        fuse_res = (bnb ? bnb_enabled() : res_enabled()) && tma_epi && p.N % 64 == 0 && res->R && res->mean && res->invstd &&
+                   res->gamma && res->beta && (!stats || fuse_stats) && (bnb ? stats != nullptr : (!stats || stats->mask_mode == MOPOE_MASK_NONE));
         for (int i = 0; i < nprob && fuse_res; ++i)
             fuse_res = res->R[i].d_dtype == MOPOE_BF16 && res->R[i].N == p.N && res->R[i].d == res->R[0].d &&
                        res->R[i].s0 == res->R[0].s0 && res->R[i].s1 == res->R[0].s1 && res->R[i].s2 == res->R[0].s2 &&
                        res->R[i].s0 % 8 == 0 && res->R[i].s1 % 8 == 0 && res->R[i].s2 % 8 == 0 && res->R[i].d_off % 8 == 0 &&
                        (reinterpret_cast<uintptr_t>(res->R[i].d) & 15) == 0;
-        if (fuse_res && res->out)
+        if (fuse_res && !bnb && res->out)
             fuse_res = res->out->dtype == MOPOE_BF16 && res->out->C == p.N && res->out->sW % 8 == 0 && res->out->sH % 8 == 0 &&
                        res->out->sB % 8 == 0 && (reinterpret_cast<uintptr_t>(res->out->ptr) & 15) == 0;
-        if (fuse_res && res->mask_mode != MOPOE_MASK_NONE)
+        if (fuse_res && !bnb && res->mask_mode != MOPOE_MASK_NONE)
             fuse_res = res->mask && (reinterpret_cast<uintptr_t>(res->mask) & 7) == 0 &&
                        (res->mask_mode == MOPOE_MASK_BC || res->mask_mode == MOPOE_MASK_ELEM);
     }
     const int stage_bytes = 128 * 128 + p.BN * (pair ? 64 : 128);
     const int hdr_bytes = 16 * 8 + 48 + 64;
     const int extra = tma_epi ? (fuse_res ? 4 : 2) * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) + (bias ? 4 * p.nacc : 0) +
-                                    (fuse_res ? 8 * p.nacc : 0)
+                                    (fuse_res ? (bnb ? 16 : 8) * p.nacc : 0)
                               : 0;
     int stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes - extra) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -854,11 +973,11 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         for (int i = nprob; i < TCP_MAXP; ++i) { maps.r[i] = maps.r[0]; p.rs.moff[i] = p.rs.moff[0]; }
         p.rs.mean = res->mean; p.rs.invstd = res->invstd; p.rs.gamma = res->gamma; p.rs.beta = res->beta;
         p.rs.a = res->a; p.rs.b = res->b;
-        p.rs.mask = res->mask_mode == MOPOE_MASK_NONE ? nullptr : res->mask;
-        p.rs.mask_mode = res->mask_mode;
-        if (res->mask_mode == MOPOE_MASK_ELEM) { p.rs.ms0 = res->R[0].s0; p.rs.ms1 = res->R[0].s1; p.rs.ms2 = res->R[0].s2; }
+        p.rs.mask = (bnb || res->mask_mode == MOPOE_MASK_NONE) ? nullptr : res->mask;
+        p.rs.mask_mode = bnb ? MOPOE_MASK_NONE : res->mask_mode;
+        if (!bnb && res->mask_mode == MOPOE_MASK_ELEM) { p.rs.ms0 = res->R[0].s0; p.rs.ms1 = res->R[0].s1; p.rs.ms2 = res->R[0].s2; }
         else { p.rs.ms0 = 0; p.rs.ms1 = 0; p.rs.ms2 = p.N; }
-        if (res->out && (res->out->ph > 0 || res->out->pw > 0)) {
+        if (!bnb && res->out && (res->out->ph > 0 || res->out->pw > 0)) {
             const mopoe_view_t* o = res->out;
             p.rs.zb = reinterpret_cast<bf16*>(o->ptr);
             p.rs.zB = o->B; p.rs.zH = o->H; p.rs.zW = o->W; p.rs.zph = o->ph; p.rs.zpw = o->pw;
@@ -869,7 +988,8 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     }
     const int smem = 1024 + stages * stage_bytes + extra + hdr_bytes;
     if (fuse_res && !pair) {
-        conv_gemm_tc_persist_kernel<true, false, true><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+        if (bnb) conv_gemm_tc_persist_kernel<true, false, false, true><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+        else conv_gemm_tc_persist_kernel<true, false, true><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
     } else if (pair) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
@@ -881,8 +1001,9 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        cudaError_t e = fuse_res ? cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true, true>, maps, p)
-                                 : cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true>, maps, p);
+        cudaError_t e = !fuse_res ? cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true>, maps, p)
+                        : bnb     ? cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true, false, true>, maps, p)
+                                  : cudaLaunchKernelEx(&cfg, conv_gemm_tc_persist_kernel<true, true, true>, maps, p);
         if (e != cudaSuccess) MOPOE_FAIL("conv_gemm_tc_pair: launch: %s", cudaGetErrorString(e));
     } else if (tma_epi)
         conv_gemm_tc_persist_kernel<true, false><<<grid, TCP_THREADS, smem, (cudaStream_t)stream>>>(maps, p);

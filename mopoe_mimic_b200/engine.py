@@ -87,6 +87,7 @@ class Engine:
         self.fuse_stats = os.environ.get('MOPOE_FUSE_BN_STATS', '1') != '0'     # BatchNorm statistics in the GEMM epilogue
         self.fuse_next_stats = os.environ.get('MOPOE_FUSE_NEXT_BN_STATS', '1') != '0'   # next block's bn1 statistics in combine
         self.fuse_res = os.environ.get('MOPOE_FUSE_RES', '1') != '0'            # residual combine in conv2's GEMM epilogue
+        self.fuse_bnb = os.environ.get('MOPOE_FUSE_BNB', '1') != '0'            # bn2-backward sums in conv2's dgrad epilogue
         self.wgrad_streams = os.environ.get('MOPOE_WGRAD_STREAMS', '0') != '0'          # weight gradients on side streams (opt-in: measured +-0.1 ms)
         self._wg_streams, self._wg_used, self._wg_keep = {}, set(), []
 
@@ -238,21 +239,26 @@ class Engine:
                L.ptr(st[0]), L.ptr(st[1]), L.ptr(bn[0]), L.ptr(bn[1]), L.stream_ptr())
         return out, st
 
-    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out, accumulate=False, beta=None):
+    def bn_bwd(self, dy, gate, gscale, x, mask, mode, stats, gamma, dgamma, dbeta, addend, out, accumulate=False, beta=None,
+               sums=None):
         """Both halves of the BN(+ReLU, +dropout) backward; returns `out` = d/d(x).  gate = the saved post-ReLU
         activation (None: no ReLU).  beta: the BatchNorm's bias when `gate` is this BatchNorm's own relu output — lets both
-        passes recompute the gate from x (bit-identical) instead of reading the activation."""
-        rows = x.B * x.H * x.W
-        nc = self.nchunk(rows, x.C)
-        ws = self.ws64(2 * nc * x.C)
-        sums = self.f32(2, x.C)
+        passes recompute the gate from x (bit-identical) instead of reading the activation.  sums: the reduction's result
+        when the GEMM that produced dy already delivered it (_gemm_bnbwd; dgamma / dbeta are then written too)."""
         gv = C.byref(gate.view()) if gate is not None else None
         recomp = gate is not None and beta is not None
         gg, gb = (L.ptr(gamma), L.ptr(beta)) if recomp else (None, None)
-        self._bytes('bn_bwd_reduce', x, (2 if recomp else 3) if gate is not None else 2)
-        L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
-               L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(sums),
-               gg, gb, L.ptr(self.counters), L.stream_ptr())
+        if sums is None:
+            rows = x.B * x.H * x.W
+            nc = self.nchunk(rows, x.C)
+            ws = self.ws64(2 * nc * x.C)
+            sums = self.f32(2, x.C)
+            self._bytes('bn_bwd_reduce', x, (2 if recomp else 3) if gate is not None else 2)
+            L.call('mopoe_bn_bwd_reduce', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
+                   L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(ws), nc, L.ptr(dgamma), L.ptr(dbeta), int(accumulate), L.ptr(sums),
+                   gg, gb, L.ptr(self.counters), L.stream_ptr())
+        else:
+            assert recomp and gscale == 1.0
         av = C.byref(addend.view()) if addend is not None else None
         self._bytes('bn_bwd_apply', x, 3 + (gate is not None and not recomp) + (addend is not None))
         L.call('mopoe_bn_bwd_apply', C.byref(dy.view()), gv, float(gscale), C.byref(x.view()), L.ptr(mask), mode,
@@ -385,10 +391,49 @@ class Engine:
         if L.PROFILE is not None:
             L.annotate(kind=kind, bytes=passes * v.B * v.H * v.W * v.C * v.t.element_size() + extra)
 
-    def _gemm(self, win, wp, bias, rows, bn=None, out=None, res=None):
+    def _gemm(self, win, wp, bias, rows, bn=None, out=None, res=None, bnb=None):
         if res is not None:
             return self._gemm_res([win], [wp], bias, [rows], out, res, [self.rows_of(res['r'])])
+        if bnb is not None:
+            return self._gemm_bnbwd([win], [wp], bias, [rows], out, bnb, [self.rows_of(bnb['x'])])
         return self._gemm_batched([win], [wp], bias, [rows], bn, out)
+
+    def _gemm_bnbwd(self, wins, wps, bias, rows_list, out, bnb, x_rows):
+        """an input-gradient GEMM whose result `out` feeds a BatchNorm(+ReLU, +dropout) backward: the BatchNorm-backward
+        sums come out of the GEMM epilogue (mopoe_conv_gemm_bnbwd) instead of a reduction pass over (out, x).  bnb:
+        dict(x, mask, mode, stats, gamma, beta, dgamma, dbeta, accumulate).  Always runs the GEMM; returns the sums [2, C]
+        (for bn_bwd(..., sums=)) or None when the fused epilogue does not apply."""
+        n = len(wins)
+        x = bnb['x']
+        ok = (bias is None and wins[0].a_dtype == L.BF16 and self.impl != L.IMPL_SIMT and self.persistent and self.fuse_bnb
+              and x.dtype == torch.bfloat16 and (x.B, x.H, x.W, x.C) == (out.B, out.H, out.W, out.C))
+        if ok:
+            req = L.BnBwdReq()
+            XR = (L.Rows * n)(*x_rows)
+            req.x = XR
+            mask = bnb['mask']
+            req.mask, req.mask_mode = (mask.data_ptr() if mask is not None else None), bnb['mode']
+            req.accumulate = int(bool(bnb['accumulate']))
+            st = bnb['stats']
+            req.mean, req.invstd = st[0].data_ptr(), st[1].data_ptr()
+            req.gamma, req.beta = bnb['gamma'].data_ptr(), bnb['beta'].data_ptr()
+            ws = self.ws64(8 * 160 * out.C)
+            req.ws, req.ws_doubles = ws.data_ptr(), ws.numel()
+            sums = self.f32(2, out.C)
+            req.dgamma, req.dbeta, req.sums = bnb['dgamma'].data_ptr(), bnb['dbeta'].data_ptr(), sums.data_ptr()
+            WA = (L.Window * n)(*wins)
+            RA = (L.Rows * n)(*rows_list)
+            ok = bool(L.load().mopoe_conv_gemm_bnbwd_eligible(n, WA, RA, self.impl, C.byref(req)))
+        if not ok:
+            self._gemm_batched(wins, wps, bias, rows_list, None, out)
+            return None
+        PA = (C.c_void_p * n)(*[wp.data_ptr() for wp in wps])
+        w0 = wins[0]
+        flops = sum(2.0 * w.E0 * w.E1 * w.E2 * rr.N * w.R * w.KW for w, rr in zip(wins, rows_list))
+        self._timed('fprop/dgrad', flops, lambda: L.call('mopoe_conv_gemm_bnbwd', n, WA, PA, RA, self.impl, C.byref(req),
+                                                         L.stream_ptr()),
+                    'x%d+bnb M=%dx%dx%d N=%d K=%dx%d' % (n, w0.E2, w0.E1, w0.E0, rows_list[0].N, w0.R, w0.KW))
+        return sums
 
     def _gemm_res(self, wins, wps, bias, rows_list, out, res, res_rows):
         """conv2 of a residual block with the block's combine in the epilogue (mopoe_conv_gemm_res): `out` receives
@@ -550,13 +595,16 @@ class Engine:
         return L.Rows(act.t.data_ptr(), L.dtype_code(act.dtype), N or act.C, act.origin(), act.C,
                       act.Ws * act.C, act.Hs * act.Ws * act.C)
 
-    def gemm_down(self, x, wc, bias, k, s, p, n, out_dtype=None, out=None, bn=None, res=None):
+    def gemm_down(self, x, wc, bias, k, s, p, n, out_dtype=None, out=None, bn=None, res=None, bnb=None):
+        """bnb: see _gemm_bnbwd -> returns (out, sums or None)"""
         win, OH, OW = self.win_down(x, k, s, p)
         if out is None:
             out = Act.empty(x.B, OH, OW, n, 0, 0, out_dtype or x.dtype, self.device)
         assert (out.B, out.H, out.W, out.C) == (x.B, OH, OW, n)
         if res is not None:
             return self._gemm(win, wc, bias, self.rows_of(out), None, out, res)
+        if bnb is not None:
+            return out, self._gemm(win, wc, bias, self.rows_of(out), None, out, None, bnb)
         st = self._gemm(win, wc, bias, self.rows_of(out), bn, out)
         return out if bn is None else (out, st)
 
@@ -573,7 +621,7 @@ class Engine:
         assert (yrows.H, yrows.W, yrows.B) == (OH, OW, xwin.B), ((yrows.H, yrows.W), (OH, OW))
         return self._wgrad(win, self.rows_of(yrows), yrows.C, win.R * win.KW)
 
-    def gemm_up(self, x, wph, bias, n, out_dtype=None, bn=None, out=None, res=None):
+    def gemm_up(self, x, wph, bias, n, out_dtype=None, bn=None, out=None, res=None, bnb=None):
         """stride-2 k4 p1 transposed conv as 2^nd sub-pixel phase GEMMs (x must carry a border >= 1).  out: an existing
         (possibly bordered) activation to write the interior of.  res: see _gemm_res (returns its result)."""
         Cc = x.C
@@ -587,8 +635,8 @@ class Engine:
                 wins.append(L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, 1, x.B, 1, 2 * Cc, 0,
                                      (x.pw - 1 + px) * Cc, Cc, 0, x.Ws * Cc, 0))
                 rows_l.append(self.phase_rows(out, n, 0, px))
-                if res is not None:
-                    res_rows.append(self.phase_rows(res['r'], n, 0, px))
+                if res is not None or bnb is not None:
+                    res_rows.append(self.phase_rows(res['r'] if res is not None else bnb['x'], n, 0, px))
         else:
             for py in range(2):
                 for px in range(2):
@@ -596,10 +644,12 @@ class Engine:
                     wins.append(L.Window(x.t.data_ptr(), L.dtype_code(x.dtype), x.W, x.H, x.B, 2, 2 * Cc, 0,
                                          a_off, Cc, x.Ws * Cc, x.Hs * x.Ws * Cc, x.Ws * Cc))
                     rows_l.append(self.phase_rows(out, n, py, px))
-                    if res is not None:
-                        res_rows.append(self.phase_rows(res['r'], n, py, px))
+                    if res is not None or bnb is not None:
+                        res_rows.append(self.phase_rows(res['r'] if res is not None else bnb['x'], n, py, px))
         if res is not None:
             return self._gemm_res(wins, list(wph), bias, rows_l, out, res, res_rows)
+        if bnb is not None:
+            return out, self._gemm_bnbwd(wins, list(wph), bias, rows_l, out, bnb, res_rows)
         st = self._gemm_batched(wins, list(wph), bias, rows_l, bn, out)
         return out if bn is None else (out, st)
 

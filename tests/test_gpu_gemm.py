@@ -388,3 +388,92 @@ def test_gemm_with_the_residual_combine_in_its_epilogue(kind, nd, B, ci, co, sp,
         cnt = float(rows)
         torch.testing.assert_close(rm.double(), 0.9 * rm0.double().cuda() + 0.1 * m_, rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(rv.double(), 0.9 * rv0.double().cuda() + 0.1 * var * cnt / (cnt - 1), rtol=1e-4, atol=1e-5)
+
+
+BNB_CASES = [
+    # (kind, nd, B, ci, co, sp, mask, accumulate): GEMM = input gradient of a k4 s2 p1 (de)conv, ci gradient channels in, co out
+    ('up', 2, 4, 128, 64, 8, 'bc', False),         # dgrad of a 2-D down block's conv2: 4 phases, Dropout2d mask by sample
+    ('up', 2, 3, 64, 128, 10, 'bc', True),         # ragged tiles, accumulate into dgamma / dbeta
+    ('up', 2, 2, 64, 192, 4, 'bc', False),         # 16-pixel images: a warp's 32 rows span two samples (per-row masks)
+    ('down', 2, 4, 64, 128, 16, 'bc', False),      # dgrad of a deconv block's conv2
+    ('down', 2, 5, 128, 640, 8, None, True),       # no dropout, wide layer
+    ('down', 1, 3, 64, 256, 200, 'elem', False),   # 1-D deconv block: elementwise mask, single problem
+    ('up', 1, 5, 64, 128, 50, 'elem', False),      # elementwise mask over 2 phase problems: falls back to the reduction pass
+    # CTA-pair kernel
+    ('down', 2, 19, 64, 256, 64, 'bc', False),
+    ('down', 2, 31, 64, 256, 40, 'bc', True),      # odd m-tile count: phantom tile
+    ('up', 2, 40, 256, 256, 16, 'bc', False),
+]
+
+
+@pytest.mark.parametrize('kind,nd,B,ci,co,sp,mask,accumulate', BNB_CASES)
+def test_input_gradient_gemm_with_the_batchnorm_backward_sums_in_its_epilogue(kind, nd, B, ci, co, sp, mask, accumulate):
+    """mopoe_conv_gemm_bnbwd: same stored output as the plain launch (bit for bit), and sums / dgamma / dbeta equal to the
+    mopoe_bn_bwd_reduce pass over that output (the pass it replaces) and to the fp64 definition."""
+    from mopoe_mimic_b200 import _lib as L
+    from mopoe_mimic_b200.engine import Act, conv_form, phase_form
+    dtype = torch.bfloat16
+    eng = _eng(dtype, 'tc')
+    shp = (B, ci, sp) if nd == 1 else (B, ci, sp, sp)
+    dyin = _rand(shp, 51, 1.0, dtype)
+    g = torch.Generator().manual_seed(54)
+    if kind == 'down':
+        w = _rand((co, ci, 4) if nd == 1 else (co, ci, 4, 4), 52, 0.05, dtype)
+        wp = conv_form(w.cuda(), dtype)
+        gemm = lambda **kw: eng.gemm_down(_act(dyin, 1, dtype, nd), wp, None, 4, 2, 1, co, **kw)
+    else:
+        w = _rand((ci, co, 4) if nd == 1 else (ci, co, 4, 4), 52, 0.05, dtype)
+        wp = phase_form(w.cuda(), dtype)
+        gemm = lambda **kw: eng.gemm_up(_act(dyin, 1, dtype, nd), wp, None, co, **kw)
+    plain = gemm()
+    OH, OW = plain.H, plain.W
+    rows = B * OH * OW
+    x = Act((torch.randn(B, OH, OW, co, generator=g) * 1.5).to(dtype).cuda(), B, OH, OW, co, 0, 0)
+    mk, mode = None, L.MASK_NONE
+    if mask == 'bc':
+        mk, mode = (torch.rand(B * co, generator=g) < 0.5).to(torch.uint8).cuda(), L.MASK_BC
+    elif mask == 'elem':
+        mk, mode = (torch.rand(rows * co, generator=g) < 0.5).to(torch.uint8).cuda(), L.MASK_ELEM
+    gamma, beta = (torch.rand(co, generator=g) + 0.5).cuda(), (torch.randn(co, generator=g) * 0.3).cuda()
+    st = eng.bn_stats(x, mk, mode)
+    a2 = eng.bn_apply(x, mk, mode, st, gamma, beta, True, Act.empty(B, OH, OW, co, 0, 0, dtype, 'cuda'))
+    dg0, db0 = torch.randn(co, generator=g).cuda(), torch.randn(co, generator=g).cuda()
+    # the pass it replaces
+    dg_ref, db_ref = dg0.clone(), db0.clone()
+    dh_ref = eng.bn_bwd(plain, a2, 1.0, x, mk, mode, st, gamma, dg_ref, db_ref, None, Act.empty(B, OH, OW, co, 0, 0, dtype, 'cuda'),
+                        accumulate=accumulate, beta=beta)
+    # fused
+    dg, db = dg0.clone(), db0.clone()
+    out, sums = gemm(bnb=dict(x=x, mask=mk, mode=mode, stats=st, gamma=gamma, beta=beta, dgamma=dg, dbeta=db,
+                              accumulate=accumulate))
+    torch.cuda.synchronize()
+    assert torch.equal(out.t, plain.t)
+    if mask == 'elem' and kind == 'up':
+        assert sums is None                      # not eligible: the GEMM ran plain, the caller runs the reduction pass
+        return
+    assert sums is not None, 'the fused epilogue must apply to this problem'
+    dh = eng.bn_bwd(out, a2, 1.0, x, mk, mode, st, gamma, dg, db, None, Act.empty(B, OH, OW, co, 0, 0, dtype, 'cuda'),
+                    accumulate=accumulate, beta=beta, sums=sums)
+    torch.cuda.synchronize()
+    # fp64 definition on the stored values
+    d = plain.t.double().reshape(rows, co)
+    xv = x.t.double().reshape(rows, co)
+    if mask == 'bc':
+        xv = (xv.view(B, -1, co) * (2.0 * mk.view(B, 1, co).double())).reshape(rows, co)
+    elif mask == 'elem':
+        xv = xv * (2.0 * mk.view(rows, co).double())
+    gate = (a2.t.reshape(rows, co) > 0).double()
+    gg = d * gate
+    xh = (xv - st[0].double()) * st[1].double()
+    s_def = torch.stack((gg.sum(0), (gg * xh).sum(0)))
+    scale = torch.stack((gg.abs().sum(0), (gg * xh).abs().sum(0))) + 1e-6
+    assert float(((sums.double() - s_def).abs() / scale).max()) <= 1e-5
+    base_g = dg0.double() if accumulate else torch.zeros(co, dtype=torch.float64, device='cuda')
+    base_b = db0.double() if accumulate else torch.zeros(co, dtype=torch.float64, device='cuda')
+    assert float(((dg.double() - base_g - s_def[1]).abs() / (scale[1] + base_g.abs())).max()) <= 1e-5
+    assert float(((db.double() - base_b - s_def[0]).abs() / (scale[0] + base_b.abs())).max()) <= 1e-5
+    # and against the reduction pass
+    assert float(((dg - dg_ref).abs() / (scale[1].float() + dg_ref.abs())).max()) <= 1e-5
+    assert float(((db - db_ref).abs() / (scale[0].float() + db_ref.abs())).max()) <= 1e-5
+    diff = (dh.t.float() - dh_ref.t.float()).abs().max()
+    assert float(diff) <= 2.0 ** -7 * float(dh_ref.t.float().abs().max())
