@@ -120,7 +120,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | RES: 2 residual tiles |
     //         statistics accumulators | bias row | RES: coefficient rows (scale, shift)] | header
     const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;
-    const uint32_t tiles_bytes = (AUX ? 4u : 2u) * STG_BYTES;
+    const uint32_t tiles_bytes = (AUX ? 3u : 2u) * STG_BYTES;
     const uint32_t res0 = stg0 + 2 * STG_BYTES;
     const uint32_t acc_bytes = (TMA_EPI && p.st.ws) ? (uint32_t)(8 * p.nacc) * 4u : 0u;
     const uint32_t bias_bytes = (TMA_EPI && p.bias) ? (uint32_t)p.nacc * 4u : 0u;
@@ -132,7 +132,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     const uint32_t hdr = stg0 + extra;
     // header: full[stages] | empty[stages] | tmem_full[2] | tmem_empty[2] | tmem_ptr | res_full[2]
     const uint32_t full0 = hdr, empty0 = hdr + 8u * p.stages, tfull0 = hdr + 16u * p.stages, tempty0 = tfull0 + 16,
-                   tmem_slot = tempty0 + 16, resfull0 = tmem_slot + 8;
+                   tmem_slot = tempty0 + 16, resfull0 = tmem_slot + 8, aux_dummy = resfull0 + 8;
     volatile uint32_t* tmem_slot_gen =
         reinterpret_cast<volatile uint32_t*>(gen + (size_t)p.stages * stage_bytes + extra + 16 * p.stages + 32);
 
@@ -154,8 +154,8 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         for (int s = 0; s < 2; ++s) {
             mbar_init(tfull0 + 8 * s, 1);
             mbar_init(tempty0 + 8 * s, PAIR ? 2 : 128);           // pair: one (remote) arrival per CTA, at the leader
-            if (AUX) mbar_init(resfull0 + 8 * s, 1);
         }
+        if (AUX) mbar_init(resfull0, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -273,18 +273,19 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         int iter = 0;
         uint32_t sbuf = 0;
         const uint32_t tempty_leader0 = PAIR ? mapa_shared(tempty0, 0) : tempty0;
-        // RES: residual tile ring (2 buffers), filled one 64-column group ahead by the leader thread
+        // RES: ONE residual tile buffer.  A group starts by pulling the thread's residual row (64 bf16) into registers; once all
+        // 128 rows are out, the leader thread refills the buffer with the next group's tile, which lands under this group's
+        // TMEM loads, math and stores.  (Two buffers cost a stage of the operand ring: -17 % on the fill-bound 128-column layers.)
         const int ri1 = row % p.BX, ri2 = (row / p.BX) % p.BY, ri4 = row / (p.BX * p.BY);
         uint32_t gcount = 0;
-        auto res_issue = [&](int tile_, int g_, uint32_t buf) {
+        auto res_issue = [&](int tile_, int g_) {
             const int nt_ = tile_ % p.NT, tq_ = tile_ / p.NT;
             const int prob_ = tq_ % p.nprob, mt_ = PAIR ? 2 * (tq_ / p.nprob) + (int)rank : tq_ / p.nprob;
             const int u0 = mt_ % p.T0, u1 = (mt_ / p.T0) % p.T1, u2 = mt_ / (p.T0 * p.T1);
-            mbar_expect_tx(resfull0 + 8 * buf, STG_BYTES);
-            tma_load_4d(res0 + buf * STG_BYTES, &maps.r[prob_], resfull0 + 8 * buf, nt_ * p.BN + g_ * 64, u0 * p.BX, u1 * p.BY,
-                        u2 * p.NB);
+            mbar_expect_tx(resfull0, STG_BYTES);
+            tma_load_4d(res0, &maps.r[prob_], resfull0, nt_ * p.BN + g_ * 64, u0 * p.BX, u1 * p.BY, u2 * p.NB);
         };
-        if (RES && leader && tile_first < p.total_tiles) res_issue(tile_first, 0, 0u);
+        if (RES && leader && tile_first < p.total_tiles) res_issue(tile_first, 0);
         for (int tile = tile_first; tile < p.total_tiles; tile += tile_step, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (uint32_t)(iter >> 1) & 1u;
@@ -299,6 +300,29 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             const int ngroups = p.BN >> 6;
             for (int g = 0; g < ngroups; ++g) {
                 const int c0 = n0 + g * 64;
+                uint32_t w[32];                                     // 64 bf16, packed (RES: the residual row first, then the result)
+                if (RES) {
+                    mbar_wait(resfull0, gcount & 1u);
+                    const uint32_t rrow = res0 + (uint32_t)row * 128u;
+                    uint32_t chk = 0u;
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch) {
+                        uint32_t rw[4];
+                        ld_shared_v4(rrow + ((((uint32_t)ch) ^ swz) << 4), rw);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { w[4 * ch + i] = rw[i]; chk ^= rw[i]; }
+                    }
+                    // the refill below may only be issued once these loads have RETURNED (a barrier arrival alone is not ordered
+                    // behind outstanding shared-memory loads): a store that depends on every loaded word sits before the barrier
+                    if (chk == 0x9e3779b9u) st_shared_b32(aux_dummy, chk);
+                    named_bar_sync(EPI_BAR, 128);
+                    if (leader) {
+                        int ntile = tile, ng = g + 1;
+                        if (ng == ngroups) { ntile = tile + tile_step; ng = 0; }
+                        if (ntile < p.total_tiles) res_issue(ntile, ng);
+                    }
+                    ++gcount;
+                }
                 uint32_t r0[32], r1[32];
                 tmem_ld32_nowait(t_addr + (uint32_t)(g * 64), r0);
                 tmem_ld32_nowait(t_addr + (uint32_t)(g * 64 + 32), r1);
@@ -308,17 +332,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     fence_before();
                     if (!PAIR) mbar_arrive(tempty0 + 8 * acc);
                 }
-                uint32_t w[32];                                     // 64 bf16, packed
                 if (RES) {
-                    const uint32_t rbuf = gcount & 1u, rph = (gcount >> 1) & 1u;
-                    if (leader) {
-                        // the NEXT group's residual tile goes into the other buffer: every thread finished reading that one
-                        // before the last barrier of the previous group
-                        int ntile = tile, ng = g + 1;
-                        if (ng == ngroups) { ntile = tile + tile_step; ng = 0; }
-                        if (ntile < p.total_tiles) res_issue(ntile, ng, rbuf ^ 1u);
-                    }
-                    ++gcount;
                     const int m0 = t0 * p.BX + ri1, m1 = t1 * p.BY + ri2, m2 = t2 * p.NB + ri4;
                     const bool rvalid = m0 < p.E0 && m1 < p.E1 && m2 < p.E2;
                     const uint8_t* mrow = nullptr;                  // this row's 64 keep-mask bytes
@@ -335,12 +349,9 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     const float4* b4 = reinterpret_cast<const float4*>(sbias + c0);
                     const bool has_bias = p.bias != nullptr;
                     const float bco = p.rs.b;
-                    mbar_wait(resfull0 + 8 * rbuf, rph);
-                    const uint32_t rrow = res0 + rbuf * STG_BYTES + (uint32_t)row * 128u;
 #pragma unroll
                     for (int ch = 0; ch < 8; ++ch) {
-                        uint32_t rw[4];
-                        ld_shared_v4(rrow + ((((uint32_t)ch) ^ swz) << 4), rw);
+                        const uint32_t rw[4] = {w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]};
                         const float4 sA = s4[2 * ch], sB = s4[2 * ch + 1], hA = h4[2 * ch], hB = h4[2 * ch + 1];
                         const float scv[8] = {sA.x, sA.y, sA.z, sA.w, sB.x, sB.y, sB.z, sB.w};
                         const float shv[8] = {hA.x, hA.y, hA.z, hA.w, hB.x, hB.y, hB.z, hB.w};
@@ -455,7 +466,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
             for (int i = st_tid; i < 8 * p.nacc; i += 128) sacc[i] = 0.f;
             const int ngroups_c = p.BN >> 6;
-            // BNB: the x tile of linear group G (= tile iteration * groups per tile + group) goes to buffer G & 1
+            // BNB: the x tile of linear group G (= tile iteration * groups per tile + group); ONE buffer, see below
             auto x_issue = [&](int G) {
                 const int it_ = G / ngroups_c, g_ = G - it_ * ngroups_c;
                 const long long tile_l = (long long)tile_first + (long long)it_ * tile_step;
@@ -464,10 +475,8 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                 const int nt_ = tile_ % p.NT, tq_ = tile_ / p.NT;
                 const int prob_ = tq_ % p.nprob, mt_ = PAIR ? 2 * (tq_ / p.nprob) + (int)rank : tq_ / p.nprob;
                 const int u0 = mt_ % p.T0, u1 = (mt_ / p.T0) % p.T1, u2 = mt_ / (p.T0 * p.T1);
-                const uint32_t buf = (uint32_t)G & 1u;
-                mbar_expect_tx(resfull0 + 8 * buf, STG_BYTES);
-                tma_load_4d(res0 + buf * STG_BYTES, &maps.r[prob_], resfull0 + 8 * buf, nt_ * p.BN + g_ * 64, u0 * p.BX, u1 * p.BY,
-                            u2 * p.NB);
+                mbar_expect_tx(resfull0, STG_BYTES);
+                tma_load_4d(res0, &maps.r[prob_], resfull0, nt_ * p.BN + g_ * 64, u0 * p.BX, u1 * p.BY, u2 * p.NB);
             };
             if (BNB) {
                 // per-column mean, 1/std and the forward's affine (sc, sh) — the SAME instruction sequence as the forward apply
@@ -485,7 +494,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                     scoef[2 * p.nacc + i] = sc;
                     scoef[3 * p.nacc + i] = sh;
                 }
-                if (st_tid == 0) { x_issue(0); x_issue(1); }
+                if (st_tid == 0) x_issue(0);
             }
             named_bar_sync(STAT_BAR, 128);
             named_bar_arrive(STG_FREE_BAR, 256);                    // both staging tiles start out free
@@ -537,11 +546,26 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                                         ? *reinterpret_cast<const unsigned short*>(p.st.mask + (size_t)key * p.N + cn) : (unsigned short)0;
                         }
                     }
+                    uint32_t xw[BNB ? 32 : 1];
+                    if (BNB) {
+                        // pull this warp's 32 x 2 x values into registers ahead of the output tile; once every statistics thread has
+                        // them the single x buffer is refilled with the next group's tile (lands under this group's math)
+                        mbar_wait(resfull0, (uint32_t)gcount & 1u);
+                        const uint32_t xbase = res0 + (uint32_t)(q * 32) * 128u + wsel;
+                        uint32_t chk = 0u;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            xw[i] = ld_shared_b32(xbase + (uint32_t)i * 128u + ((jchunk ^ (uint32_t)(i & 7)) << 4));
+                            chk ^= xw[i];
+                        }
+                        // (a store that depends on every loaded word, before the barrier: the loads have returned — see RES)
+                        if (chk == 0x9e3779b9u) st_shared_b32(aux_dummy, chk);
+                        named_bar_sync(STAT_BAR, 128);
+                        if (st_tid == 0) x_issue(gcount + 1);
+                        ++gcount;
+                    }
                     named_bar_sync(STG_FULL_BAR + (int)sbuf, 256);      // the epilogue warps have written (and fenced) the tile
                     if (BNB) {
-                        const uint32_t xb = (uint32_t)gcount & 1u, xph = ((uint32_t)gcount >> 1) & 1u;
-                        mbar_wait(resfull0 + 8 * xb, xph);
-                        const uint32_t xbase = res0 + xb * STG_BYTES + (uint32_t)(q * 32) * 128u + wsel;
                         const float2 mu2 = *reinterpret_cast<const float2*>(scoef + cn);
                         const float2 is2 = *reinterpret_cast<const float2*>(scoef + p.nacc + cn);
                         const float2 sc2 = *reinterpret_cast<const float2*>(scoef + 2 * p.nacc + cn);
@@ -556,18 +580,15 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
                         for (int hlf = 0; hlf < 2; ++hlf) {
-                            uint32_t dv[16], xw[16];
+                            uint32_t dv[16];
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const uint32_t off = (uint32_t)(hlf * 16 + i) * 128u + ((jchunk ^ (uint32_t)(i & 7)) << 4);
-                                dv[i] = ld_shared_b32(lbase + off);
-                                xw[i] = ld_shared_b32(xbase + off);
-                            }
+                            for (int i = 0; i < 16; ++i)
+                                dv[i] = ld_shared_b32(lbase + (uint32_t)(hlf * 16 + i) * 128u + ((jchunk ^ (uint32_t)(i & 7)) << 4));
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 const int r_ = hlf * 16 + i;
                                 float d0 = __uint_as_float(dv[i] << 16), d1 = __uint_as_float(dv[i] & 0xffff0000u);
-                                float x0 = __uint_as_float(xw[i] << 16), x1 = __uint_as_float(xw[i] & 0xffff0000u);
+                                float x0 = __uint_as_float(xw[r_] << 16), x1 = __uint_as_float(xw[r_] & 0xffff0000u);
                                 if (row_masks) {
                                     x0 *= (mk[r_] & 0xffu) ? 2.f : 0.f;           // exact: the forward's masked input
                                     x1 *= (mk[r_] & 0xff00u) ? 2.f : 0.f;
@@ -585,9 +606,6 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                             }
                         }
                         named_bar_arrive(STG_FREE_BAR + (int)sbuf, 256);
-                        named_bar_sync(STAT_BAR, 128);                  // every statistics thread has read this x tile
-                        if (st_tid == 0) x_issue(gcount + 2);
-                        ++gcount;
                         if (cvalid) {
                             float* a = sacc + (size_t)(q * 2) * p.nacc + cn;           // exclusive owner of these entries
                             a[0] += s0;
@@ -916,7 +934,7 @@ int mopoe_conv_gemm_tc_batched_ex(int nprob, const mopoe_window_t* A, const void
     }
     const int stage_bytes = 128 * 128 + p.BN * (pair ? 64 : 128);
     const int hdr_bytes = 16 * 8 + 48 + 64;
-    const int extra = tma_epi ? (fuse_res ? 4 : 2) * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) + (bias ? 4 * p.nacc : 0) +
+    const int extra = tma_epi ? (fuse_res ? 3 : 2) * (int)STG_BYTES + (fuse_stats ? 32 * p.nacc : 0) + (bias ? 4 * p.nacc : 0) +
                                     (fuse_res ? (bnb ? 16 : 8) * p.nacc : 0)
                               : 0;
     int stages = (TCP_SMEM_LIMIT - 1024 - hdr_bytes - extra) / stage_bytes;
