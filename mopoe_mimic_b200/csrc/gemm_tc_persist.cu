@@ -32,7 +32,9 @@ int mopoe_tc_init_state();
 void mopoe_tc_tile_split(int E0, int E1, int rows, int& BX, int& BY, int& NB);
 int mopoe_tc_pick_bn(int N);
 
-constexpr int TCP_THREADS = 320;      // TMA warp, MMA warp, 4 epilogue warps, 4 statistics warps
+// TMA warp, MMA warp, 4 epilogue warps, 4 statistics warps.  (Measured and dropped: 384 threads with the statistics warps on
+// warps 6, 7, 10, 11 — off the two schedulers that issue the TMA and MMA warps — was 0.15 ms/step SLOWER.)
+constexpr int TCP_THREADS = 320;
 constexpr int TCP_SMEM_LIMIT = 232448;
 constexpr int TCP_MAXP = 4;
 
@@ -434,6 +436,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
         // this themselves — on short-K layers, where the epilogue is the critical path, it doubled the kernel: 158 us against
         // 87 for the M = 1M 1x1 layer.)
         const bool stats = p.st.ws != nullptr;
+        const int sq = warp - 6;
         if (RES && p.rs.zb) {
             // border pixels per image: the ph top / bottom rows (full width) + the pw left / right columns of the H middle
             // rows (same enumeration as zero_border_kernel, elementwise.cu); items = (pixel, 16-byte chunk), dealt to all CTAs
@@ -441,7 +444,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             const int per = 2 * p.rs.zph * Ws + 2 * p.rs.zpw * p.rs.zH;
             const int cv8 = p.N >> 3;
             const long long total = (long long)p.rs.zB * per * cv8;
-            for (long long i = (long long)blockIdx.x * 128 + (threadIdx.x - 192); i < total; i += (long long)gridDim.x * 128) {
+            for (long long i = (long long)blockIdx.x * 128 + (sq * 32 + lane); i < total; i += (long long)gridDim.x * 128) {
                 const int cv = (int)(i % cv8);
                 const long long qq = i / cv8;
                 const int k = (int)(qq % per);
@@ -460,9 +463,9 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
             }
         }
         if (stats) {
-            const int q = warp - 6;
+            const int q = sq;
             const int row = q * 32 + lane;
-            const int st_tid = threadIdx.x - 192;
+            const int st_tid = q * 32 + lane;
             const int i1 = row % p.BX, i2 = (row / p.BX) % p.BY, i4 = row / (p.BX * p.BY);
             for (int i = st_tid; i < 8 * p.nacc; i += 128) sacc[i] = 0.f;
             const int ngroups_c = p.BN >> 6;
@@ -596,15 +599,15 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
                                     x0 *= wf0;
                                     x1 *= wf1;
                                 }
-                                if (vmask != 0xffffffffu && !((vmask >> r_) & 1u)) d0 = d1 = 0.f;   // tile overhang rows
-                                // relu gate: the stored activation is > 0  <=>  y rounds to a non-zero bf16 (stream.cu gate_open)
-                                if (!(__fmaf_rn(x0, sc2.x, sh2.x) > 0x1p-134f)) d0 = 0.f;
-                                if (!(__fmaf_rn(x1, sc2.y, sh2.y) > 0x1p-134f)) d1 = 0.f;
-                                const float xh0 = (x0 - mu2.x) * is2.x, xh1 = (x1 - mu2.y) * is2.y;
-                                s0 += d0; s1 += d1;
-                                q0 = fmaf(d0, xh0, q0); q1 = fmaf(d1, xh1, q1);
+                                // relu gate: the stored activation is > 0  <=>  y rounds to a non-zero bf16 (stream.cu gate_open);
+                                // tile overhang rows contribute nothing
+                                const bool rv_ = vmask == 0xffffffffu || ((vmask >> r_) & 1u);
+                                if (rv_ && __fmaf_rn(x0, sc2.x, sh2.x) > 0x1p-134f) { s0 += d0; q0 = fmaf(d0, x0 - mu2.x, q0); }
+                                if (rv_ && __fmaf_rn(x1, sc2.y, sh2.y) > 0x1p-134f) { s1 += d1; q1 = fmaf(d1, x1 - mu2.y, q1); }
                             }
                         }
+                        q0 *= is2.x;                                    // sum g * xhat = invstd * sum g * (x - mean)
+                        q1 *= is2.y;
                         named_bar_arrive(STG_FREE_BAR + (int)sbuf, 256);
                         if (cvalid) {
                             float* a = sacc + (size_t)(q * 2) * p.nacc + cn;           // exclusive owner of these entries
