@@ -212,7 +212,10 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
              ('mopoe_pack_job_t', L.PackJob, ['W', 'dst', 'A', 'bpad', 'tile0', 'nx']),
              ('mopoe_dp_peers_t', L.DpPeers, ['grad', 'param', 'flags']),
              ('mopoe_bn_req_t', L.BnReq, ['out', 'mask', 'mask_mode', 'nchunk', 'ws', 'ws_doubles', 'eps', 'momentum', 'mean',
-                                          'running_var'])]
+                                          'running_var']),
+             ('mopoe_res_req_t', L.ResReq, ['r', 'mean', 'invstd', 'gamma', 'beta', 'a', 'b', 'mask', 'mask_mode', 'out']),
+             ('mopoe_bnbwd_req_t', L.BnBwdReq, ['x', 'mask', 'mask_mode', 'accumulate', 'mean', 'invstd', 'gamma', 'beta', 'ws',
+                                                'ws_doubles', 'dgamma', 'dbeta', 'sums'])]
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "mopoe_b200.h"', 'int main(void) {']
     for cname, _, fields in pairs:
         src.append('  printf("%s %%zu", sizeof(%s));' % (cname, cname))
