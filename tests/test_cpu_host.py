@@ -283,3 +283,27 @@ def test_word_encoding_state_dict_matches_the_reference_layout():
         exp = P.Experiment(P.default_flags(device=torch.device('cpu'), **kw))
         sd = exp.mm_vae.state_dict()
         assert [(k, tuple(v.shape)) for k, v in sd.items()] == [(k, tuple(s_)) for k, s_ in spec.items()]
+
+
+@pytest.mark.parametrize('nd,pad', [(2, 0), (2, 1), (1, 0), (1, 1)])
+def test_phase_rows_partition_the_interior_of_a_deconv_output(nd, pad):
+    """Engine.phase_rows: the 2^nd sub-pixel phase row addressings of a stride-2 deconv output (plain or bordered) visit every
+    interior pixel exactly once and nothing else — the addressing the phase-batched GEMM, its residual stream (the shortcut
+    tensor) and its BatchNorm-backward stream (the BatchNorm input) all share."""
+    import torch
+    from mopoe_mimic_b200.engine import Act, Engine
+    B, H, W, n = 3, (1 if nd == 1 else 4), 5, 8
+    OH, OW = (1 if nd == 1 else 2 * H), 2 * W
+    ph, pw = (0, pad) if nd == 1 else (pad, pad)
+    act = Act(torch.zeros(B, OH + 2 * ph, OW + 2 * pw, n), B, OH, OW, n, ph, pw)
+    seen = []
+    for py in range(1 if nd == 1 else 2):
+        for px in range(2):
+            r = Engine.phase_rows(act, n, py, px)
+            assert r.N == n and r.d == act.t.data_ptr()
+            for b in range(B):
+                for y in range(H):
+                    for x in range(W):
+                        seen.append(r.d_off + x * r.s0 + y * r.s1 + b * r.s2)
+    want = [((b * act.Hs + ph + y) * act.Ws + pw + x) * n for b in range(B) for y in range(OH) for x in range(OW)]
+    assert sorted(seen) == sorted(want) and len(set(seen)) == len(seen)
