@@ -24,7 +24,7 @@ def main():
             continue
         if cur is None:
             continue
-        m = re.match(r'\s*/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)', line)
+        m = re.match(r'\s*/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)', line)
         if m:
             cur['_n'] += 1
             op = m.group(1)
