@@ -96,13 +96,13 @@ constexpr uint32_t STG_BYTES = 128 * 128;   // one staging tile: 128 rows x 64 b
 // the SM's operand fill — ncu: 65-67 B/clk/SM of L2->shared traffic on the 128 x 256 layers (75 % tensor pipe), 57 B/clk on
 // the 128 x 128 layers (47 %): a CTA moves 48 KB per 128x256x64 k-step (85 flop/B).  A pair moves 32 KB per CTA for the same
 // math (128 flop/B); N = 128 layers 24 KB instead of 32 (85 instead of 64 flop/B).
-// RES (with TMA_EPI): the epilogue also reads the shortcut branch's tile (TMA, double-buffered, one 64-column group ahead)
+// RES (with TMA_EPI): the epilogue also reads the shortcut branch's tile (TMA into ONE buffer, refilled one 64-column group ahead)
 // and stores a * BN(r) + b * dropout(acc) — the block's residual combine without the round trip of the conv2 output through
 // HBM (one write + one read of the activation) and without the combine launch.  The statistics warps then sum the COMBINED
 // tile: the statistics of the next block's bn1.
 // BNB (with TMA_EPI): the GEMM is the input gradient that feeds a BatchNorm(+ReLU, +dropout) backward; the statistics warps
-// read, next to every staged output tile dy, the matching tile of the BatchNorm's INPUT x (maps.r; their own 2-buffer TMA
-// ring, two groups ahead) and accumulate the two per-channel sums of the BatchNorm backward, sum(g) and sum(g * xhat) with
+// read, next to every staged output tile dy, the matching tile of the BatchNorm's INPUT x (maps.r; their own one-tile TMA
+// stream, refilled one group ahead) and accumulate the two per-channel sums of the BatchNorm backward, sum(g) and sum(g * xhat) with
 // g = dy * [relu gate recomputed from x] — the reduction pass over (dy, x) that otherwise follows the GEMM.
 template <bool TMA_EPI, bool PAIR, bool RES = false, bool BNB = false>
 __global__ void __launch_bounds__(TCP_THREADS, 1)
@@ -119,7 +119,7 @@ conv_gemm_tc_persist_kernel(const __grid_constant__ TcMaps maps, const TcPersist
     const int tile_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const uint32_t stage_bytes = a_bytes + b_bytes;
-    // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | RES: 2 residual tiles |
+    // ring | [TMA_EPI: 2 staging tiles (1024-B aligned: stage_bytes is a multiple of 1024) | RES / BNB: 1 auxiliary tile |
     //         statistics accumulators | bias row | RES: coefficient rows (scale, shift)] | header
     const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes;
     const uint32_t tiles_bytes = (AUX ? 3u : 2u) * STG_BYTES;
